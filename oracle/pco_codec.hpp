@@ -1,0 +1,1252 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see pco_core.hpp header).
+// Mode split/join, delta encode/decode, per-latent-var page (de)compression,
+// chunk compressor (planner driver) and the standalone/wrapped entry points.
+#pragma once
+#include "pco_planner.hpp"
+
+namespace pco_oracle {
+
+// ===========================================================================
+// Config (pco/src/chunk_config.rs:15-224)
+// ===========================================================================
+enum class ModeSpecKind : int { Auto = 0, Classic = 1, TryFloatMult = 2, TryFloatQuant = 3, TryIntMult = 4, TryDict = 5 };
+enum class DeltaSpecKind : int { Auto = 0, NoOp = 1, TryConsecutive = 2, TryLookback = 3, TryConv1 = 4 };
+enum class PagingKind : int { EqualPagesUpTo = 0, Exact = 1 };
+
+struct ChunkConfig {
+  size_t compression_level = DEFAULT_COMPRESSION_LEVEL;
+  ModeSpecKind mode_kind = ModeSpecKind::Auto;
+  double float_mult_base = 0.0;
+  Bitlen float_quant_k = 0;
+  uint64_t int_mult_base = 0;
+  DeltaSpecKind delta_kind = DeltaSpecKind::Auto;
+  size_t delta_order = 0;
+  PagingKind paging_kind = PagingKind::EqualPagesUpTo;
+  size_t max_page_n = DEFAULT_MAX_PAGE_N;
+  std::vector<size_t> exact_pages;
+  bool enable_8_bit = false;
+};
+
+// chunk_config.rs:134-183
+inline std::vector<size_t> n_per_page(const ChunkConfig& c, size_t n) {
+  std::vector<size_t> res;
+  if (c.paging_kind == PagingKind::EqualPagesUpTo) {
+    if (n == 0) return res;
+    if (c.max_page_n == 0) invalid_argument("max_page_n must be positive");  // Rust would panic on div by zero
+    size_t n_pages = (n + c.max_page_n - 1) / c.max_page_n;
+    size_t low = n / n_pages, high = low + 1, r = n % n_pages;
+    res.assign(n_pages, low);
+    for (size_t i = 0; i < r; i++) res[i] = high;
+  } else {
+    res = c.exact_pages;
+  }
+  size_t summed = 0;
+  for (size_t p : res) summed += p;
+  if (summed != n) invalid_argument("paging spec suggests " + std::to_string(summed) + " numbers but " + std::to_string(n) + " were given");
+  for (size_t p : res) if (p == 0) invalid_argument("cannot write data page of 0 numbers");
+  return res;
+}
+
+// chunk_config.rs:269-314
+inline void validate_config(const ChunkConfig& c, Bitlen latent_bits) {
+  if (c.compression_level > MAX_COMPRESSION_LEVEL) invalid_argument("compression level may not exceed 12");
+  if (c.delta_kind == DeltaSpecKind::TryConsecutive && c.delta_order > MAX_CONSECUTIVE_DELTA_ORDER)
+    invalid_argument("consecutive delta order may not exceed 7");
+  if (c.delta_kind == DeltaSpecKind::TryConv1) {
+    if (c.delta_order > MAX_CONV1_DELTA_ORDER) invalid_argument("conv1 delta order may not exceed 32");
+    if (latent_bits > 32) invalid_argument("Conv1 delta encoding is only supported for types with 32 or fewer bits");
+  }
+  if (latent_bits == 8 && !c.enable_8_bit) invalid_argument("compressing 8-bit types with Pco is often a mistake");
+}
+
+// ===========================================================================
+// Float helpers (pco/src/data_types/float.rs:130-252)
+// ===========================================================================
+template <typename L> struct FloatOps;
+template <> struct FloatOps<uint32_t> {
+  using F = float;
+  static constexpr int MANTISSA_DIGITS = 24;
+  static F from_bits(uint32_t b) { F f; std::memcpy(&f, &b, 4); return f; }
+  static uint32_t to_bits(F f) { uint32_t b; std::memcpy(&b, &f, 4); return b; }
+  static F mul(F a, F b) { return a * b; }
+  static F round_(F a) { return std::round(a); }
+  static F from_f64(double x) { return F(x); }
+  static F inv(F a) { return 1.0f / a; }
+  static F from_uint(uint32_t x) { return F(x); }
+  static uint32_t to_uint(F x) { return uint32_t(x); }
+  static bool lt(F a, F b) { return a < b; }
+};
+template <> struct FloatOps<uint64_t> {
+  using F = double;
+  static constexpr int MANTISSA_DIGITS = 53;
+  static F from_bits(uint64_t b) { F f; std::memcpy(&f, &b, 8); return f; }
+  static uint64_t to_bits(F f) { uint64_t b; std::memcpy(&b, &f, 8); return b; }
+  static F mul(F a, F b) { return a * b; }
+  static F round_(F a) { return std::round(a); }
+  static F from_f64(double x) { return x; }
+  static F inv(F a) { return 1.0 / a; }
+  static F from_uint(uint64_t x) { return F(x); }
+  static uint64_t to_uint(F x) { return uint64_t(x); }
+  static bool lt(F a, F b) { return a < b; }
+};
+// f16 via the half crate's semantics: every op widens to f32 and rounds back (RNE).
+struct F16 { uint16_t bits; };
+template <> struct FloatOps<uint16_t> {
+  using F = F16;
+  static constexpr int MANTISSA_DIGITS = 11;
+  static F from_bits(uint16_t b) { return F16{b}; }
+  static uint16_t to_bits(F f) { return f.bits; }
+  static F mul(F a, F b) { return F16{f32_to_f16_bits(f16_bits_to_f32(a.bits) * f16_bits_to_f32(b.bits))}; }
+  static F round_(F a) { return F16{f32_to_f16_bits(std::round(f16_bits_to_f32(a.bits)))}; }
+  static F from_uint(uint16_t x) { return F16{f32_to_f16_bits(float(x))}; }
+  static uint16_t to_uint(F x) { return uint16_t(f16_bits_to_f32(x.bits)); }
+  static bool lt(F a, F b) { return f16_bits_to_f32(a.bits) < f16_bits_to_f32(b.bits); }
+};
+template <> struct FloatOps<uint8_t> {};  // no 8-bit floats
+
+// float.rs:208-226
+template <typename L>
+inline typename FloatOps<L>::F int_float_from_latent(L l) {
+  using FO = FloatOps<L>;
+  constexpr L MID = LatentTraits<L>::MID;
+  bool negative;
+  L abs_int;
+  if (l >= MID) { negative = false; abs_int = L(l - MID); } else { negative = true; abs_int = L(MID - 1 - l); }
+  L gpi = L(L(1) << FO::MANTISSA_DIGITS);
+  L abs_bits;
+  if (abs_int < gpi) abs_bits = FO::to_bits(FO::from_uint(abs_int));
+  else abs_bits = L(FO::to_bits(FO::from_uint(gpi)) + (abs_int - gpi));
+  if (negative) abs_bits = L(abs_bits ^ MID);  // unary minus flips the sign bit
+  return FO::from_bits(abs_bits);
+}
+// float.rs:229-244
+template <typename L>
+inline L int_float_to_latent(typename FloatOps<L>::F x) {
+  using FO = FloatOps<L>;
+  constexpr L MID = LatentTraits<L>::MID;
+  L bits = FO::to_bits(x);
+  L abs_bits = L(bits & ~MID);
+  typename FloatOps<L>::F abs = FO::from_bits(abs_bits);
+  L gpi = L(L(1) << FO::MANTISSA_DIGITS);
+  typename FloatOps<L>::F gpi_float = FO::from_uint(gpi);
+  L abs_int;
+  if (FO::lt(abs, gpi_float)) abs_int = FO::to_uint(abs);
+  else abs_int = L(gpi + (abs_bits - FO::to_bits(gpi_float)));
+  bool sign_positive = (bits & MID) == 0;
+  return sign_positive ? L(MID + abs_int) : L(MID - 1 - abs_int);
+}
+
+// ===========================================================================
+// Delta (pco/src/delta/{mod,consecutive,lookback,conv1}.rs)
+// ===========================================================================
+// delta/mod.rs:29-33
+template <typename L>
+inline void toggle_center_in_place(L* v, size_t n) {
+  for (size_t i = 0; i < n; i++) v[i] = L(v[i] + LatentTraits<L>::MID);
+}
+
+// delta/consecutive.rs:3-33
+template <typename L>
+inline std::vector<L> consecutive_encode_in_place(size_t order, L* latents, size_t len) {
+  std::vector<L> moments;
+  moments.reserve(order);
+  L* v = latents;
+  size_t n = len;
+  for (size_t k = 0; k < order; k++) {
+    moments.push_back(n > 0 ? v[0] : L(0));
+    if (n > 0)
+      for (size_t i = n - 1; i >= 1; i--) v[i] = L(v[i] - v[i - 1]);
+    size_t trunc = std::min<size_t>(n, 1);
+    v += trunc;
+    n -= trunc;
+  }
+  toggle_center_in_place(v, n);
+  return moments;
+}
+
+// delta/consecutive.rs:35-50
+template <typename L>
+inline void consecutive_decode_in_place(std::vector<L>& moments, L* latents, size_t len) {
+  toggle_center_in_place(latents, len);
+  for (size_t k = moments.size(); k-- > 0;) {
+    L m = moments[k];
+    for (size_t i = 0; i < len; i++) {
+      L tmp = latents[i];
+      latents[i] = m;
+      m = L(m + tmp);
+    }
+    moments[k] = m;
+  }
+}
+
+// ----- lookback (delta/lookback.rs) -----------------------------------------
+constexpr size_t LB_PROPOSED = 16, LB_BRUTE = 6, LB_REPEATING = 4;
+constexpr Bitlen LB_COARSENESSES[2] = {0, 8};
+constexpr Bitlen ENCODING_LOOKBACK_MAX_WINDOW_N_LOG = 15, ENCODING_LOOKBACK_MIN_WINDOW_N_LOG = 4;
+
+// delta/mod.rs:37-49
+inline DeltaEncoding new_lookback(size_t n) {
+  DeltaEncoding d;
+  d.kind = DeltaKind::Lookback;
+  Bitlen w = bits_to_encode_offset<uint32_t>(uint32_t(n) - 1);
+  d.window_n_log = std::min(std::max(w, ENCODING_LOOKBACK_MIN_WINDOW_N_LOG), ENCODING_LOOKBACK_MAX_WINDOW_N_LOG);
+  d.state_n_log = 0;
+  d.secondary_uses_delta = false;
+  return d;
+}
+
+// delta/lookback.rs:23-159
+template <typename L>
+inline std::vector<DeltaLookback> choose_lookbacks(const DeltaEncoding& cfg, const L* latents, size_t len) {
+  size_t state_n = size_t(1) << cfg.state_n_log;
+  if (len <= state_n) return {};
+  size_t hash_table_n = size_t(1) << (cfg.window_n_log + 1);
+  size_t window_n = size_t(1) << cfg.window_n_log;
+  if (window_n < LB_PROPOSED) invalid_argument("we do not support tiny windows during compression");
+  std::vector<uint32_t> lookback_counts(std::min(window_n, len), 1);
+  std::vector<DeltaLookback> lookbacks(len - state_n);
+  std::vector<size_t> idx_hash_table(2 * hash_table_n, 0);
+  size_t proposed[LB_PROPOSED];
+  for (size_t i = 0; i < LB_PROPOSED; i++) proposed[i] = std::min(i + 1, state_n);
+  size_t best_lookback = 1;
+  size_t repeating_idx = 0;
+  size_t hash_mask = hash_table_n - 1;
+  auto hash_fn = [&](uint64_t x) {
+    x = (x ^ (x >> 32)) * 11400714819323197441ull;
+    x = x ^ (x >> 32);
+    return size_t(x) & hash_mask;
+  };
+  for (size_t i = state_n; i < len; i++) {
+    L l = latents[i];
+    size_t new_brute = std::min(i, LB_PROPOSED);
+    proposed[new_brute - 1] = new_brute;
+    // hash_lookup
+    {
+      size_t proposal_idx = LB_BRUTE + LB_REPEATING;
+      size_t offset = 0;
+      for (Bitlen coarseness : LB_COARSENESSES) {
+        uint64_t bucket = uint64_t(l) >> coarseness;
+        uint64_t buckets[3] = {bucket - 1, bucket, bucket + 1};
+        size_t hashes[3];
+        for (int t = 0; t < 3; t++) hashes[t] = hash_fn(buckets[t]);
+        for (int t = 0; t < 3; t++) {
+          size_t lb_last = i - idx_hash_table[offset + hashes[t]];
+          proposed[proposal_idx] = lb_last <= window_n ? lb_last : std::min(proposal_idx, i);
+          proposal_idx++;
+        }
+        idx_hash_table[offset + hashes[1]] = i;
+        offset += hash_table_n;
+      }
+    }
+    // find_best_lookback
+    size_t new_best = 0;
+    {
+      Bitlen best_goodness = 0;
+      for (size_t t = 0; t < LB_PROPOSED; t++) {
+        size_t lookback = proposed[t];
+        uint32_t count = lookback_counts[lookback - 1];
+        L other = latents[i - lookback];
+        Bitlen lookback_goodness = 32 - (count == 0 ? 32 : Bitlen(__builtin_clz(count)));
+        L d0 = L(l - other), d1 = L(other - l);
+        L delta = std::min(d0, d1);
+        Bitlen goodness = lookback_goodness + leading_zeros<L>(delta);
+        if (goodness > best_goodness) { best_goodness = goodness; new_best = lookback; }
+      }
+    }
+    if (new_best != best_lookback) repeating_idx += 1;
+    proposed[LB_BRUTE + repeating_idx % LB_REPEATING] = new_best;
+    best_lookback = new_best;
+    lookbacks[i - state_n] = DeltaLookback(best_lookback);
+    lookback_counts[best_lookback - 1] += 1;
+  }
+  return lookbacks;
+}
+
+// delta/lookback.rs:166-187
+template <typename L>
+inline std::vector<L> lookback_encode_in_place(const DeltaEncoding& cfg, const DeltaLookback* lookbacks, L* latents, size_t len) {
+  size_t state_n = size_t(1) << cfg.state_n_log;
+  size_t real_state_n = std::min(len, state_n);
+  for (size_t i = len; i-- > real_state_n;) {
+    size_t lookback = lookbacks[i - state_n];
+    latents[i] = L(latents[i] - latents[i - lookback]);
+  }
+  std::vector<L> state(state_n, 0);
+  for (size_t i = 0; i < real_state_n; i++) state[state_n - real_state_n + i] = latents[i];
+  toggle_center_in_place(latents, len);
+  return state;
+}
+
+// ----- conv1 decode (delta/conv1.rs:149-160,191-253,464-483) ----------------
+template <typename L> struct ConvType;
+template <> struct ConvType<uint8_t> { using S = int16_t; };
+template <> struct ConvType<uint16_t> { using S = int32_t; };
+template <> struct ConvType<uint32_t> { using S = int64_t; };
+template <> struct ConvType<uint64_t> { using S = int64_t; };
+
+template <typename L>
+inline void conv1_decode_in_place(const DeltaEncoding& cfg, std::vector<L>& state, L* latents, size_t len) {
+  using S = typename ConvType<L>::S;
+  using US = typename std::make_unsigned<S>::type;
+  size_t order = cfg.weights.size();
+  std::vector<S> weights(order);
+  for (size_t i = 0; i < order; i++) weights[i] = S(cfg.weights[i]);
+  S bias = S(cfg.bias);
+  Bitlen q = cfg.quantization;
+  toggle_center_in_place(latents, len);
+  // The reference's order-6 specialisation computes the same sums in a
+  // different association order; integer wrapping arithmetic is associative,
+  // so one general implementation covers both.
+  std::vector<L> residuals(len + order);
+  for (size_t i = 0; i < order; i++) residuals[i] = state[i];
+  for (size_t i = 0; i < len; i++) residuals[order + i] = latents[i];
+  for (size_t i = order; i < residuals.size(); i++) {
+    US s = US(bias);
+    for (size_t j = 0; j < order; j++) s = US(s + US(US(weights[j]) * US(S(residuals[i - order + j]))));
+    S ss = S(s);
+    if (ss < 0) ss = 0;
+    L pred = L(ss >> q);
+    residuals[i] = L(residuals[i] + pred);
+  }
+  for (size_t i = 0; i < len; i++) latents[i] = residuals[i];
+  for (size_t i = 0; i < order; i++) state[i] = residuals[len + i];
+}
+
+// ===========================================================================
+// Per-latent-var decompression
+// (pco/src/chunk_latent_decompressor.rs, page_latent_decompressor.rs)
+// ===========================================================================
+struct VarDecoderBase {
+  virtual ~VarDecoderBase() {}
+  virtual void init_page(const PageVarMeta& pv) = 0;
+  virtual void read_batch_pre_delta(BitReader& r, size_t batch_n) = 0;
+  virtual void read_batch(BitReader& r, const uint32_t* delta_latents, size_t n_remaining_in_page) = 0;
+  virtual const void* latents() const = 0;
+  size_t n_bins = 0;
+};
+
+template <typename L>
+struct VarDecoder : VarDecoderBase {
+  LatentVarDelta delta;
+  Bitlen max_offset_bits = 0;
+  std::vector<L> state_lowers;
+  std::vector<AnsNode> nodes;
+  alignas(64) uint32_t offset_bits_csum[FULL_BATCH_N];
+  alignas(64) uint32_t offset_bits[FULL_BATCH_N];
+  alignas(64) L lat[FULL_BATCH_N];
+  // page state (page_latent_decompressor.rs:65-87)
+  AnsState ans_state_idxs[ANS_INTERLEAVING];
+  std::vector<L> delta_state;
+  size_t delta_state_pos = 0;
+
+  // chunk_latent_decompressor.rs:30-75
+  VarDecoder(const LatentVarMeta& vm, LatentVarDelta d) : delta(d) {
+    n_bins = vm.bins.size();
+    max_offset_bits = vm.max_offset_bits();
+    std::vector<Weight> weights;
+    std::vector<Bitlen> bin_offset_bits;
+    for (const Bin& b : vm.bins) { weights.push_back(b.weight); bin_offset_bits.push_back(b.offset_bits); }
+    AnsSpec spec = ans_spec_from_weights(vm.ans_size_log, weights);
+    state_lowers.reserve(spec.state_symbols.size());
+    for (Symbol s : spec.state_symbols) state_lowers.push_back(s < vm.bins.size() ? L(vm.bins[s].lower) : L(0));
+    nodes = ans_decoder_nodes(spec, bin_offset_bits);
+    for (size_t i = 0; i < FULL_BATCH_N; i++) { offset_bits_csum[i] = 0; offset_bits[i] = 0; lat[i] = 0; }
+    if (vm.bins.size() == 1) {
+      uint32_t csum = 0;
+      for (size_t i = 0; i < FULL_BATCH_N; i++) {
+        offset_bits[i] = vm.bins[0].offset_bits;
+        offset_bits_csum[i] = csum;
+        lat[i] = L(vm.bins[0].lower);
+        csum += vm.bins[0].offset_bits;
+      }
+    }
+  }
+
+  // page_latent_decompressor.rs:72-87 + delta/mod.rs:86-99, lookback.rs:189-199
+  void init_page(const PageVarMeta& pv) override {
+    for (size_t j = 0; j < ANS_INTERLEAVING; j++) ans_state_idxs[j] = pv.ans_final_state_idxs[j];
+    std::vector<L> stored(pv.delta_state.size());
+    for (size_t i = 0; i < stored.size(); i++) stored[i] = L(pv.delta_state[i]);
+    if (delta.kind == DeltaKind::Lookback) {
+      size_t window_n = size_t(1) << delta.enc->window_n_log;
+      size_t buffer_n = std::max(window_n, FULL_BATCH_N) * 2;
+      delta_state.assign(buffer_n, 0);
+      for (size_t i = 0; i < stored.size(); i++) delta_state[window_n - stored.size() + i] = stored[i];
+      delta_state_pos = window_n;
+    } else {
+      delta_state = std::move(stored);
+      delta_state_pos = 0;
+    }
+  }
+
+  // page_latent_decompressor.rs:89-177 (one loop covers the full and partial batch variants)
+  inline void read_ans_symbols(BitReader& r, size_t batch_n) {
+    size_t bit = r.bit_idx;
+    uint32_t offset_bit_idx = 0;
+    AnsState st[ANS_INTERLEAVING] = {ans_state_idxs[0], ans_state_idxs[1], ans_state_idxs[2], ans_state_idxs[3]};
+    const AnsNode* nd = nodes.data();
+    const L* lowers = state_lowers.data();
+    for (size_t i = 0; i < batch_n; i++) {
+      size_t j = i % ANS_INTERLEAVING;
+      AnsState s = st[j];
+      uint64_t packed = r.u64_at(bit / 8);
+      AnsNode node = nd[s];
+      Bitlen btr = node.bits_to_read;
+      AnsState ans_val = AnsState(packed >> (bit % 8)) & ((AnsState(1) << btr) - 1);
+      offset_bits_csum[i] = offset_bit_idx;
+      offset_bits[i] = node.offset_bits;
+      lat[i] = lowers[s];
+      bit += btr;
+      offset_bit_idx += node.offset_bits;
+      st[j] = AnsState(node.next_state_idx_base) + ans_val;
+    }
+    r.bit_idx = bit;
+    for (size_t j = 0; j < ANS_INTERLEAVING; j++) ans_state_idxs[j] = st[j];
+  }
+
+  // page_latent_decompressor.rs:15-44
+  inline void read_offsets(BitReader& r, size_t n) {
+    size_t base = r.bit_idx;
+    for (size_t i = 0; i < n; i++) {
+      Bitlen ob = offset_bits[i];
+      size_t bit = base + offset_bits_csum[i];
+      size_t byte = bit / 8;
+      Bitlen bpb = Bitlen(bit % 8);
+      uint64_t w = r.u64_at(byte) >> bpb;
+      if (sizeof(L) == 8 && bpb + ob > 64) w |= r.u64_at(byte + 8) << (64 - bpb);
+      lat[i] = L(lat[i] + L(lowest_bits_u64(w, ob)));
+    }
+    r.bit_idx = base + offset_bits_csum[n - 1] + offset_bits[n - 1];
+  }
+
+  // page_latent_decompressor.rs:181-235
+  void read_batch_pre_delta(BitReader& r, size_t batch_n) override {
+    if (batch_n == 0) return;
+    if (n_bins > 1) read_ans_symbols(r, batch_n);
+    else for (size_t i = 0; i < batch_n; i++) lat[i] = state_lowers[0];
+    if (max_offset_bits > 0) read_offsets(r, batch_n);
+  }
+
+  // page_latent_decompressor.rs:237-257 + delta/mod.rs:125-159
+  void read_batch(BitReader& r, const uint32_t* delta_latents, size_t n_remaining_in_page) override {
+    size_t n_state = delta.n_latents_per_state();
+    size_t n_remaining_pre_delta = n_remaining_in_page > n_state ? n_remaining_in_page - n_state : 0;
+    size_t pre_delta_len = std::min(FULL_BATCH_N, n_remaining_pre_delta);
+    read_batch_pre_delta(r, pre_delta_len);
+    size_t dst_len = std::min(n_remaining_in_page, FULL_BATCH_N);
+    switch (delta.kind) {
+      case DeltaKind::NoOp: break;
+      case DeltaKind::Consecutive: consecutive_decode_in_place(delta_state, lat, dst_len); break;
+      case DeltaKind::Conv1: conv1_decode_in_place(*delta.enc, delta_state, lat, dst_len); break;
+      case DeltaKind::Lookback: {
+        // delta/lookback.rs:201-246
+        toggle_center_in_place(lat, dst_len);
+        size_t window_n = size_t(1) << delta.enc->window_n_log, state_n = size_t(1) << delta.enc->state_n_log;
+        size_t start_pos = delta_state_pos;
+        if (start_pos + dst_len > delta_state.size()) {
+          std::memmove(delta_state.data(), delta_state.data() + (start_pos - window_n), window_n * sizeof(L));
+          start_pos = window_n;
+        }
+        bool oob = false;
+        // zip(latents, lookbacks): lookbacks hold pre_delta_len valid entries; the
+        // reference zips against the delta var's 256-entry scratch, so stale
+        // entries beyond pre_delta_len are consumed too.
+        for (size_t i = 0; i < dst_len; i++) {
+          size_t pos = start_pos + i;
+          uint32_t lb = delta_latents[i];
+          size_t lookback;
+          if (lb <= uint32_t(window_n)) lookback = lb; else { oob = true; lookback = 1; }
+          delta_state[pos] = L(lat[i] + delta_state[pos - lookback]);
+        }
+        size_t end_pos = start_pos + dst_len;
+        for (size_t i = 0; i < dst_len; i++) lat[i] = delta_state[start_pos - state_n + i];
+        delta_state_pos = end_pos;
+        if (oob) corruption("delta lookback exceeded window n");
+        break;
+      }
+    }
+  }
+  const void* latents() const override { return lat; }
+};
+
+inline std::unique_ptr<VarDecoderBase> make_var_decoder(const LatentVarMeta& vm, LatentVarDelta d) {
+  switch (vm.latent_bits) {
+    case 8: return std::unique_ptr<VarDecoderBase>(new VarDecoder<uint8_t>(vm, d));
+    case 16: return std::unique_ptr<VarDecoderBase>(new VarDecoder<uint16_t>(vm, d));
+    case 32: return std::unique_ptr<VarDecoderBase>(new VarDecoder<uint32_t>(vm, d));
+    default: return std::unique_ptr<VarDecoderBase>(new VarDecoder<uint64_t>(vm, d));
+  }
+}
+
+// ===========================================================================
+// Mode split / join (pco/src/mode/*.rs)
+// ===========================================================================
+template <typename L>
+inline void join_latents(const ChunkMeta& cm, uint8_t number_type, const void* primary_v, const void* secondary_v, L* dst, size_t n) {
+  bool isf = number_type_is_float(number_type), iss = number_type_is_signed(number_type);
+  const Mode& mode = cm.mode;
+  switch (mode.kind) {
+    case ModeKind::Classic: {  // mode/classic.rs:14-24
+      const L* p = static_cast<const L*>(primary_v);
+      for (size_t i = 0; i < n; i++) dst[i] = from_latent_ordered_bits<L>(p[i], isf, iss);
+      break;
+    }
+    case ModeKind::Dict: {  // mode/dict.rs:70-90
+      const uint32_t* idxs = static_cast<const uint32_t*>(primary_v);
+      for (size_t i = 0; i < n; i++)
+        if (idxs[i] >= uint32_t(mode.dict.size())) corruption("dict index exceeded dict length " + std::to_string(mode.dict.size()));
+      for (size_t i = 0; i < n; i++) dst[i] = from_latent_ordered_bits<L>(L(mode.dict[idxs[i]]), isf, iss);
+      break;
+    }
+    case ModeKind::IntMult: {  // mode/int_mult.rs:38-54
+      const L* p = static_cast<const L*>(primary_v);
+      const L* s = static_cast<const L*>(secondary_v);
+      L base = L(mode.base_latent);
+      for (size_t i = 0; i < n; i++) dst[i] = from_latent_ordered_bits<L>(L(L(p[i] * base) + s[i]), isf, iss);
+      break;
+    }
+    case ModeKind::FloatMult: {  // mode/float_mult.rs:17-36
+      if constexpr (sizeof(L) >= 2) {
+        using FO = FloatOps<L>;
+        const L* p = static_cast<const L*>(primary_v);
+        const L* s = static_cast<const L*>(secondary_v);
+        auto base = FO::from_bits(from_latent_ordered_bits<L>(L(mode.base_latent), true, false));
+        for (size_t i = 0; i < n; i++) {
+          auto unadjusted = FO::mul(int_float_from_latent<L>(p[i]), base);
+          L u = to_latent_ordered_bits<L>(FO::to_bits(unadjusted), true, false);
+          dst[i] = from_latent_ordered_bits<L>(L(L(u + s[i]) + LatentTraits<L>::MID), true, false);
+        }
+      }
+      break;
+    }
+    case ModeKind::FloatQuant: {  // mode/float_quant.rs:13-39
+      const L* p = static_cast<const L*>(primary_v);
+      const L* s = static_cast<const L*>(secondary_v);
+      Bitlen k = mode.k;
+      L sign_cutoff = L(LatentTraits<L>::MID >> k);
+      L lowest_k_bits_max = L(L(L(1) << k) - 1);
+      for (size_t i = 0; i < n; i++) {
+        bool pos = p[i] >= sign_cutoff;
+        L lowest = pos ? s[i] : L(lowest_k_bits_max - s[i]);
+        dst[i] = from_latent_ordered_bits<L>(L(L(p[i] << k) + lowest), true, false);
+      }
+      break;
+    }
+  }
+}
+
+// ===========================================================================
+// Page decompression (pco/src/wrapped/page_decompressor.rs)
+// ===========================================================================
+struct ChunkDecoder {
+  ChunkMeta meta;
+  uint8_t number_type;
+  std::unique_ptr<VarDecoderBase> delta_var, primary, secondary;
+
+  // wrapped/chunk_decompressor.rs:17-72
+  ChunkDecoder(ChunkMeta m, uint8_t nt) : meta(std::move(m)), number_type(nt) {
+    if (!mode_is_valid(meta.mode, nt)) corruption("invalid mode for number type");
+    if (meta.has_delta_var) delta_var = make_var_decoder(meta.delta_var, delta_for_latent_var(meta.delta, VarKey::Delta));
+    primary = make_var_decoder(meta.primary, delta_for_latent_var(meta.delta, VarKey::Primary));
+    if (meta.has_secondary) secondary = make_var_decoder(meta.secondary, delta_for_latent_var(meta.delta, VarKey::Secondary));
+  }
+  size_t n_latents_per_delta_state() const { return delta_for_latent_var(meta.delta, VarKey::Primary).n_latents_per_state(); }
+};
+
+struct Progress {
+  size_t n_processed = 0;
+  bool finished = false;
+};
+
+// State of one page being decoded: PageDecompressorState (page_decompressor.rs:22-221)
+template <typename L>
+struct PageDecoder {
+  ChunkDecoder& cd;
+  BitReader& r;
+  size_t n_remaining;
+
+  PageDecoder(ChunkDecoder& cd_, BitReader& r_, size_t n) : cd(cd_), r(r_), n_remaining(n) {
+    PageMeta pm = read_page_meta(r, cd.meta);
+    r.check_in_bounds();
+    size_t n_state = cd.n_latents_per_delta_state();
+    size_t n_in_body = n > n_state ? n - n_state : 0;
+    auto init = [&](VarDecoderBase* vd, const PageVarMeta& pv) {
+      if (vd->n_bins == 0 && n_in_body > 0)
+        corruption("unable to decompress chunk with no bins and " + std::to_string(n_in_body) + " latents");
+      vd->init_page(pv);
+    };
+    if (cd.delta_var) init(cd.delta_var.get(), pm.delta_var);
+    init(cd.primary.get(), pm.primary);
+    if (cd.secondary) init(cd.secondary.get(), pm.secondary);
+  }
+
+  // page_decompressor.rs:115-191
+  void read_batch(L* dst, size_t batch_n) {
+    const uint32_t* delta_latents = nullptr;
+    if (cd.delta_var) {
+      size_t n_state = cd.n_latents_per_delta_state();
+      size_t limit = std::min(n_remaining > n_state ? n_remaining - n_state : 0, batch_n);
+      cd.delta_var->read_batch_pre_delta(r, limit);
+      r.check_in_bounds();
+      delta_latents = static_cast<const uint32_t*>(cd.delta_var->latents());
+    }
+    cd.primary->read_batch(r, delta_latents, n_remaining);
+    r.check_in_bounds();
+    const void* sec = nullptr;
+    if (cd.secondary) {
+      cd.secondary->read_batch(r, delta_latents, n_remaining);
+      r.check_in_bounds();
+      sec = cd.secondary->latents();
+    }
+    join_latents<L>(cd.meta, cd.number_type, cd.primary->latents(), sec, dst, batch_n);
+    n_remaining -= batch_n;
+    if (n_remaining == 0) r.drain_empty_byte("expected trailing bits at end of page to be empty");
+  }
+
+  // page_decompressor.rs:193-221
+  Progress read(L* dst, size_t dst_len) {
+    if (dst_len % FULL_BATCH_N != 0 && dst_len < n_remaining)
+      invalid_argument("num_dst's length must either be a multiple of 256 or be at least the count of numbers remaining");
+    size_t n_to_process = std::min(dst_len, n_remaining);
+    size_t n_processed = 0;
+    while (n_processed < n_to_process) {
+      size_t end = std::min(n_processed + FULL_BATCH_N, n_to_process);
+      read_batch(dst + n_processed, end - n_processed);
+      n_processed = end;
+    }
+    Progress p;
+    p.n_processed = n_processed;
+    p.finished = n_remaining == 0;
+    return p;
+  }
+};
+
+// ===========================================================================
+// Per-latent-var compression
+// (pco/src/compression_table.rs, chunk_latent_compressor.rs)
+// ===========================================================================
+template <typename L>
+struct PageDissectedVar {
+  std::vector<AnsState> ans_vals;
+  std::vector<Bitlen> ans_bits;
+  std::vector<L> offsets;
+  std::vector<Bitlen> offset_bits;
+  AnsState ans_final_states[ANS_INTERLEAVING];
+};
+
+template <typename L>
+struct VarCompressor {
+  // compression_table.rs:9-33
+  size_t search_size_log = 0;
+  std::vector<L> search_lowers;
+  std::vector<BinCompressionInfo<L>> infos;  // sorted by lower
+  AnsEncoder encoder;
+  double avg_bits_per_latent = 0.0;
+  bool is_trivial = false, needs_ans = false;
+  Bitlen max_bits_per_offset = 0;
+  std::vector<L> latents;
+  alignas(64) L scratch_lowers[FULL_BATCH_N];
+  alignas(64) Symbol scratch_symbols[FULL_BATCH_N];
+
+  // chunk_latent_compressor.rs:135-161
+  VarCompressor(const TrainedBins<L>& trained, const LatentVarMeta& vm, std::vector<L> lat) : latents(std::move(lat)) {
+    needs_ans = vm.bins.size() != 1;
+    infos = trained.infos;
+    search_size_log = infos.size() <= 1 ? 0 : 1 + ilog2_u64(infos.size() - 1);
+    // sort_unstable_by_key(lower): lowers are distinct for trained bins
+    std::sort(infos.begin(), infos.end(), [](const BinCompressionInfo<L>& a, const BinCompressionInfo<L>& b) { return a.lower < b.lower; });
+    for (auto& i : infos) search_lowers.push_back(i.lower);
+    while (search_lowers.size() < (size_t(1) << search_size_log)) search_lowers.push_back(LatentTraits<L>::MAX);
+    std::vector<Weight> weights;
+    for (const Bin& b : vm.bins) weights.push_back(b.weight);
+    AnsSpec spec = ans_spec_from_weights(trained.ans_size_log, weights);
+    encoder = AnsEncoder(spec);
+    max_bits_per_offset = vm.max_offset_bits();
+    // metadata/bins.rs:23-32
+    double total_weight = double(uint64_t(1) << trained.ans_size_log);
+    double acc = 0.0;
+    for (const Bin& b : vm.bins) {
+      double ans_bits = double(trained.ans_size_log) - std::log2(double(b.weight));
+      acc += (ans_bits + double(b.offset_bits)) * double(b.weight) / total_weight;
+    }
+    avg_bits_per_latent = acc;
+    is_trivial = vm.are_trivial();
+    L default_lower = infos.size() == 1 ? infos[0].lower : L(0);
+    for (size_t i = 0; i < FULL_BATCH_N; i++) { scratch_lowers[i] = default_lower; scratch_symbols[i] = 0; }
+  }
+
+  // chunk_latent_compressor.rs:194-233 (binary_search compression_table.rs:51-74, dissect_bins :163-182,
+  // set_offsets :185-192, encode_ans_in_reverse :96-132)
+  void dissect_batch(size_t page_start, size_t rel_start, size_t rel_end, PageDissectedVar<L>& dst) {
+    size_t batch_n = rel_end - rel_start;
+    const L* lat = latents.data() + page_start + rel_start;
+    size_t search_idxs[FULL_BATCH_N];
+    for (size_t i = 0; i < batch_n; i++) search_idxs[i] = 0;
+    for (size_t depth = 0; depth < search_size_log; depth++) {
+      size_t bisection = size_t(1) << (search_size_log - 1 - depth);
+      for (size_t i = 0; i < batch_n; i++) {
+        size_t cand = search_idxs[i] + bisection;
+        search_idxs[i] += (lat[i] >= search_lowers[cand]) ? bisection : 0;
+      }
+    }
+    size_t n_bins = infos.size();
+    if (n_bins < (size_t(1) << search_size_log))
+      for (size_t i = 0; i < batch_n; i++) search_idxs[i] = std::min(search_idxs[i], n_bins - 1);
+    Bitlen* ob = dst.offset_bits.data() + rel_start;
+    if (infos.size() <= 1) {
+      Bitlen d = infos.size() == 1 ? infos[0].offset_bits : 0;
+      for (size_t i = 0; i < batch_n; i++) ob[i] = d;
+    } else {
+      for (size_t i = 0; i < batch_n; i++) {
+        const auto& info = infos[search_idxs[i]];
+        scratch_lowers[i] = info.lower;
+        scratch_symbols[i] = info.symbol;
+        ob[i] = info.offset_bits;
+      }
+    }
+    L* offs = dst.offsets.data() + rel_start;
+    for (size_t i = 0; i < batch_n; i++) offs[i] = L(lat[i] - scratch_lowers[i]);
+    // reverse tANS
+    AnsState* ans_vals = dst.ans_vals.data() + rel_start;
+    Bitlen* ans_bits = dst.ans_bits.data() + rel_start;
+    if (encoder.size_log == 0) {
+      for (size_t i = 0; i < batch_n; i++) ans_bits[i] = 0;
+      return;
+    }
+    for (size_t i = batch_n; i-- > 0;) {
+      size_t j = i % ANS_INTERLEAVING;
+      Bitlen bitlen;
+      AnsState st = dst.ans_final_states[j];
+      AnsState ns = encoder.encode(st, scratch_symbols[i], &bitlen);
+      ans_vals[i] = AnsState(lowest_bits_u64(st, bitlen));
+      ans_bits[i] = bitlen;
+      dst.ans_final_states[j] = ns;
+    }
+  }
+
+  // chunk_latent_compressor.rs:246-270
+  PageDissectedVar<L> dissect_page(size_t start, size_t end) {
+    PageDissectedVar<L> d;
+    for (size_t j = 0; j < ANS_INTERLEAVING; j++) d.ans_final_states[j] = encoder.default_state();
+    if (is_trivial) return d;
+    size_t page_n = end - start;
+    d.ans_vals.resize(page_n);
+    d.ans_bits.resize(page_n);
+    d.offsets.resize(page_n);
+    d.offset_bits.resize(page_n);
+    size_t n_batches = (page_n + FULL_BATCH_N - 1) / FULL_BATCH_N;
+    for (size_t b = n_batches; b-- > 0;) dissect_batch(start, b * FULL_BATCH_N, std::min((b + 1) * FULL_BATCH_N, page_n), d);
+    return d;
+  }
+
+  // chunk_latent_compressor.rs:272-329
+  void write_dissected_batch(const PageDissectedVar<L>& d, size_t batch_start, BitWriter& w) const {
+    if (batch_start >= d.offsets.size()) return;
+    size_t end = std::min(batch_start + FULL_BATCH_N, d.offsets.size());
+    if (needs_ans)
+      for (size_t i = batch_start; i < end; i++) w.write_uint(d.ans_vals[i], d.ans_bits[i]);
+    if (max_bits_per_offset > 0)
+      for (size_t i = batch_start; i < end; i++) w.write_uint(uint64_t(d.offsets[i]), d.offset_bits[i]);
+  }
+};
+
+// ===========================================================================
+// Chunk compressor (pco/src/wrapped/chunk_compressor.rs)
+// ===========================================================================
+struct VarCompressorBase {
+  virtual ~VarCompressorBase() {}
+};
+
+template <typename L>
+struct PageInfoVar {
+  std::vector<uint64_t> delta_state;
+  size_t start = 0, end = 0;  // stored range in the var's latent array
+};
+
+template <typename L>  // L = number's latent type
+struct ChunkCompressor {
+  ChunkMeta meta;
+  uint8_t number_type;
+  std::vector<size_t> page_ns;
+  // per page, per var
+  std::vector<PageInfoVar<L>> pi_delta, pi_primary, pi_secondary;
+  std::unique_ptr<VarCompressor<uint32_t>> vc_delta;
+  std::unique_ptr<VarCompressor<L>> vc_primary, vc_secondary;
+  std::vector<Weight> counts_delta, counts_primary, counts_secondary;
+
+  size_t n_pages() const { return page_ns.size(); }
+
+  // chunk_compressor.rs:502-541
+  bool should_fallback(size_t n) const {
+    if (meta.delta.kind == DeltaKind::NoOp && meta.mode.kind == ModeKind::Classic) return false;
+    size_t worst_case_body_bit_size = 7 * n_pages();
+    auto add = [&](const LatentVarMeta& vm, const std::vector<Weight>& counts) {
+      for (size_t i = 0; i < vm.bins.size() && i < counts.size(); i++) {
+        const Bin& b = vm.bins[i];
+        Bitlen wc = b.offset_bits + vm.ans_size_log - ilog2_u64(b.weight);
+        worst_case_body_bit_size += size_t(counts[i]) * size_t(wc);
+      }
+    };
+    if (meta.has_delta_var) add(meta.delta_var, counts_delta);
+    add(meta.primary, counts_primary);
+    if (meta.has_secondary) add(meta.secondary, counts_secondary);
+    size_t worst_case_size = meta.max_size() + n_pages() * meta.exact_page_meta_size() + (worst_case_body_bit_size + 7) / 8;
+    // wrapped/guarantee.rs:11-37
+    ChunkMeta base;
+    base.number_bits = meta.number_bits;
+    base.primary.latent_bits = meta.number_bits;
+    base.primary.ans_size_log = 0;
+    base.primary.bins = {Bin{1, 0, meta.number_bits}};
+    size_t baseline = base.max_size() + (n * size_t(meta.number_bits) + 7) / 8;
+    return worst_case_size > baseline;
+  }
+
+  // chunk_compressor.rs:575-603 (page_size_hint_inner)
+  size_t page_size_hint_inner(size_t page_idx, double overestimation) const {
+    size_t body_bit_size = 0;
+    auto add = [&](double avg_bits, size_t n_stored) {
+      double nums_bit_size = double(n_stored) * avg_bits;
+      body_bit_size += size_t(std::ceil(nums_bit_size * overestimation));
+    };
+    if (vc_delta) add(vc_delta->avg_bits_per_latent, pi_delta[page_idx].end - pi_delta[page_idx].start);
+    add(vc_primary->avg_bits_per_latent, pi_primary[page_idx].end - pi_primary[page_idx].start);
+    if (vc_secondary) add(vc_secondary->avg_bits_per_latent, pi_secondary[page_idx].end - pi_secondary[page_idx].start);
+    return meta.exact_page_meta_size() + (body_bit_size + 7) / 8;
+  }
+  size_t meta_size_hint() const { return meta.max_size(); }
+  size_t page_size_hint(size_t page_idx) const { return page_size_hint_inner(page_idx, 1.2); }
+
+  void write_meta(std::vector<uint8_t>& dst) const { write_chunk_meta(meta, dst); }
+
+  // chunk_compressor.rs:624-705
+  void write_page(size_t page_idx, std::vector<uint8_t>& dst) {
+    if (page_idx >= n_pages()) invalid_argument("page idx exceeds num pages");
+    PageDissectedVar<uint32_t> dd;
+    PageDissectedVar<L> dp, ds;
+    if (vc_delta) dd = vc_delta->dissect_page(pi_delta[page_idx].start, pi_delta[page_idx].end);
+    dp = vc_primary->dissect_page(pi_primary[page_idx].start, pi_primary[page_idx].end);
+    if (vc_secondary) ds = vc_secondary->dissect_page(pi_secondary[page_idx].start, pi_secondary[page_idx].end);
+    PageMeta pm;
+    auto fill = [&](PageVarMeta& pv, const std::vector<uint64_t>& state, const AnsState* finals, AnsState default_state) {
+      pv.delta_state = state;
+      for (size_t j = 0; j < ANS_INTERLEAVING; j++) pv.ans_final_state_idxs[j] = finals[j] - default_state;
+    };
+    if (vc_delta) fill(pm.delta_var, pi_delta[page_idx].delta_state, dd.ans_final_states, vc_delta->encoder.default_state());
+    fill(pm.primary, pi_primary[page_idx].delta_state, dp.ans_final_states, vc_primary->encoder.default_state());
+    if (vc_secondary) fill(pm.secondary, pi_secondary[page_idx].delta_state, ds.ans_final_states, vc_secondary->encoder.default_state());
+    BitWriter w(dst);
+    write_page_meta(meta, pm, w);
+    size_t page_n = page_ns[page_idx];
+    for (size_t batch_start = 0; batch_start < page_n; batch_start += FULL_BATCH_N) {
+      if (vc_delta) vc_delta->write_dissected_batch(dd, batch_start, w);
+      vc_primary->write_dissected_batch(dp, batch_start, w);
+      if (vc_secondary) vc_secondary->write_dissected_batch(ds, batch_start, w);
+    }
+    w.finish();
+  }
+};
+
+// ----- sampling for Auto delta (pco/src/sampling.rs:9-60) -------------------
+inline bool calc_sample_n(size_t n, size_t* out) {
+  if (n >= 10) { *out = 10 + (n - 10) / 40; return true; }
+  return false;
+}
+template <typename L>
+inline bool choose_delta_sample(const std::vector<L>& primary, std::vector<L>* sample) {
+  size_t n = primary.size();
+  size_t target;
+  if (!calc_sample_n(n, &target)) return false;
+  size_t group_n = std::min<size_t>(200, n);
+  size_t n_groups = (target + 199) / 200;
+  size_t nominal = n_groups * group_n;
+  size_t stride = group_n + ((n > nominal ? n - nominal : 0) / (std::max<size_t>(n_groups, 2) - 1));
+  sample->clear();
+  sample->reserve(nominal);
+  for (size_t i = 0; i < n_groups; i++) {
+    size_t gs = stride * i;
+    sample->insert(sample->end(), primary.begin() + gs, primary.begin() + gs + group_n);
+  }
+  return true;
+}
+
+template <typename L>
+struct SplitLatents {
+  std::vector<L> primary;
+  bool has_secondary = false;
+  std::vector<L> secondary;
+};
+
+// chunk_compressor.rs:142-217 + :219-308 new_candidate
+template <typename L>
+inline std::unique_ptr<ChunkCompressor<L>> new_candidate(SplitLatents<L> latents, const std::vector<size_t>& page_ns, const Mode& mode,
+                                                         const DeltaEncoding& delta, Bitlen unoptimized_bins_log,
+                                                         uint8_t number_type) {
+  std::unique_ptr<ChunkCompressor<L>> cc(new ChunkCompressor<L>());
+  cc->number_type = number_type;
+  cc->page_ns = page_ns;
+  cc->meta.number_bits = sizeof(L) * 8;
+  cc->meta.mode = mode;
+  cc->meta.delta = delta;
+  cc->meta.has_secondary = latents.has_secondary;
+  cc->meta.has_delta_var = delta.kind == DeltaKind::Lookback;
+  size_t n = latents.primary.size();
+  std::vector<uint32_t> delta_latents;
+  if (cc->meta.has_delta_var) delta_latents.reserve(n);
+  size_t start_idx = 0;
+  LatentVarDelta enc_primary = delta_for_latent_var(cc->meta.delta, VarKey::Primary);
+  LatentVarDelta enc_secondary = delta_for_latent_var(cc->meta.delta, VarKey::Secondary);
+  auto encode_var = [&](const LatentVarDelta& enc, const std::vector<DeltaLookback>& page_lookbacks, std::vector<L>& v, size_t s, size_t e) {
+    PageInfoVar<L> pi;
+    std::vector<L> st;
+    switch (enc.kind) {
+      case DeltaKind::NoOp: break;
+      case DeltaKind::Consecutive: st = consecutive_encode_in_place<L>(enc.enc->order, v.data() + s, e - s); break;
+      case DeltaKind::Lookback: st = lookback_encode_in_place<L>(*enc.enc, page_lookbacks.data(), v.data() + s, e - s); break;
+      case DeltaKind::Conv1: invalid_argument("oracle: Conv1 encode not restated"); break;
+    }
+    for (L x : st) pi.delta_state.push_back(uint64_t(x));
+    pi.start = std::min(s + enc.n_latents_per_state(), e);
+    pi.end = e;
+    return pi;
+  };
+  for (size_t page_n : page_ns) {
+    size_t end_idx = start_idx + page_n;
+    std::vector<DeltaLookback> page_lookbacks;
+    if (cc->meta.has_delta_var) page_lookbacks = choose_lookbacks<L>(cc->meta.delta, latents.primary.data() + start_idx, page_n);
+    cc->pi_primary.push_back(encode_var(enc_primary, page_lookbacks, latents.primary, start_idx, end_idx));
+    if (latents.has_secondary) cc->pi_secondary.push_back(encode_var(enc_secondary, page_lookbacks, latents.secondary, start_idx, end_idx));
+    if (cc->meta.has_delta_var) {
+      PageInfoVar<L> pi;
+      pi.start = delta_latents.size();
+      pi.end = delta_latents.size() + page_lookbacks.size();
+      cc->pi_delta.push_back(pi);
+      delta_latents.insert(delta_latents.end(), page_lookbacks.begin(), page_lookbacks.end());
+    }
+    start_idx = end_idx;
+  }
+  // train bins per var, in file order
+  auto train = [&](auto tag, const auto& var_latents, const auto& page_infos, Bitlen bins_log, LatentVarMeta& vm,
+                   std::vector<Weight>& counts) {
+    using VL = decltype(tag);
+    std::vector<VL> contiguous;
+    contiguous.reserve(var_latents.size());
+    for (const auto& pi : page_infos) contiguous.insert(contiguous.end(), var_latents.begin() + pi.start, var_latents.begin() + pi.end);
+    TrainedBins<VL> trained = train_infos<VL>(std::move(contiguous), bins_log);
+    vm.latent_bits = sizeof(VL) * 8;
+    vm.ans_size_log = trained.ans_size_log;
+    vm.bins.clear();
+    for (auto& info : trained.infos) vm.bins.push_back(Bin{info.weight, uint64_t(info.lower), info.offset_bits});
+    counts = trained.counts;
+    return trained;
+  };
+  if (cc->meta.has_delta_var) {
+    auto trained = train(uint32_t(0), delta_latents, cc->pi_delta, unoptimized_bins_log, cc->meta.delta_var, cc->counts_delta);
+    cc->vc_delta.reset(new VarCompressor<uint32_t>(trained, cc->meta.delta_var, std::move(delta_latents)));
+  }
+  {
+    auto trained = train(L(0), latents.primary, cc->pi_primary, unoptimized_bins_log, cc->meta.primary, cc->counts_primary);
+    cc->vc_primary.reset(new VarCompressor<L>(trained, cc->meta.primary, std::move(latents.primary)));
+  }
+  if (latents.has_secondary) {
+    auto trained = train(L(0), latents.secondary, cc->pi_secondary, std::min(unoptimized_bins_log, LIMITED_UNOPTIMIZED_BINS_LOG),
+                         cc->meta.secondary, cc->counts_secondary);
+    cc->vc_secondary.reset(new VarCompressor<L>(trained, cc->meta.secondary, std::move(latents.secondary)));
+  }
+  validate_chunk_meta(cc->meta);
+  return cc;
+}
+
+// chunk_compressor.rs:310-360 + :373-394
+template <typename L>
+inline DeltaEncoding choose_delta_encoding(const SplitLatents<L>& latents, const ChunkConfig& config, Bitlen unoptimized_bins_log,
+                                           uint8_t number_type) {
+  DeltaEncoding noop;
+  size_t n = latents.primary.size();
+  switch (config.delta_kind) {
+    case DeltaSpecKind::NoOp: return noop;
+    case DeltaSpecKind::TryConsecutive: {
+      if (config.delta_order == 0) return noop;
+      DeltaEncoding d;
+      d.kind = DeltaKind::Consecutive;
+      d.order = config.delta_order;
+      return d;
+    }
+    case DeltaSpecKind::TryLookback: return new_lookback(n);
+    case DeltaSpecKind::TryConv1:
+      if (config.delta_order == 0) return noop;
+      invalid_argument("oracle: Conv1 encode not restated");
+    case DeltaSpecKind::Auto: break;
+  }
+  // choose_auto_delta_encoding
+  std::vector<L> sample;
+  if (!choose_delta_sample<L>(latents.primary, &sample)) return noop;
+  size_t sample_n = sample.size();
+  auto cost_of = [&](const DeltaEncoding& enc) -> float {
+    SplitLatents<L> s;
+    s.primary = sample;
+    Mode classic;
+    auto cc = new_candidate<L>(std::move(s), {sample_n}, classic, enc, unoptimized_bins_log, number_type);
+    return float(cc->meta_size_hint() + cc->page_size_hint_inner(0, 1.0));
+  };
+  DeltaEncoding best = noop;
+  float best_cost = cost_of(noop);
+  float lookback_penalty = 0.25f * float(sample_n);
+  if (best_cost > lookback_penalty) {
+    float lookback_cost = cost_of(new_lookback(sample_n)) + lookback_penalty;
+    if (lookback_cost < best_cost) {
+      best = new_lookback(n);
+      best_cost = lookback_cost;
+    }
+  }
+  for (size_t order = 1; order <= MAX_CONSECUTIVE_DELTA_ORDER; order++) {
+    DeltaEncoding enc;
+    enc.kind = DeltaKind::Consecutive;
+    enc.order = order;
+    float cost = cost_of(enc);
+    if (cost < best_cost) { best = enc; best_cost = cost; } else break;
+  }
+  return best;
+}
+
+// Mode split (mode/classic.rs:6-12, float_mult.rs:38-60, int_mult.rs:20-36, float_quant.rs:41-73)
+template <typename L>
+inline SplitLatents<L> split_latents(const L* nums, size_t n, uint8_t number_type, const ChunkConfig& config, Mode* mode_out) {
+  bool isf = number_type_is_float(number_type), iss = number_type_is_signed(number_type);
+  SplitLatents<L> out;
+  Mode mode;
+  ModeSpecKind kind = config.mode_kind;
+  if (kind == ModeSpecKind::Auto) invalid_argument("oracle: ModeSpec::Auto not restated; pass an explicit mode");
+  if (kind == ModeSpecKind::TryDict) invalid_argument("oracle: Dict encode not restated");
+  if (isf && kind == ModeSpecKind::TryIntMult) invalid_argument("unable to use int mult mode on floats");
+  if (!isf && (kind == ModeSpecKind::TryFloatMult || kind == ModeSpecKind::TryFloatQuant)) invalid_argument("unable to use float mode for ints");
+  out.primary.resize(n);
+  switch (kind) {
+    case ModeSpecKind::Classic:
+      for (size_t i = 0; i < n; i++) out.primary[i] = to_latent_ordered_bits<L>(nums[i], isf, iss);
+      break;
+    case ModeSpecKind::TryIntMult: {
+      mode.kind = ModeKind::IntMult;
+      L base = L(config.int_mult_base);
+      mode.base_latent = base;
+      if (!mode_is_valid(mode, number_type)) invalid_argument("The chosen mode was invalid for the number type");
+      out.has_secondary = true;
+      out.secondary.resize(n);
+      for (size_t i = 0; i < n; i++) {
+        L u = to_latent_ordered_bits<L>(nums[i], isf, iss);
+        out.primary[i] = L(u / base);
+        out.secondary[i] = L(u % base);
+      }
+      break;
+    }
+    case ModeSpecKind::TryFloatQuant: {
+      mode.kind = ModeKind::FloatQuant;
+      mode.k = config.float_quant_k;
+      if (!mode_is_valid(mode, number_type)) invalid_argument("The chosen mode was invalid for the number type");
+      out.has_secondary = true;
+      out.secondary.resize(n);
+      Bitlen k = mode.k;
+      L lowest_k_bits_max = L(L(L(1) << k) - 1);
+      for (size_t i = 0; i < n; i++) {
+        L num_ = to_latent_ordered_bits<L>(nums[i], true, false);
+        out.primary[i] = L(num_ >> k);
+        L lowest = L(num_ & lowest_k_bits_max);
+        bool sign_positive = (nums[i] & LatentTraits<L>::MID) == 0;
+        out.secondary[i] = sign_positive ? lowest : L(lowest_k_bits_max - lowest);
+      }
+      break;
+    }
+    case ModeSpecKind::TryFloatMult: {
+      if constexpr (sizeof(L) == 4 || sizeof(L) == 8) {
+        using FO = FloatOps<L>;
+        mode.kind = ModeKind::FloatMult;
+        auto base = FO::from_f64(config.float_mult_base);
+        auto inv_base = FO::inv(base);
+        mode.base_latent = to_latent_ordered_bits<L>(FO::to_bits(base), true, false);
+        if (!mode_is_valid(mode, number_type)) invalid_argument("The chosen mode was invalid for the number type");
+        out.has_secondary = true;
+        out.secondary.resize(n);
+        for (size_t i = 0; i < n; i++) {
+          auto num = FO::from_bits(nums[i]);
+          auto mult = FO::round_(FO::mul(num, inv_base));
+          out.primary[i] = int_float_to_latent<L>(mult);
+          L a = to_latent_ordered_bits<L>(nums[i], true, false);
+          L b = to_latent_ordered_bits<L>(FO::to_bits(FO::mul(mult, base)), true, false);
+          out.secondary[i] = L(L(a - b) + LatentTraits<L>::MID);
+        }
+      } else {
+        invalid_argument("oracle: FloatMult encode restated for f32/f64 only");
+      }
+      break;
+    }
+    default: break;
+  }
+  *mode_out = mode;
+  return out;
+}
+
+// chunk_compressor.rs:396-500 ChunkCompressor::new (+ fallback_chunk_compressor)
+template <typename L>
+inline std::unique_ptr<ChunkCompressor<L>> new_chunk_compressor(const L* nums, size_t n, uint8_t number_type, const ChunkConfig& config) {
+  validate_config(config, sizeof(L) * 8);
+  if (n == 0) invalid_argument("cannot compress empty chunk");
+  if (n > MAX_ENTRIES) invalid_argument("count may not exceed 16777216 per chunk");
+  Mode mode;
+  SplitLatents<L> latents = split_latents<L>(nums, n, number_type, config, &mode);
+  Bitlen unoptimized_bins_log = choose_unoptimized_bins_log(config.compression_level, n);
+  DeltaEncoding delta = choose_delta_encoding<L>(latents, config, unoptimized_bins_log, number_type);
+  std::vector<size_t> page_ns = n_per_page(config, n);
+  auto candidate = new_candidate<L>(std::move(latents), page_ns, mode, delta, unoptimized_bins_log, number_type);
+  if (candidate->should_fallback(n)) {
+    // fallback_chunk_compressor: Classic, NoOp, one bin {weight 1, lower 0, offset_bits L::BITS}
+    ChunkConfig cfg = config;
+    cfg.mode_kind = ModeSpecKind::Classic;
+    Mode classic;
+    SplitLatents<L> split = split_latents<L>(nums, n, number_type, cfg, &classic);
+    std::unique_ptr<ChunkCompressor<L>> cc(new ChunkCompressor<L>());
+    cc->number_type = number_type;
+    cc->page_ns = page_ns;
+    cc->meta.number_bits = sizeof(L) * 8;
+    cc->meta.primary.latent_bits = sizeof(L) * 8;
+    cc->meta.primary.ans_size_log = 0;
+    cc->meta.primary.bins = {Bin{1, 0, Bitlen(sizeof(L) * 8)}};
+    size_t s = 0;
+    for (size_t page_n : page_ns) {
+      PageInfoVar<L> pi;
+      pi.start = s;
+      pi.end = s + page_n;
+      cc->pi_primary.push_back(pi);
+      s += page_n;
+    }
+    TrainedBins<L> trained;
+    trained.infos = {BinCompressionInfo<L>{1, 0, LatentTraits<L>::MAX, Bitlen(sizeof(L) * 8), 0}};
+    trained.ans_size_log = 0;
+    trained.counts = {Weight(n)};
+    cc->counts_primary = trained.counts;
+    cc->vc_primary.reset(new VarCompressor<L>(trained, cc->meta.primary, std::move(split.primary)));
+    return cc;
+  }
+  return candidate;
+}
+
+// ===========================================================================
+// Standalone (pco/src/standalone/{compressor,decompressor,simple}.rs)
+// ===========================================================================
+// standalone/compressor.rs:191-203
+template <typename L>
+inline void write_standalone_chunk(ChunkCompressor<L>& cc, std::vector<uint8_t>& dst) {
+  BitWriter w(dst);
+  w.write_aligned_bytes(&cc.number_type, 1);
+  w.write_uint(cc.page_ns[0] - 1, BITS_TO_ENCODE_N_ENTRIES);
+  w.finish();
+  cc.write_meta(dst);
+  cc.write_page(0, dst);
+}
+
+// standalone/simple.rs:22-91; `uniform_type` selects the _into flavour (header byte 5)
+template <typename L>
+inline void simple_compress(const L* nums, size_t n, uint8_t number_type, const ChunkConfig& config, bool uniform_type,
+                            std::vector<uint8_t>& dst) {
+  write_standalone_header(dst, n, uniform_type ? number_type : 0);
+  std::vector<size_t> chunks = n_per_page(config, n);
+  size_t start = 0;
+  ChunkConfig this_cfg = config;
+  for (size_t page_n : chunks) {
+    this_cfg.paging_kind = PagingKind::Exact;
+    this_cfg.exact_pages = {page_n};
+    auto cc = new_chunk_compressor<L>(nums + start, page_n, number_type, this_cfg);
+    write_standalone_chunk<L>(*cc, dst);
+    start += page_n;
+  }
+  dst.push_back(MAGIC_TERMINATION_BYTE);
+}
+
+// A standalone file reader over a padded copy of the source
+struct PaddedSrc {
+  std::vector<uint8_t> buf;
+  size_t len;
+  PaddedSrc(const uint8_t* src, size_t n) : buf(n + READ_PADDING, 0), len(n) {
+    if (n) std::memcpy(buf.data(), src, n);
+  }
+};
+
+// standalone/decompressor.rs:190-258: returns false at the terminator
+template <typename L>
+inline bool read_chunk_preamble(BitReader& r, const StandaloneHeader& h, uint8_t expected_type, size_t* n_out) {
+  uint8_t b = r.read_aligned_bytes(1)[0];
+  r.check_in_bounds();
+  if (b == MAGIC_TERMINATION_BYTE) return false;
+  if (h.uniform_type != 0 && h.uniform_type != b) corruption("chunk's number type does not match file's uniform number type");
+  if (b != expected_type) corruption("requested chunk decompression does not match chunk's number type");
+  *n_out = size_t(r.read_uint(BITS_TO_ENCODE_N_ENTRIES)) + 1;
+  r.check_in_bounds();
+  return true;
+}
+
+// standalone/decompressor.rs:265-275 simple_decompress
+template <typename L>
+inline void simple_decompress(const uint8_t* src, size_t src_len, uint8_t number_type, std::vector<L>& out) {
+  PaddedSrc ps(src, src_len);
+  BitReader r(ps.buf.data(), ps.len);
+  StandaloneHeader h = read_standalone_header(r);
+  size_t n;
+  while (read_chunk_preamble<L>(r, h, number_type, &n)) {
+    ChunkMeta cm = read_chunk_meta(r, h.format, sizeof(L) * 8);
+    ChunkDecoder cd(std::move(cm), number_type);
+    PageDecoder<L> pd(cd, r, n);
+    size_t old = out.size();
+    out.resize(old + n);
+    pd.read(out.data() + old, n);
+  }
+}
+
+// standalone/simple.rs:100-143 simple_decompress_into
+template <typename L>
+inline Progress simple_decompress_into(const uint8_t* src, size_t src_len, uint8_t number_type, L* dst, size_t dst_len) {
+  PaddedSrc ps(src, src_len);
+  BitReader r(ps.buf.data(), ps.len);
+  StandaloneHeader h = read_standalone_header(r);
+  std::vector<L> incomplete(FULL_BATCH_N);
+  Progress progress;
+  for (;;) {
+    size_t n;
+    if (!read_chunk_preamble<L>(r, h, number_type, &n)) { progress.finished = true; break; }
+    ChunkMeta cm = read_chunk_meta(r, h.format, sizeof(L) * 8);
+    ChunkDecoder cd(std::move(cm), number_type);
+    PageDecoder<L> pd(cd, r, n);
+    size_t limit;
+    bool is_limited;
+    if (dst_len < n) { limit = dst_len / FULL_BATCH_N * FULL_BATCH_N; is_limited = true; } else { limit = dst_len; is_limited = false; }
+    Progress p = pd.read(dst, limit);
+    dst += p.n_processed;
+    dst_len -= p.n_processed;
+    progress.n_processed += p.n_processed;
+    if (dst_len != 0) {
+      Progress p2 = pd.read(incomplete.data(), FULL_BATCH_N);
+      size_t np = std::min(dst_len, p2.n_processed);
+      std::memcpy(dst, incomplete.data(), np * sizeof(L));
+      dst += np;
+      dst_len -= np;
+      progress.n_processed += np;
+    }
+    if (dst_len == 0 && is_limited) break;
+  }
+  return progress;
+}
+
+// standalone/guarantee.rs:11-38 + wrapped/guarantee.rs:35-37
+inline size_t standalone_header_size() { return 4 + 1 + (BITS_TO_ENCODE_VARINT_POWER + 64 + BITS_TO_ENCODE_STANDALONE_VERSION + 7) / 8 + 2; }
+inline size_t wrapped_chunk_size(Bitlen latent_bits, size_t n) {
+  ChunkMeta base;
+  base.number_bits = latent_bits;
+  base.primary.latent_bits = latent_bits;
+  base.primary.bins = {Bin{1, 0, latent_bits}};
+  return base.max_size() + (n * size_t(latent_bits) + 7) / 8;
+}
+inline size_t standalone_chunk_size(Bitlen latent_bits, size_t n) { return 1 + 3 + wrapped_chunk_size(latent_bits, n); }
+inline size_t standalone_file_size(Bitlen latent_bits, size_t n, const ChunkConfig& paging) {
+  size_t res = standalone_header_size();
+  for (size_t c : n_per_page(paging, n)) res += standalone_chunk_size(latent_bits, c);
+  return res + 1;
+}
+
+}  // namespace pco_oracle
