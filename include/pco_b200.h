@@ -1,0 +1,98 @@
+/* pco_b200.h — extensions to the reference C ABI (cpcodec.h) that the three reference
+ * functions cannot express: explicit mode/delta/paging specs, the non-uniform header
+ * flavour, partial-destination decompression, the wrapped chunk/page API, device-resident
+ * buffers on a caller stream, and the per-batch side index.
+ *
+ * Every entry point is plain C: pointers, sizes and POD structs; no torch / CUDA types in
+ * signatures (a cudaStream_t travels as void*).  Each declaration cites the reference
+ * interface it stands in for.  All functions are thread-safe; the library keeps only a
+ * mutex-guarded cache of device scratch memory between calls.
+ */
+#ifndef PCO_B200_H
+#define PCO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "cpcodec.h"
+
+#if defined(__cplusplus)
+extern "C" {
+#endif
+
+/* pco::errors::ErrorKind (pco/src/errors.rs:8-24), plus two kinds the CPU reference cannot
+ * produce: a missing/failed CUDA device, and a format feature the GPU path does not decode. */
+typedef enum PcoB200Error {
+  PCO_B200_OK = 0,
+  PCO_B200_CORRUPTION = 1,
+  PCO_B200_INSUFFICIENT_DATA = 2,
+  PCO_B200_INVALID_ARGUMENT = 3,
+  PCO_B200_IO = 4,          /* destination buffer too small (std::io::ErrorKind::WriteZero) */
+  PCO_B200_INVALID_TYPE = 5,
+  PCO_B200_CUDA = 6,        /* no device / launch failure: this library has no CPU fallback */
+  PCO_B200_UNSUPPORTED = 7  /* valid pco, but outside the GPU hot path */
+} PcoB200Error;
+
+/* pco::ModeSpec (pco/src/chunk_config.rs:15-51) */
+enum { PCO_B200_MODE_AUTO = 0, PCO_B200_MODE_CLASSIC = 1, PCO_B200_MODE_TRY_FLOAT_MULT = 2,
+       PCO_B200_MODE_TRY_FLOAT_QUANT = 3, PCO_B200_MODE_TRY_INT_MULT = 4, PCO_B200_MODE_TRY_DICT = 5 };
+/* pco::DeltaSpec (pco/src/chunk_config.rs:63-109) */
+enum { PCO_B200_DELTA_AUTO = 0, PCO_B200_DELTA_NOOP = 1, PCO_B200_DELTA_TRY_CONSECUTIVE = 2,
+       PCO_B200_DELTA_TRY_LOOKBACK = 3, PCO_B200_DELTA_TRY_CONV1 = 4 };
+/* pco::PagingSpec (pco/src/chunk_config.rs:114-125) */
+enum { PCO_B200_PAGING_EQUAL_PAGES_UP_TO = 0, PCO_B200_PAGING_EXACT = 1 };
+
+/* pco::ChunkConfig (pco/src/chunk_config.rs:193-224) as a POD. */
+typedef struct PcoB200ChunkConfig {
+  uint32_t compression_level;   /* 0..12, default 8 */
+  uint32_t mode_spec;           /* PCO_B200_MODE_* */
+  double float_mult_base;       /* TryFloatMult(base) */
+  uint64_t int_mult_base;       /* TryIntMult(base) */
+  uint32_t float_quant_k;       /* TryFloatQuant(k) */
+  uint32_t delta_spec;          /* PCO_B200_DELTA_* */
+  uint32_t delta_order;         /* TryConsecutive(order) / TryConv1(order) */
+  uint32_t paging_spec;         /* PCO_B200_PAGING_* */
+  uint64_t max_page_n;          /* EqualPagesUpTo(n); 0 -> 2^18 */
+  const uint64_t *exact_page_ns;/* Exact(vec) */
+  uint64_t n_exact_pages;
+  uint32_t enable_8_bit;
+  uint32_t reserved;
+} PcoB200ChunkConfig;
+
+/* pco::Progress (pco/src/progress.rs:3-11) */
+typedef struct PcoB200Progress {
+  size_t n_processed;
+  int finished;
+} PcoB200Progress;
+
+/* Buffer-location flags for the *_ex entry points. */
+enum { PCO_B200_SRC_ON_DEVICE = 1u, PCO_B200_DST_ON_DEVICE = 2u };
+
+/* Message of the last error raised on the calling thread (pco::errors::PcoError::message). */
+const char *pco_b200_last_error_message(void);
+/* 1 if a usable sm_100 device is present. */
+int pco_b200_device_available(void);
+
+/* pco::standalone::simple_decompress_into (pco/src/standalone/simple.rs:100-143): never errors on a
+ * short or long dst; decodes whole 256-batches then one scratch batch into a short dst. */
+PcoB200Error pco_b200_simple_decompress_into(const void *compressed, size_t compressed_len, unsigned char dtype,
+                                             void *dst, size_t dst_len, PcoB200Progress *progress);
+
+/* As above, with buffers optionally resident in HBM (flags), work enqueued on `cuda_stream`
+ * (NULL = default stream; the call returns after the stream work completes), and an optional
+ * side index (`index`, `index_len` bytes; NULL = walk the tANS stream on the device first).
+ * The side index is metadata *beside* the bit-exact .pco bytes (docs/format.md:34-38). */
+PcoB200Error pco_b200_decompress_ex(const void *compressed, size_t compressed_len, unsigned char dtype, void *dst,
+                                    size_t dst_len, PcoB200Progress *progress, const void *index, size_t index_len,
+                                    uint32_t flags, void *cuda_stream);
+
+/* Build the side index of a standalone file (one serial tANS walk per chunk on the device).
+ * index_cap >= pco_b200_index_size_bound(n_total, 2). */
+size_t pco_b200_index_size_bound(size_t n, size_t n_chunks_hint);
+PcoB200Error pco_b200_build_index(const void *compressed, size_t compressed_len, unsigned char dtype, void *index,
+                                  size_t index_cap, size_t *index_len, uint32_t flags, void *cuda_stream);
+
+#if defined(__cplusplus)
+}
+#endif
+#endif /* PCO_B200_H */

@@ -1,0 +1,747 @@
+// Decode-side kernels for the pco hot path on sm_100a:
+//   walk_kernel    — K6: serial tANS walk that produces the per-batch side index (cold path)
+//   decode_kernel  — K7+K8+K9 fused: tANS symbols -> offsets unpack -> un-delta -> join -> store
+//
+// Reference behaviour restated here (paths relative to /root/reference):
+//   tANS decode step        pco/src/page_latent_decompressor.rs:89-177, pco/src/ans/decoding.rs:27-48
+//   table spread            pco/src/ans/spec.rs:24-59
+//   offsets                 pco/src/page_latent_decompressor.rs:15-44
+//   consecutive un-delta    pco/src/delta/consecutive.rs:35-50, pco/src/delta/mod.rs:29-33
+//   joins                   pco/src/mode/{classic.rs:14-24,float_mult.rs:17-36,int_mult.rs:38-54,float_quant.rs:13-39}
+//   per-batch driver        pco/src/wrapped/page_decompressor.rs:115-221
+#pragma once
+#include "codec_common.cuh"
+
+namespace pcob200 {
+
+constexpr int DEC_THREADS = 256;
+constexpr int DEC_WARPS = DEC_THREADS / 32;
+constexpr int SMALL_MAX_SIZE_LOG = 10;
+constexpr int SMALL_MAX_BINS = 256;
+constexpr int SYM_ROW_WORDS = 65;  // 256 one-byte symbols + 4 bytes pad: odd word stride -> conflict-free rows
+constexpr int CARRY_RING = 32;
+
+// node word: next_state_idx_base (14 bits) | field (14 bits) << 14 | bits_to_read (4 bits) << 28
+//   decode tables: field = bin index;  walker tables: field = bin offset_bits
+__device__ __forceinline__ uint32_t node_base(uint32_t n) { return n & 0x3fffu; }
+__device__ __forceinline__ uint32_t node_field(uint32_t n) { return (n >> 14) & 0x3fffu; }
+__device__ __forceinline__ uint32_t node_btr(uint32_t n) { return n >> 28; }
+
+// ---------------------------------------------------------------------------
+// Shared memory layout of one decode CTA (SMALL variant: size_log <= 10, n_bins <= 256)
+// ---------------------------------------------------------------------------
+struct DecodeSmem {
+  ChunkHdr hdr;
+  uint32_t node[MAX_VARS][1 << SMALL_MAX_SIZE_LOG];
+  uint64_t bin_lower[MAX_VARS][SMALL_MAX_BINS];
+  uint8_t bin_ob[MAX_VARS][SMALL_MAX_BINS];
+  uint16_t bin_weight[MAX_VARS][SMALL_MAX_BINS];
+  uint32_t bin_cum[MAX_VARS][SMALL_MAX_BINS + 1];
+  uint16_t sym_of_state[MAX_VARS][1 << SMALL_MAX_SIZE_LOG];
+  uint32_t rank_counter[MAX_VARS][SMALL_MAX_BINS];
+  uint32_t off_start[DEC_THREADS];        // per (var, batch-in-tile): bit position of the offsets section
+  uint64_t carry[CARRY_RING][MAX_ORDER];  // delta moments at the start of batch b (ring slot b % CARRY_RING)
+  volatile uint32_t carry_seq[CARRY_RING];
+  uint32_t err;
+  uint32_t sym[DEC_THREADS * SYM_ROW_WORDS];
+};
+
+// ---------------------------------------------------------------------------
+// Cooperative table build for one latent var (all threads of the CTA call this).
+// WALKER = true stores offset_bits in the node field; false stores the bin index.
+// ---------------------------------------------------------------------------
+template <bool WALKER>
+__device__ void build_var_tables(const BitSrc& src, ChunkHdr& hdr, int v, uint32_t* node, uint64_t* bin_lower, uint8_t* bin_ob,
+                                 uint16_t* bin_weight, uint32_t* bin_cum, uint16_t* sym_of_state, uint32_t* rank_counter, uint32_t* err,
+                                 bool add_mid_to_lower) {
+  const VarHdr vh = hdr.var[v];
+  const uint32_t n_bins = vh.n_bins;
+  const uint32_t size_log = vh.ans_size_log;
+  const uint32_t size = 1u << size_log;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const uint64_t mid = uint64_t(1) << (vh.latent_bits - 1);
+  const uint64_t lmask = vh.latent_bits == 64 ? ~uint64_t(0) : ((uint64_t(1) << vh.latent_bits) - 1);
+  const uint32_t obb = offset_bits_bits(vh.latent_bits);
+  // 1. bins (metadata/chunk_latent_var.rs:22-53)
+  uint32_t my_max_ob = 0;
+  for (uint32_t i = tid; i < n_bins; i += nt) {
+    uint64_t p = vh.bins_bit + uint64_t(i) * vh.bin_stride;
+    uint32_t weight = uint32_t(read_bits_safe(src, p, size_log)) + 1;
+    uint64_t lower = read_bits_safe(src, p + size_log, vh.latent_bits);
+    uint32_t ob = uint32_t(read_bits_safe(src, p + size_log + vh.latent_bits, obb));
+    if (ob > vh.latent_bits) atomicMax(err, (uint32_t)ST_CORRUPTION);
+    bin_weight[i] = uint16_t(weight);
+    if (!WALKER) bin_lower[i] = add_mid_to_lower ? ((lower + mid) & lmask) : lower;
+    bin_ob[i] = uint8_t(ob);
+    rank_counter[i] = 0;
+    my_max_ob = max(my_max_ob, ob);
+  }
+  if (n_bins == 0 && tid == 0) {
+    // zero bins: one implicit symbol with weight 1 (ans/spec.rs:61-66); size_log must be 0
+    bin_weight[0] = 1;
+    if (!WALKER) bin_lower[0] = add_mid_to_lower ? mid : 0;
+    bin_ob[0] = 0;
+    rank_counter[0] = 0;
+  }
+  if (my_max_ob) atomicMax(&hdr.var[v].max_offset_bits, my_max_ob);
+  __syncthreads();
+  const uint32_t nb = n_bins == 0 ? 1 : n_bins;
+  // 2. cumulative weights (serial: <= 256 adds by one thread; a few hundred cycles)
+  if (tid == 0) {
+    uint32_t c = 0;
+    for (uint32_t i = 0; i < nb; i++) { bin_cum[i] = c; c += bin_weight[i]; }
+    bin_cum[nb] = c;
+    if (c != size) atomicMax(err, (uint32_t)ST_CORRUPTION);  // ans/spec.rs:38-44
+  }
+  __syncthreads();
+  if (*err) return;
+  // 3. spread (ans/spec.rs:24-59): step t -> state (stride * t) & (size - 1)
+  uint32_t stride = (3 * size) / 5;
+  if ((stride & 1) == 0) stride += 1;
+  for (uint32_t t = tid; t < size; t += nt) {
+    // largest i with bin_cum[i] <= t
+    uint32_t lo = 0, hi = nb;  // invariant: cum[lo] <= t < cum[hi]
+    while (hi - lo > 1) {
+      uint32_t m = (lo + hi) >> 1;
+      if (bin_cum[m] <= t) lo = m; else hi = m;
+    }
+    sym_of_state[(stride * t) & (size - 1)] = uint16_t(lo);
+  }
+  __syncthreads();
+  // 4. decoder nodes in state order (ans/decoding.rs:27-48): x_s = weight + (#earlier states of the symbol)
+  if (tid < 32) {
+    const uint32_t lane = tid;
+    for (uint32_t base = 0; base < size; base += 32) {
+      uint32_t s = base + lane;
+      bool active = s < size;
+      uint32_t sym = active ? sym_of_state[s] : 0xffffffffu;
+      uint32_t m = __match_any_sync(0xffffffffu, sym);
+      uint32_t in_group = __popc(m & ((1u << lane) - 1));
+      uint32_t prev = active ? rank_counter[sym] : 0;
+      __syncwarp();
+      if (active && in_group == 0) rank_counter[sym] = prev + __popc(m);
+      __syncwarp();
+      if (active) {
+        uint32_t x_s = uint32_t(bin_weight[sym]) + prev + in_group;
+        uint32_t btr = __clz(x_s) - __clz(size);
+        uint32_t nbase = (x_s << btr) - size;
+        uint32_t field = WALKER ? uint32_t(bin_ob[sym]) : sym;
+        node[s] = nbase | (field << 14) | (btr << 28);
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------
+// tANS symbol walk of one batch by ONE thread (page_latent_decompressor.rs:89-177).
+//   cw   : aligned words of the file; bit: absolute bit position; max_word: last readable word index
+//   Returns the bit position after the batch's ANS section and (WALKER) the sum of offset bits.
+// ---------------------------------------------------------------------------
+struct WalkState {
+  uint32_t st[4];
+};
+
+template <bool WALKER>
+__device__ __forceinline__ uint64_t ans_walk_batch(const uint64_t* __restrict__ cw, uint64_t max_word, uint64_t bit, WalkState& ws,
+                                                   const uint32_t* __restrict__ node, int count, uint32_t* __restrict__ sym_row,
+                                                   uint32_t& ob_sum) {
+  uint64_t wi = bit >> 6;
+  auto ld = [&](uint64_t i) -> uint64_t { return __ldg(cw + (i <= max_word ? i : max_word)); };
+  uint64_t w0 = ld(wi), w1 = ld(wi + 1), w2 = ld(wi + 2);
+  uint32_t s0 = ws.st[0], s1 = ws.st[1], s2 = ws.st[2], s3 = ws.st[3];
+  uint32_t obs = 0;
+  int i = 0;
+  for (; i + 4 <= count; i += 4) {
+    uint32_t n0 = node[s0], n1 = node[s1], n2 = node[s2], n3 = node[s3];
+    uint32_t r = uint32_t(bit & 63);
+    uint64_t g = r ? ((w0 >> r) | (w1 << (64 - r))) : w0;
+    uint32_t b0 = node_btr(n0), b1 = node_btr(n1), b2 = node_btr(n2), b3 = node_btr(n3);
+    uint32_t sh1 = b0, sh2 = b0 + b1, sh3 = sh2 + b2, tot = sh3 + b3;
+    uint32_t v0 = uint32_t(g) & ((1u << b0) - 1);
+    uint32_t v1 = uint32_t(g >> sh1) & ((1u << b1) - 1);
+    uint32_t v2 = uint32_t(g >> sh2) & ((1u << b2) - 1);
+    uint32_t v3 = uint32_t(g >> sh3) & ((1u << b3) - 1);
+    if (WALKER) {
+      obs += node_field(n0) + node_field(n1) + node_field(n2) + node_field(n3);
+    } else {
+      sym_row[i >> 2] = node_field(n0) | (node_field(n1) << 8) | (node_field(n2) << 16) | (node_field(n3) << 24);
+    }
+    s0 = node_base(n0) + v0;
+    s1 = node_base(n1) + v1;
+    s2 = node_base(n2) + v2;
+    s3 = node_base(n3) + v3;
+    bit += tot;
+    if ((bit >> 6) != wi) {
+      wi += 1;
+      w0 = w1;
+      w1 = w2;
+      w2 = ld(wi + 2);
+    }
+  }
+  if (i < count) {  // ragged tail of the page's last batch (page_latent_decompressor.rs:144-177)
+    uint32_t packed = 0;
+    uint32_t sarr[4] = {s0, s1, s2, s3};
+    for (int j = 0; i + j < count; j++) {
+      uint32_t n = node[sarr[j]];
+      uint32_t r = uint32_t(bit & 63);
+      uint64_t lo = ld(bit >> 6), hi = ld((bit >> 6) + 1);
+      uint64_t g = r ? ((lo >> r) | (hi << (64 - r))) : lo;
+      uint32_t b = node_btr(n);
+      uint32_t v = uint32_t(g) & ((1u << b) - 1);
+      if (WALKER) obs += node_field(n); else packed |= node_field(n) << (8 * j);
+      sarr[j] = node_base(n) + v;
+      bit += b;
+    }
+    if (!WALKER) sym_row[i >> 2] = packed;
+    s0 = sarr[0]; s1 = sarr[1]; s2 = sarr[2]; s3 = sarr[3];
+  }
+  ws.st[0] = s0; ws.st[1] = s1; ws.st[2] = s2; ws.st[3] = s3;
+  ob_sum = obs;
+  return bit;
+}
+
+struct FileParams {
+  const void* src;
+  uint64_t src_len;
+  uint32_t dtype;
+  uint32_t uniform_type;
+  uint32_t format_major;
+};
+
+// ---------------------------------------------------------------------------
+// walk_kernel (K6): builds the side index of a standalone file in place.
+//   serial_file_mode = 1: a single CTA walks the file chunk after chunk from `first_chunk_byte`
+//       (chunk boundaries are not in the stream: a chunk's length is only known once its tANS
+//       sections have been walked), appending IndexChunk records and BatchEntry arrays.
+//   serial_file_mode = 0: one CTA per pre-filled IndexChunk (offsets, n and entries_offset known).
+// Layout written: index_base + chunks_offset : IndexChunk[]; entries at index_base + entries_offset.
+// ---------------------------------------------------------------------------
+struct WalkSmem {
+  ChunkHdr hdr;
+  uint32_t node[MAX_VARS][1 << 12];
+  uint8_t bin_ob[MAX_VARS][1 << 12];
+  uint16_t bin_weight[MAX_VARS][1 << 12];
+  uint32_t bin_cum[MAX_VARS][(1 << 12) + 1];
+  uint16_t sym_of_state[MAX_VARS][1 << 12];
+  uint32_t rank_counter[MAX_VARS][1 << 12];
+  uint32_t err;
+  uint64_t next_chunk_byte;
+  uint32_t status;
+};
+
+struct WalkResult {     // written by the serial walker
+  uint32_t n_chunks;    // chunks fully indexed in this launch
+  uint32_t status;      // ST_TERMINATOR (clean end), ST_INDEX_FULL (resume later), or an error kind
+  uint64_t next_byte;   // where the next chunk (or the byte after the terminator) starts
+  uint64_t entries_end; // first free byte (from index_base) after the entries written
+  uint64_t n_total;     // numbers in the indexed chunks
+};
+
+__host__ __device__ inline uint32_t n_batches_of(uint32_t n) { return (n + BATCH_N - 1) / BATCH_N; }
+
+// Walk one chunk whose header is already parsed and tables built (WALKER nodes). One thread.
+__device__ inline uint32_t walk_chunk_serial(const BitSrc& src, const ChunkHdr& hdr, const uint32_t (*node)[1 << 12], uint64_t chunk_bit0,
+                                             BatchEntry* entries, uint64_t* end_bit_out) {
+  const uint64_t max_word = src.n_bits == 0 ? 0 : (src.n_bits - 1) >> 6;
+  const uint32_t nb = n_batches_of(hdr.n);
+  uint64_t bit = hdr.body_bit;
+  WalkState ws[MAX_VARS];
+  for (uint32_t v = 0; v < hdr.n_vars; v++)
+    for (int j = 0; j < 4; j++) ws[v].st[j] = hdr.init_state[v][j];
+  for (uint32_t b = 0; b < nb; b++) {
+    for (uint32_t v = 0; v < hdr.n_vars; v++) {
+      const VarHdr& vh = hdr.var[v];
+      uint32_t cnt = batch_count(var_stored_n(hdr.n, vh.delta_order), b);
+      BatchEntry e;
+      e.bit_pos = uint32_t(bit - chunk_bit0);
+      for (int j = 0; j < 4; j++) e.st[j] = uint16_t(ws[v].st[j]);
+      entries[size_t(v) * nb + b] = e;
+      if (cnt == 0) continue;
+      uint32_t obs;
+      if (vh.n_bins > 1) {
+        bit = ans_walk_batch<true>(src.words, max_word, bit, ws[v], node[v], int(cnt), nullptr, obs);
+      } else {
+        obs = cnt * node_field(node[v][0]);
+      }
+      bit += obs;
+      if (bit > src.n_bits) return ST_INSUFFICIENT_DATA;
+    }
+  }
+  // trailing bits of the page must be zero (wrapped/page_decompressor.rs:184-188)
+  uint32_t pad = uint32_t((8 - (bit & 7)) & 7);
+  if (pad && read_bits_safe(src, bit, pad) != 0) return ST_CORRUPTION;
+  bit += pad;
+  *end_bit_out = bit;
+  return ST_OK;
+}
+
+__global__ void __launch_bounds__(128) walk_kernel(FileParams fp, uint8_t* index_base, uint64_t chunks_offset, uint32_t max_chunks,
+                                                   uint64_t entries_begin, uint64_t entries_cap_end, uint64_t first_chunk_byte,
+                                                   uint64_t first_out_offset, uint64_t stop_after_total, uint32_t* statuses, WalkResult* result,
+                                                   int serial_file_mode) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  WalkSmem& sm = *reinterpret_cast<WalkSmem*>(smem_raw);
+  const BitSrc src = make_bitsrc(fp.src, fp.src_len);
+  const int tid = threadIdx.x;
+  IndexChunk* chunks = reinterpret_cast<IndexChunk*>(index_base + chunks_offset);
+  uint32_t c = serial_file_mode ? 0 : blockIdx.x;
+  uint64_t chunk_byte = serial_file_mode ? first_chunk_byte : chunks[c].chunk_offset;
+  uint64_t entries_off = entries_begin, out_off = first_out_offset;
+  uint32_t final_status = ST_OK;
+  for (;;) {
+    if (serial_file_mode && c >= max_chunks) { final_status = ST_INDEX_FULL; break; }
+    const uint64_t chunk_bit0 = src.mis_bits + chunk_byte * 8;
+    if (tid == 0) {
+      sm.err = 0;
+      parse_chunk_header(src, chunk_bit0, fp.dtype, fp.uniform_type, fp.format_major, true, sm.hdr);
+      if (sm.hdr.status == ST_OK) {
+        for (uint32_t v = 0; v < sm.hdr.n_vars; v++) {
+          const VarHdr& vh = sm.hdr.var[v];
+          if (vh.ans_size_log > 12 || vh.n_bins > (1u << 12)) sm.hdr.status = ST_UNSUPPORTED;
+          if (vh.n_bins == 0 && var_stored_n(sm.hdr.n, vh.delta_order) > 0) sm.hdr.status = ST_CORRUPTION;  // page_decompressor.rs:52-57
+        }
+      }
+    }
+    __syncthreads();
+    uint32_t st = sm.hdr.status;
+    if (st == ST_OK) {
+      for (uint32_t v = 0; v < sm.hdr.n_vars; v++)
+        build_var_tables<true>(src, sm.hdr, v, sm.node[v], nullptr, sm.bin_ob[v], sm.bin_weight[v], sm.bin_cum[v], sm.sym_of_state[v],
+                               sm.rank_counter[v], &sm.err, false);
+      __syncthreads();
+      if (sm.err) st = sm.err;
+    }
+    if (tid == 0) {
+      uint64_t end_bit = chunk_bit0;
+      if (st == ST_OK) {
+        uint32_t nb = n_batches_of(sm.hdr.n);
+        uint64_t need = uint64_t(sm.hdr.n_vars) * nb * sizeof(BatchEntry);
+        uint64_t eo = serial_file_mode ? entries_off : chunks[c].entries_offset;
+        if (eo + need > entries_cap_end) {
+          st = ST_INDEX_FULL;
+        } else {
+          st = walk_chunk_serial(src, sm.hdr, sm.node, chunk_bit0, reinterpret_cast<BatchEntry*>(index_base + eo), &end_bit);
+          if (st == ST_OK) {
+            IndexChunk ic;
+            ic.chunk_offset = chunk_byte;
+            ic.n = sm.hdr.n;
+            ic.n_vars = sm.hdr.n_vars;
+            ic.entries_offset = eo;
+            ic.out_offset = serial_file_mode ? out_off : chunks[c].out_offset;
+            chunks[c] = ic;
+            entries_off = eo + ((need + 15) & ~uint64_t(15));
+            out_off += sm.hdr.n;
+          }
+        }
+      }
+      if (statuses) statuses[c] = st;
+      sm.status = st;
+      sm.next_chunk_byte = (end_bit - src.mis_bits) >> 3;
+    }
+    __syncthreads();
+    if (!serial_file_mode) return;
+    if (sm.status != ST_OK) { final_status = sm.status; break; }
+    chunk_byte = sm.next_chunk_byte;
+    c += 1;
+    // pco::standalone::simple_decompress_into stops reading once dst is exhausted mid-chunk (simple.rs:116-139)
+    if (tid == 0) sm.status = (out_off > stop_after_total) ? ST_DST_FULL : ST_OK;
+    __syncthreads();
+    if (sm.status == ST_DST_FULL) { final_status = ST_DST_FULL; break; }
+    __syncthreads();
+  }
+  if (tid == 0 && serial_file_mode) {
+    result->n_chunks = c;
+    result->status = final_status;
+    result->next_byte = chunk_byte + (final_status == ST_TERMINATOR ? 1 : 0);
+    result->entries_end = entries_off;
+    result->n_total = out_off - first_out_offset;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Latent-type helpers
+// ---------------------------------------------------------------------------
+template <typename L> struct LT;
+template <> struct LT<uint8_t> { static constexpr int BITS = 8; };
+template <> struct LT<uint16_t> { static constexpr int BITS = 16; };
+template <> struct LT<uint32_t> { static constexpr int BITS = 32; };
+template <> struct LT<uint64_t> { static constexpr int BITS = 64; };
+
+// from_latent_ordered on bit patterns (data_types/unsigned.rs:155-161, signed.rs:46-52, float.rs:392-400)
+template <typename L>
+__device__ __forceinline__ L from_latent_ordered(L l, bool is_float, bool is_signed) {
+  constexpr L MID = L(L(1) << (LT<L>::BITS - 1));
+  if (is_float) return (l & MID) ? L(l ^ MID) : L(~l);
+  if (is_signed) return L(l + MID);
+  return l;
+}
+template <typename L>
+__device__ __forceinline__ L to_latent_ordered(L bits, bool is_float, bool is_signed) {
+  constexpr L MID = L(L(1) << (LT<L>::BITS - 1));
+  if (is_float) return (bits & MID) ? L(~bits) : L(bits ^ MID);
+  if (is_signed) return L(bits - MID);
+  return bits;
+}
+
+// int_float_from_latent (data_types/float.rs:208-226) then `* base` without FMA contraction, returned as bits
+__device__ __forceinline__ uint64_t float_mult_unadjusted(uint64_t l, uint64_t base_bits) {
+  const uint64_t MID = uint64_t(1) << 63;
+  bool neg = l < MID;
+  uint64_t abs_int = neg ? (MID - 1 - l) : (l - MID);
+  const uint64_t gpi = uint64_t(1) << 53;
+  double f = abs_int < gpi ? __ull2double_rn(abs_int) : __longlong_as_double((long long)(0x4340000000000000ull + (abs_int - gpi)));
+  if (neg) f = -f;
+  return (uint64_t)__double_as_longlong(__dmul_rn(f, __longlong_as_double((long long)base_bits)));
+}
+__device__ __forceinline__ uint32_t float_mult_unadjusted(uint32_t l, uint32_t base_bits) {
+  const uint32_t MID = 1u << 31;
+  bool neg = l < MID;
+  uint32_t abs_int = neg ? (MID - 1 - l) : (l - MID);
+  const uint32_t gpi = 1u << 24;
+  float f = abs_int < gpi ? __uint2float_rn(abs_int) : __uint_as_float(0x4b800000u + (abs_int - gpi));
+  if (neg) f = -f;
+  return __float_as_uint(__fmul_rn(f, __uint_as_float(base_bits)));
+}
+__device__ __forceinline__ uint16_t float_mult_unadjusted(uint16_t, uint16_t) { return 0; }  // f16 float_mult: not on the GPU path
+__device__ __forceinline__ uint8_t float_mult_unadjusted(uint8_t, uint8_t) { return 0; }
+
+// C(n, j) mod 2^64 for j < MAX_ORDER, by Pascal additions (exact in wrapping arithmetic)
+struct Binoms {
+  uint64_t lane8[32][MAX_ORDER];  // C(8 * lane, j)
+  uint64_t full[MAX_ORDER];       // C(256, j)
+};
+
+// read `nbits` (<= LT<L>::BITS) at absolute bit position `pos` from global words
+template <typename L>
+__device__ __forceinline__ L read_offset(const uint64_t* __restrict__ cw, uint64_t max_word, uint64_t pos, uint32_t nbits) {
+  if (LT<L>::BITS <= 32) {
+    // 32-bit words: up to 32 bits at bit offset r < 32 span two words
+    const uint32_t* c32 = reinterpret_cast<const uint32_t*>(cw);
+    uint64_t wi = pos >> 5;
+    uint64_t max32 = max_word * 2 + 1;
+    uint32_t lo = __ldg(c32 + (wi <= max32 ? wi : max32));
+    uint32_t hi = __ldg(c32 + (wi + 1 <= max32 ? wi + 1 : max32));
+    uint32_t v = __funnelshift_r(lo, hi, uint32_t(pos & 31));
+    return L(nbits >= 32 ? v : (v & ((1u << nbits) - 1)));
+  } else {
+    uint64_t wi = pos >> 6;
+    uint32_t r = uint32_t(pos & 63);
+    uint64_t lo = __ldg(cw + (wi <= max_word ? wi : max_word));
+    uint64_t hi = __ldg(cw + (wi + 1 <= max_word ? wi + 1 : max_word));
+    uint64_t v = r ? ((lo >> r) | (hi << (64 - r))) : lo;
+    return L(nbits >= 64 ? v : (v & ((uint64_t(1) << nbits) - 1)));
+  }
+}
+
+template <typename L>
+__device__ __forceinline__ L shfl_up_L(L v, int d) {
+  if (sizeof(L) == 8) {
+    uint32_t lo = __shfl_up_sync(0xffffffffu, uint32_t(uint64_t(v)), d);
+    uint32_t hi = __shfl_up_sync(0xffffffffu, uint32_t(uint64_t(v) >> 32), d);
+    return L((uint64_t(hi) << 32) | lo);
+  }
+  return L(__shfl_up_sync(0xffffffffu, uint32_t(v), d));
+}
+template <typename L>
+__device__ __forceinline__ L shfl_idx_L(L v, int src) {
+  if (sizeof(L) == 8) {
+    uint32_t lo = __shfl_sync(0xffffffffu, uint32_t(uint64_t(v)), src);
+    uint32_t hi = __shfl_sync(0xffffffffu, uint32_t(uint64_t(v) >> 32), src);
+    return L((uint64_t(hi) << 32) | lo);
+  }
+  return L(__shfl_sync(0xffffffffu, uint32_t(v), src));
+}
+
+// One zero-seeded exclusive scan level over the warp's 256 values (8 consecutive per lane), wrapping.
+// Returns the batch total through `total` (valid in all lanes).
+template <typename L>
+__device__ __forceinline__ void warp_excl_scan8(L (&x)[8], L& total, int lane) {
+  L run = 0;
+#pragma unroll
+  for (int e = 0; e < 8; e++) {
+    L t = x[e];
+    x[e] = run;
+    run = L(run + t);
+  }
+  L inc = run;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    L o = shfl_up_L<L>(inc, d);
+    if (lane >= d) inc = L(inc + o);
+  }
+  L excl = L(inc - run);
+#pragma unroll
+  for (int e = 0; e < 8; e++) x[e] = L(x[e] + excl);
+  total = shfl_idx_L<L>(inc, 31);
+}
+
+// ---------------------------------------------------------------------------
+// decode_kernel: one CTA per chunk.
+// ---------------------------------------------------------------------------
+template <typename L>
+__global__ void __launch_bounds__(DEC_THREADS, 2)
+decode_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, uint32_t* __restrict__ statuses, const uint8_t* __restrict__ index_base,
+              L* __restrict__ out, uint64_t out_len, const Binoms* __restrict__ binoms) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  DecodeSmem& sm = *reinterpret_cast<DecodeSmem*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const IndexChunk task = chunks[blockIdx.x];
+  const BitSrc src = make_bitsrc(fp.src, fp.src_len);
+  const uint64_t max_word = src.n_bits == 0 ? 0 : (src.n_bits - 1) >> 6;
+  const uint64_t chunk_bit0 = src.mis_bits + task.chunk_offset * 8;
+  const bool is_float = nt_is_float(fp.dtype), is_signed = nt_is_signed(fp.dtype);
+
+  if (tid == 0) {
+    sm.err = 0;
+    parse_chunk_header(src, chunk_bit0, fp.dtype, fp.uniform_type, fp.format_major, true, sm.hdr);
+    if (sm.hdr.status == ST_OK) {
+      for (uint32_t v = 0; v < sm.hdr.n_vars; v++) {
+        const VarHdr& vh = sm.hdr.var[v];
+        if (vh.ans_size_log > SMALL_MAX_SIZE_LOG || vh.n_bins > SMALL_MAX_BINS) sm.hdr.status = ST_UNSUPPORTED;
+        if (v > 0 && vh.delta_order > 0) sm.hdr.status = ST_UNSUPPORTED;  // secondary_uses_delta: never written by pco
+        if (vh.n_bins == 0 && var_stored_n(sm.hdr.n, vh.delta_order) > 0) sm.hdr.status = ST_CORRUPTION;
+      }
+      if (sm.hdr.mode == MODE_FLOAT_MULT && LT<L>::BITS < 32) sm.hdr.status = ST_UNSUPPORTED;
+      if (task.n != 0 && task.n != sm.hdr.n) sm.hdr.status = ST_CORRUPTION;
+    }
+  }
+  for (int i = tid; i < CARRY_RING; i += DEC_THREADS) sm.carry_seq[i] = 0;
+  __syncthreads();
+  if (sm.hdr.status != ST_OK) {
+    if (tid == 0) statuses[blockIdx.x] = sm.hdr.status;
+    return;
+  }
+  const uint32_t n_vars = sm.hdr.n_vars;
+  for (uint32_t v = 0; v < n_vars; v++)
+    build_var_tables<false>(src, sm.hdr, v, sm.node[v], sm.bin_lower[v], sm.bin_ob[v], sm.bin_weight[v], sm.bin_cum[v], sm.sym_of_state[v],
+                            sm.rank_counter[v], &sm.err, /*add_mid_to_lower=*/sm.hdr.var[v].delta_order > 0);
+  __syncthreads();
+  if (sm.err) {
+    if (tid == 0) statuses[blockIdx.x] = sm.err;
+    return;
+  }
+
+  const uint32_t n = sm.hdr.n;
+  // pco::standalone::simple_decompress_into semantics: emit only what fits in the destination
+  const uint32_t n_out = task.out_offset >= out_len ? 0u : uint32_t(min(uint64_t(n), out_len - task.out_offset));
+  const uint32_t nb_total = n_batches_of(n);
+  const uint32_t nb_out = n_batches_of(n_out);
+  const uint32_t order = sm.hdr.var[0].delta_order;
+  const uint32_t tile_b = DEC_THREADS / n_vars;  // batches per tile
+  const bool need_index = (sm.hdr.var[0].n_bins > 1) || (n_vars > 1 && sm.hdr.var[1].n_bins > 1);
+  const BatchEntry* entries = (task.entries_offset != 0 && index_base)
+                                  ? reinterpret_cast<const BatchEntry*>(index_base + task.entries_offset) : nullptr;
+  if (need_index && !entries) {
+    if (tid == 0) statuses[blockIdx.x] = ST_INVALID_ARGUMENT;
+    return;
+  }
+  // closed-form section sizes when every var is trivial (n_bins <= 1): bits per full batch
+  const uint32_t ob0 = sm.hdr.var[0].n_bins >= 1 ? sm.bin_ob[0][0] : 0;
+  const uint32_t ob1 = (n_vars > 1 && sm.hdr.var[1].n_bins >= 1) ? sm.bin_ob[1][0] : 0;
+  const uint32_t stored0 = var_stored_n(n, sm.hdr.var[0].delta_order);
+  const uint32_t stored1 = n_vars > 1 ? var_stored_n(n, sm.hdr.var[1].delta_order) : 0;
+
+  if (tid == 0 && order > 0) {
+    for (uint32_t k = 0; k < order; k++) sm.carry[0][k] = sm.hdr.moments[0][k];
+    __threadfence_block();
+    sm.carry_seq[0] = 1;  // seq = batch index + 1
+  }
+  __syncthreads();
+
+  uint32_t end_err = 0;
+  for (uint32_t tile_start = 0; tile_start < nb_out; tile_start += tile_b) {
+    const uint32_t tile_n = min(tile_b, nb_out - tile_start);
+    // ---------------- phase A: one thread per (var, batch): tANS symbols -> shared memory ----------------
+    {
+      const uint32_t v = tid / tile_b, bl = tid % tile_b;
+      if (v < n_vars && bl < tile_n) {
+        const uint32_t b = tile_start + bl;
+        const VarHdr& vh = sm.hdr.var[v];
+        const uint32_t cnt = batch_count(v == 0 ? stored0 : stored1, b);
+        uint64_t bit;
+        if (need_index) {
+          const BatchEntry e = entries[size_t(v) * nb_total + b];
+          bit = chunk_bit0 + e.bit_pos;
+          if (vh.n_bins > 1 && cnt > 0) {
+            WalkState ws;
+            for (int j = 0; j < 4; j++) ws.st[j] = min(uint32_t(e.st[j]), (1u << vh.ans_size_log) - 1);
+            uint32_t dummy;
+            bit = ans_walk_batch<false>(src.words, max_word, min(bit, src.n_bits), ws, sm.node[v], int(cnt), &sm.sym[tid * SYM_ROW_WORDS], dummy);
+          }
+        } else {
+          // all vars trivial: batch b' < b contributes count0*ob0 + count1*ob1 bits
+          uint64_t before = 0;
+          uint32_t full = b;  // full batches before b hold 256 each unless truncated by stored_n
+          uint64_t c0 = min(uint64_t(full) * BATCH_N, uint64_t(stored0));
+          uint64_t c1 = min(uint64_t(full) * BATCH_N, uint64_t(stored1));
+          before = c0 * ob0 + c1 * ob1;
+          if (v == 1) before += uint64_t(batch_count(stored0, b)) * ob0;
+          bit = sm.hdr.body_bit + before;
+        }
+        sm.off_start[tid] = uint32_t(min(bit, src.n_bits) - chunk_bit0);
+      }
+    }
+    __syncthreads();
+    // ---------------- phase B: one warp per batch ----------------
+    for (uint32_t bl = warp; bl < tile_n; bl += DEC_WARPS) {
+      const uint32_t b = tile_start + bl;
+      const uint32_t out_cnt = min(uint32_t(BATCH_N), n_out - b * BATCH_N);  // numbers this batch emits
+      L lat[MAX_VARS][8];
+      uint64_t last_end = 0;
+#pragma unroll
+      for (uint32_t v = 0; v < MAX_VARS; v++) {
+        if (v >= n_vars) break;
+        const VarHdr& vh = sm.hdr.var[v];
+        const uint32_t cnt = batch_count(v == 0 ? stored0 : stored1, b);
+        const uint32_t row = (v * tile_b + bl);
+        uint32_t sy[8];
+        uint32_t ob[8];
+        uint32_t lane_bits = 0;
+        if (vh.n_bins > 1) {
+          const uint32_t* rowp = &sm.sym[row * SYM_ROW_WORDS + lane * 2];
+          uint32_t p0 = rowp[0], p1 = rowp[1];
+#pragma unroll
+          for (int e = 0; e < 8; e++) sy[e] = ((e < 4 ? p0 : p1) >> (8 * (e & 3))) & 0xffu;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; e++) sy[e] = 0;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+          bool valid = uint32_t(lane * 8 + e) < cnt;
+          if (!valid) sy[e] = 0;
+          ob[e] = valid ? uint32_t(sm.bin_ob[v][sy[e]]) : 0;
+          lane_bits += ob[e];
+        }
+        // exclusive scan of lane_bits across the warp
+        uint32_t inc = lane_bits;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+          if (lane >= d) inc += o;
+        }
+        uint64_t pos = chunk_bit0 + sm.off_start[row] + (inc - lane_bits);
+        const uint32_t total_bits = __shfl_sync(0xffffffffu, inc, 31);
+        last_end = chunk_bit0 + sm.off_start[row] + total_bits;
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+          bool valid = uint32_t(lane * 8 + e) < cnt;
+          L lower = L(sm.bin_lower[v][sy[e]]);
+          L off = 0;
+          if (ob[e] != 0) off = read_offset<L>(src.words, max_word, min(pos, src.n_bits), ob[e]);
+          pos += ob[e];
+          // positions past the stored latents of a delta'd var hold deltas that cannot influence
+          // any emitted number (page_latent_decompressor.rs:244-248); use the toggled zero
+          lat[v][e] = valid ? L(lower + off) : L(0);
+        }
+      }
+      // ---- un-delta of the primary (delta/consecutive.rs:35-50)
+      if (order > 0) {
+        L c[MAX_ORDER];
+        for (uint32_t lvl = 0; lvl < order; lvl++) {
+          // level j = order-1-lvl: x^(j) = exclusive scan of x^(j+1); c_j = sum of x^(j+1)
+          L total;
+          warp_excl_scan8<L>(lat[0], total, lane);
+          c[order - 1 - lvl] = total;
+        }
+        // wait for the moments at the start of this batch, publish those of the next
+        const uint32_t slot = b % CARRY_RING, nslot = (b + 1) % CARRY_RING;
+        if (lane == 0) {
+          while (sm.carry_seq[slot] != b + 1) { __nanosleep(20); }
+        }
+        __syncwarp();
+        __threadfence_block();
+        L m[MAX_ORDER];
+        for (uint32_t k = 0; k < order; k++) m[k] = L(sm.carry[slot][k]);
+        __syncwarp();
+        if (lane == 0) {
+          // m' = A^256 m + c, (A^n)_{j,j+t} = C(n, t)
+          for (uint32_t j = 0; j < order; j++) {
+            L acc = c[j];
+            for (uint32_t t = 0; j + t < order; t++) acc = L(acc + L(L(binoms->full[t]) * m[j + t]));
+            sm.carry[nslot][j] = uint64_t(acc);
+          }
+          __threadfence_block();
+          sm.carry_seq[nslot] = b + 2;
+        }
+        // fix-up: x_i += sum_j C(i, j) m_j, evaluated by running the recurrence from s = A^(8*lane) m
+        L s[MAX_ORDER];
+        for (uint32_t j = 0; j < order; j++) {
+          L acc = 0;
+          for (uint32_t t = 0; j + t < order; t++) acc = L(acc + L(L(binoms->lane8[lane][t]) * m[j + t]));
+          s[j] = acc;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+          lat[0][e] = L(lat[0][e] + s[0]);
+          for (uint32_t j = 0; j + 1 < order; j++) s[j] = L(s[j] + s[j + 1]);
+        }
+      }
+      // ---- join (mode/*.rs) and store
+      L res[8];
+      const uint32_t mode = sm.hdr.mode;
+#pragma unroll
+      for (int e = 0; e < 8; e++) {
+        L p = lat[0][e];
+        L r;
+        if (mode == MODE_CLASSIC) {
+          r = from_latent_ordered<L>(p, is_float, is_signed);
+        } else if (mode == MODE_INT_MULT) {
+          r = from_latent_ordered<L>(L(L(p * L(sm.hdr.mode_base)) + lat[1][e]), is_float, is_signed);
+        } else if (mode == MODE_FLOAT_MULT) {
+          constexpr L MID = L(L(1) << (LT<L>::BITS - 1));
+          L base_bits = from_latent_ordered<L>(L(sm.hdr.mode_base), true, false);
+          L un = float_mult_unadjusted(p, base_bits);
+          L u = to_latent_ordered<L>(un, true, false);
+          r = from_latent_ordered<L>(L(L(u + lat[1][e]) + MID), true, false);
+        } else {  // MODE_FLOAT_QUANT
+          const uint32_t k = sm.hdr.mode_k;
+          constexpr L MID = L(L(1) << (LT<L>::BITS - 1));
+          L sign_cutoff = L(MID >> k);
+          L kmax = L(L(L(1) << k) - 1);
+          L lowest = p >= sign_cutoff ? lat[1][e] : L(kmax - lat[1][e]);
+          r = from_latent_ordered<L>(L(L(p << k) + lowest), true, false);
+        }
+        res[e] = r;
+      }
+      L* dst = out + task.out_offset + size_t(b) * BATCH_N + lane * 8;
+      if (out_cnt == BATCH_N) {
+        if (sizeof(L) == 8) {
+          uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            uint64_t a = uint64_t(res[2 * q]), bb = uint64_t(res[2 * q + 1]);
+            d4[q] = make_uint4(uint32_t(a), uint32_t(a >> 32), uint32_t(bb), uint32_t(bb >> 32));
+          }
+        } else if (sizeof(L) == 4) {
+          uint4* d4 = reinterpret_cast<uint4*>(dst);
+          d4[0] = make_uint4(uint32_t(res[0]), uint32_t(res[1]), uint32_t(res[2]), uint32_t(res[3]));
+          d4[1] = make_uint4(uint32_t(res[4]), uint32_t(res[5]), uint32_t(res[6]), uint32_t(res[7]));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; e++) dst[e] = res[e];
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; e++)
+          if (uint32_t(lane * 8 + e) < out_cnt) dst[e] = res[e];
+      }
+      // ---- end-of-page checks by the warp that owns the last batch (page_decompressor.rs:184-188)
+      if (b == nb_total - 1 && lane == 0) {
+        uint64_t bit = last_end;
+        if (bit > src.n_bits) end_err = ST_INSUFFICIENT_DATA;
+        else {
+          uint32_t pad = uint32_t((8 - (bit & 7)) & 7);
+          if (pad && read_bits_safe(src, bit, pad) != 0) end_err = ST_CORRUPTION;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (end_err) atomicMax(&sm.err, end_err);
+  __syncthreads();
+  if (tid == 0) statuses[blockIdx.x] = sm.err;
+}
+
+}  // namespace pcob200

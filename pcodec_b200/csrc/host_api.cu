@@ -1,0 +1,350 @@
+// libcpcodec.so — C-ABI entry points (include/cpcodec.h, include/pco_b200.h) over the sm_100a kernels.
+// There is no CPU implementation of the hot path in this library: without a CUDA device every
+// compute entry point fails with PCO_B200_CUDA.
+#include <algorithm>
+
+#include "decode_kernels.cuh"
+#include "host_common.hpp"
+
+namespace pcob200 {
+
+struct Context {
+  std::mutex mu;
+  bool initialized = false;
+  bool device_ok = false;
+  std::string device_err;
+  DevBuf src, out, index, statuses, misc;
+  Binoms* d_binoms = nullptr;
+  int sm_count = 0;
+};
+
+static Context& ctx() {
+  static Context c;
+  return c;
+}
+
+static PcoB200Error ensure_device(Context& c) {
+  if (!c.initialized) {
+    c.initialized = true;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+      c.device_err = e != cudaSuccess ? cudaGetErrorString(e) : "no CUDA device";
+      cudaGetLastError();
+    } else {
+      cudaDeviceProp prop;
+      int dev = 0;
+      cudaGetDevice(&dev);
+      e = cudaGetDeviceProperties(&prop, dev);
+      if (e != cudaSuccess) c.device_err = cudaGetErrorString(e);
+      else if (prop.major < 10) c.device_err = std::string("device ") + prop.name + " is not sm_100";
+      else {
+        c.sm_count = prop.multiProcessorCount;
+        // binomials mod 2^64 by Pascal additions
+        static Binoms hb;
+        std::vector<std::vector<uint64_t>> C(257, std::vector<uint64_t>(MAX_ORDER, 0));
+        for (int nn = 0; nn <= 256; nn++) {
+          C[nn][0] = 1;
+          for (int j = 1; j < MAX_ORDER; j++) C[nn][j] = nn == 0 ? 0 : C[nn - 1][j - 1] + C[nn - 1][j];
+        }
+        for (int l = 0; l < 32; l++)
+          for (int j = 0; j < MAX_ORDER; j++) hb.lane8[l][j] = C[8 * l][j];
+        for (int j = 0; j < MAX_ORDER; j++) hb.full[j] = C[256][j];
+        e = cudaMalloc(&c.d_binoms, sizeof(Binoms));
+        if (e == cudaSuccess) e = cudaMemcpy(c.d_binoms, &hb, sizeof(Binoms), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WalkSmem));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(decode_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecodeSmem));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(decode_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecodeSmem));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(decode_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecodeSmem));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(decode_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecodeSmem));
+        if (e != cudaSuccess) c.device_err = cudaGetErrorString(e);
+        else c.device_ok = true;
+      }
+    }
+  }
+  if (!c.device_ok)
+    return fail(PCO_B200_CUDA, "CUDA device unavailable (" + c.device_err + "); libcpcodec has no CPU fallback");
+  return PCO_B200_OK;
+}
+
+template <typename Fn>
+static auto dispatch_latent(uint32_t dtype, Fn&& fn) {
+  switch (nt_bits(dtype)) {
+    case 8: return fn(uint8_t(0));
+    case 16: return fn(uint16_t(0));
+    case 32: return fn(uint32_t(0));
+    default: return fn(uint64_t(0));
+  }
+}
+
+struct DecodeOutcome {
+  uint64_t n_total = 0;   // numbers in the chunks seen
+  bool terminated = false;
+};
+
+// Launch the fused decode over `n_chunks` IndexChunk records that live on the device.
+static PcoB200Error launch_decode(Context& c, const FileParams& fp, const uint8_t* d_index, uint64_t chunks_offset, uint32_t n_chunks,
+                                  void* d_out, uint64_t out_len, cudaStream_t stream) {
+  if (n_chunks == 0) return PCO_B200_OK;
+  PCOB_CUDA_TRY(c.statuses.reserve(size_t(n_chunks + 1) * sizeof(uint32_t)));
+  uint32_t* d_st = c.statuses.as<uint32_t>();
+  PCOB_CUDA_TRY(cudaMemsetAsync(d_st, 0xff, size_t(n_chunks) * sizeof(uint32_t), stream));
+  const IndexChunk* d_chunks = reinterpret_cast<const IndexChunk*>(d_index + chunks_offset);
+  dispatch_latent(fp.dtype, [&](auto tag) {
+    using L = decltype(tag);
+    decode_kernel<L><<<n_chunks, DEC_THREADS, sizeof(DecodeSmem), stream>>>(fp, d_chunks, d_st, d_index, static_cast<L*>(d_out), out_len,
+                                                                             c.d_binoms);
+    return 0;
+  });
+  PCOB_CUDA_TRY(cudaGetLastError());
+  std::vector<uint32_t> st(n_chunks);
+  PCOB_CUDA_TRY(cudaMemcpyAsync(st.data(), d_st, size_t(n_chunks) * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+  PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
+  for (uint32_t i = 0; i < n_chunks; i++)
+    if (st[i] != ST_OK) return status_to_error(st[i], ("chunk " + std::to_string(i)).c_str());
+  return PCO_B200_OK;
+}
+
+// Core of every decompress entry point.
+//   stop_when_full: pco::standalone::simple_decompress_into semantics (stop reading once dst is full);
+//                   false = simple_decompress semantics (walk the whole file; the caller checks capacity).
+static PcoB200Error decompress_core(const void* compressed, size_t compressed_len, uint32_t dtype, void* dst, size_t dst_len,
+                                    const void* index, size_t index_len, uint32_t flags, void* cuda_stream, bool stop_when_full,
+                                    DecodeOutcome* outcome) {
+  if (!nt_valid(dtype)) return fail(PCO_B200_INVALID_TYPE, "unknown number type byte: " + std::to_string(dtype));
+  Context& c = ctx();
+  std::lock_guard<std::mutex> lock(c.mu);
+  if (PcoB200Error e = ensure_device(c)) return e;
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  const bool src_dev = flags & PCO_B200_SRC_ON_DEVICE, dst_dev = flags & PCO_B200_DST_ON_DEVICE;
+  const size_t elem = nt_bits(dtype) / 8;
+
+  // 1. standalone header (host parse of the first bytes)
+  uint8_t head[32] = {0};
+  size_t avail = std::min<size_t>(compressed_len, sizeof(head));
+  if (avail) {
+    if (src_dev) PCOB_CUDA_TRY(cudaMemcpyAsync(head, compressed, avail, cudaMemcpyDeviceToHost, stream));
+    else std::memcpy(head, compressed, avail);
+    if (src_dev) PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
+  }
+  StandaloneHeader hdr;
+  if (PcoB200Error e = parse_standalone_header(head, avail, compressed_len, &hdr)) return e;
+
+  // 2. the file in HBM
+  const uint8_t* d_src;
+  if (src_dev) d_src = static_cast<const uint8_t*>(compressed);
+  else {
+    PCOB_CUDA_TRY(c.src.reserve(compressed_len + 16));
+    PCOB_CUDA_TRY(cudaMemcpyAsync(c.src.p, compressed, compressed_len, cudaMemcpyHostToDevice, stream));
+    d_src = c.src.as<uint8_t>();
+  }
+  FileParams fp;
+  fp.src = d_src;
+  fp.src_len = compressed_len;
+  fp.dtype = dtype;
+  fp.uniform_type = hdr.uniform_type;
+  fp.format_major = hdr.format_major;
+
+  // 3a. caller-supplied side index
+  if (index != nullptr && index_len >= sizeof(IndexHeader)) {
+    IndexHeader ih;
+    std::memcpy(&ih, index, sizeof(ih));
+    if (ih.magic != INDEX_MAGIC || ih.version != 1 || ih.file_len != compressed_len || ih.chunks_offset + ih.n_chunks * sizeof(IndexChunk) > index_len)
+      return fail(PCO_B200_INVALID_ARGUMENT, "side index does not belong to this file");
+    PCOB_CUDA_TRY(c.index.reserve(index_len));
+    PCOB_CUDA_TRY(cudaMemcpyAsync(c.index.p, index, index_len, cudaMemcpyHostToDevice, stream));
+    uint64_t n_emit = std::min<uint64_t>(ih.n_total, dst_len);
+    void* d_out = dst;
+    if (!dst_dev) {
+      PCOB_CUDA_TRY(c.out.reserve(n_emit * elem + 64));
+      d_out = c.out.p;
+    }
+    if (ih.n_chunks > 0xffffffffull) return fail(PCO_B200_INVALID_ARGUMENT, "too many chunks");
+    if (PcoB200Error e = launch_decode(c, fp, c.index.as<uint8_t>(), ih.chunks_offset, uint32_t(ih.n_chunks), d_out, dst_len, stream)) return e;
+    if (!dst_dev && n_emit) {
+      PCOB_CUDA_TRY(cudaMemcpyAsync(dst, d_out, n_emit * elem, cudaMemcpyDeviceToHost, stream));
+      PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
+    }
+    outcome->n_total = ih.n_total;
+    outcome->terminated = ih.end_byte != 0;
+    return PCO_B200_OK;
+  }
+
+  // 3b. no index: walk the file on the device in rounds, decoding each round's chunks.
+  // Chunk boundaries are not in the stream, so this is one serial tANS walk (cold path).
+  const uint32_t max_chunks = uint32_t(std::min<uint64_t>(uint64_t(compressed_len) / 5 + 2, 1u << 16));
+  uint64_t next_byte = hdr.first_chunk_byte;
+  uint64_t out_off = 0;
+  PCOB_CUDA_TRY(c.misc.reserve(sizeof(WalkResult)));
+  WalkResult* d_res = c.misc.as<WalkResult>();
+  void* d_out = dst;
+  for (;;) {
+    // scratch index: header | IndexChunk[max_chunks] | entries for the batches dst can still take (+2 per chunk) x 2 vars
+    const uint64_t chunks_offset = sizeof(IndexHeader);
+    const uint64_t entries_begin = chunks_offset + uint64_t(max_chunks) * sizeof(IndexChunk);
+    uint64_t want_batches = (dst_len > out_off ? (dst_len - out_off) / BATCH_N : 0) + 2ull * max_chunks + 2;
+    want_batches = std::min<uint64_t>(want_batches, uint64_t(1) << 23);
+    const uint64_t entries_bytes = want_batches * MAX_VARS * sizeof(BatchEntry) + 16ull * max_chunks + 64;
+    PCOB_CUDA_TRY(c.index.reserve(entries_begin + entries_bytes));
+    uint8_t* d_index = c.index.as<uint8_t>();
+    walk_kernel<<<1, 128, sizeof(WalkSmem), stream>>>(fp, d_index, chunks_offset, max_chunks, entries_begin, entries_begin + entries_bytes,
+                                                      next_byte, out_off, uint64_t(dst_len), nullptr, d_res, 1);
+    PCOB_CUDA_TRY(cudaGetLastError());
+    WalkResult res;
+    PCOB_CUDA_TRY(cudaMemcpyAsync(&res, d_res, sizeof(res), cudaMemcpyDeviceToHost, stream));
+    PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
+    const bool soft = res.status == ST_TERMINATOR || res.status == ST_INDEX_FULL || res.status == ST_DST_FULL;
+    // decode what was indexed this round (the reference also emits the chunks before a failing one)
+    if (res.n_chunks > 0) {
+      uint64_t round_emit_end = std::min<uint64_t>(out_off + res.n_total, dst_len);
+      if (!dst_dev) {
+        PCOB_CUDA_TRY(c.out.grow_preserve(round_emit_end * elem + 64, std::min<uint64_t>(out_off, dst_len) * elem, stream));
+        d_out = c.out.p;
+      }
+      if (PcoB200Error e = launch_decode(c, fp, d_index, chunks_offset, res.n_chunks, d_out, dst_len, stream)) return e;
+    }
+    out_off += res.n_total;
+    next_byte = res.next_byte;
+    if (!soft) return status_to_error(res.status, ("chunk " + std::to_string(res.n_chunks) + " of this walk round").c_str());
+    if (res.status == ST_TERMINATOR) { outcome->terminated = true; break; }
+    if (res.status == ST_DST_FULL) break;
+    if (res.n_chunks == 0) return fail(PCO_B200_UNSUPPORTED, "a single chunk exceeds the device index scratch");
+  }
+  (void)stop_when_full;
+  outcome->n_total = out_off;
+  uint64_t n_emit = std::min<uint64_t>(out_off, dst_len);
+  if (!dst_dev && n_emit) {
+    PCOB_CUDA_TRY(cudaMemcpyAsync(dst, d_out, n_emit * elem, cudaMemcpyDeviceToHost, stream));
+    PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
+  }
+  return PCO_B200_OK;
+}
+
+}  // namespace pcob200
+
+using namespace pcob200;
+
+extern "C" {
+
+const char* pco_b200_last_error_message(void) { return last_error_ref().c_str(); }
+
+int pco_b200_device_available(void) {
+  Context& c = ctx();
+  std::lock_guard<std::mutex> lock(c.mu);
+  return ensure_device(c) == PCO_B200_OK ? 1 : 0;
+}
+
+// pco_c/src/lib.rs:127-139
+size_t pco_standalone_guarantee_file_size(size_t n, unsigned char dtype) {
+  if (!nt_valid(dtype)) return 0;
+  // PagingSpec::default() = EqualPagesUpTo(2^18) (pco/src/chunk_config.rs:127-132, :134-183)
+  const size_t max_page_n = size_t(1) << 18;
+  size_t res = standalone_header_size();
+  if (n > 0) {
+    size_t n_pages = (n + max_page_n - 1) / max_page_n;
+    size_t low = n / n_pages, r = n % n_pages;
+    res += r * standalone_chunk_size_guarantee(nt_bits(dtype), low + 1) + (n_pages - r) * standalone_chunk_size_guarantee(nt_bits(dtype), low);
+  }
+  return res + 1;
+}
+
+// pco_c/src/lib.rs:98-120,178-195: full simple_decompress, then fail if it does not fit.
+enum PcoError pco_standalone_simple_decompress_into(const void* compressed, size_t compressed_len, unsigned char dtype, void* dst,
+                                                    size_t dst_cap, size_t* n_written) {
+  if (!nt_valid(dtype)) return PcoInvalidType;
+  DecodeOutcome oc;
+  PcoB200Error e = decompress_core(compressed, compressed_len, dtype, dst, dst_cap, nullptr, 0, 0, nullptr, /*stop_when_full=*/false, &oc);
+  if (e != PCO_B200_OK) return PcoDecompressionError;
+  if (oc.n_total > dst_cap) {
+    fail(PCO_B200_IO, "decompressed count exceeds dst_cap");
+    return PcoDecompressionError;
+  }
+  if (n_written) *n_written = size_t(oc.n_total);
+  return PcoSuccess;
+}
+
+PcoB200Error pco_b200_decompress_ex(const void* compressed, size_t compressed_len, unsigned char dtype, void* dst, size_t dst_len,
+                                    PcoB200Progress* progress, const void* index, size_t index_len, uint32_t flags, void* cuda_stream) {
+  DecodeOutcome oc;
+  PcoB200Error e = decompress_core(compressed, compressed_len, dtype, dst, dst_len, index, index_len, flags, cuda_stream, true, &oc);
+  if (e != PCO_B200_OK) return e;
+  if (progress) {
+    progress->n_processed = size_t(std::min<uint64_t>(oc.n_total, dst_len));
+    progress->finished = (oc.terminated && oc.n_total <= dst_len) ? 1 : 0;
+  }
+  return PCO_B200_OK;
+}
+
+PcoB200Error pco_b200_simple_decompress_into(const void* compressed, size_t compressed_len, unsigned char dtype, void* dst, size_t dst_len,
+                                             PcoB200Progress* progress) {
+  return pco_b200_decompress_ex(compressed, compressed_len, dtype, dst, dst_len, progress, nullptr, 0, 0, nullptr);
+}
+
+size_t pco_b200_index_size_bound(size_t n, size_t n_chunks_hint) {
+  size_t chunks = n_chunks_hint + 2;
+  size_t batches = n / BATCH_N + 2 * chunks;
+  return sizeof(IndexHeader) + chunks * sizeof(IndexChunk) + batches * MAX_VARS * sizeof(BatchEntry) + 16 * chunks + 64;
+}
+
+PcoB200Error pco_b200_build_index(const void* compressed, size_t compressed_len, unsigned char dtype, void* index, size_t index_cap,
+                                  size_t* index_len, uint32_t flags, void* cuda_stream) {
+  if (!nt_valid(dtype)) return fail(PCO_B200_INVALID_TYPE, "unknown number type byte");
+  Context& c = ctx();
+  std::lock_guard<std::mutex> lock(c.mu);
+  if (PcoB200Error e = ensure_device(c)) return e;
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  const bool src_dev = flags & PCO_B200_SRC_ON_DEVICE;
+  uint8_t head[32] = {0};
+  size_t avail = std::min<size_t>(compressed_len, sizeof(head));
+  if (avail) {
+    if (src_dev) { PCOB_CUDA_TRY(cudaMemcpyAsync(head, compressed, avail, cudaMemcpyDeviceToHost, stream)); PCOB_CUDA_TRY(cudaStreamSynchronize(stream)); }
+    else std::memcpy(head, compressed, avail);
+  }
+  StandaloneHeader hdr;
+  if (PcoB200Error e = parse_standalone_header(head, avail, compressed_len, &hdr)) return e;
+  const uint8_t* d_src;
+  if (src_dev) d_src = static_cast<const uint8_t*>(compressed);
+  else {
+    PCOB_CUDA_TRY(c.src.reserve(compressed_len + 16));
+    PCOB_CUDA_TRY(cudaMemcpyAsync(c.src.p, compressed, compressed_len, cudaMemcpyHostToDevice, stream));
+    d_src = c.src.as<uint8_t>();
+  }
+  FileParams fp{d_src, compressed_len, dtype, hdr.uniform_type, hdr.format_major};
+  if (index_cap < sizeof(IndexHeader) + sizeof(IndexChunk) + 64) return fail(PCO_B200_IO, "index buffer too small");
+  // Split the caller's capacity: chunk records sized from a lower bound on chunk bytes, the rest for entries.
+  uint64_t max_chunks = std::min<uint64_t>(uint64_t(compressed_len) / 5 + 2, (index_cap - sizeof(IndexHeader)) / (4 * sizeof(IndexChunk)));
+  max_chunks = std::max<uint64_t>(1, std::min<uint64_t>(max_chunks, 0x7fffffffull));
+  const uint64_t chunks_offset = sizeof(IndexHeader);
+  uint64_t entries_begin = (chunks_offset + max_chunks * sizeof(IndexChunk) + 15) & ~uint64_t(15);
+  if (entries_begin > index_cap) return fail(PCO_B200_IO, "index buffer too small");
+  PCOB_CUDA_TRY(c.index.reserve(index_cap));
+  PCOB_CUDA_TRY(c.misc.reserve(sizeof(WalkResult)));
+  uint8_t* d_index = c.index.as<uint8_t>();
+  walk_kernel<<<1, 128, sizeof(WalkSmem), stream>>>(fp, d_index, chunks_offset, uint32_t(max_chunks), entries_begin, index_cap, hdr.first_chunk_byte,
+                                                    0, ~uint64_t(0), nullptr, c.misc.as<WalkResult>(), 1);
+  PCOB_CUDA_TRY(cudaGetLastError());
+  WalkResult res;
+  PCOB_CUDA_TRY(cudaMemcpyAsync(&res, c.misc.p, sizeof(res), cudaMemcpyDeviceToHost, stream));
+  PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
+  if (res.status == ST_INDEX_FULL) return fail(PCO_B200_IO, "index buffer too small");
+  if (res.status != ST_TERMINATOR) return status_to_error(res.status, ("chunk " + std::to_string(res.n_chunks)).c_str());
+  IndexHeader ih;
+  std::memset(&ih, 0, sizeof(ih));
+  ih.magic = INDEX_MAGIC;
+  ih.version = 1;
+  ih.n_chunks = res.n_chunks;
+  ih.n_total = res.n_total;
+  ih.file_len = compressed_len;
+  ih.chunks_offset = chunks_offset;
+  ih.end_byte = res.next_byte;
+  size_t used = std::max<uint64_t>(res.entries_end, entries_begin);
+  std::memcpy(index, &ih, sizeof(ih));
+  if (used > sizeof(ih)) {
+    PCOB_CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t*>(index) + sizeof(ih), d_index + sizeof(ih), used - sizeof(ih), cudaMemcpyDeviceToHost, stream));
+    PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
+  }
+  if (index_len) *index_len = used;
+  return PCO_B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,162 @@
+// Host-side support for libcpcodec.so: error state, device scratch cache, standalone header
+// parse/write and size guarantees.  Independent of oracle/ (the product never links it).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/pco_b200.h"
+#include "codec_common.cuh"
+
+namespace pcob200 {
+
+// ---- thread-local error message (pco::errors::PcoError::message) -----------
+inline std::string& last_error_ref() {
+  static thread_local std::string s;
+  return s;
+}
+inline PcoB200Error fail(PcoB200Error e, const std::string& msg) {
+  last_error_ref() = msg;
+  return e;
+}
+inline PcoB200Error cuda_fail(cudaError_t ce, const char* what) {
+  return fail(PCO_B200_CUDA, std::string(what) + ": " + cudaGetErrorString(ce) +
+                                 " (libcpcodec has no CPU fallback: a CUDA device is required)");
+}
+#define PCOB_CUDA_TRY(expr)                                   \
+  do {                                                        \
+    cudaError_t _ce = (expr);                                 \
+    if (_ce != cudaSuccess) return cuda_fail(_ce, #expr);     \
+  } while (0)
+
+inline PcoB200Error status_to_error(uint32_t st, const char* where) {
+  switch (st) {
+    case ST_OK: return PCO_B200_OK;
+    case ST_CORRUPTION: return fail(PCO_B200_CORRUPTION, std::string("corrupt data in ") + where);
+    case ST_INSUFFICIENT_DATA: return fail(PCO_B200_INSUFFICIENT_DATA, std::string("insufficient data in ") + where);
+    case ST_INVALID_ARGUMENT: return fail(PCO_B200_INVALID_ARGUMENT, std::string("invalid argument in ") + where);
+    case ST_UNSUPPORTED:
+      return fail(PCO_B200_UNSUPPORTED, std::string("valid pco outside the GPU hot path (dict/lookback/conv1, >256 bins or "
+                                                    "ans_size_log > 10) in ") + where);
+    default: return fail(PCO_B200_CORRUPTION, std::string("unexpected device status in ") + where);
+  }
+}
+
+// ---- grow-only device buffer -----------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = n + (n >> 3) + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { e = cudaMalloc(&p, n); want = n; }
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  // grow while keeping the first `keep` bytes (device-to-device copy)
+  cudaError_t grow_preserve(size_t n, size_t keep, cudaStream_t stream) {
+    if (n <= cap) return cudaSuccess;
+    void* np = nullptr;
+    size_t want = n + (n >> 2) + 256;
+    cudaError_t e = cudaMalloc(&np, want);
+    if (e != cudaSuccess) { e = cudaMalloc(&np, n); want = n; }
+    if (e != cudaSuccess) return e;
+    if (p && keep) {
+      e = cudaMemcpyAsync(np, p, keep, cudaMemcpyDeviceToDevice, stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    }
+    if (p) cudaFree(p);
+    p = np;
+    cap = want;
+    return e;
+  }
+  template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+// ---- standalone header (docs/format.md:173-192; pco/src/standalone/decompressor.rs:85-148) ----
+struct StandaloneHeader {
+  uint32_t standalone_version = 0;
+  uint32_t uniform_type = 0;
+  uint64_t n_hint = 0;
+  uint32_t format_major = 4, format_minor = 1;
+  uint64_t first_chunk_byte = 0;
+};
+
+// Parses from the first bytes of the file (at most 32 are needed).  `avail` may be shorter than the file.
+inline PcoB200Error parse_standalone_header(const uint8_t* b, size_t avail, size_t file_len, StandaloneHeader* h) {
+  auto need = [&](size_t n) { return n <= file_len && n <= avail; };
+  if (!need(4)) return fail(PCO_B200_INSUFFICIENT_DATA, "[BitReader] out of bounds reading magic header");
+  static const uint8_t MAGIC[4] = {112, 99, 111, 33};
+  if (std::memcmp(b, MAGIC, 4) != 0) return fail(PCO_B200_CORRUPTION, "magic header does not match \"pco!\"");
+  size_t pos = 4;
+  // The reference reads this section from a zero-padded buffer and bounds-checks afterwards.
+  auto byte_at = [&](size_t i) -> uint8_t { return (i < file_len && i < avail) ? b[i] : 0; };
+  uint32_t ver = byte_at(pos);
+  if (ver < 2) {
+    // versions 0/1 had no standalone header: this byte is the wrapped major version (decompressor.rs:101-107)
+    h->standalone_version = ver;
+  } else {
+    pos += 1;
+    h->standalone_version = ver;
+    if (ver >= 3) {
+      uint8_t t = byte_at(pos);
+      pos += 1;
+      if (t != 0) {
+        if (!nt_valid(t)) return fail(PCO_B200_CORRUPTION, "unknown number type byte: " + std::to_string(t));
+        h->uniform_type = t;
+      }
+    }
+    // varint: 6 bits (power - 1), then `power` bits (standalone/decompressor.rs:14-19)
+    unsigned __int128 wide = 0;
+    for (int i = 0; i < 10; i++) wide |= (unsigned __int128)byte_at(pos + i) << (8 * i);
+    uint32_t power = 1 + uint32_t(uint64_t(wide) & 63);
+    unsigned __int128 v = wide >> 6;
+    uint64_t n_hint = power >= 64 ? uint64_t(v) : uint64_t(v) & ((uint64_t(1) << power) - 1);
+    uint32_t total_bits = 6 + power;
+    uint32_t nbytes = (total_bits + 7) / 8;
+    if (pos + nbytes > file_len) return fail(PCO_B200_INSUFFICIENT_DATA, "[BitReader] out of bounds in standalone header");
+    uint32_t pad = nbytes * 8 - total_bits;
+    if (pad) {
+      uint32_t last = byte_at(pos + nbytes - 1);
+      if ((last >> (8 - pad)) != 0) return fail(PCO_B200_CORRUPTION, "standalone size hint");
+    }
+    h->n_hint = n_hint;
+    pos += nbytes;
+  }
+  if (pos > file_len) return fail(PCO_B200_INSUFFICIENT_DATA, "[BitReader] out of bounds in standalone header");
+  if (h->standalone_version > 3)
+    return fail(PCO_B200_CORRUPTION, "file's standalone version exceeds max supported (3); consider upgrading pco");
+  // wrapped header (metadata/format_version.rs:65-85)
+  uint8_t major = byte_at(pos);
+  pos += 1;
+  uint8_t minor = 0;
+  if (major >= 4) { minor = byte_at(pos); pos += 1; }
+  if (major > 4) return fail(PCO_B200_CORRUPTION, "file's format version cannot be decompressed by this library version");
+  if (pos > file_len) return fail(PCO_B200_INSUFFICIENT_DATA, "[BitReader] out of bounds reading format version");
+  h->format_major = major;
+  h->format_minor = minor;
+  h->first_chunk_byte = pos;
+  return PCO_B200_OK;
+}
+
+// ---- size guarantees (pco/src/standalone/guarantee.rs:11-38, wrapped/guarantee.rs:11-37) ----
+inline size_t standalone_header_size() { return 4 + 1 + (6 + 64 + 8 + 7) / 8 + 2; }
+inline size_t baseline_chunk_meta_size(uint32_t latent_bits) {
+  // mode 4 bits + DeltaEncoding::MAX_BIT_SIZE (4+5+5+64+32*32) + 4 + 15 + one bin (0 + L + log2(L)+1)
+  size_t bits = 4 + (4 + 5 + 5 + 64 + 32 * 32) + 4 + 15 + (latent_bits + offset_bits_bits(latent_bits));
+  return (bits + 7) / 8;
+}
+inline size_t wrapped_chunk_size_guarantee(uint32_t latent_bits, size_t n) {
+  return baseline_chunk_meta_size(latent_bits) + (n * size_t(latent_bits) + 7) / 8;
+}
+inline size_t standalone_chunk_size_guarantee(uint32_t latent_bits, size_t n) { return 1 + 3 + wrapped_chunk_size_guarantee(latent_bits, n); }
+
+}  // namespace pcob200

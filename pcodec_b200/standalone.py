@@ -1,0 +1,115 @@
+"""Mirror of `pcodec.standalone` (pco_python/src/standalone.rs:44-135) over libcpcodec.so."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import ChunkConfig, PcoError, Progress  # noqa: F401
+
+
+def _src_buf(data):
+    mv = memoryview(data)
+    n = mv.nbytes
+    arr = np.frombuffer(mv, dtype=np.uint8) if n else np.zeros(1, dtype=np.uint8)
+    return arr, n
+
+
+def simple_decompress_into(src, dst):
+    """pcodec.standalone.simple_decompress_into (pco_python/src/standalone.rs:90-118): decompresses into a
+    numpy array, returning Progress; never errors on a too-short or too-long dst."""
+    return decompress_into_with_index(src, dst, None)
+
+
+def simple_decompress(src, dtype=None, index=None):
+    """pcodec.standalone.simple_decompress (pco_python/src/standalone.rs:120-135).  The reference infers the
+    dtype from the file; pass `dtype` to assert it.  `index` is an optional side index (bytes)."""
+    if dtype is None:
+        dtype = peek_dtype(src)
+        if dtype is None:
+            return None
+    # size the destination from n_hint when present, growing if the file holds more
+    cap = max(n_hint(src), 1)
+    while True:
+        dst = np.empty(cap, dtype=dtype)
+        prog = decompress_into_with_index(src, dst, index)
+        if prog.finished:
+            return dst[: prog.n_processed]
+        cap = max(cap * 2, 1 << 16)
+
+
+def decompress_into_with_index(src, dst, index=None):
+    L = _lib.lib()
+    arr, n = _src_buf(src)
+    prog = _lib._CProgress()
+    if index is not None:
+        iarr, ilen = _src_buf(index)
+        iptr, ilen_c = iarr.ctypes.data_as(C.c_void_p), C.c_size_t(ilen)
+    else:
+        iptr, ilen_c = None, C.c_size_t(0)
+    rc = L.pco_b200_decompress_ex(arr.ctypes.data_as(C.c_void_p), C.c_size_t(n), C.c_ubyte(_lib.dtype_byte(dst.dtype)),
+                                  dst.ctypes.data_as(C.c_void_p), C.c_size_t(dst.size), C.byref(prog), iptr, ilen_c,
+                                  C.c_uint32(0), None)
+    _lib.check(rc)
+    return Progress(prog.n_processed, bool(prog.finished))
+
+
+def build_index(src, dtype, n_total_hint=None):
+    """Builds the per-batch side index of a standalone file on the device (one serial tANS walk)."""
+    L = _lib.lib()
+    arr, n = _src_buf(src)
+    hint = n_total_hint if n_total_hint is not None else max(n_hint(src), 1)
+    cap = L.pco_b200_index_size_bound(hint, max(hint >> 8, 64))
+    while True:
+        buf = np.empty(cap, dtype=np.uint8)
+        used = C.c_size_t()
+        rc = L.pco_b200_build_index(arr.ctypes.data_as(C.c_void_p), C.c_size_t(n), C.c_ubyte(_lib.dtype_byte(dtype)),
+                                    buf.ctypes.data_as(C.c_void_p), C.c_size_t(cap), C.byref(used), C.c_uint32(0), None)
+        if rc == 4:  # Io: index buffer too small
+            cap *= 4
+            continue
+        _lib.check(rc)
+        return buf[: used.value].tobytes()
+
+
+def _header(src):
+    """(standalone_version, uniform_type, n_hint, first_chunk_byte) — docs/format.md:173-192."""
+    b = bytes(memoryview(src)[:32])
+    if len(b) < 5 or b[:4] != b"pco!":
+        return None
+    ver = b[4]
+    if ver < 2:
+        return ver, 0, 0, 4 + 1
+    pos = 5
+    uniform = 0
+    if ver >= 3:
+        uniform = b[pos] if pos < len(b) else 0
+        pos += 1
+    wide = int.from_bytes(b[pos:pos + 10].ljust(10, b"\0"), "little")
+    power = 1 + (wide & 63)
+    n = (wide >> 6) & ((1 << power) - 1)
+    pos += (6 + power + 7) // 8
+    major = b[pos] if pos < len(b) else 0
+    pos += 2 if major >= 4 else 1
+    return ver, uniform, n, pos
+
+
+def n_hint(src):
+    h = _header(src)
+    return h[2] if h else 0
+
+
+def peek_dtype(src):
+    h = _header(src)
+    if h is None:
+        raise PcoError("Corruption", "magic header does not match")
+    if h[1]:
+        return _lib.BYTE_TO_NP[h[1]]
+    mv = memoryview(src)
+    if h[3] >= mv.nbytes:
+        raise PcoError("InsufficientData", "unable to peek number type from empty bytes")
+    t = mv[h[3]]
+    if t == 0:
+        return None
+    if t not in _lib.BYTE_TO_NP:
+        raise PcoError("Corruption", f"peeked unknown number type byte: {t}")
+    return _lib.BYTE_TO_NP[t]
