@@ -392,6 +392,9 @@ __device__ __forceinline__ uint64_t float_mult_unadjusted(uint64_t l, uint64_t b
   const uint64_t gpi = uint64_t(1) << 53;
   double f = abs_int < gpi ? __ull2double_rn(abs_int) : __longlong_as_double((long long)(0x4340000000000000ull + (abs_int - gpi)));
   if (neg) f = -f;
+  // x86/ARM propagate the operand NaN (quieted, sign and payload kept); NVIDIA GPUs return the canonical NaN.
+  // The reference runs on the CPU, so reproduce its bits (base is validated finite, so only f can be NaN).
+  if (f != f) return (uint64_t)__double_as_longlong(f) | 0x0008000000000000ull;
   return (uint64_t)__double_as_longlong(__dmul_rn(f, __longlong_as_double((long long)base_bits)));
 }
 __device__ __forceinline__ uint32_t float_mult_unadjusted(uint32_t l, uint32_t base_bits) {
@@ -401,6 +404,7 @@ __device__ __forceinline__ uint32_t float_mult_unadjusted(uint32_t l, uint32_t b
   const uint32_t gpi = 1u << 24;
   float f = abs_int < gpi ? __uint2float_rn(abs_int) : __uint_as_float(0x4b800000u + (abs_int - gpi));
   if (neg) f = -f;
+  if (f != f) return __float_as_uint(f) | 0x00400000u;  // CPU NaN propagation, see the f64 overload
   return __float_as_uint(__fmul_rn(f, __uint_as_float(base_bits)));
 }
 __device__ __forceinline__ uint16_t float_mult_unadjusted(uint16_t, uint16_t) { return 0; }  // f16 float_mult: not on the GPU path
