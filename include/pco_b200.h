@@ -66,7 +66,7 @@ typedef struct PcoB200Progress {
 } PcoB200Progress;
 
 /* Buffer-location flags for the *_ex entry points. */
-enum { PCO_B200_SRC_ON_DEVICE = 1u, PCO_B200_DST_ON_DEVICE = 2u };
+enum { PCO_B200_SRC_ON_DEVICE = 1u, PCO_B200_DST_ON_DEVICE = 2u, PCO_B200_INDEX_ON_DEVICE = 4u };
 
 /* Message of the last error raised on the calling thread (pco::errors::PcoError::message). */
 const char *pco_b200_last_error_message(void);
@@ -85,6 +85,19 @@ PcoB200Error pco_b200_simple_decompress_into(const void *compressed, size_t comp
 PcoB200Error pco_b200_decompress_ex(const void *compressed, size_t compressed_len, unsigned char dtype, void *dst,
                                     size_t dst_len, PcoB200Progress *progress, const void *index, size_t index_len,
                                     uint32_t flags, void *cuda_stream);
+
+/* pco::standalone::simple_compress (pco/src/standalone/simple.rs:58-91): header carries uniform type 0.
+ * config may be NULL (pco::ChunkConfig::default()).  Fails with PCO_B200_IO if dst is too small. */
+PcoB200Error pco_b200_simple_compress(const void *nums, size_t n, unsigned char dtype, const PcoB200ChunkConfig *config,
+                                      void *dst, size_t dst_cap, size_t *n_written);
+/* pco::standalone::simple_compress_into (pco/src/standalone/simple.rs:22-48): header carries the number type. */
+PcoB200Error pco_b200_simple_compress_into(const void *nums, size_t n, unsigned char dtype, const PcoB200ChunkConfig *config,
+                                           void *dst, size_t dst_cap, size_t *n_written);
+/* Full-control compress: header flavour (uniform_type_header), optional side index output
+ * (index_cap >= pco_b200_index_size_bound(n, n_chunks)), device-resident buffers and stream. */
+PcoB200Error pco_b200_compress_ex(const void *nums, size_t n, unsigned char dtype, const PcoB200ChunkConfig *config,
+                                  int uniform_type_header, void *dst, size_t dst_cap, size_t *n_written, void *index,
+                                  size_t index_cap, size_t *index_len, uint32_t flags, void *cuda_stream);
 
 /* Build the side index of a standalone file (one serial tANS walk per chunk on the device).
  * index_cap >= pco_b200_index_size_bound(n_total, 2). */

@@ -1,0 +1,1159 @@
+// Encode-side kernels for the pco hot path on sm_100a (one launch handles many independent chunks):
+//   split_delta_kernel  — K1+K2: mode split and consecutive delta encode, page moments, per-chunk min/max
+//   sort_keys_kernel    — range-reduced copy of the stored latents (input of the planner's segmented sort)
+//   plan_kernel         — bin training: equal-count histogram, bin-merge DP, tANS weight quantisation, tables
+//   fallback_kernel     — size-guarantee check (Classic/NoOp/one wide bin fallback)
+//   bin_kernel          — K3: branchless bin search -> symbol per latent, per-batch offset-bit sums
+//   ans_encode_kernel   — K4: reverse 4-way interleaved tANS over the page, per-batch states (side index)
+//   layout_kernel       — per-chunk scan of batch bit sizes -> bit offsets, chunk byte size
+//   pack_kernel         — K5: header/meta/page-meta emission and the variable-width bit-pack of every batch
+//
+// Reference behaviour restated here (paths relative to /root/reference):
+//   split                    pco/src/mode/classic.rs:6-12, float_mult.rs:38-60, int_mult.rs:20-36, float_quant.rs:41-73
+//   delta encode             pco/src/delta/consecutive.rs:3-33, pco/src/wrapped/chunk_compressor.rs:142-217
+//   histogram                pco/src/histograms.rs:87-298 (pivot-independent restatement on sorted data)
+//   bin optimisation         pco/src/bin_optimization.rs:19-198
+//   weight quantisation      pco/src/ans/encoding.rs:95-175, pco/src/wrapped/chunk_compressor.rs:38-99
+//   fallback                 pco/src/wrapped/chunk_compressor.rs:396-440,502-541
+//   bin search / dissect     pco/src/compression_table.rs:51-74, pco/src/chunk_latent_compressor.rs:163-233
+//   tANS encode              pco/src/ans/encoding.rs:28-92, pco/src/chunk_latent_compressor.rs:96-132
+//   page / meta emission     pco/src/chunk_latent_compressor.rs:272-329, pco/src/metadata/{chunk,chunk_latent_var,page}.rs
+#pragma once
+#include "decode_kernels.cuh"
+
+namespace pcob200 {
+
+constexpr int ENC_MAXB = 256;        // bins per latent var (compression level <= 8)
+constexpr int ENC_MAX_SIZE_LOG = 10;
+
+struct EncParams {
+  const void* nums;
+  uint64_t n_total;
+  const uint64_t* chunk_starts;  // device, n_chunks + 1 element offsets
+  uint32_t n_chunks;
+  uint32_t max_chunk_n;
+  uint32_t dtype;
+  uint32_t mode;           // MODE_*
+  uint64_t mode_base;      // IntMult base, or FloatMult base as ordered latent
+  uint64_t base_bits;      // FloatMult: bits of base (as the number type)
+  uint64_t inv_base_bits;  // FloatMult: bits of 1/base
+  uint32_t mode_k;
+  uint32_t order;          // consecutive delta order on the primary (0 = none)
+  uint32_t n_vars;
+  uint32_t bins_log[MAX_VARS];  // unoptimized_bins_log per var
+  uint32_t uniform_type;   // header flavour
+};
+
+struct VarPlan {
+  uint32_t n_bins, size_log, max_ob, n_lat;
+  uint64_t wc_bits;            // sum over bins of count * worst-case bits per latent
+  uint64_t lower[ENC_MAXB];
+  uint8_t ob[ENC_MAXB];
+  uint16_t weight[ENC_MAXB];
+  uint64_t syminfo[ENC_MAXB];  // cutoff (bits 0-15) | min_renorm_bits (16-23) | weight (24-39) | cum (40-55)
+  uint16_t next_states[1 << ENC_MAX_SIZE_LOG];
+};
+
+struct ChunkEnc {              // per chunk, device
+  uint64_t moments[MAX_VARS][MAX_ORDER];
+  uint64_t vmin[MAX_VARS], vmax[MAX_VARS];
+  uint32_t final_state[MAX_VARS][4];
+  uint32_t fallback;           // 1 = Classic / NoOp / one bin of L::BITS offset bits
+  uint32_t status;
+  uint32_t meta_bytes, page_meta_bytes;
+  uint64_t body_bits;
+  uint64_t chunk_bytes;        // preamble + meta + page
+  uint64_t out_offset;         // byte offset of the chunk in the output file
+};
+
+// ---------------------------------------------------------------------------
+// f32 helpers with explicit rounding (never contracted to FMA)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float log2_approx_dev(float x) {  // pco/src/bin_optimization.rs:19-43
+  const float Z = 0.674f;
+  const uint32_t SIGNIF_MASK = 0x7FFFFFu;
+  const uint32_t Z_SIGNIF = __float_as_uint(Z) & SIGNIF_MASK;
+  const float B = __fdiv_rn(2.0f, Z);
+  const float Cc = __fdiv_rn(-B, __fmul_rn(6.0f, Z));
+  const float A = __fsub_rn(-B, Cc);
+  uint32_t bits = __float_as_uint(x);
+  uint32_t exp = bits >> 23;
+  uint32_t signif = bits & SIGNIF_MASK;
+  uint32_t high_bit = signif > Z_SIGNIF ? 1u : 0u;
+  uint32_t log_int = exp + high_bit - 127u;
+  float normalized = __uint_as_float(((0x7Fu ^ high_bit) << 23) | signif);
+  float t0 = __fadd_rn(__uint2float_rn(log_int), A);
+  float t2 = __fadd_rn(B, __fmul_rn(Cc, normalized));
+  return __fadd_rn(t0, __fmul_rn(normalized, t2));
+}
+__device__ __forceinline__ uint32_t bits_to_encode_u64(uint64_t x) { return x == 0 ? 0u : 64u - uint32_t(__clzll((long long)x)); }
+__device__ __forceinline__ float bin_cost_dev(float bin_meta_cost, uint64_t range, uint32_t count, float total_log2) {  // bin_optimization.rs:46-57
+  float cf = __uint2float_rn(count);
+  float ans_cost = __fsub_rn(total_log2, log2_approx_dev(cf));
+  float offset_cost = __uint2float_rn(bits_to_encode_u64(range));
+  return __fadd_rn(bin_meta_cost, __fmul_rn(__fadd_rn(ans_cost, offset_cost), cf));
+}
+
+// ---------------------------------------------------------------------------
+// K1 + K2: split into latents, delta encode the primary, moments, min/max of the stored latents
+// ---------------------------------------------------------------------------
+template <typename L>
+__device__ __forceinline__ L round_mult_to_latent(L bits, const EncParams& ep, L* adj_out);
+
+// int_float_to_latent (pco/src/data_types/float.rs:229-244) on bit patterns
+__device__ __forceinline__ uint64_t int_float_to_latent_bits(uint64_t fbits) {
+  const uint64_t MID = uint64_t(1) << 63;
+  uint64_t abs_bits = fbits & ~MID;
+  const uint64_t gpi = uint64_t(1) << 53;
+  const uint64_t gpi_bits = 0x4340000000000000ull;
+  double a = __longlong_as_double((long long)abs_bits);
+  uint64_t abs_int = (a < 9007199254740992.0) ? (uint64_t)__double2ull_rz(a) : gpi + (abs_bits - gpi_bits);
+  return (fbits & MID) ? (MID - 1 - abs_int) : (MID + abs_int);
+}
+__device__ __forceinline__ uint32_t int_float_to_latent_bits(uint32_t fbits) {
+  const uint32_t MID = 1u << 31;
+  uint32_t abs_bits = fbits & ~MID;
+  const uint32_t gpi = 1u << 24;
+  const uint32_t gpi_bits = 0x4b800000u;
+  float a = __uint_as_float(abs_bits);
+  uint32_t abs_int = (a < 16777216.0f) ? __float2uint_rz(a) : gpi + (abs_bits - gpi_bits);
+  return (fbits & MID) ? (MID - 1 - abs_int) : (MID + abs_int);
+}
+
+// float_mult split of one number (pco/src/mode/float_mult.rs:38-60).  NaN operands follow the CPU rule
+// (operand NaN propagates quieted), see float_mult_unadjusted in decode_kernels.cuh.
+__device__ __forceinline__ void float_mult_split(uint64_t xbits, uint64_t base_bits, uint64_t inv_bits, uint64_t& primary, uint64_t& secondary) {
+  const uint64_t MID = uint64_t(1) << 63, QUIET = 0x0008000000000000ull;
+  double x = __longlong_as_double((long long)xbits);
+  uint64_t mult_bits;
+  if (x != x) mult_bits = xbits | QUIET;
+  else {
+    double q = __dmul_rn(x, __longlong_as_double((long long)inv_bits));
+    mult_bits = (uint64_t)__double_as_longlong(round(q));  // round half away from zero
+  }
+  primary = int_float_to_latent_bits(mult_bits);
+  double mult = __longlong_as_double((long long)mult_bits);
+  uint64_t prod_bits = (mult != mult) ? (mult_bits | QUIET) : (uint64_t)__double_as_longlong(__dmul_rn(mult, __longlong_as_double((long long)base_bits)));
+  uint64_t a = (xbits & MID) ? ~xbits : (xbits ^ MID);
+  uint64_t b = (prod_bits & MID) ? ~prod_bits : (prod_bits ^ MID);
+  secondary = (a - b) + MID;
+}
+__device__ __forceinline__ void float_mult_split(uint32_t xbits, uint32_t base_bits, uint32_t inv_bits, uint32_t& primary, uint32_t& secondary) {
+  const uint32_t MID = 1u << 31, QUIET = 0x00400000u;
+  float x = __uint_as_float(xbits);
+  uint32_t mult_bits;
+  if (x != x) mult_bits = xbits | QUIET;
+  else {
+    float q = __fmul_rn(x, __uint_as_float(inv_bits));
+    mult_bits = __float_as_uint(roundf(q));
+  }
+  primary = int_float_to_latent_bits(mult_bits);
+  float mult = __uint_as_float(mult_bits);
+  uint32_t prod_bits = (mult != mult) ? (mult_bits | QUIET) : __float_as_uint(__fmul_rn(mult, __uint_as_float(base_bits)));
+  uint32_t a = (xbits & MID) ? ~xbits : (xbits ^ MID);
+  uint32_t b = (prod_bits & MID) ? ~prod_bits : (prod_bits ^ MID);
+  secondary = (a - b) + MID;
+}
+
+template <typename L>
+__device__ __forceinline__ void split_one(L xbits, const EncParams& ep, bool is_float, bool is_signed, L& p, L& s) {
+  constexpr L MID = L(L(1) << (LT<L>::BITS - 1));
+  s = 0;
+  switch (ep.mode) {
+    case MODE_CLASSIC: p = to_latent_ordered<L>(xbits, is_float, is_signed); break;
+    case MODE_INT_MULT: {
+      L u = to_latent_ordered<L>(xbits, is_float, is_signed);
+      L base = L(ep.mode_base);
+      p = L(u / base);
+      s = L(u % base);
+      break;
+    }
+    case MODE_FLOAT_QUANT: {
+      L u = to_latent_ordered<L>(xbits, true, false);
+      L kmax = L(L(L(1) << ep.mode_k) - 1);
+      p = L(u >> ep.mode_k);
+      L lowest = L(u & kmax);
+      s = (xbits & MID) ? L(kmax - lowest) : lowest;
+      break;
+    }
+    default: {  // MODE_FLOAT_MULT
+      if constexpr (sizeof(L) == 8) {
+        uint64_t pp, ss;
+        float_mult_split(uint64_t(xbits), ep.base_bits, ep.inv_base_bits, pp, ss);
+        p = pp; s = ss;
+      } else if constexpr (sizeof(L) == 4) {
+        uint32_t pp, ss;
+        float_mult_split(uint32_t(xbits), uint32_t(ep.base_bits), uint32_t(ep.inv_base_bits), pp, ss);
+        p = pp; s = ss;
+      } else {
+        p = 0;
+      }
+    }
+  }
+}
+
+constexpr int SPLIT_THREADS = 256;
+constexpr int SPLIT_PER_THREAD = 8;
+constexpr int SPLIT_TILE = SPLIT_THREADS * SPLIT_PER_THREAD;
+
+__device__ __forceinline__ void atomic_min_u64(uint64_t* a, uint64_t v) { atomicMin(reinterpret_cast<unsigned long long*>(a), (unsigned long long)v); }
+__device__ __forceinline__ void atomic_max_u64(uint64_t* a, uint64_t v) { atomicMax(reinterpret_cast<unsigned long long*>(a), (unsigned long long)v); }
+
+// grid: n_chunks * tiles_per_chunk.  lat0/lat1 are indexed like nums (element g of the input).
+template <typename L>
+__global__ void __launch_bounds__(SPLIT_THREADS) split_delta_kernel(EncParams ep, uint32_t tiles_per_chunk, L* __restrict__ lat0, L* __restrict__ lat1,
+                                                                     ChunkEnc* __restrict__ chunks) {
+  __shared__ L tile[SPLIT_TILE + MAX_ORDER];
+  __shared__ uint64_t red_min[MAX_VARS][SPLIT_THREADS / 32], red_max[MAX_VARS][SPLIT_THREADS / 32];
+  const uint32_t c = blockIdx.x / tiles_per_chunk, t = blockIdx.x % tiles_per_chunk;
+  const uint64_t cs = ep.chunk_starts[c], ce = ep.chunk_starts[c + 1];
+  const uint32_t n = uint32_t(ce - cs);
+  const uint32_t tile_start = t * SPLIT_TILE;
+  if (tile_start >= n) return;
+  const L* nums = static_cast<const L*>(ep.nums) + cs;
+  const bool is_float = nt_is_float(ep.dtype), is_signed = nt_is_signed(ep.dtype);
+  const uint32_t order = ep.order;
+  const int tid = threadIdx.x;
+  constexpr L MID = L(L(1) << (LT<L>::BITS - 1));
+  // primary latents of [tile_start - order, tile_start + SPLIT_TILE) into shared memory (halo of `order`)
+  uint64_t mn1 = ~uint64_t(0), mx1 = 0;
+  for (int i = tid; i < SPLIT_TILE + int(order); i += SPLIT_THREADS) {
+    int64_t idx = int64_t(tile_start) + i - int64_t(order);
+    L p = 0, s = 0;
+    if (idx >= 0 && idx < int64_t(n)) {
+      split_one<L>(nums[idx], ep, is_float, is_signed, p, s);
+      if (i >= int(order) && ep.n_vars > 1) {
+        lat1[cs + idx] = s;
+        mn1 = min(mn1, uint64_t(s));
+        mx1 = max(mx1, uint64_t(s));
+      }
+    }
+    tile[i] = p;
+  }
+  __syncthreads();
+  uint64_t mn0 = ~uint64_t(0), mx0 = 0;
+  for (int i = tid; i < SPLIT_TILE; i += SPLIT_THREADS) {
+    uint32_t idx = tile_start + i;
+    if (idx >= n) break;
+    // order-th backward difference, binomial stencil in wrapping arithmetic (== `order` passes of x[i] -= x[i-1])
+    L d = tile[i + order];
+    if (order > 0) {
+      L acc = 0;
+      // sum_j (-1)^j C(order, j) x[i - j]
+      uint32_t binom = 1;
+      for (uint32_t j = 0; j <= order; j++) {
+        L term = L(L(binom) * tile[i + order - j]);
+        acc = (j & 1) ? L(acc - term) : L(acc + term);
+        binom = binom * (order - j) / (j + 1);
+      }
+      d = L(acc + MID);  // toggle_center (delta/mod.rs:29-33)
+    }
+    if (idx >= order) {
+      lat0[cs + idx] = d;
+      mn0 = min(mn0, uint64_t(d));
+      mx0 = max(mx0, uint64_t(d));
+    }
+  }
+  // page moments: moment_j = (j-th backward difference)[j]  (delta/consecutive.rs:19-33)
+  if (t == 0 && tid < int(order)) {
+    uint32_t j = tid;
+    L acc = 0;
+    if (j < n) {
+      uint32_t binom = 1;
+      for (uint32_t q = 0; q <= j; q++) {
+        L term = L(L(binom) * tile[order + j - q]);
+        acc = (q & 1) ? L(acc - term) : L(acc + term);
+        binom = binom * (j - q) / (q + 1);
+      }
+    }
+    chunks[c].moments[0][j] = uint64_t(acc);
+  }
+  // block min/max -> per-chunk atomics
+  for (int d = 16; d > 0; d >>= 1) {
+    mn0 = min(mn0, __shfl_xor_sync(0xffffffffu, mn0, d));
+    mx0 = max(mx0, __shfl_xor_sync(0xffffffffu, mx0, d));
+    mn1 = min(mn1, __shfl_xor_sync(0xffffffffu, mn1, d));
+    mx1 = max(mx1, __shfl_xor_sync(0xffffffffu, mx1, d));
+  }
+  if ((tid & 31) == 0) { red_min[0][tid >> 5] = mn0; red_max[0][tid >> 5] = mx0; red_min[1][tid >> 5] = mn1; red_max[1][tid >> 5] = mx1; }
+  __syncthreads();
+  if (tid < int(ep.n_vars)) {
+    uint64_t a = ~uint64_t(0), b = 0;
+    for (int w = 0; w < SPLIT_THREADS / 32; w++) { a = min(a, red_min[tid][w]); b = max(b, red_max[tid][w]); }
+    if (a <= b) { atomic_min_u64(&chunks[c].vmin[tid], a); atomic_max_u64(&chunks[c].vmax[tid], b); }
+  }
+}
+
+__global__ void init_chunks_kernel(ChunkEnc* chunks, uint32_t n_chunks) {
+  uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_chunks) return;
+  ChunkEnc z;
+  memset(&z, 0, sizeof(z));
+  z.vmin[0] = z.vmin[1] = ~uint64_t(0);
+  chunks[c] = z;
+}
+
+// Stored range of var v in chunk [cs, ce): [cs + order_v, ce)
+__device__ __forceinline__ uint64_t stored_begin(uint64_t cs, uint64_t ce, uint32_t order_v) { return min(cs + order_v, ce); }
+
+// keys = latent - min(chunk, var): order-preserving, and lets the planner's sort skip the constant high bits
+template <typename L>
+__global__ void sort_keys_kernel(EncParams ep, uint32_t tiles_per_chunk, const L* __restrict__ lat, L* __restrict__ keys,
+                                 const ChunkEnc* __restrict__ chunks, int v) {
+  const uint32_t c = blockIdx.x / tiles_per_chunk, t = blockIdx.x % tiles_per_chunk;
+  const uint64_t cs = ep.chunk_starts[c], ce = ep.chunk_starts[c + 1];
+  const uint64_t sb = stored_begin(cs, ce, v == 0 ? ep.order : 0);
+  const L mn = L(chunks[c].vmin[v]);
+  for (int i = threadIdx.x; i < SPLIT_TILE; i += blockDim.x) {
+    uint64_t g = cs + uint64_t(t) * SPLIT_TILE + i;
+    if (g >= sb && g < ce) keys[g] = L(lat[g] - mn);
+  }
+}
+
+// segment offsets for the segmented sort
+__global__ void segment_offsets_kernel(EncParams ep, uint32_t order_v, uint64_t* begins, uint64_t* ends) {
+  uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ep.n_chunks) return;
+  uint64_t cs = ep.chunk_starts[c], ce = ep.chunk_starts[c + 1];
+  begins[c] = stored_begin(cs, ce, order_v);
+  ends[c] = ce;
+}
+
+// ---------------------------------------------------------------------------
+// plan_kernel: one CTA per (chunk, var).  Input: the var's stored latents sorted ascending (as keys = l - min).
+// ---------------------------------------------------------------------------
+constexpr int PLAN_THREADS = 256;
+
+struct PlanSmem {
+  // histogram boundary probes
+  uint64_t vB1[ENC_MAXB], vB[ENC_MAXB], vLm1[ENC_MAXB], vR[ENC_MAXB];
+  uint32_t runL[ENC_MAXB], runR[ENC_MAXB];
+  // unoptimized bins
+  uint32_t h_count[ENC_MAXB];
+  uint64_t h_lower[ENC_MAXB], h_upper[ENC_MAXB];
+  uint32_t n_hist;
+  // DP
+  uint32_t c_counts[ENC_MAXB + 1];
+  float best_cost[ENC_MAXB + 1];
+  uint32_t best_j[ENC_MAXB];
+  float red_cost[PLAN_THREADS / 32];
+  uint32_t red_j[PLAN_THREADS / 32];
+  // optimized bins
+  uint32_t o_count[ENC_MAXB];
+  uint64_t o_lower[ENC_MAXB], o_upper[ENC_MAXB];
+  uint32_t o_ob[ENC_MAXB];
+  uint32_t n_opt;
+  float fweights[ENC_MAXB];
+  uint32_t weights[ENC_MAXB];
+  uint32_t cum[ENC_MAXB + 1];
+  uint32_t size_log;
+  uint16_t sym_of_state[1 << ENC_MAX_SIZE_LOG];
+  uint32_t rank_counter[ENC_MAXB];
+};
+
+template <typename L>
+__global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(EncParams ep, const L* __restrict__ sorted_keys, const ChunkEnc* __restrict__ chunks,
+                                                             VarPlan* __restrict__ plans, int v) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  PlanSmem& sm = *reinterpret_cast<PlanSmem*>(smem_raw);
+  const uint32_t c = blockIdx.x;
+  const int tid = threadIdx.x;
+  const uint64_t cs = ep.chunk_starts[c], ce = ep.chunk_starts[c + 1];
+  const uint64_t sb = stored_begin(cs, ce, v == 0 ? ep.order : 0);
+  const uint32_t n = uint32_t(ce - sb);  // stored latents
+  const L* s = sorted_keys + sb;
+  VarPlan& plan = plans[size_t(c) * MAX_VARS + v];
+  const uint64_t vmin = chunks[c].vmin[v];
+  constexpr uint32_t LBITS = LT<L>::BITS;
+  if (n == 0) {  // train_infos on an empty var (chunk_compressor.rs:56-58): zero bins
+    if (tid == 0) { plan.n_bins = 0; plan.size_log = 0; plan.max_ob = 0; plan.n_lat = 0; plan.wc_bits = 0; plan.next_states[0] = 0; }
+    return;
+  }
+  const uint32_t n_bins_log = ep.bins_log[v];
+  const uint32_t nbk = 1u << n_bins_log;
+  auto bin_idx_of = [&](uint64_t cc) -> uint32_t { return uint32_t((cc << n_bins_log) / n); };
+  auto c_count_of = [&](uint32_t b) -> uint32_t { return uint32_t((uint64_t(b + 1) * n + nbk - 1) >> n_bins_log); };
+  // ---- 1. probes at every equal-count boundary, in parallel (histograms.rs:132-140)
+  for (uint32_t k = tid; k < nbk; k += PLAN_THREADS) {
+    uint32_t B = c_count_of(k);
+    uint64_t vb1 = 0, vb = 0, vlm1 = 0, vr = 0;
+    uint32_t l = 0, r = 0;
+    if (B >= 1 && B <= n) {
+      vb1 = uint64_t(s[B - 1]);
+      if (B < n) vb = uint64_t(s[B]);
+      if (B < n && vb == vb1) {
+        // extent [l, r) of the run of vb1: lower_bound / upper_bound
+        uint32_t lo = 0, hi = B - 1;  // first index with s[idx] >= vb1 is in [0, B-1]
+        while (lo < hi) { uint32_t m = (lo + hi) >> 1; if (uint64_t(s[m]) < vb1) lo = m + 1; else hi = m; }
+        l = lo;
+        lo = B; hi = n;               // first index with s[idx] > vb1 is in [B+1, n]
+        while (lo < hi) { uint32_t m = (lo + hi) >> 1; if (uint64_t(s[m]) <= vb1) lo = m + 1; else hi = m; }
+        r = lo;
+        if (l > 0) vlm1 = uint64_t(s[l - 1]);
+        if (r < n) vr = uint64_t(s[r]);
+      }
+    }
+    sm.vB1[k] = vb1; sm.vB[k] = vb; sm.vLm1[k] = vlm1; sm.vR[k] = vr; sm.runL[k] = l; sm.runR[k] = r;
+  }
+  __syncthreads();
+  // ---- 2. histogram state machine (HistogramBuilder), sequential over at most 2^log boundaries
+  if (tid == 0) {
+    uint32_t n_hist = 0, next_avail = 0, pos = 0;
+    bool has_inc = false;
+    uint32_t inc_count = 0;
+    uint64_t inc_lower = 0, inc_upper = 0;
+    uint64_t pos_val = uint64_t(s[0]);
+    auto apply_incomplete = [&](uint32_t cnt, uint64_t lo_v, uint64_t hi_v) {
+      if (cnt == 0) return;
+      if (has_inc) { inc_upper = hi_v; inc_count += cnt; }
+      else { has_inc = true; inc_count = cnt; inc_lower = lo_v; inc_upper = hi_v; }
+    };
+    auto complete_bin = [&](uint32_t b) -> bool {
+      if (!has_inc) return false;
+      next_avail = b + 1;
+      sm.h_count[n_hist] = inc_count; sm.h_lower[n_hist] = inc_lower; sm.h_upper[n_hist] = inc_upper;
+      n_hist++;
+      has_inc = false;
+      return true;
+    };
+    while (pos < n) {
+      uint32_t k = bin_idx_of(pos);
+      uint32_t B = c_count_of(k);
+      if (B >= n || sm.vB1[k] != sm.vB[k]) {
+        apply_incomplete(B - pos, pos_val, sm.vB1[k]);
+        complete_bin(k);
+        pos = B;
+        pos_val = sm.vB[k];
+      } else {
+        uint32_t l = sm.runL[k], r = sm.runR[k];
+        uint64_t val = sm.vB1[k];
+        if (l > pos) apply_incomplete(l - pos, pos_val, sm.vLm1[k]);
+        // apply_constant_run (histograms.rs:142-161)
+        uint32_t mid = l + (r - l) / 2;
+        uint32_t b = bin_idx_of(mid);
+        if (b > next_avail) {
+          uint32_t spare = b - 1;
+          if (!complete_bin(spare)) b = spare;
+        }
+        apply_incomplete(r - l, val, val);
+        if (r >= c_count_of(b)) complete_bin(b);
+        pos = r;
+        pos_val = sm.vR[k];
+      }
+    }
+    sm.n_hist = n_hist;
+  }
+  __syncthreads();
+  const uint32_t nh = sm.n_hist;
+  // estimated_ans_size_log (chunk_compressor.rs:63-79)
+  const uint32_t n_log_ceil = n <= 1 ? 0 : (32 - __clz(n - 1));
+  const uint32_t est_size_log = min(min(n_bins_log + 2, 12u), n_log_ceil);
+  // ---- 3. bin-merge DP (bin_optimization.rs:104-178)
+  if (tid == 0) {
+    uint32_t cc = 0;
+    sm.c_counts[0] = 0;
+    sm.best_cost[0] = 0.0f;
+    for (uint32_t i = 0; i < nh; i++) { cc += sm.h_count[i]; sm.c_counts[i + 1] = cc; }
+  }
+  __syncthreads();
+  const uint32_t total_count = sm.c_counts[nh];
+  const float total_log2 = log2_approx_dev(__uint2float_rn(total_count));
+  const float bin_meta_cost = __uint2float_rn(est_size_log + LBITS + offset_bits_bits(LBITS));
+  for (uint32_t i = 0; i < nh; i++) {
+    float my_cost = 3.402823466e+38f;
+    uint32_t my_j = 0xffffffffu;
+    const uint64_t upper = sm.h_upper[i];
+    const uint32_t cci = sm.c_counts[i + 1];
+    // each thread scans its js downward (strict <: the largest j wins ties)
+    for (int j = int(i) - tid; j >= 0; j -= PLAN_THREADS) {
+      float cost = __fadd_rn(sm.best_cost[j], bin_cost_dev(bin_meta_cost, upper - sm.h_lower[j], cci - sm.c_counts[j], total_log2));
+      if (cost < my_cost) { my_cost = cost; my_j = uint32_t(j); }
+    }
+    // warp then block argmin with "largest j among equal costs"
+    for (int d = 16; d > 0; d >>= 1) {
+      float oc = __shfl_xor_sync(0xffffffffu, my_cost, d);
+      uint32_t oj = __shfl_xor_sync(0xffffffffu, my_j, d);
+      bool take = (oj != 0xffffffffu) && (my_j == 0xffffffffu || oc < my_cost || (oc == my_cost && oj > my_j));
+      if (take) { my_cost = oc; my_j = oj; }
+    }
+    if ((tid & 31) == 0) { sm.red_cost[tid >> 5] = my_cost; sm.red_j[tid >> 5] = my_j; }
+    __syncthreads();
+    if (tid == 0) {
+      float bc = sm.red_cost[0];
+      uint32_t bj = sm.red_j[0];
+      for (int w = 1; w < PLAN_THREADS / 32; w++) {
+        float oc = sm.red_cost[w];
+        uint32_t oj = sm.red_j[w];
+        bool take = (oj != 0xffffffffu) && (bj == 0xffffffffu || oc < bc || (oc == bc && oj > bj));
+        if (take) { bc = oc; bj = oj; }
+      }
+      sm.best_cost[i + 1] = bc;
+      sm.best_j[i] = bj;
+    }
+    __syncthreads();
+  }
+  // ---- 4. shortcuts, rewind, weights (thread 0: short sequential f32 sums whose order matters)
+  if (tid == 0) {
+    const float best = sm.best_cost[nh];
+    const float slack = __fmul_rn(0.1f, __uint2float_rn(total_count));
+    const float single = bin_cost_dev(bin_meta_cost, sm.h_upper[nh - 1] - sm.h_lower[0], total_count, total_log2);
+    uint32_t n_opt = 0;
+    bool done = false;
+    if (single < __fadd_rn(best, slack)) {
+      sm.o_lower[0] = sm.h_lower[0]; sm.o_upper[0] = sm.h_upper[nh - 1]; sm.o_count[0] = total_count;
+      n_opt = 1;
+      done = true;
+    }
+    if (!done) {
+      bool all_trivial = true;
+      for (uint32_t i = 0; i < nh; i++) if (sm.h_lower[i] != sm.h_upper[i]) { all_trivial = false; break; }
+      if (all_trivial) {
+        float cost = 0.0f;
+        for (uint32_t i = 0; i < nh; i++) cost = __fadd_rn(cost, bin_cost_dev(bin_meta_cost, 0, sm.h_count[i], total_log2));
+        if (cost < __fadd_rn(best, slack)) {
+          for (uint32_t i = 0; i < nh; i++) { sm.o_lower[i] = sm.h_lower[i]; sm.o_upper[i] = sm.h_upper[i]; sm.o_count[i] = sm.h_count[i]; }
+          n_opt = nh;
+          done = true;
+        }
+      }
+    }
+    if (!done) {
+      // rewind best_js into groups, last group first, then reverse
+      uint32_t i = nh - 1;
+      uint32_t cnt = 0;
+      for (;;) {
+        uint32_t j = sm.best_j[i];
+        sm.o_lower[nh - 1 - cnt] = sm.h_lower[j];
+        sm.o_upper[nh - 1 - cnt] = sm.h_upper[i];
+        sm.o_count[nh - 1 - cnt] = sm.c_counts[i + 1] - sm.c_counts[j];
+        cnt++;
+        if (j > 0) i = j - 1; else break;
+      }
+      for (uint32_t q = 0; q < cnt; q++) {
+        sm.o_lower[q] = sm.o_lower[nh - cnt + q]; sm.o_upper[q] = sm.o_upper[nh - cnt + q]; sm.o_count[q] = sm.o_count[nh - cnt + q];
+      }
+      n_opt = cnt;
+    }
+    for (uint32_t q = 0; q < n_opt; q++) sm.o_ob[q] = bits_to_encode_u64(sm.o_upper[q] - sm.o_lower[q]);
+    sm.n_opt = n_opt;
+    // ---- quantize_weights (ans/encoding.rs:95-175)
+    uint32_t size_log;
+    if (n_opt == 1) {
+      size_log = 0;
+      sm.weights[0] = 1;
+    } else {
+      uint32_t min_size_log = 32 - __clz(n_opt - 1);
+      size_log = max(min_size_log, est_size_log);
+      const uint32_t required = 1u << size_log;
+      const float multiplier = __fdiv_rn(__uint2float_rn(required), __uint2float_rn(n));
+      float desired_surplus = 0.0f;
+      for (uint32_t q = 0; q < n_opt; q++) {
+        float vv = __fsub_rn(__fmul_rn(__uint2float_rn(sm.o_count[q]), multiplier), 1.0f);
+        vv = vv > 0.0f ? vv : 0.0f;
+        sm.fweights[q] = vv;
+        desired_surplus = __fadd_rn(desired_surplus, vv);
+      }
+      const uint32_t required_surplus = required - n_opt;
+      const float surplus_mult = desired_surplus == 0.0f ? 0.0f : __fdiv_rn(__uint2float_rn(required_surplus), desired_surplus);
+      uint32_t weight_sum = 0;
+      for (uint32_t q = 0; q < n_opt; q++) {
+        float fw = __fadd_rn(1.0f, __fmul_rn(sm.fweights[q], surplus_mult));
+        sm.fweights[q] = fw;
+        uint32_t w = __float2uint_rz(roundf(fw));
+        sm.weights[q] = w;
+        weight_sum += w;
+      }
+      uint32_t q = 0;
+      while (weight_sum > required && q < n_opt) {
+        if (sm.weights[q] > 1 && __uint2float_rn(sm.weights[q]) > sm.fweights[q]) { sm.weights[q] -= 1; weight_sum -= 1; }
+        q += 1;
+      }
+      q = 0;
+      while (weight_sum < required && q < n_opt) {
+        if (__uint2float_rn(sm.weights[q]) < sm.fweights[q]) { sm.weights[q] += 1; weight_sum += 1; }
+        q += 1;
+      }
+      uint32_t p2 = 32;
+      for (uint32_t t = 0; t < n_opt; t++) p2 = min(p2, uint32_t(__ffs(sm.weights[t]) - 1));
+      size_log -= p2;
+      for (uint32_t t = 0; t < n_opt; t++) sm.weights[t] >>= p2;
+    }
+    sm.size_log = size_log;
+    uint32_t cm = 0;
+    uint64_t wc = 0;
+    uint32_t max_ob = 0;
+    for (uint32_t t = 0; t < n_opt; t++) {
+      sm.cum[t] = cm;
+      cm += sm.weights[t];
+      wc += uint64_t(sm.o_count[t]) * (sm.o_ob[t] + size_log - (31 - __clz(sm.weights[t])));  // bin.rs:25-27
+      max_ob = max(max_ob, sm.o_ob[t]);
+    }
+    sm.cum[n_opt] = cm;
+    plan.n_bins = n_opt;
+    plan.size_log = size_log;
+    plan.max_ob = max_ob;
+    plan.n_lat = n;
+    plan.wc_bits = wc;
+  }
+  __syncthreads();
+  const uint32_t n_opt = sm.n_opt, size_log = sm.size_log, size = 1u << size_log;
+  const uint64_t lmask = LBITS == 64 ? ~uint64_t(0) : ((uint64_t(1) << LBITS) - 1);
+  for (uint32_t q = tid; q < n_opt; q += PLAN_THREADS) {
+    plan.lower[q] = (sm.o_lower[q] + vmin) & lmask;
+    plan.ob[q] = uint8_t(sm.o_ob[q]);
+    plan.weight[q] = uint16_t(sm.weights[q]);
+    sm.rank_counter[q] = 0;
+    // SymbolInfo (ans/encoding.rs:36-49)
+    uint32_t w = sm.weights[q];
+    uint32_t max_x_s = 2 * w - 1;
+    uint32_t min_renorm = size_log - (31 - __clz(max_x_s));
+    uint32_t cutoff = (2 * w) << min_renorm;
+    plan.syminfo[q] = uint64_t(cutoff) | (uint64_t(min_renorm) << 16) | (uint64_t(w) << 24) | (uint64_t(sm.cum[q]) << 40);
+  }
+  // spread (ans/spec.rs:37-59) and per-symbol ascending state lists (ans/encoding.rs:51-55)
+  uint32_t stride = (3 * size) / 5;
+  if ((stride & 1) == 0) stride += 1;
+  for (uint32_t t = tid; t < size; t += PLAN_THREADS) {
+    uint32_t lo = 0, hi = n_opt;
+    while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (sm.cum[m] <= t) lo = m; else hi = m; }
+    sm.sym_of_state[(stride * t) & (size - 1)] = uint16_t(lo);
+  }
+  __syncthreads();
+  if (tid < 32) {
+    const uint32_t lane = tid;
+    for (uint32_t base = 0; base < size; base += 32) {
+      uint32_t st = base + lane;
+      bool active = st < size;
+      uint32_t sym = active ? sm.sym_of_state[st] : 0xffffffffu;
+      uint32_t m = __match_any_sync(0xffffffffu, sym);
+      uint32_t in_group = __popc(m & ((1u << lane) - 1));
+      uint32_t prev = active ? sm.rank_counter[sym] : 0;
+      __syncwarp();
+      if (active && in_group == 0) sm.rank_counter[sym] = prev + __popc(m);
+      __syncwarp();
+      if (active) plan.next_states[sm.cum[sym] + prev + in_group] = uint16_t(st);  // state = size + st
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// should_fallback (chunk_compressor.rs:502-541): one thread per chunk
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t var_meta_bits(uint32_t n_bins, uint32_t size_log, uint32_t lbits) {
+  return 4 + 15 + n_bins * (size_log + lbits + offset_bits_bits(lbits));
+}
+__device__ __forceinline__ uint32_t mode_payload_bits(uint32_t mode, uint32_t lbits) {
+  return mode == MODE_CLASSIC ? 0 : mode == MODE_FLOAT_QUANT ? 8 : lbits;
+}
+
+__global__ void fallback_kernel(EncParams ep, const VarPlan* __restrict__ plans, ChunkEnc* __restrict__ chunks) {
+  uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ep.n_chunks) return;
+  const uint32_t lbits = nt_bits(ep.dtype);
+  const uint64_t n = ep.chunk_starts[c + 1] - ep.chunk_starts[c];
+  uint32_t fb = 0;
+  if (!(ep.order == 0 && ep.mode == MODE_CLASSIC)) {
+    uint64_t wc_bits = 7;  // 7 * n_pages
+    uint64_t meta_bits = 4 + mode_payload_bits(ep.mode, lbits) + (4 + 5 + 5 + 64 + 32 * 32);  // mode.max_bit_size + DeltaEncoding::MAX_BIT_SIZE
+    uint64_t page_meta_bits = 0;
+    for (uint32_t v = 0; v < ep.n_vars; v++) {
+      const VarPlan& p = plans[size_t(c) * MAX_VARS + v];
+      wc_bits += p.wc_bits;
+      meta_bits += var_meta_bits(p.n_bins, p.size_log, lbits);
+      page_meta_bits += 4 * p.size_log + uint64_t(lbits) * (v == 0 ? ep.order : 0);
+    }
+    uint64_t worst = (meta_bits + 7) / 8 + (page_meta_bits + 7) / 8 + (wc_bits + 7) / 8;
+    uint64_t baseline_meta_bits = 4 + (4 + 5 + 5 + 64 + 32 * 32) + 4 + 15 + (lbits + offset_bits_bits(lbits));
+    uint64_t baseline = (baseline_meta_bits + 7) / 8 + (n * lbits + 7) / 8;
+    fb = worst > baseline ? 1 : 0;
+  }
+  chunks[c].fallback = fb;
+}
+
+// ---------------------------------------------------------------------------
+// K3: bin search.  One warp per batch; writes the symbol of every stored latent and the batch's offset-bit sum.
+// Batch b of var v covers stored latents [256 b, 256 b + 256) of the var's stored range.
+// ---------------------------------------------------------------------------
+constexpr int BIN_THREADS = 256;
+
+template <typename L>
+__device__ __forceinline__ L fallback_latent(const EncParams& ep, uint64_t g) {
+  return to_latent_ordered<L>(static_cast<const L*>(ep.nums)[g], nt_is_float(ep.dtype), nt_is_signed(ep.dtype));
+}
+
+template <typename L>
+__global__ void __launch_bounds__(BIN_THREADS) bin_kernel(EncParams ep, uint32_t batches_per_chunk, const L* __restrict__ lat, const VarPlan* __restrict__ plans,
+                                                           const ChunkEnc* __restrict__ chunks, uint8_t* __restrict__ sym, uint32_t* __restrict__ ob_sum, int v) {
+  __shared__ uint64_t lowers[ENC_MAXB];
+  __shared__ uint8_t obs[ENC_MAXB];
+  // one CTA handles 8 consecutive batches of one chunk
+  const uint32_t groups_per_chunk = (batches_per_chunk + 7) / 8;
+  const uint32_t c = blockIdx.x / groups_per_chunk, grp = blockIdx.x % groups_per_chunk;
+  const uint64_t cs = ep.chunk_starts[c], ce = ep.chunk_starts[c + 1];
+  const bool fb = chunks[c].fallback != 0;
+  if (fb && v > 0) return;
+  const uint64_t sb = fb ? cs : stored_begin(cs, ce, v == 0 ? ep.order : 0);
+  const uint32_t n = uint32_t(ce - sb);
+  const uint32_t b = grp * 8 + (threadIdx.x >> 5);
+  const VarPlan& plan = plans[size_t(c) * MAX_VARS + v];
+  const uint32_t n_bins = fb ? 1 : plan.n_bins;
+  for (int i = threadIdx.x; i < int(n_bins); i += BIN_THREADS) {
+    lowers[i] = fb ? 0 : plan.lower[i];
+    obs[i] = fb ? uint8_t(LT<L>::BITS) : plan.ob[i];
+  }
+  __syncthreads();
+  if (uint64_t(b) * BATCH_N >= n) return;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cnt = min(uint32_t(BATCH_N), n - b * BATCH_N);
+  uint32_t search_log = n_bins <= 1 ? 0 : (32 - __clz(n_bins - 1));
+  uint32_t bits = 0;
+  uint32_t packed[2] = {0, 0};
+#pragma unroll
+  for (int e = 0; e < 8; e++) {
+    uint32_t i = lane * 8 + e;
+    uint32_t sidx = 0;
+    if (i < cnt) {
+      uint64_t g = sb + uint64_t(b) * BATCH_N + i;
+      uint64_t l = fb ? uint64_t(fallback_latent<L>(ep, g)) : uint64_t(lat[g]);
+      // compression_table.rs:51-74: balanced search over lowers padded with MAX, then clamp
+      for (uint32_t depth = 0; depth < search_log; depth++) {
+        uint32_t bis = 1u << (search_log - 1 - depth);
+        uint32_t cand = sidx + bis;
+        // padding entries (L::MAX in the reference) can only move the index past n_bins - 1, which the clamp undoes
+        bool ge = cand < n_bins && l >= lowers[cand];
+        sidx += ge ? bis : 0;
+      }
+      if (n_bins > 0) sidx = min(sidx, n_bins - 1);
+      bits += obs[sidx];
+    }
+    packed[e >> 2] |= sidx << (8 * (e & 3));
+  }
+  uint8_t* row = sym + sb + uint64_t(b) * BATCH_N;  // symbol array is indexed like the input
+  // 8 symbols per lane; stores are 1-byte aligned in general (sb need not be 8-aligned)
+#pragma unroll
+  for (int e = 0; e < 8; e++) {
+    uint32_t i = lane * 8 + e;
+    if (i < cnt) row[i] = uint8_t(packed[e >> 2] >> (8 * (e & 3)));
+  }
+  for (int d = 16; d > 0; d >>= 1) bits += __shfl_xor_sync(0xffffffffu, bits, d);
+  if (lane == 0) ob_sum[(size_t(c) * MAX_VARS + v) * batches_per_chunk + b] = bits;
+}
+
+// ---------------------------------------------------------------------------
+// K4: reverse tANS.  One warp per (chunk, var); lanes 0-3 carry the 4 interleaved states over the whole page
+// (latency-bound serial chains); all lanes stage symbols in and results out.
+// Output per latent: u16 = ans_val | (1 << ans_bits)  (length-prefixed, ans_bits <= 14)
+// ---------------------------------------------------------------------------
+constexpr int ANS_THREADS = 32;
+
+struct AnsSmem {
+  uint64_t syminfo[ENC_MAXB];
+  uint16_t next_states[1 << ENC_MAX_SIZE_LOG];
+  uint8_t sym[2][BATCH_N];
+  uint16_t out[BATCH_N];
+};
+
+__global__ void __launch_bounds__(ANS_THREADS) ans_encode_kernel(EncParams ep, uint32_t batches_per_chunk, const VarPlan* __restrict__ plans,
+                                                                  ChunkEnc* __restrict__ chunks, const uint8_t* __restrict__ sym0,
+                                                                  const uint8_t* __restrict__ sym1, uint16_t* __restrict__ ans0,
+                                                                  uint16_t* __restrict__ ans1, uint32_t* __restrict__ ans_sum,
+                                                                  BatchEntry* __restrict__ entries) {
+  __shared__ AnsSmem sm;
+  const uint32_t c = blockIdx.x / MAX_VARS, v = blockIdx.x % MAX_VARS;
+  if (v >= ep.n_vars) return;
+  const int lane = threadIdx.x;
+  const uint64_t cs = ep.chunk_starts[c], ce = ep.chunk_starts[c + 1];
+  const bool fb = chunks[c].fallback != 0;
+  if (fb && v > 0) return;
+  const uint64_t sb = fb ? cs : stored_begin(cs, ce, v == 0 ? ep.order : 0);
+  const uint32_t n = uint32_t(ce - sb);
+  const uint32_t n_page = uint32_t(ce - cs);
+  const uint32_t nb_page = n_batches_of(n_page);
+  const VarPlan& plan = plans[size_t(c) * MAX_VARS + v];
+  const uint32_t n_bins = fb ? 1 : plan.n_bins;
+  const uint32_t size_log = fb ? 0 : plan.size_log;
+  const uint32_t size = 1u << size_log;
+  uint32_t* sums = ans_sum + (size_t(c) * MAX_VARS + v) * batches_per_chunk;
+  BatchEntry* ent = entries + (size_t(c) * MAX_VARS + v) * batches_per_chunk;
+  if (size_log == 0) {
+    // one symbol: no ANS bits, states stay at the default (chunk_latent_compressor.rs:103-108)
+    for (uint32_t b = lane; b < nb_page; b += 32) {
+      sums[b] = 0;
+      BatchEntry e; e.bit_pos = 0; e.st[0] = e.st[1] = e.st[2] = e.st[3] = 0;
+      ent[b] = e;
+    }
+    if (lane < 4) chunks[c].final_state[v][lane] = 0;
+    return;
+  }
+  for (uint32_t i = lane; i < n_bins; i += 32) sm.syminfo[i] = plan.syminfo[i];
+  for (uint32_t i = lane; i < size; i += 32) sm.next_states[i] = plan.next_states[i];
+  const uint32_t nb = n_batches_of(n);
+  // batches past the var's stored range (e.g. the last page batch of a delta'd var): no symbols
+  for (uint32_t b = nb + lane; b < nb_page; b += 32) sums[b] = 0;
+  uint32_t state = size;  // encoder.default_state()
+  const uint8_t* symp = (v == 0 ? sym0 : sym1) + sb;
+  uint16_t* ansp = (v == 0 ? ans0 : ans1) + sb;
+  auto load_batch = [&](uint32_t b, int buf) {
+    uint32_t cnt = min(uint32_t(BATCH_N), n - b * BATCH_N);
+    for (uint32_t i = lane; i < cnt; i += 32) sm.sym[buf][i] = symp[uint64_t(b) * BATCH_N + i];
+  };
+  if (nb > 0) load_batch(nb - 1, (nb - 1) & 1);
+  __syncwarp();
+  for (uint32_t bb = nb; bb-- > 0;) {
+    const int buf = bb & 1;
+    const uint32_t cnt = min(uint32_t(BATCH_N), n - bb * BATCH_N);
+    if (bb > 0) load_batch(bb - 1, (bb - 1) & 1);  // prefetch the next (earlier) batch
+    uint32_t bits_total = 0;
+    if (lane < 4) {
+      // lane j encodes symbols i = j (mod 4), i descending (chunk_latent_compressor.rs:110-131)
+      int i = int(cnt) - 1;
+      i -= ((i - lane) % 4 + 4) % 4;  // largest i <= cnt-1 with i % 4 == lane
+      for (; i >= 0; i -= 4) {
+        uint64_t info = sm.syminfo[sm.sym[buf][i]];
+        uint32_t cutoff = uint32_t(info & 0xffff), min_renorm = uint32_t(info >> 16) & 0xff;
+        uint32_t w = uint32_t(info >> 24) & 0xffff, cum = uint32_t(info >> 40) & 0xffff;
+        uint32_t bits = min_renorm + (state >= cutoff ? 1u : 0u);
+        sm.out[i] = uint16_t((state & ((1u << bits) - 1)) | (1u << bits));
+        bits_total += bits;
+        state = size + sm.next_states[cum + (state >> bits) - w];
+      }
+    }
+    __syncwarp();
+    // decoder state at the START of batch bb == encoder state after encoding it (side index)
+    uint32_t s0 = __shfl_sync(0xffffffffu, state, 0), s1 = __shfl_sync(0xffffffffu, state, 1);
+    uint32_t s2 = __shfl_sync(0xffffffffu, state, 2), s3 = __shfl_sync(0xffffffffu, state, 3);
+    bits_total += __shfl_xor_sync(0xffffffffu, bits_total, 1);
+    bits_total += __shfl_xor_sync(0xffffffffu, bits_total, 2);
+    if (lane == 0) {
+      sums[bb] = bits_total;
+      BatchEntry e;
+      e.bit_pos = 0;
+      e.st[0] = uint16_t(s0 - size); e.st[1] = uint16_t(s1 - size); e.st[2] = uint16_t(s2 - size); e.st[3] = uint16_t(s3 - size);
+      ent[bb] = e;
+    }
+    for (uint32_t i = lane; i < cnt; i += 32) ansp[uint64_t(bb) * BATCH_N + i] = sm.out[i];
+    __syncwarp();
+  }
+  if (lane < 4) chunks[c].final_state[v][lane] = state - size;
+  // page batches beyond the stored range inherit the state at the end of the stream
+  for (uint32_t b = nb + lane; b < nb_page; b += 32) {
+    BatchEntry e; e.bit_pos = 0; e.st[0] = e.st[1] = e.st[2] = e.st[3] = 0;
+    // the decoder never reads symbols there; states are irrelevant but keep them well-defined
+    ent[b] = e;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// layout_kernel: one CTA per chunk.  Exclusive scan over (batch, var) bit sizes -> side-index bit positions,
+// meta / page sizes, chunk byte size.
+// ---------------------------------------------------------------------------
+constexpr int LAYOUT_THREADS = 256;
+
+__global__ void __launch_bounds__(LAYOUT_THREADS) layout_kernel(EncParams ep, uint32_t batches_per_chunk, const VarPlan* __restrict__ plans,
+                                                                 ChunkEnc* __restrict__ chunks, const uint32_t* __restrict__ ans_sum,
+                                                                 const uint32_t* __restrict__ ob_sum, BatchEntry* __restrict__ entries) {
+  __shared__ uint64_t warp_tot[LAYOUT_THREADS / 32];
+  __shared__ uint64_t carry;
+  const uint32_t c = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t lbits = nt_bits(ep.dtype);
+  const uint64_t n = ep.chunk_starts[c + 1] - ep.chunk_starts[c];
+  const bool fb = chunks[c].fallback != 0;
+  const uint32_t n_vars = fb ? 1 : ep.n_vars;
+  const uint32_t order = fb ? 0 : ep.order;
+  const uint32_t mode = fb ? MODE_CLASSIC : ep.mode;
+  const uint32_t nb = n_batches_of(uint32_t(n));
+  // meta and page-meta sizes (metadata/chunk.rs:176-189, page.rs:22-34)
+  uint32_t meta_bits = 4 + mode_payload_bits(mode, lbits) + 4 + (order > 0 ? 4 : 0);
+  uint32_t page_meta_bits = 0;
+  for (uint32_t v = 0; v < n_vars; v++) {
+    const VarPlan& p = plans[size_t(c) * MAX_VARS + v];
+    uint32_t n_bins = fb ? 1 : p.n_bins, size_log = fb ? 0 : p.size_log;
+    meta_bits += var_meta_bits(n_bins, size_log, lbits);
+    page_meta_bits += 4 * size_log + lbits * (v == 0 ? order : 0);
+  }
+  const uint32_t meta_bytes = (meta_bits + 7) / 8, page_meta_bytes = (page_meta_bits + 7) / 8;
+  const uint64_t body_bit0 = uint64_t(4 + meta_bytes + page_meta_bytes) * 8;  // relative to the chunk's type byte
+  if (tid == 0) carry = 0;
+  __syncthreads();
+  // items in stream order: item = b * n_vars + v; size = ans bits + offset bits of that (batch, var)
+  const uint32_t n_items = nb * n_vars;
+  for (uint32_t base = 0; base < n_items; base += LAYOUT_THREADS) {
+    uint32_t item = base + tid;
+    uint64_t sz = 0;
+    uint32_t b = 0, v = 0;
+    if (item < n_items) {
+      b = item / n_vars; v = item % n_vars;
+      size_t k = (size_t(c) * MAX_VARS + v) * batches_per_chunk + b;
+      const VarPlan& p = plans[size_t(c) * MAX_VARS + v];
+      bool trivial_ans = fb || p.n_bins <= 1;
+      sz = uint64_t(trivial_ans ? 0 : ans_sum[k]) + ob_sum[k];
+    }
+    uint64_t inc = sz;
+    for (int d = 1; d < 32; d <<= 1) {
+      uint64_t o = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += o;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    uint64_t wbase = carry;
+    for (int w = 0; w < warp; w++) wbase += warp_tot[w];
+    if (item < n_items) {
+      size_t k = (size_t(c) * MAX_VARS + v) * batches_per_chunk + b;
+      entries[k].bit_pos = uint32_t(body_bit0 + wbase + inc - sz);
+    }
+    __syncthreads();
+    if (tid == LAYOUT_THREADS - 1) carry = wbase + inc;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    uint64_t body_bits = carry;
+    chunks[c].meta_bytes = meta_bytes;
+    chunks[c].page_meta_bytes = page_meta_bytes;
+    chunks[c].body_bits = body_bits;
+    chunks[c].chunk_bytes = 4 + meta_bytes + page_meta_bytes + (body_bits + 7) / 8;
+  }
+}
+
+// exclusive scan of chunk sizes -> output offsets (one CTA; chunk counts are small)
+__global__ void chunk_offsets_kernel(ChunkEnc* chunks, uint32_t n_chunks, uint64_t header_bytes, uint64_t* total_bytes) {
+  __shared__ uint64_t part[1024];
+  const int tid = threadIdx.x;
+  uint32_t per = (n_chunks + blockDim.x - 1) / blockDim.x;
+  uint32_t lo = min(n_chunks, tid * per), hi = min(n_chunks, lo + per);
+  uint64_t s = 0;
+  for (uint32_t c = lo; c < hi; c++) s += chunks[c].chunk_bytes;
+  part[tid] = s;
+  __syncthreads();
+  if (tid == 0) {
+    uint64_t acc = header_bytes;
+    for (uint32_t t = 0; t < blockDim.x; t++) { uint64_t x = part[t]; part[t] = acc; acc += x; }
+    *total_bytes = acc + 1;  // + terminator byte
+  }
+  __syncthreads();
+  uint64_t off = part[tid];
+  for (uint32_t c = lo; c < hi; c++) { chunks[c].out_offset = off; off += chunks[c].chunk_bytes; }
+}
+
+// ---------------------------------------------------------------------------
+// K5: pack.  One CTA per chunk writes the chunk's bytes [out_offset, out_offset + chunk_bytes) with plain stores.
+// Bits are OR-ed into a zeroed shared-memory staging window (32-bit atomics), then copied out; partial bytes at
+// window boundaries are carried in shared memory, so no global atomics or pre-zeroed output are needed.
+// ---------------------------------------------------------------------------
+constexpr int PACK_THREADS = 256;
+constexpr int PACK_WINDOW_WORDS = 8192;  // 32 KiB staging window
+
+struct PackSmem {
+  uint32_t win[PACK_WINDOW_WORDS + 4];
+  uint64_t lowers[MAX_VARS][ENC_MAXB];
+  uint8_t obs[MAX_VARS][ENC_MAXB];
+};
+
+// OR `nbits` (<= 64) of `val` at bit position `pos` (relative to the window start) into the window
+__device__ __forceinline__ void win_or(uint32_t* win, uint32_t pos, uint64_t val, uint32_t nbits) {
+  if (nbits == 0) return;
+  if (nbits < 64) val &= (uint64_t(1) << nbits) - 1;
+  uint32_t w = pos >> 5, r = pos & 31;
+  uint32_t lo = uint32_t(val) << r;
+  if (lo) atomicOr(&win[w], lo);
+  uint64_t rest = r ? (val >> (32 - r)) : (val >> 32);
+  if (r + nbits > 32) {
+    uint32_t mid = uint32_t(rest);
+    if (mid) atomicOr(&win[w + 1], mid);
+    if (r + nbits > 64) {
+      uint32_t hi = uint32_t(rest >> 32);
+      if (hi) atomicOr(&win[w + 2], hi);
+    }
+  }
+}
+
+template <typename L>
+__global__ void __launch_bounds__(PACK_THREADS) pack_kernel(EncParams ep, uint32_t batches_per_chunk, const L* __restrict__ lat0, const L* __restrict__ lat1,
+                                                             const VarPlan* __restrict__ plans, const ChunkEnc* __restrict__ chunks,
+                                                             const uint8_t* __restrict__ sym0, const uint8_t* __restrict__ sym1,
+                                                             const uint16_t* __restrict__ ans0, const uint16_t* __restrict__ ans1,
+                                                             const BatchEntry* __restrict__ entries, uint8_t* __restrict__ out, uint64_t out_cap) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  PackSmem& sm = *reinterpret_cast<PackSmem*>(smem_raw);
+  const uint32_t c = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const ChunkEnc& ch = chunks[c];
+  if (ch.out_offset + ch.chunk_bytes > out_cap) return;  // host reports the Io error from the total size
+  const uint64_t cs = ep.chunk_starts[c], ce = ep.chunk_starts[c + 1];
+  const uint32_t n = uint32_t(ce - cs);
+  const uint32_t lbits = LT<L>::BITS;
+  const bool fb = ch.fallback != 0;
+  const uint32_t n_vars = fb ? 1 : ep.n_vars;
+  const uint32_t order = fb ? 0 : ep.order;
+  const uint32_t mode = fb ? MODE_CLASSIC : ep.mode;
+  const uint32_t nb = n_batches_of(n);
+  uint8_t* dst = out + ch.out_offset;
+  for (uint32_t v = 0; v < n_vars; v++) {
+    const VarPlan& p = plans[size_t(c) * MAX_VARS + v];
+    uint32_t n_bins = fb ? 1 : p.n_bins;
+    for (uint32_t i = tid; i < n_bins; i += PACK_THREADS) {
+      sm.lowers[v][i] = fb ? 0 : p.lower[i];
+      sm.obs[v][i] = fb ? uint8_t(lbits) : p.ob[i];
+    }
+  }
+  // ---------------- head window: preamble + chunk meta + page meta ----------------
+  const uint32_t head_bytes = 4 + ch.meta_bytes + ch.page_meta_bytes;
+  for (uint32_t i = tid; i < (head_bytes + 3) / 4 + 2; i += PACK_THREADS) sm.win[i] = 0;
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t pos = 0;
+    win_or(sm.win, pos, ep.dtype, 8); pos += 8;
+    win_or(sm.win, pos, n - 1, 24); pos += 24;
+    win_or(sm.win, pos, mode, 4); pos += 4;
+    if (mode == MODE_INT_MULT || mode == MODE_FLOAT_MULT) { win_or(sm.win, pos, ep.mode_base, lbits); pos += lbits; }
+    if (mode == MODE_FLOAT_QUANT) { win_or(sm.win, pos, ep.mode_k, 8); pos += 8; }
+    if (order > 0) { win_or(sm.win, pos, 1, 4); win_or(sm.win, pos + 4, order, 3); pos += 8; }  // Consecutive, secondary_uses_delta = 0
+    else { pos += 4; }
+    // page meta (metadata/page_latent_var.rs:19-26): moments, then 4 final state indices per var
+    uint32_t ppos = (4 + ch.meta_bytes) * 8;
+    for (uint32_t v = 0; v < n_vars; v++) {
+      const VarPlan& p = plans[size_t(c) * MAX_VARS + v];
+      uint32_t size_log = fb ? 0 : p.size_log;
+      if (v == 0) for (uint32_t k = 0; k < order; k++) { win_or(sm.win, ppos, ch.moments[0][k], lbits); ppos += lbits; }
+      for (int j = 0; j < 4; j++) { win_or(sm.win, ppos, ch.final_state[v][j], size_log); ppos += size_log; }
+    }
+  }
+  {
+    // bins of every var, in parallel (metadata/chunk_latent_var.rs:55-71)
+    uint32_t pos = 32 + 4 + mode_payload_bits(mode, lbits) + 4 + (order > 0 ? 4 : 0);
+    for (uint32_t v = 0; v < n_vars; v++) {
+      const VarPlan& p = plans[size_t(c) * MAX_VARS + v];
+      uint32_t n_bins = fb ? 1 : p.n_bins, size_log = fb ? 0 : p.size_log;
+      uint32_t stride = size_log + lbits + offset_bits_bits(lbits);
+      if (tid == 0) { win_or(sm.win, pos, size_log, 4); win_or(sm.win, pos + 4, n_bins, 15); }
+      pos += 19;
+      for (uint32_t i = tid; i < n_bins; i += PACK_THREADS) {
+        uint32_t bp = pos + i * stride;
+        uint32_t w = fb ? 1 : p.weight[i];
+        win_or(sm.win, bp, w - 1, size_log);
+        win_or(sm.win, bp + size_log, sm.lowers[v][i], lbits);
+        win_or(sm.win, bp + size_log + lbits, sm.obs[v][i], offset_bits_bits(lbits));
+      }
+      pos += n_bins * stride;
+    }
+  }
+  __syncthreads();
+  {
+    const uint8_t* wb = reinterpret_cast<const uint8_t*>(sm.win);
+    for (uint32_t i = tid; i < head_bytes; i += PACK_THREADS) dst[i] = wb[i];
+  }
+  __syncthreads();
+  // ---------------- body: windows of whole batches ----------------
+  const uint64_t body_bit0 = uint64_t(head_bytes) * 8;
+  const uint64_t body_end = body_bit0 + ch.body_bits;
+  auto entry_pos = [&](uint32_t b, uint32_t v) -> uint64_t {
+    return entries[(size_t(c) * MAX_VARS + v) * batches_per_chunk + b].bit_pos;
+  };
+  uint32_t carry_byte = 0;  // partially filled last byte of the previous window (only thread 0's copy is used)
+  __shared__ uint32_t s_carry;
+  if (tid == 0) s_carry = 0;
+  uint32_t b0 = 0;
+  uint64_t win_bit0 = body_bit0;  // multiple of 8
+  while (b0 < nb) {
+    // choose b1 > b0 so that [start(b0), end(b1 - 1)) fits the window; a single batch always fits (<= 2*256*78 bits)
+    uint32_t b1 = b0 + 1;
+    const uint64_t win_cap_bits = uint64_t(PACK_WINDOW_WORDS) * 32 - 64;
+    while (b1 < nb) {
+      uint64_t endb = (b1 + 1 < nb) ? entry_pos(b1 + 1, 0) : body_end;
+      if (endb - win_bit0 > win_cap_bits) break;
+      b1++;
+    }
+    const uint64_t win_end_bit = (b1 < nb) ? entry_pos(b1, 0) : body_end;
+    const uint32_t win_words = uint32_t((win_end_bit - win_bit0 + 31) / 32) + 1;
+    for (uint32_t i = tid; i < win_words; i += PACK_THREADS) sm.win[i] = 0;
+    __syncthreads();
+    if (tid == 0 && s_carry) sm.win[0] = s_carry;
+    __syncthreads();
+    for (uint32_t bv = (b0 * n_vars) + warp; bv < b1 * n_vars; bv += PACK_THREADS / 32) {
+      const uint32_t b = bv / n_vars, v = bv % n_vars;
+      const VarPlan& p = plans[size_t(c) * MAX_VARS + v];
+      const uint32_t ord_v = v == 0 ? order : 0;
+      const uint64_t sb = fb ? cs : stored_begin(cs, ce, ord_v);
+      const uint32_t stored = uint32_t(ce - sb);
+      const uint32_t cnt = batch_count(stored, b);
+      if (cnt == 0) continue;
+      const bool needs_ans = !fb && p.n_bins != 1;
+      const uint32_t max_ob = fb ? lbits : p.max_ob;
+      const uint8_t* symp = (v == 0 ? sym0 : sym1) + sb + uint64_t(b) * BATCH_N;
+      const uint16_t* ansp = (v == 0 ? ans0 : ans1) + sb + uint64_t(b) * BATCH_N;
+      const L* latp = (v == 0 ? lat0 : lat1) + sb + uint64_t(b) * BATCH_N;
+      uint32_t pos = uint32_t(entry_pos(b, v) - win_bit0);
+      // --- ANS fields (chunk_latent_compressor.rs:285-297)
+      uint32_t a_val[8], a_bits[8], a_tot = 0;
+      uint32_t sy[8];
+#pragma unroll
+      for (int e = 0; e < 8; e++) {
+        uint32_t i = lane * 8 + e;
+        a_val[e] = 0; a_bits[e] = 0; sy[e] = 0;
+        if (i < cnt) {
+          sy[e] = symp[i];
+          if (needs_ans && p.size_log > 0) {
+            uint32_t x = ansp[i];
+            uint32_t nbits = 31 - __clz(x);
+            a_bits[e] = nbits;
+            a_val[e] = x ^ (1u << nbits);
+          }
+        }
+        a_tot += a_bits[e];
+      }
+      uint32_t inc = a_tot;
+      for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+      uint32_t apos = pos + inc - a_tot;
+      const uint32_t ans_total = __shfl_sync(0xffffffffu, inc, 31);
+#pragma unroll
+      for (int e = 0; e < 8; e++) { win_or(sm.win, apos, a_val[e], a_bits[e]); apos += a_bits[e]; }
+      // --- offsets (chunk_latent_compressor.rs:299-327)
+      if (max_ob > 0) {
+        uint32_t o_bits[8], o_tot = 0;
+        uint64_t o_val[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+          uint32_t i = lane * 8 + e;
+          o_bits[e] = 0; o_val[e] = 0;
+          if (i < cnt) {
+            uint64_t l = fb ? uint64_t(fallback_latent<L>(ep, sb + uint64_t(b) * BATCH_N + i)) : uint64_t(latp[i]);
+            o_bits[e] = sm.obs[v][sy[e]];
+            o_val[e] = l - sm.lowers[v][sy[e]];
+          }
+          o_tot += o_bits[e];
+        }
+        uint32_t oinc = o_tot;
+        for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, oinc, d); if (lane >= d) oinc += o; }
+        uint32_t opos = pos + ans_total + oinc - o_tot;
+#pragma unroll
+        for (int e = 0; e < 8; e++) { win_or(sm.win, opos, o_val[e], o_bits[e]); opos += o_bits[e]; }
+      }
+    }
+    __syncthreads();
+    // copy out whole bytes; the last partial byte (if any) carries into the next window
+    const uint64_t span_bits = win_end_bit - win_bit0;
+    const uint32_t whole_bytes = (b1 < nb) ? uint32_t(span_bits / 8) : uint32_t((span_bits + 7) / 8);
+    {
+      const uint8_t* wb = reinterpret_cast<const uint8_t*>(sm.win);
+      uint8_t* d = dst + (win_bit0 / 8);
+      for (uint32_t i = tid; i < whole_bytes; i += PACK_THREADS) d[i] = wb[i];
+      if (tid == 0) s_carry = (b1 < nb && (span_bits & 7)) ? uint32_t(wb[whole_bytes]) : 0;
+    }
+    __syncthreads();
+    win_bit0 += uint64_t(whole_bytes) * 8;
+    b0 = b1;
+    (void)carry_byte;
+  }
+}
+
+// standalone header + terminator (standalone/compressor.rs:85-105,157-163), written by one thread
+__global__ void header_footer_kernel(uint8_t* out, uint64_t out_cap, const uint8_t* header, uint32_t header_bytes, const uint64_t* total_bytes) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    uint64_t total = *total_bytes;
+    if (total > out_cap) return;
+    for (uint32_t i = 0; i < header_bytes; i++) out[i] = header[i];
+    out[total - 1] = 0;
+  }
+}
+
+}  // namespace pcob200

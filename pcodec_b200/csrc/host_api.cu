@@ -3,6 +3,7 @@
 // compute entry point fails with PCO_B200_CUDA.
 #include <algorithm>
 
+#include "compress_host.cuh"
 #include "decode_kernels.cuh"
 #include "host_common.hpp"
 
@@ -14,6 +15,7 @@ struct Context {
   bool device_ok = false;
   std::string device_err;
   DevBuf src, out, index, statuses, misc;
+  CompressScratch enc;
   Binoms* d_binoms = nullptr;
   int sm_count = 0;
 };
@@ -278,6 +280,59 @@ PcoB200Error pco_b200_decompress_ex(const void* compressed, size_t compressed_le
 PcoB200Error pco_b200_simple_decompress_into(const void* compressed, size_t compressed_len, unsigned char dtype, void* dst, size_t dst_len,
                                              PcoB200Progress* progress) {
   return pco_b200_decompress_ex(compressed, compressed_len, dtype, dst, dst_len, progress, nullptr, 0, 0, nullptr);
+}
+
+static PcoB200Error compress_dispatch(const void* nums, size_t n, unsigned char dtype, const PcoB200ChunkConfig* config, bool uniform, void* dst,
+                                      size_t dst_cap, size_t* n_written, void* index, size_t index_cap, size_t* index_len, uint32_t flags,
+                                      void* cuda_stream) {
+  if (!nt_valid(dtype)) return fail(PCO_B200_INVALID_TYPE, "unknown number type byte: " + std::to_string(dtype));
+  PcoB200ChunkConfig cfg;
+  if (config) cfg = *config;
+  else {
+    std::memset(&cfg, 0, sizeof(cfg));  // pco::ChunkConfig::default(): level 8, Auto, Auto, EqualPagesUpTo(2^18)
+    cfg.compression_level = 8;
+  }
+  Context& c = ctx();
+  std::lock_guard<std::mutex> lock(c.mu);
+  if (PcoB200Error e = ensure_device(c)) return e;
+  CompressResult res;
+  PcoB200Error e = dispatch_latent(dtype, [&](auto tag) {
+    using L = decltype(tag);
+    return compress_typed<L>(c.enc, nums, n, dtype, cfg, uniform, dst, dst_cap, index, index_cap, flags, static_cast<cudaStream_t>(cuda_stream), &res);
+  });
+  if (e != PCO_B200_OK) return e;
+  if (n_written) *n_written = size_t(res.total_bytes);
+  if (index_len) *index_len = size_t(res.index_bytes);
+  return PCO_B200_OK;
+}
+
+PcoB200Error pco_b200_compress_ex(const void* nums, size_t n, unsigned char dtype, const PcoB200ChunkConfig* config, int uniform_type_header,
+                                  void* dst, size_t dst_cap, size_t* n_written, void* index, size_t index_cap, size_t* index_len, uint32_t flags,
+                                  void* cuda_stream) {
+  return compress_dispatch(nums, n, dtype, config, uniform_type_header != 0, dst, dst_cap, n_written, index, index_cap, index_len, flags, cuda_stream);
+}
+PcoB200Error pco_b200_simple_compress(const void* nums, size_t n, unsigned char dtype, const PcoB200ChunkConfig* config, void* dst, size_t dst_cap,
+                                      size_t* n_written) {
+  return compress_dispatch(nums, n, dtype, config, false, dst, dst_cap, n_written, nullptr, 0, nullptr, 0, nullptr);
+}
+PcoB200Error pco_b200_simple_compress_into(const void* nums, size_t n, unsigned char dtype, const PcoB200ChunkConfig* config, void* dst,
+                                           size_t dst_cap, size_t* n_written) {
+  return compress_dispatch(nums, n, dtype, config, true, dst, dst_cap, n_written, nullptr, 0, nullptr, 0, nullptr);
+}
+
+// pco_c/src/lib.rs:76-96,146-169: Auto mode / Auto delta, enable_8_bit, uniform-type header
+enum PcoError pco_standalone_simple_compress_into(const void* nums, size_t n, unsigned char dtype, const struct PcoChunkConfig* config, void* dst,
+                                                  size_t dst_cap, size_t* n_written) {
+  if (!nt_valid(dtype)) return PcoInvalidType;
+  PcoB200ChunkConfig cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.compression_level = config ? config->compression_level : 8;
+  cfg.max_page_n = config ? config->max_page_n : 0;
+  cfg.mode_spec = PCO_B200_MODE_AUTO;
+  cfg.delta_spec = PCO_B200_DELTA_AUTO;
+  cfg.enable_8_bit = 1;
+  PcoB200Error e = compress_dispatch(nums, n, dtype, &cfg, true, dst, dst_cap, n_written, nullptr, 0, nullptr, 0, nullptr);
+  return e == PCO_B200_OK ? PcoSuccess : PcoCompressionError;
 }
 
 size_t pco_b200_index_size_bound(size_t n, size_t n_chunks_hint) {

@@ -113,3 +113,49 @@ def peek_dtype(src):
     if t not in _lib.BYTE_TO_NP:
         raise PcoError("Corruption", f"peeked unknown number type byte: {t}")
     return _lib.BYTE_TO_NP[t]
+
+
+def _compress(nums, config, uniform_type, want_index):
+    L = _lib.lib()
+    arr = np.ascontiguousarray(nums)
+    dt = _lib.dtype_byte(arr.dtype)
+    cfg = (config or ChunkConfig())._to_c()
+    cap = L.pco_standalone_guarantee_file_size(arr.size, dt)
+    if cfg.paging_spec == 1 or (cfg.max_page_n and cfg.max_page_n < (1 << 18)):
+        # the guarantee above assumes default paging; small pages add a per-chunk meta allowance
+        n_pages = cfg.n_exact_pages if cfg.paging_spec == 1 else -(-arr.size // max(cfg.max_page_n, 1))
+        cap += int(n_pages) * 160
+    dst = np.empty(cap, dtype=np.uint8)
+    n_written = C.c_size_t()
+    if want_index:
+        icap = L.pco_b200_index_size_bound(arr.size, max(arr.size >> 8, 64))
+        if cfg.paging_spec == 1 or cfg.max_page_n:
+            icap += 64 * (int(cfg.n_exact_pages) if cfg.paging_spec == 1 else -(-arr.size // max(cfg.max_page_n, 1)))
+        idx = np.empty(icap, dtype=np.uint8)
+        ilen = C.c_size_t()
+        iptr, icap_c, ilen_p = idx.ctypes.data_as(C.c_void_p), C.c_size_t(icap), C.byref(ilen)
+    else:
+        idx, ilen, iptr, icap_c, ilen_p = None, None, None, C.c_size_t(0), None
+    rc = L.pco_b200_compress_ex(arr.ctypes.data_as(C.c_void_p), C.c_size_t(arr.size), C.c_ubyte(dt), C.byref(cfg),
+                                C.c_int(1 if uniform_type else 0), dst.ctypes.data_as(C.c_void_p), C.c_size_t(cap), C.byref(n_written),
+                                iptr, icap_c, ilen_p, C.c_uint32(0), None)
+    _lib.check(rc)
+    out = dst[: n_written.value].tobytes()
+    if want_index:
+        return out, idx[: ilen.value].tobytes()
+    return out
+
+
+def simple_compress(nums, config=None):
+    """pcodec.standalone.simple_compress (pco_python/src/standalone.rs:44-88; pco/src/standalone/simple.rs:58-91)."""
+    return _compress(nums, config, False, False)
+
+
+def simple_compress_into(nums, config=None):
+    """pco::standalone::simple_compress_into flavour (uniform-type header, pco/src/standalone/simple.rs:22-48)."""
+    return _compress(nums, config, True, False)
+
+
+def simple_compress_with_index(nums, config=None, uniform_type=False):
+    """simple_compress plus the per-batch side index the GPU decoder uses (metadata beside the .pco bytes)."""
+    return _compress(nums, config, uniform_type, True)
