@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py — the hot-path benchmark (BASELINE.json metric: compress+decompress MB/s, % HBM roofline).
+
+A "step" is one pass of the hot path over one batch of synthetic input: compress, then decompress, 1024 independent
+chunks of 2^18 u64 (BASELINE config 2: classic mode, consecutive delta order 1; C2(i) data).  Per rank, N ranks = weak
+scaling (8 ranks = config 4's 8192 chunks).  MB = 10^6 uncompressed bytes (pco_cli/src/bench/mod.rs:233-241).
+
+  value     resident: inputs already in HBM, device buffers in and out, through the C-ABI (*_ex, flags DEVICE).
+  e2e       same calls with pinned HOST buffers (H2D of the inputs and D2H of the results inside the timed region).
+  roofline  decode_kernel: (U + C + side index) bytes / its CUDA-event duration vs MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline / --impl reference: oracle/ (C++ restatement of pco 1.0.3; the Rust reference cannot be built here)
+            on the host cores, on a bounded sample of the same chunks.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CHUNK_N = 1 << 18
+N_CHUNKS = 1024
+METRIC = "compress+decompress MB/s per chunk (u64, 2^18 elems)"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--chunks", type=int, default=N_CHUNKS, help="chunks per rank (default: BASELINE config 2)")
+    ap.add_argument("--cpu-sample-chunks", type=int, default=32)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores (the one place bench.py may execute oracle/)
+# ------------------------------------------------------------------------------------------------
+def cpu_roundtrip(n_chunks, threads, repeats=1):
+    """Compress + decompress `n_chunks` C2(i) chunks with the oracle, one chunk per task over `threads` threads.
+    Returns (MB/s round trip, compress MB/s, decompress MB/s, compressed bytes)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import pyoracle
+    from pcodec_b200 import datagen
+
+    cfg = pyoracle.make_config(level=8, mode=pyoracle.MODE_CLASSIC, delta=pyoracle.DELTA_CONSECUTIVE, delta_order=1)
+    chunks = [datagen.c2_u64_cumsum_geometric(CHUNK_N, seed=i) for i in range(n_chunks)]
+    pyoracle.lib()
+    best = None
+    for _ in range(repeats):
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            t0 = time.perf_counter()
+            comp = list(ex.map(lambda x: pyoracle.simple_compress(x, cfg), chunks))
+            t1 = time.perf_counter()
+            dec = list(ex.map(lambda d: pyoracle.simple_decompress(d, np.uint64), comp))
+            t2 = time.perf_counter()
+        assert all(np.array_equal(a, b) for a, b in zip(dec, chunks)), "oracle round trip mismatch"
+        mb = n_chunks * CHUNK_N * 8 / 1e6
+        cur = (mb / (t2 - t0), mb / (t1 - t0), mb / (t2 - t1), sum(len(c) for c in comp))
+        if best is None or cur[0] > best[0]:
+            best = cur
+    return best
+
+
+def run_reference_arm(args, rank):
+    """--impl reference: the reference's own CPU path of the same workload.  pco is Rust and there is no cargo/rustc in the
+    image, so this runs the oracle port and says so (cpu_baseline.kind = "port")."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = max(threads, min(args.cpu_sample_chunks, 64))
+    for _ in range(args.warmup):
+        cpu_roundtrip(min(sample, threads), threads)
+    vals, t0 = [], time.perf_counter()
+    for _ in range(args.steps):
+        vals.append(cpu_roundtrip(sample, threads))
+    ms = (time.perf_counter() - t0) * 1e3 / max(args.steps, 1)
+    v = float(np.median([x[0] for x in vals]))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "MB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "C2: 2^18-element u64 chunks, classic, consecutive delta order 1, level 8 (cumsum of geometric(0.001))",
+                   "chunks_per_step": sample, "chunk_n": CHUNK_N},
+        "cpu_baseline": {"value": v, "unit": "MB/s", "cores": threads, "kind": "port",
+                         "sample": f"{sample} chunks of 2^18 u64 per step, one chunk per thread; C++ restatement of pco 1.0.3 (oracle/), not the Rust crate",
+                         "compress_mb_s": float(np.median([x[1] for x in vals])), "decompress_mb_s": float(np.median([x[2] for x in vals]))},
+        "e2e": {"value": v, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu_index = gpu_index
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.gpu_index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm, smax, reasons = [], 0, set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                smax = max(smax, float(s[1]))
+                for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], s[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def parse_profile(L):
+    buf = C.create_string_buffer(4096)
+    L.pco_b200_profile_last(buf, C.c_size_t(4096))
+    out = {}
+    for item in buf.value.decode().split(";"):
+        if "=" in item:
+            k, v = item.split("=")
+            out[k] = out.get(k, 0.0) + float(v)
+    return out
+
+
+def run_gpu_arm(args, rank, world):
+    import torch
+
+    from pcodec_b200 import ChunkConfig, DeltaSpec, ModeSpec, _lib, datagen
+
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+    if not L.pco_b200_device_available():
+        raise RuntimeError("libcpcodec.so found no usable CUDA device: " + L.pco_b200_last_error_message().decode())
+
+    n_chunks = args.chunks
+    n = n_chunks * CHUNK_N
+    U = n * 8
+    cfg = ChunkConfig(compression_level=8, mode_spec=ModeSpec.classic(), delta_spec=DeltaSpec.try_consecutive(1))._to_c()
+    nums = datagen.c2_u64_torch(n_chunks, CHUNK_N, seed=1000 + rank, device=dev)
+    cap = L.pco_standalone_guarantee_file_size(n, 2)
+    icap = L.pco_b200_index_size_bound(n, n_chunks)
+    d_comp = torch.empty(cap, dtype=torch.uint8, device=dev)
+    d_index = torch.empty(icap, dtype=torch.uint8, device=dev)
+    d_out = torch.empty(n, dtype=torch.int64, device=dev)
+    stream = torch.cuda.current_stream()
+    sp = C.c_void_p(stream.cuda_stream)
+    SRC, DST, IDX = 1, 2, 4
+    n_written, ilen = C.c_size_t(), C.c_size_t()
+    prog = _lib._CProgress()
+
+    def compress_resident():
+        rc = L.pco_b200_compress_ex(C.c_void_p(nums.data_ptr()), C.c_size_t(n), C.c_ubyte(2), C.byref(cfg), C.c_int(0), C.c_void_p(d_comp.data_ptr()),
+                                    C.c_size_t(cap), C.byref(n_written), C.c_void_p(d_index.data_ptr()), C.c_size_t(icap), C.byref(ilen),
+                                    C.c_uint32(SRC | DST | IDX), sp)
+        _lib.check(rc)
+
+    def decompress_resident():
+        rc = L.pco_b200_decompress_ex(C.c_void_p(d_comp.data_ptr()), n_written, C.c_ubyte(2), C.c_void_p(d_out.data_ptr()), C.c_size_t(n), C.byref(prog),
+                                      C.c_void_p(d_index.data_ptr()), ilen, C.c_uint32(SRC | DST | IDX), sp)
+        _lib.check(rc)
+        assert prog.n_processed == n and prog.finished
+
+    gathered = None
+
+    def gather_pages():
+        # config 4: one NCCL all-gather that concatenates the ranks' compressed pages (sizes first, then padded bytes)
+        nonlocal gathered
+        if world == 1:
+            return
+        import torch.distributed as dist
+
+        sizes = torch.zeros(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(sizes, torch.tensor([n_written.value], dtype=torch.int64, device=dev))
+        mx = int(sizes.max().item())
+        mx = (mx + 255) // 256 * 256
+        if gathered is None or gathered.numel() < world * mx:
+            gathered = torch.empty(world * mx, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(gathered[: world * mx], d_comp[:mx])
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also verifies the bit-exact round trip)
+    L.pco_b200_profile_enable(1)
+    for w in range(max(args.warmup, 3)):
+        compress_resident()
+        gather_pages()
+        decompress_resident()
+    torch.cuda.synchronize()
+    assert torch.equal(d_out, nums), "GPU round trip is not bit-exact"
+    Cbytes, Ibytes = n_written.value, ilen.value
+
+    # ---- timed region: resident
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    t_c, t_d, t_g, prof_c, prof_d = [], [], [], [], []
+    barrier()
+    ev_all0, ev_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev_all0.record(stream)
+    for _ in range(args.steps):
+        ev[0].record(stream)
+        compress_resident()
+        ev[1].record(stream)
+        prof_c.append(parse_profile(L))
+        gather_pages()
+        ev[2].record(stream)
+        decompress_resident()
+        ev[3].record(stream)
+        prof_d.append(parse_profile(L))
+        torch.cuda.synchronize()
+        t_c.append(ev[0].elapsed_time(ev[1]))
+        t_g.append(ev[1].elapsed_time(ev[2]))
+        t_d.append(ev[2].elapsed_time(ev[3]))
+    ev_all1.record(stream)
+    barrier()
+    total_ms = ev_all0.elapsed_time(ev_all1)
+    if world > 1:
+        import torch.distributed as dist
+
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / max(args.steps, 1)
+    value = world * U / 1e6 / (ms_per_step / 1e3)
+
+    # ---- e2e: the same calls with pinned host buffers (H2D / D2H inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        h_nums = torch.empty(n, dtype=torch.int64, pin_memory=True)
+        h_nums.copy_(nums)
+        h_comp = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+        h_index = torch.empty(icap, dtype=torch.uint8, pin_memory=True)
+        h_out = torch.empty(n, dtype=torch.int64, pin_memory=True)
+        nw2, il2 = C.c_size_t(), C.c_size_t()
+
+        def e2e_step():
+            rc = L.pco_b200_compress_ex(C.c_void_p(h_nums.data_ptr()), C.c_size_t(n), C.c_ubyte(2), C.byref(cfg), C.c_int(0), C.c_void_p(h_comp.data_ptr()),
+                                        C.c_size_t(cap), C.byref(nw2), C.c_void_p(h_index.data_ptr()), C.c_size_t(icap), C.byref(il2), C.c_uint32(0), sp)
+            _lib.check(rc)
+            rc = L.pco_b200_decompress_ex(C.c_void_p(h_comp.data_ptr()), nw2, C.c_ubyte(2), C.c_void_p(h_out.data_ptr()), C.c_size_t(n), C.byref(prog),
+                                          C.c_void_p(h_index.data_ptr()), il2, C.c_uint32(0), sp)
+            _lib.check(rc)
+
+        e2e_step()
+        assert torch.equal(h_out, h_nums), "e2e round trip is not bit-exact"
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2e_steps = max(1, min(args.steps, 3))
+        e0.record(stream)
+        for _ in range(e2e_steps):
+            e2e_step()
+        e1.record(stream)
+        barrier()
+        e2e_ms = e0.elapsed_time(e1) / e2e_steps
+        if world > 1:
+            import torch.distributed as dist
+
+            t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_ms = float(t.item())
+        e2e = {"value": world * U / 1e6 / (e2e_ms / 1e3), "unit": "MB/s", "h2d_bytes_per_step": int(U + nw2.value + il2.value),
+               "d2h_bytes_per_step": int(nw2.value + il2.value + U), "ms_per_step": e2e_ms,
+               "api": "pco_b200_compress_ex + pco_b200_decompress_ex (C-ABI), pinned host buffers"}
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel (decode_kernel): algorithmic bytes / CUDA-event duration
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    dk_ms = float(np.mean([p.get("decode_kernel", 0.0) for p in prof_d]))
+    alg_bytes = U + Cbytes + Ibytes
+    achieved = alg_bytes / 1e9 / (dk_ms / 1e3) if dk_ms > 0 else None
+    comp_spans = {}
+    for p in prof_c:
+        for k, v in p.items():
+            comp_spans.setdefault(k, []).append(v)
+    comp_spans = {k: float(np.mean(v)) for k, v in comp_spans.items()}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        sample = max(threads, min(args.cpu_sample_chunks, 64))
+        v = cpu_roundtrip(sample, threads)
+        cpu = {"value": v[0], "unit": "MB/s", "cores": threads, "kind": "port",
+               "sample": f"{sample} chunks of 2^18 u64 (same generator), one chunk per thread; C++ restatement of pco 1.0.3 (oracle/), not the Rust crate",
+               "compress_mb_s": v[1], "decompress_mb_s": v[2]}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "MB/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": f"C2: {n_chunks} chunks x 2^18 u64 per GPU, classic mode, consecutive delta order 1, level 8 (cumsum of geometric(0.001)); "
+                               "step = compress + decompress of every chunk, buffers resident in HBM",
+                   "chunks_per_gpu": n_chunks, "chunk_n": CHUNK_N, "l2": "inputs (2 GiB per GPU) exceed the 126 MB L2",
+                   "multi_gpu": "independent chunk shards per rank; one NCCL all-gather of compressed pages per step" if world > 1 else "single GPU",
+                   "side_index": "decompress uses the per-batch side index emitted by the compressor (bytes counted in the roofline)"},
+        "compress_mb_s": world * U / 1e6 / (float(np.mean(t_c)) / 1e3), "decompress_mb_s": world * U / 1e6 / (float(np.mean(t_d)) / 1e3),
+        "gather_ms": float(np.mean(t_g)), "compressed_bytes_per_gpu": Cbytes, "index_bytes_per_gpu": Ibytes, "ratio": U / Cbytes,
+        "kernel_ms": {"decode_kernel": dk_ms, **comp_spans},
+        "roofline": {"bound": "hbm", "kernel": "decode_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": (achieved / peak) if achieved else None, "traffic": None, "algorithmic_bytes": alg_bytes, "peak_source": peak_src},
+        "cpu_baseline": cpu, "e2e": e2e, "clocks": sampler.summary(),
+        "gpu_launches": 14,  # per step: 13 of this repo's kernels in compress (+ CUB's sort kernels) and decode_kernel
+    }
+    print(json.dumps(line))
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+    run_gpu_arm(args, rank, world)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -105,6 +105,11 @@ size_t pco_b200_index_size_bound(size_t n, size_t n_chunks_hint);
 PcoB200Error pco_b200_build_index(const void *compressed, size_t compressed_len, unsigned char dtype, void *index,
                                   size_t index_cap, size_t *index_len, uint32_t flags, void *cuda_stream);
 
+/* Measurement hooks (no reference counterpart): when enabled, every kernel launched by the next call is bracketed by
+ * CUDA events on the launching stream; pco_b200_profile_last returns "kernel=milliseconds;..." for the last call. */
+void pco_b200_profile_enable(int on);
+int pco_b200_profile_last(char *buf, size_t cap);
+
 #if defined(__cplusplus)
 }
 #endif

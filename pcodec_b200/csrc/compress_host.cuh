@@ -244,7 +244,9 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
 
   // ---- K1+K2
   init_chunks_kernel<<<(n_chunks + 255) / 256, 256, 0, stream>>>(d_chunks, n_chunks);
+  profiler().begin("split_delta_kernel", stream);
   split_delta_kernel<L><<<n_chunks * tiles_per_chunk, SPLIT_THREADS, 0, stream>>>(ep, tiles_per_chunk, d_lat[0], d_lat[1], d_chunks);
+  profiler().end(stream);
   // ---- planner per var: range-reduced keys -> segmented radix sort over the significant bits -> plan
   static bool plan_attr_set = false;
   if (!plan_attr_set) {
@@ -259,7 +261,9 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
     uint32_t range_bits = 0;
     PCOB_CUDA_TRY(cudaMemcpyAsync(&range_bits, d_small, 4, cudaMemcpyDeviceToHost, stream));
     PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
-    sort_keys_kernel<L><<<n_chunks * tiles_per_chunk, 256, 0, stream>>>(ep, tiles_per_chunk, d_lat[v], S.keys_a.as<L>(), d_chunks, int(v));
+    profiler().begin("sort_keys_kernel", stream);
+  sort_keys_kernel<L><<<n_chunks * tiles_per_chunk, 256, 0, stream>>>(ep, tiles_per_chunk, d_lat[v], S.keys_a.as<L>(), d_chunks, int(v));
+  profiler().end(stream);
     uint64_t* seg_begin = S.seg.as<uint64_t>();
     uint64_t* seg_end = seg_begin + n_chunks;
     segment_offsets_kernel<<<(n_chunks + 255) / 256, 256, 0, stream>>>(ep, order_v, seg_begin, seg_end);
@@ -270,22 +274,34 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
       PCOB_CUDA_TRY(cub::DeviceSegmentedRadixSort::SortKeys(nullptr, tmp_bytes, db, int64_t(n), int64_t(n_chunks), seg_begin, seg_end, 0,
                                                             int(range_bits), stream));
       PCOB_CUDA_TRY(S.cub_tmp.reserve(tmp_bytes + 16));
+      profiler().begin("cub_segmented_radix_sort", stream);
       PCOB_CUDA_TRY(cub::DeviceSegmentedRadixSort::SortKeys(S.cub_tmp.p, tmp_bytes, db, int64_t(n), int64_t(n_chunks), seg_begin, seg_end, 0,
                                                             int(range_bits), stream));
+      profiler().end(stream);
       sorted = db.Current();
     }
-    plan_kernel<L><<<n_chunks, PLAN_THREADS, sizeof(PlanSmem), stream>>>(ep, sorted, d_chunks, d_plans, int(v));
+    profiler().begin("plan_kernel", stream);
+  plan_kernel<L><<<n_chunks, PLAN_THREADS, sizeof(PlanSmem), stream>>>(ep, sorted, d_chunks, d_plans, int(v));
+  profiler().end(stream);
   }
   fallback_kernel<<<(n_chunks + 255) / 256, 256, 0, stream>>>(ep, d_plans, d_chunks);
   // ---- K3, K4
   const uint32_t groups_per_chunk = (bpc + 7) / 8;
   for (uint32_t v = 0; v < ep.n_vars; v++)
+  {
+    profiler().begin("bin_kernel", stream);
     bin_kernel<L><<<n_chunks * groups_per_chunk, BIN_THREADS, 0, stream>>>(ep, bpc, d_lat[v], d_plans, d_chunks, d_sym[v], S.ob_sum.as<uint32_t>(), int(v));
+    profiler().end(stream);
+  }
   // the ans kernel indexes (chunk, var) by blockIdx; both vars share the launch via separate symbol arrays
+  profiler().begin("ans_encode_kernel", stream);
   ans_encode_kernel<<<n_chunks * MAX_VARS, ANS_THREADS, 0, stream>>>(ep, bpc, d_plans, d_chunks, d_sym[0], d_sym[1], d_ans[0], d_ans[1], S.ans_sum.as<uint32_t>(),
                                                                      S.entries.as<BatchEntry>());
+  profiler().end(stream);
   // ---- layout, offsets, K5
+  profiler().begin("layout_kernel", stream);
   layout_kernel<<<n_chunks, LAYOUT_THREADS, 0, stream>>>(ep, bpc, d_plans, d_chunks, S.ans_sum.as<uint32_t>(), S.ob_sum.as<uint32_t>(), S.entries.as<BatchEntry>());
+  profiler().end(stream);
   chunk_offsets_kernel<<<1, 1024, 0, stream>>>(d_chunks, n_chunks, header.size(), d_total);
   uint64_t total = 0;
   PCOB_CUDA_TRY(cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, stream));
@@ -297,8 +313,10 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
     PCOB_CUDA_TRY(S.out.reserve(total + 64));
     d_out = S.out.as<uint8_t>();
   }
+  profiler().begin("pack_kernel", stream);
   pack_kernel<L><<<n_chunks, PACK_THREADS, sizeof(PackSmem), stream>>>(ep, bpc, d_lat[0], d_lat[1], d_plans, d_chunks, d_sym[0], d_sym[1], d_ans[0], d_ans[1],
                                                                       S.entries.as<BatchEntry>(), d_out, total);
+  profiler().end(stream);
   header_footer_kernel<<<1, 32, 0, stream>>>(d_out, total, d_header, uint32_t(header.size()), d_total);
   PCOB_CUDA_TRY(cudaGetLastError());
   if (!dst_dev) PCOB_CUDA_TRY(cudaMemcpyAsync(dst, d_out, total, cudaMemcpyDeviceToHost, stream));

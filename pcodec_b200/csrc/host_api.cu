@@ -92,12 +92,14 @@ static PcoB200Error launch_decode(Context& c, const FileParams& fp, const uint8_
   uint32_t* d_st = c.statuses.as<uint32_t>();
   PCOB_CUDA_TRY(cudaMemsetAsync(d_st, 0xff, size_t(n_chunks) * sizeof(uint32_t), stream));
   const IndexChunk* d_chunks = reinterpret_cast<const IndexChunk*>(d_index + chunks_offset);
+  profiler().begin("decode_kernel", stream);
   dispatch_latent(fp.dtype, [&](auto tag) {
     using L = decltype(tag);
     decode_kernel<L><<<n_chunks, DEC_THREADS, sizeof(DecodeSmem), stream>>>(fp, d_chunks, d_st, d_index, static_cast<L*>(d_out), out_len,
                                                                              c.d_binoms);
     return 0;
   });
+  profiler().end(stream);
   PCOB_CUDA_TRY(cudaGetLastError());
   std::vector<uint32_t> st(n_chunks);
   PCOB_CUDA_TRY(cudaMemcpyAsync(st.data(), d_st, size_t(n_chunks) * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
@@ -149,12 +151,22 @@ static PcoB200Error decompress_core(const void* compressed, size_t compressed_le
 
   // 3a. caller-supplied side index
   if (index != nullptr && index_len >= sizeof(IndexHeader)) {
+    const bool idx_dev = flags & PCO_B200_INDEX_ON_DEVICE;
     IndexHeader ih;
-    std::memcpy(&ih, index, sizeof(ih));
+    if (idx_dev) {
+      PCOB_CUDA_TRY(cudaMemcpyAsync(&ih, index, sizeof(ih), cudaMemcpyDeviceToHost, stream));
+      PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
+    } else {
+      std::memcpy(&ih, index, sizeof(ih));
+    }
     if (ih.magic != INDEX_MAGIC || ih.version != 1 || ih.file_len != compressed_len || ih.chunks_offset + ih.n_chunks * sizeof(IndexChunk) > index_len)
       return fail(PCO_B200_INVALID_ARGUMENT, "side index does not belong to this file");
-    PCOB_CUDA_TRY(c.index.reserve(index_len));
-    PCOB_CUDA_TRY(cudaMemcpyAsync(c.index.p, index, index_len, cudaMemcpyHostToDevice, stream));
+    const uint8_t* d_idx = static_cast<const uint8_t*>(index);
+    if (!idx_dev) {
+      PCOB_CUDA_TRY(c.index.reserve(index_len));
+      PCOB_CUDA_TRY(cudaMemcpyAsync(c.index.p, index, index_len, cudaMemcpyHostToDevice, stream));
+      d_idx = c.index.as<uint8_t>();
+    }
     uint64_t n_emit = std::min<uint64_t>(ih.n_total, dst_len);
     void* d_out = dst;
     if (!dst_dev) {
@@ -162,7 +174,7 @@ static PcoB200Error decompress_core(const void* compressed, size_t compressed_le
       d_out = c.out.p;
     }
     if (ih.n_chunks > 0xffffffffull) return fail(PCO_B200_INVALID_ARGUMENT, "too many chunks");
-    if (PcoB200Error e = launch_decode(c, fp, c.index.as<uint8_t>(), ih.chunks_offset, uint32_t(ih.n_chunks), d_out, dst_len, stream)) return e;
+    if (PcoB200Error e = launch_decode(c, fp, d_idx, ih.chunks_offset, uint32_t(ih.n_chunks), d_out, dst_len, stream)) return e;
     if (!dst_dev && n_emit) {
       PCOB_CUDA_TRY(cudaMemcpyAsync(dst, d_out, n_emit * elem, cudaMemcpyDeviceToHost, stream));
       PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
@@ -189,8 +201,10 @@ static PcoB200Error decompress_core(const void* compressed, size_t compressed_le
     const uint64_t entries_bytes = want_batches * MAX_VARS * sizeof(BatchEntry) + 16ull * max_chunks + 64;
     PCOB_CUDA_TRY(c.index.reserve(entries_begin + entries_bytes));
     uint8_t* d_index = c.index.as<uint8_t>();
+    profiler().begin("walk_kernel", stream);
     walk_kernel<<<1, 128, sizeof(WalkSmem), stream>>>(fp, d_index, chunks_offset, max_chunks, entries_begin, entries_begin + entries_bytes,
                                                       next_byte, out_off, uint64_t(dst_len), nullptr, d_res, 1);
+    profiler().end(stream);
     PCOB_CUDA_TRY(cudaGetLastError());
     WalkResult res;
     PCOB_CUDA_TRY(cudaMemcpyAsync(&res, d_res, sizeof(res), cudaMemcpyDeviceToHost, stream));
@@ -269,6 +283,7 @@ PcoB200Error pco_b200_decompress_ex(const void* compressed, size_t compressed_le
                                     PcoB200Progress* progress, const void* index, size_t index_len, uint32_t flags, void* cuda_stream) {
   DecodeOutcome oc;
   PcoB200Error e = decompress_core(compressed, compressed_len, dtype, dst, dst_len, index, index_len, flags, cuda_stream, true, &oc);
+  profiler().resolve();
   if (e != PCO_B200_OK) return e;
   if (progress) {
     progress->n_processed = size_t(std::min<uint64_t>(oc.n_total, dst_len));
@@ -300,6 +315,7 @@ static PcoB200Error compress_dispatch(const void* nums, size_t n, unsigned char 
     using L = decltype(tag);
     return compress_typed<L>(c.enc, nums, n, dtype, cfg, uniform, dst, dst_cap, index, index_cap, flags, static_cast<cudaStream_t>(cuda_stream), &res);
   });
+  profiler().resolve();
   if (e != PCO_B200_OK) return e;
   if (n_written) *n_written = size_t(res.total_bytes);
   if (index_len) *index_len = size_t(res.index_bytes);
@@ -333,6 +349,19 @@ enum PcoError pco_standalone_simple_compress_into(const void* nums, size_t n, un
   cfg.enable_8_bit = 1;
   PcoB200Error e = compress_dispatch(nums, n, dtype, &cfg, true, dst, dst_cap, n_written, nullptr, 0, nullptr, 0, nullptr);
   return e == PCO_B200_OK ? PcoSuccess : PcoCompressionError;
+}
+
+void pco_b200_profile_enable(int on) { profiler().enabled = on != 0; }
+// Copies "name=ms;name=ms;..." of the last finished call into buf; returns the number of spans.
+int pco_b200_profile_last(char* buf, size_t cap) {
+  std::string s;
+  for (auto& kv : profiler().last) s += kv.first + "=" + std::to_string(kv.second) + ";";
+  if (cap) {
+    size_t n = std::min(cap - 1, s.size());
+    std::memcpy(buf, s.data(), n);
+    buf[n] = 0;
+  }
+  return int(profiler().last.size());
 }
 
 size_t pco_b200_index_size_bound(size_t n, size_t n_chunks_hint) {

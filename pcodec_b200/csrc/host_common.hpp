@@ -46,6 +46,44 @@ inline PcoB200Error status_to_error(uint32_t st, const char* where) {
   }
 }
 
+// ---- optional per-kernel timing (CUDA events on the launching stream; off by default) ----
+struct Profiler {
+  bool enabled = false;
+  struct Span { std::string name; cudaEvent_t e0, e1; };
+  std::vector<Span> spans;                              // of the call in flight
+  std::vector<std::pair<std::string, float>> last;      // resolved spans of the last finished call
+  void begin(const char* name, cudaStream_t s) {
+    if (!enabled) return;
+    Span sp;
+    sp.name = name;
+    cudaEventCreate(&sp.e0);
+    cudaEventCreate(&sp.e1);
+    cudaEventRecord(sp.e0, s);
+    spans.push_back(sp);
+  }
+  void end(cudaStream_t s) {
+    if (!enabled || spans.empty()) return;
+    cudaEventRecord(spans.back().e1, s);
+  }
+  void resolve() {  // call after the stream has been synchronised
+    if (!enabled) return;
+    last.clear();
+    for (auto& sp : spans) {
+      float ms = 0.f;
+      cudaEventSynchronize(sp.e1);
+      cudaEventElapsedTime(&ms, sp.e0, sp.e1);
+      last.push_back({sp.name, ms});
+      cudaEventDestroy(sp.e0);
+      cudaEventDestroy(sp.e1);
+    }
+    spans.clear();
+  }
+};
+inline Profiler& profiler() {
+  static Profiler p;
+  return p;
+}
+
 // ---- grow-only device buffer -----------------------------------------------
 struct DevBuf {
   void* p = nullptr;
