@@ -20,6 +20,8 @@ constexpr int SMALL_MAX_SIZE_LOG = 10;
 constexpr int SMALL_MAX_BINS = 256;
 constexpr int SYM_ROW_WORDS = 65;  // 256 one-byte symbols + 4 bytes pad: odd word stride -> conflict-free rows
 constexpr int CARRY_RING = 32;
+constexpr int WIN_WORDS = 128;                  // 512-byte window of compressed bytes per (warp, var)
+constexpr uint32_t WIN_USABLE_BITS = WIN_WORDS * 32 - 64;
 
 // node word: next_state_idx_base (14 bits) | field (14 bits) << 14 | bits_to_read (4 bits) << 28
 //   decode tables: field = bin index;  walker tables: field = bin offset_bits
@@ -43,6 +45,7 @@ struct DecodeSmem {
   uint64_t carry[CARRY_RING][MAX_ORDER];  // delta moments at the start of batch b (ring slot b % CARRY_RING)
   volatile uint32_t carry_seq[CARRY_RING];
   uint32_t err;
+  alignas(16) uint32_t win[DEC_WARPS][MAX_VARS][WIN_WORDS + 4];  // per-warp staged copy of a batch's offset bits
   uint32_t sym[DEC_THREADS * SYM_ROW_WORDS];
 };
 
@@ -480,6 +483,82 @@ __device__ __forceinline__ void warp_excl_scan8(L (&x)[8], L& total, int lane) {
   total = shfl_idx_L<L>(inc, 31);
 }
 
+// Field of `nbits` bits at bit position p of a shared-memory window of 32-bit words.
+__device__ __forceinline__ uint32_t bfe32(uint32_t v, uint32_t nbits) {
+  uint32_t r;
+  asm("bfe.u32 %0, %1, 0, %2;" : "=r"(r) : "r"(v), "r"(nbits));
+  return r;
+}
+template <typename L, bool WIDE>
+__device__ __forceinline__ L win_extract(const uint32_t* __restrict__ win, uint32_t p, uint32_t nbits) {
+  const uint32_t w = p >> 5, r = p & 31;
+  const uint32_t lo = win[w], mid = win[w + 1];
+  const uint32_t v0 = __funnelshift_r(lo, mid, r);
+  if (!WIDE) return L(bfe32(v0, nbits));
+  const uint32_t hi = win[w + 2];
+  const uint32_t v1 = __funnelshift_r(mid, hi, r);
+  if (nbits <= 32) return L(bfe32(v0, nbits));
+  return L((uint64_t(bfe32(v1, nbits - 32)) << 32) | v0);
+}
+
+// from_latent_ordered with the number kind hoisted: 0 unsigned, 1 signed, 2 float
+template <typename L>
+__device__ __forceinline__ L from_latent_kind(L l, int kind) {
+  constexpr L MID = L(L(1) << (LT<L>::BITS - 1));
+  if (kind == 0) return l;
+  if (kind == 1) return L(l ^ MID);
+  const L s = L(l >> (LT<L>::BITS - 1));
+  return L(l ^ L(L(s - 1) | MID));
+}
+
+// Un-delta of one batch held 8-per-lane in registers.  The batch is scanned with zero-seeded moments (K nested exclusive
+// scans), which needs nothing from earlier batches; the true moments m at the batch start arrive through a shared-memory
+// ring from the warp that owns the previous batch (m' = A^256 m + c, A = I + superdiagonal, so (A^n)_{j,j+t} = C(n,t)),
+// and are folded in by linearity: x_i += (A^i m)_0.
+template <typename L, int K>
+__device__ __forceinline__ void undelta_batch(L (&x)[8], DecodeSmem& sm, const Binoms* __restrict__ binoms, uint32_t b, int lane) {
+  L c[K];
+#pragma unroll
+  for (int lvl = 0; lvl < K; lvl++) {
+    L total;
+    warp_excl_scan8<L>(x, total, lane);
+    c[K - 1 - lvl] = total;  // c_j = sum over the batch of x^(j+1)
+  }
+  const uint32_t slot = b % CARRY_RING, nslot = (b + 1) % CARRY_RING;
+  // every lane polls (a broadcast shared-memory read), so no extra warp barrier sits on the chain
+  while (sm.carry_seq[slot] != b + 1) {
+  }
+  __threadfence_block();
+  L m[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) m[k] = L(sm.carry[slot][k]);
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+      L acc = c[j];
+#pragma unroll
+      for (int t = 0; j + t < K; t++) acc = L(acc + L(L(binoms->full[t]) * m[j + t]));
+      sm.carry[nslot][j] = uint64_t(acc);
+    }
+    __threadfence_block();
+    sm.carry_seq[nslot] = b + 2;
+  }
+  L s[K];
+#pragma unroll
+  for (int j = 0; j < K; j++) {
+    L acc = 0;
+#pragma unroll
+    for (int t = 0; j + t < K; t++) acc = L(acc + L(L(binoms->lane8[lane][t]) * m[j + t]));
+    s[j] = acc;
+  }
+#pragma unroll
+  for (int e = 0; e < 8; e++) {
+    x[e] = L(x[e] + s[0]);
+#pragma unroll
+    for (int j = 0; j + 1 < K; j++) s[j] = L(s[j] + s[j + 1]);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // decode_kernel: one CTA per chunk.
 // ---------------------------------------------------------------------------
@@ -588,156 +667,186 @@ decode_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, uint32_t* __
     }
     __syncthreads();
     // ---------------- phase B: one warp per batch ----------------
-    for (uint32_t bl = warp; bl < tile_n; bl += DEC_WARPS) {
-      const uint32_t b = tile_start + bl;
-      const uint32_t out_cnt = min(uint32_t(BATCH_N), n_out - b * BATCH_N);  // numbers this batch emits
-      L lat[MAX_VARS][8];
-      uint64_t last_end = 0;
-#pragma unroll
-      for (uint32_t v = 0; v < MAX_VARS; v++) {
-        if (v >= n_vars) break;
-        const VarHdr& vh = sm.hdr.var[v];
-        const uint32_t cnt = batch_count(v == 0 ? stored0 : stored1, b);
-        const uint32_t row = (v * tile_b + bl);
-        uint32_t sy[8];
-        uint32_t ob[8];
-        uint32_t lane_bits = 0;
-        if (vh.n_bins > 1) {
-          const uint32_t* rowp = &sm.sym[row * SYM_ROW_WORDS + lane * 2];
-          uint32_t p0 = rowp[0], p1 = rowp[1];
-#pragma unroll
-          for (int e = 0; e < 8; e++) sy[e] = ((e < 4 ? p0 : p1) >> (8 * (e & 3))) & 0xffu;
-        } else {
-#pragma unroll
-          for (int e = 0; e < 8; e++) sy[e] = 0;
-        }
-#pragma unroll
-        for (int e = 0; e < 8; e++) {
-          bool valid = uint32_t(lane * 8 + e) < cnt;
-          if (!valid) sy[e] = 0;
-          ob[e] = valid ? uint32_t(sm.bin_ob[v][sy[e]]) : 0;
-          lane_bits += ob[e];
-        }
-        // exclusive scan of lane_bits across the warp
-        uint32_t inc = lane_bits;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
-          if (lane >= d) inc += o;
-        }
-        uint64_t pos = chunk_bit0 + sm.off_start[row] + (inc - lane_bits);
-        const uint32_t total_bits = __shfl_sync(0xffffffffu, inc, 31);
-        last_end = chunk_bit0 + sm.off_start[row] + total_bits;
-#pragma unroll
-        for (int e = 0; e < 8; e++) {
-          bool valid = uint32_t(lane * 8 + e) < cnt;
-          L lower = L(sm.bin_lower[v][sy[e]]);
-          L off = 0;
-          if (ob[e] != 0) off = read_offset<L>(src.words, max_word, min(pos, src.n_bits), ob[e]);
-          pos += ob[e];
-          // positions past the stored latents of a delta'd var hold deltas that cannot influence
-          // any emitted number (page_latent_decompressor.rs:244-248); use the toggled zero
-          lat[v][e] = valid ? L(lower + off) : L(0);
-        }
-      }
-      // ---- un-delta of the primary (delta/consecutive.rs:35-50)
-      if (order > 0) {
-        L c[MAX_ORDER];
-        for (uint32_t lvl = 0; lvl < order; lvl++) {
-          // level j = order-1-lvl: x^(j) = exclusive scan of x^(j+1); c_j = sum of x^(j+1)
-          L total;
-          warp_excl_scan8<L>(lat[0], total, lane);
-          c[order - 1 - lvl] = total;
-        }
-        // wait for the moments at the start of this batch, publish those of the next
-        const uint32_t slot = b % CARRY_RING, nslot = (b + 1) % CARRY_RING;
-        if (lane == 0) {
-          while (sm.carry_seq[slot] != b + 1) { __nanosleep(20); }
-        }
-        __syncwarp();
-        __threadfence_block();
-        L m[MAX_ORDER];
-        for (uint32_t k = 0; k < order; k++) m[k] = L(sm.carry[slot][k]);
-        __syncwarp();
-        if (lane == 0) {
-          // m' = A^256 m + c, (A^n)_{j,j+t} = C(n, t)
-          for (uint32_t j = 0; j < order; j++) {
-            L acc = c[j];
-            for (uint32_t t = 0; j + t < order; t++) acc = L(acc + L(L(binoms->full[t]) * m[j + t]));
-            sm.carry[nslot][j] = uint64_t(acc);
-          }
-          __threadfence_block();
-          sm.carry_seq[nslot] = b + 2;
-        }
-        // fix-up: x_i += sum_j C(i, j) m_j, evaluated by running the recurrence from s = A^(8*lane) m
-        L s[MAX_ORDER];
-        for (uint32_t j = 0; j < order; j++) {
-          L acc = 0;
-          for (uint32_t t = 0; j + t < order; t++) acc = L(acc + L(L(binoms->lane8[lane][t]) * m[j + t]));
-          s[j] = acc;
-        }
-#pragma unroll
-        for (int e = 0; e < 8; e++) {
-          lat[0][e] = L(lat[0][e] + s[0]);
-          for (uint32_t j = 0; j + 1 < order; j++) s[j] = L(s[j] + s[j + 1]);
-        }
-      }
-      // ---- join (mode/*.rs) and store
-      L res[8];
+    // A batch's offset bits are one contiguous run of the compressed stream.  Each warp copies a 512-byte window of
+    // it with two coalesced 8-byte loads per lane -- issued one batch ahead, so the DRAM/L2 latency is covered by
+    // the previous batch's work -- parks it in shared memory and extracts the variable-width fields from there.
+    {
+      const int kind = is_float ? 2 : (is_signed ? 1 : 0);
       const uint32_t mode = sm.hdr.mode;
+      uint64_t pf[MAX_VARS][2];
+      auto issue_window_loads = [&](uint32_t bl_n) {
 #pragma unroll
-      for (int e = 0; e < 8; e++) {
-        L p = lat[0][e];
-        L r;
+        for (uint32_t v = 0; v < MAX_VARS; v++) {
+          if (v < n_vars && sm.hdr.var[v].max_offset_bits > 0) {
+            const uint64_t wb = (chunk_bit0 + sm.off_start[v * tile_b + bl_n]) >> 6;
+            const uint64_t i0 = wb + lane, i1 = wb + 32 + lane;
+            pf[v][0] = __ldg(src.words + (i0 <= max_word ? i0 : max_word));
+            pf[v][1] = __ldg(src.words + (i1 <= max_word ? i1 : max_word));
+          }
+        }
+      };
+      if (uint32_t(warp) < tile_n) issue_window_loads(warp);
+      for (uint32_t bl = warp; bl < tile_n; bl += DEC_WARPS) {
+        const uint32_t b = tile_start + bl;
+        const uint32_t out_cnt = min(uint32_t(BATCH_N), n_out - b * BATCH_N);  // numbers this batch emits
+        __syncwarp();
+#pragma unroll
+        for (uint32_t v = 0; v < MAX_VARS; v++) {
+          if (v < n_vars && sm.hdr.var[v].max_offset_bits > 0) {
+            uint2* w2 = reinterpret_cast<uint2*>(sm.win[warp][v]);
+            w2[lane] = make_uint2(uint32_t(pf[v][0]), uint32_t(pf[v][0] >> 32));
+            w2[32 + lane] = make_uint2(uint32_t(pf[v][1]), uint32_t(pf[v][1] >> 32));
+          }
+        }
+        __syncwarp();
+        if (bl + DEC_WARPS < tile_n) issue_window_loads(bl + DEC_WARPS);
+        L lat[MAX_VARS][8];
+        uint64_t last_end = 0;
+#pragma unroll
+        for (uint32_t v = 0; v < MAX_VARS; v++) {
+          if (v >= n_vars) break;
+          const VarHdr& vh = sm.hdr.var[v];
+          const uint32_t cnt = batch_count(v == 0 ? stored0 : stored1, b);
+          const uint32_t row = (v * tile_b + bl);
+          const bool full = cnt == BATCH_N;
+          uint32_t sy[8];
+          uint32_t ob[8];
+          uint32_t lane_bits = 0;
+          if (vh.n_bins > 1) {
+            const uint32_t* rowp = &sm.sym[row * SYM_ROW_WORDS + lane * 2];
+            const uint32_t p0 = rowp[0], p1 = rowp[1];
+#pragma unroll
+            for (int e = 0; e < 8; e++) sy[e] = ((e < 4 ? p0 : p1) >> (8 * (e & 3))) & 0xffu;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; e++) sy[e] = 0;
+          }
+          if (full) {
+#pragma unroll
+            for (int e = 0; e < 8; e++) { ob[e] = sm.bin_ob[v][sy[e]]; lane_bits += ob[e]; }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+              const bool valid = uint32_t(lane * 8 + e) < cnt;
+              if (!valid) sy[e] = 0;
+              ob[e] = valid ? uint32_t(sm.bin_ob[v][sy[e]]) : 0;
+              lane_bits += ob[e];
+            }
+          }
+          uint32_t inc = lane_bits;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += o;
+          }
+          const uint32_t total_bits = __shfl_sync(0xffffffffu, inc, 31);
+          const uint64_t sec_bit = chunk_bit0 + sm.off_start[row];
+          last_end = sec_bit + total_bits;
+          if (vh.max_offset_bits == 0) {
+#pragma unroll
+            for (int e = 0; e < 8; e++) lat[v][e] = L(sm.bin_lower[v][sy[e]]);
+          } else if (total_bits <= WIN_USABLE_BITS) {
+            const uint32_t* win = sm.win[warp][v];
+            uint32_t p = uint32_t(sec_bit & 63) + (inc - lane_bits);
+            if (LT<L>::BITS <= 32 || vh.max_offset_bits <= 32) {
+#pragma unroll
+              for (int e = 0; e < 8; e++) {
+                lat[v][e] = L(L(sm.bin_lower[v][sy[e]]) + win_extract<L, false>(win, p, ob[e]));
+                p += ob[e];
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; e++) {
+                lat[v][e] = L(L(sm.bin_lower[v][sy[e]]) + win_extract<L, true>(win, p, ob[e]));
+                p += ob[e];
+              }
+            }
+          } else {
+            // section longer than the staged window (mean offset > ~15.7 bits): read the stream directly
+            uint64_t pos = sec_bit + (inc - lane_bits);
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+              L off = 0;
+              if (ob[e] != 0) off = read_offset<L>(src.words, max_word, min(pos, src.n_bits), ob[e]);
+              pos += ob[e];
+              lat[v][e] = L(L(sm.bin_lower[v][sy[e]]) + off);
+            }
+          }
+          // positions past the stored latents of a delta'd var hold deltas that cannot influence any emitted
+          // number (page_latent_decompressor.rs:244-248); any value works there
+        }
+        // ---- un-delta of the primary (delta/consecutive.rs:35-50), specialised on the order
+        switch (order) {
+          case 0: break;
+          case 1: undelta_batch<L, 1>(lat[0], sm, binoms, b, lane); break;
+          case 2: undelta_batch<L, 2>(lat[0], sm, binoms, b, lane); break;
+          case 3: undelta_batch<L, 3>(lat[0], sm, binoms, b, lane); break;
+          case 4: undelta_batch<L, 4>(lat[0], sm, binoms, b, lane); break;
+          case 5: undelta_batch<L, 5>(lat[0], sm, binoms, b, lane); break;
+          case 6: undelta_batch<L, 6>(lat[0], sm, binoms, b, lane); break;
+          default: undelta_batch<L, 7>(lat[0], sm, binoms, b, lane); break;
+        }
+        // ---- join (mode/*.rs)
+        L res[8];
         if (mode == MODE_CLASSIC) {
-          r = from_latent_ordered<L>(p, is_float, is_signed);
+#pragma unroll
+          for (int e = 0; e < 8; e++) res[e] = from_latent_kind<L>(lat[0][e], kind);
         } else if (mode == MODE_INT_MULT) {
-          r = from_latent_ordered<L>(L(L(p * L(sm.hdr.mode_base)) + lat[1][e]), is_float, is_signed);
+          const L base = L(sm.hdr.mode_base);
+#pragma unroll
+          for (int e = 0; e < 8; e++) res[e] = from_latent_kind<L>(L(L(lat[0][e] * base) + lat[1][e]), kind);
         } else if (mode == MODE_FLOAT_MULT) {
           constexpr L MID = L(L(1) << (LT<L>::BITS - 1));
-          L base_bits = from_latent_ordered<L>(L(sm.hdr.mode_base), true, false);
-          L un = float_mult_unadjusted(p, base_bits);
-          L u = to_latent_ordered<L>(un, true, false);
-          r = from_latent_ordered<L>(L(L(u + lat[1][e]) + MID), true, false);
+          const L base_bits = from_latent_ordered<L>(L(sm.hdr.mode_base), true, false);
+#pragma unroll
+          for (int e = 0; e < 8; e++) {
+            const L un = float_mult_unadjusted(lat[0][e], base_bits);
+            const L u = to_latent_ordered<L>(un, true, false);
+            res[e] = from_latent_kind<L>(L(L(u + lat[1][e]) + MID), 2);
+          }
         } else {  // MODE_FLOAT_QUANT
           const uint32_t k = sm.hdr.mode_k;
           constexpr L MID = L(L(1) << (LT<L>::BITS - 1));
-          L sign_cutoff = L(MID >> k);
-          L kmax = L(L(L(1) << k) - 1);
-          L lowest = p >= sign_cutoff ? lat[1][e] : L(kmax - lat[1][e]);
-          r = from_latent_ordered<L>(L(L(p << k) + lowest), true, false);
-        }
-        res[e] = r;
-      }
-      L* dst = out + task.out_offset + size_t(b) * BATCH_N + lane * 8;
-      if (out_cnt == BATCH_N) {
-        if (sizeof(L) == 8) {
-          uint4* d4 = reinterpret_cast<uint4*>(dst);
+          const L sign_cutoff = L(MID >> k);
+          const L kmax = L(L(L(1) << k) - 1);
 #pragma unroll
-          for (int q = 0; q < 4; q++) {
-            uint64_t a = uint64_t(res[2 * q]), bb = uint64_t(res[2 * q + 1]);
-            d4[q] = make_uint4(uint32_t(a), uint32_t(a >> 32), uint32_t(bb), uint32_t(bb >> 32));
+          for (int e = 0; e < 8; e++) {
+            const L pq = lat[0][e];
+            const L lowest = pq >= sign_cutoff ? lat[1][e] : L(kmax - lat[1][e]);
+            res[e] = from_latent_kind<L>(L(L(pq << k) + lowest), 2);
           }
-        } else if (sizeof(L) == 4) {
-          uint4* d4 = reinterpret_cast<uint4*>(dst);
-          d4[0] = make_uint4(uint32_t(res[0]), uint32_t(res[1]), uint32_t(res[2]), uint32_t(res[3]));
-          d4[1] = make_uint4(uint32_t(res[4]), uint32_t(res[5]), uint32_t(res[6]), uint32_t(res[7]));
+        }
+        // ---- store: 8 consecutive numbers per lane
+        L* dst = out + task.out_offset + size_t(b) * BATCH_N + lane * 8;
+        if (out_cnt == BATCH_N) {
+          if (sizeof(L) == 8) {
+            uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+              const uint64_t a = uint64_t(res[2 * q]), bb = uint64_t(res[2 * q + 1]);
+              d4[q] = make_uint4(uint32_t(a), uint32_t(a >> 32), uint32_t(bb), uint32_t(bb >> 32));
+            }
+          } else if (sizeof(L) == 4) {
+            uint4* d4 = reinterpret_cast<uint4*>(dst);
+            d4[0] = make_uint4(uint32_t(res[0]), uint32_t(res[1]), uint32_t(res[2]), uint32_t(res[3]));
+            d4[1] = make_uint4(uint32_t(res[4]), uint32_t(res[5]), uint32_t(res[6]), uint32_t(res[7]));
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; e++) dst[e] = res[e];
+          }
         } else {
 #pragma unroll
-          for (int e = 0; e < 8; e++) dst[e] = res[e];
+          for (int e = 0; e < 8; e++)
+            if (uint32_t(lane * 8 + e) < out_cnt) dst[e] = res[e];
         }
-      } else {
-#pragma unroll
-        for (int e = 0; e < 8; e++)
-          if (uint32_t(lane * 8 + e) < out_cnt) dst[e] = res[e];
-      }
-      // ---- end-of-page checks by the warp that owns the last batch (page_decompressor.rs:184-188)
-      if (b == nb_total - 1 && lane == 0) {
-        uint64_t bit = last_end;
-        if (bit > src.n_bits) end_err = ST_INSUFFICIENT_DATA;
-        else {
-          uint32_t pad = uint32_t((8 - (bit & 7)) & 7);
-          if (pad && read_bits_safe(src, bit, pad) != 0) end_err = ST_CORRUPTION;
+        // ---- end-of-page checks by the warp that owns the last batch (page_decompressor.rs:184-188)
+        if (b == nb_total - 1 && lane == 0) {
+          const uint64_t bit = last_end;
+          if (bit > src.n_bits) end_err = ST_INSUFFICIENT_DATA;
+          else {
+            const uint32_t pad = uint32_t((8 - (bit & 7)) & 7);
+            if (pad && read_bits_safe(src, bit, pad) != 0) end_err = ST_CORRUPTION;
+          }
         }
       }
     }

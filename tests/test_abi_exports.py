@@ -35,9 +35,11 @@ def test_guarantee_file_size_matches_reference_formula():  # pco/src/standalone/
     assert f(0, 3) == 18
     assert f(1 << 18, 2) == 17 + (4 + 150 + (1 << 21)) + 1
     assert f(10, 99) == 0
-    # two equal pages of 2^18 + 1 numbers split (chunk_config.rs:134-183)
+    # 2^19 + 1 numbers -> three equal pages of 174763 (chunk_config.rs:134-183); u32 baseline meta = 146 bytes
     n = (1 << 19) + 1
-    assert f(n, 1) == 17 + 2 * (4 + 146 + 4 * 174763) + (4 + 146 + 4 * 174763 - 4) + 1
+    assert f(n, 1) == 17 + 3 * (4 + 146 + 4 * 174763) + 1
+    # 2^18 + 1 -> pages of 131073 and 131072
+    assert f((1 << 18) + 1, 2) == 17 + (4 + 150 + 8 * 131073) + (4 + 150 + 8 * 131072) + 1
 
 
 def test_product_never_imports_oracle():
