@@ -66,7 +66,10 @@ typedef struct PcoB200Progress {
 } PcoB200Progress;
 
 /* Buffer-location flags for the *_ex entry points. */
-enum { PCO_B200_SRC_ON_DEVICE = 1u, PCO_B200_DST_ON_DEVICE = 2u, PCO_B200_INDEX_ON_DEVICE = 4u };
+enum { PCO_B200_SRC_ON_DEVICE = 1u, PCO_B200_DST_ON_DEVICE = 2u, PCO_B200_INDEX_ON_DEVICE = 4u,
+       /* compress only: emit the chunks (type byte, n, meta, page) back to back with no standalone header and no
+        * terminator -- the unit a rank contributes when chunks are sharded across GPUs */
+       PCO_B200_CHUNKS_ONLY = 8u };
 
 /* Message of the last error raised on the calling thread (pco::errors::PcoError::message). */
 const char *pco_b200_last_error_message(void);

@@ -169,13 +169,15 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
   ep.n_vars = ep.mode == MODE_CLASSIC ? 1 : 2;
   ep.n_total = n;
   ep.n_chunks = uint32_t(pages.size());
+  const bool chunks_only = flags & PCO_B200_CHUNKS_ONLY;
   std::vector<uint8_t> header = make_standalone_header(n, uint8_t(ep.uniform_type));
+  if (chunks_only) header.clear();
   // empty input: header + terminator only (standalone/simple.rs:62-91)
   if (n == 0) {
-    header.push_back(0);
+    if (!chunks_only) header.push_back(0);
     if (header.size() > dst_cap) return fail(PCO_B200_IO, "failed to write whole buffer");
-    if (dst_dev) PCOB_CUDA_TRY(cudaMemcpyAsync(dst, header.data(), header.size(), cudaMemcpyHostToDevice, stream));
-    else std::memcpy(dst, header.data(), header.size());
+    if (dst_dev && !header.empty()) PCOB_CUDA_TRY(cudaMemcpyAsync(dst, header.data(), header.size(), cudaMemcpyHostToDevice, stream));
+    else if (!header.empty()) std::memcpy(dst, header.data(), header.size());
     PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
     res->total_bytes = header.size();
     if (index_dst && index_cap >= sizeof(IndexHeader)) {
@@ -302,7 +304,7 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
   profiler().begin("layout_kernel", stream);
   layout_kernel<<<n_chunks, LAYOUT_THREADS, 0, stream>>>(ep, bpc, d_plans, d_chunks, S.ans_sum.as<uint32_t>(), S.ob_sum.as<uint32_t>(), S.entries.as<BatchEntry>());
   profiler().end(stream);
-  chunk_offsets_kernel<<<1, 1024, 0, stream>>>(d_chunks, n_chunks, header.size(), d_total);
+  chunk_offsets_kernel<<<1, 1024, 0, stream>>>(d_chunks, n_chunks, header.size(), chunks_only ? 0u : 1u, d_total);
   uint64_t total = 0;
   PCOB_CUDA_TRY(cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, stream));
   PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
@@ -317,7 +319,7 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
   pack_kernel<L><<<n_chunks, PACK_THREADS, sizeof(PackSmem), stream>>>(ep, bpc, d_lat[0], d_lat[1], d_plans, d_chunks, d_sym[0], d_sym[1], d_ans[0], d_ans[1],
                                                                       S.entries.as<BatchEntry>(), d_out, total);
   profiler().end(stream);
-  header_footer_kernel<<<1, 32, 0, stream>>>(d_out, total, d_header, uint32_t(header.size()), d_total);
+  if (!chunks_only) header_footer_kernel<<<1, 32, 0, stream>>>(d_out, total, d_header, uint32_t(header.size()), d_total);
   PCOB_CUDA_TRY(cudaGetLastError());
   if (!dst_dev) PCOB_CUDA_TRY(cudaMemcpyAsync(dst, d_out, total, cudaMemcpyDeviceToHost, stream));
   res->total_bytes = total;
@@ -338,7 +340,7 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
     PCOB_CUDA_TRY(cudaMemcpyAsync(S.seg.p, eoff.data(), size_t(n_chunks) * 8, cudaMemcpyHostToDevice, stream));
     IndexHeader ih;
     std::memset(&ih, 0, sizeof(ih));
-    ih.magic = INDEX_MAGIC; ih.version = 1; ih.n_chunks = n_chunks; ih.n_total = n; ih.file_len = total; ih.chunks_offset = chunks_offset; ih.end_byte = total;
+    ih.magic = INDEX_MAGIC; ih.version = 1; ih.n_chunks = n_chunks; ih.n_total = n; ih.file_len = total; ih.chunks_offset = chunks_offset; ih.end_byte = chunks_only ? 0 : total;
     PCOB_CUDA_TRY(cudaMemcpyAsync(idx.p, &ih, sizeof(ih), cudaMemcpyHostToDevice, stream));
     emit_index_kernel<<<n_chunks, 256, 0, stream>>>(ep, bpc, d_chunks, S.entries.as<BatchEntry>(), idx.as<uint8_t>(), chunks_offset, S.seg.as<uint64_t>());
     PCOB_CUDA_TRY(cudaGetLastError());

@@ -916,7 +916,7 @@ __global__ void __launch_bounds__(LAYOUT_THREADS) layout_kernel(EncParams ep, ui
 }
 
 // exclusive scan of chunk sizes -> output offsets (one CTA; chunk counts are small)
-__global__ void chunk_offsets_kernel(ChunkEnc* chunks, uint32_t n_chunks, uint64_t header_bytes, uint64_t* total_bytes) {
+__global__ void chunk_offsets_kernel(ChunkEnc* chunks, uint32_t n_chunks, uint64_t header_bytes, uint32_t footer_bytes, uint64_t* total_bytes) {
   __shared__ uint64_t part[1024];
   const int tid = threadIdx.x;
   uint32_t per = (n_chunks + blockDim.x - 1) / blockDim.x;
@@ -928,7 +928,7 @@ __global__ void chunk_offsets_kernel(ChunkEnc* chunks, uint32_t n_chunks, uint64
   if (tid == 0) {
     uint64_t acc = header_bytes;
     for (uint32_t t = 0; t < blockDim.x; t++) { uint64_t x = part[t]; part[t] = acc; acc += x; }
-    *total_bytes = acc + 1;  // + terminator byte
+    *total_bytes = acc + footer_bytes;  // + terminator byte
   }
   __syncthreads();
   uint64_t off = part[tid];

@@ -187,3 +187,31 @@ def test_exact_paging(sa, oracle):
         return
     b = oracle.simple_compress(nums, ocfg)
     assert a == b
+
+
+def test_sharded_chunks_only_equals_whole_file(sa, oracle):
+    """SURVEY §8e on one GPU: two virtual ranks compress their round-robin chunk shards with PCO_B200_CHUNKS_ONLY;
+    header | chunks in order | 0x00 must equal the whole-array compress (ours and the oracle's)."""
+    from pcodec_b200 import ChunkConfig, DeltaSpec, ModeSpec, PagingSpec, sharded
+
+    n, page = 9 * 4096 + 5, 4096
+    nums = _walk(np.uint64, n, 77)
+    cfg = ChunkConfig(mode_spec=ModeSpec.classic(), delta_spec=DeltaSpec.try_consecutive(1), paging_spec=PagingSpec.equal_pages_up_to(page))
+    world = 2
+    plan = sharded.shard_plan(n, world, page)
+    shards = []
+    for r in range(world):
+        local = np.concatenate([nums[s:e] for (_, s, e) in plan[r]])
+        shards.append(sharded.compress_local_shard(local, [e - s for (_, s, e) in plan[r]], cfg))
+    parts = [sharded.standalone_header(n)]
+    n_chunks = sum(len(p) for p in plan)
+    offs = [np.concatenate([[0], np.cumsum(sz)]) for (_, sz) in shards]
+    for c in range(n_chunks):
+        r, j = c % world, c // world
+        parts.append(shards[r][0][offs[r][j]: offs[r][j + 1]])
+    parts.append(b"\x00")
+    assembled = b"".join(parts)
+    whole = sa.simple_compress(nums, cfg)
+    assert assembled == whole
+    ocfg = oracle.make_config(mode=oracle.MODE_CLASSIC, delta=oracle.DELTA_CONSECUTIVE, delta_order=1, max_page_n=page)
+    assert assembled == oracle.simple_compress(nums, ocfg)
