@@ -29,6 +29,19 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_variant(name, defines, verbose=False):
+    """Experiment builds: pcodec_b200/libcpcodec_<name>.so with extra -D flags (select with PCOB200_LIB)."""
+    out = os.path.join(HERE, f"libcpcodec_{name}.so")
+    ccbin = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
+    cmd = [_nvcc(), "-ccbin", ccbin] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + SOURCES
+    res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return out
+
+
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB

@@ -161,7 +161,7 @@ def lib():
     """Loads libcpcodec.so, building it in-tree if needed.  Never falls back to anything else."""
     global _lib
     if _lib is None:
-        path = _build.LIB
+        path = os.environ.get("PCOB200_LIB") or _build.LIB  # PCOB200_LIB: experiment builds of the same library
         if not os.path.exists(path):
             path = _build.build()
         L = C.CDLL(path)

@@ -67,7 +67,7 @@ static_assert(sizeof(IndexHeader) == 64 && sizeof(IndexChunk) == 32 && sizeof(Ba
 // Bit stream view: a byte range addressed through 8-byte aligned words.
 // ---------------------------------------------------------------------------
 struct BitSrc {
-  const uint64_t* words;  // 8-byte aligned base at or below the first byte
+  const uint64_t* words;  // 16-byte aligned base at or below the first byte (kernels also read it as 16-byte blocks)
   uint64_t n_bits;        // valid bits from `words` (i.e. (misalign + len) * 8)
   uint32_t mis_bits;      // bits between `words` and the first byte of the buffer
 };
@@ -75,8 +75,8 @@ struct BitSrc {
 __host__ __device__ inline BitSrc make_bitsrc(const void* p, size_t len) {
   uintptr_t a = (uintptr_t)p;
   BitSrc s;
-  s.words = (const uint64_t*)(a & ~uintptr_t(7));
-  s.mis_bits = uint32_t(a & 7) * 8;
+  s.words = (const uint64_t*)(a & ~uintptr_t(15));
+  s.mis_bits = uint32_t(a & 15) * 8;
   s.n_bits = uint64_t(s.mis_bits) + uint64_t(len) * 8;
   return s;
 }

@@ -14,14 +14,34 @@
 
 namespace pcob200 {
 
+#ifndef PCOB_DEC_MIN_BLOCKS
+#define PCOB_DEC_MIN_BLOCKS 2
+#endif
+#ifndef PCOB_DEC_TILE_ROWS
+#define PCOB_DEC_TILE_ROWS 256
+#endif
 constexpr int DEC_THREADS = 256;
+constexpr int DEC_TILE_ROWS = PCOB_DEC_TILE_ROWS;  // (var, batch) rows of the symbol tile; <= DEC_THREADS
 constexpr int DEC_WARPS = DEC_THREADS / 32;
 constexpr int SMALL_MAX_SIZE_LOG = 10;
 constexpr int SMALL_MAX_BINS = 256;
 constexpr int SYM_ROW_WORDS = 65;  // 256 one-byte symbols + 4 bytes pad: odd word stride -> conflict-free rows
-constexpr int CARRY_RING = 32;
+constexpr int CHAIN_RING = 32;
 constexpr int WIN_WORDS = 128;                  // 512-byte window of compressed bytes per (warp, var)
 constexpr uint32_t WIN_USABLE_BITS = WIN_WORDS * 32 - 64;
+
+// Optional region timers (build with -DPCOB_DEC_TIMING): per-warp clock64() deltas accumulated into global counters.
+#ifdef PCOB_DEC_TIMING
+__device__ unsigned long long g_dec_timing[16];
+#define PCOB_TICK(idx)                              \
+  do {                                              \
+    long long _now = clock64();                     \
+    _tacc[idx] += (unsigned long long)(_now - _tprev); \
+    _tprev = _now;                                  \
+  } while (0)
+#else
+#define PCOB_TICK(idx) do { } while (0)
+#endif
 
 // node word: next_state_idx_base (14 bits) | field (14 bits) << 14 | bits_to_read (4 bits) << 28
 //   decode tables: field = bin index;  walker tables: field = bin offset_bits
@@ -32,21 +52,40 @@ __device__ __forceinline__ uint32_t node_btr(uint32_t n) { return n >> 28; }
 // ---------------------------------------------------------------------------
 // Shared memory layout of one decode CTA (SMALL variant: size_log <= 10, n_bins <= 256)
 // ---------------------------------------------------------------------------
-struct DecodeSmem {
-  ChunkHdr hdr;
-  uint32_t node[MAX_VARS][1 << SMALL_MAX_SIZE_LOG];
+struct BinEntry {            // what phase B needs about a bin, in one 16-byte shared-memory load
+  uint64_t lower;            // (+ MID when the var is delta'd: folds toggle_center into the add)
+  uint32_t ob;               // offset bits
+  uint32_t mask;             // (1 << ob) - 1 for ob <= 32
+};
+
+struct BuildScratch {        // only live while the tables are built; shares storage with the symbol tile
   uint64_t bin_lower[MAX_VARS][SMALL_MAX_BINS];
   uint8_t bin_ob[MAX_VARS][SMALL_MAX_BINS];
   uint16_t bin_weight[MAX_VARS][SMALL_MAX_BINS];
   uint32_t bin_cum[MAX_VARS][SMALL_MAX_BINS + 1];
   uint16_t sym_of_state[MAX_VARS][1 << SMALL_MAX_SIZE_LOG];
   uint32_t rank_counter[MAX_VARS][SMALL_MAX_BINS];
+};
+
+struct DecodeSmem {
+  ChunkHdr hdr;
+  uint32_t node[MAX_VARS][1 << SMALL_MAX_SIZE_LOG];
+  alignas(16) BinEntry bin[MAX_VARS][SMALL_MAX_BINS];
+  uint32_t bin32[MAX_VARS][SMALL_MAX_BINS];  // compact: (lower - bin_base) | offset_bits << 25, valid when bin_compact[v]
+  uint64_t bin_base[MAX_VARS];
+  uint32_t bin_compact[MAX_VARS];
   uint32_t off_start[DEC_THREADS];        // per (var, batch-in-tile): bit position of the offsets section
-  uint64_t carry[CARRY_RING][MAX_ORDER];  // delta moments at the start of batch b (ring slot b % CARRY_RING)
-  volatile uint32_t carry_seq[CARRY_RING];
+  // delta carry chain: mvec[b % CHAIN_RING] = true moments at the start of batch b once m_flag[...] == b + 1
+  uint64_t mvec[CHAIN_RING][MAX_ORDER];
+  volatile uint32_t m_flag[CHAIN_RING];
+  uint64_t binom_full[MAX_ORDER];          // C(256, t): keeps the chain link free of global loads
+  uint64_t binom_lane8[32][MAX_ORDER];     // C(8 * lane, t)
   uint32_t err;
   alignas(16) uint32_t win[DEC_WARPS][MAX_VARS][WIN_WORDS + 4];  // per-warp staged copy of a batch's offset bits
-  uint32_t sym[DEC_THREADS * SYM_ROW_WORDS];
+  union {
+    uint32_t sym[DEC_TILE_ROWS * SYM_ROW_WORDS];
+    BuildScratch build;
+  };
 };
 
 // ---------------------------------------------------------------------------
@@ -149,16 +188,26 @@ template <bool WALKER>
 __device__ __forceinline__ uint64_t ans_walk_batch(const uint64_t* __restrict__ cw, uint64_t max_word, uint64_t bit, WalkState& ws,
                                                    const uint32_t* __restrict__ node, int count, uint32_t* __restrict__ sym_row,
                                                    uint32_t& ob_sum) {
-  uint64_t wi = bit >> 6;
+  // The stream is read as 16-byte blocks (two u64 words): the current block and the next one live in registers, the
+  // next one having been requested a whole block (~3 iterations) before its first use.  One 16-byte load per 128 bits
+  // halves the L1 wavefronts of these per-thread scattered reads compared with 8-byte refills.
   auto ld = [&](uint64_t i) -> uint64_t { return __ldg(cw + (i <= max_word ? i : max_word)); };
-  uint64_t w0 = ld(wi), w1 = ld(wi + 1), w2 = ld(wi + 2);
+  const uint64_t max_blk = max_word >> 1;
+  auto ldb = [&](uint64_t bidx) -> ulonglong2 {
+    return __ldg(reinterpret_cast<const ulonglong2*>(cw) + (bidx <= max_blk ? bidx : max_blk));
+  };
+  uint64_t blk = bit >> 7;
+  uint32_t pb = uint32_t(bit & 127);
+  ulonglong2 cb = ldb(blk), nb = ldb(blk + 1), nb2 = ldb(blk + 2);
   uint32_t s0 = ws.st[0], s1 = ws.st[1], s2 = ws.st[2], s3 = ws.st[3];
   uint32_t obs = 0;
   int i = 0;
   for (; i + 4 <= count; i += 4) {
     uint32_t n0 = node[s0], n1 = node[s1], n2 = node[s2], n3 = node[s3];
-    uint32_t r = uint32_t(bit & 63);
-    uint64_t g = r ? ((w0 >> r) | (w1 << (64 - r))) : w0;
+    const bool upper = pb >= 64;
+    const uint64_t lo = upper ? cb.y : cb.x, hi = upper ? nb.x : cb.y;
+    const uint32_t r = pb & 63;
+    uint64_t g = r ? ((lo >> r) | (hi << (64 - r))) : lo;
     uint32_t b0 = node_btr(n0), b1 = node_btr(n1), b2 = node_btr(n2), b3 = node_btr(n3);
     uint32_t sh1 = b0, sh2 = b0 + b1, sh3 = sh2 + b2, tot = sh3 + b3;
     uint32_t v0 = uint32_t(g) & ((1u << b0) - 1);
@@ -174,14 +223,20 @@ __device__ __forceinline__ uint64_t ans_walk_batch(const uint64_t* __restrict__ 
     s1 = node_base(n1) + v1;
     s2 = node_base(n2) + v2;
     s3 = node_base(n3) + v3;
-    bit += tot;
-    if ((bit >> 6) != wi) {
-      wi += 1;
-      w0 = w1;
-      w1 = w2;
-      w2 = ld(wi + 2);
+    pb += tot;
+    if (pb >= 128) {
+      pb -= 128;
+      blk += 1;
+      cb = nb;
+      nb = nb2;
+      nb2 = ldb(blk + 2);  // two blocks (~6 iterations) ahead of its first use
+      if ((blk & 7) == 0) {  // entering a new 128-byte line: pull the line after next into L2
+        const uint64_t pblk = blk + 16 <= max_blk ? blk + 16 : max_blk;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const ulonglong2*>(cw) + pblk));
+      }
     }
   }
+  bit = (blk << 7) + pb;
   if (i < count) {  // ragged tail of the page's last batch (page_latent_decompressor.rs:144-177)
     uint32_t packed = 0;
     uint32_t sarr[4] = {s0, s1, s2, s3};
@@ -483,22 +538,18 @@ __device__ __forceinline__ void warp_excl_scan8(L (&x)[8], L& total, int lane) {
   total = shfl_idx_L<L>(inc, 31);
 }
 
-// Field of `nbits` bits at bit position p of a shared-memory window of 32-bit words.
-__device__ __forceinline__ uint32_t bfe32(uint32_t v, uint32_t nbits) {
-  uint32_t r;
-  asm("bfe.u32 %0, %1, 0, %2;" : "=r"(r) : "r"(v), "r"(nbits));
-  return r;
-}
+// Field of up to 32 (WIDE: 64) bits at bit position p of a shared-memory window of 32-bit words.
 template <typename L, bool WIDE>
-__device__ __forceinline__ L win_extract(const uint32_t* __restrict__ win, uint32_t p, uint32_t nbits) {
+__device__ __forceinline__ L win_extract(const uint32_t* __restrict__ win, uint32_t p, uint32_t nbits, uint32_t mask) {
   const uint32_t w = p >> 5, r = p & 31;
   const uint32_t lo = win[w], mid = win[w + 1];
   const uint32_t v0 = __funnelshift_r(lo, mid, r);
-  if (!WIDE) return L(bfe32(v0, nbits));
+  if (!WIDE) return L(v0 & mask);
+  if (nbits <= 32) return L(v0 & mask);
   const uint32_t hi = win[w + 2];
   const uint32_t v1 = __funnelshift_r(mid, hi, r);
-  if (nbits <= 32) return L(bfe32(v0, nbits));
-  return L((uint64_t(bfe32(v1, nbits - 32)) << 32) | v0);
+  const uint32_t m1 = nbits >= 64 ? 0xffffffffu : ((1u << (nbits - 32)) - 1);
+  return L((uint64_t(v1 & m1) << 32) | v0);
 }
 
 // from_latent_ordered with the number kind hoisted: 0 unsigned, 1 signed, 2 float
@@ -511,44 +562,58 @@ __device__ __forceinline__ L from_latent_kind(L l, int kind) {
   return L(l ^ L(L(s - 1) | MID));
 }
 
-// Un-delta of one batch held 8-per-lane in registers.  The batch is scanned with zero-seeded moments (K nested exclusive
-// scans), which needs nothing from earlier batches; the true moments m at the batch start arrive through a shared-memory
-// ring from the warp that owns the previous batch (m' = A^256 m + c, A = I + superdiagonal, so (A^n)_{j,j+t} = C(n,t)),
-// and are folded in by linearity: x_i += (A^i m)_0.
+// ---------------------------------------------------------------------------
+// Consecutive un-delta (delta/consecutive.rs:35-50) of a batch held 8-per-lane in registers, split in two:
+//   undelta_local : K nested exclusive scans with ZERO seeds (needs nothing from earlier batches); c_j = batch sum of x^(j+1)
+//   apply_moments : adds (A^i m)_0 to element i, where m are the true moments at the batch start (linearity of the recurrence
+//                   m' = A m + e d,  A = I + superdiagonal, so (A^n)_{j,j+t} = C(n,t) mod 2^w)
+// The moments travel along a chain m_{b+1} = A^256 m_b + c_b; each warp runs the link of its own batch.
+// ---------------------------------------------------------------------------
 template <typename L, int K>
-__device__ __forceinline__ void undelta_batch(L (&x)[8], DecodeSmem& sm, const Binoms* __restrict__ binoms, uint32_t b, int lane) {
-  L c[K];
+__device__ __forceinline__ void undelta_local(L (&x)[8], L (&c)[K], int lane) {
 #pragma unroll
   for (int lvl = 0; lvl < K; lvl++) {
     L total;
     warp_excl_scan8<L>(x, total, lane);
-    c[K - 1 - lvl] = total;  // c_j = sum over the batch of x^(j+1)
+    c[K - 1 - lvl] = total;
   }
-  const uint32_t slot = b % CARRY_RING, nslot = (b + 1) % CARRY_RING;
-  // every lane polls (a broadcast shared-memory read), so no extra warp barrier sits on the chain
-  while (sm.carry_seq[slot] != b + 1) {
+}
+
+// One batch's un-delta, everything in registers: zero-seeded scans, then this warp's link of the moment chain
+// (wait for m_b, publish m_{b+1} = A^256 m_b + c_b), then fold m_b into the 8 values of each lane.  The link reads only
+// shared memory: with most of L1 carved out for shared memory, a global or local load here is an L2 round trip on
+// the one serial dependency of the chunk (measured: 52 % of warp time was chain wait before this).
+template <typename L, int K>
+__device__ __forceinline__ void undelta_chain(L (&x)[8], DecodeSmem& sm, uint32_t b, int lane) {
+  L c[K];
+  undelta_local<L, K>(x, c, lane);
+  const uint32_t slot = b % CHAIN_RING, nslot = (b + 1) % CHAIN_RING;
+  L bl8[K];
+#pragma unroll
+  for (int t = 0; t < K; t++) bl8[t] = L(sm.binom_lane8[lane][t]);
+  while (sm.m_flag[slot] != b + 1) {
   }
   __threadfence_block();
   L m[K];
 #pragma unroll
-  for (int k = 0; k < K; k++) m[k] = L(sm.carry[slot][k]);
+  for (int k = 0; k < K; k++) m[k] = L(sm.mvec[slot][k]);
   if (lane == 0) {
 #pragma unroll
     for (int j = 0; j < K; j++) {
       L acc = c[j];
 #pragma unroll
-      for (int t = 0; j + t < K; t++) acc = L(acc + L(L(binoms->full[t]) * m[j + t]));
-      sm.carry[nslot][j] = uint64_t(acc);
+      for (int t = 0; j + t < K; t++) acc = L(acc + L(L(sm.binom_full[t]) * m[j + t]));
+      sm.mvec[nslot][j] = uint64_t(acc);
     }
     __threadfence_block();
-    sm.carry_seq[nslot] = b + 2;
+    sm.m_flag[nslot] = b + 2;
   }
   L s[K];
 #pragma unroll
   for (int j = 0; j < K; j++) {
     L acc = 0;
 #pragma unroll
-    for (int t = 0; j + t < K; t++) acc = L(acc + L(L(binoms->lane8[lane][t]) * m[j + t]));
+    for (int t = 0; j + t < K; t++) acc = L(acc + L(bl8[t] * m[j + t]));
     s[j] = acc;
   }
 #pragma unroll
@@ -559,11 +624,51 @@ __device__ __forceinline__ void undelta_batch(L (&x)[8], DecodeSmem& sm, const B
   }
 }
 
+// 8 consecutive numbers per lane <-> global memory, 16-byte accesses
+template <typename L>
+__device__ __forceinline__ void store8(L* __restrict__ dst, const L (&r)[8]) {
+  if (sizeof(L) == 8) {
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const uint64_t a = uint64_t(r[2 * q]), bb = uint64_t(r[2 * q + 1]);
+      d4[q] = make_uint4(uint32_t(a), uint32_t(a >> 32), uint32_t(bb), uint32_t(bb >> 32));
+    }
+  } else if (sizeof(L) == 4) {
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    d4[0] = make_uint4(uint32_t(r[0]), uint32_t(r[1]), uint32_t(r[2]), uint32_t(r[3]));
+    d4[1] = make_uint4(uint32_t(r[4]), uint32_t(r[5]), uint32_t(r[6]), uint32_t(r[7]));
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; e++) dst[e] = r[e];
+  }
+}
+template <typename L>
+__device__ __forceinline__ void load8(const L* __restrict__ src, L (&r)[8]) {
+  if (sizeof(L) == 8) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const uint4 v = s4[q];
+      r[2 * q] = L((uint64_t(v.y) << 32) | v.x);
+      r[2 * q + 1] = L((uint64_t(v.w) << 32) | v.z);
+    }
+  } else if (sizeof(L) == 4) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    const uint4 a = s4[0], bq = s4[1];
+    r[0] = L(a.x); r[1] = L(a.y); r[2] = L(a.z); r[3] = L(a.w);
+    r[4] = L(bq.x); r[5] = L(bq.y); r[6] = L(bq.z); r[7] = L(bq.w);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 8; e++) r[e] = src[e];
+  }
+}
+
 // ---------------------------------------------------------------------------
 // decode_kernel: one CTA per chunk.
 // ---------------------------------------------------------------------------
 template <typename L>
-__global__ void __launch_bounds__(DEC_THREADS, 2)
+__global__ void __launch_bounds__(DEC_THREADS, PCOB_DEC_MIN_BLOCKS)
 decode_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, uint32_t* __restrict__ statuses, const uint8_t* __restrict__ index_base,
               L* __restrict__ out, uint64_t out_len, const Binoms* __restrict__ binoms) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -574,6 +679,10 @@ decode_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, uint32_t* __
   const uint64_t max_word = src.n_bits == 0 ? 0 : (src.n_bits - 1) >> 6;
   const uint64_t chunk_bit0 = src.mis_bits + task.chunk_offset * 8;
   const bool is_float = nt_is_float(fp.dtype), is_signed = nt_is_signed(fp.dtype);
+#ifdef PCOB_DEC_TIMING
+  long long _tprev = clock64();
+  unsigned long long _tacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#endif
 
   if (tid == 0) {
     sm.err = 0;
@@ -589,7 +698,9 @@ decode_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, uint32_t* __
       if (task.n != 0 && task.n != sm.hdr.n) sm.hdr.status = ST_CORRUPTION;
     }
   }
-  for (int i = tid; i < CARRY_RING; i += DEC_THREADS) sm.carry_seq[i] = 0;
+  for (int i = tid; i < CHAIN_RING; i += DEC_THREADS) sm.m_flag[i] = 0;
+  for (int i = tid; i < 32 * MAX_ORDER; i += DEC_THREADS) sm.binom_lane8[i / MAX_ORDER][i % MAX_ORDER] = binoms->lane8[i / MAX_ORDER][i % MAX_ORDER];
+  if (tid < MAX_ORDER) sm.binom_full[tid] = binoms->full[tid];
   __syncthreads();
   if (sm.hdr.status != ST_OK) {
     if (tid == 0) statuses[blockIdx.x] = sm.hdr.status;
@@ -597,12 +708,40 @@ decode_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, uint32_t* __
   }
   const uint32_t n_vars = sm.hdr.n_vars;
   for (uint32_t v = 0; v < n_vars; v++)
-    build_var_tables<false>(src, sm.hdr, v, sm.node[v], sm.bin_lower[v], sm.bin_ob[v], sm.bin_weight[v], sm.bin_cum[v], sm.sym_of_state[v],
-                            sm.rank_counter[v], &sm.err, /*add_mid_to_lower=*/sm.hdr.var[v].delta_order > 0);
+    build_var_tables<false>(src, sm.hdr, v, sm.node[v], sm.build.bin_lower[v], sm.build.bin_ob[v], sm.build.bin_weight[v], sm.build.bin_cum[v],
+                            sm.build.sym_of_state[v], sm.build.rank_counter[v], &sm.err, /*add_mid_to_lower=*/sm.hdr.var[v].delta_order > 0);
   __syncthreads();
   if (sm.err) {
     if (tid == 0) statuses[blockIdx.x] = sm.err;
     return;
+  }
+  for (uint32_t v = 0; v < n_vars; v++) {
+    const uint32_t nbv = max(sm.hdr.var[v].n_bins, 1u);
+    for (uint32_t i = tid; i < nbv; i += DEC_THREADS) {
+      BinEntry be;
+      be.lower = sm.build.bin_lower[v][i];
+      be.ob = sm.build.bin_ob[v][i];
+      be.mask = be.ob >= 32 ? 0xffffffffu : ((1u << be.ob) - 1);
+      sm.bin[v][i] = be;
+    }
+  }
+  __syncthreads();
+  if (tid < int(n_vars)) {
+    // bins whose lowers span < 2^25 (deltas around a centre, small alphabets, ...) get a 4-byte table entry: one
+    // shared-memory wavefront per lookup instead of four
+    const uint32_t v = tid, nbv = max(sm.hdr.var[v].n_bins, 1u);
+    const uint64_t lmask = LT<L>::BITS == 64 ? ~uint64_t(0) : ((uint64_t(1) << LT<L>::BITS) - 1);
+    uint64_t base = sm.bin[v][0].lower;
+    bool ok = true;
+    // lowers ascend in symbol order for every stream pco writes; measure the span relative to the first bin
+    for (uint32_t i = 0; i < nbv; i++) {
+      const uint64_t d = (sm.bin[v][i].lower - base) & lmask;
+      if (d >= (1u << 25)) ok = false;
+    }
+    sm.bin_base[v] = base;
+    sm.bin_compact[v] = ok ? 1u : 0u;
+    if (ok)
+      for (uint32_t i = 0; i < nbv; i++) sm.bin32[v][i] = uint32_t((sm.bin[v][i].lower - base) & lmask) | (sm.bin[v][i].ob << 25);
   }
 
   const uint32_t n = sm.hdr.n;
@@ -611,7 +750,7 @@ decode_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, uint32_t* __
   const uint32_t nb_total = n_batches_of(n);
   const uint32_t nb_out = n_batches_of(n_out);
   const uint32_t order = sm.hdr.var[0].delta_order;
-  const uint32_t tile_b = DEC_THREADS / n_vars;  // batches per tile
+  const uint32_t tile_b = DEC_TILE_ROWS / n_vars;  // batches per tile
   const bool need_index = (sm.hdr.var[0].n_bins > 1) || (n_vars > 1 && sm.hdr.var[1].n_bins > 1);
   const BatchEntry* entries = (task.entries_offset != 0 && index_base)
                                   ? reinterpret_cast<const BatchEntry*>(index_base + task.entries_offset) : nullptr;
@@ -619,19 +758,22 @@ decode_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, uint32_t* __
     if (tid == 0) statuses[blockIdx.x] = ST_INVALID_ARGUMENT;
     return;
   }
-  // closed-form section sizes when every var is trivial (n_bins <= 1): bits per full batch
-  const uint32_t ob0 = sm.hdr.var[0].n_bins >= 1 ? sm.bin_ob[0][0] : 0;
-  const uint32_t ob1 = (n_vars > 1 && sm.hdr.var[1].n_bins >= 1) ? sm.bin_ob[1][0] : 0;
+  // closed-form section sizes when every var is trivial (n_bins <= 1)
+  const uint32_t ob0 = sm.hdr.var[0].n_bins >= 1 ? sm.build.bin_ob[0][0] : 0;
+  const uint32_t ob1 = (n_vars > 1 && sm.hdr.var[1].n_bins >= 1) ? sm.build.bin_ob[1][0] : 0;
   const uint32_t stored0 = var_stored_n(n, sm.hdr.var[0].delta_order);
   const uint32_t stored1 = n_vars > 1 ? var_stored_n(n, sm.hdr.var[1].delta_order) : 0;
 
   if (tid == 0 && order > 0) {
-    for (uint32_t k = 0; k < order; k++) sm.carry[0][k] = sm.hdr.moments[0][k];
+    for (uint32_t k = 0; k < order; k++) sm.mvec[0][k] = sm.hdr.moments[0][k];
     __threadfence_block();
-    sm.carry_seq[0] = 1;  // seq = batch index + 1
+    sm.m_flag[0] = 1;
   }
-  __syncthreads();
+  __syncthreads();  // tables, bin entries and the chain seed are in place; the build scratch (aliased by the tile) is dead
 
+  PCOB_TICK(0);  // prologue
+  const int kind = is_float ? 2 : (is_signed ? 1 : 0);
+  const uint32_t mode = sm.hdr.mode;
   uint32_t end_err = 0;
   for (uint32_t tile_start = 0; tile_start < nb_out; tile_start += tile_b) {
     const uint32_t tile_n = min(tile_b, nb_out - tile_start);
@@ -653,26 +795,24 @@ decode_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, uint32_t* __
             bit = ans_walk_batch<false>(src.words, max_word, min(bit, src.n_bits), ws, sm.node[v], int(cnt), &sm.sym[tid * SYM_ROW_WORDS], dummy);
           }
         } else {
-          // all vars trivial: batch b' < b contributes count0*ob0 + count1*ob1 bits
-          uint64_t before = 0;
-          uint32_t full = b;  // full batches before b hold 256 each unless truncated by stored_n
-          uint64_t c0 = min(uint64_t(full) * BATCH_N, uint64_t(stored0));
-          uint64_t c1 = min(uint64_t(full) * BATCH_N, uint64_t(stored1));
-          before = c0 * ob0 + c1 * ob1;
+          // all vars trivial: batches before b contribute count0*ob0 + count1*ob1 bits
+          const uint64_t c0 = min(uint64_t(b) * BATCH_N, uint64_t(stored0));
+          const uint64_t c1 = min(uint64_t(b) * BATCH_N, uint64_t(stored1));
+          uint64_t before = c0 * ob0 + c1 * ob1;
           if (v == 1) before += uint64_t(batch_count(stored0, b)) * ob0;
           bit = sm.hdr.body_bit + before;
         }
         sm.off_start[tid] = uint32_t(min(bit, src.n_bits) - chunk_bit0);
       }
     }
+    PCOB_TICK(1);  // phase A work
     __syncthreads();
+    PCOB_TICK(2);  // barrier after phase A
     // ---------------- phase B: one warp per batch ----------------
-    // A batch's offset bits are one contiguous run of the compressed stream.  Each warp copies a 512-byte window of
-    // it with two coalesced 8-byte loads per lane -- issued one batch ahead, so the DRAM/L2 latency is covered by
-    // the previous batch's work -- parks it in shared memory and extracts the variable-width fields from there.
+    // A batch's offset bits are one contiguous run of the stream.  Each warp copies a 512-byte window of it with two
+    // coalesced 8-byte loads per lane -- issued one batch ahead so the DRAM/L2 latency hides behind the previous
+    // batch -- parks it in shared memory and extracts the variable-width fields from there.
     {
-      const int kind = is_float ? 2 : (is_signed ? 1 : 0);
-      const uint32_t mode = sm.hdr.mode;
       uint64_t pf[MAX_VARS][2];
       auto issue_window_loads = [&](uint32_t bl_n) {
 #pragma unroll
@@ -700,6 +840,7 @@ decode_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, uint32_t* __
         }
         __syncwarp();
         if (bl + DEC_WARPS < tile_n) issue_window_loads(bl + DEC_WARPS);
+        PCOB_TICK(3);  // window staging
         L lat[MAX_VARS][8];
         uint64_t last_end = 0;
 #pragma unroll
@@ -710,8 +851,6 @@ decode_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, uint32_t* __
           const uint32_t row = (v * tile_b + bl);
           const bool full = cnt == BATCH_N;
           uint32_t sy[8];
-          uint32_t ob[8];
-          uint32_t lane_bits = 0;
           if (vh.n_bins > 1) {
             const uint32_t* rowp = &sm.sym[row * SYM_ROW_WORDS + lane * 2];
             const uint32_t p0 = rowp[0], p1 = rowp[1];
@@ -721,17 +860,31 @@ decode_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, uint32_t* __
 #pragma unroll
             for (int e = 0; e < 8; e++) sy[e] = 0;
           }
-          if (full) {
+          // ---- bins: offset bits and lower bound of every latent
+          const bool compact = sm.bin_compact[v] != 0;
+          uint32_t obv[8];
+          L lowv[8];
+          uint32_t lane_bits = 0;
+          if (compact) {
+            const L base = L(sm.bin_base[v]);
 #pragma unroll
-            for (int e = 0; e < 8; e++) { ob[e] = sm.bin_ob[v][sy[e]]; lane_bits += ob[e]; }
+            for (int e = 0; e < 8; e++) {
+              const uint32_t q = sm.bin32[v][sy[e]];
+              obv[e] = q >> 25;
+              lowv[e] = L(base + L(q & 0x1ffffffu));
+            }
           } else {
 #pragma unroll
             for (int e = 0; e < 8; e++) {
-              const bool valid = uint32_t(lane * 8 + e) < cnt;
-              if (!valid) sy[e] = 0;
-              ob[e] = valid ? uint32_t(sm.bin_ob[v][sy[e]]) : 0;
-              lane_bits += ob[e];
+              const uint4 q = *reinterpret_cast<const uint4*>(&sm.bin[v][sy[e]]);
+              lowv[e] = L((uint64_t(q.y) << 32) | q.x);
+              obv[e] = q.z;
             }
+          }
+#pragma unroll
+          for (int e = 0; e < 8; e++) {
+            if (!full && uint32_t(lane * 8 + e) >= cnt) obv[e] = 0;
+            lane_bits += obv[e];
           }
           uint32_t inc = lane_bits;
 #pragma unroll
@@ -744,21 +897,36 @@ decode_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, uint32_t* __
           last_end = sec_bit + total_bits;
           if (vh.max_offset_bits == 0) {
 #pragma unroll
-            for (int e = 0; e < 8; e++) lat[v][e] = L(sm.bin_lower[v][sy[e]]);
+            for (int e = 0; e < 8; e++) lat[v][e] = lowv[e];
           } else if (total_bits <= WIN_USABLE_BITS) {
             const uint32_t* win = sm.win[warp][v];
             uint32_t p = uint32_t(sec_bit & 63) + (inc - lane_bits);
-            if (LT<L>::BITS <= 32 || vh.max_offset_bits <= 32) {
+            const bool narrow = LT<L>::BITS <= 32 || vh.max_offset_bits <= 32;
+            if (narrow && !__any_sync(0xffffffffu, lane_bits > 64)) {
+              // the lane's 8 fields are contiguous and span <= 64 bits: fetch its 3 words once, extract from registers
+              const uint32_t w = p >> 5;
+              const uint32_t x0 = win[w], x1 = win[w + 1], x2 = win[w + 2];
+              uint32_t pos = p & 31;
 #pragma unroll
               for (int e = 0; e < 8; e++) {
-                lat[v][e] = L(L(sm.bin_lower[v][sy[e]]) + win_extract<L, false>(win, p, ob[e]));
-                p += ob[e];
+                const uint32_t wd = pos >> 5, rr = pos & 31;
+                const uint32_t lo = wd == 0 ? x0 : (wd == 1 ? x1 : x2);
+                const uint32_t hi = wd == 0 ? x1 : (wd == 1 ? x2 : 0u);
+                const uint32_t f = __funnelshift_r(lo, hi, rr) & uint32_t(~(~uint64_t(0) << obv[e]));
+                lat[v][e] = L(lowv[e] + L(f));
+                pos += obv[e];
+              }
+            } else if (narrow) {
+#pragma unroll
+              for (int e = 0; e < 8; e++) {
+                lat[v][e] = L(lowv[e] + win_extract<L, false>(win, p, obv[e], uint32_t(~(~uint64_t(0) << obv[e]))));
+                p += obv[e];
               }
             } else {
 #pragma unroll
               for (int e = 0; e < 8; e++) {
-                lat[v][e] = L(L(sm.bin_lower[v][sy[e]]) + win_extract<L, true>(win, p, ob[e]));
-                p += ob[e];
+                lat[v][e] = L(lowv[e] + win_extract<L, true>(win, p, obv[e], uint32_t(~(~uint64_t(0) << min(obv[e], 32u)))));
+                p += obv[e];
               }
             }
           } else {
@@ -767,78 +935,70 @@ decode_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, uint32_t* __
 #pragma unroll
             for (int e = 0; e < 8; e++) {
               L off = 0;
-              if (ob[e] != 0) off = read_offset<L>(src.words, max_word, min(pos, src.n_bits), ob[e]);
-              pos += ob[e];
-              lat[v][e] = L(L(sm.bin_lower[v][sy[e]]) + off);
+              if (obv[e] != 0) off = read_offset<L>(src.words, max_word, min(pos, src.n_bits), obv[e]);
+              pos += obv[e];
+              lat[v][e] = L(lowv[e] + off);
             }
           }
           // positions past the stored latents of a delta'd var hold deltas that cannot influence any emitted
           // number (page_latent_decompressor.rs:244-248); any value works there
         }
-        // ---- un-delta of the primary (delta/consecutive.rs:35-50), specialised on the order
-        switch (order) {
-          case 0: break;
-          case 1: undelta_batch<L, 1>(lat[0], sm, binoms, b, lane); break;
-          case 2: undelta_batch<L, 2>(lat[0], sm, binoms, b, lane); break;
-          case 3: undelta_batch<L, 3>(lat[0], sm, binoms, b, lane); break;
-          case 4: undelta_batch<L, 4>(lat[0], sm, binoms, b, lane); break;
-          case 5: undelta_batch<L, 5>(lat[0], sm, binoms, b, lane); break;
-          case 6: undelta_batch<L, 6>(lat[0], sm, binoms, b, lane); break;
-          default: undelta_batch<L, 7>(lat[0], sm, binoms, b, lane); break;
-        }
-        // ---- join (mode/*.rs)
-        L res[8];
-        if (mode == MODE_CLASSIC) {
-#pragma unroll
-          for (int e = 0; e < 8; e++) res[e] = from_latent_kind<L>(lat[0][e], kind);
-        } else if (mode == MODE_INT_MULT) {
-          const L base = L(sm.hdr.mode_base);
-#pragma unroll
-          for (int e = 0; e < 8; e++) res[e] = from_latent_kind<L>(L(L(lat[0][e] * base) + lat[1][e]), kind);
-        } else if (mode == MODE_FLOAT_MULT) {
-          constexpr L MID = L(L(1) << (LT<L>::BITS - 1));
-          const L base_bits = from_latent_ordered<L>(L(sm.hdr.mode_base), true, false);
-#pragma unroll
-          for (int e = 0; e < 8; e++) {
-            const L un = float_mult_unadjusted(lat[0][e], base_bits);
-            const L u = to_latent_ordered<L>(un, true, false);
-            res[e] = from_latent_kind<L>(L(L(u + lat[1][e]) + MID), 2);
-          }
-        } else {  // MODE_FLOAT_QUANT
-          const uint32_t k = sm.hdr.mode_k;
-          constexpr L MID = L(L(1) << (LT<L>::BITS - 1));
-          const L sign_cutoff = L(MID >> k);
-          const L kmax = L(L(L(1) << k) - 1);
-#pragma unroll
-          for (int e = 0; e < 8; e++) {
-            const L pq = lat[0][e];
-            const L lowest = pq >= sign_cutoff ? lat[1][e] : L(kmax - lat[1][e]);
-            res[e] = from_latent_kind<L>(L(L(pq << k) + lowest), 2);
-          }
-        }
-        // ---- store: 8 consecutive numbers per lane
+        PCOB_TICK(4);  // symbols, bins, scan, extraction
         L* dst = out + task.out_offset + size_t(b) * BATCH_N + lane * 8;
-        if (out_cnt == BATCH_N) {
-          if (sizeof(L) == 8) {
-            uint4* d4 = reinterpret_cast<uint4*>(dst);
+        if (order > 0) {
+          // ---- un-delta of the primary (delta/consecutive.rs:35-50)
+          PCOB_TICK(5);
+          switch (order) {
+            case 1: undelta_chain<L, 1>(lat[0], sm, b, lane); break;
+            case 2: undelta_chain<L, 2>(lat[0], sm, b, lane); break;
+            case 3: undelta_chain<L, 3>(lat[0], sm, b, lane); break;
+            case 4: undelta_chain<L, 4>(lat[0], sm, b, lane); break;
+            case 5: undelta_chain<L, 5>(lat[0], sm, b, lane); break;
+            case 6: undelta_chain<L, 6>(lat[0], sm, b, lane); break;
+            default: undelta_chain<L, 7>(lat[0], sm, b, lane); break;
+          }
+          PCOB_TICK(6);  // scans + chain wait + link + fold
+        }
+        {
+          // ---- join (mode/*.rs)
+          L res[8];
+          if (mode == MODE_CLASSIC) {
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-              const uint64_t a = uint64_t(res[2 * q]), bb = uint64_t(res[2 * q + 1]);
-              d4[q] = make_uint4(uint32_t(a), uint32_t(a >> 32), uint32_t(bb), uint32_t(bb >> 32));
+            for (int e = 0; e < 8; e++) res[e] = from_latent_kind<L>(lat[0][e], kind);
+          } else if (mode == MODE_INT_MULT) {
+            const L base = L(sm.hdr.mode_base);
+#pragma unroll
+            for (int e = 0; e < 8; e++) res[e] = from_latent_kind<L>(L(L(lat[0][e] * base) + lat[1][e]), kind);
+          } else if (mode == MODE_FLOAT_MULT) {
+            constexpr L MID = L(L(1) << (LT<L>::BITS - 1));
+            const L base_bits = from_latent_ordered<L>(L(sm.hdr.mode_base), true, false);
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+              const L un = float_mult_unadjusted(lat[0][e], base_bits);
+              const L u = to_latent_ordered<L>(un, true, false);
+              res[e] = from_latent_kind<L>(L(L(u + lat[1][e]) + MID), 2);
             }
-          } else if (sizeof(L) == 4) {
-            uint4* d4 = reinterpret_cast<uint4*>(dst);
-            d4[0] = make_uint4(uint32_t(res[0]), uint32_t(res[1]), uint32_t(res[2]), uint32_t(res[3]));
-            d4[1] = make_uint4(uint32_t(res[4]), uint32_t(res[5]), uint32_t(res[6]), uint32_t(res[7]));
+          } else {  // MODE_FLOAT_QUANT
+            const uint32_t k = sm.hdr.mode_k;
+            constexpr L MID = L(L(1) << (LT<L>::BITS - 1));
+            const L sign_cutoff = L(MID >> k);
+            const L kmax = L(L(L(1) << k) - 1);
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+              const L pq = lat[0][e];
+              const L lowest = pq >= sign_cutoff ? lat[1][e] : L(kmax - lat[1][e]);
+              res[e] = from_latent_kind<L>(L(L(pq << k) + lowest), 2);
+            }
+          }
+          if (out_cnt == BATCH_N) {
+            store8<L>(dst, res);
           } else {
 #pragma unroll
-            for (int e = 0; e < 8; e++) dst[e] = res[e];
+            for (int e = 0; e < 8; e++)
+              if (uint32_t(lane * 8 + e) < out_cnt) dst[e] = res[e];
           }
-        } else {
-#pragma unroll
-          for (int e = 0; e < 8; e++)
-            if (uint32_t(lane * 8 + e) < out_cnt) dst[e] = res[e];
         }
+        PCOB_TICK(7);  // chain link, moments, join, store
         // ---- end-of-page checks by the warp that owns the last batch (page_decompressor.rs:184-188)
         if (b == nb_total - 1 && lane == 0) {
           const uint64_t bit = last_end;
@@ -850,8 +1010,14 @@ decode_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, uint32_t* __
         }
       }
     }
+    PCOB_TICK(8);  // loop tail
     __syncthreads();
+    PCOB_TICK(9);  // barrier after phase B
   }
+#ifdef PCOB_DEC_TIMING
+  if (lane == 0)
+    for (int i = 0; i < 10; i++) atomicAdd(&g_dec_timing[i], _tacc[i]);
+#endif
   if (end_err) atomicMax(&sm.err, end_err);
   __syncthreads();
   if (tid == 0) statuses[blockIdx.x] = sm.err;

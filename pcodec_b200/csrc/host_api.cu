@@ -351,6 +351,17 @@ enum PcoError pco_standalone_simple_compress_into(const void* nums, size_t n, un
   return e == PCO_B200_OK ? PcoSuccess : PcoCompressionError;
 }
 
+#ifdef PCOB_DEC_TIMING
+// experiment builds only: read and reset the decode kernel's region timers
+int pco_b200_debug_dec_timing(unsigned long long* out16) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out16, g_dec_timing, sizeof(unsigned long long) * 16);
+  unsigned long long z[16] = {0};
+  cudaMemcpyToSymbol(g_dec_timing, z, sizeof(z));
+  return 0;
+}
+#endif
+
 void pco_b200_profile_enable(int on) { profiler().enabled = on != 0; }
 // Copies "name=ms;name=ms;..." of the last finished call into buf; returns the number of spans.
 int pco_b200_profile_last(char* buf, size_t cap) {
