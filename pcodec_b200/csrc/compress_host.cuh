@@ -253,7 +253,9 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
   static bool plan_attr_set = false;
   if (!plan_attr_set) {
     plan_attr_set = true;
-    PCOB_CUDA_TRY(cudaFuncSetAttribute(plan_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PlanSmem)));
+    PCOB_CUDA_TRY(cudaFuncSetAttribute(plan_kernel<L, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PlanSmem) + 64));
+    PCOB_CUDA_TRY(cudaFuncSetAttribute(plan_kernel<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(sizeof(PlanSmem) + 64 + ((size_t(1) << PLAN_MAX_COUNT_BITS) + 1) * 4)));
     PCOB_CUDA_TRY(cudaFuncSetAttribute(pack_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PackSmem)));
   }
   for (uint32_t v = 0; v < ep.n_vars; v++) {
@@ -263,14 +265,22 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
     uint32_t range_bits = 0;
     PCOB_CUDA_TRY(cudaMemcpyAsync(&range_bits, d_small, 4, cudaMemcpyDeviceToHost, stream));
     PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
+    if (range_bits <= PLAN_MAX_COUNT_BITS) {
+      // small key range (the usual case once the chunk minimum is subtracted): counting histogram, no sort
+      const size_t smem = ((sizeof(PlanSmem) + 15) & ~size_t(15)) + ((size_t(1) << range_bits) + 1) * 4 + 16;
+      profiler().begin("plan_kernel_counting", stream);
+      plan_kernel<L, true><<<n_chunks, PLAN_THREADS, smem, stream>>>(ep, d_lat[v], d_chunks, d_plans, int(v), range_bits);
+      profiler().end(stream);
+      continue;
+    }
     profiler().begin("sort_keys_kernel", stream);
-  sort_keys_kernel<L><<<n_chunks * tiles_per_chunk, 256, 0, stream>>>(ep, tiles_per_chunk, d_lat[v], S.keys_a.as<L>(), d_chunks, int(v));
-  profiler().end(stream);
+    sort_keys_kernel<L><<<n_chunks * tiles_per_chunk, 256, 0, stream>>>(ep, tiles_per_chunk, d_lat[v], S.keys_a.as<L>(), d_chunks, int(v));
+    profiler().end(stream);
     uint64_t* seg_begin = S.seg.as<uint64_t>();
     uint64_t* seg_end = seg_begin + n_chunks;
     segment_offsets_kernel<<<(n_chunks + 255) / 256, 256, 0, stream>>>(ep, order_v, seg_begin, seg_end);
     const L* sorted = S.keys_a.as<L>();
-    if (range_bits > 0) {
+    {
       cub::DoubleBuffer<L> db(S.keys_a.as<L>(), S.keys_b.as<L>());
       size_t tmp_bytes = 0;
       PCOB_CUDA_TRY(cub::DeviceSegmentedRadixSort::SortKeys(nullptr, tmp_bytes, db, int64_t(n), int64_t(n_chunks), seg_begin, seg_end, 0,
@@ -283,8 +293,8 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
       sorted = db.Current();
     }
     profiler().begin("plan_kernel", stream);
-  plan_kernel<L><<<n_chunks, PLAN_THREADS, sizeof(PlanSmem), stream>>>(ep, sorted, d_chunks, d_plans, int(v));
-  profiler().end(stream);
+    plan_kernel<L, false><<<n_chunks, PLAN_THREADS, sizeof(PlanSmem) + 64, stream>>>(ep, sorted, d_chunks, d_plans, int(v), range_bits);
+    profiler().end(stream);
   }
   fallback_kernel<<<(n_chunks + 255) / 256, 256, 0, stream>>>(ep, d_plans, d_chunks);
   // ---- K3, K4

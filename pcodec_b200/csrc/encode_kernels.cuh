@@ -322,7 +322,8 @@ __global__ void segment_offsets_kernel(EncParams ep, uint32_t order_v, uint64_t*
 // ---------------------------------------------------------------------------
 // plan_kernel: one CTA per (chunk, var).  Input: the var's stored latents sorted ascending (as keys = l - min).
 // ---------------------------------------------------------------------------
-constexpr int PLAN_THREADS = 256;
+constexpr int PLAN_THREADS = 512;
+constexpr uint32_t PLAN_MAX_COUNT_BITS = 15;  // counting histogram (no sort) when the key range fits 2^15 shared-memory counters
 
 struct PlanSmem {
   // histogram boundary probes
@@ -351,17 +352,53 @@ struct PlanSmem {
   uint32_t rank_counter[ENC_MAXB];
 };
 
-template <typename L>
-__global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(EncParams ep, const L* __restrict__ sorted_keys, const ChunkEnc* __restrict__ chunks,
-                                                             VarPlan* __restrict__ plans, int v) {
+// COUNTING = false: `keys` holds the var's stored latents minus the chunk minimum, sorted ascending per chunk.
+// COUNTING = true : `keys` holds the raw (unsorted) latents and the key range is < 2^range_bits <= 2^15: the CTA counts
+//                   every key into shared memory, prefix-sums the counters, and reads ranks / run extents off the
+//                   cumulative counts -- the planner only ever needs order statistics, never the sorted array.
+template <typename L, bool COUNTING>
+__global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(EncParams ep, const L* __restrict__ keys, const ChunkEnc* __restrict__ chunks,
+                                                             VarPlan* __restrict__ plans, int v, uint32_t range_bits) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   PlanSmem& sm = *reinterpret_cast<PlanSmem*>(smem_raw);
+  uint32_t* cum = reinterpret_cast<uint32_t*>(smem_raw + ((sizeof(PlanSmem) + 15) & ~size_t(15)));  // COUNTING: 2^range_bits + 1 entries
+  __shared__ uint32_t scan_part[PLAN_THREADS / 32];
   const uint32_t c = blockIdx.x;
   const int tid = threadIdx.x;
   const uint64_t cs = ep.chunk_starts[c], ce = ep.chunk_starts[c + 1];
   const uint64_t sb = stored_begin(cs, ce, v == 0 ? ep.order : 0);
   const uint32_t n = uint32_t(ce - sb);  // stored latents
-  const L* s = sorted_keys + sb;
+  const L* s = keys + sb;
+  const uint32_t n_vals = COUNTING ? (1u << range_bits) : 0u;
+  if (COUNTING && n > 0) {
+    const L mn = L(chunks[c].vmin[v]);
+    for (uint32_t i = tid; i <= n_vals; i += PLAN_THREADS) cum[i] = 0;
+    __syncthreads();
+    for (uint32_t i = tid; i < n; i += PLAN_THREADS) atomicAdd(&cum[uint32_t(L(s[i] - mn))], 1u);
+    __syncthreads();
+    // exclusive scan of the counters: each thread owns a contiguous slice
+    const uint32_t per = (n_vals + PLAN_THREADS - 1) / PLAN_THREADS;
+    const uint32_t lo = min(n_vals, tid * per), hi = min(n_vals, lo + per);
+    uint32_t sum = 0;
+    for (uint32_t i = lo; i < hi; i++) sum += cum[i];
+    uint32_t inc = sum;
+    for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if ((tid & 31) >= d) inc += o; }
+    if ((tid & 31) == 31) scan_part[tid >> 5] = inc;
+    __syncthreads();
+    uint32_t wbase = 0;
+    for (int w = 0; w < (tid >> 5); w++) wbase += scan_part[w];
+    uint32_t run = wbase + inc - sum;
+    for (uint32_t i = lo; i < hi; i++) { uint32_t t = cum[i]; cum[i] = run; run += t; }
+    if (tid == PLAN_THREADS - 1) cum[n_vals] = n;
+    __syncthreads();
+  }
+  // value at sorted rank idx
+  auto s_at = [&](uint32_t idx) -> uint64_t {
+    if (!COUNTING) return uint64_t(s[idx]);
+    uint32_t lo = 0, hi = n_vals;  // invariant: cum[lo] <= idx < cum[hi]
+    while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (cum[m] <= idx) lo = m; else hi = m; }
+    return lo;
+  };
   VarPlan& plan = plans[size_t(c) * MAX_VARS + v];
   const uint64_t vmin = chunks[c].vmin[v];
   constexpr uint32_t LBITS = LT<L>::BITS;
@@ -379,18 +416,23 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(EncParams ep, const 
     uint64_t vb1 = 0, vb = 0, vlm1 = 0, vr = 0;
     uint32_t l = 0, r = 0;
     if (B >= 1 && B <= n) {
-      vb1 = uint64_t(s[B - 1]);
-      if (B < n) vb = uint64_t(s[B]);
+      vb1 = s_at(B - 1);
+      if (B < n) vb = s_at(B);
       if (B < n && vb == vb1) {
-        // extent [l, r) of the run of vb1: lower_bound / upper_bound
-        uint32_t lo = 0, hi = B - 1;  // first index with s[idx] >= vb1 is in [0, B-1]
-        while (lo < hi) { uint32_t m = (lo + hi) >> 1; if (uint64_t(s[m]) < vb1) lo = m + 1; else hi = m; }
-        l = lo;
-        lo = B; hi = n;               // first index with s[idx] > vb1 is in [B+1, n]
-        while (lo < hi) { uint32_t m = (lo + hi) >> 1; if (uint64_t(s[m]) <= vb1) lo = m + 1; else hi = m; }
-        r = lo;
-        if (l > 0) vlm1 = uint64_t(s[l - 1]);
-        if (r < n) vr = uint64_t(s[r]);
+        // extent [l, r) of the run of vb1
+        if (COUNTING) {
+          l = cum[uint32_t(vb1)];
+          r = cum[uint32_t(vb1) + 1];
+        } else {
+          uint32_t lo = 0, hi = B - 1;  // first index with s[idx] >= vb1 is in [0, B-1]
+          while (lo < hi) { uint32_t m = (lo + hi) >> 1; if (uint64_t(s[m]) < vb1) lo = m + 1; else hi = m; }
+          l = lo;
+          lo = B; hi = n;               // first index with s[idx] > vb1 is in [B+1, n]
+          while (lo < hi) { uint32_t m = (lo + hi) >> 1; if (uint64_t(s[m]) <= vb1) lo = m + 1; else hi = m; }
+          r = lo;
+        }
+        if (l > 0) vlm1 = s_at(l - 1);
+        if (r < n) vr = s_at(r);
       }
     }
     sm.vB1[k] = vb1; sm.vB[k] = vb; sm.vLm1[k] = vlm1; sm.vR[k] = vr; sm.runL[k] = l; sm.runR[k] = r;
@@ -402,7 +444,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(EncParams ep, const 
     bool has_inc = false;
     uint32_t inc_count = 0;
     uint64_t inc_lower = 0, inc_upper = 0;
-    uint64_t pos_val = uint64_t(s[0]);
+    uint64_t pos_val = s_at(0);
     auto apply_incomplete = [&](uint32_t cnt, uint64_t lo_v, uint64_t hi_v) {
       if (cnt == 0) return;
       if (has_inc) { inc_upper = hi_v; inc_count += cnt; }
@@ -747,11 +789,21 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_kernel(EncParams ep, uint32_t
 constexpr int ANS_THREADS = 32;
 
 struct AnsSmem {
-  uint64_t syminfo[ENC_MAXB];
-  uint16_t next_states[1 << ENC_MAX_SIZE_LOG];
-  uint8_t sym[2][BATCH_N];
+  uint32_t desc_tab[ENC_MAXB];                 // per symbol: cutoff (12 bits) | min_renorm_bits << 12 | (cum - weight + 2048) << 16
+  uint16_t next_states[1 << ENC_MAX_SIZE_LOG];  // full next state (size + slot), indexed cum + (x_s - weight)
+  uint32_t desc[2][BATCH_N];                    // descriptors of the batch in flight / the next one
   uint16_t out[BATCH_N];
 };
+
+// One tANS step (ans/encoding.rs:72-83) from a pre-resolved descriptor.  The only memory access that depends on the
+// state is the next_states lookup; everything about the symbol was fetched ahead of the chain.
+__device__ __forceinline__ void ans_step(uint32_t d, uint32_t& state, uint32_t& bits_total, uint16_t* out_slot, const uint16_t* next_states) {
+  const uint32_t cutoff = d & 0xfffu, mr = (d >> 12) & 0xfu, base = d >> 16;
+  const uint32_t bits = mr + (state >= cutoff ? 1u : 0u);
+  *out_slot = uint16_t((state & ((1u << bits) - 1)) | (1u << bits));
+  bits_total += bits;
+  state = next_states[base + (state >> bits) - 2048u];
+}
 
 __global__ void __launch_bounds__(ANS_THREADS) ans_encode_kernel(EncParams ep, uint32_t batches_per_chunk, const VarPlan* __restrict__ plans,
                                                                   ChunkEnc* __restrict__ chunks, const uint8_t* __restrict__ sym0,
@@ -785,43 +837,59 @@ __global__ void __launch_bounds__(ANS_THREADS) ans_encode_kernel(EncParams ep, u
     if (lane < 4) chunks[c].final_state[v][lane] = 0;
     return;
   }
-  for (uint32_t i = lane; i < n_bins; i += 32) sm.syminfo[i] = plan.syminfo[i];
-  for (uint32_t i = lane; i < size; i += 32) sm.next_states[i] = plan.next_states[i];
+  for (uint32_t i = lane; i < n_bins; i += 32) {
+    const uint64_t info = plan.syminfo[i];
+    const uint32_t cutoff = uint32_t(info & 0xffff), mr = uint32_t(info >> 16) & 0xff, w = uint32_t(info >> 24) & 0xffff, cum = uint32_t(info >> 40) & 0xffff;
+    sm.desc_tab[i] = cutoff | (mr << 12) | ((cum + 2048u - w) << 16);
+  }
+  for (uint32_t i = lane; i < size; i += 32) sm.next_states[i] = uint16_t(size + plan.next_states[i]);
   const uint32_t nb = n_batches_of(n);
-  // batches past the var's stored range (e.g. the last page batch of a delta'd var): no symbols
-  for (uint32_t b = nb + lane; b < nb_page; b += 32) sums[b] = 0;
+  for (uint32_t b = nb + lane; b < nb_page; b += 32) {  // page batches past the var's stored range: no symbols
+    sums[b] = 0;
+    BatchEntry e; e.bit_pos = 0; e.st[0] = e.st[1] = e.st[2] = e.st[3] = 0;
+    ent[b] = e;
+  }
+  __syncwarp();
   uint32_t state = size;  // encoder.default_state()
   const uint8_t* symp = (v == 0 ? sym0 : sym1) + sb;
   uint16_t* ansp = (v == 0 ? ans0 : ans1) + sb;
-  auto load_batch = [&](uint32_t b, int buf) {
-    uint32_t cnt = min(uint32_t(BATCH_N), n - b * BATCH_N);
-    for (uint32_t i = lane; i < cnt; i += 32) sm.sym[buf][i] = symp[uint64_t(b) * BATCH_N + i];
+  // symbols of a batch: lane l holds bytes l, l+32, ..., l+224
+  auto load_syms = [&](uint32_t b, uint32_t (&r)[8]) {
+    const uint32_t cnt = min(uint32_t(BATCH_N), n - b * BATCH_N);
+    const uint8_t* p = symp + uint64_t(b) * BATCH_N;
+#pragma unroll
+    for (int k = 0; k < 8; k++) r[k] = (uint32_t(lane + 32 * k) < cnt) ? uint32_t(p[lane + 32 * k]) : 0u;
   };
-  if (nb > 0) load_batch(nb - 1, (nb - 1) & 1);
+  auto stage_desc = [&](const uint32_t (&r)[8], int buf) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) sm.desc[buf][lane + 32 * k] = sm.desc_tab[r[k]];
+  };
+  uint32_t pre[8];
+  if (nb > 0) { load_syms(nb - 1, pre); stage_desc(pre, (nb - 1) & 1); }
   __syncwarp();
   for (uint32_t bb = nb; bb-- > 0;) {
     const int buf = bb & 1;
     const uint32_t cnt = min(uint32_t(BATCH_N), n - bb * BATCH_N);
-    if (bb > 0) load_batch(bb - 1, (bb - 1) & 1);  // prefetch the next (earlier) batch
+    if (bb > 0) load_syms(bb - 1, pre);  // in flight during the chain below, consumed after it
     uint32_t bits_total = 0;
     if (lane < 4) {
       // lane j encodes symbols i = j (mod 4), i descending (chunk_latent_compressor.rs:110-131)
+      const uint32_t* dsc = sm.desc[buf];
       int i = int(cnt) - 1;
       i -= ((i - lane) % 4 + 4) % 4;  // largest i <= cnt-1 with i % 4 == lane
-      for (; i >= 0; i -= 4) {
-        uint64_t info = sm.syminfo[sm.sym[buf][i]];
-        uint32_t cutoff = uint32_t(info & 0xffff), min_renorm = uint32_t(info >> 16) & 0xff;
-        uint32_t w = uint32_t(info >> 24) & 0xffff, cum = uint32_t(info >> 40) & 0xffff;
-        uint32_t bits = min_renorm + (state >= cutoff ? 1u : 0u);
-        sm.out[i] = uint16_t((state & ((1u << bits) - 1)) | (1u << bits));
-        bits_total += bits;
-        state = size + sm.next_states[cum + (state >> bits) - w];
+      for (; i >= 12; i -= 16) {
+        const uint32_t d0 = dsc[i], d1 = dsc[i - 4], d2 = dsc[i - 8], d3 = dsc[i - 12];
+        ans_step(d0, state, bits_total, &sm.out[i], sm.next_states);
+        ans_step(d1, state, bits_total, &sm.out[i - 4], sm.next_states);
+        ans_step(d2, state, bits_total, &sm.out[i - 8], sm.next_states);
+        ans_step(d3, state, bits_total, &sm.out[i - 12], sm.next_states);
       }
+      for (; i >= 0; i -= 4) ans_step(dsc[i], state, bits_total, &sm.out[i], sm.next_states);
     }
     __syncwarp();
     // decoder state at the START of batch bb == encoder state after encoding it (side index)
-    uint32_t s0 = __shfl_sync(0xffffffffu, state, 0), s1 = __shfl_sync(0xffffffffu, state, 1);
-    uint32_t s2 = __shfl_sync(0xffffffffu, state, 2), s3 = __shfl_sync(0xffffffffu, state, 3);
+    const uint32_t s0 = __shfl_sync(0xffffffffu, state, 0), s1 = __shfl_sync(0xffffffffu, state, 1);
+    const uint32_t s2 = __shfl_sync(0xffffffffu, state, 2), s3 = __shfl_sync(0xffffffffu, state, 3);
     bits_total += __shfl_xor_sync(0xffffffffu, bits_total, 1);
     bits_total += __shfl_xor_sync(0xffffffffu, bits_total, 2);
     if (lane == 0) {
@@ -831,16 +899,13 @@ __global__ void __launch_bounds__(ANS_THREADS) ans_encode_kernel(EncParams ep, u
       e.st[0] = uint16_t(s0 - size); e.st[1] = uint16_t(s1 - size); e.st[2] = uint16_t(s2 - size); e.st[3] = uint16_t(s3 - size);
       ent[bb] = e;
     }
-    for (uint32_t i = lane; i < cnt; i += 32) ansp[uint64_t(bb) * BATCH_N + i] = sm.out[i];
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      if (uint32_t(lane + 32 * k) < cnt) ansp[uint64_t(bb) * BATCH_N + lane + 32 * k] = sm.out[lane + 32 * k];
+    if (bb > 0) stage_desc(pre, (bb - 1) & 1);
     __syncwarp();
   }
   if (lane < 4) chunks[c].final_state[v][lane] = state - size;
-  // page batches beyond the stored range inherit the state at the end of the stream
-  for (uint32_t b = nb + lane; b < nb_page; b += 32) {
-    BatchEntry e; e.bit_pos = 0; e.st[0] = e.st[1] = e.st[2] = e.st[3] = 0;
-    // the decoder never reads symbols there; states are irrelevant but keep them well-defined
-    ent[b] = e;
-  }
 }
 
 // ---------------------------------------------------------------------------
