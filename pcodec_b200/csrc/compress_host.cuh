@@ -257,6 +257,7 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
     PCOB_CUDA_TRY(cudaFuncSetAttribute(plan_kernel<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(sizeof(PlanSmem) + 64 + ((size_t(1) << PLAN_MAX_COUNT_BITS) + 1) * 4)));
     PCOB_CUDA_TRY(cudaFuncSetAttribute(pack_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PackSmem)));
+    PCOB_CUDA_TRY(cudaFuncSetAttribute(ans_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AnsSmem)));
   }
   for (uint32_t v = 0; v < ep.n_vars; v++) {
     const uint32_t order_v = v == 0 ? ep.order : 0;
@@ -307,7 +308,7 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
   }
   // the ans kernel indexes (chunk, var) by blockIdx; both vars share the launch via separate symbol arrays
   profiler().begin("ans_encode_kernel", stream);
-  ans_encode_kernel<<<n_chunks * MAX_VARS, ANS_THREADS, 0, stream>>>(ep, bpc, d_plans, d_chunks, d_sym[0], d_sym[1], d_ans[0], d_ans[1], S.ans_sum.as<uint32_t>(),
+  ans_encode_kernel<<<n_chunks * MAX_VARS, ANS_THREADS, sizeof(AnsSmem), stream>>>(ep, bpc, d_plans, d_chunks, d_sym[0], d_sym[1], d_ans[0], d_ans[1], S.ans_sum.as<uint32_t>(),
                                                                      S.entries.as<BatchEntry>());
   profiler().end(stream);
   // ---- layout, offsets, K5

@@ -23,6 +23,15 @@
 
 namespace pcob200 {
 
+#ifdef PCOB_ENC_TIMING
+// experiment builds only: per-phase clock64 sums of CTA-level phases (thread 0 of every CTA), read by pco_b200_debug_enc_timing
+__device__ unsigned long long g_enc_timing[32];
+#define ENC_TICK_INIT() long long enc_t0_ = clock64()
+#define ENC_TICK(idx) do { if (threadIdx.x == 0) { long long t_ = clock64(); atomicAdd(&g_enc_timing[idx], (unsigned long long)(t_ - enc_t0_)); enc_t0_ = t_; } } while (0)
+#else
+#define ENC_TICK_INIT() do { } while (0)
+#define ENC_TICK(idx) do { } while (0)
+#endif
 constexpr int ENC_MAXB = 256;        // bins per latent var (compression level <= 8)
 constexpr int ENC_MAX_SIZE_LOG = 10;
 
@@ -369,6 +378,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(EncParams ep, const 
   const uint64_t sb = stored_begin(cs, ce, v == 0 ? ep.order : 0);
   const uint32_t n = uint32_t(ce - sb);  // stored latents
   const L* s = keys + sb;
+  ENC_TICK_INIT();
   const uint32_t n_vals = COUNTING ? (1u << range_bits) : 0u;
   if (COUNTING && n > 0) {
     const L mn = L(chunks[c].vmin[v]);
@@ -376,6 +386,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(EncParams ep, const 
     __syncthreads();
     for (uint32_t i = tid; i < n; i += PLAN_THREADS) atomicAdd(&cum[uint32_t(L(s[i] - mn))], 1u);
     __syncthreads();
+    ENC_TICK(0);  // zero + count
     // exclusive scan of the counters: each thread owns a contiguous slice
     const uint32_t per = (n_vals + PLAN_THREADS - 1) / PLAN_THREADS;
     const uint32_t lo = min(n_vals, tid * per), hi = min(n_vals, lo + per);
@@ -392,6 +403,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(EncParams ep, const 
     if (tid == PLAN_THREADS - 1) cum[n_vals] = n;
     __syncthreads();
   }
+  ENC_TICK(1);  // scan
   // value at sorted rank idx
   auto s_at = [&](uint32_t idx) -> uint64_t {
     if (!COUNTING) return uint64_t(s[idx]);
@@ -438,6 +450,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(EncParams ep, const 
     sm.vB1[k] = vb1; sm.vB[k] = vb; sm.vLm1[k] = vlm1; sm.vR[k] = vr; sm.runL[k] = l; sm.runR[k] = r;
   }
   __syncthreads();
+  ENC_TICK(2);  // probes
   // ---- 2. histogram state machine (HistogramBuilder), sequential over at most 2^log boundaries
   if (tid == 0) {
     uint32_t n_hist = 0, next_avail = 0, pos = 0;
@@ -486,6 +499,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(EncParams ep, const 
     sm.n_hist = n_hist;
   }
   __syncthreads();
+  ENC_TICK(3);  // histogram state machine
   const uint32_t nh = sm.n_hist;
   // estimated_ans_size_log (chunk_compressor.rs:63-79)
   const uint32_t n_log_ceil = n <= 1 ? 0 : (32 - __clz(n - 1));
@@ -534,6 +548,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(EncParams ep, const 
     }
     __syncthreads();
   }
+  ENC_TICK(4);  // DP
   // ---- 4. shortcuts, rewind, weights (thread 0: short sequential f32 sums whose order matters)
   if (tid == 0) {
     const float best = sm.best_cost[nh];
@@ -638,6 +653,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(EncParams ep, const 
     plan.wc_bits = wc;
   }
   __syncthreads();
+  ENC_TICK(5);  // rewind + quantize
   const uint32_t n_opt = sm.n_opt, size_log = sm.size_log, size = 1u << size_log;
   const uint64_t lmask = LBITS == 64 ? ~uint64_t(0) : ((uint64_t(1) << LBITS) - 1);
   for (uint32_t q = tid; q < n_opt; q += PLAN_THREADS) {
@@ -676,6 +692,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(EncParams ep, const 
       if (active) plan.next_states[sm.cum[sym] + prev + in_group] = uint16_t(st);  // state = size + st
     }
   }
+  ENC_TICK(6);  // tables
 }
 
 // ---------------------------------------------------------------------------
@@ -786,23 +803,41 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_kernel(EncParams ep, uint32_t
 // (latency-bound serial chains); all lanes stage symbols in and results out.
 // Output per latent: u16 = ans_val | (1 << ans_bits)  (length-prefixed, ans_bits <= 14)
 // ---------------------------------------------------------------------------
-constexpr int ANS_THREADS = 32;
+// The encoder state chain of a page is serial (each step's state feeds the next, 2^16 steps per chain), but a tANS
+// step with a symbol of weight w maps all 2^size_log states onto w values, so two trajectories that start from different
+// states over the same symbols merge after a few steps and are identical from there on.  The kernel uses that: every
+// batch (segment) of a 64-batch round is encoded at once from a GUESSED input state; then each segment re-runs from its
+// TRUE input (the output of the segment before it in encode order) only until it meets the guessed trajectory.  A segment
+// that never merges changes its output and the round iterates until no output moves (worst case: one segment per
+// iteration, i.e. the serial order) - the result is always exactly the serial encoder's.
+constexpr int ANS_THREADS = 256;
+constexpr int ANS_SEGS = ANS_THREADS / 4;  // batches per round: one thread per (batch, interleaved chain)
+constexpr int ANS_SYM_STRIDE = 260;        // staged symbol row, bytes (65 words: the 8 rows a warp touches hit 8 banks)
+constexpr int ANS_OUT_STRIDE = 260;        // staged output row, u16 (130 words)
 
 struct AnsSmem {
   uint32_t desc_tab[ENC_MAXB];                 // per symbol: cutoff (12 bits) | min_renorm_bits << 12 | (cum - weight + 2048) << 16
   uint16_t next_states[1 << ENC_MAX_SIZE_LOG];  // full next state (size + slot), indexed cum + (x_s - weight)
-  uint32_t desc[2][BATCH_N];                    // descriptors of the batch in flight / the next one
-  uint16_t out[BATCH_N];
+  uint16_t out_state[ANS_SEGS][4];
+  uint16_t carry[4];
+  alignas(4) uint8_t sym[ANS_SEGS * ANS_SYM_STRIDE];
+  alignas(4) uint16_t out[ANS_SEGS * ANS_OUT_STRIDE];
 };
 
-// One tANS step (ans/encoding.rs:72-83) from a pre-resolved descriptor.  The only memory access that depends on the
-// state is the next_states lookup; everything about the symbol was fetched ahead of the chain.
-__device__ __forceinline__ void ans_step(uint32_t d, uint32_t& state, uint32_t& bits_total, uint16_t* out_slot, const uint16_t* next_states) {
+// One tANS step (ans/encoding.rs:72-83) from a pre-resolved descriptor.
+__device__ __forceinline__ uint32_t ans_step(uint32_t d, uint32_t& state, uint16_t* out_slot, const uint16_t* next_states) {
   const uint32_t cutoff = d & 0xfffu, mr = (d >> 12) & 0xfu, base = d >> 16;
   const uint32_t bits = mr + (state >= cutoff ? 1u : 0u);
   *out_slot = uint16_t((state & ((1u << bits) - 1)) | (1u << bits));
-  bits_total += bits;
   state = next_states[base + (state >> bits) - 2048u];
+  return bits;
+}
+// the same step without the output (the guessed trajectory replayed next to the true one)
+__device__ __forceinline__ uint32_t ans_step_quiet(uint32_t d, uint32_t& state, const uint16_t* next_states) {
+  const uint32_t cutoff = d & 0xfffu, mr = (d >> 12) & 0xfu, base = d >> 16;
+  const uint32_t bits = mr + (state >= cutoff ? 1u : 0u);
+  state = next_states[base + (state >> bits) - 2048u];
+  return bits;
 }
 
 __global__ void __launch_bounds__(ANS_THREADS) ans_encode_kernel(EncParams ep, uint32_t batches_per_chunk, const VarPlan* __restrict__ plans,
@@ -810,10 +845,11 @@ __global__ void __launch_bounds__(ANS_THREADS) ans_encode_kernel(EncParams ep, u
                                                                   const uint8_t* __restrict__ sym1, uint16_t* __restrict__ ans0,
                                                                   uint16_t* __restrict__ ans1, uint32_t* __restrict__ ans_sum,
                                                                   BatchEntry* __restrict__ entries) {
-  __shared__ AnsSmem sm;
+  extern __shared__ __align__(16) unsigned char ans_smem_raw[];
+  AnsSmem& sm = *reinterpret_cast<AnsSmem*>(ans_smem_raw);
   const uint32_t c = blockIdx.x / MAX_VARS, v = blockIdx.x % MAX_VARS;
   if (v >= ep.n_vars) return;
-  const int lane = threadIdx.x;
+  const int tid = threadIdx.x;
   const uint64_t cs = ep.chunk_starts[c], ce = ep.chunk_starts[c + 1];
   const bool fb = chunks[c].fallback != 0;
   if (fb && v > 0) return;
@@ -829,83 +865,93 @@ __global__ void __launch_bounds__(ANS_THREADS) ans_encode_kernel(EncParams ep, u
   BatchEntry* ent = entries + (size_t(c) * MAX_VARS + v) * batches_per_chunk;
   if (size_log == 0) {
     // one symbol: no ANS bits, states stay at the default (chunk_latent_compressor.rs:103-108)
-    for (uint32_t b = lane; b < nb_page; b += 32) {
+    for (uint32_t b = tid; b < nb_page; b += ANS_THREADS) {
       sums[b] = 0;
       BatchEntry e; e.bit_pos = 0; e.st[0] = e.st[1] = e.st[2] = e.st[3] = 0;
       ent[b] = e;
     }
-    if (lane < 4) chunks[c].final_state[v][lane] = 0;
+    if (tid < 4) chunks[c].final_state[v][tid] = 0;
     return;
   }
-  for (uint32_t i = lane; i < n_bins; i += 32) {
+  for (uint32_t i = tid; i < n_bins; i += ANS_THREADS) {
     const uint64_t info = plan.syminfo[i];
     const uint32_t cutoff = uint32_t(info & 0xffff), mr = uint32_t(info >> 16) & 0xff, w = uint32_t(info >> 24) & 0xffff, cum = uint32_t(info >> 40) & 0xffff;
     sm.desc_tab[i] = cutoff | (mr << 12) | ((cum + 2048u - w) << 16);
   }
-  for (uint32_t i = lane; i < size; i += 32) sm.next_states[i] = uint16_t(size + plan.next_states[i]);
+  for (uint32_t i = tid; i < size; i += ANS_THREADS) sm.next_states[i] = uint16_t(size + plan.next_states[i]);
   const uint32_t nb = n_batches_of(n);
-  for (uint32_t b = nb + lane; b < nb_page; b += 32) {  // page batches past the var's stored range: no symbols
+  for (uint32_t b = nb + tid; b < nb_page; b += ANS_THREADS) {  // page batches past the var's stored range: no symbols
     sums[b] = 0;
     BatchEntry e; e.bit_pos = 0; e.st[0] = e.st[1] = e.st[2] = e.st[3] = 0;
     ent[b] = e;
   }
-  __syncwarp();
-  uint32_t state = size;  // encoder.default_state()
+  if (tid < 4) sm.carry[tid] = uint16_t(size);  // encoder.default_state()
+  __syncthreads();
   const uint8_t* symp = (v == 0 ? sym0 : sym1) + sb;
   uint16_t* ansp = (v == 0 ? ans0 : ans1) + sb;
-  // symbols of a batch: lane l holds bytes l, l+32, ..., l+224
-  auto load_syms = [&](uint32_t b, uint32_t (&r)[8]) {
-    const uint32_t cnt = min(uint32_t(BATCH_N), n - b * BATCH_N);
-    const uint8_t* p = symp + uint64_t(b) * BATCH_N;
-#pragma unroll
-    for (int k = 0; k < 8; k++) r[k] = (uint32_t(lane + 32 * k) < cnt) ? uint32_t(p[lane + 32 * k]) : 0u;
-  };
-  auto stage_desc = [&](const uint32_t (&r)[8], int buf) {
-#pragma unroll
-    for (int k = 0; k < 8; k++) sm.desc[buf][lane + 32 * k] = sm.desc_tab[r[k]];
-  };
-  uint32_t pre[8];
-  if (nb > 0) { load_syms(nb - 1, pre); stage_desc(pre, (nb - 1) & 1); }
-  __syncwarp();
-  for (uint32_t bb = nb; bb-- > 0;) {
-    const int buf = bb & 1;
-    const uint32_t cnt = min(uint32_t(BATCH_N), n - bb * BATCH_N);
-    if (bb > 0) load_syms(bb - 1, pre);  // in flight during the chain below, consumed after it
-    uint32_t bits_total = 0;
-    if (lane < 4) {
-      // lane j encodes symbols i = j (mod 4), i descending (chunk_latent_compressor.rs:110-131)
-      const uint32_t* dsc = sm.desc[buf];
-      int i = int(cnt) - 1;
-      i -= ((i - lane) % 4 + 4) % 4;  // largest i <= cnt-1 with i % 4 == lane
-      for (; i >= 12; i -= 16) {
-        const uint32_t d0 = dsc[i], d1 = dsc[i - 4], d2 = dsc[i - 8], d3 = dsc[i - 12];
-        ans_step(d0, state, bits_total, &sm.out[i], sm.next_states);
-        ans_step(d1, state, bits_total, &sm.out[i - 4], sm.next_states);
-        ans_step(d2, state, bits_total, &sm.out[i - 8], sm.next_states);
-        ans_step(d3, state, bits_total, &sm.out[i - 12], sm.next_states);
+  const int j = tid & 3, s = tid >> 2;  // chain j of the s-th batch below the round's top
+  const uint8_t* srow = sm.sym + s * ANS_SYM_STRIDE;
+  uint16_t* orow = sm.out + s * ANS_OUT_STRIDE;
+  for (uint32_t hi = nb; hi > 0;) {
+    const uint32_t nseg = min(uint32_t(ANS_SEGS), hi), lo = hi - nseg;
+    // stage the symbols of batches [lo, hi): row r holds batch hi-1-r (encode order)
+    const uint32_t tile_n = min(n, hi * BATCH_N) - lo * BATCH_N;
+    for (uint32_t k = tid; k < tile_n; k += ANS_THREADS)
+      sm.sym[(nseg - 1 - (k >> 8)) * ANS_SYM_STRIDE + (k & 255)] = symp[uint64_t(lo) * BATCH_N + k];
+    __syncthreads();
+    const bool active = uint32_t(s) < nseg;
+    const uint32_t bb = hi - 1 - uint32_t(s);
+    const uint32_t cnt = active ? min(uint32_t(BATCH_N), n - bb * BATCH_N) : 0u;
+    const int steps = cnt > uint32_t(j) ? int((cnt - 1 - j) / 4 + 1) : 0;  // chain j encodes i = j (mod 4), descending
+    uint32_t my_in = (s == 0) ? uint32_t(sm.carry[j]) : size;  // the round's first segment knows its input; the others guess
+    uint32_t state = my_in, bits_total = 0;
+    {
+      int m = steps - 1;
+      for (; m >= 3; m -= 4) {
+        const int i = 4 * m + j;
+        const uint32_t d0 = sm.desc_tab[srow[i]], d1 = sm.desc_tab[srow[i - 4]], d2 = sm.desc_tab[srow[i - 8]], d3 = sm.desc_tab[srow[i - 12]];
+        bits_total += ans_step(d0, state, &orow[i], sm.next_states);
+        bits_total += ans_step(d1, state, &orow[i - 4], sm.next_states);
+        bits_total += ans_step(d2, state, &orow[i - 8], sm.next_states);
+        bits_total += ans_step(d3, state, &orow[i - 12], sm.next_states);
       }
-      for (; i >= 0; i -= 4) ans_step(dsc[i], state, bits_total, &sm.out[i], sm.next_states);
+      for (; m >= 0; m--) bits_total += ans_step(sm.desc_tab[srow[4 * m + j]], state, &orow[4 * m + j], sm.next_states);
     }
-    __syncwarp();
-    // decoder state at the START of batch bb == encoder state after encoding it (side index)
-    const uint32_t s0 = __shfl_sync(0xffffffffu, state, 0), s1 = __shfl_sync(0xffffffffu, state, 1);
-    const uint32_t s2 = __shfl_sync(0xffffffffu, state, 2), s3 = __shfl_sync(0xffffffffu, state, 3);
+    uint32_t my_out = state;
+    if (active) sm.out_state[s][j] = uint16_t(my_out);
+    __syncthreads();
+    while (true) {
+      const uint32_t in_true = (s == 0 || !active) ? my_in : uint32_t(sm.out_state[s - 1][j]);
+      bool changed = false;
+      if (in_true != my_in) {
+        uint32_t a = in_true, g = my_in;
+        for (int m = steps - 1; m >= 0 && a != g; m--) {
+          const int i = 4 * m + j;
+          const uint32_t d = sm.desc_tab[srow[i]];
+          bits_total += ans_step(d, a, &orow[i], sm.next_states);
+          bits_total -= ans_step_quiet(d, g, sm.next_states);
+        }
+        my_in = in_true;
+        if (a != g) { changed = true; my_out = a; }  // ran off the segment without meeting the old trajectory
+      }
+      __syncthreads();  // every segment has read its predecessor's output
+      if (changed) sm.out_state[s][j] = uint16_t(my_out);
+      if (!__syncthreads_or(changed ? 1 : 0)) break;
+    }
+    // decoder state at the START of a batch == encoder state after encoding it (side index)
     bits_total += __shfl_xor_sync(0xffffffffu, bits_total, 1);
     bits_total += __shfl_xor_sync(0xffffffffu, bits_total, 2);
-    if (lane == 0) {
-      sums[bb] = bits_total;
-      BatchEntry e;
-      e.bit_pos = 0;
-      e.st[0] = uint16_t(s0 - size); e.st[1] = uint16_t(s1 - size); e.st[2] = uint16_t(s2 - size); e.st[3] = uint16_t(s3 - size);
-      ent[bb] = e;
+    if (active) {
+      if (j == 0) { sums[bb] = bits_total; ent[bb].bit_pos = 0; }
+      ent[bb].st[j] = uint16_t(my_out - size);
+      if (uint32_t(s) == nseg - 1) sm.carry[j] = uint16_t(my_out);
     }
-#pragma unroll
-    for (int k = 0; k < 8; k++)
-      if (uint32_t(lane + 32 * k) < cnt) ansp[uint64_t(bb) * BATCH_N + lane + 32 * k] = sm.out[lane + 32 * k];
-    if (bb > 0) stage_desc(pre, (bb - 1) & 1);
-    __syncwarp();
+    for (uint32_t k = tid; k < tile_n; k += ANS_THREADS)
+      ansp[uint64_t(lo) * BATCH_N + k] = sm.out[(nseg - 1 - (k >> 8)) * ANS_OUT_STRIDE + (k & 255)];
+    __syncthreads();
+    hi = lo;
   }
-  if (lane < 4) chunks[c].final_state[v][lane] = state - size;
+  if (tid < 4) chunks[c].final_state[v][tid] = uint32_t(sm.carry[tid]) - size;
 }
 
 // ---------------------------------------------------------------------------

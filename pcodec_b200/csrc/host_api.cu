@@ -362,6 +362,16 @@ int pco_b200_debug_dec_timing(unsigned long long* out16) {
 }
 #endif
 
+#ifdef PCOB_ENC_TIMING
+int pco_b200_debug_enc_timing(unsigned long long* out32) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out32, g_enc_timing, sizeof(unsigned long long) * 32);
+  unsigned long long z[32] = {0};
+  cudaMemcpyToSymbol(g_enc_timing, z, sizeof(z));
+  return 0;
+}
+#endif
+
 void pco_b200_profile_enable(int on) { profiler().enabled = on != 0; }
 // Copies "name=ms;name=ms;..." of the last finished call into buf; returns the number of spans.
 int pco_b200_profile_last(char* buf, size_t cap) {

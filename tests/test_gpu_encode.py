@@ -83,7 +83,7 @@ def test_classic_bytes_equal_oracle(sa, oracle, dtype, order):
         np.testing.assert_array_equal(bits_view(got), bits_view(nums))
 
 
-@pytest.mark.parametrize("dist", ["few_values", "heavy_run", "geometric_p9", "uniform_small", "constant", "arith", "uniform_u64", "sorted"])
+@pytest.mark.parametrize("dist", ["few_values", "heavy_run", "geometric_p9", "uniform_small", "constant", "arith", "uniform_u64", "sorted", "skewed_995", "coin", "three_skewed"])
 def test_planner_on_adversarial_distributions(sa, oracle, dist):
     rng = np.random.default_rng(11)
     n = 50000
@@ -96,6 +96,10 @@ def test_planner_on_adversarial_distributions(sa, oracle, dist):
         "arith": np.arange(n) * 3 + 7,
         "uniform_u64": rng.integers(0, 2**63, size=n),
         "sorted": np.sort(rng.integers(0, 10**9, size=n)),
+        # low-entropy streams: tANS trajectories from different states merge slowly or never (speculative encoder's iteration path)
+        "skewed_995": np.where(rng.random(n) < 0.995, 3, 4),
+        "coin": rng.integers(0, 2, size=n),
+        "three_skewed": rng.choice([10, 11, 500], p=[0.97, 0.02, 0.01], size=n),
     }[dist].astype(np.uint64)
     for order in (0, 1):
         ours_cfg, their_cfg = _cfgs(oracle, order=order)
