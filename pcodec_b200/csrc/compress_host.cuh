@@ -11,7 +11,7 @@
 namespace pcob200 {
 
 struct CompressScratch {
-  DevBuf lat0, lat1, keys_a, keys_b, sym0, sym1, ans0, ans1, ob_sum, ans_sum, entries, plans, chunks, starts, seg, cub_tmp, out, small, index;
+  DevBuf lat0, lat1, keys_a, keys_b, sym0, sym1, ans0, ans1, ob_sum, ans_sum, entries, plans, chunks, starts, seg, cub_tmp, out, small, index, probes;
 };
 
 // pco/src/wrapped/chunk_compressor.rs:362-371
@@ -235,6 +235,8 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
   ep.chunk_starts = S.starts.as<uint64_t>();
   ChunkEnc* d_chunks = S.chunks.as<ChunkEnc>();
   VarPlan* d_plans = S.plans.as<VarPlan>();
+  PCOB_CUDA_TRY(S.probes.reserve(size_t(n_chunks) * sizeof(PlanProbes)));
+  PlanProbes* d_probes = S.probes.as<PlanProbes>();
   L* d_lat[2] = {S.lat0.as<L>(), S.lat1.as<L>()};
   uint8_t* d_sym[2] = {S.sym0.as<uint8_t>(), S.sym1.as<uint8_t>()};
   uint16_t* d_ans[2] = {S.ans0.as<uint16_t>(), S.ans1.as<uint16_t>()};
@@ -247,18 +249,23 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
   // ---- K1+K2
   init_chunks_kernel<<<(n_chunks + 255) / 256, 256, 0, stream>>>(d_chunks, n_chunks);
   profiler().begin("split_delta_kernel", stream);
-  split_delta_kernel<L><<<n_chunks * tiles_per_chunk, SPLIT_THREADS, 0, stream>>>(ep, tiles_per_chunk, d_lat[0], d_lat[1], d_chunks);
+  switch (ep.mode) {
+    case MODE_CLASSIC: split_delta_kernel<L, MODE_CLASSIC><<<n_chunks * tiles_per_chunk, SPLIT_THREADS, 0, stream>>>(ep, tiles_per_chunk, d_lat[0], d_lat[1], d_chunks); break;
+    case MODE_INT_MULT: split_delta_kernel<L, MODE_INT_MULT><<<n_chunks * tiles_per_chunk, SPLIT_THREADS, 0, stream>>>(ep, tiles_per_chunk, d_lat[0], d_lat[1], d_chunks); break;
+    case MODE_FLOAT_QUANT: split_delta_kernel<L, MODE_FLOAT_QUANT><<<n_chunks * tiles_per_chunk, SPLIT_THREADS, 0, stream>>>(ep, tiles_per_chunk, d_lat[0], d_lat[1], d_chunks); break;
+    default: split_delta_kernel<L, MODE_FLOAT_MULT><<<n_chunks * tiles_per_chunk, SPLIT_THREADS, 0, stream>>>(ep, tiles_per_chunk, d_lat[0], d_lat[1], d_chunks); break;
+  }
   profiler().end(stream);
   // ---- planner per var: range-reduced keys -> segmented radix sort over the significant bits -> plan
   static bool plan_attr_set = false;
   if (!plan_attr_set) {
     plan_attr_set = true;
-    PCOB_CUDA_TRY(cudaFuncSetAttribute(plan_kernel<L, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PlanSmem) + 64));
-    PCOB_CUDA_TRY(cudaFuncSetAttribute(plan_kernel<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(sizeof(PlanSmem) + 64 + ((size_t(1) << PLAN_MAX_COUNT_BITS) + 1) * 4)));
+    PCOB_CUDA_TRY(cudaFuncSetAttribute(plan_probe_kernel<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(((size_t(1) << PLAN_MAX_COUNT_BITS) + 1) * 4 + 16)));
     PCOB_CUDA_TRY(cudaFuncSetAttribute(pack_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PackSmem)));
     PCOB_CUDA_TRY(cudaFuncSetAttribute(ans_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AnsSmem)));
   }
+  uint32_t var_range_bits[MAX_VARS] = {64, 64};
   for (uint32_t v = 0; v < ep.n_vars; v++) {
     const uint32_t order_v = v == 0 ? ep.order : 0;
     PCOB_CUDA_TRY(cudaMemsetAsync(d_small, 0, 4, stream));
@@ -266,11 +273,15 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
     uint32_t range_bits = 0;
     PCOB_CUDA_TRY(cudaMemcpyAsync(&range_bits, d_small, 4, cudaMemcpyDeviceToHost, stream));
     PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
+    var_range_bits[v] = range_bits;
     if (range_bits <= PLAN_MAX_COUNT_BITS) {
       // small key range (the usual case once the chunk minimum is subtracted): counting histogram, no sort
-      const size_t smem = ((sizeof(PlanSmem) + 15) & ~size_t(15)) + ((size_t(1) << range_bits) + 1) * 4 + 16;
-      profiler().begin("plan_kernel_counting", stream);
-      plan_kernel<L, true><<<n_chunks, PLAN_THREADS, smem, stream>>>(ep, d_lat[v], d_chunks, d_plans, int(v), range_bits);
+      const size_t smem = ((size_t(1) << range_bits) + 1) * 4 + 16;
+      profiler().begin("plan_probe_kernel_counting", stream);
+      plan_probe_kernel<L, true><<<n_chunks, PLAN_THREADS, smem, stream>>>(ep, d_lat[v], d_chunks, d_probes, int(v), range_bits);
+      profiler().end(stream);
+      profiler().begin("plan_solve_kernel", stream);
+      plan_solve_kernel<L><<<n_chunks, SOLVE_THREADS, 0, stream>>>(ep, d_probes, d_chunks, d_plans, int(v));
       profiler().end(stream);
       continue;
     }
@@ -293,8 +304,11 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
       profiler().end(stream);
       sorted = db.Current();
     }
-    profiler().begin("plan_kernel", stream);
-    plan_kernel<L, false><<<n_chunks, PLAN_THREADS, sizeof(PlanSmem) + 64, stream>>>(ep, sorted, d_chunks, d_plans, int(v), range_bits);
+    profiler().begin("plan_probe_kernel_sorted", stream);
+    plan_probe_kernel<L, false><<<n_chunks, PLAN_THREADS, 16, stream>>>(ep, sorted, d_chunks, d_probes, int(v), range_bits);
+    profiler().end(stream);
+    profiler().begin("plan_solve_kernel", stream);
+    plan_solve_kernel<L><<<n_chunks, SOLVE_THREADS, 0, stream>>>(ep, d_probes, d_chunks, d_plans, int(v));
     profiler().end(stream);
   }
   fallback_kernel<<<(n_chunks + 255) / 256, 256, 0, stream>>>(ep, d_plans, d_chunks);
@@ -302,6 +316,14 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
   const uint32_t groups_per_chunk = (bpc + 7) / 8;
   for (uint32_t v = 0; v < ep.n_vars; v++)
   {
+    if (var_range_bits[v] <= PLAN_MAX_COUNT_BITS) {
+      const uint32_t parts = (bpc + BINL_BATCHES - 1) / BINL_BATCHES;
+      profiler().begin("bin_lut_kernel", stream);
+      bin_lut_kernel<L><<<n_chunks * parts, BINL_THREADS, (size_t(1) << var_range_bits[v]) + 16, stream>>>(ep, bpc, parts, d_lat[v], d_plans, d_chunks, d_sym[v],
+                                                                                                           S.ob_sum.as<uint32_t>(), int(v), var_range_bits[v]);
+      profiler().end(stream);
+      continue;
+    }
     profiler().begin("bin_kernel", stream);
     bin_kernel<L><<<n_chunks * groups_per_chunk, BIN_THREADS, 0, stream>>>(ep, bpc, d_lat[v], d_plans, d_chunks, d_sym[v], S.ob_sum.as<uint32_t>(), int(v));
     profiler().end(stream);

@@ -164,39 +164,34 @@ __device__ __forceinline__ void float_mult_split(uint32_t xbits, uint32_t base_b
   secondary = (a - b) + MID;
 }
 
-template <typename L>
+template <typename L, int MODE>
 __device__ __forceinline__ void split_one(L xbits, const EncParams& ep, bool is_float, bool is_signed, L& p, L& s) {
   constexpr L MID = L(L(1) << (LT<L>::BITS - 1));
   s = 0;
-  switch (ep.mode) {
-    case MODE_CLASSIC: p = to_latent_ordered<L>(xbits, is_float, is_signed); break;
-    case MODE_INT_MULT: {
-      L u = to_latent_ordered<L>(xbits, is_float, is_signed);
-      L base = L(ep.mode_base);
-      p = L(u / base);
-      s = L(u % base);
-      break;
-    }
-    case MODE_FLOAT_QUANT: {
-      L u = to_latent_ordered<L>(xbits, true, false);
-      L kmax = L(L(L(1) << ep.mode_k) - 1);
-      p = L(u >> ep.mode_k);
-      L lowest = L(u & kmax);
-      s = (xbits & MID) ? L(kmax - lowest) : lowest;
-      break;
-    }
-    default: {  // MODE_FLOAT_MULT
-      if constexpr (sizeof(L) == 8) {
-        uint64_t pp, ss;
-        float_mult_split(uint64_t(xbits), ep.base_bits, ep.inv_base_bits, pp, ss);
-        p = pp; s = ss;
-      } else if constexpr (sizeof(L) == 4) {
-        uint32_t pp, ss;
-        float_mult_split(uint32_t(xbits), uint32_t(ep.base_bits), uint32_t(ep.inv_base_bits), pp, ss);
-        p = pp; s = ss;
-      } else {
-        p = 0;
-      }
+  if constexpr (MODE == MODE_CLASSIC) {
+    p = to_latent_ordered<L>(xbits, is_float, is_signed);
+  } else if constexpr (MODE == MODE_INT_MULT) {
+    L u = to_latent_ordered<L>(xbits, is_float, is_signed);
+    L base = L(ep.mode_base);
+    p = L(u / base);
+    s = L(u % base);
+  } else if constexpr (MODE == MODE_FLOAT_QUANT) {
+    L u = to_latent_ordered<L>(xbits, true, false);
+    L kmax = L(L(L(1) << ep.mode_k) - 1);
+    p = L(u >> ep.mode_k);
+    L lowest = L(u & kmax);
+    s = (xbits & MID) ? L(kmax - lowest) : lowest;
+  } else {  // MODE_FLOAT_MULT
+    if constexpr (sizeof(L) == 8) {
+      uint64_t pp, ss;
+      float_mult_split(uint64_t(xbits), ep.base_bits, ep.inv_base_bits, pp, ss);
+      p = pp; s = ss;
+    } else if constexpr (sizeof(L) == 4) {
+      uint32_t pp, ss;
+      float_mult_split(uint32_t(xbits), uint32_t(ep.base_bits), uint32_t(ep.inv_base_bits), pp, ss);
+      p = pp; s = ss;
+    } else {
+      p = 0;
     }
   }
 }
@@ -209,7 +204,9 @@ __device__ __forceinline__ void atomic_min_u64(uint64_t* a, uint64_t v) { atomic
 __device__ __forceinline__ void atomic_max_u64(uint64_t* a, uint64_t v) { atomicMax(reinterpret_cast<unsigned long long*>(a), (unsigned long long)v); }
 
 // grid: n_chunks * tiles_per_chunk.  lat0/lat1 are indexed like nums (element g of the input).
-template <typename L>
+// MODE is a template parameter and the difference stencil's signed binomials live in registers: the kernel must stay
+// HBM-bound (read n, write n_vars * n latents), a generic per-element mode switch made it issue-bound.
+template <typename L, int MODE>
 __global__ void __launch_bounds__(SPLIT_THREADS) split_delta_kernel(EncParams ep, uint32_t tiles_per_chunk, L* __restrict__ lat0, L* __restrict__ lat1,
                                                                      ChunkEnc* __restrict__ chunks) {
   __shared__ L tile[SPLIT_TILE + MAX_ORDER];
@@ -222,45 +219,63 @@ __global__ void __launch_bounds__(SPLIT_THREADS) split_delta_kernel(EncParams ep
   const L* nums = static_cast<const L*>(ep.nums) + cs;
   const bool is_float = nt_is_float(ep.dtype), is_signed = nt_is_signed(ep.dtype);
   const uint32_t order = ep.order;
+  const bool two_vars = MODE != MODE_CLASSIC && ep.n_vars > 1;
   const int tid = threadIdx.x;
   constexpr L MID = L(L(1) << (LT<L>::BITS - 1));
-  // primary latents of [tile_start - order, tile_start + SPLIT_TILE) into shared memory (halo of `order`)
-  uint64_t mn1 = ~uint64_t(0), mx1 = 0;
-  for (int i = tid; i < SPLIT_TILE + int(order); i += SPLIT_THREADS) {
-    int64_t idx = int64_t(tile_start) + i - int64_t(order);
+  constexpr L LMAX = L(~L(0));
+  // coef[j] = (-1)^j C(order, j) in wrapping arithmetic: the order-th backward difference is sum_j coef[j] x[i - j]
+  // (== `order` passes of x[i] -= x[i-1], delta/consecutive.rs:19-33)
+  L coef[MAX_ORDER + 1];
+  {
+    uint32_t binom = 1;
+#pragma unroll
+    for (uint32_t j = 0; j <= MAX_ORDER; j++) {
+      coef[j] = j <= order ? ((j & 1) ? L(L(0) - L(binom)) : L(binom)) : L(0);
+      if (j < order) binom = binom * (order - j) / (j + 1);
+    }
+  }
+  // primary latents of [tile_start - order, tile_start + SPLIT_TILE) into shared memory (tile[0, order) is the halo)
+  L mn1 = LMAX, mx1 = 0;
+#pragma unroll
+  for (int q = 0; q < SPLIT_PER_THREAD; q++) {
+    const int i = q * SPLIT_THREADS + tid;
+    const uint32_t idx = tile_start + uint32_t(i);
     L p = 0, s = 0;
-    if (idx >= 0 && idx < int64_t(n)) {
-      split_one<L>(nums[idx], ep, is_float, is_signed, p, s);
-      if (i >= int(order) && ep.n_vars > 1) {
+    if (idx < n) {
+      split_one<L, MODE>(nums[idx], ep, is_float, is_signed, p, s);
+      if (two_vars) {
         lat1[cs + idx] = s;
-        mn1 = min(mn1, uint64_t(s));
-        mx1 = max(mx1, uint64_t(s));
+        mn1 = min(mn1, s);
+        mx1 = max(mx1, s);
       }
     }
-    tile[i] = p;
+    tile[order + i] = p;
+  }
+  if (tid < int(order)) {
+    L p = 0, s = 0;
+    if (tile_start + uint32_t(tid) >= order) split_one<L, MODE>(nums[tile_start + tid - order], ep, is_float, is_signed, p, s);
+    tile[tid] = p;
   }
   __syncthreads();
-  uint64_t mn0 = ~uint64_t(0), mx0 = 0;
-  for (int i = tid; i < SPLIT_TILE; i += SPLIT_THREADS) {
-    uint32_t idx = tile_start + i;
-    if (idx >= n) break;
-    // order-th backward difference, binomial stencil in wrapping arithmetic (== `order` passes of x[i] -= x[i-1])
-    L d = tile[i + order];
+  L mn0 = LMAX, mx0 = 0;
+#pragma unroll
+  for (int q = 0; q < SPLIT_PER_THREAD; q++) {
+    const int i = q * SPLIT_THREADS + tid;
+    const uint32_t idx = tile_start + uint32_t(i);
+    L d = tile[order + i];
     if (order > 0) {
-      L acc = 0;
-      // sum_j (-1)^j C(order, j) x[i - j]
-      uint32_t binom = 1;
-      for (uint32_t j = 0; j <= order; j++) {
-        L term = L(L(binom) * tile[i + order - j]);
-        acc = (j & 1) ? L(acc - term) : L(acc + term);
-        binom = binom * (order - j) / (j + 1);
+      L acc = d;  // coef[0] == 1
+#pragma unroll
+      for (uint32_t j = 1; j <= MAX_ORDER; j++) {
+        if (j > order) break;
+        acc = L(acc + L(coef[j] * tile[order + i - j]));
       }
       d = L(acc + MID);  // toggle_center (delta/mod.rs:29-33)
     }
-    if (idx >= order) {
+    if (idx < n && idx >= order) {
       lat0[cs + idx] = d;
-      mn0 = min(mn0, uint64_t(d));
-      mx0 = max(mx0, uint64_t(d));
+      mn0 = min(mn0, d);
+      mx0 = max(mx0, d);
     }
   }
   // page moments: moment_j = (j-th backward difference)[j]  (delta/consecutive.rs:19-33)
@@ -277,14 +292,20 @@ __global__ void __launch_bounds__(SPLIT_THREADS) split_delta_kernel(EncParams ep
     }
     chunks[c].moments[0][j] = uint64_t(acc);
   }
-  // block min/max -> per-chunk atomics
+  // block min/max -> per-chunk atomics (an empty range keeps min > max and is skipped)
+  uint64_t a0 = mn0, b0 = mx0, a1 = mn1, b1 = mx1;
+  bool any0 = mn0 <= mx0, any1 = mn1 <= mx1;
+  if (!any0) { a0 = ~uint64_t(0); b0 = 0; }
+  if (!any1) { a1 = ~uint64_t(0); b1 = 0; }
   for (int d = 16; d > 0; d >>= 1) {
-    mn0 = min(mn0, __shfl_xor_sync(0xffffffffu, mn0, d));
-    mx0 = max(mx0, __shfl_xor_sync(0xffffffffu, mx0, d));
-    mn1 = min(mn1, __shfl_xor_sync(0xffffffffu, mn1, d));
-    mx1 = max(mx1, __shfl_xor_sync(0xffffffffu, mx1, d));
+    a0 = min(a0, __shfl_xor_sync(0xffffffffu, a0, d));
+    b0 = max(b0, __shfl_xor_sync(0xffffffffu, b0, d));
+    if (two_vars) {
+      a1 = min(a1, __shfl_xor_sync(0xffffffffu, a1, d));
+      b1 = max(b1, __shfl_xor_sync(0xffffffffu, b1, d));
+    }
   }
-  if ((tid & 31) == 0) { red_min[0][tid >> 5] = mn0; red_max[0][tid >> 5] = mx0; red_min[1][tid >> 5] = mn1; red_max[1][tid >> 5] = mx1; }
+  if ((tid & 31) == 0) { red_min[0][tid >> 5] = a0; red_max[0][tid >> 5] = b0; red_min[1][tid >> 5] = a1; red_max[1][tid >> 5] = b1; }
   __syncthreads();
   if (tid < int(ep.n_vars)) {
     uint64_t a = ~uint64_t(0), b = 0;
@@ -329,15 +350,38 @@ __global__ void segment_offsets_kernel(EncParams ep, uint32_t order_v, uint64_t*
 }
 
 // ---------------------------------------------------------------------------
-// plan_kernel: one CTA per (chunk, var).  Input: the var's stored latents sorted ascending (as keys = l - min).
+// Bin training (train_infos, chunk_compressor.rs:52-99) in two kernels per latent var:
+//   plan_probe_kernel — one 512-thread CTA per chunk, HBM-bound: order statistics at the 2^log equal-count boundaries
+//                       (from shared-memory counters when the key range is narrow, else from the sorted keys)
+//   plan_solve_kernel — one WARP per chunk, latency-bound and short: histogram state machine, bin-merge DP, weight
+//                       quantisation, tANS tables.  All chunks are resident at once, so the serial parts overlap.
 // ---------------------------------------------------------------------------
 constexpr int PLAN_THREADS = 512;
+constexpr int SOLVE_THREADS = 32;
 constexpr uint32_t PLAN_MAX_COUNT_BITS = 15;  // counting histogram (no sort) when the key range fits 2^15 shared-memory counters
 
-struct PlanSmem {
-  // histogram boundary probes
+// Order statistics handed from the probe kernel to the solver (per chunk and var, in HBM scratch)
+struct PlanProbes {
   uint64_t vB1[ENC_MAXB], vB[ENC_MAXB], vLm1[ENC_MAXB], vR[ENC_MAXB];
   uint32_t runL[ENC_MAXB], runR[ENC_MAXB];
+  uint64_t first;  // smallest key
+  uint64_t pad;
+};
+
+struct PlanSmem {
+  union {
+    PlanProbes probes;  // dead once the unoptimized histogram exists
+    struct {
+      uint32_t o_count[ENC_MAXB];
+      uint64_t o_lower[ENC_MAXB], o_upper[ENC_MAXB];
+      uint32_t o_ob[ENC_MAXB];
+      float fweights[ENC_MAXB];
+      uint32_t weights[ENC_MAXB];
+      uint32_t cum[ENC_MAXB + 1];
+      uint16_t sym_of_state[1 << ENC_MAX_SIZE_LOG];
+      uint32_t rank_counter[ENC_MAXB];
+    };
+  };
   // unoptimized bins
   uint32_t h_count[ENC_MAXB];
   uint64_t h_lower[ENC_MAXB], h_upper[ENC_MAXB];
@@ -346,19 +390,8 @@ struct PlanSmem {
   uint32_t c_counts[ENC_MAXB + 1];
   float best_cost[ENC_MAXB + 1];
   uint32_t best_j[ENC_MAXB];
-  float red_cost[PLAN_THREADS / 32];
-  uint32_t red_j[PLAN_THREADS / 32];
-  // optimized bins
-  uint32_t o_count[ENC_MAXB];
-  uint64_t o_lower[ENC_MAXB], o_upper[ENC_MAXB];
-  uint32_t o_ob[ENC_MAXB];
   uint32_t n_opt;
-  float fweights[ENC_MAXB];
-  uint32_t weights[ENC_MAXB];
-  uint32_t cum[ENC_MAXB + 1];
   uint32_t size_log;
-  uint16_t sym_of_state[1 << ENC_MAX_SIZE_LOG];
-  uint32_t rank_counter[ENC_MAXB];
 };
 
 // COUNTING = false: `keys` holds the var's stored latents minus the chunk minimum, sorted ascending per chunk.
@@ -366,44 +399,59 @@ struct PlanSmem {
 //                   every key into shared memory, prefix-sums the counters, and reads ranks / run extents off the
 //                   cumulative counts -- the planner only ever needs order statistics, never the sorted array.
 template <typename L, bool COUNTING>
-__global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(EncParams ep, const L* __restrict__ keys, const ChunkEnc* __restrict__ chunks,
-                                                             VarPlan* __restrict__ plans, int v, uint32_t range_bits) {
+__global__ void __launch_bounds__(PLAN_THREADS) plan_probe_kernel(EncParams ep, const L* __restrict__ keys, const ChunkEnc* __restrict__ chunks,
+                                                                   PlanProbes* __restrict__ probes, int v, uint32_t range_bits) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  PlanSmem& sm = *reinterpret_cast<PlanSmem*>(smem_raw);
-  uint32_t* cum = reinterpret_cast<uint32_t*>(smem_raw + ((sizeof(PlanSmem) + 15) & ~size_t(15)));  // COUNTING: 2^range_bits + 1 entries
+  uint32_t* cum = reinterpret_cast<uint32_t*>(smem_raw);  // COUNTING: 2^range_bits + 1 entries
   __shared__ uint32_t scan_part[PLAN_THREADS / 32];
   const uint32_t c = blockIdx.x;
   const int tid = threadIdx.x;
   const uint64_t cs = ep.chunk_starts[c], ce = ep.chunk_starts[c + 1];
   const uint64_t sb = stored_begin(cs, ce, v == 0 ? ep.order : 0);
   const uint32_t n = uint32_t(ce - sb);  // stored latents
+  if (n == 0) return;
   const L* s = keys + sb;
   ENC_TICK_INIT();
   const uint32_t n_vals = COUNTING ? (1u << range_bits) : 0u;
-  if (COUNTING && n > 0) {
+  if (COUNTING) {
     const L mn = L(chunks[c].vmin[v]);
     for (uint32_t i = tid; i <= n_vals; i += PLAN_THREADS) cum[i] = 0;
     __syncthreads();
-    for (uint32_t i = tid; i < n; i += PLAN_THREADS) atomicAdd(&cum[uint32_t(L(s[i] - mn))], 1u);
+    {
+      uint32_t i = tid;
+      for (; i + 3 * PLAN_THREADS < n; i += 4 * PLAN_THREADS) {  // four loads in flight per thread
+        const L a0 = s[i], a1 = s[i + PLAN_THREADS], a2 = s[i + 2 * PLAN_THREADS], a3 = s[i + 3 * PLAN_THREADS];
+        atomicAdd(&cum[uint32_t(L(a0 - mn))], 1u);
+        atomicAdd(&cum[uint32_t(L(a1 - mn))], 1u);
+        atomicAdd(&cum[uint32_t(L(a2 - mn))], 1u);
+        atomicAdd(&cum[uint32_t(L(a3 - mn))], 1u);
+      }
+      for (; i < n; i += PLAN_THREADS) atomicAdd(&cum[uint32_t(L(s[i] - mn))], 1u);
+    }
     __syncthreads();
     ENC_TICK(0);  // zero + count
-    // exclusive scan of the counters: each thread owns a contiguous slice
-    const uint32_t per = (n_vals + PLAN_THREADS - 1) / PLAN_THREADS;
-    const uint32_t lo = min(n_vals, tid * per), hi = min(n_vals, lo + per);
-    uint32_t sum = 0;
-    for (uint32_t i = lo; i < hi; i++) sum += cum[i];
-    uint32_t inc = sum;
-    for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if ((tid & 31) >= d) inc += o; }
-    if ((tid & 31) == 31) scan_part[tid >> 5] = inc;
+    // exclusive scan of the counters: warp w owns a contiguous span and walks it 32 counters at a time
+    const int lane = tid & 31, warp = tid >> 5;
+    const uint32_t span = (n_vals + PLAN_THREADS / 32 - 1) / (PLAN_THREADS / 32);
+    const uint32_t w_lo = min(n_vals, warp * span), w_hi = min(n_vals, w_lo + span);
+    uint32_t carry = 0;
+    for (uint32_t base = w_lo; base < w_hi; base += 32) {
+      const uint32_t idx = base + lane;
+      const uint32_t cnt = idx < w_hi ? cum[idx] : 0u;
+      uint32_t inc = cnt;
+      for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+      if (idx < w_hi) cum[idx] = carry + inc - cnt;
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) scan_part[warp] = carry;
     __syncthreads();
     uint32_t wbase = 0;
-    for (int w = 0; w < (tid >> 5); w++) wbase += scan_part[w];
-    uint32_t run = wbase + inc - sum;
-    for (uint32_t i = lo; i < hi; i++) { uint32_t t = cum[i]; cum[i] = run; run += t; }
-    if (tid == PLAN_THREADS - 1) cum[n_vals] = n;
+    for (int w = 0; w < warp; w++) wbase += scan_part[w];
+    for (uint32_t idx = w_lo + lane; idx < w_hi; idx += 32) cum[idx] += wbase;
+    if (tid == 0) cum[n_vals] = n;
     __syncthreads();
+    ENC_TICK(1);  // scan
   }
-  ENC_TICK(1);  // scan
   // value at sorted rank idx
   auto s_at = [&](uint32_t idx) -> uint64_t {
     if (!COUNTING) return uint64_t(s[idx]);
@@ -411,18 +459,12 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(EncParams ep, const 
     while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (cum[m] <= idx) lo = m; else hi = m; }
     return lo;
   };
-  VarPlan& plan = plans[size_t(c) * MAX_VARS + v];
-  const uint64_t vmin = chunks[c].vmin[v];
-  constexpr uint32_t LBITS = LT<L>::BITS;
-  if (n == 0) {  // train_infos on an empty var (chunk_compressor.rs:56-58): zero bins
-    if (tid == 0) { plan.n_bins = 0; plan.size_log = 0; plan.max_ob = 0; plan.n_lat = 0; plan.wc_bits = 0; plan.next_states[0] = 0; }
-    return;
-  }
+  PlanProbes& pr = probes[c];
   const uint32_t n_bins_log = ep.bins_log[v];
   const uint32_t nbk = 1u << n_bins_log;
-  auto bin_idx_of = [&](uint64_t cc) -> uint32_t { return uint32_t((cc << n_bins_log) / n); };
   auto c_count_of = [&](uint32_t b) -> uint32_t { return uint32_t((uint64_t(b + 1) * n + nbk - 1) >> n_bins_log); };
-  // ---- 1. probes at every equal-count boundary, in parallel (histograms.rs:132-140)
+  if (tid == 0) pr.first = s_at(0);
+  // probes at every equal-count boundary, in parallel (histograms.rs:132-140)
   for (uint32_t k = tid; k < nbk; k += PLAN_THREADS) {
     uint32_t B = c_count_of(k);
     uint64_t vb1 = 0, vb = 0, vlm1 = 0, vr = 0;
@@ -447,17 +489,47 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(EncParams ep, const 
         if (r < n) vr = s_at(r);
       }
     }
-    sm.vB1[k] = vb1; sm.vB[k] = vb; sm.vLm1[k] = vlm1; sm.vR[k] = vr; sm.runL[k] = l; sm.runR[k] = r;
+    pr.vB1[k] = vb1; pr.vB[k] = vb; pr.vLm1[k] = vlm1; pr.vR[k] = vr; pr.runL[k] = l; pr.runR[k] = r;
+  }
+  ENC_TICK(2);  // probes
+}
+
+template <typename L>
+__global__ void __launch_bounds__(SOLVE_THREADS) plan_solve_kernel(EncParams ep, const PlanProbes* __restrict__ probes,
+                                                                    const ChunkEnc* __restrict__ chunks, VarPlan* __restrict__ plans, int v) {
+  __shared__ PlanSmem sm;
+  const uint32_t c = blockIdx.x;
+  const int tid = threadIdx.x;
+  const uint64_t cs = ep.chunk_starts[c], ce = ep.chunk_starts[c + 1];
+  const uint64_t sb = stored_begin(cs, ce, v == 0 ? ep.order : 0);
+  const uint32_t n = uint32_t(ce - sb);  // stored latents
+  VarPlan& plan = plans[size_t(c) * MAX_VARS + v];
+  const uint64_t vmin = chunks[c].vmin[v];
+  constexpr uint32_t LBITS = LT<L>::BITS;
+  if (n == 0) {  // train_infos on an empty var (chunk_compressor.rs:56-58): zero bins
+    if (tid == 0) { plan.n_bins = 0; plan.size_log = 0; plan.max_ob = 0; plan.n_lat = 0; plan.wc_bits = 0; plan.next_states[0] = 0; }
+    return;
+  }
+  ENC_TICK_INIT();
+  const uint32_t n_bins_log = ep.bins_log[v];
+  const uint32_t nbk = 1u << n_bins_log;
+  const bool small_n = n <= (1u << 20);  // (cc << n_bins_log) fits 32 bits (n_bins_log <= 8)
+  auto bin_idx_of = [&](uint64_t cc) -> uint32_t { return small_n ? (uint32_t(cc) << n_bins_log) / n : uint32_t((cc << n_bins_log) / n); };
+  auto c_count_of = [&](uint32_t b) -> uint32_t { return uint32_t((uint64_t(b + 1) * n + nbk - 1) >> n_bins_log); };
+  {
+    // stage this chunk's probes (coalesced 16-byte copies)
+    const uint4* src = reinterpret_cast<const uint4*>(&probes[c]);
+    uint4* dst = reinterpret_cast<uint4*>(&sm.probes);
+    for (uint32_t i = tid; i < sizeof(PlanProbes) / 16; i += SOLVE_THREADS) dst[i] = src[i];
   }
   __syncthreads();
-  ENC_TICK(2);  // probes
   // ---- 2. histogram state machine (HistogramBuilder), sequential over at most 2^log boundaries
   if (tid == 0) {
     uint32_t n_hist = 0, next_avail = 0, pos = 0;
     bool has_inc = false;
     uint32_t inc_count = 0;
     uint64_t inc_lower = 0, inc_upper = 0;
-    uint64_t pos_val = s_at(0);
+    uint64_t pos_val = sm.probes.first;
     auto apply_incomplete = [&](uint32_t cnt, uint64_t lo_v, uint64_t hi_v) {
       if (cnt == 0) return;
       if (has_inc) { inc_upper = hi_v; inc_count += cnt; }
@@ -474,15 +546,15 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(EncParams ep, const 
     while (pos < n) {
       uint32_t k = bin_idx_of(pos);
       uint32_t B = c_count_of(k);
-      if (B >= n || sm.vB1[k] != sm.vB[k]) {
-        apply_incomplete(B - pos, pos_val, sm.vB1[k]);
+      if (B >= n || sm.probes.vB1[k] != sm.probes.vB[k]) {
+        apply_incomplete(B - pos, pos_val, sm.probes.vB1[k]);
         complete_bin(k);
         pos = B;
-        pos_val = sm.vB[k];
+        pos_val = sm.probes.vB[k];
       } else {
-        uint32_t l = sm.runL[k], r = sm.runR[k];
-        uint64_t val = sm.vB1[k];
-        if (l > pos) apply_incomplete(l - pos, pos_val, sm.vLm1[k]);
+        uint32_t l = sm.probes.runL[k], r = sm.probes.runR[k];
+        uint64_t val = sm.probes.vB1[k];
+        if (l > pos) apply_incomplete(l - pos, pos_val, sm.probes.vLm1[k]);
         // apply_constant_run (histograms.rs:142-161)
         uint32_t mid = l + (r - l) / 2;
         uint32_t b = bin_idx_of(mid);
@@ -493,7 +565,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(EncParams ep, const 
         apply_incomplete(r - l, val, val);
         if (r >= c_count_of(b)) complete_bin(b);
         pos = r;
-        pos_val = sm.vR[k];
+        pos_val = sm.probes.vR[k];
       }
     }
     sm.n_hist = n_hist;
@@ -521,32 +593,19 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(EncParams ep, const 
     const uint64_t upper = sm.h_upper[i];
     const uint32_t cci = sm.c_counts[i + 1];
     // each thread scans its js downward (strict <: the largest j wins ties)
-    for (int j = int(i) - tid; j >= 0; j -= PLAN_THREADS) {
+    for (int j = int(i) - tid; j >= 0; j -= SOLVE_THREADS) {
       float cost = __fadd_rn(sm.best_cost[j], bin_cost_dev(bin_meta_cost, upper - sm.h_lower[j], cci - sm.c_counts[j], total_log2));
       if (cost < my_cost) { my_cost = cost; my_j = uint32_t(j); }
     }
-    // warp then block argmin with "largest j among equal costs"
+    // warp argmin with "largest j among equal costs" (one warp per chunk: no block barrier on the DP's serial axis)
     for (int d = 16; d > 0; d >>= 1) {
       float oc = __shfl_xor_sync(0xffffffffu, my_cost, d);
       uint32_t oj = __shfl_xor_sync(0xffffffffu, my_j, d);
       bool take = (oj != 0xffffffffu) && (my_j == 0xffffffffu || oc < my_cost || (oc == my_cost && oj > my_j));
       if (take) { my_cost = oc; my_j = oj; }
     }
-    if ((tid & 31) == 0) { sm.red_cost[tid >> 5] = my_cost; sm.red_j[tid >> 5] = my_j; }
-    __syncthreads();
-    if (tid == 0) {
-      float bc = sm.red_cost[0];
-      uint32_t bj = sm.red_j[0];
-      for (int w = 1; w < PLAN_THREADS / 32; w++) {
-        float oc = sm.red_cost[w];
-        uint32_t oj = sm.red_j[w];
-        bool take = (oj != 0xffffffffu) && (bj == 0xffffffffu || oc < bc || (oc == bc && oj > bj));
-        if (take) { bc = oc; bj = oj; }
-      }
-      sm.best_cost[i + 1] = bc;
-      sm.best_j[i] = bj;
-    }
-    __syncthreads();
+    if (tid == 0) { sm.best_cost[i + 1] = my_cost; sm.best_j[i] = my_j; }
+    __syncwarp();
   }
   ENC_TICK(4);  // DP
   // ---- 4. shortcuts, rewind, weights (thread 0: short sequential f32 sums whose order matters)
@@ -656,7 +715,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(EncParams ep, const 
   ENC_TICK(5);  // rewind + quantize
   const uint32_t n_opt = sm.n_opt, size_log = sm.size_log, size = 1u << size_log;
   const uint64_t lmask = LBITS == 64 ? ~uint64_t(0) : ((uint64_t(1) << LBITS) - 1);
-  for (uint32_t q = tid; q < n_opt; q += PLAN_THREADS) {
+  for (uint32_t q = tid; q < n_opt; q += SOLVE_THREADS) {
     plan.lower[q] = (sm.o_lower[q] + vmin) & lmask;
     plan.ob[q] = uint8_t(sm.o_ob[q]);
     plan.weight[q] = uint16_t(sm.weights[q]);
@@ -671,7 +730,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(EncParams ep, const 
   // spread (ans/spec.rs:37-59) and per-symbol ascending state lists (ans/encoding.rs:51-55)
   uint32_t stride = (3 * size) / 5;
   if ((stride & 1) == 0) stride += 1;
-  for (uint32_t t = tid; t < size; t += PLAN_THREADS) {
+  for (uint32_t t = tid; t < size; t += SOLVE_THREADS) {
     uint32_t lo = 0, hi = n_opt;
     while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (sm.cum[m] <= t) lo = m; else hi = m; }
     sm.sym_of_state[(stride * t) & (size - 1)] = uint16_t(lo);
@@ -796,6 +855,100 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_kernel(EncParams ep, uint32_t
   }
   for (int d = 16; d > 0; d >>= 1) bits += __shfl_xor_sync(0xffffffffu, bits, d);
   if (lane == 0) ob_sum[(size_t(c) * MAX_VARS + v) * batches_per_chunk + b] = bits;
+}
+
+// Narrow key range (the counting-planner case, keys < 2^range_bits <= 2^15): the bin of a latent is a direct lookup in a
+// per-chunk shared-memory table key -> bin (marks at every bin's lower bound, then a running max), instead of a
+// search_log-deep binary search per latent.  One CTA bins BINL_BATCHES batches of one chunk, one warp per batch,
+// lanes striding the batch so that every load is a fully used 256-byte line.
+constexpr int BINL_THREADS = 256;
+constexpr int BINL_BATCHES = 128;
+
+template <typename L>
+__global__ void __launch_bounds__(BINL_THREADS) bin_lut_kernel(EncParams ep, uint32_t batches_per_chunk, uint32_t parts_per_chunk, const L* __restrict__ lat,
+                                                                const VarPlan* __restrict__ plans, const ChunkEnc* __restrict__ chunks,
+                                                                uint8_t* __restrict__ sym, uint32_t* __restrict__ ob_sum, int v, uint32_t range_bits) {
+  extern __shared__ __align__(16) unsigned char binl_smem[];
+  uint32_t* lut_w = reinterpret_cast<uint32_t*>(binl_smem);  // 2^range_bits bytes, 4 keys per word
+  uint8_t* lut = binl_smem;
+  __shared__ uint8_t obs[ENC_MAXB];
+  __shared__ uint32_t warp_top[BINL_THREADS / 32];
+  const uint32_t c = blockIdx.x / parts_per_chunk, part = blockIdx.x % parts_per_chunk;
+  const uint64_t cs = ep.chunk_starts[c], ce = ep.chunk_starts[c + 1];
+  const bool fb = chunks[c].fallback != 0;
+  if (fb && v > 0) return;
+  const uint64_t sb = fb ? cs : stored_begin(cs, ce, v == 0 ? ep.order : 0);
+  const uint32_t n = uint32_t(ce - sb);
+  const uint32_t b_begin = part * BINL_BATCHES;
+  if (uint64_t(b_begin) * BATCH_N >= n) return;
+  const uint32_t b_end = min(b_begin + BINL_BATCHES, n_batches_of(n));
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t* sums = ob_sum + (size_t(c) * MAX_VARS + v) * batches_per_chunk;
+  if (fb) {
+    // one bin of L::BITS offset bits (chunk_compressor.rs:502-541): every symbol is 0
+    for (uint32_t b = b_begin + warp; b < b_end; b += BINL_THREADS / 32) {
+      const uint32_t cnt = min(uint32_t(BATCH_N), n - b * BATCH_N);
+      uint8_t* row = sym + sb + uint64_t(b) * BATCH_N;
+      for (uint32_t i = lane; i < cnt; i += 32) row[i] = 0;
+      if (lane == 0) sums[b] = cnt * LT<L>::BITS;
+    }
+    return;
+  }
+  const VarPlan& plan = plans[size_t(c) * MAX_VARS + v];
+  const uint32_t n_bins = plan.n_bins;
+  const L vmin = L(chunks[c].vmin[v]);
+  const uint32_t n_words = max(1u, (1u << range_bits) / 4);
+  for (uint32_t i = tid; i < n_words; i += BINL_THREADS) lut_w[i] = 0;
+  for (uint32_t i = tid; i < n_bins; i += BINL_THREADS) obs[i] = plan.ob[i];
+  __syncthreads();
+  for (uint32_t i = tid; i < n_bins; i += BINL_THREADS) lut[uint32_t(L(L(plan.lower[i]) - vmin))] = uint8_t(i);  // lowers are strictly increasing
+  __syncthreads();
+  {
+    // running max over the marks: warp w owns a contiguous span of words and walks it 32 words at a time
+    const uint32_t span = (n_words + BINL_THREADS / 32 - 1) / (BINL_THREADS / 32);
+    const uint32_t w_lo = min(n_words, warp * span), w_hi = min(n_words, w_lo + span);
+    uint32_t carry = 0;  // max bin index seen so far in this warp's span
+    for (uint32_t base = w_lo; base < w_hi; base += 32) {
+      const uint32_t idx = base + lane;
+      uint32_t x = idx < w_hi ? lut_w[idx] : 0u;
+      x = __vmaxu4(x, x << 8);
+      x = __vmaxu4(x, x << 16);  // byte k = max of bytes 0..k
+      uint32_t top = x >> 24;
+      uint32_t inc = top;
+      for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc = max(inc, o); }
+      uint32_t before = __shfl_up_sync(0xffffffffu, inc, 1);
+      before = lane == 0 ? carry : max(before, carry);
+      x = __vmaxu4(x, before * 0x01010101u);
+      if (idx < w_hi) lut_w[idx] = x;
+      carry = max(carry, __shfl_sync(0xffffffffu, inc, 31));
+    }
+    if (lane == 0) warp_top[warp] = carry;
+    __syncthreads();
+    uint32_t prev = 0;
+    for (int w = 0; w < warp; w++) prev = max(prev, warp_top[w]);
+    const uint32_t prev4 = prev * 0x01010101u;
+    for (uint32_t idx = w_lo + lane; idx < w_hi; idx += 32) lut_w[idx] = __vmaxu4(lut_w[idx], prev4);
+    __syncthreads();
+  }
+  for (uint32_t b = b_begin + warp; b < b_end; b += BINL_THREADS / 32) {
+    const uint32_t cnt = min(uint32_t(BATCH_N), n - b * BATCH_N);
+    const L* src = lat + sb + uint64_t(b) * BATCH_N;
+    uint8_t* row = sym + sb + uint64_t(b) * BATCH_N;  // symbol array is indexed like the input
+    L x[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) x[e] = uint32_t(lane + 32 * e) < cnt ? src[lane + 32 * e] : vmin;
+    uint32_t bits = 0;
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+      const uint32_t sidx = lut[uint32_t(L(x[e] - vmin))];
+      if (uint32_t(lane + 32 * e) < cnt) {
+        bits += obs[sidx];
+        row[lane + 32 * e] = uint8_t(sidx);
+      }
+    }
+    for (int d = 16; d > 0; d >>= 1) bits += __shfl_xor_sync(0xffffffffu, bits, d);
+    if (lane == 0) sums[b] = bits;
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -1167,12 +1320,19 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(EncParams ep, uint32
   uint64_t win_bit0 = body_bit0;  // multiple of 8
   while (b0 < nb) {
     // choose b1 > b0 so that [start(b0), end(b1 - 1)) fits the window; a single batch always fits (<= 2*256*78 bits)
+    // (batch ends are monotone, so the batches that still fit form a prefix: every thread probes one candidate per round)
     uint32_t b1 = b0 + 1;
     const uint64_t win_cap_bits = uint64_t(PACK_WINDOW_WORDS) * 32 - 64;
-    while (b1 < nb) {
-      uint64_t endb = (b1 + 1 < nb) ? entry_pos(b1 + 1, 0) : body_end;
-      if (endb - win_bit0 > win_cap_bits) break;
-      b1++;
+    for (;;) {
+      const uint32_t cand = b1 + tid;
+      bool fits = false;
+      if (cand < nb) {
+        const uint64_t endb = (cand + 1 < nb) ? entry_pos(cand + 1, 0) : body_end;
+        fits = endb - win_bit0 <= win_cap_bits;
+      }
+      const uint32_t more = __syncthreads_count(fits ? 1 : 0);
+      b1 += more;
+      if (more < PACK_THREADS) break;
     }
     const uint64_t win_end_bit = (b1 < nb) ? entry_pos(b1, 0) : body_end;
     const uint32_t win_words = uint32_t((win_end_bit - win_bit0 + 31) / 32) + 1;
