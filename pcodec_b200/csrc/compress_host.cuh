@@ -207,20 +207,22 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
   const uint32_t bpc = n_batches_of(uint32_t(max_chunk_n));
   const uint32_t tiles_per_chunk = uint32_t((max_chunk_n + SPLIT_TILE - 1) / SPLIT_TILE);
   const void* d_nums = nums;
-  PCOB_CUDA_TRY(S.lat0.reserve(n * sizeof(L) + 64));
-  if (ep.n_vars > 1) PCOB_CUDA_TRY(S.lat1.reserve(n * sizeof(L) + 64));
-  PCOB_CUDA_TRY(S.keys_a.reserve(n * sizeof(L) + 64));
-  PCOB_CUDA_TRY(S.keys_b.reserve(n * sizeof(L) + 64));
-  PCOB_CUDA_TRY(S.sym0.reserve(n + 64));
-  PCOB_CUDA_TRY(S.ans0.reserve(n * 2 + 64));
-  if (ep.n_vars > 1) { PCOB_CUDA_TRY(S.sym1.reserve(n + 64)); PCOB_CUDA_TRY(S.ans1.reserve(n * 2 + 64)); }
+  // every chunk's rows start on a 256-slot boundary in the latent / symbol / ans arrays (vector accesses per batch row)
+  std::vector<uint64_t> rows(pages.size() + 1, 0);
+  for (size_t i = 0; i < pages.size(); i++) rows[i + 1] = rows[i] + ((pages[i] + BATCH_N - 1) / BATCH_N) * BATCH_N;
+  const size_t n_slots = size_t(rows.back());
+  PCOB_CUDA_TRY(S.lat0.reserve(n_slots * sizeof(L) + 64));
+  if (ep.n_vars > 1) PCOB_CUDA_TRY(S.lat1.reserve(n_slots * sizeof(L) + 64));
+  PCOB_CUDA_TRY(S.sym0.reserve(n_slots + 64));
+  PCOB_CUDA_TRY(S.ans0.reserve(n_slots * 2 + 64));
+  if (ep.n_vars > 1) { PCOB_CUDA_TRY(S.sym1.reserve(n_slots + 64)); PCOB_CUDA_TRY(S.ans1.reserve(n_slots * 2 + 64)); }
   const size_t n_cvb = size_t(n_chunks) * MAX_VARS * bpc;
   PCOB_CUDA_TRY(S.ob_sum.reserve(n_cvb * 4));
   PCOB_CUDA_TRY(S.ans_sum.reserve(n_cvb * 4));
   PCOB_CUDA_TRY(S.entries.reserve(n_cvb * sizeof(BatchEntry)));
   PCOB_CUDA_TRY(S.plans.reserve(size_t(n_chunks) * MAX_VARS * sizeof(VarPlan)));
   PCOB_CUDA_TRY(S.chunks.reserve(size_t(n_chunks) * sizeof(ChunkEnc)));
-  PCOB_CUDA_TRY(S.starts.reserve(starts.size() * 8));
+  PCOB_CUDA_TRY(S.starts.reserve(starts.size() * 16));
   PCOB_CUDA_TRY(S.seg.reserve(size_t(n_chunks) * 16));
   PCOB_CUDA_TRY(S.small.reserve(256 + header.size()));
   // a dedicated input staging buffer when nums live on the host (kept apart from the sort buffers)
@@ -233,6 +235,8 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
   ep.nums = d_nums;
   PCOB_CUDA_TRY(cudaMemcpyAsync(S.starts.p, starts.data(), starts.size() * 8, cudaMemcpyHostToDevice, stream));
   ep.chunk_starts = S.starts.as<uint64_t>();
+  PCOB_CUDA_TRY(cudaMemcpyAsync(S.starts.as<uint64_t>() + starts.size(), rows.data(), rows.size() * 8, cudaMemcpyHostToDevice, stream));
+  ep.row_base = S.starts.as<uint64_t>() + starts.size();
   ChunkEnc* d_chunks = S.chunks.as<ChunkEnc>();
   VarPlan* d_plans = S.plans.as<VarPlan>();
   PCOB_CUDA_TRY(S.probes.reserve(size_t(n_chunks) * sizeof(PlanProbes)));
@@ -263,7 +267,6 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
     PCOB_CUDA_TRY(cudaFuncSetAttribute(plan_probe_kernel<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(((size_t(1) << PLAN_MAX_COUNT_BITS) + 1) * 4 + 16)));
     PCOB_CUDA_TRY(cudaFuncSetAttribute(pack_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PackSmem)));
-    PCOB_CUDA_TRY(cudaFuncSetAttribute(ans_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AnsSmem)));
   }
   uint32_t var_range_bits[MAX_VARS] = {64, 64};
   for (uint32_t v = 0; v < ep.n_vars; v++) {
@@ -285,6 +288,9 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
       profiler().end(stream);
       continue;
     }
+    // wide key range: sort the range-reduced keys (the two key buffers exist only on this path)
+    PCOB_CUDA_TRY(S.keys_a.reserve(n_slots * sizeof(L) + 64));
+    PCOB_CUDA_TRY(S.keys_b.reserve(n_slots * sizeof(L) + 64));
     profiler().begin("sort_keys_kernel", stream);
     sort_keys_kernel<L><<<n_chunks * tiles_per_chunk, 256, 0, stream>>>(ep, tiles_per_chunk, d_lat[v], S.keys_a.as<L>(), d_chunks, int(v));
     profiler().end(stream);
@@ -295,11 +301,11 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
     {
       cub::DoubleBuffer<L> db(S.keys_a.as<L>(), S.keys_b.as<L>());
       size_t tmp_bytes = 0;
-      PCOB_CUDA_TRY(cub::DeviceSegmentedRadixSort::SortKeys(nullptr, tmp_bytes, db, int64_t(n), int64_t(n_chunks), seg_begin, seg_end, 0,
+      PCOB_CUDA_TRY(cub::DeviceSegmentedRadixSort::SortKeys(nullptr, tmp_bytes, db, int64_t(n_slots), int64_t(n_chunks), seg_begin, seg_end, 0,
                                                             int(range_bits), stream));
       PCOB_CUDA_TRY(S.cub_tmp.reserve(tmp_bytes + 16));
       profiler().begin("cub_segmented_radix_sort", stream);
-      PCOB_CUDA_TRY(cub::DeviceSegmentedRadixSort::SortKeys(S.cub_tmp.p, tmp_bytes, db, int64_t(n), int64_t(n_chunks), seg_begin, seg_end, 0,
+      PCOB_CUDA_TRY(cub::DeviceSegmentedRadixSort::SortKeys(S.cub_tmp.p, tmp_bytes, db, int64_t(n_slots), int64_t(n_chunks), seg_begin, seg_end, 0,
                                                             int(range_bits), stream));
       profiler().end(stream);
       sorted = db.Current();
@@ -330,7 +336,7 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
   }
   // the ans kernel indexes (chunk, var) by blockIdx; both vars share the launch via separate symbol arrays
   profiler().begin("ans_encode_kernel", stream);
-  ans_encode_kernel<<<n_chunks * MAX_VARS, ANS_THREADS, sizeof(AnsSmem), stream>>>(ep, bpc, d_plans, d_chunks, d_sym[0], d_sym[1], d_ans[0], d_ans[1], S.ans_sum.as<uint32_t>(),
+  ans_encode_kernel<<<n_chunks * MAX_VARS, ANS_THREADS, 0, stream>>>(ep, bpc, d_plans, d_chunks, d_sym[0], d_sym[1], d_ans[0], d_ans[1], S.ans_sum.as<uint32_t>(),
                                                                      S.entries.as<BatchEntry>());
   profiler().end(stream);
   // ---- layout, offsets, K5

@@ -39,6 +39,7 @@ struct EncParams {
   const void* nums;
   uint64_t n_total;
   const uint64_t* chunk_starts;  // device, n_chunks + 1 element offsets
+  const uint64_t* row_base;      // device, n_chunks + 1: first slot of each chunk in the latent / symbol / ans arrays
   uint32_t n_chunks;
   uint32_t max_chunk_n;
   uint32_t dtype;
@@ -203,7 +204,9 @@ constexpr int SPLIT_TILE = SPLIT_THREADS * SPLIT_PER_THREAD;
 __device__ __forceinline__ void atomic_min_u64(uint64_t* a, uint64_t v) { atomicMin(reinterpret_cast<unsigned long long*>(a), (unsigned long long)v); }
 __device__ __forceinline__ void atomic_max_u64(uint64_t* a, uint64_t v) { atomicMax(reinterpret_cast<unsigned long long*>(a), (unsigned long long)v); }
 
-// grid: n_chunks * tiles_per_chunk.  lat0/lat1 are indexed like nums (element g of the input).
+// grid: n_chunks * tiles_per_chunk.  The latent / symbol / ans arrays hold each chunk's STORED latents (the page minus the
+// first `order` of the primary) from slot row_base[c] on, row_base a multiple of 256: every batch row starts on a
+// 512-byte (u16) .. 2048-byte (u64) boundary and can be moved with 16-byte vector accesses.
 // MODE is a template parameter and the difference stencil's signed binomials live in registers: the kernel must stay
 // HBM-bound (read n, write n_vars * n latents), a generic per-element mode switch made it issue-bound.
 template <typename L, int MODE>
@@ -217,6 +220,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS) split_delta_kernel(EncParams ep
   const uint32_t tile_start = t * SPLIT_TILE;
   if (tile_start >= n) return;
   const L* nums = static_cast<const L*>(ep.nums) + cs;
+  const uint64_t rb = ep.row_base[c];
   const bool is_float = nt_is_float(ep.dtype), is_signed = nt_is_signed(ep.dtype);
   const uint32_t order = ep.order;
   const bool two_vars = MODE != MODE_CLASSIC && ep.n_vars > 1;
@@ -244,7 +248,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS) split_delta_kernel(EncParams ep
     if (idx < n) {
       split_one<L, MODE>(nums[idx], ep, is_float, is_signed, p, s);
       if (two_vars) {
-        lat1[cs + idx] = s;
+        lat1[rb + idx] = s;
         mn1 = min(mn1, s);
         mx1 = max(mx1, s);
       }
@@ -273,7 +277,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS) split_delta_kernel(EncParams ep
       d = L(acc + MID);  // toggle_center (delta/mod.rs:29-33)
     }
     if (idx < n && idx >= order) {
-      lat0[cs + idx] = d;
+      lat0[rb + idx - order] = d;
       mn0 = min(mn0, d);
       mx0 = max(mx0, d);
     }
@@ -333,10 +337,11 @@ __global__ void sort_keys_kernel(EncParams ep, uint32_t tiles_per_chunk, const L
   const uint32_t c = blockIdx.x / tiles_per_chunk, t = blockIdx.x % tiles_per_chunk;
   const uint64_t cs = ep.chunk_starts[c], ce = ep.chunk_starts[c + 1];
   const uint64_t sb = stored_begin(cs, ce, v == 0 ? ep.order : 0);
+  const uint64_t rb = ep.row_base[c], n = ce - sb;
   const L mn = L(chunks[c].vmin[v]);
   for (int i = threadIdx.x; i < SPLIT_TILE; i += blockDim.x) {
-    uint64_t g = cs + uint64_t(t) * SPLIT_TILE + i;
-    if (g >= sb && g < ce) keys[g] = L(lat[g] - mn);
+    uint64_t k = uint64_t(t) * SPLIT_TILE + i;
+    if (k < n) keys[rb + k] = L(lat[rb + k] - mn);
   }
 }
 
@@ -345,8 +350,8 @@ __global__ void segment_offsets_kernel(EncParams ep, uint32_t order_v, uint64_t*
   uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= ep.n_chunks) return;
   uint64_t cs = ep.chunk_starts[c], ce = ep.chunk_starts[c + 1];
-  begins[c] = stored_begin(cs, ce, order_v);
-  ends[c] = ce;
+  begins[c] = ep.row_base[c];
+  ends[c] = ep.row_base[c] + (ce - stored_begin(cs, ce, order_v));
 }
 
 // ---------------------------------------------------------------------------
@@ -410,7 +415,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_probe_kernel(EncParams ep, 
   const uint64_t sb = stored_begin(cs, ce, v == 0 ? ep.order : 0);
   const uint32_t n = uint32_t(ce - sb);  // stored latents
   if (n == 0) return;
-  const L* s = keys + sb;
+  const L* s = keys + ep.row_base[c];
   ENC_TICK_INIT();
   const uint32_t n_vals = COUNTING ? (1u << range_bits) : 0u;
   if (COUNTING) {
@@ -811,6 +816,7 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_kernel(EncParams ep, uint32_t
   const bool fb = chunks[c].fallback != 0;
   if (fb && v > 0) return;
   const uint64_t sb = fb ? cs : stored_begin(cs, ce, v == 0 ? ep.order : 0);
+  const uint64_t rb = ep.row_base[c];
   const uint32_t n = uint32_t(ce - sb);
   const uint32_t b = grp * 8 + (threadIdx.x >> 5);
   const VarPlan& plan = plans[size_t(c) * MAX_VARS + v];
@@ -831,8 +837,8 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_kernel(EncParams ep, uint32_t
     uint32_t i = lane * 8 + e;
     uint32_t sidx = 0;
     if (i < cnt) {
-      uint64_t g = sb + uint64_t(b) * BATCH_N + i;
-      uint64_t l = fb ? uint64_t(fallback_latent<L>(ep, g)) : uint64_t(lat[g]);
+      uint64_t k = uint64_t(b) * BATCH_N + i;
+      uint64_t l = fb ? uint64_t(fallback_latent<L>(ep, cs + k)) : uint64_t(lat[rb + k]);
       // compression_table.rs:51-74: balanced search over lowers padded with MAX, then clamp
       for (uint32_t depth = 0; depth < search_log; depth++) {
         uint32_t bis = 1u << (search_log - 1 - depth);
@@ -846,8 +852,7 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_kernel(EncParams ep, uint32_t
     }
     packed[e >> 2] |= sidx << (8 * (e & 3));
   }
-  uint8_t* row = sym + sb + uint64_t(b) * BATCH_N;  // symbol array is indexed like the input
-  // 8 symbols per lane; stores are 1-byte aligned in general (sb need not be 8-aligned)
+  uint8_t* row = sym + rb + uint64_t(b) * BATCH_N;
 #pragma unroll
   for (int e = 0; e < 8; e++) {
     uint32_t i = lane * 8 + e;
@@ -878,6 +883,7 @@ __global__ void __launch_bounds__(BINL_THREADS) bin_lut_kernel(EncParams ep, uin
   const bool fb = chunks[c].fallback != 0;
   if (fb && v > 0) return;
   const uint64_t sb = fb ? cs : stored_begin(cs, ce, v == 0 ? ep.order : 0);
+  const uint64_t rb = ep.row_base[c];
   const uint32_t n = uint32_t(ce - sb);
   const uint32_t b_begin = part * BINL_BATCHES;
   if (uint64_t(b_begin) * BATCH_N >= n) return;
@@ -888,7 +894,7 @@ __global__ void __launch_bounds__(BINL_THREADS) bin_lut_kernel(EncParams ep, uin
     // one bin of L::BITS offset bits (chunk_compressor.rs:502-541): every symbol is 0
     for (uint32_t b = b_begin + warp; b < b_end; b += BINL_THREADS / 32) {
       const uint32_t cnt = min(uint32_t(BATCH_N), n - b * BATCH_N);
-      uint8_t* row = sym + sb + uint64_t(b) * BATCH_N;
+      uint8_t* row = sym + rb + uint64_t(b) * BATCH_N;
       for (uint32_t i = lane; i < cnt; i += 32) row[i] = 0;
       if (lane == 0) sums[b] = cnt * LT<L>::BITS;
     }
@@ -932,8 +938,8 @@ __global__ void __launch_bounds__(BINL_THREADS) bin_lut_kernel(EncParams ep, uin
   }
   for (uint32_t b = b_begin + warp; b < b_end; b += BINL_THREADS / 32) {
     const uint32_t cnt = min(uint32_t(BATCH_N), n - b * BATCH_N);
-    const L* src = lat + sb + uint64_t(b) * BATCH_N;
-    uint8_t* row = sym + sb + uint64_t(b) * BATCH_N;  // symbol array is indexed like the input
+    const L* src = lat + rb + uint64_t(b) * BATCH_N;
+    uint8_t* row = sym + rb + uint64_t(b) * BATCH_N;
     L x[8];
 #pragma unroll
     for (int e = 0; e < 8; e++) x[e] = uint32_t(lane + 32 * e) < cnt ? src[lane + 32 * e] : vmin;
@@ -958,34 +964,36 @@ __global__ void __launch_bounds__(BINL_THREADS) bin_lut_kernel(EncParams ep, uin
 // ---------------------------------------------------------------------------
 // The encoder state chain of a page is serial (each step's state feeds the next, 2^16 steps per chain), but a tANS
 // step with a symbol of weight w maps all 2^size_log states onto w values, so two trajectories that start from different
-// states over the same symbols merge after a few steps and are identical from there on.  The kernel uses that: every
-// batch (segment) of a 64-batch round is encoded at once from a GUESSED input state; then each segment re-runs from its
-// TRUE input (the output of the segment before it in encode order) only until it meets the guessed trajectory.  A segment
-// that never merges changes its output and the round iterates until no output moves (worst case: one segment per
-// iteration, i.e. the serial order) - the result is always exactly the serial encoder's.
+// states over the same symbols merge after some steps (tens for typical bins) and are identical from there on.  The
+// kernel uses that: the page is cut into up to 64 segments of whole batches, one group of 4 threads (the 4 interleaved
+// chains) per segment, and every segment is encoded at once from a GUESSED input state - the state reached by replaying
+// the last ANS_WARM_BATCHES batches of the preceding segment from an arbitrary state, which has almost always merged
+// with the true trajectory by then.  Afterwards each segment compares its guess with its TRUE input (the output of the
+// segment before it in encode order) and, if they differ, re-runs from the true input only until it meets the guessed
+// trajectory.  A segment that never merges changes its output and the round iterates until no output moves (worst case:
+// one segment per iteration, i.e. the serial order) - the result is always exactly the serial encoder's.
 constexpr int ANS_THREADS = 256;
-constexpr int ANS_SEGS = ANS_THREADS / 4;  // batches per round: one thread per (batch, interleaved chain)
-constexpr int ANS_SYM_STRIDE = 260;        // staged symbol row, bytes (65 words: the 8 rows a warp touches hit 8 banks)
-constexpr int ANS_OUT_STRIDE = 260;        // staged output row, u16 (130 words)
+constexpr int ANS_SEGS = ANS_THREADS / 4;   // segments per round: one thread per (segment, interleaved chain)
+constexpr int ANS_WARM_BATCHES = 2;         // batches of the preceding segment replayed to form the guess
+constexpr uint32_t ANS_MAX_SEG_BATCHES = 16;
 
 struct AnsSmem {
   uint32_t desc_tab[ENC_MAXB];                 // per symbol: cutoff (12 bits) | min_renorm_bits << 12 | (cum - weight + 2048) << 16
   uint16_t next_states[1 << ENC_MAX_SIZE_LOG];  // full next state (size + slot), indexed cum + (x_s - weight)
   uint16_t out_state[ANS_SEGS][4];
   uint16_t carry[4];
-  alignas(4) uint8_t sym[ANS_SEGS * ANS_SYM_STRIDE];
-  alignas(4) uint16_t out[ANS_SEGS * ANS_OUT_STRIDE];
 };
 
-// One tANS step (ans/encoding.rs:72-83) from a pre-resolved descriptor.
-__device__ __forceinline__ uint32_t ans_step(uint32_t d, uint32_t& state, uint16_t* out_slot, const uint16_t* next_states) {
+// One tANS step (ans/encoding.rs:72-83) from a pre-resolved descriptor; returns the bit count, `o` = value | 1 << bits.
+__device__ __forceinline__ uint32_t ans_step(uint32_t d, uint32_t& state, uint32_t& o, const uint16_t* next_states) {
   const uint32_t cutoff = d & 0xfffu, mr = (d >> 12) & 0xfu, base = d >> 16;
   const uint32_t bits = mr + (state >= cutoff ? 1u : 0u);
-  *out_slot = uint16_t((state & ((1u << bits) - 1)) | (1u << bits));
+  const uint32_t top = 1u << bits;
+  o = (state & (top - 1)) | top;
   state = next_states[base + (state >> bits) - 2048u];
   return bits;
 }
-// the same step without the output (the guessed trajectory replayed next to the true one)
+// the same step without the output (warm-up, and the guessed trajectory replayed next to the true one)
 __device__ __forceinline__ uint32_t ans_step_quiet(uint32_t d, uint32_t& state, const uint16_t* next_states) {
   const uint32_t cutoff = d & 0xfffu, mr = (d >> 12) & 0xfu, base = d >> 16;
   const uint32_t bits = mr + (state >= cutoff ? 1u : 0u);
@@ -993,13 +1001,54 @@ __device__ __forceinline__ uint32_t ans_step_quiet(uint32_t d, uint32_t& state, 
   return bits;
 }
 
-__global__ void __launch_bounds__(ANS_THREADS) ans_encode_kernel(EncParams ep, uint32_t batches_per_chunk, const VarPlan* __restrict__ plans,
-                                                                  ChunkEnc* __restrict__ chunks, const uint8_t* __restrict__ sym0,
-                                                                  const uint8_t* __restrict__ sym1, uint16_t* __restrict__ ans0,
-                                                                  uint16_t* __restrict__ ans1, uint32_t* __restrict__ ans_sum,
-                                                                  BatchEntry* __restrict__ entries) {
-  extern __shared__ __align__(16) unsigned char ans_smem_raw[];
-  AnsSmem& sm = *reinterpret_cast<AnsSmem*>(ans_smem_raw);
+// Chain j's 64 steps over one FULL batch row (256 symbols, 16-byte aligned).  The 4 lanes of a segment read the same 16
+// symbols per group of 4 steps (one LDG.128), and transpose their 4x4 outputs with two shuffles so that each lane stores
+// 4 consecutive u16 (one STG.64).  `gmask` names the 4 lanes of the group; they execute this together.
+template <bool QUIET>
+__device__ __forceinline__ uint32_t ans_full_batch(const AnsSmem& sm, const uint8_t* __restrict__ row_sym, uint16_t* __restrict__ row_out, int j,
+                                                   uint32_t gmask, uint32_t& state) {
+  const uint4* src = reinterpret_cast<const uint4*>(row_sym);
+  const uint32_t pick = 0x4440u | uint32_t(j);  // __byte_perm selector: byte j of the word, zero-extended
+  const uint32_t sel_send = (j & 1) ? 0x5410u : 0x7632u, sel_q01 = (j & 1) ? 0x3254u : 0x5410u, sel_q23 = (j & 1) ? 0x3276u : 0x7610u;
+  uint32_t bits_total = 0;
+  uint4 cur = src[15], nxt = cur;
+#pragma unroll 2
+  for (int q = 15; q >= 0; q--) {
+    if (q > 0) nxt = src[q - 1];
+    const uint32_t d3 = sm.desc_tab[__byte_perm(cur.w, 0, pick)], d2 = sm.desc_tab[__byte_perm(cur.z, 0, pick)];
+    const uint32_t d1 = sm.desc_tab[__byte_perm(cur.y, 0, pick)], d0 = sm.desc_tab[__byte_perm(cur.x, 0, pick)];
+    if (QUIET) {
+      ans_step_quiet(d3, state, sm.next_states);
+      ans_step_quiet(d2, state, sm.next_states);
+      ans_step_quiet(d1, state, sm.next_states);
+      ans_step_quiet(d0, state, sm.next_states);
+    } else {
+      uint32_t o0, o1, o2, o3;  // element 16 q + 4 k + j
+      bits_total += ans_step(d3, state, o3, sm.next_states);
+      bits_total += ans_step(d2, state, o2, sm.next_states);
+      bits_total += ans_step(d1, state, o1, sm.next_states);
+      bits_total += ans_step(d0, state, o0, sm.next_states);
+      const uint32_t p01 = o0 | (o1 << 16), p23 = o2 | (o3 << 16);
+      // 4x4 transpose over the group: lane t ends up with element k = t of lanes 0..3
+      const uint32_t r2 = __shfl_xor_sync(gmask, (j & 2) ? p01 : p23, 2);
+      const uint32_t a = (j & 2) ? r2 : p01, b = (j & 2) ? p23 : r2;
+      const uint32_t r1 = __shfl_xor_sync(gmask, __byte_perm(a, b, sel_send), 1);
+      uint2 w;
+      w.x = __byte_perm(a, r1, sel_q01);
+      w.y = __byte_perm(b, r1, sel_q23);
+      *reinterpret_cast<uint2*>(row_out + 16 * q + 4 * j) = w;
+    }
+    cur = nxt;
+  }
+  return bits_total;
+}
+
+__global__ void __launch_bounds__(ANS_THREADS, 4) ans_encode_kernel(EncParams ep, uint32_t batches_per_chunk, const VarPlan* __restrict__ plans,
+                                                                     ChunkEnc* __restrict__ chunks, const uint8_t* __restrict__ sym0,
+                                                                     const uint8_t* __restrict__ sym1, uint16_t* __restrict__ ans0,
+                                                                     uint16_t* __restrict__ ans1, uint32_t* __restrict__ ans_sum,
+                                                                     BatchEntry* __restrict__ entries) {
+  __shared__ AnsSmem sm;
   const uint32_t c = blockIdx.x / MAX_VARS, v = blockIdx.x % MAX_VARS;
   if (v >= ep.n_vars) return;
   const int tid = threadIdx.x;
@@ -1026,8 +1075,9 @@ __global__ void __launch_bounds__(ANS_THREADS) ans_encode_kernel(EncParams ep, u
     if (tid < 4) chunks[c].final_state[v][tid] = 0;
     return;
   }
-  for (uint32_t i = tid; i < n_bins; i += ANS_THREADS) {
-    const uint64_t info = plan.syminfo[i];
+  for (uint32_t i = tid; i < ENC_MAXB; i += ANS_THREADS) {
+    // entries past n_bins alias symbol 0 (never looked up: every staged symbol is < n_bins)
+    const uint64_t info = plan.syminfo[i < n_bins ? i : 0];
     const uint32_t cutoff = uint32_t(info & 0xffff), mr = uint32_t(info >> 16) & 0xff, w = uint32_t(info >> 24) & 0xffff, cum = uint32_t(info >> 40) & 0xffff;
     sm.desc_tab[i] = cutoff | (mr << 12) | ((cum + 2048u - w) << 16);
   }
@@ -1040,49 +1090,80 @@ __global__ void __launch_bounds__(ANS_THREADS) ans_encode_kernel(EncParams ep, u
   }
   if (tid < 4) sm.carry[tid] = uint16_t(size);  // encoder.default_state()
   __syncthreads();
-  const uint8_t* symp = (v == 0 ? sym0 : sym1) + sb;
-  uint16_t* ansp = (v == 0 ? ans0 : ans1) + sb;
-  const int j = tid & 3, s = tid >> 2;  // chain j of the s-th batch below the round's top
-  const uint8_t* srow = sm.sym + s * ANS_SYM_STRIDE;
-  uint16_t* orow = sm.out + s * ANS_OUT_STRIDE;
-  for (uint32_t hi = nb; hi > 0;) {
-    const uint32_t nseg = min(uint32_t(ANS_SEGS), hi), lo = hi - nseg;
-    // stage the symbols of batches [lo, hi): row r holds batch hi-1-r (encode order)
-    const uint32_t tile_n = min(n, hi * BATCH_N) - lo * BATCH_N;
-    for (uint32_t k = tid; k < tile_n; k += ANS_THREADS)
-      sm.sym[(nseg - 1 - (k >> 8)) * ANS_SYM_STRIDE + (k & 255)] = symp[uint64_t(lo) * BATCH_N + k];
-    __syncthreads();
-    const bool active = uint32_t(s) < nseg;
-    const uint32_t bb = hi - 1 - uint32_t(s);
-    const uint32_t cnt = active ? min(uint32_t(BATCH_N), n - bb * BATCH_N) : 0u;
-    const int steps = cnt > uint32_t(j) ? int((cnt - 1 - j) / 4 + 1) : 0;  // chain j encodes i = j (mod 4), descending
-    uint32_t my_in = (s == 0) ? uint32_t(sm.carry[j]) : size;  // the round's first segment knows its input; the others guess
-    uint32_t state = my_in, bits_total = 0;
-    {
-      int m = steps - 1;
-      for (; m >= 3; m -= 4) {
-        const int i = 4 * m + j;
-        const uint32_t d0 = sm.desc_tab[srow[i]], d1 = sm.desc_tab[srow[i - 4]], d2 = sm.desc_tab[srow[i - 8]], d3 = sm.desc_tab[srow[i - 12]];
-        bits_total += ans_step(d0, state, &orow[i], sm.next_states);
-        bits_total += ans_step(d1, state, &orow[i - 4], sm.next_states);
-        bits_total += ans_step(d2, state, &orow[i - 8], sm.next_states);
-        bits_total += ans_step(d3, state, &orow[i - 12], sm.next_states);
+  const uint8_t* symp = (v == 0 ? sym0 : sym1) + ep.row_base[c];  // rows are 256-aligned (see split_delta_kernel)
+  uint16_t* ansp = (v == 0 ? ans0 : ans1) + ep.row_base[c];
+  const int j = tid & 3, s = tid >> 2;  // chain j of the s-th segment below the round's top
+  const uint32_t gmask = 0xfu << ((tid & 31) & ~3);
+  const uint32_t nb_full = n / BATCH_N;  // batches [0, nb_full) are full; batch nb_full (if any) is the short last one
+  const uint32_t seg_b = min(max((nb + ANS_SEGS - 1) / ANS_SEGS, 2u), ANS_MAX_SEG_BATCHES);  // batches per segment
+  const uint32_t n_segs = (nb + seg_b - 1) / seg_b;
+  // chain j over a short batch, element by element (only the page's last batch can be short)
+  auto short_batch = [&](uint32_t b, uint32_t& state) -> uint32_t {
+    const uint32_t cnt = n - b * BATCH_N;
+    const int steps = cnt > uint32_t(j) ? int((cnt - 1 - j) / 4 + 1) : 0;
+    const uint8_t* rs = symp + uint64_t(b) * BATCH_N;
+    uint16_t* ro = ansp + uint64_t(b) * BATCH_N;
+    uint32_t bits_total = 0;
+    for (int m = steps - 1; m >= 0; m--) {
+      uint32_t o;
+      bits_total += ans_step(sm.desc_tab[rs[4 * m + j]], state, o, sm.next_states);
+      ro[4 * m + j] = uint16_t(o);
+    }
+    return bits_total;
+  };
+  for (uint32_t done = 0; done < n_segs; done += ANS_SEGS) {
+    // this round: segments n_segs-1-done, n_segs-2-done, ... (encode order); thread group s takes the s-th of them
+    const bool active = done + uint32_t(s) < n_segs;
+    const uint32_t seg = active ? n_segs - 1 - done - uint32_t(s) : 0u;
+    const uint32_t b_lo = seg * seg_b, b_hi = min(b_lo + seg_b, nb);
+    uint32_t my_in = sm.carry[j];  // the round's first segment knows its input
+    if (active && s > 0) {
+      // guess: replay the tail of the preceding segment (full batches only) from an arbitrary state
+      uint32_t g = size;
+      const uint32_t w_hi = min(b_hi + ANS_WARM_BATCHES, nb_full);
+      for (uint32_t b = w_hi; b > b_hi; b--)
+        ans_full_batch<true>(sm, symp + uint64_t(b - 1) * BATCH_N, nullptr, j, gmask, g);
+      my_in = g;
+    }
+    uint32_t state = my_in;
+    if (active) {
+      for (uint32_t b = b_hi; b > b_lo; b--) {
+        const uint32_t bb = b - 1;
+        uint32_t bits = bb < nb_full ? ans_full_batch<false>(sm, symp + uint64_t(bb) * BATCH_N, ansp + uint64_t(bb) * BATCH_N, j, gmask, state)
+                                     : short_batch(bb, state);
+        bits += __shfl_xor_sync(gmask, bits, 1);
+        bits += __shfl_xor_sync(gmask, bits, 2);
+        // decoder state at the START of a batch == encoder state after encoding it (side index)
+        if (j == 0) { sums[bb] = bits; ent[bb].bit_pos = 0; }
+        ent[bb].st[j] = uint16_t(state - size);
       }
-      for (; m >= 0; m--) bits_total += ans_step(sm.desc_tab[srow[4 * m + j]], state, &orow[4 * m + j], sm.next_states);
+      sm.out_state[s][j] = uint16_t(state);
     }
     uint32_t my_out = state;
-    if (active) sm.out_state[s][j] = uint16_t(my_out);
     __syncthreads();
     while (true) {
       const uint32_t in_true = (s == 0 || !active) ? my_in : uint32_t(sm.out_state[s - 1][j]);
       bool changed = false;
       if (in_true != my_in) {
+        // re-run from the true input next to the old trajectory until they meet (rare: element-wise path)
         uint32_t a = in_true, g = my_in;
-        for (int m = steps - 1; m >= 0 && a != g; m--) {
-          const int i = 4 * m + j;
-          const uint32_t d = sm.desc_tab[srow[i]];
-          bits_total += ans_step(d, a, &orow[i], sm.next_states);
-          bits_total -= ans_step_quiet(d, g, sm.next_states);
+        for (uint32_t b = b_hi; b > b_lo && a != g; b--) {
+          const uint32_t bb = b - 1;
+          const uint32_t cnt = min(uint32_t(BATCH_N), n - bb * BATCH_N);
+          const int steps = cnt > uint32_t(j) ? int((cnt - 1 - j) / 4 + 1) : 0;
+          const uint8_t* rs = symp + uint64_t(bb) * BATCH_N;
+          uint16_t* ro = ansp + uint64_t(bb) * BATCH_N;
+          int delta = 0;
+          int m = steps - 1;
+          for (; m >= 0 && a != g; m--) {
+            const uint32_t d = sm.desc_tab[rs[4 * m + j]];
+            uint32_t o;
+            delta += int(ans_step(d, a, o, sm.next_states));
+            delta -= int(ans_step_quiet(d, g, sm.next_states));
+            ro[4 * m + j] = uint16_t(o);
+          }
+          if (delta != 0) atomicAdd(&sums[bb], uint32_t(delta));
+          if (m < 0 && a != g) ent[bb].st[j] = uint16_t(a - size);  // the batch ended on the corrected trajectory
         }
         my_in = in_true;
         if (a != g) { changed = true; my_out = a; }  // ran off the segment without meeting the old trajectory
@@ -1091,18 +1172,8 @@ __global__ void __launch_bounds__(ANS_THREADS) ans_encode_kernel(EncParams ep, u
       if (changed) sm.out_state[s][j] = uint16_t(my_out);
       if (!__syncthreads_or(changed ? 1 : 0)) break;
     }
-    // decoder state at the START of a batch == encoder state after encoding it (side index)
-    bits_total += __shfl_xor_sync(0xffffffffu, bits_total, 1);
-    bits_total += __shfl_xor_sync(0xffffffffu, bits_total, 2);
-    if (active) {
-      if (j == 0) { sums[bb] = bits_total; ent[bb].bit_pos = 0; }
-      ent[bb].st[j] = uint16_t(my_out - size);
-      if (uint32_t(s) == nseg - 1) sm.carry[j] = uint16_t(my_out);
-    }
-    for (uint32_t k = tid; k < tile_n; k += ANS_THREADS)
-      ansp[uint64_t(lo) * BATCH_N + k] = sm.out[(nseg - 1 - (k >> 8)) * ANS_OUT_STRIDE + (k & 255)];
+    if (active && done + uint32_t(s) + 1 == min(n_segs, done + ANS_SEGS)) sm.carry[j] = uint16_t(my_out);  // the round's last segment
     __syncthreads();
-    hi = lo;
   }
   if (tid < 4) chunks[c].final_state[v][tid] = uint32_t(sm.carry[tid]) - size;
 }
@@ -1231,6 +1302,33 @@ __device__ __forceinline__ void win_or(uint32_t* win, uint32_t pos, uint64_t val
   }
 }
 
+// 8 consecutive latents of an aligned batch row as one vector access
+template <typename L>
+struct alignas(sizeof(L) * 8 > 16 ? 16 : sizeof(L) * 8) Vec8 { L v[8]; };
+
+// Appends fields (<= 32 bits each, already masked to their width) at increasing bit positions of the shared window and
+// ORs finished 32-bit words in; neighbouring lanes share at most the first and last word of a span.
+struct BitAcc {
+  uint32_t* win;
+  uint64_t acc;
+  uint32_t fill, w;
+  __device__ __forceinline__ BitAcc(uint32_t* win_, uint32_t pos) : win(win_), acc(0), fill(pos & 31), w(pos >> 5) {}
+  __device__ __forceinline__ void put(uint32_t val, uint32_t nbits) {
+    acc |= uint64_t(val) << fill;
+    fill += nbits;
+    if (fill >= 32) {
+      const uint32_t lo = uint32_t(acc);
+      if (lo) atomicOr(&win[w], lo);
+      w++;
+      acc >>= 32;
+      fill -= 32;
+    }
+  }
+  __device__ __forceinline__ void flush() {
+    if (fill > 0 && uint32_t(acc)) atomicOr(&win[w], uint32_t(acc));
+  }
+};
+
 template <typename L>
 __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(EncParams ep, uint32_t batches_per_chunk, const L* __restrict__ lat0, const L* __restrict__ lat1,
                                                              const VarPlan* __restrict__ plans, const ChunkEnc* __restrict__ chunks,
@@ -1350,54 +1448,77 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(EncParams ep, uint32
       if (cnt == 0) continue;
       const bool needs_ans = !fb && p.n_bins != 1;
       const uint32_t max_ob = fb ? lbits : p.max_ob;
-      const uint8_t* symp = (v == 0 ? sym0 : sym1) + sb + uint64_t(b) * BATCH_N;
-      const uint16_t* ansp = (v == 0 ? ans0 : ans1) + sb + uint64_t(b) * BATCH_N;
-      const L* latp = (v == 0 ? lat0 : lat1) + sb + uint64_t(b) * BATCH_N;
+      const uint64_t rb = ep.row_base[c];
+      const uint8_t* symp = (v == 0 ? sym0 : sym1) + rb + uint64_t(b) * BATCH_N;
+      const uint16_t* ansp = (v == 0 ? ans0 : ans1) + rb + uint64_t(b) * BATCH_N;
+      const L* latp = (v == 0 ? lat0 : lat1) + rb + uint64_t(b) * BATCH_N;
       uint32_t pos = uint32_t(entry_pos(b, v) - win_bit0);
-      // --- ANS fields (chunk_latent_compressor.rs:285-297)
-      uint32_t a_val[8], a_bits[8], a_tot = 0;
+      // lane owns elements 8 lane .. 8 lane + 7: its fields are contiguous in the stream, so it assembles them in a
+      // register and ORs whole 32-bit words into the window.  Rows are 256-aligned (split_delta_kernel): vector loads.
+      const uint32_t first = lane * 8;
+      const uint2 s8 = *reinterpret_cast<const uint2*>(symp + first);
       uint32_t sy[8];
 #pragma unroll
-      for (int e = 0; e < 8; e++) {
-        uint32_t i = lane * 8 + e;
-        a_val[e] = 0; a_bits[e] = 0; sy[e] = 0;
-        if (i < cnt) {
-          sy[e] = symp[i];
-          if (needs_ans && p.size_log > 0) {
-            uint32_t x = ansp[i];
-            uint32_t nbits = 31 - __clz(x);
-            a_bits[e] = nbits;
-            a_val[e] = x ^ (1u << nbits);
-          }
+      for (int e = 0; e < 8; e++) sy[e] = ((e < 4 ? s8.x : s8.y) >> (8 * (e & 3))) & 0xffu;
+      // --- ANS fields (chunk_latent_compressor.rs:285-297)
+      uint32_t a_val[8], a_bits[8], a_tot = 0;
+      if (needs_ans && p.size_log > 0) {
+        const uint4 a8 = *reinterpret_cast<const uint4*>(ansp + first);
+        const uint32_t aw[4] = {a8.x, a8.y, a8.z, a8.w};
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+          const uint32_t x = (aw[e >> 1] >> (16 * (e & 1))) & 0xffffu;
+          const bool live = first + e < cnt;
+          const uint32_t nbits = live ? 31 - __clz(x | 1u) : 0u;
+          a_bits[e] = nbits;
+          a_val[e] = live ? x ^ (1u << nbits) : 0u;
+          a_tot += nbits;
         }
-        a_tot += a_bits[e];
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; e++) { a_val[e] = 0; a_bits[e] = 0; }
       }
       uint32_t inc = a_tot;
       for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
-      uint32_t apos = pos + inc - a_tot;
       const uint32_t ans_total = __shfl_sync(0xffffffffu, inc, 31);
+      {
+        BitAcc acc(sm.win, pos + inc - a_tot);
 #pragma unroll
-      for (int e = 0; e < 8; e++) { win_or(sm.win, apos, a_val[e], a_bits[e]); apos += a_bits[e]; }
+        for (int e = 0; e < 8; e++) acc.put(a_val[e], a_bits[e]);
+        acc.flush();
+      }
       // --- offsets (chunk_latent_compressor.rs:299-327)
       if (max_ob > 0) {
         uint32_t o_bits[8], o_tot = 0;
-        uint64_t o_val[8];
+        L o_val[8];
+        if (fb) {
+#pragma unroll
+          for (int e = 0; e < 8; e++) o_val[e] = first + e < cnt ? fallback_latent<L>(ep, sb + uint64_t(b) * BATCH_N + first + e) : L(0);
+        } else {
+          const Vec8<L> l8 = *reinterpret_cast<const Vec8<L>*>(latp + first);
+#pragma unroll
+          for (int e = 0; e < 8; e++) o_val[e] = l8.v[e];
+        }
 #pragma unroll
         for (int e = 0; e < 8; e++) {
-          uint32_t i = lane * 8 + e;
-          o_bits[e] = 0; o_val[e] = 0;
-          if (i < cnt) {
-            uint64_t l = fb ? uint64_t(fallback_latent<L>(ep, sb + uint64_t(b) * BATCH_N + i)) : uint64_t(latp[i]);
-            o_bits[e] = sm.obs[v][sy[e]];
-            o_val[e] = l - sm.lowers[v][sy[e]];
-          }
+          const bool live = first + e < cnt;
+          o_bits[e] = live ? uint32_t(sm.obs[v][sy[e]]) : 0u;
+          o_val[e] = live ? L(o_val[e] - L(sm.lowers[v][sy[e]])) : L(0);
           o_tot += o_bits[e];
         }
         uint32_t oinc = o_tot;
         for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, oinc, d); if (lane >= d) oinc += o; }
-        uint32_t opos = pos + ans_total + oinc - o_tot;
+        BitAcc acc(sm.win, pos + ans_total + oinc - o_tot);
 #pragma unroll
-        for (int e = 0; e < 8; e++) { win_or(sm.win, opos, o_val[e], o_bits[e]); opos += o_bits[e]; }
+        for (int e = 0; e < 8; e++) {
+          if constexpr (sizeof(L) == 8) {
+            if (o_bits[e] > 32) { acc.put(uint32_t(o_val[e]), 32); acc.put(uint32_t(uint64_t(o_val[e]) >> 32), o_bits[e] - 32); }
+            else acc.put(uint32_t(o_val[e]), o_bits[e]);
+          } else {
+            acc.put(uint32_t(o_val[e]), o_bits[e]);
+          }
+        }
+        acc.flush();
       }
     }
     __syncthreads();
