@@ -1329,6 +1329,23 @@ struct BitAcc {
   }
 };
 
+// 8 consecutive fields of <= 12 bits each (already masked) at bit `pos` of the window: a 3-level concatenation tree in
+// registers (<= 96 bits), one shift to the word phase, then at most four 32-bit ORs into shared memory.
+__device__ __forceinline__ void emit8_narrow(uint32_t* win, uint32_t pos, const uint32_t (&v)[8], const uint32_t (&nb)[8]) {
+  const uint32_t p0 = v[0] | (v[1] << nb[0]), p1 = v[2] | (v[3] << nb[2]), p2 = v[4] | (v[5] << nb[4]), p3 = v[6] | (v[7] << nb[6]);
+  const uint32_t l0 = nb[0] + nb[1], l1 = nb[2] + nb[3], l2 = nb[4] + nb[5];  // each <= 24
+  const uint64_t q0 = uint64_t(p0) | (uint64_t(p1) << l0), q1 = uint64_t(p2) | (uint64_t(p3) << l2);  // each <= 48 bits
+  const uint32_t m0 = l0 + l1;                                                                         // <= 48
+  const uint64_t lo = q0 | (q1 << m0), hi = (q1 >> 1) >> (63 - m0);
+  const uint32_t r = pos & 31, w = pos >> 5;
+  const uint32_t x0 = uint32_t(lo), x1 = uint32_t(lo >> 32), x2 = uint32_t(hi), x3 = uint32_t(hi >> 32);
+  const uint32_t w0 = x0 << r, w1 = __funnelshift_l(x0, x1, r), w2 = __funnelshift_l(x1, x2, r), w3 = __funnelshift_l(x2, x3, r);
+  if (w0) atomicOr(&win[w], w0);
+  if (w1) atomicOr(&win[w + 1], w1);
+  if (w2) atomicOr(&win[w + 2], w2);
+  if (w3) atomicOr(&win[w + 3], w3);
+}
+
 template <typename L>
 __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(EncParams ep, uint32_t batches_per_chunk, const L* __restrict__ lat0, const L* __restrict__ lat1,
                                                              const VarPlan* __restrict__ plans, const ChunkEnc* __restrict__ chunks,
@@ -1481,12 +1498,7 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(EncParams ep, uint32
       uint32_t inc = a_tot;
       for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
       const uint32_t ans_total = __shfl_sync(0xffffffffu, inc, 31);
-      {
-        BitAcc acc(sm.win, pos + inc - a_tot);
-#pragma unroll
-        for (int e = 0; e < 8; e++) acc.put(a_val[e], a_bits[e]);
-        acc.flush();
-      }
+      if (a_tot) emit8_narrow(sm.win, pos + inc - a_tot, a_val, a_bits);  // a field is <= size_log <= 10 bits
       // --- offsets (chunk_latent_compressor.rs:299-327)
       if (max_ob > 0) {
         uint32_t o_bits[8], o_tot = 0;
@@ -1508,6 +1520,13 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(EncParams ep, uint32
         }
         uint32_t oinc = o_tot;
         for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, oinc, d); if (lane >= d) oinc += o; }
+        if (max_ob <= 12) {
+          uint32_t o32[8];
+#pragma unroll
+          for (int e = 0; e < 8; e++) o32[e] = uint32_t(o_val[e]);
+          if (o_tot) emit8_narrow(sm.win, pos + ans_total + oinc - o_tot, o32, o_bits);
+          continue;
+        }
         BitAcc acc(sm.win, pos + ans_total + oinc - o_tot);
 #pragma unroll
         for (int e = 0; e < 8; e++) {

@@ -1,4 +1,4 @@
-"""Experiment tool: per-phase clock64 sums inside plan_kernel (build variant -DPCOB_ENC_TIMING).
+"""Experiment tool: per-phase clock64 sums inside plan_probe_kernel / plan_solve_kernel (build variant -DPCOB_ENC_TIMING).
 Run on the GPU box with PCOB200_LIB=pcodec_b200/libcpcodec_enctiming.so."""
 import ctypes as C, os, sys
 sys.path.insert(0, os.getcwd())
@@ -19,7 +19,7 @@ buf = (C.c_ulonglong * 32)()
 L.pco_b200_debug_enc_timing(buf)
 comp()
 L.pco_b200_debug_enc_timing(buf)
-names = ['plan: zero+count', 'plan: scan', 'plan: probes', 'plan: histogram state machine', 'plan: DP', 'plan: rewind+quantize', 'plan: tables']
+names = ['probe: zero+count', 'probe: scan', 'probe: probes', 'solve: stage + histogram state machine', 'solve: DP', 'solve: rewind+quantize', 'solve: tables']
 tot = sum(buf[:7])
 for i, nm in enumerate(names):
     print(f"{nm:32s} {buf[i] / n_chunks / 1e3:10.1f} kcycles/CTA  {100 * buf[i] / tot:5.1f}%")
