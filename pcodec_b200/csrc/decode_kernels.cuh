@@ -69,24 +69,31 @@ struct BuildScratch {        // only live while the tables are built; shares sto
 
 struct DecodeSmem {
   ChunkHdr hdr;
-  uint32_t node[MAX_VARS][1 << SMALL_MAX_SIZE_LOG];
   alignas(16) BinEntry bin[MAX_VARS][SMALL_MAX_BINS];
   uint32_t bin32[MAX_VARS][SMALL_MAX_BINS];  // compact: (lower - bin_base) | offset_bits << 25, valid when bin_compact[v]
   uint64_t bin_base[MAX_VARS];
   uint32_t bin_compact[MAX_VARS];
-  uint32_t off_start[DEC_THREADS];        // per (var, batch-in-tile): bit position of the offsets section
   // delta carry chain: mvec[b % CHAIN_RING] = true moments at the start of batch b once m_flag[...] == b + 1
   uint64_t mvec[CHAIN_RING][MAX_ORDER];
   volatile uint32_t m_flag[CHAIN_RING];
   uint64_t binom_full[MAX_ORDER];          // C(256, t): keeps the chain link free of global loads
   uint64_t binom_lane8[32][MAX_ORDER];     // C(8 * lane, t)
   uint32_t err;
-  alignas(16) uint32_t win[DEC_WARPS][MAX_VARS][WIN_WORDS + 4];  // per-warp staged copy of a batch's offset bits
   union {
-    uint32_t sym[DEC_TILE_ROWS * SYM_ROW_WORDS];
-    BuildScratch build;
+    alignas(16) uint32_t win[DEC_WARPS][MAX_VARS][WIN_WORDS + 4];  // per-warp staged copy of a batch's offset bits
+    BuildScratch build;                                             // only live while the bins are loaded
   };
 };
+
+// ---------------------------------------------------------------------------
+// Scratch produced by symwalk_kernel and consumed by decode_kernel (HBM, sized from the destination):
+//   symbols : one byte per stored latent, rows of 256; chunk task t owns rows from sym_row0(t) on, row (v, b) = v * nb_out + b
+//   offsets : per (v, b) the chunk-relative bit position of the batch's offsets section (= end of its tANS section)
+// nb_out = batches the destination can take from the chunk, so both arrays are bounded by the destination length
+// whatever an (untrusted) index claims.
+// ---------------------------------------------------------------------------
+__host__ __device__ inline uint64_t scratch_row0(uint64_t out_offset, uint32_t task_idx) { return uint64_t(MAX_VARS) * (out_offset / BATCH_N + task_idx); }
+__host__ __device__ inline uint64_t scratch_rows_total(uint64_t out_len, uint32_t n_tasks) { return uint64_t(MAX_VARS) * (out_len / BATCH_N + n_tasks + 1); }
 
 // ---------------------------------------------------------------------------
 // Cooperative table build for one latent var (all threads of the CTA call this).
@@ -95,7 +102,7 @@ struct DecodeSmem {
 template <bool WALKER>
 __device__ void build_var_tables(const BitSrc& src, ChunkHdr& hdr, int v, uint32_t* node, uint64_t* bin_lower, uint8_t* bin_ob,
                                  uint16_t* bin_weight, uint32_t* bin_cum, uint16_t* sym_of_state, uint32_t* rank_counter, uint32_t* err,
-                                 bool add_mid_to_lower) {
+                                 bool add_mid_to_lower, bool build_nodes = true) {
   const VarHdr vh = hdr.var[v];
   const uint32_t n_bins = vh.n_bins;
   const uint32_t size_log = vh.ans_size_log;
@@ -136,7 +143,7 @@ __device__ void build_var_tables(const BitSrc& src, ChunkHdr& hdr, int v, uint32
     if (c != size) atomicMax(err, (uint32_t)ST_CORRUPTION);  // ans/spec.rs:38-44
   }
   __syncthreads();
-  if (*err) return;
+  if (*err || !build_nodes) return;
   // 3. spread (ans/spec.rs:24-59): step t -> state (stride * t) & (size - 1)
   uint32_t stride = (3 * size) / 5;
   if ((stride & 1) == 0) stride += 1;
@@ -665,12 +672,178 @@ __device__ __forceinline__ void load8(const L* __restrict__ src, L (&r)[8]) {
 }
 
 // ---------------------------------------------------------------------------
-// decode_kernel: one CTA per chunk.
+// symwalk_kernel (K7a): the serial part of decoding a batch - its 256-symbol tANS walk - for every batch of a chunk.
+// One CTA of 4 warps per chunk; a warp takes 32 consecutive batches of one var at a time:
+//   1. copies the bytes they span (one contiguous run of the stream) into its shared-memory stage with 16-byte
+//      cp.async, fully coalesced - the per-thread scattered global reads of a thread-per-batch walk were what stalled it;
+//   2. each lane walks one batch out of shared memory (page_latent_decompressor.rs:89-177): per 4 symbols one
+//      64-bit window, 4 node lookups, 4 extractions; the bin indices go to a padded shared tile;
+//   3. the tile leaves as 256-byte rows (coalesced), and each batch's end position = start of its offsets section.
+// Latency-bound by construction (a 256-step dependent chain per lane) but cheap to issue: two warps per scheduler
+// keep it near the issue limit, so it does not need occupancy.
+// ---------------------------------------------------------------------------
+constexpr int SW_THREADS = 128;
+constexpr int SW_WARPS = SW_THREADS / 32;
+constexpr int SW_STAGE_BYTES = 16384;
+constexpr int SW_STAGE_WORDS = SW_STAGE_BYTES / 4;
+
+struct SymWalkSmem {
+  ChunkHdr hdr;
+  uint32_t node[MAX_VARS][1 << SMALL_MAX_SIZE_LOG];
+  uint32_t err;
+  union {
+    BuildScratch build;
+    struct {
+      alignas(16) uint32_t stage[SW_WARPS][SW_STAGE_WORDS + 16];
+      uint32_t tile[SW_WARPS][32 * SYM_ROW_WORDS];
+    } w;
+  };
+};
+
+__global__ void __launch_bounds__(SW_THREADS) symwalk_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, const uint8_t* __restrict__ index_base,
+                                                              uint64_t out_len, uint8_t* __restrict__ d_syms, uint32_t* __restrict__ d_offs) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SymWalkSmem& sm = *reinterpret_cast<SymWalkSmem*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const IndexChunk task = chunks[blockIdx.x];
+  const BitSrc src = make_bitsrc(fp.src, fp.src_len);
+  const uint64_t max_word = src.n_bits == 0 ? 0 : (src.n_bits - 1) >> 6;
+  const uint64_t max_blk = max_word >> 1;
+  const uint64_t chunk_bit0 = src.mis_bits + task.chunk_offset * 8;
+  // every refusal below is reported by decode_kernel, which parses the same header
+  if (tid == 0) {
+    sm.err = 0;
+    parse_chunk_header(src, chunk_bit0, fp.dtype, fp.uniform_type, fp.format_major, true, sm.hdr);
+    if (sm.hdr.status == ST_OK) {
+      for (uint32_t v = 0; v < sm.hdr.n_vars; v++) {
+        const VarHdr& vh = sm.hdr.var[v];
+        if (vh.ans_size_log > SMALL_MAX_SIZE_LOG || vh.n_bins > SMALL_MAX_BINS) sm.hdr.status = ST_UNSUPPORTED;
+        if (vh.n_bins == 0 && var_stored_n(sm.hdr.n, vh.delta_order) > 0) sm.hdr.status = ST_CORRUPTION;
+      }
+      if (task.n != 0 && task.n != sm.hdr.n) sm.hdr.status = ST_CORRUPTION;
+    }
+  }
+  __syncthreads();
+  if (sm.hdr.status != ST_OK) return;
+  const uint32_t n_vars = sm.hdr.n_vars;
+  const bool need_index = (sm.hdr.var[0].n_bins > 1) || (n_vars > 1 && sm.hdr.var[1].n_bins > 1);
+  if (!need_index || task.entries_offset == 0 || !index_base) return;  // trivial vars: section starts are closed-form
+  for (uint32_t v = 0; v < n_vars; v++)
+    build_var_tables<false>(src, sm.hdr, v, sm.node[v], sm.build.bin_lower[v], sm.build.bin_ob[v], sm.build.bin_weight[v], sm.build.bin_cum[v],
+                            sm.build.sym_of_state[v], sm.build.rank_counter[v], &sm.err, false);
+  __syncthreads();  // the build scratch (aliased by stage and tile) is dead
+  if (sm.err) return;
+  const uint32_t n = sm.hdr.n;
+  const uint32_t n_out = task.out_offset >= out_len ? 0u : uint32_t(min(uint64_t(n), out_len - task.out_offset));
+  const uint32_t nb_total = n_batches_of(n), nb_out = n_batches_of(n_out);
+  const BatchEntry* entries = reinterpret_cast<const BatchEntry*>(index_base + task.entries_offset);
+  const uint64_t row0 = scratch_row0(task.out_offset, blockIdx.x);
+  const uint32_t groups = (nb_out + 31) / 32;
+  uint32_t* stg = sm.w.stage[warp];
+  uint32_t* tile = sm.w.tile[warp];
+  const uint32_t stg_sa = uint32_t(__cvta_generic_to_shared(stg));
+  for (uint32_t item = warp; item < n_vars * groups; item += SW_WARPS) {
+    const uint32_t v = item / groups, b0 = (item % groups) * 32;
+    const VarHdr& vh = sm.hdr.var[v];
+    const uint32_t stored = var_stored_n(n, vh.delta_order);
+    const uint32_t nbg = min(32u, nb_out - b0);  // batches of this group
+    uint32_t* offs = d_offs + row0 + size_t(v) * nb_out;
+    // lane k: entry of batch b0 + k
+    BatchEntry e;
+    e.bit_pos = 0; e.st[0] = e.st[1] = e.st[2] = e.st[3] = 0;
+    if (uint32_t(lane) < nbg) e = entries[size_t(v) * nb_total + b0 + lane];
+    if (vh.n_bins <= 1) {  // no tANS bits: the offsets section starts where the batch starts
+      if (uint32_t(lane) < nbg) offs[b0 + lane] = e.bit_pos;
+      continue;
+    }
+    const uint32_t ans_max_bits = BATCH_N * vh.ans_size_log;  // a symbol reads <= size_log bits
+    uint32_t k0 = 0;  // batches [k0, k1) of the group are staged per pass
+    while (k0 < nbg) {
+      const uint64_t base_bit = (chunk_bit0 + __shfl_sync(0xffffffffu, e.bit_pos, int(k0))) & ~uint64_t(127);  // 16-byte block
+      const uint64_t my_bit = chunk_bit0 + e.bit_pos;
+      // lane k fits if its whole tANS section lies inside the stage; positions ascend, so the fits form a prefix.
+      // The first batch of a pass always fits (a section is <= 320 bytes + 16 of alignment).
+      const bool fits = uint32_t(lane) >= k0 && uint32_t(lane) < nbg && my_bit >= base_bit &&
+                        my_bit + ans_max_bits + 64 <= base_bit + uint64_t(SW_STAGE_BYTES) * 8;
+      const uint32_t fm = __ballot_sync(0xffffffffu, fits) >> k0;
+      const uint32_t npass = max(1u, uint32_t(__ffs(~fm) - 1));  // leading run of fitting lanes (>= 1 for a sane index)
+      const uint32_t k1 = min(nbg, k0 + npass);
+      // bytes to stage: up to the start of the next batch after the pass (known from the index), else the whole stage
+      uint64_t end_bit = base_bit + uint64_t(SW_STAGE_BYTES) * 8;
+      if (k1 < nbg) end_bit = min(end_bit, chunk_bit0 + __shfl_sync(0xffffffffu, e.bit_pos, int(k1)) + 64);
+      else end_bit = min(end_bit, chunk_bit0 + __shfl_sync(0xffffffffu, e.bit_pos, int(k1 - 1)) + ans_max_bits + 64);
+      const uint32_t n_blk = end_bit > base_bit ? min(uint32_t(SW_STAGE_BYTES / 16), uint32_t((end_bit - base_bit + 127) >> 7)) : 1u;
+      const uint64_t blk0 = base_bit >> 7;
+      for (uint32_t q = lane; q < n_blk; q += 32) {
+        const uint64_t bi = min(blk0 + q, max_blk);
+        const void* gp = reinterpret_cast<const ulonglong2*>(src.words) + bi;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stg_sa + q * 16), "l"(gp));
+      }
+      asm volatile("cp.async.commit_group;");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
+      const bool mine = uint32_t(lane) >= k0 && uint32_t(lane) < k1;
+      if (mine) {
+        const uint32_t b = b0 + lane;
+        const int cnt = int(batch_count(stored, b));
+        // clamp what an untrusted index could push outside the stage: garbage in, garbage out, but in bounds
+        uint32_t wpos = uint32_t(min(my_bit >= base_bit ? my_bit - base_bit : 0, uint64_t(SW_STAGE_BYTES) * 8 - ans_max_bits - 64));
+        const uint32_t smask = (1u << vh.ans_size_log) - 1;
+        uint32_t s0 = min(uint32_t(e.st[0]), smask), s1 = min(uint32_t(e.st[1]), smask), s2 = min(uint32_t(e.st[2]), smask), s3 = min(uint32_t(e.st[3]), smask);
+        const uint32_t* node = sm.node[v];
+        uint32_t* row = tile + lane * SYM_ROW_WORDS;
+        int i = 0;
+        for (; i + 4 <= cnt; i += 4) {
+          const uint32_t n0 = node[s0], n1 = node[s1], n2 = node[s2], n3 = node[s3];
+          const uint32_t w = wpos >> 5, r = wpos & 31;
+          const uint32_t x0 = stg[w], x1 = stg[w + 1], x2 = stg[w + 2];
+          const uint64_t g = (uint64_t(__funnelshift_r(x1, x2, r)) << 32) | __funnelshift_r(x0, x1, r);
+          const uint32_t c0 = node_btr(n0), c1 = node_btr(n1), c2 = node_btr(n2), c3 = node_btr(n3);
+          const uint32_t sh2 = c0 + c1, sh3 = sh2 + c2;
+          s0 = node_base(n0) + (uint32_t(g) & ((1u << c0) - 1));
+          s1 = node_base(n1) + (uint32_t(g >> c0) & ((1u << c1) - 1));
+          s2 = node_base(n2) + (uint32_t(g >> sh2) & ((1u << c2) - 1));
+          s3 = node_base(n3) + (uint32_t(g >> sh3) & ((1u << c3) - 1));
+          row[i >> 2] = node_field(n0) | (node_field(n1) << 8) | (node_field(n2) << 16) | (node_field(n3) << 24);
+          wpos += sh3 + c3;
+        }
+        if (i < cnt) {  // ragged tail of the page's last batch (page_latent_decompressor.rs:144-177)
+          uint32_t packed = 0;
+          uint32_t sarr[4] = {s0, s1, s2, s3};
+          for (int j = 0; i + j < cnt; j++) {
+            const uint32_t nn = node[sarr[j]];
+            const uint32_t w = wpos >> 5, r = wpos & 31;
+            const uint32_t val = __funnelshift_r(stg[w], stg[w + 1], r) & ((1u << node_btr(nn)) - 1);
+            packed |= node_field(nn) << (8 * j);
+            sarr[j] = node_base(nn) + val;
+            wpos += node_btr(nn);
+          }
+          row[i >> 2] = packed;
+        }
+        offs[b] = uint32_t(min(base_bit + wpos, src.n_bits) - chunk_bit0);
+      }
+      __syncwarp();
+      // rows k0..k1 of the tile -> 256-byte symbol rows (16 lanes x 16 bytes each)
+      uint8_t* sym_rows = d_syms + (row0 + size_t(v) * nb_out + b0) * BATCH_N;
+      for (uint32_t idx = k0 * 16 + lane; idx < k1 * 16; idx += 32) {
+        const uint32_t rr = idx >> 4, seg = idx & 15;
+        const uint32_t* tp = tile + rr * SYM_ROW_WORDS + seg * 4;
+        *reinterpret_cast<uint4*>(sym_rows + size_t(rr) * BATCH_N + seg * 16) = make_uint4(tp[0], tp[1], tp[2], tp[3]);
+      }
+      __syncwarp();
+      k0 = k1;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// decode_kernel: one CTA per chunk, one warp per batch; symbols and section starts come from symwalk_kernel.
 // ---------------------------------------------------------------------------
 template <typename L>
 __global__ void __launch_bounds__(DEC_THREADS, PCOB_DEC_MIN_BLOCKS)
 decode_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, uint32_t* __restrict__ statuses, const uint8_t* __restrict__ index_base,
-              L* __restrict__ out, uint64_t out_len, const Binoms* __restrict__ binoms) {
+              L* __restrict__ out, uint64_t out_len, const Binoms* __restrict__ binoms, const uint8_t* __restrict__ d_syms,
+              const uint32_t* __restrict__ d_offs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   DecodeSmem& sm = *reinterpret_cast<DecodeSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -708,8 +881,9 @@ decode_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, uint32_t* __
   }
   const uint32_t n_vars = sm.hdr.n_vars;
   for (uint32_t v = 0; v < n_vars; v++)
-    build_var_tables<false>(src, sm.hdr, v, sm.node[v], sm.build.bin_lower[v], sm.build.bin_ob[v], sm.build.bin_weight[v], sm.build.bin_cum[v],
-                            sm.build.sym_of_state[v], sm.build.rank_counter[v], &sm.err, /*add_mid_to_lower=*/sm.hdr.var[v].delta_order > 0);
+    build_var_tables<false>(src, sm.hdr, v, nullptr, sm.build.bin_lower[v], sm.build.bin_ob[v], sm.build.bin_weight[v], sm.build.bin_cum[v],
+                            sm.build.sym_of_state[v], sm.build.rank_counter[v], &sm.err, /*add_mid_to_lower=*/sm.hdr.var[v].delta_order > 0,
+                            /*build_nodes=*/false);
   __syncthreads();
   if (sm.err) {
     if (tid == 0) statuses[blockIdx.x] = sm.err;
@@ -750,7 +924,6 @@ decode_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, uint32_t* __
   const uint32_t nb_total = n_batches_of(n);
   const uint32_t nb_out = n_batches_of(n_out);
   const uint32_t order = sm.hdr.var[0].delta_order;
-  const uint32_t tile_b = DEC_TILE_ROWS / n_vars;  // batches per tile
   const bool need_index = (sm.hdr.var[0].n_bins > 1) || (n_vars > 1 && sm.hdr.var[1].n_bins > 1);
   const BatchEntry* entries = (task.entries_offset != 0 && index_base)
                                   ? reinterpret_cast<const BatchEntry*>(index_base + task.entries_offset) : nullptr;
@@ -775,245 +948,247 @@ decode_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, uint32_t* __
   const int kind = is_float ? 2 : (is_signed ? 1 : 0);
   const uint32_t mode = sm.hdr.mode;
   uint32_t end_err = 0;
-  for (uint32_t tile_start = 0; tile_start < nb_out; tile_start += tile_b) {
-    const uint32_t tile_n = min(tile_b, nb_out - tile_start);
-    // ---------------- phase A: one thread per (var, batch): tANS symbols -> shared memory ----------------
-    {
-      const uint32_t v = tid / tile_b, bl = tid % tile_b;
-      if (v < n_vars && bl < tile_n) {
-        const uint32_t b = tile_start + bl;
+  const uint64_t row0 = scratch_row0(task.out_offset, blockIdx.x);
+  // chunk-relative bit position of batch b's offsets section for var v
+  auto off_of = [&](uint32_t v, uint32_t b) -> uint32_t {
+    if (need_index) return d_offs[row0 + size_t(v) * nb_out + b];
+    // all vars trivial: batches before b contribute count0*ob0 + count1*ob1 bits
+    const uint64_t c0 = min(uint64_t(b) * BATCH_N, uint64_t(stored0));
+    const uint64_t c1 = min(uint64_t(b) * BATCH_N, uint64_t(stored1));
+    uint64_t before = c0 * ob0 + c1 * ob1;
+    if (v == 1) before += uint64_t(batch_count(stored0, b)) * ob0;
+    return uint32_t(min(sm.hdr.body_bit + before, src.n_bits) - chunk_bit0);
+  };
+  // ---------------- one warp per batch ----------------
+  // A batch's offset bits are one contiguous run of the stream.  Each warp copies a 512-byte window of it with two
+  // coalesced 8-byte loads per lane -- issued one batch ahead so the DRAM/L2 latency hides behind the previous
+  // batch -- parks it in shared memory and extracts the variable-width fields from there.  The section starts and the
+  // symbols (8 per lane) were produced by symwalk_kernel.
+  {
+    uint64_t pf[MAX_VARS][2];
+    uint32_t off_cur[MAX_VARS] = {0, 0}, off_nxt[MAX_VARS] = {0, 0};
+    uint2 sy_nxt[MAX_VARS];
+    auto issue_window_loads = [&](const uint32_t (&off)[MAX_VARS]) {
+#pragma unroll
+      for (uint32_t v = 0; v < MAX_VARS; v++) {
+        if (v < n_vars && sm.hdr.var[v].max_offset_bits > 0) {
+          const uint64_t wb = (chunk_bit0 + off[v]) >> 6;
+          const uint64_t i0 = wb + lane, i1 = wb + 32 + lane;
+          pf[v][0] = __ldg(src.words + (i0 <= max_word ? i0 : max_word));
+          pf[v][1] = __ldg(src.words + (i1 <= max_word ? i1 : max_word));
+        }
+      }
+    };
+    auto load_syms = [&](uint32_t b) {
+#pragma unroll
+      for (uint32_t v = 0; v < MAX_VARS; v++) {
+        sy_nxt[v] = make_uint2(0u, 0u);
+        if (v < n_vars && sm.hdr.var[v].n_bins > 1)
+          sy_nxt[v] = __ldg(reinterpret_cast<const uint2*>(d_syms + (row0 + size_t(v) * nb_out + b) * BATCH_N) + lane);
+      }
+    };
+    if (uint32_t(warp) < nb_out) {
+#pragma unroll
+      for (uint32_t v = 0; v < MAX_VARS; v++) if (v < n_vars) off_cur[v] = off_of(v, warp);
+      issue_window_loads(off_cur);
+      load_syms(warp);
+      if (uint32_t(warp) + DEC_WARPS < nb_out) {
+#pragma unroll
+        for (uint32_t v = 0; v < MAX_VARS; v++) if (v < n_vars) off_nxt[v] = off_of(v, warp + DEC_WARPS);
+      }
+    }
+    for (uint32_t b = warp; b < nb_out; b += DEC_WARPS) {
+      const uint32_t out_cnt = min(uint32_t(BATCH_N), n_out - b * BATCH_N);  // numbers this batch emits
+      __syncwarp();
+#pragma unroll
+      for (uint32_t v = 0; v < MAX_VARS; v++) {
+        if (v < n_vars && sm.hdr.var[v].max_offset_bits > 0) {
+          uint2* w2 = reinterpret_cast<uint2*>(sm.win[warp][v]);
+          w2[lane] = make_uint2(uint32_t(pf[v][0]), uint32_t(pf[v][0] >> 32));
+          w2[32 + lane] = make_uint2(uint32_t(pf[v][1]), uint32_t(pf[v][1] >> 32));
+        }
+      }
+      __syncwarp();
+      uint2 sy_cur[MAX_VARS];
+#pragma unroll
+      for (uint32_t v = 0; v < MAX_VARS; v++) sy_cur[v] = sy_nxt[v];
+      uint32_t off_n2[MAX_VARS] = {0, 0};
+      if (b + DEC_WARPS < nb_out) {
+        issue_window_loads(off_nxt);
+        load_syms(b + DEC_WARPS);
+        if (b + 2 * DEC_WARPS < nb_out) {
+#pragma unroll
+          for (uint32_t v = 0; v < MAX_VARS; v++) if (v < n_vars) off_n2[v] = off_of(v, b + 2 * DEC_WARPS);
+        }
+      }
+      PCOB_TICK(3);  // window staging
+      L lat[MAX_VARS][8];
+      uint64_t last_end = 0;
+#pragma unroll
+      for (uint32_t v = 0; v < MAX_VARS; v++) {
+        if (v >= n_vars) break;
         const VarHdr& vh = sm.hdr.var[v];
         const uint32_t cnt = batch_count(v == 0 ? stored0 : stored1, b);
-        uint64_t bit;
-        if (need_index) {
-          const BatchEntry e = entries[size_t(v) * nb_total + b];
-          bit = chunk_bit0 + e.bit_pos;
-          if (vh.n_bins > 1 && cnt > 0) {
-            WalkState ws;
-            for (int j = 0; j < 4; j++) ws.st[j] = min(uint32_t(e.st[j]), (1u << vh.ans_size_log) - 1);
-            uint32_t dummy;
-            bit = ans_walk_batch<false>(src.words, max_word, min(bit, src.n_bits), ws, sm.node[v], int(cnt), &sm.sym[tid * SYM_ROW_WORDS], dummy);
-          }
-        } else {
-          // all vars trivial: batches before b contribute count0*ob0 + count1*ob1 bits
-          const uint64_t c0 = min(uint64_t(b) * BATCH_N, uint64_t(stored0));
-          const uint64_t c1 = min(uint64_t(b) * BATCH_N, uint64_t(stored1));
-          uint64_t before = c0 * ob0 + c1 * ob1;
-          if (v == 1) before += uint64_t(batch_count(stored0, b)) * ob0;
-          bit = sm.hdr.body_bit + before;
+        const bool full = cnt == BATCH_N;
+        uint32_t sy[8];
+        {
+          const uint32_t p0 = sy_cur[v].x, p1 = sy_cur[v].y;  // zero when the var has one bin
+#pragma unroll
+          for (int e = 0; e < 8; e++) sy[e] = ((e < 4 ? p0 : p1) >> (8 * (e & 3))) & 0xffu;
         }
-        sm.off_start[tid] = uint32_t(min(bit, src.n_bits) - chunk_bit0);
-      }
-    }
-    PCOB_TICK(1);  // phase A work
-    __syncthreads();
-    PCOB_TICK(2);  // barrier after phase A
-    // ---------------- phase B: one warp per batch ----------------
-    // A batch's offset bits are one contiguous run of the stream.  Each warp copies a 512-byte window of it with two
-    // coalesced 8-byte loads per lane -- issued one batch ahead so the DRAM/L2 latency hides behind the previous
-    // batch -- parks it in shared memory and extracts the variable-width fields from there.
-    {
-      uint64_t pf[MAX_VARS][2];
-      auto issue_window_loads = [&](uint32_t bl_n) {
-#pragma unroll
-        for (uint32_t v = 0; v < MAX_VARS; v++) {
-          if (v < n_vars && sm.hdr.var[v].max_offset_bits > 0) {
-            const uint64_t wb = (chunk_bit0 + sm.off_start[v * tile_b + bl_n]) >> 6;
-            const uint64_t i0 = wb + lane, i1 = wb + 32 + lane;
-            pf[v][0] = __ldg(src.words + (i0 <= max_word ? i0 : max_word));
-            pf[v][1] = __ldg(src.words + (i1 <= max_word ? i1 : max_word));
-          }
-        }
-      };
-      if (uint32_t(warp) < tile_n) issue_window_loads(warp);
-      for (uint32_t bl = warp; bl < tile_n; bl += DEC_WARPS) {
-        const uint32_t b = tile_start + bl;
-        const uint32_t out_cnt = min(uint32_t(BATCH_N), n_out - b * BATCH_N);  // numbers this batch emits
-        __syncwarp();
-#pragma unroll
-        for (uint32_t v = 0; v < MAX_VARS; v++) {
-          if (v < n_vars && sm.hdr.var[v].max_offset_bits > 0) {
-            uint2* w2 = reinterpret_cast<uint2*>(sm.win[warp][v]);
-            w2[lane] = make_uint2(uint32_t(pf[v][0]), uint32_t(pf[v][0] >> 32));
-            w2[32 + lane] = make_uint2(uint32_t(pf[v][1]), uint32_t(pf[v][1] >> 32));
-          }
-        }
-        __syncwarp();
-        if (bl + DEC_WARPS < tile_n) issue_window_loads(bl + DEC_WARPS);
-        PCOB_TICK(3);  // window staging
-        L lat[MAX_VARS][8];
-        uint64_t last_end = 0;
-#pragma unroll
-        for (uint32_t v = 0; v < MAX_VARS; v++) {
-          if (v >= n_vars) break;
-          const VarHdr& vh = sm.hdr.var[v];
-          const uint32_t cnt = batch_count(v == 0 ? stored0 : stored1, b);
-          const uint32_t row = (v * tile_b + bl);
-          const bool full = cnt == BATCH_N;
-          uint32_t sy[8];
-          if (vh.n_bins > 1) {
-            const uint32_t* rowp = &sm.sym[row * SYM_ROW_WORDS + lane * 2];
-            const uint32_t p0 = rowp[0], p1 = rowp[1];
-#pragma unroll
-            for (int e = 0; e < 8; e++) sy[e] = ((e < 4 ? p0 : p1) >> (8 * (e & 3))) & 0xffu;
-          } else {
-#pragma unroll
-            for (int e = 0; e < 8; e++) sy[e] = 0;
-          }
-          // ---- bins: offset bits and lower bound of every latent
-          const bool compact = sm.bin_compact[v] != 0;
-          uint32_t obv[8];
-          L lowv[8];
-          uint32_t lane_bits = 0;
-          if (compact) {
-            const L base = L(sm.bin_base[v]);
-#pragma unroll
-            for (int e = 0; e < 8; e++) {
-              const uint32_t q = sm.bin32[v][sy[e]];
-              obv[e] = q >> 25;
-              lowv[e] = L(base + L(q & 0x1ffffffu));
-            }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 8; e++) {
-              const uint4 q = *reinterpret_cast<const uint4*>(&sm.bin[v][sy[e]]);
-              lowv[e] = L((uint64_t(q.y) << 32) | q.x);
-              obv[e] = q.z;
-            }
-          }
+        // ---- bins: offset bits and lower bound of every latent
+        const bool compact = sm.bin_compact[v] != 0;
+        uint32_t obv[8];
+        L lowv[8];
+        uint32_t lane_bits = 0;
+        if (compact) {
+          const L base = L(sm.bin_base[v]);
 #pragma unroll
           for (int e = 0; e < 8; e++) {
-            if (!full && uint32_t(lane * 8 + e) >= cnt) obv[e] = 0;
-            lane_bits += obv[e];
+            const uint32_t q = sm.bin32[v][sy[e]];
+            obv[e] = q >> 25;
+            lowv[e] = L(base + L(q & 0x1ffffffu));
           }
-          uint32_t inc = lane_bits;
+        } else {
 #pragma unroll
-          for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
-            if (lane >= d) inc += o;
+          for (int e = 0; e < 8; e++) {
+            const uint4 q = *reinterpret_cast<const uint4*>(&sm.bin[v][sy[e]]);
+            lowv[e] = L((uint64_t(q.y) << 32) | q.x);
+            obv[e] = q.z;
           }
-          const uint32_t total_bits = __shfl_sync(0xffffffffu, inc, 31);
-          const uint64_t sec_bit = chunk_bit0 + sm.off_start[row];
-          last_end = sec_bit + total_bits;
-          if (vh.max_offset_bits == 0) {
+        }
 #pragma unroll
-            for (int e = 0; e < 8; e++) lat[v][e] = lowv[e];
-          } else if (total_bits <= WIN_USABLE_BITS) {
-            const uint32_t* win = sm.win[warp][v];
-            uint32_t p = uint32_t(sec_bit & 63) + (inc - lane_bits);
-            const bool narrow = LT<L>::BITS <= 32 || vh.max_offset_bits <= 32;
-            if (narrow && !__any_sync(0xffffffffu, lane_bits > 64)) {
-              // the lane's 8 fields are contiguous and span <= 64 bits: fetch its 3 words once, extract from registers
-              const uint32_t w = p >> 5;
-              const uint32_t x0 = win[w], x1 = win[w + 1], x2 = win[w + 2];
-              uint32_t pos = p & 31;
+        for (int e = 0; e < 8; e++) {
+          if (!full && uint32_t(lane * 8 + e) >= cnt) obv[e] = 0;
+          lane_bits += obv[e];
+        }
+        uint32_t inc = lane_bits;
 #pragma unroll
-              for (int e = 0; e < 8; e++) {
-                const uint32_t wd = pos >> 5, rr = pos & 31;
-                const uint32_t lo = wd == 0 ? x0 : (wd == 1 ? x1 : x2);
-                const uint32_t hi = wd == 0 ? x1 : (wd == 1 ? x2 : 0u);
-                const uint32_t f = __funnelshift_r(lo, hi, rr) & uint32_t(~(~uint64_t(0) << obv[e]));
-                lat[v][e] = L(lowv[e] + L(f));
-                pos += obv[e];
-              }
-            } else if (narrow) {
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+          if (lane >= d) inc += o;
+        }
+        const uint32_t total_bits = __shfl_sync(0xffffffffu, inc, 31);
+        const uint64_t sec_bit = chunk_bit0 + off_cur[v];
+        last_end = sec_bit + total_bits;
+        if (vh.max_offset_bits == 0) {
 #pragma unroll
-              for (int e = 0; e < 8; e++) {
-                lat[v][e] = L(lowv[e] + win_extract<L, false>(win, p, obv[e], uint32_t(~(~uint64_t(0) << obv[e]))));
-                p += obv[e];
-              }
-            } else {
-#pragma unroll
-              for (int e = 0; e < 8; e++) {
-                lat[v][e] = L(lowv[e] + win_extract<L, true>(win, p, obv[e], uint32_t(~(~uint64_t(0) << min(obv[e], 32u)))));
-                p += obv[e];
-              }
-            }
-          } else {
-            // section longer than the staged window (mean offset > ~15.7 bits): read the stream directly
-            uint64_t pos = sec_bit + (inc - lane_bits);
+          for (int e = 0; e < 8; e++) lat[v][e] = lowv[e];
+        } else if (total_bits <= WIN_USABLE_BITS) {
+          const uint32_t* win = sm.win[warp][v];
+          uint32_t p = uint32_t(sec_bit & 63) + (inc - lane_bits);
+          const bool narrow = LT<L>::BITS <= 32 || vh.max_offset_bits <= 32;
+          if (narrow && !__any_sync(0xffffffffu, lane_bits > 64)) {
+            // the lane's 8 fields are contiguous and span <= 64 bits: fetch its 3 words once, extract from registers
+            const uint32_t w = p >> 5;
+            const uint32_t x0 = win[w], x1 = win[w + 1], x2 = win[w + 2];
+            uint32_t pos = p & 31;
 #pragma unroll
             for (int e = 0; e < 8; e++) {
-              L off = 0;
-              if (obv[e] != 0) off = read_offset<L>(src.words, max_word, min(pos, src.n_bits), obv[e]);
+              const uint32_t wd = pos >> 5, rr = pos & 31;
+              const uint32_t lo = wd == 0 ? x0 : (wd == 1 ? x1 : x2);
+              const uint32_t hi = wd == 0 ? x1 : (wd == 1 ? x2 : 0u);
+              const uint32_t f = __funnelshift_r(lo, hi, rr) & uint32_t(~(~uint64_t(0) << obv[e]));
+              lat[v][e] = L(lowv[e] + L(f));
               pos += obv[e];
-              lat[v][e] = L(lowv[e] + off);
             }
-          }
-          // positions past the stored latents of a delta'd var hold deltas that cannot influence any emitted
-          // number (page_latent_decompressor.rs:244-248); any value works there
-        }
-        PCOB_TICK(4);  // symbols, bins, scan, extraction
-        L* dst = out + task.out_offset + size_t(b) * BATCH_N + lane * 8;
-        if (order > 0) {
-          // ---- un-delta of the primary (delta/consecutive.rs:35-50)
-          PCOB_TICK(5);
-          switch (order) {
-            case 1: undelta_chain<L, 1>(lat[0], sm, b, lane); break;
-            case 2: undelta_chain<L, 2>(lat[0], sm, b, lane); break;
-            case 3: undelta_chain<L, 3>(lat[0], sm, b, lane); break;
-            case 4: undelta_chain<L, 4>(lat[0], sm, b, lane); break;
-            case 5: undelta_chain<L, 5>(lat[0], sm, b, lane); break;
-            case 6: undelta_chain<L, 6>(lat[0], sm, b, lane); break;
-            default: undelta_chain<L, 7>(lat[0], sm, b, lane); break;
-          }
-          PCOB_TICK(6);  // scans + chain wait + link + fold
-        }
-        {
-          // ---- join (mode/*.rs)
-          L res[8];
-          if (mode == MODE_CLASSIC) {
-#pragma unroll
-            for (int e = 0; e < 8; e++) res[e] = from_latent_kind<L>(lat[0][e], kind);
-          } else if (mode == MODE_INT_MULT) {
-            const L base = L(sm.hdr.mode_base);
-#pragma unroll
-            for (int e = 0; e < 8; e++) res[e] = from_latent_kind<L>(L(L(lat[0][e] * base) + lat[1][e]), kind);
-          } else if (mode == MODE_FLOAT_MULT) {
-            constexpr L MID = L(L(1) << (LT<L>::BITS - 1));
-            const L base_bits = from_latent_ordered<L>(L(sm.hdr.mode_base), true, false);
+          } else if (narrow) {
 #pragma unroll
             for (int e = 0; e < 8; e++) {
-              const L un = float_mult_unadjusted(lat[0][e], base_bits);
-              const L u = to_latent_ordered<L>(un, true, false);
-              res[e] = from_latent_kind<L>(L(L(u + lat[1][e]) + MID), 2);
+              lat[v][e] = L(lowv[e] + win_extract<L, false>(win, p, obv[e], uint32_t(~(~uint64_t(0) << obv[e]))));
+              p += obv[e];
             }
-          } else {  // MODE_FLOAT_QUANT
-            const uint32_t k = sm.hdr.mode_k;
-            constexpr L MID = L(L(1) << (LT<L>::BITS - 1));
-            const L sign_cutoff = L(MID >> k);
-            const L kmax = L(L(L(1) << k) - 1);
-#pragma unroll
-            for (int e = 0; e < 8; e++) {
-              const L pq = lat[0][e];
-              const L lowest = pq >= sign_cutoff ? lat[1][e] : L(kmax - lat[1][e]);
-              res[e] = from_latent_kind<L>(L(L(pq << k) + lowest), 2);
-            }
-          }
-          if (out_cnt == BATCH_N) {
-            store8<L>(dst, res);
           } else {
 #pragma unroll
-            for (int e = 0; e < 8; e++)
-              if (uint32_t(lane * 8 + e) < out_cnt) dst[e] = res[e];
+            for (int e = 0; e < 8; e++) {
+              lat[v][e] = L(lowv[e] + win_extract<L, true>(win, p, obv[e], uint32_t(~(~uint64_t(0) << min(obv[e], 32u)))));
+              p += obv[e];
+            }
+          }
+        } else {
+          // section longer than the staged window (mean offset > ~15.7 bits): read the stream directly
+          uint64_t pos = sec_bit + (inc - lane_bits);
+#pragma unroll
+          for (int e = 0; e < 8; e++) {
+            L off = 0;
+            if (obv[e] != 0) off = read_offset<L>(src.words, max_word, min(pos, src.n_bits), obv[e]);
+            pos += obv[e];
+            lat[v][e] = L(lowv[e] + off);
           }
         }
-        PCOB_TICK(7);  // chain link, moments, join, store
-        // ---- end-of-page checks by the warp that owns the last batch (page_decompressor.rs:184-188)
-        if (b == nb_total - 1 && lane == 0) {
-          const uint64_t bit = last_end;
-          if (bit > src.n_bits) end_err = ST_INSUFFICIENT_DATA;
-          else {
-            const uint32_t pad = uint32_t((8 - (bit & 7)) & 7);
-            if (pad && read_bits_safe(src, bit, pad) != 0) end_err = ST_CORRUPTION;
+        // positions past the stored latents of a delta'd var hold deltas that cannot influence any emitted
+        // number (page_latent_decompressor.rs:244-248); any value works there
+      }
+      PCOB_TICK(4);  // symbols, bins, scan, extraction
+      L* dst = out + task.out_offset + size_t(b) * BATCH_N + lane * 8;
+      if (order > 0) {
+        // ---- un-delta of the primary (delta/consecutive.rs:35-50)
+        PCOB_TICK(5);
+        switch (order) {
+          case 1: undelta_chain<L, 1>(lat[0], sm, b, lane); break;
+          case 2: undelta_chain<L, 2>(lat[0], sm, b, lane); break;
+          case 3: undelta_chain<L, 3>(lat[0], sm, b, lane); break;
+          case 4: undelta_chain<L, 4>(lat[0], sm, b, lane); break;
+          case 5: undelta_chain<L, 5>(lat[0], sm, b, lane); break;
+          case 6: undelta_chain<L, 6>(lat[0], sm, b, lane); break;
+          default: undelta_chain<L, 7>(lat[0], sm, b, lane); break;
+        }
+        PCOB_TICK(6);  // scans + chain wait + link + fold
+      }
+      {
+        // ---- join (mode/*.rs)
+        L res[8];
+        if (mode == MODE_CLASSIC) {
+#pragma unroll
+          for (int e = 0; e < 8; e++) res[e] = from_latent_kind<L>(lat[0][e], kind);
+        } else if (mode == MODE_INT_MULT) {
+          const L base = L(sm.hdr.mode_base);
+#pragma unroll
+          for (int e = 0; e < 8; e++) res[e] = from_latent_kind<L>(L(L(lat[0][e] * base) + lat[1][e]), kind);
+        } else if (mode == MODE_FLOAT_MULT) {
+          constexpr L MID = L(L(1) << (LT<L>::BITS - 1));
+          const L base_bits = from_latent_ordered<L>(L(sm.hdr.mode_base), true, false);
+#pragma unroll
+          for (int e = 0; e < 8; e++) {
+            const L un = float_mult_unadjusted(lat[0][e], base_bits);
+            const L u = to_latent_ordered<L>(un, true, false);
+            res[e] = from_latent_kind<L>(L(L(u + lat[1][e]) + MID), 2);
           }
+        } else {  // MODE_FLOAT_QUANT
+          const uint32_t k = sm.hdr.mode_k;
+          constexpr L MID = L(L(1) << (LT<L>::BITS - 1));
+          const L sign_cutoff = L(MID >> k);
+          const L kmax = L(L(L(1) << k) - 1);
+#pragma unroll
+          for (int e = 0; e < 8; e++) {
+            const L pq = lat[0][e];
+            const L lowest = pq >= sign_cutoff ? lat[1][e] : L(kmax - lat[1][e]);
+            res[e] = from_latent_kind<L>(L(L(pq << k) + lowest), 2);
+          }
+        }
+        if (out_cnt == BATCH_N) {
+          store8<L>(dst, res);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; e++)
+            if (uint32_t(lane * 8 + e) < out_cnt) dst[e] = res[e];
         }
       }
+      PCOB_TICK(7);  // chain link, moments, join, store
+      // ---- end-of-page checks by the warp that owns the last batch (page_decompressor.rs:184-188)
+      if (b == nb_total - 1 && lane == 0) {
+        const uint64_t bit = last_end;
+        if (bit > src.n_bits) end_err = ST_INSUFFICIENT_DATA;
+        else {
+          const uint32_t pad = uint32_t((8 - (bit & 7)) & 7);
+          if (pad && read_bits_safe(src, bit, pad) != 0) end_err = ST_CORRUPTION;
+        }
+      }
+#pragma unroll
+      for (uint32_t v = 0; v < MAX_VARS; v++) { off_cur[v] = off_nxt[v]; off_nxt[v] = off_n2[v]; }
     }
-    PCOB_TICK(8);  // loop tail
-    __syncthreads();
-    PCOB_TICK(9);  // barrier after phase B
   }
+  PCOB_TICK(8);  // loop tail
 #ifdef PCOB_DEC_TIMING
   if (lane == 0)
     for (int i = 0; i < 10; i++) atomicAdd(&g_dec_timing[i], _tacc[i]);

@@ -14,7 +14,7 @@ struct Context {
   bool initialized = false;
   bool device_ok = false;
   std::string device_err;
-  DevBuf src, out, index, statuses, misc;
+  DevBuf src, out, index, statuses, misc, dec_syms, dec_offs;
   CompressScratch enc;
   Binoms* d_binoms = nullptr;
   int sm_count = 0;
@@ -92,11 +92,24 @@ static PcoB200Error launch_decode(Context& c, const FileParams& fp, const uint8_
   uint32_t* d_st = c.statuses.as<uint32_t>();
   PCOB_CUDA_TRY(cudaMemsetAsync(d_st, 0xff, size_t(n_chunks) * sizeof(uint32_t), stream));
   const IndexChunk* d_chunks = reinterpret_cast<const IndexChunk*>(d_index + chunks_offset);
+  // scratch between the two kernels: one symbol byte per latent the destination can take, one section start per batch
+  const uint64_t rows = scratch_rows_total(out_len, n_chunks);
+  PCOB_CUDA_TRY(c.dec_syms.reserve(rows * BATCH_N + 64));
+  PCOB_CUDA_TRY(c.dec_offs.reserve(rows * sizeof(uint32_t) + 64));
+  static bool attr_set = false;
+  if (!attr_set) {
+    attr_set = true;
+    PCOB_CUDA_TRY(cudaFuncSetAttribute(symwalk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SymWalkSmem)));
+    PCOB_CUDA_TRY(cudaFuncSetAttribute(symwalk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+  }
+  profiler().begin("symwalk_kernel", stream);
+  symwalk_kernel<<<n_chunks, SW_THREADS, sizeof(SymWalkSmem), stream>>>(fp, d_chunks, d_index, out_len, c.dec_syms.as<uint8_t>(), c.dec_offs.as<uint32_t>());
+  profiler().end(stream);
   profiler().begin("decode_kernel", stream);
   dispatch_latent(fp.dtype, [&](auto tag) {
     using L = decltype(tag);
     decode_kernel<L><<<n_chunks, DEC_THREADS, sizeof(DecodeSmem), stream>>>(fp, d_chunks, d_st, d_index, static_cast<L*>(d_out), out_len,
-                                                                             c.d_binoms);
+                                                                             c.d_binoms, c.dec_syms.as<uint8_t>(), c.dec_offs.as<uint32_t>());
     return 0;
   });
   profiler().end(stream);
