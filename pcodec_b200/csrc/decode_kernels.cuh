@@ -14,6 +14,9 @@
 
 namespace pcob200 {
 
+#ifndef PCOB_DEC_NV1_BLOCKS
+#define PCOB_DEC_NV1_BLOCKS 2
+#endif
 #ifndef PCOB_DEC_MIN_BLOCKS
 #define PCOB_DEC_MIN_BLOCKS 2
 #endif
@@ -43,11 +46,16 @@ __device__ unsigned long long g_dec_timing[16];
 #define PCOB_TICK(idx) do { } while (0)
 #endif
 
-// node word: next_state_idx_base (14 bits) | field (14 bits) << 14 | bits_to_read (4 bits) << 28
+// node word: next_state_idx_base (bits 0-15) | field (bits 16-23) | bits_to_read (bits 24-31): byte-aligned so that
+// four symbols pack with byte permutes
 //   decode tables: field = bin index;  walker tables: field = bin offset_bits
-__device__ __forceinline__ uint32_t node_base(uint32_t n) { return n & 0x3fffu; }
-__device__ __forceinline__ uint32_t node_field(uint32_t n) { return (n >> 14) & 0x3fffu; }
-__device__ __forceinline__ uint32_t node_btr(uint32_t n) { return n >> 28; }
+__device__ __forceinline__ uint32_t node_base(uint32_t n) { return n & 0xffffu; }
+__device__ __forceinline__ uint32_t node_field(uint32_t n) { return (n >> 16) & 0xffu; }
+__device__ __forceinline__ uint32_t node_btr(uint32_t n) { return n >> 24; }
+// the fields of four nodes as four bytes
+__device__ __forceinline__ uint32_t node_fields4(uint32_t n0, uint32_t n1, uint32_t n2, uint32_t n3) {
+  return __byte_perm(__byte_perm(n0, n1, 0x0062), __byte_perm(n2, n3, 0x0062), 0x5410);
+}
 
 // ---------------------------------------------------------------------------
 // Shared memory layout of one decode CTA (SMALL variant: size_log <= 10, n_bins <= 256)
@@ -175,7 +183,7 @@ __device__ void build_var_tables(const BitSrc& src, ChunkHdr& hdr, int v, uint32
         uint32_t btr = __clz(x_s) - __clz(size);
         uint32_t nbase = (x_s << btr) - size;
         uint32_t field = WALKER ? uint32_t(bin_ob[sym]) : sym;
-        node[s] = nbase | (field << 14) | (btr << 28);
+        node[s] = nbase | (field << 16) | (btr << 24);
       }
     }
   }
@@ -684,24 +692,33 @@ __device__ __forceinline__ void load8(const L* __restrict__ src, L (&r)[8]) {
 // ---------------------------------------------------------------------------
 constexpr int SW_THREADS = 128;
 constexpr int SW_WARPS = SW_THREADS / 32;
-constexpr int SW_STAGE_BYTES = 16384;
+constexpr int SW_STAGE_BYTES = 13312;
 constexpr int SW_STAGE_WORDS = SW_STAGE_BYTES / 4;
+constexpr int SW_NODE_WORDS = 2048;   // decoder nodes per CTA, replicated when the tables are small (see below)
+constexpr int SW_SLAB = 64;           // symbols per tile flush
+constexpr int SW_TILE_ROW = SW_SLAB / 4 + 1;  // words per tile row (odd: conflict-free rows)
 
+// 32 lanes look up 32 unrelated states per step.  A var's node table is stored R times when it is small, copy r
+// interleaved at word (state * R + r), lane l reading copy l mod R: lanes with different copies never share a bank.
 struct SymWalkSmem {
   ChunkHdr hdr;
-  uint32_t node[MAX_VARS][1 << SMALL_MAX_SIZE_LOG];
+  uint32_t node[SW_NODE_WORDS];
   uint32_t err;
   union {
-    BuildScratch build;
+    struct {
+      BuildScratch build;
+      uint32_t node_plain[MAX_VARS][1 << SMALL_MAX_SIZE_LOG];
+    } b;
     struct {
       alignas(16) uint32_t stage[SW_WARPS][SW_STAGE_WORDS + 16];
-      uint32_t tile[SW_WARPS][32 * SYM_ROW_WORDS];
+      alignas(16) uint32_t tile[SW_WARPS][32 * SW_TILE_ROW + 3];
     } w;
   };
 };
 
 __global__ void __launch_bounds__(SW_THREADS) symwalk_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, const uint8_t* __restrict__ index_base,
-                                                              uint64_t out_len, uint8_t* __restrict__ d_syms, uint32_t* __restrict__ d_offs) {
+                                                              uint64_t out_len, uint8_t* __restrict__ d_syms, uint32_t* __restrict__ d_offs,
+                                                              uint8_t* __restrict__ d_nvars) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SymWalkSmem& sm = *reinterpret_cast<SymWalkSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -724,15 +741,27 @@ __global__ void __launch_bounds__(SW_THREADS) symwalk_kernel(FileParams fp, cons
     }
   }
   __syncthreads();
+  // which decode_kernel instantiation owns the chunk (a refused header goes to the one-var kernel, which reports it)
+  if (tid == 0) d_nvars[blockIdx.x] = uint8_t(sm.hdr.status == ST_OK && sm.hdr.n_vars == 2 ? 2 : 1);
   if (sm.hdr.status != ST_OK) return;
   const uint32_t n_vars = sm.hdr.n_vars;
   const bool need_index = (sm.hdr.var[0].n_bins > 1) || (n_vars > 1 && sm.hdr.var[1].n_bins > 1);
   if (!need_index || task.entries_offset == 0 || !index_base) return;  // trivial vars: section starts are closed-form
   for (uint32_t v = 0; v < n_vars; v++)
-    build_var_tables<false>(src, sm.hdr, v, sm.node[v], sm.build.bin_lower[v], sm.build.bin_ob[v], sm.build.bin_weight[v], sm.build.bin_cum[v],
-                            sm.build.sym_of_state[v], sm.build.rank_counter[v], &sm.err, false);
-  __syncthreads();  // the build scratch (aliased by stage and tile) is dead
+    build_var_tables<false>(src, sm.hdr, v, sm.b.node_plain[v], sm.b.build.bin_lower[v], sm.b.build.bin_ob[v], sm.b.build.bin_weight[v],
+                            sm.b.build.bin_cum[v], sm.b.build.sym_of_state[v], sm.b.build.rank_counter[v], &sm.err, false);
+  __syncthreads();
   if (sm.err) return;
+  // replicate: var v owns SW_NODE_WORDS / n_vars words (>= its 2^size_log); rep_log = log2 of its copy count
+  const uint32_t region = SW_NODE_WORDS / n_vars;
+  const uint32_t rep_log0 = min(5u, uint32_t(31 - __clz(region >> sm.hdr.var[0].ans_size_log)));
+  const uint32_t rep_log1 = n_vars > 1 ? min(5u, uint32_t(31 - __clz(region >> sm.hdr.var[1].ans_size_log))) : 0u;
+  for (uint32_t v = 0; v < n_vars; v++) {
+    const uint32_t rl = v == 0 ? rep_log0 : rep_log1;
+    const uint32_t cells = (1u << sm.hdr.var[v].ans_size_log) << rl;
+    for (uint32_t i = tid; i < cells; i += SW_THREADS) sm.node[v * region + i] = sm.b.node_plain[v][i >> rl];
+  }
+  __syncthreads();  // the build scratch and plain tables (aliased by stage and tile) are dead
   const uint32_t n = sm.hdr.n;
   const uint32_t n_out = task.out_offset >= out_len ? 0u : uint32_t(min(uint64_t(n), out_len - task.out_offset));
   const uint32_t nb_total = n_batches_of(n), nb_out = n_batches_of(n_out);
@@ -756,7 +785,10 @@ __global__ void __launch_bounds__(SW_THREADS) symwalk_kernel(FileParams fp, cons
       if (uint32_t(lane) < nbg) offs[b0 + lane] = e.bit_pos;
       continue;
     }
-    const uint32_t ans_max_bits = BATCH_N * vh.ans_size_log;  // a symbol reads <= size_log bits
+    const uint32_t size_log = vh.ans_size_log;
+    const uint32_t ans_max_bits = BATCH_N * size_log;  // a symbol reads <= size_log bits
+    const uint32_t rl = v == 0 ? rep_log0 : rep_log1;
+    const uint32_t* node = sm.node + v * region + (uint32_t(lane) & ((1u << rl) - 1));  // this lane's copy
     uint32_t k0 = 0;  // batches [k0, k1) of the group are staged per pass
     while (k0 < nbg) {
       const uint64_t base_bit = (chunk_bit0 + __shfl_sync(0xffffffffu, e.bit_pos, int(k0))) & ~uint64_t(127);  // 16-byte block
@@ -783,54 +815,82 @@ __global__ void __launch_bounds__(SW_THREADS) symwalk_kernel(FileParams fp, cons
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncwarp();
       const bool mine = uint32_t(lane) >= k0 && uint32_t(lane) < k1;
-      if (mine) {
-        const uint32_t b = b0 + lane;
-        const int cnt = int(batch_count(stored, b));
-        // clamp what an untrusted index could push outside the stage: garbage in, garbage out, but in bounds
-        uint32_t wpos = uint32_t(min(my_bit >= base_bit ? my_bit - base_bit : 0, uint64_t(SW_STAGE_BYTES) * 8 - ans_max_bits - 64));
-        const uint32_t smask = (1u << vh.ans_size_log) - 1;
-        uint32_t s0 = min(uint32_t(e.st[0]), smask), s1 = min(uint32_t(e.st[1]), smask), s2 = min(uint32_t(e.st[2]), smask), s3 = min(uint32_t(e.st[3]), smask);
-        const uint32_t* node = sm.node[v];
-        uint32_t* row = tile + lane * SYM_ROW_WORDS;
-        int i = 0;
-        for (; i + 4 <= cnt; i += 4) {
-          const uint32_t n0 = node[s0], n1 = node[s1], n2 = node[s2], n3 = node[s3];
-          const uint32_t w = wpos >> 5, r = wpos & 31;
-          const uint32_t x0 = stg[w], x1 = stg[w + 1], x2 = stg[w + 2];
-          const uint64_t g = (uint64_t(__funnelshift_r(x1, x2, r)) << 32) | __funnelshift_r(x0, x1, r);
-          const uint32_t c0 = node_btr(n0), c1 = node_btr(n1), c2 = node_btr(n2), c3 = node_btr(n3);
-          const uint32_t sh2 = c0 + c1, sh3 = sh2 + c2;
-          s0 = node_base(n0) + (uint32_t(g) & ((1u << c0) - 1));
-          s1 = node_base(n1) + (uint32_t(g >> c0) & ((1u << c1) - 1));
-          s2 = node_base(n2) + (uint32_t(g >> sh2) & ((1u << c2) - 1));
-          s3 = node_base(n3) + (uint32_t(g >> sh3) & ((1u << c3) - 1));
-          row[i >> 2] = node_field(n0) | (node_field(n1) << 8) | (node_field(n2) << 16) | (node_field(n3) << 24);
-          wpos += sh3 + c3;
+      const uint32_t b = b0 + lane;
+      const int cnt = mine ? int(batch_count(stored, b)) : 0;
+      // clamp what an untrusted index could push outside the stage: garbage in, garbage out, but in bounds
+      uint32_t wpos = uint32_t(min(my_bit >= base_bit ? my_bit - base_bit : 0, uint64_t(SW_STAGE_BYTES) * 8 - ans_max_bits - 64));
+      const uint32_t smask = (1u << size_log) - 1;
+      uint32_t s0 = min(uint32_t(e.st[0]), smask) << rl, s1 = min(uint32_t(e.st[1]), smask) << rl;  // states kept pre-scaled by the copy count
+      uint32_t s2 = min(uint32_t(e.st[2]), smask) << rl, s3 = min(uint32_t(e.st[3]), smask) << rl;
+      uint32_t* row = tile + lane * SW_TILE_ROW;
+      uint8_t* sym_rows = d_syms + (row0 + size_t(v) * nb_out + b0) * BATCH_N;
+      uint32_t w = wpos >> 5;
+      uint32_t x0 = stg[w], x1 = stg[w + 1], x2 = stg[w + 2];  // register window over the stream, reloaded when the word index moves
+      for (int slab = 0; slab < BATCH_N / SW_SLAB; slab++) {
+        const int i0 = slab * SW_SLAB;
+        if (size_log <= 8) {
+          // four symbols read <= 32 bits: one 32-bit window per group, fields by bit-field extract
+#pragma unroll 4
+          for (int i = i0; i < i0 + SW_SLAB; i += 4) {
+            if (i + 4 <= cnt) {
+              const uint32_t n0 = node[s0], n1 = node[s1], n2 = node[s2], n3 = node[s3];
+              const uint32_t g = __funnelshift_r(x0, x1, wpos & 31);
+              const uint32_t c0 = node_btr(n0), c1 = node_btr(n1), c2 = node_btr(n2), c3 = node_btr(n3);
+              const uint32_t sh2 = c0 + c1, sh3 = sh2 + c2;
+              s0 = (node_base(n0) + (g & ((1u << c0) - 1))) << rl;
+              s1 = (node_base(n1) + ((g >> c0) & ((1u << c1) - 1))) << rl;
+              s2 = (node_base(n2) + ((g >> sh2) & ((1u << c2) - 1))) << rl;
+              s3 = (node_base(n3) + ((g >> sh3) & ((1u << c3) - 1))) << rl;
+              row[(i - i0) >> 2] = node_fields4(n0, n1, n2, n3);
+              wpos += sh3 + c3;
+              if ((wpos >> 5) != w) { w = wpos >> 5; x0 = stg[w]; x1 = stg[w + 1]; }
+            }
+          }
+        } else {
+#pragma unroll 2
+          for (int i = i0; i < i0 + SW_SLAB; i += 4) {
+            if (i + 4 <= cnt) {
+              const uint32_t n0 = node[s0], n1 = node[s1], n2 = node[s2], n3 = node[s3];
+              const uint32_t r = wpos & 31;
+              const uint64_t g = (uint64_t(__funnelshift_r(x1, x2, r)) << 32) | __funnelshift_r(x0, x1, r);
+              const uint32_t c0 = node_btr(n0), c1 = node_btr(n1), c2 = node_btr(n2), c3 = node_btr(n3);
+              const uint32_t sh2 = c0 + c1, sh3 = sh2 + c2;
+              s0 = (node_base(n0) + (uint32_t(g) & ((1u << c0) - 1))) << rl;
+              s1 = (node_base(n1) + (uint32_t(g >> c0) & ((1u << c1) - 1))) << rl;
+              s2 = (node_base(n2) + (uint32_t(g >> sh2) & ((1u << c2) - 1))) << rl;
+              s3 = (node_base(n3) + (uint32_t(g >> sh3) & ((1u << c3) - 1))) << rl;
+              row[(i - i0) >> 2] = node_fields4(n0, n1, n2, n3);
+              wpos += sh3 + c3;
+              if ((wpos >> 5) != w) { w = wpos >> 5; x0 = stg[w]; x1 = stg[w + 1]; x2 = stg[w + 2]; }
+            }
+          }
         }
-        if (i < cnt) {  // ragged tail of the page's last batch (page_latent_decompressor.rs:144-177)
+        if (cnt > i0 && cnt < i0 + SW_SLAB && (cnt & 3)) {  // ragged tail of the page's last batch (page_latent_decompressor.rs:144-177)
+          const int i = cnt & ~3;
           uint32_t packed = 0;
           uint32_t sarr[4] = {s0, s1, s2, s3};
           for (int j = 0; i + j < cnt; j++) {
             const uint32_t nn = node[sarr[j]];
-            const uint32_t w = wpos >> 5, r = wpos & 31;
-            const uint32_t val = __funnelshift_r(stg[w], stg[w + 1], r) & ((1u << node_btr(nn)) - 1);
+            const uint32_t ww = wpos >> 5, r = wpos & 31;
+            const uint32_t val = __funnelshift_r(stg[ww], stg[ww + 1], r) & ((1u << node_btr(nn)) - 1);
             packed |= node_field(nn) << (8 * j);
-            sarr[j] = node_base(nn) + val;
+            sarr[j] = (node_base(nn) + val) << rl;
             wpos += node_btr(nn);
           }
-          row[i >> 2] = packed;
+          row[(i - i0) >> 2] = packed;
         }
-        offs[b] = uint32_t(min(base_bit + wpos, src.n_bits) - chunk_bit0);
+        __syncwarp();
+        // the slab of rows k0..k1 -> 64-byte pieces of the 256-byte symbol rows (4 lanes x 16 bytes per row)
+        if (__any_sync(0xffffffffu, cnt > i0)) {
+          for (uint32_t idx = k0 * 4 + lane; idx < k1 * 4; idx += 32) {
+            const uint32_t rr = idx >> 2, seg = idx & 3;
+            const uint32_t* tp = tile + rr * SW_TILE_ROW + seg * 4;
+            *reinterpret_cast<uint4*>(sym_rows + size_t(rr) * BATCH_N + i0 + seg * 16) = make_uint4(tp[0], tp[1], tp[2], tp[3]);
+          }
+        }
+        __syncwarp();
       }
-      __syncwarp();
-      // rows k0..k1 of the tile -> 256-byte symbol rows (16 lanes x 16 bytes each)
-      uint8_t* sym_rows = d_syms + (row0 + size_t(v) * nb_out + b0) * BATCH_N;
-      for (uint32_t idx = k0 * 16 + lane; idx < k1 * 16; idx += 32) {
-        const uint32_t rr = idx >> 4, seg = idx & 15;
-        const uint32_t* tp = tile + rr * SYM_ROW_WORDS + seg * 4;
-        *reinterpret_cast<uint4*>(sym_rows + size_t(rr) * BATCH_N + seg * 16) = make_uint4(tp[0], tp[1], tp[2], tp[3]);
-      }
-      __syncwarp();
+      if (mine) offs[b] = uint32_t(min(base_bit + wpos, src.n_bits) - chunk_bit0);
       k0 = k1;
     }
   }
@@ -839,11 +899,15 @@ __global__ void __launch_bounds__(SW_THREADS) symwalk_kernel(FileParams fp, cons
 // ---------------------------------------------------------------------------
 // decode_kernel: one CTA per chunk, one warp per batch; symbols and section starts come from symwalk_kernel.
 // ---------------------------------------------------------------------------
-template <typename L>
-__global__ void __launch_bounds__(DEC_THREADS, PCOB_DEC_MIN_BLOCKS)
+// NV = latent vars of the chunks this instantiation serves (1: classic, 2: int_mult / float_mult / float_quant); the
+// host launches both and a CTA leaves at once when its chunk belongs to the other (symwalk_kernel recorded each
+// chunk's var count) - one-var chunks then run with the registers of one var and a third CTA per SM.
+template <typename L, int NV>
+__global__ void __launch_bounds__(DEC_THREADS, NV == 1 ? PCOB_DEC_NV1_BLOCKS : 2)
 decode_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, uint32_t* __restrict__ statuses, const uint8_t* __restrict__ index_base,
               L* __restrict__ out, uint64_t out_len, const Binoms* __restrict__ binoms, const uint8_t* __restrict__ d_syms,
-              const uint32_t* __restrict__ d_offs) {
+              const uint32_t* __restrict__ d_offs, const uint8_t* __restrict__ d_nvars) {
+  if (d_nvars[blockIdx.x] != NV) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   DecodeSmem& sm = *reinterpret_cast<DecodeSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -869,6 +933,7 @@ decode_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, uint32_t* __
       }
       if (sm.hdr.mode == MODE_FLOAT_MULT && LT<L>::BITS < 32) sm.hdr.status = ST_UNSUPPORTED;
       if (task.n != 0 && task.n != sm.hdr.n) sm.hdr.status = ST_CORRUPTION;
+      if (sm.hdr.n_vars != NV) sm.hdr.status = ST_CORRUPTION;  // cannot happen: symwalk_kernel parsed the same bytes
     }
   }
   for (int i = tid; i < CHAIN_RING; i += DEC_THREADS) sm.m_flag[i] = 0;
@@ -879,7 +944,7 @@ decode_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, uint32_t* __
     if (tid == 0) statuses[blockIdx.x] = sm.hdr.status;
     return;
   }
-  const uint32_t n_vars = sm.hdr.n_vars;
+  constexpr uint32_t n_vars = NV;
   for (uint32_t v = 0; v < n_vars; v++)
     build_var_tables<false>(src, sm.hdr, v, nullptr, sm.build.bin_lower[v], sm.build.bin_ob[v], sm.build.bin_weight[v], sm.build.bin_cum[v],
                             sm.build.sym_of_state[v], sm.build.rank_counter[v], &sm.err, /*add_mid_to_lower=*/sm.hdr.var[v].delta_order > 0,
@@ -965,12 +1030,12 @@ decode_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, uint32_t* __
   // batch -- parks it in shared memory and extracts the variable-width fields from there.  The section starts and the
   // symbols (8 per lane) were produced by symwalk_kernel.
   {
-    uint64_t pf[MAX_VARS][2];
-    uint32_t off_cur[MAX_VARS] = {0, 0}, off_nxt[MAX_VARS] = {0, 0};
-    uint2 sy_nxt[MAX_VARS];
-    auto issue_window_loads = [&](const uint32_t (&off)[MAX_VARS]) {
+    uint64_t pf[NV][2];
+    uint32_t off_cur[NV] = {}, off_nxt[NV] = {};
+    uint2 sy_nxt[NV];
+    auto issue_window_loads = [&](const uint32_t (&off)[NV]) {
 #pragma unroll
-      for (uint32_t v = 0; v < MAX_VARS; v++) {
+      for (uint32_t v = 0; v < NV; v++) {
         if (v < n_vars && sm.hdr.var[v].max_offset_bits > 0) {
           const uint64_t wb = (chunk_bit0 + off[v]) >> 6;
           const uint64_t i0 = wb + lane, i1 = wb + 32 + lane;
@@ -981,7 +1046,7 @@ decode_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, uint32_t* __
     };
     auto load_syms = [&](uint32_t b) {
 #pragma unroll
-      for (uint32_t v = 0; v < MAX_VARS; v++) {
+      for (uint32_t v = 0; v < NV; v++) {
         sy_nxt[v] = make_uint2(0u, 0u);
         if (v < n_vars && sm.hdr.var[v].n_bins > 1)
           sy_nxt[v] = __ldg(reinterpret_cast<const uint2*>(d_syms + (row0 + size_t(v) * nb_out + b) * BATCH_N) + lane);
@@ -989,19 +1054,19 @@ decode_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, uint32_t* __
     };
     if (uint32_t(warp) < nb_out) {
 #pragma unroll
-      for (uint32_t v = 0; v < MAX_VARS; v++) if (v < n_vars) off_cur[v] = off_of(v, warp);
+      for (uint32_t v = 0; v < NV; v++) if (v < n_vars) off_cur[v] = off_of(v, warp);
       issue_window_loads(off_cur);
       load_syms(warp);
       if (uint32_t(warp) + DEC_WARPS < nb_out) {
 #pragma unroll
-        for (uint32_t v = 0; v < MAX_VARS; v++) if (v < n_vars) off_nxt[v] = off_of(v, warp + DEC_WARPS);
+        for (uint32_t v = 0; v < NV; v++) if (v < n_vars) off_nxt[v] = off_of(v, warp + DEC_WARPS);
       }
     }
     for (uint32_t b = warp; b < nb_out; b += DEC_WARPS) {
       const uint32_t out_cnt = min(uint32_t(BATCH_N), n_out - b * BATCH_N);  // numbers this batch emits
       __syncwarp();
 #pragma unroll
-      for (uint32_t v = 0; v < MAX_VARS; v++) {
+      for (uint32_t v = 0; v < NV; v++) {
         if (v < n_vars && sm.hdr.var[v].max_offset_bits > 0) {
           uint2* w2 = reinterpret_cast<uint2*>(sm.win[warp][v]);
           w2[lane] = make_uint2(uint32_t(pf[v][0]), uint32_t(pf[v][0] >> 32));
@@ -1009,23 +1074,23 @@ decode_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, uint32_t* __
         }
       }
       __syncwarp();
-      uint2 sy_cur[MAX_VARS];
+      uint2 sy_cur[NV];
 #pragma unroll
-      for (uint32_t v = 0; v < MAX_VARS; v++) sy_cur[v] = sy_nxt[v];
-      uint32_t off_n2[MAX_VARS] = {0, 0};
+      for (uint32_t v = 0; v < NV; v++) sy_cur[v] = sy_nxt[v];
+      uint32_t off_n2[NV] = {};
       if (b + DEC_WARPS < nb_out) {
         issue_window_loads(off_nxt);
         load_syms(b + DEC_WARPS);
         if (b + 2 * DEC_WARPS < nb_out) {
 #pragma unroll
-          for (uint32_t v = 0; v < MAX_VARS; v++) if (v < n_vars) off_n2[v] = off_of(v, b + 2 * DEC_WARPS);
+          for (uint32_t v = 0; v < NV; v++) if (v < n_vars) off_n2[v] = off_of(v, b + 2 * DEC_WARPS);
         }
       }
       PCOB_TICK(3);  // window staging
-      L lat[MAX_VARS][8];
+      L lat[NV][8];
       uint64_t last_end = 0;
 #pragma unroll
-      for (uint32_t v = 0; v < MAX_VARS; v++) {
+      for (uint32_t v = 0; v < NV; v++) {
         if (v >= n_vars) break;
         const VarHdr& vh = sm.hdr.var[v];
         const uint32_t cnt = batch_count(v == 0 ? stored0 : stored1, b);
@@ -1141,20 +1206,20 @@ decode_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, uint32_t* __
         if (mode == MODE_CLASSIC) {
 #pragma unroll
           for (int e = 0; e < 8; e++) res[e] = from_latent_kind<L>(lat[0][e], kind);
-        } else if (mode == MODE_INT_MULT) {
+        } else if (NV > 1 && mode == MODE_INT_MULT) {
           const L base = L(sm.hdr.mode_base);
 #pragma unroll
-          for (int e = 0; e < 8; e++) res[e] = from_latent_kind<L>(L(L(lat[0][e] * base) + lat[1][e]), kind);
-        } else if (mode == MODE_FLOAT_MULT) {
+          for (int e = 0; e < 8; e++) res[e] = from_latent_kind<L>(L(L(lat[0][e] * base) + lat[NV - 1][e]), kind);
+        } else if (NV > 1 && mode == MODE_FLOAT_MULT) {
           constexpr L MID = L(L(1) << (LT<L>::BITS - 1));
           const L base_bits = from_latent_ordered<L>(L(sm.hdr.mode_base), true, false);
 #pragma unroll
           for (int e = 0; e < 8; e++) {
             const L un = float_mult_unadjusted(lat[0][e], base_bits);
             const L u = to_latent_ordered<L>(un, true, false);
-            res[e] = from_latent_kind<L>(L(L(u + lat[1][e]) + MID), 2);
+            res[e] = from_latent_kind<L>(L(L(u + lat[NV - 1][e]) + MID), 2);
           }
-        } else {  // MODE_FLOAT_QUANT
+        } else if (NV > 1) {  // MODE_FLOAT_QUANT
           const uint32_t k = sm.hdr.mode_k;
           constexpr L MID = L(L(1) << (LT<L>::BITS - 1));
           const L sign_cutoff = L(MID >> k);
@@ -1162,7 +1227,7 @@ decode_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, uint32_t* __
 #pragma unroll
           for (int e = 0; e < 8; e++) {
             const L pq = lat[0][e];
-            const L lowest = pq >= sign_cutoff ? lat[1][e] : L(kmax - lat[1][e]);
+            const L lowest = pq >= sign_cutoff ? lat[NV - 1][e] : L(kmax - lat[NV - 1][e]);
             res[e] = from_latent_kind<L>(L(L(pq << k) + lowest), 2);
           }
         }
@@ -1185,7 +1250,7 @@ decode_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, uint32_t* __
         }
       }
 #pragma unroll
-      for (uint32_t v = 0; v < MAX_VARS; v++) { off_cur[v] = off_nxt[v]; off_nxt[v] = off_n2[v]; }
+      for (uint32_t v = 0; v < NV; v++) { off_cur[v] = off_nxt[v]; off_nxt[v] = off_n2[v]; }
     }
   }
   PCOB_TICK(8);  // loop tail

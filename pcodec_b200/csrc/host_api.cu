@@ -14,7 +14,7 @@ struct Context {
   bool initialized = false;
   bool device_ok = false;
   std::string device_err;
-  DevBuf src, out, index, statuses, misc, dec_syms, dec_offs;
+  DevBuf src, out, index, statuses, misc, dec_syms, dec_offs, dec_nvars;
   CompressScratch enc;
   Binoms* d_binoms = nullptr;
   int sm_count = 0;
@@ -55,10 +55,6 @@ static PcoB200Error ensure_device(Context& c) {
         e = cudaMalloc(&c.d_binoms, sizeof(Binoms));
         if (e == cudaSuccess) e = cudaMemcpy(c.d_binoms, &hb, sizeof(Binoms), cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WalkSmem));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(decode_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecodeSmem));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(decode_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecodeSmem));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(decode_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecodeSmem));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(decode_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DecodeSmem));
         if (e != cudaSuccess) c.device_err = cudaGetErrorString(e);
         else c.device_ok = true;
       }
@@ -96,6 +92,7 @@ static PcoB200Error launch_decode(Context& c, const FileParams& fp, const uint8_
   const uint64_t rows = scratch_rows_total(out_len, n_chunks);
   PCOB_CUDA_TRY(c.dec_syms.reserve(rows * BATCH_N + 64));
   PCOB_CUDA_TRY(c.dec_offs.reserve(rows * sizeof(uint32_t) + 64));
+  PCOB_CUDA_TRY(c.dec_nvars.reserve(size_t(n_chunks) + 64));
   static bool attr_set = false;
   if (!attr_set) {
     attr_set = true;
@@ -103,13 +100,16 @@ static PcoB200Error launch_decode(Context& c, const FileParams& fp, const uint8_
     PCOB_CUDA_TRY(cudaFuncSetAttribute(symwalk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
   }
   profiler().begin("symwalk_kernel", stream);
-  symwalk_kernel<<<n_chunks, SW_THREADS, sizeof(SymWalkSmem), stream>>>(fp, d_chunks, d_index, out_len, c.dec_syms.as<uint8_t>(), c.dec_offs.as<uint32_t>());
+  symwalk_kernel<<<n_chunks, SW_THREADS, sizeof(SymWalkSmem), stream>>>(fp, d_chunks, d_index, out_len, c.dec_syms.as<uint8_t>(), c.dec_offs.as<uint32_t>(),
+                                                                        c.dec_nvars.as<uint8_t>());
   profiler().end(stream);
   profiler().begin("decode_kernel", stream);
   dispatch_latent(fp.dtype, [&](auto tag) {
     using L = decltype(tag);
-    decode_kernel<L><<<n_chunks, DEC_THREADS, sizeof(DecodeSmem), stream>>>(fp, d_chunks, d_st, d_index, static_cast<L*>(d_out), out_len,
-                                                                             c.d_binoms, c.dec_syms.as<uint8_t>(), c.dec_offs.as<uint32_t>());
+    decode_kernel<L, 1><<<n_chunks, DEC_THREADS, sizeof(DecodeSmem), stream>>>(fp, d_chunks, d_st, d_index, static_cast<L*>(d_out), out_len, c.d_binoms,
+                                                                                c.dec_syms.as<uint8_t>(), c.dec_offs.as<uint32_t>(), c.dec_nvars.as<uint8_t>());
+    decode_kernel<L, 2><<<n_chunks, DEC_THREADS, sizeof(DecodeSmem), stream>>>(fp, d_chunks, d_st, d_index, static_cast<L*>(d_out), out_len, c.d_binoms,
+                                                                                c.dec_syms.as<uint8_t>(), c.dec_offs.as<uint32_t>(), c.dec_nvars.as<uint8_t>());
     return 0;
   });
   profiler().end(stream);
