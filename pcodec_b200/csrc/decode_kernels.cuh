@@ -57,6 +57,16 @@ __device__ __forceinline__ uint32_t node_fields4(uint32_t n0, uint32_t n1, uint3
   return __byte_perm(__byte_perm(n0, n1, 0x0062), __byte_perm(n2, n3, 0x0062), 0x5410);
 }
 
+// Shared-memory accesses by explicit 32-bit shared address: the compiler otherwise re-derives the CTA's shared window
+// (S2UR SR_CgaCtaId + ULEA) in front of every access made through a generic pointer, on the address path of the lookups.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
 // ---------------------------------------------------------------------------
 // Shared memory layout of one decode CTA (SMALL variant: size_log <= 10, n_bins <= 256)
 // ---------------------------------------------------------------------------
@@ -640,6 +650,26 @@ __device__ __forceinline__ void undelta_chain(L (&x)[8], DecodeSmem& sm, uint32_
 }
 
 // 8 consecutive numbers per lane <-> global memory, 16-byte accesses
+template <typename L, int K>
+__device__ __noinline__ void undelta_chain_out_of_line(L* x, DecodeSmem& sm, uint32_t b, int lane) {
+  L r[8];
+#pragma unroll
+  for (int e = 0; e < 8; e++) r[e] = x[e];
+  undelta_chain<L, K>(r, sm, b, lane);
+#pragma unroll
+  for (int e = 0; e < 8; e++) x[e] = r[e];
+}
+// only the copy handed to the out-of-line function lives in local memory; the caller's registers stay registers
+template <typename L, int K>
+__device__ __forceinline__ void undelta_chain_cold(L (&x)[8], DecodeSmem& sm, uint32_t b, int lane) {
+  L tmp[8];
+#pragma unroll
+  for (int e = 0; e < 8; e++) tmp[e] = x[e];
+  undelta_chain_out_of_line<L, K>(tmp, sm, b, lane);
+#pragma unroll
+  for (int e = 0; e < 8; e++) x[e] = tmp[e];
+}
+
 template <typename L>
 __device__ __forceinline__ void store8(L* __restrict__ dst, const L (&r)[8]) {
   if (sizeof(L) == 8) {
@@ -789,6 +819,8 @@ __global__ void __launch_bounds__(SW_THREADS) symwalk_kernel(FileParams fp, cons
     const uint32_t ans_max_bits = BATCH_N * size_log;  // a symbol reads <= size_log bits
     const uint32_t rl = v == 0 ? rep_log0 : rep_log1;
     const uint32_t* node = sm.node + v * region + (uint32_t(lane) & ((1u << rl) - 1));  // this lane's copy
+    const uint32_t node_sa = smem_addr(node);
+    const uint32_t sl = rl + 2;  // states are kept as byte offsets into the lane's copy
     uint32_t k0 = 0;  // batches [k0, k1) of the group are staged per pass
     while (k0 < nbg) {
       const uint64_t base_bit = (chunk_bit0 + __shfl_sync(0xffffffffu, e.bit_pos, int(k0))) & ~uint64_t(127);  // 16-byte block
@@ -820,12 +852,13 @@ __global__ void __launch_bounds__(SW_THREADS) symwalk_kernel(FileParams fp, cons
       // clamp what an untrusted index could push outside the stage: garbage in, garbage out, but in bounds
       uint32_t wpos = uint32_t(min(my_bit >= base_bit ? my_bit - base_bit : 0, uint64_t(SW_STAGE_BYTES) * 8 - ans_max_bits - 64));
       const uint32_t smask = (1u << size_log) - 1;
-      uint32_t s0 = min(uint32_t(e.st[0]), smask) << rl, s1 = min(uint32_t(e.st[1]), smask) << rl;  // states kept pre-scaled by the copy count
-      uint32_t s2 = min(uint32_t(e.st[2]), smask) << rl, s3 = min(uint32_t(e.st[3]), smask) << rl;
+      uint32_t s0 = min(uint32_t(e.st[0]), smask) << sl, s1 = min(uint32_t(e.st[1]), smask) << sl;
+      uint32_t s2 = min(uint32_t(e.st[2]), smask) << sl, s3 = min(uint32_t(e.st[3]), smask) << sl;
       uint32_t* row = tile + lane * SW_TILE_ROW;
+      const uint32_t row_sa = smem_addr(row);
       uint8_t* sym_rows = d_syms + (row0 + size_t(v) * nb_out + b0) * BATCH_N;
       uint32_t w = wpos >> 5;
-      uint32_t x0 = stg[w], x1 = stg[w + 1], x2 = stg[w + 2];  // register window over the stream, reloaded when the word index moves
+      uint32_t x0 = lds_u32(stg_sa + 4 * w), x1 = lds_u32(stg_sa + 4 * w + 4), x2 = lds_u32(stg_sa + 4 * w + 8);  // register window over the stream
       for (int slab = 0; slab < BATCH_N / SW_SLAB; slab++) {
         const int i0 = slab * SW_SLAB;
         if (size_log <= 8) {
@@ -833,35 +866,35 @@ __global__ void __launch_bounds__(SW_THREADS) symwalk_kernel(FileParams fp, cons
 #pragma unroll 4
           for (int i = i0; i < i0 + SW_SLAB; i += 4) {
             if (i + 4 <= cnt) {
-              const uint32_t n0 = node[s0], n1 = node[s1], n2 = node[s2], n3 = node[s3];
+              const uint32_t n0 = lds_u32(node_sa + s0), n1 = lds_u32(node_sa + s1), n2 = lds_u32(node_sa + s2), n3 = lds_u32(node_sa + s3);
               const uint32_t g = __funnelshift_r(x0, x1, wpos & 31);
               const uint32_t c0 = node_btr(n0), c1 = node_btr(n1), c2 = node_btr(n2), c3 = node_btr(n3);
               const uint32_t sh2 = c0 + c1, sh3 = sh2 + c2;
-              s0 = (node_base(n0) + (g & ((1u << c0) - 1))) << rl;
-              s1 = (node_base(n1) + ((g >> c0) & ((1u << c1) - 1))) << rl;
-              s2 = (node_base(n2) + ((g >> sh2) & ((1u << c2) - 1))) << rl;
-              s3 = (node_base(n3) + ((g >> sh3) & ((1u << c3) - 1))) << rl;
-              row[(i - i0) >> 2] = node_fields4(n0, n1, n2, n3);
+              s0 = (node_base(n0) + (g & ((1u << c0) - 1))) << sl;
+              s1 = (node_base(n1) + ((g >> c0) & ((1u << c1) - 1))) << sl;
+              s2 = (node_base(n2) + ((g >> sh2) & ((1u << c2) - 1))) << sl;
+              s3 = (node_base(n3) + ((g >> sh3) & ((1u << c3) - 1))) << sl;
+              sts_u32(row_sa + (i - i0), node_fields4(n0, n1, n2, n3));
               wpos += sh3 + c3;
-              if ((wpos >> 5) != w) { w = wpos >> 5; x0 = stg[w]; x1 = stg[w + 1]; }
+              if ((wpos >> 5) != w) { w = wpos >> 5; x0 = lds_u32(stg_sa + 4 * w); x1 = lds_u32(stg_sa + 4 * w + 4); }
             }
           }
         } else {
 #pragma unroll 2
           for (int i = i0; i < i0 + SW_SLAB; i += 4) {
             if (i + 4 <= cnt) {
-              const uint32_t n0 = node[s0], n1 = node[s1], n2 = node[s2], n3 = node[s3];
+              const uint32_t n0 = lds_u32(node_sa + s0), n1 = lds_u32(node_sa + s1), n2 = lds_u32(node_sa + s2), n3 = lds_u32(node_sa + s3);
               const uint32_t r = wpos & 31;
               const uint64_t g = (uint64_t(__funnelshift_r(x1, x2, r)) << 32) | __funnelshift_r(x0, x1, r);
               const uint32_t c0 = node_btr(n0), c1 = node_btr(n1), c2 = node_btr(n2), c3 = node_btr(n3);
               const uint32_t sh2 = c0 + c1, sh3 = sh2 + c2;
-              s0 = (node_base(n0) + (uint32_t(g) & ((1u << c0) - 1))) << rl;
-              s1 = (node_base(n1) + (uint32_t(g >> c0) & ((1u << c1) - 1))) << rl;
-              s2 = (node_base(n2) + (uint32_t(g >> sh2) & ((1u << c2) - 1))) << rl;
-              s3 = (node_base(n3) + (uint32_t(g >> sh3) & ((1u << c3) - 1))) << rl;
-              row[(i - i0) >> 2] = node_fields4(n0, n1, n2, n3);
+              s0 = (node_base(n0) + (uint32_t(g) & ((1u << c0) - 1))) << sl;
+              s1 = (node_base(n1) + (uint32_t(g >> c0) & ((1u << c1) - 1))) << sl;
+              s2 = (node_base(n2) + (uint32_t(g >> sh2) & ((1u << c2) - 1))) << sl;
+              s3 = (node_base(n3) + (uint32_t(g >> sh3) & ((1u << c3) - 1))) << sl;
+              sts_u32(row_sa + (i - i0), node_fields4(n0, n1, n2, n3));
               wpos += sh3 + c3;
-              if ((wpos >> 5) != w) { w = wpos >> 5; x0 = stg[w]; x1 = stg[w + 1]; x2 = stg[w + 2]; }
+              if ((wpos >> 5) != w) { w = wpos >> 5; x0 = lds_u32(stg_sa + 4 * w); x1 = lds_u32(stg_sa + 4 * w + 4); x2 = lds_u32(stg_sa + 4 * w + 8); }
             }
           }
         }
@@ -870,14 +903,14 @@ __global__ void __launch_bounds__(SW_THREADS) symwalk_kernel(FileParams fp, cons
           uint32_t packed = 0;
           uint32_t sarr[4] = {s0, s1, s2, s3};
           for (int j = 0; i + j < cnt; j++) {
-            const uint32_t nn = node[sarr[j]];
+            const uint32_t nn = lds_u32(node_sa + sarr[j]);
             const uint32_t ww = wpos >> 5, r = wpos & 31;
             const uint32_t val = __funnelshift_r(stg[ww], stg[ww + 1], r) & ((1u << node_btr(nn)) - 1);
             packed |= node_field(nn) << (8 * j);
-            sarr[j] = (node_base(nn) + val) << rl;
+            sarr[j] = (node_base(nn) + val) << sl;
             wpos += node_btr(nn);
           }
-          row[(i - i0) >> 2] = packed;
+          sts_u32(row_sa + (i - i0), packed);
         }
         __syncwarp();
         // the slab of rows k0..k1 -> 64-byte pieces of the 256-byte symbol rows (4 lanes x 16 bytes per row)
@@ -1101,8 +1134,48 @@ decode_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, uint32_t* __
 #pragma unroll
           for (int e = 0; e < 8; e++) sy[e] = ((e < 4 ? p0 : p1) >> (8 * (e & 3))) & 0xffu;
         }
-        // ---- bins: offset bits and lower bound of every latent
         const bool compact = sm.bin_compact[v] != 0;
+        if (compact && vh.max_offset_bits <= 32) {
+          // ---- fast path: 4-byte bin entries (lower - base | offset_bits << 25) and fields of <= 32 bits.  The lane keeps
+          // the 8 packed entries, finds its bit span by the warp scan, pulls the 4 words that cover a span of <= 96 bits
+          // once, and peels the fields off the low end of that register window.
+          const uint32_t bin_sa = smem_addr(&sm.bin32[v][0]);
+          uint32_t q[8];
+          uint32_t lane_bits = 0;
+#pragma unroll
+          for (int e = 0; e < 8; e++) {
+            q[e] = lds_u32(bin_sa + 4 * sy[e]);
+            if (!full && uint32_t(lane * 8 + e) >= cnt) q[e] &= 0x1ffffffu;
+            lane_bits += q[e] >> 25;
+          }
+          uint32_t inc = lane_bits;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += o;
+          }
+          const uint32_t total_bits = __shfl_sync(0xffffffffu, inc, 31);
+          const uint64_t sec_bit = chunk_bit0 + off_cur[v];
+          if (total_bits <= WIN_USABLE_BITS && !__any_sync(0xffffffffu, lane_bits > 96)) {
+            last_end = sec_bit + total_bits;
+            const L base = L(sm.bin_base[v]);
+            const uint32_t p = uint32_t(sec_bit & 63) + (inc - lane_bits);
+            const uint32_t wa = smem_addr(sm.win[warp][v]) + 4 * (p >> 5), r = p & 31;
+            uint32_t x0 = lds_u32(wa), x1 = lds_u32(wa + 4), x2 = lds_u32(wa + 8);
+            const uint32_t x3 = lds_u32(wa + 12);
+            x0 = __funnelshift_r(x0, x1, r); x1 = __funnelshift_r(x1, x2, r); x2 = __funnelshift_r(x2, x3, r);
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+              const uint32_t ob = q[e] >> 25;
+              uint32_t f;
+              asm("bfe.u32 %0, %1, 0, %2;" : "=r"(f) : "r"(x0), "r"(ob));
+              lat[v][e] = L(L(base + L(q[e] & 0x1ffffffu)) + L(f));
+              x0 = __funnelshift_rc(x0, x1, ob); x1 = __funnelshift_rc(x1, x2, ob); x2 = __funnelshift_rc(x2, 0u, ob);
+            }
+            continue;
+          }
+        }
+        // ---- bins: offset bits and lower bound of every latent
         uint32_t obv[8];
         L lowv[8];
         uint32_t lane_bits = 0;
@@ -1192,11 +1265,12 @@ decode_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, uint32_t* __
         switch (order) {
           case 1: undelta_chain<L, 1>(lat[0], sm, b, lane); break;
           case 2: undelta_chain<L, 2>(lat[0], sm, b, lane); break;
-          case 3: undelta_chain<L, 3>(lat[0], sm, b, lane); break;
-          case 4: undelta_chain<L, 4>(lat[0], sm, b, lane); break;
-          case 5: undelta_chain<L, 5>(lat[0], sm, b, lane); break;
-          case 6: undelta_chain<L, 6>(lat[0], sm, b, lane); break;
-          default: undelta_chain<L, 7>(lat[0], sm, b, lane); break;
+          // orders >= 3 are rare: out of line, so that their moment vectors do not set the kernel's register budget
+          case 3: undelta_chain_cold<L, 3>(lat[0], sm, b, lane); break;
+          case 4: undelta_chain_cold<L, 4>(lat[0], sm, b, lane); break;
+          case 5: undelta_chain_cold<L, 5>(lat[0], sm, b, lane); break;
+          case 6: undelta_chain_cold<L, 6>(lat[0], sm, b, lane); break;
+          default: undelta_chain_cold<L, 7>(lat[0], sm, b, lane); break;
         }
         PCOB_TICK(6);  // scans + chain wait + link + fold
       }
