@@ -1305,8 +1305,8 @@ decode_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, uint32_t* __
             res[e] = from_latent_kind<L>(L(L(pq << k) + lowest), 2);
           }
         }
-        if (out_cnt == BATCH_N) {
-          store8<L>(dst, res);
+        if (out_cnt == BATCH_N && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+          store8<L>(dst, res);  // 16-byte stores; a chunk that starts at an odd element offset takes the element-wise path
         } else {
 #pragma unroll
           for (int e = 0; e < 8; e++)

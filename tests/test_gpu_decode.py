@@ -199,3 +199,23 @@ def test_bit_flips_never_crash_and_match_oracle_verdict(sa, oracle):  # corrupti
             ref = None
         if ours is not None and ref is not None:
             np.testing.assert_array_equal(ours, ref)
+
+
+@pytest.mark.parametrize("dtype", [np.uint64, np.uint32, np.uint16])
+def test_chunks_starting_at_odd_element_offsets(sa, oracle, dtype):
+    """Multi-chunk files whose chunk sizes are odd: a chunk's destination is then not 16-byte aligned (vector stores must not
+    assume it), with and without the side index."""
+    rng = np.random.default_rng(3)
+    n = 4 * 7685 + 3
+    x = np.cumsum(rng.geometric(0.01, size=n)).astype(dtype)
+    for order in (0, 1):
+        cfg = oracle.make_config(mode=oracle.MODE_CLASSIC, delta=oracle.DELTA_CONSECUTIVE, delta_order=order, max_page_n=7685)
+        data = oracle.simple_compress(x, cfg)
+        got = sa.simple_decompress(data, dtype)  # no index: device walk, then decode
+        assert np.array_equal(bits_view(got), bits_view(x))
+        idx = sa.build_index(data, dtype)
+        assert np.array_equal(bits_view(sa.simple_decompress(data, dtype, index=idx)), bits_view(x))
+        out = np.zeros(n, dtype=dtype)
+        prog = sa.simple_decompress_into(data, out)
+        assert prog.finished and prog.n_processed == n
+        assert np.array_equal(bits_view(out), bits_view(x))
