@@ -40,6 +40,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-chunks", type=int, default=32)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather-pages", action="store_true", help="N > 1: also all-gather the compressed page bytes (every rank ends up with the whole file)")
     return ap.parse_args()
 
 
@@ -193,9 +194,13 @@ def run_gpu_arm(args, rank, world):
         assert prog.n_processed == n and prog.finished
 
     gathered = None
+    file_offset = [0]
 
     def gather_pages():
-        # config 4: one NCCL all-gather that concatenates the ranks' compressed pages (sizes first, then padded bytes)
+        # The exchange step of the sharded path: chunks are independent, so a rank only needs to know WHERE its
+        # pages go in the logical standalone file - one NCCL all-gather of the per-rank compressed byte counts; the exclusive
+        # prefix is this rank's byte offset (a sharded writer pwrite()s there; decompress stays sharded and needs nothing).
+        # --gather-pages additionally all-gathers the page bytes themselves so that every rank holds the whole file.
         nonlocal gathered
         if world == 1:
             return
@@ -203,11 +208,13 @@ def run_gpu_arm(args, rank, world):
 
         sizes = torch.zeros(world, dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(sizes, torch.tensor([n_written.value], dtype=torch.int64, device=dev))
-        mx = int(sizes.max().item())
-        mx = (mx + 255) // 256 * 256
-        if gathered is None or gathered.numel() < world * mx:
-            gathered = torch.empty(world * mx, dtype=torch.uint8, device=dev)
-        dist.all_gather_into_tensor(gathered[: world * mx], d_comp[:mx])
+        sizes_h = sizes.cpu()
+        file_offset[0] = int(sizes_h[:rank].sum().item())
+        if args.gather_pages:
+            mx = (int(sizes_h.max().item()) + 255) // 256 * 256
+            if gathered is None or gathered.numel() < world * mx:
+                gathered = torch.empty(world * mx, dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(gathered[: world * mx], d_comp[:mx])
 
     def barrier():
         if world > 1:
@@ -339,7 +346,7 @@ def run_gpu_arm(args, rank, world):
         "config": {"workload": f"C2: {n_chunks} chunks x 2^18 u64 per GPU, classic mode, consecutive delta order 1, level 8 (cumsum of geometric(0.001)); "
                                "step = compress + decompress of every chunk, buffers resident in HBM",
                    "chunks_per_gpu": n_chunks, "chunk_n": CHUNK_N, "l2": "inputs (2 GiB per GPU) exceed the 126 MB L2",
-                   "multi_gpu": "independent chunk shards per rank; one NCCL all-gather of compressed pages per step" if world > 1 else "single GPU",
+                   "multi_gpu": ("independent chunk shards per rank; one NCCL all-gather per step of the per-rank compressed sizes (file offsets of the shards)" + ("; plus an all-gather of the page bytes" if args.gather_pages else "; pages stay sharded")) if world > 1 else "single GPU",
                    "side_index": "decompress uses the per-batch side index emitted by the compressor (bytes counted in the roofline)"},
         "compress_mb_s": world * U / 1e6 / (float(np.mean(t_c)) / 1e3), "decompress_mb_s": world * U / 1e6 / (float(np.mean(t_d)) / 1e3),
         "gather_ms": float(np.mean(t_g)), "compressed_bytes_per_gpu": Cbytes, "index_bytes_per_gpu": Ibytes, "ratio": U / Cbytes,
