@@ -11,7 +11,7 @@
 namespace pcob200 {
 
 struct CompressScratch {
-  DevBuf lat0, lat1, keys_a, keys_b, sym0, sym1, ans0, ans1, ob_sum, ans_sum, entries, plans, chunks, starts, seg, cub_tmp, out, small, index, probes;
+  DevBuf lat0, lat1, keys_a, keys_b, sym0, sym1, ans0, ans1, ob_sum, ans_sum, entries, plans, chunks, starts, seg, cub_tmp, out, small, index, probes, sample, sample_starts;
 };
 
 // pco/src/wrapped/chunk_compressor.rs:362-371
@@ -154,13 +154,17 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
       break;
     }
     case PCO_B200_MODE_AUTO:
-      return fail(PCO_B200_UNSUPPORTED, "ModeSpec::Auto is not on the GPU hot path yet; pass an explicit mode");
+      // The reference's Auto mode search (int_mult::choose_base, float_mult / float_quant detection on a random sample,
+      // with HashMap-order-dependent ties) is not restated: Auto on the GPU path means Classic, which is always valid.
+      ep.mode = MODE_CLASSIC;
+      break;
     default: return fail(PCO_B200_UNSUPPORTED, "ModeSpec::TryDict is outside the GPU hot path");
   }
+  bool auto_delta = false;
   switch (cfg.delta_spec) {
     case PCO_B200_DELTA_NOOP: ep.order = 0; break;
     case PCO_B200_DELTA_TRY_CONSECUTIVE: ep.order = cfg.delta_order; break;
-    case PCO_B200_DELTA_AUTO: return fail(PCO_B200_UNSUPPORTED, "DeltaSpec::Auto is not on the GPU hot path yet; pass an explicit delta");
+    case PCO_B200_DELTA_AUTO: auto_delta = true; ep.order = 0; break;  // resolved below by the sampled order search
     case PCO_B200_DELTA_TRY_CONV1:
       if (cfg.delta_order == 0) { ep.order = 0; break; }
       return fail(PCO_B200_UNSUPPORTED, "DeltaSpec::TryConv1 is outside the GPU hot path");
@@ -250,77 +254,124 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
   PCOB_CUDA_TRY(cudaMemcpyAsync(d_header, header.data(), header.size(), cudaMemcpyHostToDevice, stream));
   PCOB_CUDA_TRY(cudaMemsetAsync(S.ob_sum.p, 0, n_cvb * 4, stream));
 
-  // ---- K1+K2
-  init_chunks_kernel<<<(n_chunks + 255) / 256, 256, 0, stream>>>(d_chunks, n_chunks);
-  profiler().begin("split_delta_kernel", stream);
-  switch (ep.mode) {
-    case MODE_CLASSIC: split_delta_kernel<L, MODE_CLASSIC><<<n_chunks * tiles_per_chunk, SPLIT_THREADS, 0, stream>>>(ep, tiles_per_chunk, d_lat[0], d_lat[1], d_chunks); break;
-    case MODE_INT_MULT: split_delta_kernel<L, MODE_INT_MULT><<<n_chunks * tiles_per_chunk, SPLIT_THREADS, 0, stream>>>(ep, tiles_per_chunk, d_lat[0], d_lat[1], d_chunks); break;
-    case MODE_FLOAT_QUANT: split_delta_kernel<L, MODE_FLOAT_QUANT><<<n_chunks * tiles_per_chunk, SPLIT_THREADS, 0, stream>>>(ep, tiles_per_chunk, d_lat[0], d_lat[1], d_chunks); break;
-    default: split_delta_kernel<L, MODE_FLOAT_MULT><<<n_chunks * tiles_per_chunk, SPLIT_THREADS, 0, stream>>>(ep, tiles_per_chunk, d_lat[0], d_lat[1], d_chunks); break;
-  }
-  profiler().end(stream);
-  // ---- planner per var: range-reduced keys -> segmented radix sort over the significant bits -> plan
-  static bool plan_attr_set = false;
-  if (!plan_attr_set) {
-    plan_attr_set = true;
-    PCOB_CUDA_TRY(cudaFuncSetAttribute(plan_probe_kernel<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(((size_t(1) << PLAN_MAX_COUNT_BITS) + 1) * 4 + 16)));
-    PCOB_CUDA_TRY(cudaFuncSetAttribute(pack_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PackSmem)));
-    // several counting CTAs per SM: ask for the largest shared-memory carveout
-    PCOB_CUDA_TRY(cudaFuncSetAttribute(plan_probe_kernel<L, true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-    PCOB_CUDA_TRY(cudaFuncSetAttribute(pack_kernel<L>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-    PCOB_CUDA_TRY(cudaFuncSetAttribute(bin_lut_kernel<L>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-  }
+  // ---- K1+K2 and the planner for one set of chunks (the call's chunks, or their samples during the Auto delta search)
   uint32_t var_range_bits[MAX_VARS] = {64, 64};
-  for (uint32_t v = 0; v < ep.n_vars; v++) {
-    const uint32_t order_v = v == 0 ? ep.order : 0;
-    PCOB_CUDA_TRY(cudaMemsetAsync(d_small, 0, 4, stream));
-    range_bits_kernel<<<(n_chunks + 255) / 256, 256, 0, stream>>>(d_chunks, n_chunks, int(v), d_small);
-    uint32_t range_bits = 0;
-    PCOB_CUDA_TRY(cudaMemcpyAsync(&range_bits, d_small, 4, cudaMemcpyDeviceToHost, stream));
-    PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
-    var_range_bits[v] = range_bits;
-    if (range_bits <= PLAN_MAX_COUNT_BITS) {
-      // small key range (the usual case once the chunk minimum is subtracted): counting histogram, no sort
-      const size_t smem = ((size_t(1) << range_bits) + 1) * 4 + 16;
-      profiler().begin("plan_probe_kernel_counting", stream);
-      plan_probe_kernel<L, true><<<n_chunks, PLAN_THREADS, smem, stream>>>(ep, d_lat[v], d_chunks, d_probes, int(v), range_bits);
+  auto front = [&](const EncParams& e, uint32_t tiles, size_t slots, uint32_t (&vrb)[MAX_VARS]) -> PcoB200Error {
+    init_chunks_kernel<<<(n_chunks + 255) / 256, 256, 0, stream>>>(d_chunks, n_chunks);
+    profiler().begin("split_delta_kernel", stream);
+    switch (e.mode) {
+      case MODE_CLASSIC: split_delta_kernel<L, MODE_CLASSIC><<<n_chunks * tiles, SPLIT_THREADS, 0, stream>>>(e, tiles, d_lat[0], d_lat[1], d_chunks); break;
+      case MODE_INT_MULT: split_delta_kernel<L, MODE_INT_MULT><<<n_chunks * tiles, SPLIT_THREADS, 0, stream>>>(e, tiles, d_lat[0], d_lat[1], d_chunks); break;
+      case MODE_FLOAT_QUANT: split_delta_kernel<L, MODE_FLOAT_QUANT><<<n_chunks * tiles, SPLIT_THREADS, 0, stream>>>(e, tiles, d_lat[0], d_lat[1], d_chunks); break;
+      default: split_delta_kernel<L, MODE_FLOAT_MULT><<<n_chunks * tiles, SPLIT_THREADS, 0, stream>>>(e, tiles, d_lat[0], d_lat[1], d_chunks); break;
+    }
+    profiler().end(stream);
+    // ---- planner per var: range-reduced keys -> segmented radix sort over the significant bits -> plan
+    static bool plan_attr_set = false;
+    if (!plan_attr_set) {
+      plan_attr_set = true;
+      PCOB_CUDA_TRY(cudaFuncSetAttribute(plan_probe_kernel<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(((size_t(1) << PLAN_MAX_COUNT_BITS) + 1) * 4 + 16)));
+      PCOB_CUDA_TRY(cudaFuncSetAttribute(pack_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PackSmem)));
+      // several counting CTAs per SM: ask for the largest shared-memory carveout
+      PCOB_CUDA_TRY(cudaFuncSetAttribute(plan_probe_kernel<L, true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+      PCOB_CUDA_TRY(cudaFuncSetAttribute(pack_kernel<L>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+      PCOB_CUDA_TRY(cudaFuncSetAttribute(bin_lut_kernel<L>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    }
+    for (uint32_t v = 0; v < e.n_vars; v++) {
+      const uint32_t order_v = v == 0 ? e.order : 0;
+      PCOB_CUDA_TRY(cudaMemsetAsync(d_small, 0, 4, stream));
+      range_bits_kernel<<<(n_chunks + 255) / 256, 256, 0, stream>>>(d_chunks, n_chunks, int(v), d_small);
+      uint32_t range_bits = 0;
+      PCOB_CUDA_TRY(cudaMemcpyAsync(&range_bits, d_small, 4, cudaMemcpyDeviceToHost, stream));
+      PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
+      vrb[v] = range_bits;
+      if (range_bits <= PLAN_MAX_COUNT_BITS) {
+        // small key range (the usual case once the chunk minimum is subtracted): counting histogram, no sort
+        const size_t smem = ((size_t(1) << range_bits) + 1) * 4 + 16;
+        profiler().begin("plan_probe_kernel_counting", stream);
+        plan_probe_kernel<L, true><<<n_chunks, PLAN_THREADS, smem, stream>>>(e, d_lat[v], d_chunks, d_probes, int(v), range_bits);
+        profiler().end(stream);
+        profiler().begin("plan_solve_kernel", stream);
+        plan_solve_kernel<L><<<n_chunks, SOLVE_THREADS, 0, stream>>>(e, d_probes, d_chunks, d_plans, int(v));
+        profiler().end(stream);
+        continue;
+      }
+      // wide key range: sort the range-reduced keys (the two key buffers exist only on this path)
+      PCOB_CUDA_TRY(S.keys_a.reserve(slots * sizeof(L) + 64));
+      PCOB_CUDA_TRY(S.keys_b.reserve(slots * sizeof(L) + 64));
+      profiler().begin("sort_keys_kernel", stream);
+      sort_keys_kernel<L><<<n_chunks * tiles, 256, 0, stream>>>(e, tiles, d_lat[v], S.keys_a.as<L>(), d_chunks, int(v));
+      profiler().end(stream);
+      uint64_t* seg_begin = S.seg.as<uint64_t>();
+      uint64_t* seg_end = seg_begin + n_chunks;
+      segment_offsets_kernel<<<(n_chunks + 255) / 256, 256, 0, stream>>>(e, order_v, seg_begin, seg_end);
+      const L* sorted = S.keys_a.as<L>();
+      {
+        cub::DoubleBuffer<L> db(S.keys_a.as<L>(), S.keys_b.as<L>());
+        size_t tmp_bytes = 0;
+        PCOB_CUDA_TRY(cub::DeviceSegmentedRadixSort::SortKeys(nullptr, tmp_bytes, db, int64_t(slots), int64_t(n_chunks), seg_begin, seg_end, 0,
+                                                              int(range_bits), stream));
+        PCOB_CUDA_TRY(S.cub_tmp.reserve(tmp_bytes + 16));
+        profiler().begin("cub_segmented_radix_sort", stream);
+        PCOB_CUDA_TRY(cub::DeviceSegmentedRadixSort::SortKeys(S.cub_tmp.p, tmp_bytes, db, int64_t(slots), int64_t(n_chunks), seg_begin, seg_end, 0,
+                                                              int(range_bits), stream));
+        profiler().end(stream);
+        sorted = db.Current();
+      }
+      profiler().begin("plan_probe_kernel_sorted", stream);
+      plan_probe_kernel<L, false><<<n_chunks, PLAN_THREADS, 16, stream>>>(e, sorted, d_chunks, d_probes, int(v), range_bits);
       profiler().end(stream);
       profiler().begin("plan_solve_kernel", stream);
-      plan_solve_kernel<L><<<n_chunks, SOLVE_THREADS, 0, stream>>>(ep, d_probes, d_chunks, d_plans, int(v));
+      plan_solve_kernel<L><<<n_chunks, SOLVE_THREADS, 0, stream>>>(e, d_probes, d_chunks, d_plans, int(v));
       profiler().end(stream);
-      continue;
     }
-    // wide key range: sort the range-reduced keys (the two key buffers exist only on this path)
-    PCOB_CUDA_TRY(S.keys_a.reserve(n_slots * sizeof(L) + 64));
-    PCOB_CUDA_TRY(S.keys_b.reserve(n_slots * sizeof(L) + 64));
-    profiler().begin("sort_keys_kernel", stream);
-    sort_keys_kernel<L><<<n_chunks * tiles_per_chunk, 256, 0, stream>>>(ep, tiles_per_chunk, d_lat[v], S.keys_a.as<L>(), d_chunks, int(v));
-    profiler().end(stream);
-    uint64_t* seg_begin = S.seg.as<uint64_t>();
-    uint64_t* seg_end = seg_begin + n_chunks;
-    segment_offsets_kernel<<<(n_chunks + 255) / 256, 256, 0, stream>>>(ep, order_v, seg_begin, seg_end);
-    const L* sorted = S.keys_a.as<L>();
-    {
-      cub::DoubleBuffer<L> db(S.keys_a.as<L>(), S.keys_b.as<L>());
-      size_t tmp_bytes = 0;
-      PCOB_CUDA_TRY(cub::DeviceSegmentedRadixSort::SortKeys(nullptr, tmp_bytes, db, int64_t(n_slots), int64_t(n_chunks), seg_begin, seg_end, 0,
-                                                            int(range_bits), stream));
-      PCOB_CUDA_TRY(S.cub_tmp.reserve(tmp_bytes + 16));
-      profiler().begin("cub_segmented_radix_sort", stream);
-      PCOB_CUDA_TRY(cub::DeviceSegmentedRadixSort::SortKeys(S.cub_tmp.p, tmp_bytes, db, int64_t(n_slots), int64_t(n_chunks), seg_begin, seg_end, 0,
-                                                            int(range_bits), stream));
-      profiler().end(stream);
-      sorted = db.Current();
+    return PCO_B200_OK;
+  };
+  if (auto_delta) {
+    // ---- DeltaSpec::Auto: sampled search over consecutive orders (see gather_sample_kernel)
+    std::vector<uint64_t> s_starts(pages.size() + 1, 0), s_rows(pages.size() + 1, 0);
+    uint64_t max_ns = 0;
+    for (size_t i = 0; i < pages.size(); i++) {
+      const SampleGeom g = delta_sample_geom(pages[i]);
+      const uint64_t ns = uint64_t(g.n_groups) * g.group_n;
+      s_starts[i + 1] = s_starts[i] + ns;
+      s_rows[i + 1] = s_rows[i] + ((ns + BATCH_N - 1) / BATCH_N) * BATCH_N;
+      max_ns = std::max(max_ns, ns);
     }
-    profiler().begin("plan_probe_kernel_sorted", stream);
-    plan_probe_kernel<L, false><<<n_chunks, PLAN_THREADS, 16, stream>>>(ep, sorted, d_chunks, d_probes, int(v), range_bits);
-    profiler().end(stream);
-    profiler().begin("plan_solve_kernel", stream);
-    plan_solve_kernel<L><<<n_chunks, SOLVE_THREADS, 0, stream>>>(ep, d_probes, d_chunks, d_plans, int(v));
-    profiler().end(stream);
+    if (s_starts.back() > 0) {
+      PCOB_CUDA_TRY(S.sample.reserve(s_starts.back() * sizeof(L) + 64));
+      PCOB_CUDA_TRY(S.sample_starts.reserve(s_starts.size() * 16 + 16));
+      uint64_t* d_ss = S.sample_starts.as<uint64_t>();
+      PCOB_CUDA_TRY(cudaMemcpyAsync(d_ss, s_starts.data(), s_starts.size() * 8, cudaMemcpyHostToDevice, stream));
+      PCOB_CUDA_TRY(cudaMemcpyAsync(d_ss + s_starts.size(), s_rows.data(), s_rows.size() * 8, cudaMemcpyHostToDevice, stream));
+      gather_sample_kernel<L><<<n_chunks, 256, 0, stream>>>(static_cast<const L*>(d_nums), ep.chunk_starts, d_ss, S.sample.as<L>());
+      EncParams es = ep;
+      es.nums = S.sample.p;
+      es.chunk_starts = d_ss;
+      es.row_base = d_ss + s_starts.size();
+      es.n_total = s_starts.back();
+      es.max_chunk_n = uint32_t(max_ns);
+      const uint32_t s_tiles = uint32_t((max_ns + SPLIT_TILE - 1) / SPLIT_TILE);
+      unsigned long long* d_cost = reinterpret_cast<unsigned long long*>(d_small + 4);
+      unsigned long long best_cost = 0;
+      uint32_t best_order = 0;
+      for (uint32_t k = 0; k <= MAX_ORDER; k++) {
+        es.order = k;
+        uint32_t vrb[MAX_VARS] = {64, 64};
+        if (PcoB200Error e = front(es, s_tiles, size_t(s_rows.back()), vrb)) return e;
+        PCOB_CUDA_TRY(cudaMemsetAsync(d_cost, 0, 8, stream));
+        auto_cost_kernel<<<(n_chunks + 255) / 256, 256, 0, stream>>>(es, d_plans, d_cost);
+        unsigned long long cost = 0;
+        PCOB_CUDA_TRY(cudaMemcpyAsync(&cost, d_cost, 8, cudaMemcpyDeviceToHost, stream));
+        PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
+        if (k == 0 || cost < best_cost) { best_cost = cost; best_order = k; }
+        else break;  // "it's almost always convex" (chunk_compressor.rs:347-357)
+      }
+      ep.order = best_order;
+    }
   }
+  if (PcoB200Error e = front(ep, tiles_per_chunk, n_slots, var_range_bits)) return e;
   fallback_kernel<<<(n_chunks + 255) / 256, 256, 0, stream>>>(ep, d_plans, d_chunks);
   // ---- K3, K4
   const uint32_t groups_per_chunk = (bpc + 7) / 8;

@@ -57,6 +57,7 @@ struct EncParams {
 struct VarPlan {
   uint32_t n_bins, size_log, max_ob, n_lat;
   uint64_t wc_bits;            // sum over bins of count * worst-case bits per latent
+  uint64_t est_bits;           // sum over bins of count * (offset bits + tANS bits at the bin's weight): size estimate for the Auto delta search
   uint64_t lower[ENC_MAXB];
   uint8_t ob[ENC_MAXB];
   uint16_t weight[ENC_MAXB];
@@ -512,7 +513,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) plan_solve_kernel(EncParams ep,
   const uint64_t vmin = chunks[c].vmin[v];
   constexpr uint32_t LBITS = LT<L>::BITS;
   if (n == 0) {  // train_infos on an empty var (chunk_compressor.rs:56-58): zero bins
-    if (tid == 0) { plan.n_bins = 0; plan.size_log = 0; plan.max_ob = 0; plan.n_lat = 0; plan.wc_bits = 0; plan.next_states[0] = 0; }
+    if (tid == 0) { plan.n_bins = 0; plan.size_log = 0; plan.max_ob = 0; plan.n_lat = 0; plan.wc_bits = 0; plan.est_bits = 0; plan.next_states[0] = 0; }
     return;
   }
   ENC_TICK_INIT();
@@ -703,10 +704,12 @@ __global__ void __launch_bounds__(SOLVE_THREADS) plan_solve_kernel(EncParams ep,
     uint32_t cm = 0;
     uint64_t wc = 0;
     uint32_t max_ob = 0;
+    float est = 0.0f;
     for (uint32_t t = 0; t < n_opt; t++) {
       sm.cum[t] = cm;
       cm += sm.weights[t];
       wc += uint64_t(sm.o_count[t]) * (sm.o_ob[t] + size_log - (31 - __clz(sm.weights[t])));  // bin.rs:25-27
+      est += float(sm.o_count[t]) * (float(sm.o_ob[t] + size_log) - __log2f(float(sm.weights[t])));
       max_ob = max(max_ob, sm.o_ob[t]);
     }
     sm.cum[n_opt] = cm;
@@ -715,6 +718,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) plan_solve_kernel(EncParams ep,
     plan.max_ob = max_ob;
     plan.n_lat = n;
     plan.wc_bits = wc;
+    plan.est_bits = uint64_t(est);
   }
   __syncthreads();
   ENC_TICK(5);  // rewind + quantize
@@ -757,6 +761,49 @@ __global__ void __launch_bounds__(SOLVE_THREADS) plan_solve_kernel(EncParams ep,
     }
   }
   ENC_TICK(6);  // tables
+}
+
+// ---------------------------------------------------------------------------
+// DeltaSpec::Auto on the GPU path: the reference (chunk_compressor.rs:310-360) trial-compresses a sample of each chunk -
+// groups of 200 consecutive numbers at a regular stride (sampling.rs:21-60) - with consecutive orders 1, 2, ... until the
+// estimated size stops shrinking (and with Lookback, which this path does not encode).  Here the same sample of every
+// chunk is gathered into a side array, the ordinary split/delta + planner kernels run on it per order, and
+// auto_cost_kernel adds up the estimated sizes; one order is chosen for the whole call.
+// ---------------------------------------------------------------------------
+struct SampleGeom { uint32_t group_n, n_groups, stride; };
+__host__ __device__ inline SampleGeom delta_sample_geom(uint64_t n) {
+  SampleGeom g{0, 0, 0};
+  if (n < 10) return g;                                   // sampling.rs:14-20 calc_sample_n
+  const uint64_t target = 10 + (n - 10) / 40;
+  g.group_n = uint32_t(n < 200 ? n : 200);                // DELTA_TARGET_GROUP_N
+  g.n_groups = uint32_t((target + 199) / 200);
+  const uint64_t nominal = uint64_t(g.n_groups) * g.group_n;
+  const uint64_t spare = n > nominal ? n - nominal : 0;
+  g.stride = uint32_t(g.group_n + spare / ((g.n_groups > 2 ? g.n_groups : 2) - 1));
+  return g;
+}
+
+template <typename L>
+__global__ void gather_sample_kernel(const L* __restrict__ nums, const uint64_t* __restrict__ chunk_starts, const uint64_t* __restrict__ sample_starts,
+                                     L* __restrict__ sample) {
+  const uint32_t c = blockIdx.x;
+  const uint64_t cs = chunk_starts[c], n = chunk_starts[c + 1] - cs;
+  const SampleGeom g = delta_sample_geom(n);
+  const uint32_t ns = g.n_groups * g.group_n;
+  L* dst = sample + sample_starts[c];
+  for (uint32_t i = threadIdx.x; i < ns; i += blockDim.x) dst[i] = nums[cs + uint64_t(i / g.group_n) * g.stride + i % g.group_n];
+}
+
+// estimated compressed bits of the sampled chunks at the delta order the plans were trained with
+__global__ void auto_cost_kernel(EncParams ep, const VarPlan* __restrict__ plans, unsigned long long* __restrict__ cost) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ep.n_chunks) return;
+  if (ep.chunk_starts[c + 1] == ep.chunk_starts[c]) return;
+  const uint32_t lbits = nt_bits(ep.dtype);
+  const VarPlan& p = plans[size_t(c) * MAX_VARS];
+  const uint32_t stride = p.size_log + lbits + offset_bits_bits(lbits);
+  const unsigned long long bits = 4 + 15 + uint64_t(p.n_bins) * stride + uint64_t(ep.order) * lbits + 4 * p.size_log + p.est_bits;
+  atomicAdd(cost, bits);
 }
 
 // ---------------------------------------------------------------------------

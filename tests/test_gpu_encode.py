@@ -219,3 +219,58 @@ def test_sharded_chunks_only_equals_whole_file(sa, oracle):
     assert assembled == whole
     ocfg = oracle.make_config(mode=oracle.MODE_CLASSIC, delta=oracle.DELTA_CONSECUTIVE, delta_order=1, max_page_n=page)
     assert assembled == oracle.simple_compress(nums, ocfg)
+
+
+@pytest.mark.parametrize("dtype", [np.uint64, np.int32, np.float64, np.uint16, np.int8])
+@pytest.mark.parametrize("shape", ["walk", "walk2", "noise", "tiny"])
+def test_auto_config_is_valid_pco_and_picks_a_sane_delta(sa, oracle, dtype, shape):
+    """ChunkConfig::default() (Auto mode, Auto delta - what pco_c and the Python binding use).  On the GPU path Auto means
+    Classic + a sampled search over consecutive delta orders, so the bytes are NOT the reference's when that would pick another
+    mode or Lookback; the contract is a valid standalone file (the oracle decodes it to the input) of comparable size."""
+    from pcodec_b200 import ChunkConfig
+
+    rng = np.random.default_rng(5)
+    n = {"walk": 60000, "walk2": 60000, "noise": 30000, "tiny": 7}[shape]
+    if shape in ("walk", "tiny"):
+        x = _walk(dtype, n, seed=9)
+    elif shape == "walk2":
+        base = np.cumsum(np.cumsum(rng.integers(-3, 4, size=n)))
+        x = base.astype(np.float64).astype(dtype) if np.dtype(dtype).kind == "f" else base.astype(np.int64).astype(np.uint64).astype(np.dtype(dtype).str.replace("i", "u")).view(dtype)
+    else:
+        x = rng.integers(0, 200, size=n).astype(dtype)
+    ours = sa.simple_compress(x, ChunkConfig(enable_8_bit=True))
+    np.testing.assert_array_equal(bits_view(oracle.simple_decompress(ours, dtype)), bits_view(x))
+    np.testing.assert_array_equal(bits_view(sa.simple_decompress(ours, dtype)), bits_view(x))
+    info = oracle.inspect(ours, dtype)
+    assert all(c["mode"] == 0 for c in info["chunks"])  # Classic
+    # against the oracle's own Auto delta (Classic mode): same order when it stays within consecutive deltas, similar size
+    theirs = oracle.simple_compress(x, oracle.make_config(mode=oracle.MODE_CLASSIC, delta=oracle.DELTA_AUTO))
+    tinfo = oracle.inspect(theirs, dtype)
+    if all(c["delta"] in (0, 1) for c in tinfo["chunks"]):  # None or Consecutive
+        assert len(ours) <= len(theirs) * 1.05 + 64
+    if shape == "walk":
+        assert info["chunks"][0]["delta_order"] >= 1
+    if shape == "noise":
+        assert info["chunks"][0]["delta_order"] == 0
+
+
+def test_reference_c_abi_compress_into(oracle):
+    """pco_standalone_simple_compress_into (pco_c/include/cpcodec_generated.h:33-48): Auto config, uniform-type header."""
+    import ctypes as C
+
+    from pcodec_b200 import _lib
+
+    L = _lib.lib()
+    nums = _walk(np.int64, 50000, 4)
+    cap = L.pco_standalone_guarantee_file_size(C.c_size_t(nums.size), C.c_ubyte(4))
+    dst = np.zeros(cap, dtype=np.uint8)
+    n_written = C.c_size_t()
+    rc = L.pco_standalone_simple_compress_into(nums.ctypes.data_as(C.c_void_p), C.c_size_t(nums.size), C.c_ubyte(4), None, dst.ctypes.data_as(C.c_void_p),
+                                               C.c_size_t(cap), C.byref(n_written))
+    assert rc == 0 and 0 < n_written.value < nums.nbytes // 2
+    data = dst[: n_written.value].tobytes()
+    assert data[5] == 4  # uniform-type header flavour (standalone/simple.rs:27-29)
+    np.testing.assert_array_equal(oracle.simple_decompress(data, np.int64), nums)
+    # too small a destination -> PcoCompressionError
+    assert L.pco_standalone_simple_compress_into(nums.ctypes.data_as(C.c_void_p), C.c_size_t(nums.size), C.c_ubyte(4), None, dst.ctypes.data_as(C.c_void_p),
+                                                 C.c_size_t(100), C.byref(n_written)) == 2
