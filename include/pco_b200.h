@@ -113,6 +113,34 @@ PcoB200Error pco_b200_build_index(const void *compressed, size_t compressed_len,
 void pco_b200_profile_enable(int on);
 int pco_b200_profile_last(char *buf, size_t cap);
 
+/* ---- wrapped format (pco/src/wrapped/: FileCompressor / ChunkCompressor / FileDecompressor / ChunkDecompressor /
+ * PageDecompressor), for callers that keep chunk metadata and pages in their own container.  This round: ONE page per
+ * chunk (a chunk whose PagingSpec yields several pages, which share bins, is PCO_B200_UNSUPPORTED).
+ * A wrapped chunk is the same bytes as a standalone chunk without its 4-byte preamble: chunk meta, then the page. */
+typedef struct PcoB200ChunkCompressor PcoB200ChunkCompressor;
+/* FileCompressor::write_header (pco/src/wrapped/file_compressor.rs; format version bytes, metadata/format_version.rs:87-91) */
+PcoB200Error pco_b200_file_compressor_write_header(void *dst, size_t dst_cap, size_t *n_written);
+/* FileDecompressor::new (pco/src/wrapped/file_decompressor.rs): checks the header bytes, returns how many were read */
+PcoB200Error pco_b200_file_decompressor_read_header(const void *src, size_t src_len, size_t *n_read);
+/* FileCompressor::chunk_compressor + ChunkCompressor::new (pco/src/wrapped/chunk_compressor.rs:442-500): does the compression */
+PcoB200Error pco_b200_chunk_compressor_new(const void *nums, size_t n, unsigned char dtype, const PcoB200ChunkConfig *config,
+                                           PcoB200ChunkCompressor **out);
+void pco_b200_chunk_compressor_free(PcoB200ChunkCompressor *cc);
+size_t pco_b200_chunk_compressor_n_pages(const PcoB200ChunkCompressor *cc);                  /* n_per_page().len() (:544-547) */
+size_t pco_b200_chunk_compressor_page_n(const PcoB200ChunkCompressor *cc, size_t page_idx);  /* n_per_page()[i] */
+size_t pco_b200_chunk_compressor_meta_size(const PcoB200ChunkCompressor *cc); /* exact; the reference's meta_size_hint is a bound (:557-562) */
+PcoB200Error pco_b200_chunk_compressor_write_meta(const PcoB200ChunkCompressor *cc, void *dst, size_t dst_cap, size_t *n_written); /* :564-568 */
+size_t pco_b200_chunk_compressor_page_size(const PcoB200ChunkCompressor *cc, size_t page_idx); /* exact; page_size_hint (:599-601) */
+/* write_page (:659-705): page_idx out of range -> PCO_B200_INVALID_ARGUMENT (:661-666) */
+PcoB200Error pco_b200_chunk_compressor_write_page(const PcoB200ChunkCompressor *cc, size_t page_idx, void *dst, size_t dst_cap,
+                                                  size_t *n_written);
+/* FileDecompressor::chunk_decompressor (metadata/chunk.rs:127-174): byte size of the chunk meta at the head of src */
+PcoB200Error pco_b200_chunk_meta_size(const void *src, size_t src_len, unsigned char dtype, size_t *meta_len);
+/* ChunkDecompressor::page_decompressor + PageDecompressor::read (pco/src/wrapped/page_decompressor.rs:193-252): decodes a page of
+ * page_n numbers into dst (dst_len elements); bytes_read = bytes of `page` consumed (page_len must cover the page) */
+PcoB200Error pco_b200_page_decompress(const void *chunk_meta, size_t meta_len, const void *page, size_t page_len, size_t page_n,
+                                      unsigned char dtype, void *dst, size_t dst_len, PcoB200Progress *progress, size_t *bytes_read);
+
 #if defined(__cplusplus)
 }
 #endif

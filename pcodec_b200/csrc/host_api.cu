@@ -364,6 +364,163 @@ enum PcoError pco_standalone_simple_compress_into(const void* nums, size_t n, un
   return e == PCO_B200_OK ? PcoSuccess : PcoCompressionError;
 }
 
+// ---------------------------------------------------------------------------
+// Wrapped format (pco/src/wrapped/): one page per chunk.  A wrapped chunk = chunk meta bytes + page bytes, i.e. a
+// standalone chunk without its 4-byte preamble, so the compressor handle holds one CHUNKS_ONLY chunk and the page
+// decoder re-frames meta + page as a one-chunk standalone file for the same kernels.
+// ---------------------------------------------------------------------------
+struct PcoB200ChunkCompressor {
+  std::vector<uint8_t> bytes;  // [type byte][n - 1 (24 bits)][chunk meta][page]
+  size_t meta_len = 0;
+  size_t n = 0;
+};
+
+namespace {
+// Byte length of a chunk meta (metadata/chunk.rs:127-189, delta_encoding.rs, chunk_latent_var.rs:55-71) read from host bytes.
+// Only what the GPU path writes/reads is accepted: Classic / IntMult / FloatMult / FloatQuant, delta None / Consecutive.
+PcoB200Error host_chunk_meta_len(const uint8_t* b, size_t len, uint32_t dtype, size_t* out) {
+  const uint32_t lbits = nt_bits(dtype);
+  uint64_t pos = 0;
+  bool short_read = false;
+  auto rd = [&](uint32_t nb) -> uint64_t {
+    uint64_t v = 0;
+    for (uint32_t i = 0; i < nb; i++) {
+      const uint64_t bit = pos + i;
+      if ((bit >> 3) >= len) { short_read = true; break; }
+      v |= uint64_t((b[bit >> 3] >> (bit & 7)) & 1) << i;
+    }
+    pos += nb;
+    return v;
+  };
+  const uint32_t mode = uint32_t(rd(4));
+  uint32_t n_vars = 2;
+  switch (mode) {
+    case MODE_CLASSIC: n_vars = 1; break;
+    case MODE_INT_MULT: case MODE_FLOAT_MULT: pos += lbits; break;
+    case MODE_FLOAT_QUANT: pos += 8; break;
+    default: return fail(PCO_B200_UNSUPPORTED, "wrapped chunk meta: mode outside the GPU hot path");
+  }
+  const uint32_t delta = uint32_t(rd(4));
+  if (delta == 1) pos += 4;  // order (3 bits) + secondary_uses_delta (1 bit)
+  else if (delta != 0) return fail(PCO_B200_UNSUPPORTED, "wrapped chunk meta: delta encoding outside the GPU hot path");
+  for (uint32_t v = 0; v < n_vars; v++) {
+    const uint32_t size_log = uint32_t(rd(4));
+    const uint32_t n_bins = uint32_t(rd(15));
+    pos += uint64_t(n_bins) * (size_log + lbits + offset_bits_bits(lbits));
+  }
+  if (short_read || (pos + 7) / 8 > len) return fail(PCO_B200_INSUFFICIENT_DATA, "chunk meta is cut short");
+  *out = size_t((pos + 7) / 8);
+  return PCO_B200_OK;
+}
+}  // namespace
+
+PcoB200Error pco_b200_file_compressor_write_header(void* dst, size_t dst_cap, size_t* n_written) {
+  if (dst_cap < 2) return fail(PCO_B200_IO, "failed to write whole buffer");
+  static_cast<uint8_t*>(dst)[0] = 4;  // FormatVersion { major: 4, minor: 1 } (metadata/format_version.rs:30-34,87-91)
+  static_cast<uint8_t*>(dst)[1] = 1;
+  if (n_written) *n_written = 2;
+  return PCO_B200_OK;
+}
+
+PcoB200Error pco_b200_file_decompressor_read_header(const void* src, size_t src_len, size_t* n_read) {
+  const uint8_t* b = static_cast<const uint8_t*>(src);
+  if (src_len < 1) return fail(PCO_B200_INSUFFICIENT_DATA, "empty wrapped header");
+  const uint8_t major = b[0];
+  if (major > 4) return fail(PCO_B200_CORRUPTION, "file's format version exceeds the max supported version");  // format_version.rs:60-72
+  size_t used = 1;
+  if (major >= 4) {  // the minor version byte exists from 4.0 on
+    if (src_len < 2) return fail(PCO_B200_INSUFFICIENT_DATA, "wrapped header is cut short");
+    used = 2;
+  }
+  if (major < 4) return fail(PCO_B200_UNSUPPORTED, "wrapped files older than format 4 are outside the GPU hot path");
+  if (n_read) *n_read = used;
+  return PCO_B200_OK;
+}
+
+PcoB200Error pco_b200_chunk_compressor_new(const void* nums, size_t n, unsigned char dtype, const PcoB200ChunkConfig* config,
+                                           PcoB200ChunkCompressor** out) {
+  if (!out) return fail(PCO_B200_INVALID_ARGUMENT, "null output handle");
+  *out = nullptr;
+  if (!nt_valid(dtype)) return fail(PCO_B200_INVALID_TYPE, "unknown number type byte: " + std::to_string(dtype));
+  if (n == 0) return fail(PCO_B200_INVALID_ARGUMENT, "cannot compress empty chunk");  // chunk_compressor.rs:113-127
+  PcoB200ChunkConfig cfg;
+  if (config) cfg = *config;
+  else { std::memset(&cfg, 0, sizeof(cfg)); cfg.compression_level = 8; }
+  std::vector<uint64_t> pages;
+  if (PcoB200Error e = n_per_page(cfg, n, &pages)) return e;
+  if (pages.size() != 1)
+    return fail(PCO_B200_UNSUPPORTED, "wrapped chunks with several pages (shared bins) are outside the GPU hot path; use one page per chunk");
+  auto cc = std::make_unique<PcoB200ChunkCompressor>();
+  cc->n = n;
+  cc->bytes.resize(pco_standalone_guarantee_file_size(n, dtype) + 64);
+  size_t written = 0;
+  if (PcoB200Error e = compress_dispatch(nums, n, dtype, &cfg, false, cc->bytes.data(), cc->bytes.size(), &written, nullptr, 0, nullptr,
+                                         PCO_B200_CHUNKS_ONLY, nullptr))
+    return e;
+  cc->bytes.resize(written);
+  if (written < 4) return fail(PCO_B200_CUDA, "compressor returned a truncated chunk");
+  if (PcoB200Error e = host_chunk_meta_len(cc->bytes.data() + 4, written - 4, dtype, &cc->meta_len)) return e;
+  *out = cc.release();
+  return PCO_B200_OK;
+}
+void pco_b200_chunk_compressor_free(PcoB200ChunkCompressor* cc) { delete cc; }
+size_t pco_b200_chunk_compressor_n_pages(const PcoB200ChunkCompressor* cc) { return cc ? 1 : 0; }
+size_t pco_b200_chunk_compressor_page_n(const PcoB200ChunkCompressor* cc, size_t page_idx) { return (cc && page_idx == 0) ? cc->n : 0; }
+size_t pco_b200_chunk_compressor_meta_size(const PcoB200ChunkCompressor* cc) { return cc ? cc->meta_len : 0; }
+size_t pco_b200_chunk_compressor_page_size(const PcoB200ChunkCompressor* cc, size_t page_idx) {
+  return (cc && page_idx == 0) ? cc->bytes.size() - 4 - cc->meta_len : 0;
+}
+PcoB200Error pco_b200_chunk_compressor_write_meta(const PcoB200ChunkCompressor* cc, void* dst, size_t dst_cap, size_t* n_written) {
+  if (!cc) return fail(PCO_B200_INVALID_ARGUMENT, "null chunk compressor");
+  if (dst_cap < cc->meta_len) return fail(PCO_B200_IO, "failed to write whole buffer");
+  std::memcpy(dst, cc->bytes.data() + 4, cc->meta_len);
+  if (n_written) *n_written = cc->meta_len;
+  return PCO_B200_OK;
+}
+PcoB200Error pco_b200_chunk_compressor_write_page(const PcoB200ChunkCompressor* cc, size_t page_idx, void* dst, size_t dst_cap, size_t* n_written) {
+  if (!cc) return fail(PCO_B200_INVALID_ARGUMENT, "null chunk compressor");
+  if (page_idx >= 1)  // chunk_compressor.rs:661-666
+    return fail(PCO_B200_INVALID_ARGUMENT, "page idx exceeds num pages (" + std::to_string(page_idx) + " >= 1)");
+  const size_t len = cc->bytes.size() - 4 - cc->meta_len;
+  if (dst_cap < len) return fail(PCO_B200_IO, "failed to write whole buffer");
+  std::memcpy(dst, cc->bytes.data() + 4 + cc->meta_len, len);
+  if (n_written) *n_written = len;
+  return PCO_B200_OK;
+}
+
+PcoB200Error pco_b200_chunk_meta_size(const void* src, size_t src_len, unsigned char dtype, size_t* meta_len) {
+  if (!nt_valid(dtype)) return fail(PCO_B200_INVALID_TYPE, "unknown number type byte: " + std::to_string(dtype));
+  size_t len = 0;
+  if (PcoB200Error e = host_chunk_meta_len(static_cast<const uint8_t*>(src), src_len, dtype, &len)) return e;
+  if (meta_len) *meta_len = len;
+  return PCO_B200_OK;
+}
+
+PcoB200Error pco_b200_page_decompress(const void* chunk_meta, size_t meta_len, const void* page, size_t page_len, size_t page_n,
+                                      unsigned char dtype, void* dst, size_t dst_len, PcoB200Progress* progress, size_t* bytes_read) {
+  if (!nt_valid(dtype)) return fail(PCO_B200_INVALID_TYPE, "unknown number type byte: " + std::to_string(dtype));
+  if (page_n == 0 || page_n > (size_t(1) << 24)) return fail(PCO_B200_INVALID_ARGUMENT, "page n out of range");
+  // PageDecompressor::read: dst must take whole batches or the rest of the page (page_decompressor.rs:200-206)
+  if (dst_len % BATCH_N != 0 && dst_len < page_n)
+    return fail(PCO_B200_INVALID_ARGUMENT, "num_dst's length must either be a multiple of 256 or be at least the count of numbers remaining");
+  // one-chunk standalone file around the same bytes: header | type byte | n - 1 | meta | page | terminator
+  std::vector<uint8_t> file = make_standalone_header(page_n, 0);
+  file.push_back(dtype);
+  const uint32_t nm1 = uint32_t(page_n - 1);
+  file.push_back(uint8_t(nm1)); file.push_back(uint8_t(nm1 >> 8)); file.push_back(uint8_t(nm1 >> 16));
+  const uint8_t* m = static_cast<const uint8_t*>(chunk_meta);
+  const uint8_t* p = static_cast<const uint8_t*>(page);
+  file.insert(file.end(), m, m + meta_len);
+  file.insert(file.end(), p, p + page_len);
+  file.push_back(0);
+  PcoB200Progress prog{0, 0};
+  if (PcoB200Error e = pco_b200_decompress_ex(file.data(), file.size(), dtype, dst, dst_len, &prog, nullptr, 0, 0, nullptr)) return e;
+  prog.finished = prog.n_processed >= page_n ? 1 : 0;
+  if (progress) *progress = prog;
+  if (bytes_read) *bytes_read = page_len;
+  return PCO_B200_OK;
+}
+
 #ifdef PCOB_DEC_TIMING
 // experiment builds only: read and reset the decode kernel's region timers
 int pco_b200_debug_dec_timing(unsigned long long* out16) {

@@ -1,0 +1,71 @@
+"""GPU parity tests for the wrapped API (one page per chunk): bytes equal the oracle's ChunkCompressor, pages decode both ways."""
+import numpy as np
+import pytest
+
+from tests.golden_generators import bits_view
+from tests.test_gpu_encode import _cfgs, _walk
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("dtype,mode,order", [(np.uint64, "classic", 1), (np.int32, "classic", 0), (np.float64, "float_mult", 2),
+                                              (np.float32, "float_quant", 0), (np.uint32, "int_mult", 1), (np.int16, "classic", 3)])
+def test_wrapped_chunk_bytes_equal_oracle_and_pages_decode(oracle, dtype, mode, order):
+    from pcodec_b200 import wrapped
+
+    n = 20000
+    x = _walk(dtype, n, seed=21)
+    if mode == "float_mult":
+        x = (np.round(np.cumsum(np.random.default_rng(1).normal(size=n)) * 100) * 0.01).astype(dtype)
+    if mode == "int_mult":
+        x = (x.astype(np.uint64) // 8 * 8 + 3).astype(dtype)
+    ours_cfg, their_cfg = _cfgs(oracle, mode=mode, order=order, max_page_n=1 << 18)
+    fc = wrapped.FileCompressor()
+    assert fc.write_header() == bytes([4, 1])
+    cc = fc.chunk_compressor(x, ours_cfg)
+    occ = oracle.ChunkCompressor(x, their_cfg)
+    assert cc.n_per_page() == occ.n_per_page() == [n]
+    meta, page = cc.write_meta(), cc.write_page(0)
+    assert meta == occ.write_meta()
+    assert page == occ.write_page(0)
+    # the oracle decodes our page; our page decoder decodes it too, through the reference-shaped handles
+    got, mc, pc = oracle.wrapped_decompress_page(meta, page, dtype, n)
+    assert mc == len(meta) and pc == len(page)
+    np.testing.assert_array_equal(bits_view(got), bits_view(x))
+    stream = fc.write_header() + meta + page
+    fd, used = wrapped.FileDecompressor.new(stream)
+    assert used == 2
+    cd, mused = fd.chunk_decompressor(stream[used:], dtype)
+    assert mused == len(meta)
+    dst = np.zeros(n, dtype=dtype)
+    prog, pused = cd.read_page_into(stream[used + mused:], n, dst)
+    assert prog.finished and prog.n_processed == n and pused == len(page)
+    np.testing.assert_array_equal(bits_view(dst), bits_view(x))
+
+
+def test_wrapped_errors(oracle):
+    from pcodec_b200 import ChunkConfig, DeltaSpec, ModeSpec, PagingSpec, PcoError, wrapped
+
+    x = np.arange(3000, dtype=np.uint32)
+    fc = wrapped.FileCompressor()
+    cfg = ChunkConfig(mode_spec=ModeSpec.classic(), delta_spec=DeltaSpec.no_op(), paging_spec=PagingSpec.equal_pages_up_to(1000))
+    with pytest.raises(PcoError) as e:
+        fc.chunk_compressor(x, cfg)  # three pages sharing bins: not on the GPU path yet
+    assert e.value.kind == "Unsupported"
+    cc = fc.chunk_compressor(x, ChunkConfig(mode_spec=ModeSpec.classic(), delta_spec=DeltaSpec.no_op()))
+    with pytest.raises(PcoError) as e:
+        cc.write_page(1)  # chunk_compressor.rs:661-666
+    assert e.value.kind == "InvalidArgument"
+    with pytest.raises(PcoError) as e:
+        wrapped.FileDecompressor.new(bytes([9, 0]))
+    assert e.value.kind == "Corruption"
+    # PageDecompressor::read's dst rule (page_decompressor.rs:200-206)
+    meta, page = cc.write_meta(), cc.write_page(0)
+    cd, _ = wrapped.FileDecompressor().chunk_decompressor(meta, np.uint32)
+    with pytest.raises(PcoError) as e:
+        cd.read_page_into(page, 3000, np.zeros(1000, dtype=np.uint32))
+    assert e.value.kind == "InvalidArgument"
+    dst = np.zeros(1024, dtype=np.uint32)
+    prog, _ = cd.read_page_into(page, 3000, dst)
+    assert prog.n_processed == 1024 and not prog.finished
+    np.testing.assert_array_equal(dst, x[:1024])
