@@ -11,7 +11,7 @@
 namespace pcob200 {
 
 struct CompressScratch {
-  DevBuf lat0, lat1, keys_a, keys_b, sym0, sym1, ans0, ans1, ob_sum, ans_sum, entries, plans, chunks, starts, seg, cub_tmp, out, small, index, probes, sample, sample_starts;
+  DevBuf lat0, lat1, keys_a, keys_b, sym0, sym1, ans0, ans1, ob_sum, ans_sum, entries, plans, chunks, starts, seg, cub_tmp, out, small, index, probes, sample, sample_starts, key16_0, key16_1;
 };
 
 // pco/src/wrapped/chunk_compressor.rs:362-371
@@ -290,7 +290,9 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
         // small key range (the usual case once the chunk minimum is subtracted): counting histogram, no sort
         const size_t smem = ((size_t(1) << range_bits) + 1) * 4 + 16;
         profiler().begin("plan_probe_kernel_counting", stream);
-        plan_probe_kernel<L, true><<<n_chunks, PLAN_THREADS, smem, stream>>>(e, d_lat[v], d_chunks, d_probes, int(v), range_bits);
+        PCOB_CUDA_TRY((v == 0 ? S.key16_0 : S.key16_1).reserve(slots * 2 + 64));
+      plan_probe_kernel<L, true><<<n_chunks, PLAN_THREADS, smem, stream>>>(e, d_lat[v], d_chunks, d_probes, int(v), range_bits,
+                                                                            (v == 0 ? S.key16_0 : S.key16_1).as<uint16_t>());
         profiler().end(stream);
         profiler().begin("plan_solve_kernel", stream);
         plan_solve_kernel<L><<<n_chunks, SOLVE_THREADS, 0, stream>>>(e, d_probes, d_chunks, d_plans, int(v));
@@ -320,7 +322,7 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
         sorted = db.Current();
       }
       profiler().begin("plan_probe_kernel_sorted", stream);
-      plan_probe_kernel<L, false><<<n_chunks, PLAN_THREADS, 16, stream>>>(e, sorted, d_chunks, d_probes, int(v), range_bits);
+      plan_probe_kernel<L, false><<<n_chunks, PLAN_THREADS, 16, stream>>>(e, sorted, d_chunks, d_probes, int(v), range_bits, nullptr);
       profiler().end(stream);
       profiler().begin("plan_solve_kernel", stream);
       plan_solve_kernel<L><<<n_chunks, SOLVE_THREADS, 0, stream>>>(e, d_probes, d_chunks, d_plans, int(v));
@@ -380,7 +382,7 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
     if (var_range_bits[v] <= PLAN_MAX_COUNT_BITS) {
       const uint32_t parts = (bpc + BINL_BATCHES - 1) / BINL_BATCHES;
       profiler().begin("bin_lut_kernel", stream);
-      bin_lut_kernel<L><<<n_chunks * parts, BINL_THREADS, (size_t(1) << var_range_bits[v]) + 16, stream>>>(ep, bpc, parts, d_lat[v], d_plans, d_chunks, d_sym[v],
+      bin_lut_kernel<L><<<n_chunks * parts, BINL_THREADS, (size_t(1) << var_range_bits[v]) + 16, stream>>>(ep, bpc, parts, (v == 0 ? S.key16_0 : S.key16_1).as<uint16_t>(), d_plans, d_chunks, d_sym[v],
                                                                                                            S.ob_sum.as<uint32_t>(), int(v), var_range_bits[v]);
       profiler().end(stream);
       continue;
@@ -411,7 +413,9 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
   }
   profiler().begin("pack_kernel", stream);
   pack_kernel<L><<<n_chunks, PACK_THREADS, sizeof(PackSmem), stream>>>(ep, bpc, d_lat[0], d_lat[1], d_plans, d_chunks, d_sym[0], d_sym[1], d_ans[0], d_ans[1],
-                                                                      S.entries.as<BatchEntry>(), d_out, total);
+                                                                      S.entries.as<BatchEntry>(), d_out, total,
+                                                                      var_range_bits[0] <= PLAN_MAX_COUNT_BITS ? S.key16_0.as<uint16_t>() : nullptr,
+                                                                      (ep.n_vars > 1 && var_range_bits[1] <= PLAN_MAX_COUNT_BITS) ? S.key16_1.as<uint16_t>() : nullptr);
   profiler().end(stream);
   if (!chunks_only) header_footer_kernel<<<1, 32, 0, stream>>>(d_out, total, d_header, uint32_t(header.size()), d_total);
   PCOB_CUDA_TRY(cudaGetLastError());

@@ -406,7 +406,8 @@ struct PlanSmem {
 //                   cumulative counts -- the planner only ever needs order statistics, never the sorted array.
 template <typename L, bool COUNTING>
 __global__ void __launch_bounds__(PLAN_THREADS) plan_probe_kernel(EncParams ep, const L* __restrict__ keys, const ChunkEnc* __restrict__ chunks,
-                                                                   PlanProbes* __restrict__ probes, int v, uint32_t range_bits) {
+                                                                   PlanProbes* __restrict__ probes, int v, uint32_t range_bits,
+                                                                   uint16_t* __restrict__ keys16) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* cum = reinterpret_cast<uint32_t*>(smem_raw);  // COUNTING: 2^range_bits + 1 entries
   __shared__ uint32_t scan_part[PLAN_THREADS / 32];
@@ -424,15 +425,35 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_probe_kernel(EncParams ep, 
     for (uint32_t i = tid; i <= n_vals; i += PLAN_THREADS) cum[i] = 0;
     __syncthreads();
     {
-      uint32_t i = tid;
-      for (; i + 3 * PLAN_THREADS < n; i += 4 * PLAN_THREADS) {  // four loads in flight per thread
-        const L a0 = s[i], a1 = s[i + PLAN_THREADS], a2 = s[i + 2 * PLAN_THREADS], a3 = s[i + 3 * PLAN_THREADS];
-        atomicAdd(&cum[uint32_t(L(a0 - mn))], 1u);
-        atomicAdd(&cum[uint32_t(L(a1 - mn))], 1u);
-        atomicAdd(&cum[uint32_t(L(a2 - mn))], 1u);
-        atomicAdd(&cum[uint32_t(L(a3 - mn))], 1u);
+      // COUNTING also leaves the keys behind as 16 bits each (range < 2^15): binning and packing then read a quarter of
+      // the bytes of the 64-bit latents
+      uint16_t* k16 = keys16 + ep.row_base[c];
+      // 4 consecutive latents per thread and step (rows are 256-aligned): vector loads in, one 8-byte store of keys out
+      struct alignas(sizeof(L) * 4 > 16 ? 16 : sizeof(L) * 4) Vec4 { L v[4]; };
+      const uint32_t n4 = n / 4;
+      uint32_t q = tid;
+      for (; q + PLAN_THREADS < n4; q += 2 * PLAN_THREADS) {  // two vectors in flight per thread
+        const Vec4 a = *reinterpret_cast<const Vec4*>(s + 4 * size_t(q)), b = *reinterpret_cast<const Vec4*>(s + 4 * size_t(q + PLAN_THREADS));
+        uint32_t ka[4], kb[4];
+#pragma unroll
+        for (int t = 0; t < 4; t++) { ka[t] = uint32_t(L(a.v[t] - mn)); kb[t] = uint32_t(L(b.v[t] - mn)); }
+#pragma unroll
+        for (int t = 0; t < 4; t++) { atomicAdd(&cum[ka[t]], 1u); atomicAdd(&cum[kb[t]], 1u); }
+        *reinterpret_cast<uint2*>(k16 + 4 * size_t(q)) = make_uint2(ka[0] | (ka[1] << 16), ka[2] | (ka[3] << 16));
+        *reinterpret_cast<uint2*>(k16 + 4 * size_t(q + PLAN_THREADS)) = make_uint2(kb[0] | (kb[1] << 16), kb[2] | (kb[3] << 16));
       }
-      for (; i < n; i += PLAN_THREADS) atomicAdd(&cum[uint32_t(L(s[i] - mn))], 1u);
+      for (; q < n4; q += PLAN_THREADS) {
+        const Vec4 a = *reinterpret_cast<const Vec4*>(s + 4 * size_t(q));
+        uint32_t ka[4];
+#pragma unroll
+        for (int t = 0; t < 4; t++) { ka[t] = uint32_t(L(a.v[t] - mn)); atomicAdd(&cum[ka[t]], 1u); }
+        *reinterpret_cast<uint2*>(k16 + 4 * size_t(q)) = make_uint2(ka[0] | (ka[1] << 16), ka[2] | (ka[3] << 16));
+      }
+      for (uint32_t i = 4 * n4 + tid; i < n; i += PLAN_THREADS) {
+        const uint32_t k = uint32_t(L(s[i] - mn));
+        atomicAdd(&cum[k], 1u);
+        k16[i] = uint16_t(k);
+      }
     }
     __syncthreads();
     ENC_TICK(0);  // zero + count
@@ -917,9 +938,10 @@ constexpr int BINL_THREADS = 256;
 constexpr int BINL_BATCHES = 128;
 
 template <typename L>
-__global__ void __launch_bounds__(BINL_THREADS) bin_lut_kernel(EncParams ep, uint32_t batches_per_chunk, uint32_t parts_per_chunk, const L* __restrict__ lat,
-                                                                const VarPlan* __restrict__ plans, const ChunkEnc* __restrict__ chunks,
-                                                                uint8_t* __restrict__ sym, uint32_t* __restrict__ ob_sum, int v, uint32_t range_bits) {
+__global__ void __launch_bounds__(BINL_THREADS) bin_lut_kernel(EncParams ep, uint32_t batches_per_chunk, uint32_t parts_per_chunk,
+                                                                const uint16_t* __restrict__ keys16, const VarPlan* __restrict__ plans,
+                                                                const ChunkEnc* __restrict__ chunks, uint8_t* __restrict__ sym,
+                                                                uint32_t* __restrict__ ob_sum, int v, uint32_t range_bits) {
   extern __shared__ __align__(16) unsigned char binl_smem[];
   uint32_t* lut_w = reinterpret_cast<uint32_t*>(binl_smem);  // 2^range_bits bytes, 4 keys per word
   uint8_t* lut = binl_smem;
@@ -985,20 +1007,18 @@ __global__ void __launch_bounds__(BINL_THREADS) bin_lut_kernel(EncParams ep, uin
   }
   for (uint32_t b = b_begin + warp; b < b_end; b += BINL_THREADS / 32) {
     const uint32_t cnt = min(uint32_t(BATCH_N), n - b * BATCH_N);
-    const L* src = lat + rb + uint64_t(b) * BATCH_N;
-    uint8_t* row = sym + rb + uint64_t(b) * BATCH_N;
-    L x[8];
-#pragma unroll
-    for (int e = 0; e < 8; e++) x[e] = uint32_t(lane + 32 * e) < cnt ? src[lane + 32 * e] : vmin;
-    uint32_t bits = 0;
+    // the keys the counting planner left behind (latent - chunk minimum, 16 bits): a lane owns 8 consecutive ones
+    const uint4 k8 = *reinterpret_cast<const uint4*>(keys16 + rb + uint64_t(b) * BATCH_N + lane * 8);
+    const uint32_t kw[4] = {k8.x, k8.y, k8.z, k8.w};
+    uint32_t bits = 0, lo = 0, hi = 0;
 #pragma unroll
     for (int e = 0; e < 8; e++) {
-      const uint32_t sidx = lut[uint32_t(L(x[e] - vmin))];
-      if (uint32_t(lane + 32 * e) < cnt) {
-        bits += obs[sidx];
-        row[lane + 32 * e] = uint8_t(sidx);
-      }
+      const uint32_t key = (kw[e >> 1] >> (16 * (e & 1))) & (n_words * 4 - 1);  // past the batch's count: stale bits, kept in range
+      const uint32_t sidx = lut[key];
+      if (uint32_t(lane * 8 + e) < cnt) bits += obs[sidx];
+      if (e < 4) lo |= sidx << (8 * e); else hi |= sidx << (8 * (e - 4));
     }
+    *reinterpret_cast<uint2*>(sym + rb + uint64_t(b) * BATCH_N + lane * 8) = make_uint2(lo, hi);  // rows are 256-aligned and padded
     for (int d = 16; d > 0; d >>= 1) bits += __shfl_xor_sync(0xffffffffu, bits, d);
     if (lane == 0) sums[b] = bits;
   }
@@ -1329,6 +1349,7 @@ struct PackSmem {
   uint32_t win[PACK_WINDOW_WORDS + 4];
   uint64_t lowers[MAX_VARS][ENC_MAXB];
   uint8_t obs[MAX_VARS][ENC_MAXB];
+  uint32_t lowkey_ob[MAX_VARS][ENC_MAXB];  // 16-bit-key vars: (lower - chunk minimum) | offset_bits << 16
 };
 
 // OR `nbits` (<= 64) of `val` at bit position `pos` (relative to the window start) into the window
@@ -1398,7 +1419,8 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(EncParams ep, uint32
                                                              const VarPlan* __restrict__ plans, const ChunkEnc* __restrict__ chunks,
                                                              const uint8_t* __restrict__ sym0, const uint8_t* __restrict__ sym1,
                                                              const uint16_t* __restrict__ ans0, const uint16_t* __restrict__ ans1,
-                                                             const BatchEntry* __restrict__ entries, uint8_t* __restrict__ out, uint64_t out_cap) {
+                                                             const BatchEntry* __restrict__ entries, uint8_t* __restrict__ out, uint64_t out_cap,
+                                                             const uint16_t* __restrict__ key0, const uint16_t* __restrict__ key1) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   PackSmem& sm = *reinterpret_cast<PackSmem*>(smem_raw);
   const uint32_t c = blockIdx.x;
@@ -1420,6 +1442,8 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(EncParams ep, uint32
     for (uint32_t i = tid; i < n_bins; i += PACK_THREADS) {
       sm.lowers[v][i] = fb ? 0 : p.lower[i];
       sm.obs[v][i] = fb ? uint8_t(lbits) : p.ob[i];
+      // keys (key0/key1 non-null: the counting planner ran for this var) are latent - chunk minimum, so is this table
+      sm.lowkey_ob[v][i] = fb ? 0u : (uint32_t(L(L(p.lower[i]) - L(ch.vmin[v]))) & 0xffffu) | (uint32_t(p.ob[i]) << 16);
     }
   }
   // ---------------- head window: preamble + chunk meta + page meta ----------------
@@ -1547,7 +1571,31 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(EncParams ep, uint32
       const uint32_t ans_total = __shfl_sync(0xffffffffu, inc, 31);
       if (a_tot) emit8_narrow(sm.win, pos + inc - a_tot, a_val, a_bits);  // a field is <= size_log <= 10 bits
       // --- offsets (chunk_latent_compressor.rs:299-327)
-      if (max_ob > 0) {
+      const uint16_t* keyp = v == 0 ? key0 : key1;
+      if (max_ob > 0 && keyp != nullptr && !fb) {
+        // 16-bit keys: offset = key - (lower - minimum), all in 32 bits; offset_bits <= 15
+        const uint4 k8 = *reinterpret_cast<const uint4*>(keyp + rb + uint64_t(b) * BATCH_N + first);
+        const uint32_t kw[4] = {k8.x, k8.y, k8.z, k8.w};
+        uint32_t o_bits[8], o32[8], o_tot = 0;
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+          const uint32_t t = sm.lowkey_ob[v][sy[e]];
+          const bool live = first + e < cnt;
+          o_bits[e] = live ? t >> 16 : 0u;
+          o32[e] = live ? ((kw[e >> 1] >> (16 * (e & 1))) & 0xffffu) - (t & 0xffffu) : 0u;
+          o_tot += o_bits[e];
+        }
+        uint32_t oinc = o_tot;
+        for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, oinc, d); if (lane >= d) oinc += o; }
+        if (max_ob <= 12) {
+          if (o_tot) emit8_narrow(sm.win, pos + ans_total + oinc - o_tot, o32, o_bits);
+        } else {
+          BitAcc acc(sm.win, pos + ans_total + oinc - o_tot);
+#pragma unroll
+          for (int e = 0; e < 8; e++) acc.put(o32[e], o_bits[e]);
+          acc.flush();
+        }
+      } else if (max_ob > 0) {
         uint32_t o_bits[8], o_tot = 0;
         L o_val[8];
         if (fb) {
