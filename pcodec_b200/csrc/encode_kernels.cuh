@@ -1343,10 +1343,13 @@ __global__ void chunk_offsets_kernel(ChunkEnc* chunks, uint32_t n_chunks, uint64
 // window boundaries are carried in shared memory, so no global atomics or pre-zeroed output are needed.
 // ---------------------------------------------------------------------------
 constexpr int PACK_THREADS = 256;
+#ifndef PCOB_PACK_MIN_BLOCKS
+#define PCOB_PACK_MIN_BLOCKS 4
+#endif
 constexpr int PACK_WINDOW_WORDS = 8192;  // 32 KiB staging window
 
 struct PackSmem {
-  uint32_t win[PACK_WINDOW_WORDS + 4];
+  uint32_t win[PACK_WINDOW_WORDS + 8];
   uint64_t lowers[MAX_VARS][ENC_MAXB];
   uint8_t obs[MAX_VARS][ENC_MAXB];
   uint32_t lowkey_ob[MAX_VARS][ENC_MAXB];  // 16-bit-key vars: (lower - chunk minimum) | offset_bits << 16
@@ -1397,25 +1400,27 @@ struct BitAcc {
   }
 };
 
-// 8 consecutive fields of <= 12 bits each (already masked) at bit `pos` of the window: a 3-level concatenation tree in
-// registers (<= 96 bits), one shift to the word phase, then at most four 32-bit ORs into shared memory.
+// 8 consecutive fields of <= 15 bits each (already masked) at bit `pos` of the window: a 3-level concatenation tree in
+// registers (<= 120 bits), one shift to the word phase, then at most five 32-bit ORs into shared memory.
 __device__ __forceinline__ void emit8_narrow(uint32_t* win, uint32_t pos, const uint32_t (&v)[8], const uint32_t (&nb)[8]) {
   const uint32_t p0 = v[0] | (v[1] << nb[0]), p1 = v[2] | (v[3] << nb[2]), p2 = v[4] | (v[5] << nb[4]), p3 = v[6] | (v[7] << nb[6]);
-  const uint32_t l0 = nb[0] + nb[1], l1 = nb[2] + nb[3], l2 = nb[4] + nb[5];  // each <= 24
-  const uint64_t q0 = uint64_t(p0) | (uint64_t(p1) << l0), q1 = uint64_t(p2) | (uint64_t(p3) << l2);  // each <= 48 bits
-  const uint32_t m0 = l0 + l1;                                                                         // <= 48
+  const uint32_t l0 = nb[0] + nb[1], l1 = nb[2] + nb[3], l2 = nb[4] + nb[5];  // each <= 30
+  const uint64_t q0 = uint64_t(p0) | (uint64_t(p1) << l0), q1 = uint64_t(p2) | (uint64_t(p3) << l2);  // each <= 60 bits
+  const uint32_t m0 = l0 + l1;                                                                         // <= 60
   const uint64_t lo = q0 | (q1 << m0), hi = (q1 >> 1) >> (63 - m0);
   const uint32_t r = pos & 31, w = pos >> 5;
   const uint32_t x0 = uint32_t(lo), x1 = uint32_t(lo >> 32), x2 = uint32_t(hi), x3 = uint32_t(hi >> 32);
   const uint32_t w0 = x0 << r, w1 = __funnelshift_l(x0, x1, r), w2 = __funnelshift_l(x1, x2, r), w3 = __funnelshift_l(x2, x3, r);
+  const uint32_t w4 = __funnelshift_l(x3, 0u, r);
   if (w0) atomicOr(&win[w], w0);
   if (w1) atomicOr(&win[w + 1], w1);
   if (w2) atomicOr(&win[w + 2], w2);
   if (w3) atomicOr(&win[w + 3], w3);
+  if (w4) atomicOr(&win[w + 4], w4);
 }
 
 template <typename L>
-__global__ void __launch_bounds__(PACK_THREADS) pack_kernel(EncParams ep, uint32_t batches_per_chunk, const L* __restrict__ lat0, const L* __restrict__ lat1,
+__global__ void __launch_bounds__(PACK_THREADS, PCOB_PACK_MIN_BLOCKS) pack_kernel(EncParams ep, uint32_t batches_per_chunk, const L* __restrict__ lat0, const L* __restrict__ lat1,
                                                              const VarPlan* __restrict__ plans, const ChunkEnc* __restrict__ chunks,
                                                              const uint8_t* __restrict__ sym0, const uint8_t* __restrict__ sym1,
                                                              const uint16_t* __restrict__ ans0, const uint16_t* __restrict__ ans1,
@@ -1494,64 +1499,87 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(EncParams ep, uint32
   }
   __syncthreads();
   // ---------------- body: windows of whole batches ----------------
+  // Window words mirror the destination's 4-byte words: stream bit X of the chunk sits at P(X) = X + skew from the
+  // aligned-down chunk address, windows start on multiples of 32 in P, and finished words leave as 32-bit stores
+  // (the chunk's first and last body words, which share bytes with the head / the next chunk, byte by byte).
   const uint64_t body_bit0 = uint64_t(head_bytes) * 8;
   const uint64_t body_end = body_bit0 + ch.body_bits;
+  const uint32_t dst_mis = uint32_t(reinterpret_cast<uintptr_t>(dst) & 3);
+  const uint64_t skew = 8ull * dst_mis;
+  uint32_t* const dst_words = reinterpret_cast<uint32_t*>(dst - dst_mis);
+  const uint64_t lo_byte = (body_bit0 + skew) / 8, hi_byte = (body_end + skew + 7) / 8;  // body bytes, in P
   auto entry_pos = [&](uint32_t b, uint32_t v) -> uint64_t {
-    return entries[(size_t(c) * MAX_VARS + v) * batches_per_chunk + b].bit_pos;
+    return entries[(size_t(c) * MAX_VARS + v) * batches_per_chunk + b].bit_pos + skew;
   };
-  uint32_t carry_byte = 0;  // partially filled last byte of the previous window (only thread 0's copy is used)
   __shared__ uint32_t s_carry;
   if (tid == 0) s_carry = 0;
+  // per-var constants of the chunk
+  const uint64_t rb = ep.row_base[c];
+  const VarPlan& pl0 = plans[size_t(c) * MAX_VARS], &pl1 = plans[size_t(c) * MAX_VARS + (n_vars > 1 ? 1 : 0)];
+  const bool ans_0 = !fb && pl0.n_bins != 1 && pl0.size_log > 0, ans_1 = !fb && pl1.n_bins != 1 && pl1.size_log > 0;
+  const uint32_t mob_0 = fb ? lbits : pl0.max_ob, mob_1 = fb ? lbits : pl1.max_ob;
+  const uint32_t stored_0 = uint32_t(ce - (fb ? cs : stored_begin(cs, ce, order))), stored_1 = uint32_t(ce - cs);
+  const uint16_t* const keyp_0 = fb ? nullptr : key0;
+  const uint16_t* const keyp_1 = fb ? nullptr : key1;
   uint32_t b0 = 0;
-  uint64_t win_bit0 = body_bit0;  // multiple of 8
+  uint64_t win_p0 = (body_bit0 + skew) & ~uint64_t(31);
   while (b0 < nb) {
     // choose b1 > b0 so that [start(b0), end(b1 - 1)) fits the window; a single batch always fits (<= 2*256*78 bits)
     // (batch ends are monotone, so the batches that still fit form a prefix: every thread probes one candidate per round)
     uint32_t b1 = b0 + 1;
-    const uint64_t win_cap_bits = uint64_t(PACK_WINDOW_WORDS) * 32 - 64;
+    const uint64_t win_cap_bits = uint64_t(PACK_WINDOW_WORDS) * 32 - 96;
     for (;;) {
       const uint32_t cand = b1 + tid;
       bool fits = false;
       if (cand < nb) {
-        const uint64_t endb = (cand + 1 < nb) ? entry_pos(cand + 1, 0) : body_end;
-        fits = endb - win_bit0 <= win_cap_bits;
+        const uint64_t endb = (cand + 1 < nb) ? entry_pos(cand + 1, 0) : body_end + skew;
+        fits = endb - win_p0 <= win_cap_bits;
       }
       const uint32_t more = __syncthreads_count(fits ? 1 : 0);
       b1 += more;
       if (more < PACK_THREADS) break;
     }
-    const uint64_t win_end_bit = (b1 < nb) ? entry_pos(b1, 0) : body_end;
-    const uint32_t win_words = uint32_t((win_end_bit - win_bit0 + 31) / 32) + 1;
+    const uint64_t win_end_p = (b1 < nb) ? entry_pos(b1, 0) : body_end + skew;
+    const uint32_t win_words = uint32_t((win_end_p - win_p0 + 31) / 32) + 1;
     for (uint32_t i = tid; i < win_words; i += PACK_THREADS) sm.win[i] = 0;
     __syncthreads();
     if (tid == 0 && s_carry) sm.win[0] = s_carry;
     __syncthreads();
-    for (uint32_t bv = (b0 * n_vars) + warp; bv < b1 * n_vars; bv += PACK_THREADS / 32) {
-      const uint32_t b = bv / n_vars, v = bv % n_vars;
-      const VarPlan& p = plans[size_t(c) * MAX_VARS + v];
-      const uint32_t ord_v = v == 0 ? order : 0;
-      const uint64_t sb = fb ? cs : stored_begin(cs, ce, ord_v);
-      const uint32_t stored = uint32_t(ce - sb);
-      const uint32_t cnt = batch_count(stored, b);
+    // the next batch's vectors (8 symbols, 8 tANS fields, 8 keys per lane) are requested while this one is packed
+    const uint32_t bv_end = b1 * n_vars;
+    uint2 nx_s8 = make_uint2(0u, 0u);
+    uint4 nx_a8 = make_uint4(0u, 0u, 0u, 0u), nx_k8 = make_uint4(0u, 0u, 0u, 0u);
+    auto prefetch = [&](uint32_t bvn) {
+      const uint32_t bn = n_vars == 1 ? bvn : bvn / n_vars, vn = n_vars == 1 ? 0u : bvn % n_vars;
+      const uint64_t row = rb + uint64_t(bn) * BATCH_N + lane * 8;
+      nx_s8 = *reinterpret_cast<const uint2*>((vn == 0 ? sym0 : sym1) + row);
+      if (vn == 0 ? ans_0 : ans_1) nx_a8 = *reinterpret_cast<const uint4*>((vn == 0 ? ans0 : ans1) + row);
+      const uint16_t* kp = vn == 0 ? keyp_0 : keyp_1;
+      if (kp != nullptr) nx_k8 = *reinterpret_cast<const uint4*>(kp + row);
+    };
+    uint32_t bv = b0 * n_vars + warp;
+    if (bv < bv_end) prefetch(bv);
+    for (; bv < bv_end; bv += PACK_THREADS / 32) {
+      const uint32_t b = n_vars == 1 ? bv : bv / n_vars, v = n_vars == 1 ? 0u : bv % n_vars;
+      const uint2 s8 = nx_s8;
+      const uint4 a8 = nx_a8, k8 = nx_k8;
+      if (bv + PACK_THREADS / 32 < bv_end) prefetch(bv + PACK_THREADS / 32);
+      const uint32_t cnt = batch_count(v == 0 ? stored_0 : stored_1, b);
       if (cnt == 0) continue;
-      const bool needs_ans = !fb && p.n_bins != 1;
-      const uint32_t max_ob = fb ? lbits : p.max_ob;
-      const uint64_t rb = ep.row_base[c];
-      const uint8_t* symp = (v == 0 ? sym0 : sym1) + rb + uint64_t(b) * BATCH_N;
-      const uint16_t* ansp = (v == 0 ? ans0 : ans1) + rb + uint64_t(b) * BATCH_N;
+      const bool needs_ans = v == 0 ? ans_0 : ans_1;
+      const uint32_t max_ob = v == 0 ? mob_0 : mob_1;
+      const uint64_t sb = fb ? cs : stored_begin(cs, ce, v == 0 ? order : 0);
       const L* latp = (v == 0 ? lat0 : lat1) + rb + uint64_t(b) * BATCH_N;
-      uint32_t pos = uint32_t(entry_pos(b, v) - win_bit0);
+      uint32_t pos = uint32_t(entry_pos(b, v) - win_p0);
       // lane owns elements 8 lane .. 8 lane + 7: its fields are contiguous in the stream, so it assembles them in a
       // register and ORs whole 32-bit words into the window.  Rows are 256-aligned (split_delta_kernel): vector loads.
       const uint32_t first = lane * 8;
-      const uint2 s8 = *reinterpret_cast<const uint2*>(symp + first);
       uint32_t sy[8];
 #pragma unroll
       for (int e = 0; e < 8; e++) sy[e] = ((e < 4 ? s8.x : s8.y) >> (8 * (e & 3))) & 0xffu;
       // --- ANS fields (chunk_latent_compressor.rs:285-297)
       uint32_t a_val[8], a_bits[8], a_tot = 0;
-      if (needs_ans && p.size_log > 0) {
-        const uint4 a8 = *reinterpret_cast<const uint4*>(ansp + first);
+      if (needs_ans) {
         const uint32_t aw[4] = {a8.x, a8.y, a8.z, a8.w};
 #pragma unroll
         for (int e = 0; e < 8; e++) {
@@ -1571,10 +1599,8 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(EncParams ep, uint32
       const uint32_t ans_total = __shfl_sync(0xffffffffu, inc, 31);
       if (a_tot) emit8_narrow(sm.win, pos + inc - a_tot, a_val, a_bits);  // a field is <= size_log <= 10 bits
       // --- offsets (chunk_latent_compressor.rs:299-327)
-      const uint16_t* keyp = v == 0 ? key0 : key1;
-      if (max_ob > 0 && keyp != nullptr && !fb) {
+      if (max_ob > 0 && (v == 0 ? keyp_0 : keyp_1) != nullptr) {
         // 16-bit keys: offset = key - (lower - minimum), all in 32 bits; offset_bits <= 15
-        const uint4 k8 = *reinterpret_cast<const uint4*>(keyp + rb + uint64_t(b) * BATCH_N + first);
         const uint32_t kw[4] = {k8.x, k8.y, k8.z, k8.w};
         uint32_t o_bits[8], o32[8], o_tot = 0;
 #pragma unroll
@@ -1587,14 +1613,7 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(EncParams ep, uint32
         }
         uint32_t oinc = o_tot;
         for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, oinc, d); if (lane >= d) oinc += o; }
-        if (max_ob <= 12) {
-          if (o_tot) emit8_narrow(sm.win, pos + ans_total + oinc - o_tot, o32, o_bits);
-        } else {
-          BitAcc acc(sm.win, pos + ans_total + oinc - o_tot);
-#pragma unroll
-          for (int e = 0; e < 8; e++) acc.put(o32[e], o_bits[e]);
-          acc.flush();
-        }
+        if (o_tot) emit8_narrow(sm.win, pos + ans_total + oinc - o_tot, o32, o_bits);  // a key-path offset is <= 15 bits
       } else if (max_ob > 0) {
         uint32_t o_bits[8], o_tot = 0;
         L o_val[8];
@@ -1615,7 +1634,7 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(EncParams ep, uint32
         }
         uint32_t oinc = o_tot;
         for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, oinc, d); if (lane >= d) oinc += o; }
-        if (max_ob <= 12) {
+        if (max_ob <= 15) {
           uint32_t o32[8];
 #pragma unroll
           for (int e = 0; e < 8; e++) o32[e] = uint32_t(o_val[e]);
@@ -1636,19 +1655,27 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(EncParams ep, uint32
       }
     }
     __syncthreads();
-    // copy out whole bytes; the last partial byte (if any) carries into the next window
-    const uint64_t span_bits = win_end_bit - win_bit0;
-    const uint32_t whole_bytes = (b1 < nb) ? uint32_t(span_bits / 8) : uint32_t((span_bits + 7) / 8);
+    // copy out whole words; a partially filled last word carries into the next window
+    const uint64_t span_bits = win_end_p - win_p0;
+    const uint32_t whole_words = (b1 < nb) ? uint32_t(span_bits / 32) : uint32_t((span_bits + 31) / 32);
     {
-      const uint8_t* wb = reinterpret_cast<const uint8_t*>(sm.win);
-      uint8_t* d = dst + (win_bit0 / 8);
-      for (uint32_t i = tid; i < whole_bytes; i += PACK_THREADS) d[i] = wb[i];
-      if (tid == 0) s_carry = (b1 < nb && (span_bits & 7)) ? uint32_t(wb[whole_bytes]) : 0;
+      uint32_t* gw = dst_words + (win_p0 >> 5);
+      const uint64_t byte0 = win_p0 >> 3;
+      for (uint32_t i = tid; i < whole_words; i += PACK_THREADS) {
+        const uint64_t wb0 = byte0 + 4ull * i;
+        const uint32_t word = sm.win[i];
+        if (wb0 >= lo_byte && wb0 + 4 <= hi_byte) gw[i] = word;
+        else {
+          uint8_t* g8 = reinterpret_cast<uint8_t*>(gw + i);
+          for (uint32_t k = 0; k < 4; k++)
+            if (wb0 + k >= lo_byte && wb0 + k < hi_byte) g8[k] = uint8_t(word >> (8 * k));
+        }
+      }
+      if (tid == 0) s_carry = (b1 < nb && (span_bits & 31)) ? sm.win[whole_words] : 0;
     }
     __syncthreads();
-    win_bit0 += uint64_t(whole_bytes) * 8;
+    win_p0 += uint64_t(whole_words) * 32;
     b0 = b1;
-    (void)carry_byte;
   }
 }
 
