@@ -112,6 +112,9 @@ PcoB200Error pco_b200_build_index(const void *compressed, size_t compressed_len,
  * CUDA events on the launching stream; pco_b200_profile_last returns "kernel=milliseconds;..." for the last call. */
 void pco_b200_profile_enable(int on);
 int pco_b200_profile_last(char *buf, size_t cap);
+/* counts8[k] = chunks of the last decode launch served by decode class k (1, 2: general kernel with 1 / 2 latent vars;
+ * 3, 4: narrow kernel, delta order 0 / 1); returns the number of chunks. */
+int pco_b200_profile_chunk_classes(unsigned *counts8);
 
 /* ---- wrapped format (pco/src/wrapped/: FileCompressor / ChunkCompressor / FileDecompressor / ChunkDecompressor /
  * PageDecompressor), for callers that keep chunk metadata and pages in their own container.  This round: ONE page per

@@ -114,6 +114,23 @@ __host__ __device__ inline uint64_t scratch_row0(uint64_t out_offset, uint32_t t
 __host__ __device__ inline uint64_t scratch_rows_total(uint64_t out_len, uint32_t n_tasks) { return uint64_t(MAX_VARS) * (out_len / BATCH_N + n_tasks + 1); }
 
 // ---------------------------------------------------------------------------
+// Chunk classes: symwalk_kernel parses and validates every chunk header anyway, so it also decides which decode
+// instantiation owns the chunk (d_cls, one byte per chunk): 1 / 2 = decode_kernel<L, 1 / 2> (any refusal is reported
+// by decode_kernel<L, 1>), 3 / 4 = decode_narrow_kernel (decode_narrow.cuh) with delta order 0 / 1.
+// ---------------------------------------------------------------------------
+constexpr uint32_t CLS_NARROW0 = 3, CLS_NARROW1 = 4;
+constexpr uint32_t NARROW_MAX_OB = 15, NARROW_LOW_BITS = 16;
+
+struct NarrowInfo {   // one per chunk, in HBM scratch; only written for chunks of a narrow class
+  uint64_t base;      // lower of bin 0 (+ MID when the var is delta'd: folds toggle_center into the add)
+  uint64_t moment0;   // the page's delta moment (order 1)
+  uint32_t n;
+  uint32_t pad[3];
+  uint32_t q[SMALL_MAX_BINS];  // offset_bits | (lower - lower_0) << 7
+};
+static_assert(sizeof(NarrowInfo) % 16 == 0, "NarrowInfo rows are loaded with vector accesses");
+
+// ---------------------------------------------------------------------------
 // Cooperative table build for one latent var (all threads of the CTA call this).
 // WALKER = true stores offset_bits in the node field; false stores the bin index.
 // ---------------------------------------------------------------------------
@@ -722,10 +739,31 @@ __device__ __forceinline__ void load8(const L* __restrict__ src, L (&r)[8]) {
 // ---------------------------------------------------------------------------
 constexpr int SW_THREADS = 128;
 constexpr int SW_WARPS = SW_THREADS / 32;
-constexpr int SW_STAGE_BYTES = 13312;
+#ifndef PCOB_SW_STAGE_BYTES
+#define PCOB_SW_STAGE_BYTES 13312
+#endif
+// per warp.  The stage holds the whole span of the stream that a pass's batches cover - their offsets sections lie
+// between the tANS sections - so 13 KiB takes 32 batches of <= 13 bits per number in one pass (measured: 6.5 KiB stages
+// give 5 CTAs per SM but two half-empty passes per group on the C2 data: 0.41 ms instead of 0.31 ms)
+#ifdef PCOB_SW_ROWS
+// Row staging: every lane keeps a private row with the bytes its next PCOB_SW_ROWS symbols can read (<= 10 bits each,
+// + 16 bytes of start alignment + the window's over-read), refilled with 16-byte cp.async from its exact position.
+// Nothing but tANS bits is staged, so a warp needs 32 rows instead of the whole span of its 32 batches.
+constexpr int SW_ROW_SYMS = PCOB_SW_ROWS;
+constexpr int SW_ROW_BLOCKS = ((SW_ROW_SYMS * SMALL_MAX_SIZE_LOG / 8 + 15) / 16 + 2) | 1;  // odd: rows start in different banks
+constexpr int SW_STAGE_BYTES = 32 * SW_ROW_BLOCKS * 16;
+#else
+constexpr int SW_STAGE_BYTES = PCOB_SW_STAGE_BYTES;
+#endif
 constexpr int SW_STAGE_WORDS = SW_STAGE_BYTES / 4;
-constexpr int SW_NODE_WORDS = 2048;   // decoder nodes per CTA, replicated when the tables are small (see below)
-constexpr int SW_SLAB = 64;           // symbols per tile flush
+#ifndef PCOB_SW_NODE_WORDS
+#define PCOB_SW_NODE_WORDS 2048
+#endif
+#ifndef PCOB_SW_SLAB
+#define PCOB_SW_SLAB 64
+#endif
+constexpr int SW_NODE_WORDS = PCOB_SW_NODE_WORDS;   // decoder nodes per CTA, replicated when the tables are small (see below)
+constexpr int SW_SLAB = PCOB_SW_SLAB; // symbols per tile flush
 constexpr int SW_TILE_ROW = SW_SLAB / 4 + 1;  // words per tile row (odd: conflict-free rows)
 
 // 32 lanes look up 32 unrelated states per step.  A var's node table is stored R times when it is small, copy r
@@ -734,6 +772,7 @@ struct SymWalkSmem {
   ChunkHdr hdr;
   uint32_t node[SW_NODE_WORDS];
   uint32_t err;
+  uint32_t not_narrow;
   union {
     struct {
       BuildScratch build;
@@ -748,7 +787,7 @@ struct SymWalkSmem {
 
 __global__ void __launch_bounds__(SW_THREADS) symwalk_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, const uint8_t* __restrict__ index_base,
                                                               uint64_t out_len, uint8_t* __restrict__ d_syms, uint32_t* __restrict__ d_offs,
-                                                              uint8_t* __restrict__ d_nvars) {
+                                                              uint8_t* __restrict__ d_nvars, NarrowInfo* __restrict__ d_narrow) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SymWalkSmem& sm = *reinterpret_cast<SymWalkSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -760,6 +799,7 @@ __global__ void __launch_bounds__(SW_THREADS) symwalk_kernel(FileParams fp, cons
   // every refusal below is reported by decode_kernel, which parses the same header
   if (tid == 0) {
     sm.err = 0;
+    sm.not_narrow = 0;
     parse_chunk_header(src, chunk_bit0, fp.dtype, fp.uniform_type, fp.format_major, true, sm.hdr);
     if (sm.hdr.status == ST_OK) {
       for (uint32_t v = 0; v < sm.hdr.n_vars; v++) {
@@ -782,6 +822,29 @@ __global__ void __launch_bounds__(SW_THREADS) symwalk_kernel(FileParams fp, cons
                             sm.b.build.bin_cum[v], sm.b.build.sym_of_state[v], sm.b.build.rank_counter[v], &sm.err, false);
   __syncthreads();
   if (sm.err) return;
+#ifndef PCOB_NO_NARROW
+  // narrow class (decode_narrow.cuh): the header and bins are parsed and validated at this point
+  if (d_narrow && n_vars == 1 && sm.hdr.mode == MODE_CLASSIC && sm.hdr.var[0].delta_order <= 1 && sm.hdr.var[0].latent_bits >= 32 &&
+      sm.hdr.var[0].n_bins >= 2 && sm.hdr.var[0].max_offset_bits <= NARROW_MAX_OB) {
+    const VarHdr& vh = sm.hdr.var[0];
+    const uint64_t lmask = vh.latent_bits == 64 ? ~uint64_t(0) : ((uint64_t(1) << vh.latent_bits) - 1);
+    const uint64_t lower0 = sm.b.build.bin_lower[0][0];
+    NarrowInfo* ni = d_narrow + blockIdx.x;
+    for (uint32_t i = tid; i < vh.n_bins; i += SW_THREADS) {
+      const uint64_t d = (sm.b.build.bin_lower[0][i] - lower0) & lmask;
+      if (d >> NARROW_LOW_BITS) sm.not_narrow = 1;
+      ni->q[i] = uint32_t(sm.b.build.bin_ob[0][i]) | (uint32_t(d) << 7);
+    }
+    __syncthreads();
+    if (tid == 0 && !sm.not_narrow) {
+      const uint64_t mid = uint64_t(1) << (vh.latent_bits - 1);
+      ni->base = vh.delta_order ? ((lower0 + mid) & lmask) : lower0;
+      ni->moment0 = sm.hdr.moments[0][0];
+      ni->n = sm.hdr.n;
+      d_nvars[blockIdx.x] = uint8_t(vh.delta_order ? CLS_NARROW1 : CLS_NARROW0);
+    }
+  }
+#endif
   // replicate: var v owns SW_NODE_WORDS / n_vars words (>= its 2^size_log); rep_log = log2 of its copy count
   const uint32_t region = SW_NODE_WORDS / n_vars;
   const uint32_t rep_log0 = min(5u, uint32_t(31 - __clz(region >> sm.hdr.var[0].ans_size_log)));
@@ -821,6 +884,105 @@ __global__ void __launch_bounds__(SW_THREADS) symwalk_kernel(FileParams fp, cons
     const uint32_t* node = sm.node + v * region + (uint32_t(lane) & ((1u << rl) - 1));  // this lane's copy
     const uint32_t node_sa = smem_addr(node);
     const uint32_t sl = rl + 2;  // states are kept as byte offsets into the lane's copy
+#ifdef PCOB_SW_ROWS
+    {
+      // ---- row staging: all batches of the group are walked at once
+      const bool mine = uint32_t(lane) < nbg;
+      const uint32_t b = b0 + lane;
+      const int cnt = mine ? int(batch_count(stored, b)) : 0;
+      const uint32_t smask = (1u << size_log) - 1;
+      uint32_t s0 = min(uint32_t(e.st[0]), smask) << sl, s1 = min(uint32_t(e.st[1]), smask) << sl;
+      uint32_t s2 = min(uint32_t(e.st[2]), smask) << sl, s3 = min(uint32_t(e.st[3]), smask) << sl;
+      uint32_t* row = tile + lane * SW_TILE_ROW;
+      const uint32_t row_sa = smem_addr(row);
+      const uint32_t* rowp = stg + lane * (SW_ROW_BLOCKS * 4);
+      const uint32_t row_g = stg_sa + uint32_t(lane) * (SW_ROW_BLOCKS * 16);
+      uint8_t* sym_rows = d_syms + (row0 + size_t(v) * nb_out + b0) * BATCH_N;
+      uint64_t bit = min(chunk_bit0 + e.bit_pos, src.n_bits);
+      for (int part = 0; part < BATCH_N / SW_ROW_SYMS; part++) {
+        const uint64_t blk = bit >> 7;
+        if (cnt > part * SW_ROW_SYMS) {
+#pragma unroll
+          for (uint32_t q = 0; q < uint32_t(SW_ROW_BLOCKS); q++) {
+            const void* gp = reinterpret_cast<const ulonglong2*>(src.words) + min(blk + q, max_blk);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(row_g + q * 16), "l"(gp));
+          }
+        }
+        asm volatile("cp.async.commit_group;");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        uint32_t wpos = uint32_t(bit & 127);
+        uint32_t w = wpos >> 5;
+        uint32_t x0 = lds_u32(row_g + 4 * w), x1 = lds_u32(row_g + 4 * w + 4), x2 = lds_u32(row_g + 4 * w + 8);  // register window over the stream
+        for (int slab = part * (SW_ROW_SYMS / SW_SLAB); slab < (part + 1) * (SW_ROW_SYMS / SW_SLAB); slab++) {
+          const int i0 = slab * SW_SLAB;
+          if (size_log <= 8) {
+            // four symbols read <= 32 bits: one 32-bit window per group, fields by bit-field extract
+  #pragma unroll 4
+            for (int i = i0; i < i0 + SW_SLAB; i += 4) {
+              if (i + 4 <= cnt) {
+                const uint32_t n0 = lds_u32(node_sa + s0), n1 = lds_u32(node_sa + s1), n2 = lds_u32(node_sa + s2), n3 = lds_u32(node_sa + s3);
+                const uint32_t g = __funnelshift_r(x0, x1, wpos & 31);
+                const uint32_t c0 = node_btr(n0), c1 = node_btr(n1), c2 = node_btr(n2), c3 = node_btr(n3);
+                const uint32_t sh2 = c0 + c1, sh3 = sh2 + c2;
+                s0 = (node_base(n0) + (g & ((1u << c0) - 1))) << sl;
+                s1 = (node_base(n1) + ((g >> c0) & ((1u << c1) - 1))) << sl;
+                s2 = (node_base(n2) + ((g >> sh2) & ((1u << c2) - 1))) << sl;
+                s3 = (node_base(n3) + ((g >> sh3) & ((1u << c3) - 1))) << sl;
+                sts_u32(row_sa + (i - i0), node_fields4(n0, n1, n2, n3));
+                wpos += sh3 + c3;
+                if ((wpos >> 5) != w) { w = wpos >> 5; x0 = lds_u32(row_g + 4 * w); x1 = lds_u32(row_g + 4 * w + 4); }
+              }
+            }
+          } else {
+  #pragma unroll 2
+            for (int i = i0; i < i0 + SW_SLAB; i += 4) {
+              if (i + 4 <= cnt) {
+                const uint32_t n0 = lds_u32(node_sa + s0), n1 = lds_u32(node_sa + s1), n2 = lds_u32(node_sa + s2), n3 = lds_u32(node_sa + s3);
+                const uint32_t r = wpos & 31;
+                const uint64_t g = (uint64_t(__funnelshift_r(x1, x2, r)) << 32) | __funnelshift_r(x0, x1, r);
+                const uint32_t c0 = node_btr(n0), c1 = node_btr(n1), c2 = node_btr(n2), c3 = node_btr(n3);
+                const uint32_t sh2 = c0 + c1, sh3 = sh2 + c2;
+                s0 = (node_base(n0) + (uint32_t(g) & ((1u << c0) - 1))) << sl;
+                s1 = (node_base(n1) + (uint32_t(g >> c0) & ((1u << c1) - 1))) << sl;
+                s2 = (node_base(n2) + (uint32_t(g >> sh2) & ((1u << c2) - 1))) << sl;
+                s3 = (node_base(n3) + (uint32_t(g >> sh3) & ((1u << c3) - 1))) << sl;
+                sts_u32(row_sa + (i - i0), node_fields4(n0, n1, n2, n3));
+                wpos += sh3 + c3;
+                if ((wpos >> 5) != w) { w = wpos >> 5; x0 = lds_u32(row_g + 4 * w); x1 = lds_u32(row_g + 4 * w + 4); x2 = lds_u32(row_g + 4 * w + 8); }
+              }
+            }
+          }
+          if (cnt > i0 && cnt < i0 + SW_SLAB && (cnt & 3)) {  // ragged tail of the page's last batch (page_latent_decompressor.rs:144-177)
+            const int i = cnt & ~3;
+            uint32_t packed = 0;
+            uint32_t sarr[4] = {s0, s1, s2, s3};
+            for (int j = 0; i + j < cnt; j++) {
+              const uint32_t nn = lds_u32(node_sa + sarr[j]);
+              const uint32_t ww = wpos >> 5, r = wpos & 31;
+              const uint32_t val = __funnelshift_r(rowp[ww], rowp[ww + 1], r) & ((1u << node_btr(nn)) - 1);
+              packed |= node_field(nn) << (8 * j);
+              sarr[j] = (node_base(nn) + val) << sl;
+              wpos += node_btr(nn);
+            }
+            sts_u32(row_sa + (i - i0), packed);
+          }
+          __syncwarp();
+          // the slab of rows k0..k1 -> SW_SLAB-byte pieces of the 256-byte symbol rows (16 bytes per lane)
+          if (__any_sync(0xffffffffu, cnt > i0)) {
+            constexpr uint32_t SEGS = SW_SLAB / 16;  // 16-byte pieces per row and slab
+            for (uint32_t idx = lane; idx < nbg * SEGS; idx += 32) {
+              const uint32_t rr = idx / SEGS, seg = idx % SEGS;
+              const uint32_t* tp = tile + rr * SW_TILE_ROW + seg * 4;
+              *reinterpret_cast<uint4*>(sym_rows + size_t(rr) * BATCH_N + i0 + seg * 16) = make_uint4(tp[0], tp[1], tp[2], tp[3]);
+            }
+          }
+          __syncwarp();
+        }
+        bit = (blk << 7) + wpos;
+      }
+      if (mine) offs[b] = uint32_t(min(bit, src.n_bits) - chunk_bit0);
+    }
+#else
     uint32_t k0 = 0;  // batches [k0, k1) of the group are staged per pass
     while (k0 < nbg) {
       const uint64_t base_bit = (chunk_bit0 + __shfl_sync(0xffffffffu, e.bit_pos, int(k0))) & ~uint64_t(127);  // 16-byte block
@@ -830,7 +992,11 @@ __global__ void __launch_bounds__(SW_THREADS) symwalk_kernel(FileParams fp, cons
       const bool fits = uint32_t(lane) >= k0 && uint32_t(lane) < nbg && my_bit >= base_bit &&
                         my_bit + ans_max_bits + 64 <= base_bit + uint64_t(SW_STAGE_BYTES) * 8;
       const uint32_t fm = __ballot_sync(0xffffffffu, fits) >> k0;
-      const uint32_t npass = max(1u, uint32_t(__ffs(~fm) - 1));  // leading run of fitting lanes (>= 1 for a sane index)
+      uint32_t npass = max(1u, uint32_t(__ffs(~fm) - 1));  // leading run of fitting lanes (>= 1 for a sane index)
+      if (k0 + npass < nbg) {  // several passes: split the remaining batches evenly so that later passes keep their lanes busy
+        const uint32_t rem = nbg - k0, passes = (rem + npass - 1) / npass;
+        npass = (rem + passes - 1) / passes;
+      }
       const uint32_t k1 = min(nbg, k0 + npass);
       // bytes to stage: up to the start of the next batch after the pass (known from the index), else the whole stage
       uint64_t end_bit = base_bit + uint64_t(SW_STAGE_BYTES) * 8;
@@ -913,10 +1079,11 @@ __global__ void __launch_bounds__(SW_THREADS) symwalk_kernel(FileParams fp, cons
           sts_u32(row_sa + (i - i0), packed);
         }
         __syncwarp();
-        // the slab of rows k0..k1 -> 64-byte pieces of the 256-byte symbol rows (4 lanes x 16 bytes per row)
+        // the slab of rows k0..k1 -> SW_SLAB-byte pieces of the 256-byte symbol rows (16 bytes per lane)
         if (__any_sync(0xffffffffu, cnt > i0)) {
-          for (uint32_t idx = k0 * 4 + lane; idx < k1 * 4; idx += 32) {
-            const uint32_t rr = idx >> 2, seg = idx & 3;
+          constexpr uint32_t SEGS = SW_SLAB / 16;  // 16-byte pieces per row and slab
+          for (uint32_t idx = k0 * SEGS + lane; idx < k1 * SEGS; idx += 32) {
+            const uint32_t rr = idx / SEGS, seg = idx % SEGS;
             const uint32_t* tp = tile + rr * SW_TILE_ROW + seg * 4;
             *reinterpret_cast<uint4*>(sym_rows + size_t(rr) * BATCH_N + i0 + seg * 16) = make_uint4(tp[0], tp[1], tp[2], tp[3]);
           }
@@ -926,6 +1093,7 @@ __global__ void __launch_bounds__(SW_THREADS) symwalk_kernel(FileParams fp, cons
       if (mine) offs[b] = uint32_t(min(base_bit + wpos, src.n_bits) - chunk_bit0);
       k0 = k1;
     }
+#endif
   }
 }
 

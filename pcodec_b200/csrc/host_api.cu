@@ -5,6 +5,7 @@
 
 #include "compress_host.cuh"
 #include "decode_kernels.cuh"
+#include "decode_narrow.cuh"
 #include "host_common.hpp"
 
 namespace pcob200 {
@@ -14,10 +15,11 @@ struct Context {
   bool initialized = false;
   bool device_ok = false;
   std::string device_err;
-  DevBuf src, out, index, statuses, misc, dec_syms, dec_offs, dec_nvars;
+  DevBuf src, out, index, statuses, misc, dec_syms, dec_offs, dec_nvars, dec_narrow;
   CompressScratch enc;
   Binoms* d_binoms = nullptr;
   int sm_count = 0;
+  uint32_t last_decode_chunks = 0;  // chunks of the last decode launch (their class bytes are still in dec_nvars)
 };
 
 static Context& ctx() {
@@ -93,17 +95,26 @@ static PcoB200Error launch_decode(Context& c, const FileParams& fp, const uint8_
   PCOB_CUDA_TRY(c.dec_syms.reserve(rows * BATCH_N + 64));
   PCOB_CUDA_TRY(c.dec_offs.reserve(rows * sizeof(uint32_t) + 64));
   PCOB_CUDA_TRY(c.dec_nvars.reserve(size_t(n_chunks) + 64));
+  const bool narrow_ok = nt_bits(fp.dtype) >= 32;  // decode_narrow_kernel serves the 32- and 64-bit number types
+  if (narrow_ok) PCOB_CUDA_TRY(c.dec_narrow.reserve(size_t(n_chunks) * sizeof(NarrowInfo)));
   static bool attr_set = false;
   if (!attr_set) {
     attr_set = true;
     PCOB_CUDA_TRY(cudaFuncSetAttribute(symwalk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SymWalkSmem)));
     PCOB_CUDA_TRY(cudaFuncSetAttribute(symwalk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
   }
+  c.last_decode_chunks = n_chunks;
   profiler().begin("symwalk_kernel", stream);
   symwalk_kernel<<<n_chunks, SW_THREADS, sizeof(SymWalkSmem), stream>>>(fp, d_chunks, d_index, out_len, c.dec_syms.as<uint8_t>(), c.dec_offs.as<uint32_t>(),
-                                                                        c.dec_nvars.as<uint8_t>());
+                                                                        c.dec_nvars.as<uint8_t>(), narrow_ok ? c.dec_narrow.as<NarrowInfo>() : nullptr);
   profiler().end(stream);
-  profiler().begin("decode_kernel", stream);
+  profiler().begin("decode_kernel", stream);  // the span covers every decode instantiation (a chunk runs in exactly one)
+  if (nt_bits(fp.dtype) == 64)
+    decode_narrow_kernel<uint64_t><<<n_chunks, NW_THREADS, 0, stream>>>(fp, d_chunks, d_st, static_cast<uint64_t*>(d_out), out_len, c.dec_syms.as<uint8_t>(),
+                                                                      c.dec_offs.as<uint32_t>(), c.dec_nvars.as<uint8_t>(), c.dec_narrow.as<NarrowInfo>());
+  else if (nt_bits(fp.dtype) == 32)
+    decode_narrow_kernel<uint32_t><<<n_chunks, NW_THREADS, 0, stream>>>(fp, d_chunks, d_st, static_cast<uint32_t*>(d_out), out_len, c.dec_syms.as<uint8_t>(),
+                                                                      c.dec_offs.as<uint32_t>(), c.dec_nvars.as<uint8_t>(), c.dec_narrow.as<NarrowInfo>());
   dispatch_latent(fp.dtype, [&](auto tag) {
     using L = decltype(tag);
     decode_kernel<L, 1><<<n_chunks, DEC_THREADS, sizeof(DecodeSmem), stream>>>(fp, d_chunks, d_st, d_index, static_cast<L*>(d_out), out_len, c.d_binoms,
@@ -543,6 +554,18 @@ int pco_b200_debug_enc_timing(unsigned long long* out32) {
 #endif
 
 void pco_b200_profile_enable(int on) { profiler().enabled = on != 0; }
+// Which decode instantiation served the chunks of the last decode launch: counts[k] = chunks of class k
+// (1, 2: decode_kernel<L, 1 / 2>; 3, 4: decode_narrow_kernel order 0 / 1).  Returns the number of chunks.
+int pco_b200_profile_chunk_classes(unsigned* counts8) {
+  Context& c = ctx();
+  std::lock_guard<std::mutex> lock(c.mu);
+  for (int i = 0; i < 8; i++) counts8[i] = 0;
+  if (!c.device_ok || c.last_decode_chunks == 0 || !c.dec_nvars.p) return 0;
+  std::vector<uint8_t> cls(c.last_decode_chunks);
+  if (cudaMemcpy(cls.data(), c.dec_nvars.p, cls.size(), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  for (uint8_t k : cls) counts8[k < 8 ? k : 0]++;
+  return int(cls.size());
+}
 // Copies "name=ms;name=ms;..." of the last finished call into buf; returns the number of spans.
 int pco_b200_profile_last(char* buf, size_t cap) {
   std::string s;

@@ -17,4 +17,7 @@ buf = C.create_string_buffer(4096)
 for it in range(4):
     _lib.check(L.pco_b200_decompress_ex(C.c_void_p(d_comp.data_ptr()), nw, C.c_ubyte(2), C.c_void_p(d_out.data_ptr()), C.c_size_t(n), C.byref(prog), C.c_void_p(d_idx.data_ptr()), il, C.c_uint32(7), None))
     L.pco_b200_profile_last(buf, 4096)
-print(os.environ.get("PCOB200_LIB", "default"), "compressed", nw.value, buf.value.decode(), "exact" if torch.equal(d_out, nums) else "OUTPUT DIFFERS")
+cls = (C.c_uint * 8)()
+if hasattr(L, "pco_b200_profile_chunk_classes"): L.pco_b200_profile_chunk_classes(cls)
+print(os.path.basename(os.environ.get("PCOB200_LIB", "default")), "compressed", nw.value, buf.value.decode(), "classes", list(cls)[1:5],
+      "exact" if torch.equal(d_out, nums) else "OUTPUT DIFFERS")
