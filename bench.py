@@ -7,7 +7,7 @@ scaling (8 ranks = config 4's 8192 chunks).  MB = 10^6 uncompressed bytes (pco_c
 
   value     resident: inputs already in HBM, device buffers in and out, through the C-ABI (*_ex, flags DEVICE).
   e2e       same calls with pinned HOST buffers (H2D of the inputs and D2H of the results inside the timed region).
-  roofline  decompress kernels (symwalk_kernel + decode_kernel): (U + C + side index) bytes / their CUDA-event durations vs MEASURED_PEAKS.json hbm_gbs.
+  roofline  decompress kernels (symwalk_kernel + the decode kernels, decode_narrow_kernel on this data): (U + C + side index) bytes / their CUDA-event durations vs MEASURED_PEAKS.json hbm_gbs.
   cpu_baseline / --impl reference: oracle/ (C++ restatement of pco 1.0.3; the Rust reference cannot be built here)
             on the host cores, on a bounded sample of the same chunks.
 """
@@ -325,6 +325,13 @@ def run_gpu_arm(args, rank, world):
     dec_spans = {k: float(np.mean(v)) for k, v in dec_spans.items()}
     alg_bytes = U + Cbytes + Ibytes
     achieved = alg_bytes / 1e9 / (dk_ms / 1e3) if dk_ms > 0 else None
+    # DRAM traffic of the same two kernels from the committed `ncu --set full` capture (dram__bytes_read.sum +
+    # dram__bytes_write.sum per launch, same workload); never measured under this run
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath) and n_chunks == N_CHUNKS:
+        tj = json.load(open(tpath))
+        traffic, traffic_src = int(sum(tj["dram_bytes_per_launch"].values())), tj["source"]
     comp_spans = {}
     for p in prof_c:
         for k, v in p.items():
@@ -352,9 +359,12 @@ def run_gpu_arm(args, rank, world):
         "gather_ms": float(np.mean(t_g)), "compressed_bytes_per_gpu": Cbytes, "index_bytes_per_gpu": Ibytes, "ratio": U / Cbytes,
         "kernel_ms": {**dec_spans, **comp_spans},
         "roofline": {"bound": "hbm", "kernel": "decompress path: symwalk_kernel + decode_kernel (sum of both durations)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": None, "algorithmic_bytes": alg_bytes, "peak_source": peak_src},
+                     "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": alg_bytes,
+                     "peak_source": peak_src},
         "cpu_baseline": cpu, "e2e": e2e, "clocks": sampler.summary(),
-        "gpu_launches": 15,  # per step: 13 of this repo's kernels in compress, symwalk_kernel + decode_kernel in decompress
+        # per step: 13 of this repo's kernels in compress; decompress = symwalk_kernel + decode_narrow_kernel + decode_kernel<L,1> +
+        # decode_kernel<L,2> (every chunk is decoded by exactly one of the three decode launches; the others' CTAs exit at once)
+        "gpu_launches": 17,
     }
     print(json.dumps(line))
 

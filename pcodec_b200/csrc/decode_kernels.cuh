@@ -687,19 +687,32 @@ __device__ __forceinline__ void undelta_chain_cold(L (&x)[8], DecodeSmem& sm, ui
   for (int e = 0; e < 8; e++) x[e] = tmp[e];
 }
 
+// 8 consecutive numbers of a lane -> global memory.  32-byte stores (STG.E.ENL2.256, sm_100) when the destination allows:
+// with 16-byte stores every instruction of the warp fills half of 32 sectors, and the L1 was the busiest unit of the decode
+// kernels (81 % of peak in decode_narrow_kernel; 0.78 -> 0.58 ms with whole-sector stores).
 template <typename L>
 __device__ __forceinline__ void store8(L* __restrict__ dst, const L (&r)[8]) {
   if (sizeof(L) == 8) {
-    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    if ((reinterpret_cast<uintptr_t>(dst) & 31) == 0) {
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-      const uint64_t a = uint64_t(r[2 * q]), bb = uint64_t(r[2 * q + 1]);
-      d4[q] = make_uint4(uint32_t(a), uint32_t(a >> 32), uint32_t(bb), uint32_t(bb >> 32));
+      for (int q = 0; q < 2; q++)
+        asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * q), "l"(uint64_t(r[4 * q])), "l"(uint64_t(r[4 * q + 1])),
+                     "l"(uint64_t(r[4 * q + 2])), "l"(uint64_t(r[4 * q + 3])) : "memory");
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; q++)
+        asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(dst + 2 * q), "l"(uint64_t(r[2 * q])), "l"(uint64_t(r[2 * q + 1])) : "memory");
     }
   } else if (sizeof(L) == 4) {
-    uint4* d4 = reinterpret_cast<uint4*>(dst);
-    d4[0] = make_uint4(uint32_t(r[0]), uint32_t(r[1]), uint32_t(r[2]), uint32_t(r[3]));
-    d4[1] = make_uint4(uint32_t(r[4]), uint32_t(r[5]), uint32_t(r[6]), uint32_t(r[7]));
+    if ((reinterpret_cast<uintptr_t>(dst) & 31) == 0) {
+      asm volatile("st.global.v8.u32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(uint32_t(r[0])), "r"(uint32_t(r[1])), "r"(uint32_t(r[2])),
+                   "r"(uint32_t(r[3])), "r"(uint32_t(r[4])), "r"(uint32_t(r[5])), "r"(uint32_t(r[6])), "r"(uint32_t(r[7])) : "memory");
+    } else {
+#pragma unroll
+      for (int q = 0; q < 2; q++)
+        asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * q), "r"(uint32_t(r[4 * q])), "r"(uint32_t(r[4 * q + 1])),
+                     "r"(uint32_t(r[4 * q + 2])), "r"(uint32_t(r[4 * q + 3])) : "memory");
+    }
   } else {
 #pragma unroll
     for (int e = 0; e < 8; e++) dst[e] = r[e];
@@ -728,33 +741,33 @@ __device__ __forceinline__ void load8(const L* __restrict__ src, L (&r)[8]) {
 
 // ---------------------------------------------------------------------------
 // symwalk_kernel (K7a): the serial part of decoding a batch - its 256-symbol tANS walk - for every batch of a chunk.
-// One CTA of 4 warps per chunk; a warp takes 32 consecutive batches of one var at a time:
-//   1. copies the bytes they span (one contiguous run of the stream) into its shared-memory stage with 16-byte
-//      cp.async, fully coalesced - the per-thread scattered global reads of a thread-per-batch walk were what stalled it;
-//   2. each lane walks one batch out of shared memory (page_latent_decompressor.rs:89-177): per 4 symbols one
-//      64-bit window, 4 node lookups, 4 extractions; the bin indices go to a padded shared tile;
-//   3. the tile leaves as 256-byte rows (coalesced), and each batch's end position = start of its offsets section.
-// Latency-bound by construction (a 256-step dependent chain per lane) but cheap to issue: two warps per scheduler
-// keep it near the issue limit, so it does not need occupancy.
+// One CTA of 4 warps per chunk; a warp takes 32 consecutive batches of one var at a time, a lane per batch
+// (page_latent_decompressor.rs:89-177):
+//   1. every lane stages the bytes its next 64 symbols can read into its private shared-memory row with 16-byte
+//      cp.async from its exact position (rows, not the span of the 32 batches: the offsets sections that lie between
+//      the tANS sections are never staged) - per-thread scattered global reads inside the walk were what stalled the
+//      first design;
+//   2. per 4 symbols: one register window over the row, 4 node lookups, 4 extractions; the bin indices go to a padded
+//      shared tile;
+//   3. every 64 symbols the tile leaves as 64-byte pieces of the 256-byte symbol rows, and at the end each batch's
+//      end position = start of its offsets section.
+// The walk is a 256-step dependent chain per lane: latency-bound, so it wants warps - 32 KB of shared memory per CTA
+// puts 7 CTAs (28 warps) on an SM and the whole 1024-chunk workload in a single wave.
 // ---------------------------------------------------------------------------
 constexpr int SW_THREADS = 128;
 constexpr int SW_WARPS = SW_THREADS / 32;
-#ifndef PCOB_SW_STAGE_BYTES
-#define PCOB_SW_STAGE_BYTES 13312
+#ifndef PCOB_SW_ROWS
+#define PCOB_SW_ROWS 64
 #endif
-// per warp.  The stage holds the whole span of the stream that a pass's batches cover - their offsets sections lie
-// between the tANS sections - so 13 KiB takes 32 batches of <= 13 bits per number in one pass (measured: 6.5 KiB stages
-// give 5 CTAs per SM but two half-empty passes per group on the C2 data: 0.41 ms instead of 0.31 ms)
-#ifdef PCOB_SW_ROWS
-// Row staging: every lane keeps a private row with the bytes its next PCOB_SW_ROWS symbols can read (<= 10 bits each,
+// Row staging: every lane keeps a private row with the bytes its next SW_ROW_SYMS symbols can read (<= 10 bits each,
 // + 16 bytes of start alignment + the window's over-read), refilled with 16-byte cp.async from its exact position.
-// Nothing but tANS bits is staged, so a warp needs 32 rows instead of the whole span of its 32 batches.
+// Only tANS bits are staged (the offsets sections between them are not), so a CTA needs 32 KB and 7 fit on an SM.
+// Measured on C2 (1024 chunks): one 13 KiB stage per warp holding the whole span of its 32 batches, 3 CTAs per SM:
+// 0.305 ms; rows of 128 symbols, 5 CTAs: 0.305 ms; rows of 64 symbols, 7 CTAs: 0.266 ms.  More node replicas at the
+// price of CTAs per SM (16 / 32 copies, 5 / 4 CTAs) were slower: 0.300 / 0.312 ms.
 constexpr int SW_ROW_SYMS = PCOB_SW_ROWS;
 constexpr int SW_ROW_BLOCKS = ((SW_ROW_SYMS * SMALL_MAX_SIZE_LOG / 8 + 15) / 16 + 2) | 1;  // odd: rows start in different banks
 constexpr int SW_STAGE_BYTES = 32 * SW_ROW_BLOCKS * 16;
-#else
-constexpr int SW_STAGE_BYTES = PCOB_SW_STAGE_BYTES;
-#endif
 constexpr int SW_STAGE_WORDS = SW_STAGE_BYTES / 4;
 #ifndef PCOB_SW_NODE_WORDS
 #define PCOB_SW_NODE_WORDS 2048
@@ -765,6 +778,7 @@ constexpr int SW_STAGE_WORDS = SW_STAGE_BYTES / 4;
 constexpr int SW_NODE_WORDS = PCOB_SW_NODE_WORDS;   // decoder nodes per CTA, replicated when the tables are small (see below)
 constexpr int SW_SLAB = PCOB_SW_SLAB; // symbols per tile flush
 constexpr int SW_TILE_ROW = SW_SLAB / 4 + 1;  // words per tile row (odd: conflict-free rows)
+static_assert(SW_ROW_SYMS % SW_SLAB == 0 && BATCH_N % SW_ROW_SYMS == 0, "a row refill covers whole slabs");
 
 // 32 lanes look up 32 unrelated states per step.  A var's node table is stored R times when it is small, copy r
 // interleaved at word (state * R + r), lane l reading copy l mod R: lanes with different copies never share a bank.
@@ -879,12 +893,10 @@ __global__ void __launch_bounds__(SW_THREADS) symwalk_kernel(FileParams fp, cons
       continue;
     }
     const uint32_t size_log = vh.ans_size_log;
-    const uint32_t ans_max_bits = BATCH_N * size_log;  // a symbol reads <= size_log bits
     const uint32_t rl = v == 0 ? rep_log0 : rep_log1;
     const uint32_t* node = sm.node + v * region + (uint32_t(lane) & ((1u << rl) - 1));  // this lane's copy
     const uint32_t node_sa = smem_addr(node);
     const uint32_t sl = rl + 2;  // states are kept as byte offsets into the lane's copy
-#ifdef PCOB_SW_ROWS
     {
       // ---- row staging: all batches of the group are walked at once
       const bool mine = uint32_t(lane) < nbg;
@@ -982,118 +994,6 @@ __global__ void __launch_bounds__(SW_THREADS) symwalk_kernel(FileParams fp, cons
       }
       if (mine) offs[b] = uint32_t(min(bit, src.n_bits) - chunk_bit0);
     }
-#else
-    uint32_t k0 = 0;  // batches [k0, k1) of the group are staged per pass
-    while (k0 < nbg) {
-      const uint64_t base_bit = (chunk_bit0 + __shfl_sync(0xffffffffu, e.bit_pos, int(k0))) & ~uint64_t(127);  // 16-byte block
-      const uint64_t my_bit = chunk_bit0 + e.bit_pos;
-      // lane k fits if its whole tANS section lies inside the stage; positions ascend, so the fits form a prefix.
-      // The first batch of a pass always fits (a section is <= 320 bytes + 16 of alignment).
-      const bool fits = uint32_t(lane) >= k0 && uint32_t(lane) < nbg && my_bit >= base_bit &&
-                        my_bit + ans_max_bits + 64 <= base_bit + uint64_t(SW_STAGE_BYTES) * 8;
-      const uint32_t fm = __ballot_sync(0xffffffffu, fits) >> k0;
-      uint32_t npass = max(1u, uint32_t(__ffs(~fm) - 1));  // leading run of fitting lanes (>= 1 for a sane index)
-      if (k0 + npass < nbg) {  // several passes: split the remaining batches evenly so that later passes keep their lanes busy
-        const uint32_t rem = nbg - k0, passes = (rem + npass - 1) / npass;
-        npass = (rem + passes - 1) / passes;
-      }
-      const uint32_t k1 = min(nbg, k0 + npass);
-      // bytes to stage: up to the start of the next batch after the pass (known from the index), else the whole stage
-      uint64_t end_bit = base_bit + uint64_t(SW_STAGE_BYTES) * 8;
-      if (k1 < nbg) end_bit = min(end_bit, chunk_bit0 + __shfl_sync(0xffffffffu, e.bit_pos, int(k1)) + 64);
-      else end_bit = min(end_bit, chunk_bit0 + __shfl_sync(0xffffffffu, e.bit_pos, int(k1 - 1)) + ans_max_bits + 64);
-      const uint32_t n_blk = end_bit > base_bit ? min(uint32_t(SW_STAGE_BYTES / 16), uint32_t((end_bit - base_bit + 127) >> 7)) : 1u;
-      const uint64_t blk0 = base_bit >> 7;
-      for (uint32_t q = lane; q < n_blk; q += 32) {
-        const uint64_t bi = min(blk0 + q, max_blk);
-        const void* gp = reinterpret_cast<const ulonglong2*>(src.words) + bi;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stg_sa + q * 16), "l"(gp));
-      }
-      asm volatile("cp.async.commit_group;");
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      __syncwarp();
-      const bool mine = uint32_t(lane) >= k0 && uint32_t(lane) < k1;
-      const uint32_t b = b0 + lane;
-      const int cnt = mine ? int(batch_count(stored, b)) : 0;
-      // clamp what an untrusted index could push outside the stage: garbage in, garbage out, but in bounds
-      uint32_t wpos = uint32_t(min(my_bit >= base_bit ? my_bit - base_bit : 0, uint64_t(SW_STAGE_BYTES) * 8 - ans_max_bits - 64));
-      const uint32_t smask = (1u << size_log) - 1;
-      uint32_t s0 = min(uint32_t(e.st[0]), smask) << sl, s1 = min(uint32_t(e.st[1]), smask) << sl;
-      uint32_t s2 = min(uint32_t(e.st[2]), smask) << sl, s3 = min(uint32_t(e.st[3]), smask) << sl;
-      uint32_t* row = tile + lane * SW_TILE_ROW;
-      const uint32_t row_sa = smem_addr(row);
-      uint8_t* sym_rows = d_syms + (row0 + size_t(v) * nb_out + b0) * BATCH_N;
-      uint32_t w = wpos >> 5;
-      uint32_t x0 = lds_u32(stg_sa + 4 * w), x1 = lds_u32(stg_sa + 4 * w + 4), x2 = lds_u32(stg_sa + 4 * w + 8);  // register window over the stream
-      for (int slab = 0; slab < BATCH_N / SW_SLAB; slab++) {
-        const int i0 = slab * SW_SLAB;
-        if (size_log <= 8) {
-          // four symbols read <= 32 bits: one 32-bit window per group, fields by bit-field extract
-#pragma unroll 4
-          for (int i = i0; i < i0 + SW_SLAB; i += 4) {
-            if (i + 4 <= cnt) {
-              const uint32_t n0 = lds_u32(node_sa + s0), n1 = lds_u32(node_sa + s1), n2 = lds_u32(node_sa + s2), n3 = lds_u32(node_sa + s3);
-              const uint32_t g = __funnelshift_r(x0, x1, wpos & 31);
-              const uint32_t c0 = node_btr(n0), c1 = node_btr(n1), c2 = node_btr(n2), c3 = node_btr(n3);
-              const uint32_t sh2 = c0 + c1, sh3 = sh2 + c2;
-              s0 = (node_base(n0) + (g & ((1u << c0) - 1))) << sl;
-              s1 = (node_base(n1) + ((g >> c0) & ((1u << c1) - 1))) << sl;
-              s2 = (node_base(n2) + ((g >> sh2) & ((1u << c2) - 1))) << sl;
-              s3 = (node_base(n3) + ((g >> sh3) & ((1u << c3) - 1))) << sl;
-              sts_u32(row_sa + (i - i0), node_fields4(n0, n1, n2, n3));
-              wpos += sh3 + c3;
-              if ((wpos >> 5) != w) { w = wpos >> 5; x0 = lds_u32(stg_sa + 4 * w); x1 = lds_u32(stg_sa + 4 * w + 4); }
-            }
-          }
-        } else {
-#pragma unroll 2
-          for (int i = i0; i < i0 + SW_SLAB; i += 4) {
-            if (i + 4 <= cnt) {
-              const uint32_t n0 = lds_u32(node_sa + s0), n1 = lds_u32(node_sa + s1), n2 = lds_u32(node_sa + s2), n3 = lds_u32(node_sa + s3);
-              const uint32_t r = wpos & 31;
-              const uint64_t g = (uint64_t(__funnelshift_r(x1, x2, r)) << 32) | __funnelshift_r(x0, x1, r);
-              const uint32_t c0 = node_btr(n0), c1 = node_btr(n1), c2 = node_btr(n2), c3 = node_btr(n3);
-              const uint32_t sh2 = c0 + c1, sh3 = sh2 + c2;
-              s0 = (node_base(n0) + (uint32_t(g) & ((1u << c0) - 1))) << sl;
-              s1 = (node_base(n1) + (uint32_t(g >> c0) & ((1u << c1) - 1))) << sl;
-              s2 = (node_base(n2) + (uint32_t(g >> sh2) & ((1u << c2) - 1))) << sl;
-              s3 = (node_base(n3) + (uint32_t(g >> sh3) & ((1u << c3) - 1))) << sl;
-              sts_u32(row_sa + (i - i0), node_fields4(n0, n1, n2, n3));
-              wpos += sh3 + c3;
-              if ((wpos >> 5) != w) { w = wpos >> 5; x0 = lds_u32(stg_sa + 4 * w); x1 = lds_u32(stg_sa + 4 * w + 4); x2 = lds_u32(stg_sa + 4 * w + 8); }
-            }
-          }
-        }
-        if (cnt > i0 && cnt < i0 + SW_SLAB && (cnt & 3)) {  // ragged tail of the page's last batch (page_latent_decompressor.rs:144-177)
-          const int i = cnt & ~3;
-          uint32_t packed = 0;
-          uint32_t sarr[4] = {s0, s1, s2, s3};
-          for (int j = 0; i + j < cnt; j++) {
-            const uint32_t nn = lds_u32(node_sa + sarr[j]);
-            const uint32_t ww = wpos >> 5, r = wpos & 31;
-            const uint32_t val = __funnelshift_r(stg[ww], stg[ww + 1], r) & ((1u << node_btr(nn)) - 1);
-            packed |= node_field(nn) << (8 * j);
-            sarr[j] = (node_base(nn) + val) << sl;
-            wpos += node_btr(nn);
-          }
-          sts_u32(row_sa + (i - i0), packed);
-        }
-        __syncwarp();
-        // the slab of rows k0..k1 -> SW_SLAB-byte pieces of the 256-byte symbol rows (16 bytes per lane)
-        if (__any_sync(0xffffffffu, cnt > i0)) {
-          constexpr uint32_t SEGS = SW_SLAB / 16;  // 16-byte pieces per row and slab
-          for (uint32_t idx = k0 * SEGS + lane; idx < k1 * SEGS; idx += 32) {
-            const uint32_t rr = idx / SEGS, seg = idx % SEGS;
-            const uint32_t* tp = tile + rr * SW_TILE_ROW + seg * 4;
-            *reinterpret_cast<uint4*>(sym_rows + size_t(rr) * BATCH_N + i0 + seg * 16) = make_uint4(tp[0], tp[1], tp[2], tp[3]);
-          }
-        }
-        __syncwarp();
-      }
-      if (mine) offs[b] = uint32_t(min(base_bit + wpos, src.n_bits) - chunk_bit0);
-      k0 = k1;
-    }
-#endif
   }
 }
 

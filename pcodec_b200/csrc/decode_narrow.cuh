@@ -49,34 +49,6 @@ __device__ __forceinline__ uint32_t ones_shl_wrap(uint32_t s) {  // 0xffffffff <
   asm("shf.l.wrap.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(0u), "r"(0xffffffffu), "r"(s));
   return r;
 }
-template <typename L>
-__device__ __forceinline__ void store8_pairs(L* __restrict__ dst, const L (&r)[8]) {
-  if (sizeof(L) == 8) {
-#pragma unroll
-    for (int q = 0; q < 4; q++)
-      asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(dst + 2 * q), "l"(uint64_t(r[2 * q])), "l"(uint64_t(r[2 * q + 1])) : "memory");
-  } else {
-#pragma unroll
-    for (int q = 0; q < 2; q++)
-      asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * q), "r"(uint32_t(r[4 * q])), "r"(uint32_t(r[4 * q + 1])),
-                   "r"(uint32_t(r[4 * q + 2])), "r"(uint32_t(r[4 * q + 3])) : "memory");
-  }
-}
-
-// 8 consecutive numbers per lane as 32-byte stores (STG.E.ENL2.256, sm_100): whole sectors instead of half sectors
-template <typename L>
-__device__ __forceinline__ void store8_sectors(L* __restrict__ dst, const L (&r)[8]) {
-  if (sizeof(L) == 8) {
-#pragma unroll
-    for (int q = 0; q < 2; q++)
-      asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * q), "l"(uint64_t(r[4 * q])), "l"(uint64_t(r[4 * q + 1])),
-                   "l"(uint64_t(r[4 * q + 2])), "l"(uint64_t(r[4 * q + 3])) : "memory");
-  } else {
-    asm volatile("st.global.v8.u32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(uint32_t(r[0])), "r"(uint32_t(r[1])), "r"(uint32_t(r[2])),
-                 "r"(uint32_t(r[3])), "r"(uint32_t(r[4])), "r"(uint32_t(r[5])), "r"(uint32_t(r[6])), "r"(uint32_t(r[7])) : "memory");
-  }
-}
-
 struct NarrowSmem {
   uint32_t q[SMALL_MAX_BINS];
   alignas(16) uint32_t win[NW_WARPS][2][NW_WIN_WORDS];
@@ -130,26 +102,40 @@ __device__ __forceinline__ void narrow_chunk(NarrowSmem& sm, const FileParams& f
     asm volatile("cp.async.commit_group;");
   };
 
+  // a batch's section start is requested two batches ahead, its symbols and its window one batch ahead
+  constexpr int SY_STEP = NW_WARPS * (BATCH_N / 8);  // uint2 per round of NW_WARPS batches
+#ifdef PCOB_NW_SY2
+  constexpr bool SY_TWO_AHEAD = true;
+#else
+  constexpr bool SY_TWO_AHEAD = false;
+#endif
   uint32_t off_cur = 0, off_nxt = 0;
-  uint2 sy_nxt = make_uint2(0u, 0u);
+  uint2 sy_nxt = make_uint2(0u, 0u), sy_n2 = make_uint2(0u, 0u);
   if (uint32_t(warp) < nb_out) {
     off_cur = __ldg(off_ptr);
     issue_window(off_cur, 0);
     sy_nxt = __ldg(sy_ptr);
-    if (uint32_t(warp) + NW_WARPS < nb_out) off_nxt = __ldg(off_ptr + NW_WARPS);
+    if (uint32_t(warp) + NW_WARPS < nb_out) {
+      off_nxt = __ldg(off_ptr + NW_WARPS);
+      if (SY_TWO_AHEAD) sy_n2 = __ldg(sy_ptr + SY_STEP);
+    }
   }
   uint32_t buf = 0;
   for (uint32_t b = warp; b < nb_out; b += NW_WARPS) {
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();  // this batch's window is visible to the warp; every lane is done with the other buffer
     const uint2 sy = sy_nxt;
+    if (SY_TWO_AHEAD) sy_nxt = sy_n2;
     uint32_t off_n2 = 0;
-    sy_ptr += NW_WARPS * (BATCH_N / 8);
+    sy_ptr += SY_STEP;
     off_ptr += NW_WARPS;
     if (b + NW_WARPS < nb_out) {
       issue_window(off_nxt, buf ^ 1u);
-      sy_nxt = __ldg(sy_ptr);
-      if (b + 2 * NW_WARPS < nb_out) off_n2 = __ldg(off_ptr + NW_WARPS);
+      if (!SY_TWO_AHEAD) sy_nxt = __ldg(sy_ptr);
+      if (b + 2 * NW_WARPS < nb_out) {
+        off_n2 = __ldg(off_ptr + NW_WARPS);
+        if (SY_TWO_AHEAD) sy_n2 = __ldg(sy_ptr + SY_STEP);
+      }
     }
     const uint32_t cnt = batch_count(stored, b);
     // ---- bins of the lane's 8 latents
@@ -246,12 +232,11 @@ __device__ __forceinline__ void narrow_chunk(NarrowSmem& sm, const FileParams& f
       for (int e = 0; e < 8; e++) res[e] = from_latent_kind<L>(res[e], kind);
     }
     const uint32_t out_cnt = min(uint32_t(BATCH_N), n_out - b * BATCH_N);  // numbers this batch emits
-    if (out_cnt == uint32_t(BATCH_N) && (reinterpret_cast<uintptr_t>(dst) & 31) == 0) {
-      // 32-byte stores: a lane's 16-byte stores would each fill half a sector, and the L1 was the busiest unit with them
-      // (81 % of peak; 0.78 ms -> 0.58 ms).  Staging the batch in shared memory for 512-byte-contiguous stores: 0.61 ms.
-      store8_sectors<L>(dst, res);
-    } else if (out_cnt == uint32_t(BATCH_N) && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-      store8_pairs<L>(dst, res);
+    if (out_cnt == uint32_t(BATCH_N) && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+      // 32-byte stores when aligned: a lane's 16-byte stores would each fill half a sector, and the L1 was the busiest
+      // unit with them (81 % of peak; 0.78 ms -> 0.58 ms).  Staging the batch in shared memory for 512-byte-contiguous
+      // stores instead: 0.61 ms.
+      store8<L>(dst, res);
     } else {
 #pragma unroll
       for (int e = 0; e < 8; e++)
