@@ -362,9 +362,10 @@ def run_gpu_arm(args, rank, world):
                      "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": alg_bytes,
                      "peak_source": peak_src},
         "cpu_baseline": cpu, "e2e": e2e, "clocks": sampler.summary(),
-        # per step: 13 of this repo's kernels in compress; decompress = symwalk_kernel + decode_narrow_kernel + decode_kernel<L,1> +
-        # decode_kernel<L,2> (every chunk is decoded by exactly one of the three decode launches; the others' CTAs exit at once)
-        "gpu_launches": 17,
+        # per step (profiles/r01_l_launches.csv): compress = init_chunks, split_count, plan_solve, fallback, bin_lut, ans_encode,
+        # layout, chunk_offsets, pack, header_footer, emit_index; decompress = symwalk_kernel + decode_narrow_kernel +
+        # decode_kernel<L,1> + decode_kernel<L,2> (a chunk is decoded by exactly one of the three; the others' CTAs exit at once)
+        "gpu_launches": 15,
     }
     print(json.dumps(line))
 

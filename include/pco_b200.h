@@ -102,6 +102,16 @@ PcoB200Error pco_b200_compress_ex(const void *nums, size_t n, unsigned char dtyp
                                   int uniform_type_header, void *dst, size_t dst_cap, size_t *n_written, void *index,
                                   size_t index_cap, size_t *index_len, uint32_t flags, void *cuda_stream);
 
+/* Batched decompress without a side index, for callers that know where their chunks are (no reference counterpart:
+ * the reference decodes chunk after chunk, pco/src/standalone/decompressor.rs:270-273).  `compressed` holds n_chunks standalone
+ * chunks (type byte, 24-bit n - 1, chunk meta, page) at byte offsets chunk_offsets[i] - a standalone file, or the bare chunks
+ * that PCO_B200_CHUNKS_ONLY emits; chunk_ns[i] = numbers in chunk i.  The numbers land back to back in dst (dst_len >= sum of
+ * chunk_ns).  The per-batch index is built on the device, one tANS walk per chunk, all chunks in parallel.  A count that does not
+ * match the chunk's own header is PCO_B200_INVALID_ARGUMENT. */
+PcoB200Error pco_b200_decompress_chunks(const void *compressed, size_t compressed_len, unsigned char dtype,
+                                        const uint64_t *chunk_offsets, const uint32_t *chunk_ns, size_t n_chunks, void *dst,
+                                        size_t dst_len, size_t *n_written, uint32_t flags, void *cuda_stream);
+
 /* Build the side index of a standalone file (one serial tANS walk per chunk on the device).
  * index_cap >= pco_b200_index_size_bound(n_total, 2). */
 size_t pco_b200_index_size_bound(size_t n, size_t n_chunks_hint);

@@ -1,12 +1,17 @@
 // Host orchestration of the compress path: validates the ChunkConfig like the reference, lays out the
 // chunks, runs the encode kernels on one stream and returns the .pco bytes (+ optional side index).
 #pragma once
+#include <cstdlib>
 #include <cub/device/device_segmented_radix_sort.cuh>
 
 #include <cmath>
 
 #include "encode_kernels.cuh"
 #include "host_common.hpp"
+
+#ifndef PCOB_ONE_PASS_DEFAULT
+#define PCOB_ONE_PASS_DEFAULT false  // flipped once the GPU parity suite has run with it
+#endif
 
 namespace pcob200 {
 
@@ -56,12 +61,13 @@ inline std::vector<uint8_t> make_standalone_header(uint64_t n_hint, uint8_t unif
   return h;
 }
 
-__global__ void range_bits_kernel(const ChunkEnc* chunks, uint32_t n_chunks, int v, uint32_t* out_bits) {
+__global__ void range_bits_kernel(ChunkEnc* chunks, uint32_t n_chunks, int v, uint32_t* out_bits) {
   uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n_chunks) return;
   uint64_t a = chunks[c].vmin[v], b = chunks[c].vmax[v];
   uint32_t bits = b > a ? 64 - __clzll((long long)(b - a)) : 0;
   atomicMax(out_bits, bits);
+  chunks[c].key_base[v] = a;  // plan_probe_kernel's keys are latent - vmin
 }
 
 // internal entries [(c, v)][batches_per_chunk] -> compact side index
@@ -258,6 +264,42 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
   uint32_t var_range_bits[MAX_VARS] = {64, 64};
   auto front = [&](const EncParams& e, uint32_t tiles, size_t slots, uint32_t (&vrb)[MAX_VARS]) -> PcoB200Error {
     init_chunks_kernel<<<(n_chunks + 255) / 256, 256, 0, stream>>>(d_chunks, n_chunks);
+    static bool plan_attr_set = false;
+    if (!plan_attr_set) {
+      plan_attr_set = true;
+      PCOB_CUDA_TRY(cudaFuncSetAttribute(plan_probe_kernel<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(((size_t(1) << PLAN_MAX_COUNT_BITS) + 1) * 4 + 16)));
+      PCOB_CUDA_TRY(cudaFuncSetAttribute(split_count_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(size_t(SC_N) * 4)));
+      PCOB_CUDA_TRY(cudaFuncSetAttribute(pack_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PackSmem)));
+      // several counting CTAs per SM: ask for the largest shared-memory carveout
+      PCOB_CUDA_TRY(cudaFuncSetAttribute(plan_probe_kernel<L, true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+      PCOB_CUDA_TRY(cudaFuncSetAttribute(pack_kernel<L>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+      PCOB_CUDA_TRY(cudaFuncSetAttribute(bin_lut_kernel<L>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    }
+#ifndef PCOB_NO_SPLIT_COUNT
+    static const bool one_pass = [] { const char* v = std::getenv("PCOB200_ONE_PASS_FRONT_END"); return v ? v[0] != '0' : PCOB_ONE_PASS_DEFAULT; }();
+    if (one_pass && e.mode == MODE_CLASSIC && e.n_vars == 1) {
+      // one-pass front end: split + delta + counting histogram + 16-bit keys, no 64-bit latents (split_count_kernel).
+      // It assumes every chunk's stored latents span < 2^15; a chunk that does not raises flags[1] and the call is redone
+      // on the two-kernel path below (the speculation costs one read of the input).
+      PCOB_CUDA_TRY(S.key16_0.reserve(slots * 2 + 64));
+      PCOB_CUDA_TRY(cudaMemsetAsync(d_small, 0, 8, stream));
+      profiler().begin("split_count_kernel", stream);
+      split_count_kernel<L><<<n_chunks, SC_THREADS, size_t(SC_N) * 4, stream>>>(e, d_chunks, d_probes, S.key16_0.as<uint16_t>(), d_small);
+      profiler().end(stream);
+      uint32_t fl[2] = {0, 0};
+      PCOB_CUDA_TRY(cudaMemcpyAsync(fl, d_small, 8, cudaMemcpyDeviceToHost, stream));
+      PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
+      if (fl[1] == 0) {
+        vrb[0] = fl[0];
+        profiler().begin("plan_solve_kernel", stream);
+        plan_solve_kernel<L><<<n_chunks, SOLVE_THREADS, 0, stream>>>(e, d_probes, d_chunks, d_plans, 0);
+        profiler().end(stream);
+        return PCO_B200_OK;
+      }
+      init_chunks_kernel<<<(n_chunks + 255) / 256, 256, 0, stream>>>(d_chunks, n_chunks);
+    }
+#endif
     profiler().begin("split_delta_kernel", stream);
     switch (e.mode) {
       case MODE_CLASSIC: split_delta_kernel<L, MODE_CLASSIC><<<n_chunks * tiles, SPLIT_THREADS, 0, stream>>>(e, tiles, d_lat[0], d_lat[1], d_chunks); break;
@@ -267,17 +309,6 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
     }
     profiler().end(stream);
     // ---- planner per var: range-reduced keys -> segmented radix sort over the significant bits -> plan
-    static bool plan_attr_set = false;
-    if (!plan_attr_set) {
-      plan_attr_set = true;
-      PCOB_CUDA_TRY(cudaFuncSetAttribute(plan_probe_kernel<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(((size_t(1) << PLAN_MAX_COUNT_BITS) + 1) * 4 + 16)));
-      PCOB_CUDA_TRY(cudaFuncSetAttribute(pack_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PackSmem)));
-      // several counting CTAs per SM: ask for the largest shared-memory carveout
-      PCOB_CUDA_TRY(cudaFuncSetAttribute(plan_probe_kernel<L, true>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-      PCOB_CUDA_TRY(cudaFuncSetAttribute(pack_kernel<L>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-      PCOB_CUDA_TRY(cudaFuncSetAttribute(bin_lut_kernel<L>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
-    }
     for (uint32_t v = 0; v < e.n_vars; v++) {
       const uint32_t order_v = v == 0 ? e.order : 0;
       PCOB_CUDA_TRY(cudaMemsetAsync(d_small, 0, 4, stream));

@@ -317,14 +317,15 @@ struct FileParams {
 //   serial_file_mode = 0: one CTA per pre-filled IndexChunk (offsets, n and entries_offset known).
 // Layout written: index_base + chunks_offset : IndexChunk[]; entries at index_base + entries_offset.
 // ---------------------------------------------------------------------------
+template <int CAP_LOG>   // 12: any table the format allows on this path; 10: what the decode kernels take (4x less shared memory)
 struct WalkSmem {
   ChunkHdr hdr;
-  uint32_t node[MAX_VARS][1 << 12];
-  uint8_t bin_ob[MAX_VARS][1 << 12];
-  uint16_t bin_weight[MAX_VARS][1 << 12];
-  uint32_t bin_cum[MAX_VARS][(1 << 12) + 1];
-  uint16_t sym_of_state[MAX_VARS][1 << 12];
-  uint32_t rank_counter[MAX_VARS][1 << 12];
+  uint32_t node[MAX_VARS][1 << CAP_LOG];
+  uint8_t bin_ob[MAX_VARS][1 << CAP_LOG];
+  uint16_t bin_weight[MAX_VARS][1 << CAP_LOG];
+  uint32_t bin_cum[MAX_VARS][(1 << CAP_LOG) + 1];
+  uint16_t sym_of_state[MAX_VARS][1 << CAP_LOG];
+  uint32_t rank_counter[MAX_VARS][1 << CAP_LOG];
   uint32_t err;
   uint64_t next_chunk_byte;
   uint32_t status;
@@ -341,7 +342,8 @@ struct WalkResult {     // written by the serial walker
 __host__ __device__ inline uint32_t n_batches_of(uint32_t n) { return (n + BATCH_N - 1) / BATCH_N; }
 
 // Walk one chunk whose header is already parsed and tables built (WALKER nodes). One thread.
-__device__ inline uint32_t walk_chunk_serial(const BitSrc& src, const ChunkHdr& hdr, const uint32_t (*node)[1 << 12], uint64_t chunk_bit0,
+template <int CAP_LOG>
+__device__ inline uint32_t walk_chunk_serial(const BitSrc& src, const ChunkHdr& hdr, const uint32_t (*node)[1 << CAP_LOG], uint64_t chunk_bit0,
                                              BatchEntry* entries, uint64_t* end_bit_out) {
   const uint64_t max_word = src.n_bits == 0 ? 0 : (src.n_bits - 1) >> 6;
   const uint32_t nb = n_batches_of(hdr.n);
@@ -376,12 +378,13 @@ __device__ inline uint32_t walk_chunk_serial(const BitSrc& src, const ChunkHdr& 
   return ST_OK;
 }
 
+template <int CAP_LOG>
 __global__ void __launch_bounds__(128) walk_kernel(FileParams fp, uint8_t* index_base, uint64_t chunks_offset, uint32_t max_chunks,
                                                    uint64_t entries_begin, uint64_t entries_cap_end, uint64_t first_chunk_byte,
                                                    uint64_t first_out_offset, uint64_t stop_after_total, uint32_t* statuses, WalkResult* result,
                                                    int serial_file_mode) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  WalkSmem& sm = *reinterpret_cast<WalkSmem*>(smem_raw);
+  WalkSmem<CAP_LOG>& sm = *reinterpret_cast<WalkSmem<CAP_LOG>*>(smem_raw);
   const BitSrc src = make_bitsrc(fp.src, fp.src_len);
   const int tid = threadIdx.x;
   IndexChunk* chunks = reinterpret_cast<IndexChunk*>(index_base + chunks_offset);
@@ -398,9 +401,11 @@ __global__ void __launch_bounds__(128) walk_kernel(FileParams fp, uint8_t* index
       if (sm.hdr.status == ST_OK) {
         for (uint32_t v = 0; v < sm.hdr.n_vars; v++) {
           const VarHdr& vh = sm.hdr.var[v];
-          if (vh.ans_size_log > 12 || vh.n_bins > (1u << 12)) sm.hdr.status = ST_UNSUPPORTED;
+          if (vh.ans_size_log > uint32_t(CAP_LOG) || vh.n_bins > (1u << CAP_LOG)) sm.hdr.status = ST_UNSUPPORTED;
           if (vh.n_bins == 0 && var_stored_n(sm.hdr.n, vh.delta_order) > 0) sm.hdr.status = ST_CORRUPTION;  // page_decompressor.rs:52-57
         }
+        // per-chunk mode: the caller sized this chunk's entries from the count it gave
+        if (!serial_file_mode && sm.hdr.status == ST_OK && chunks[c].n != sm.hdr.n) sm.hdr.status = ST_INVALID_ARGUMENT;
       }
     }
     __syncthreads();
@@ -421,7 +426,7 @@ __global__ void __launch_bounds__(128) walk_kernel(FileParams fp, uint8_t* index
         if (eo + need > entries_cap_end) {
           st = ST_INDEX_FULL;
         } else {
-          st = walk_chunk_serial(src, sm.hdr, sm.node, chunk_bit0, reinterpret_cast<BatchEntry*>(index_base + eo), &end_bit);
+          st = walk_chunk_serial<CAP_LOG>(src, sm.hdr, sm.node, chunk_bit0, reinterpret_cast<BatchEntry*>(index_base + eo), &end_bit);
           if (st == ST_OK) {
             IndexChunk ic;
             ic.chunk_offset = chunk_byte;

@@ -68,6 +68,7 @@ struct VarPlan {
 struct ChunkEnc {              // per chunk, device
   uint64_t moments[MAX_VARS][MAX_ORDER];
   uint64_t vmin[MAX_VARS], vmax[MAX_VARS];
+  uint64_t key_base[MAX_VARS];  // what the 16-bit keys of the counting path are relative to (mod 2^16): vmin, or the fused kernel's anchor
   uint32_t final_state[MAX_VARS][4];
   uint32_t fallback;           // 1 = Classic / NoOp / one bin of L::BITS offset bits
   uint32_t status;
@@ -421,7 +422,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_probe_kernel(EncParams ep, 
   ENC_TICK_INIT();
   const uint32_t n_vals = COUNTING ? (1u << range_bits) : 0u;
   if (COUNTING) {
-    const L mn = L(chunks[c].vmin[v]);
+    const L mn = L(chunks[c].vmin[v]);  // (the host sets key_base = vmin for this path: range_bits_kernel)
     for (uint32_t i = tid; i <= n_vals; i += PLAN_THREADS) cum[i] = 0;
     __syncthreads();
     {
@@ -519,6 +520,211 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_probe_kernel(EncParams ep, 
     pr.vB1[k] = vb1; pr.vB[k] = vb; pr.vLm1[k] = vlm1; pr.vR[k] = vr; pr.runL[k] = l; pr.runR[k] = r;
   }
   ENC_TICK(2);  // probes
+}
+
+// ---------------------------------------------------------------------------
+// split_count_kernel: K1+K2 and the counting half of the planner in ONE pass over the numbers, for the case that
+// dominates in practice - classic mode (one latent var) whose stored latents span < 2^15.  One CTA per chunk streams
+// the chunk once: ordered latents, order-k backward difference (stencil of signed binomials over vector loads),
+// min/max, shared-memory counters, 16-bit keys out.  The 64-bit latents are never written: split_delta_kernel +
+// plan_probe_kernel move 6.8 GB per 2 GiB of u64 input (write and re-read of the latents), this kernel 2.6 GB.
+// The chunk minimum is not known while counting, so everything is relative to an ANCHOR (the first stored latent):
+//   key16   = (latent - anchor) mod 2^16          (consumers subtract key_base = anchor; offsets are differences)
+//   counter = (latent - anchor) mod 2^15          (a range < 2^15 lies on an arc of the circle: no two values collide)
+// and once min/max are known the counters are read through the rotation (min - anchor) mod 2^15.  A chunk whose range
+// needs more than 15 bits raises flags[1]; the host then runs the two-kernel path for the whole call.
+// ---------------------------------------------------------------------------
+constexpr int SC_THREADS = 1024;
+constexpr uint32_t SC_N = 1u << PLAN_MAX_COUNT_BITS, SC_MASK = SC_N - 1;
+
+// The streaming pass of split_count_kernel for one delta order: 4 consecutive stored latents per thread and step.
+// Stored index s holds the difference ending at number ORDER + s, which needs numbers s .. s + ORDER + 3: aligned
+// 4-vectors at s, s + 4 (and s + 8 for orders > 4; the neighbouring threads' loads of the same lines hit L1).
+template <typename L, int ORDER>
+__device__ __forceinline__ void sc_stream(const L* __restrict__ nums, uint32_t n, uint32_t stored, L anchor, bool is_float, bool is_signed,
+                                          uint16_t* __restrict__ k16, uint32_t* __restrict__ cnt, L& mn, L& mx) {
+  constexpr L MID = L(L(1) << (LT<L>::BITS - 1));
+  constexpr int NX = ORDER > 4 ? 12 : 8;
+  struct alignas(sizeof(L) * 4 > 16 ? 16 : sizeof(L) * 4) Vec4 { L v[4]; };
+  const bool vec_ok = (reinterpret_cast<uintptr_t>(nums) & (sizeof(Vec4) - 1)) == 0;
+  const uint32_t n4 = (stored + 3) / 4;
+  const int tid = threadIdx.x;
+  for (uint32_t q = tid; q < n4; q += SC_THREADS) {
+    const uint32_t s = 4 * q;
+    L x[NX];
+    if (vec_ok && s + NX <= n) {
+#pragma unroll
+      for (int g = 0; g < NX / 4; g++) {
+        const Vec4 a = *reinterpret_cast<const Vec4*>(nums + s + 4 * g);
+#pragma unroll
+        for (int u = 0; u < 4; u++) x[4 * g + u] = to_latent_ordered<L>(a.v[u], is_float, is_signed);
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < NX; u++) x[u] = (u < ORDER + 4 && s + u < n) ? to_latent_ordered<L>(nums[s + u], is_float, is_signed) : L(0);
+    }
+    uint32_t kw[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      // d = sum_j (-1)^j C(ORDER, j) x[u + ORDER - j]  (== ORDER passes of x[i] -= x[i-1], delta/consecutive.rs:19-33)
+      L d = x[u + ORDER];
+      uint32_t binom = 1;
+#pragma unroll
+      for (int j = 1; j <= ORDER; j++) {
+        binom = binom * uint32_t(ORDER - j + 1) / uint32_t(j);
+        d = (j & 1) ? L(d - L(L(binom) * x[u + ORDER - j])) : L(d + L(L(binom) * x[u + ORDER - j]));
+      }
+      if (ORDER > 0) d = L(d + MID);  // toggle_center (delta/mod.rs:29-33)
+      const bool live = s + u < stored;
+      if (live) { mn = min(mn, d); mx = max(mx, d); }
+      const uint32_t w = uint32_t(L(d - anchor));
+      kw[u] = w & 0xffffu;
+      if (live) atomicAdd(&cnt[w & SC_MASK], 1u);
+    }
+    *reinterpret_cast<uint2*>(k16 + s) = make_uint2(kw[0] | (kw[1] << 16), kw[2] | (kw[3] << 16));  // rows are 256-aligned and padded
+  }
+}
+
+template <typename L>
+__global__ void __launch_bounds__(SC_THREADS, 1) split_count_kernel(EncParams ep, ChunkEnc* __restrict__ chunks, PlanProbes* __restrict__ probes,
+                                                                   uint16_t* __restrict__ keys16, uint32_t* __restrict__ flags) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(smem_raw);  // SC_N counters, then their exclusive scan (rotated)
+  __shared__ uint64_t red_min[SC_THREADS / 32], red_max[SC_THREADS / 32];
+  __shared__ uint32_t scan_part[SC_THREADS / 32];
+  __shared__ uint64_t sh_anchor, sh_min, sh_max;
+  const uint32_t c = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint64_t cs = ep.chunk_starts[c], ce = ep.chunk_starts[c + 1];
+  const uint32_t n = uint32_t(ce - cs);
+  const uint32_t order = ep.order;
+  const uint32_t stored = n > order ? n - order : 0;
+  const L* __restrict__ nums = static_cast<const L*>(ep.nums) + cs;
+  const bool is_float = nt_is_float(ep.dtype), is_signed = nt_is_signed(ep.dtype);
+  constexpr L MID = L(L(1) << (LT<L>::BITS - 1));
+  auto lat_at = [&](uint32_t idx) -> L { return idx < n ? to_latent_ordered<L>(nums[idx], is_float, is_signed) : L(0); };
+  // coef[j] = (-1)^j C(order, j): the order-th backward difference is sum_j coef[j] x[i - j] (delta/consecutive.rs:19-33)
+  L coef[MAX_ORDER + 1];
+  {
+    uint32_t binom = 1;
+#pragma unroll
+    for (uint32_t j = 0; j <= MAX_ORDER; j++) {
+      coef[j] = j <= order ? ((j & 1) ? L(L(0) - L(binom)) : L(binom)) : L(0);
+      if (j < order) binom = binom * (order - j) / (j + 1);
+    }
+  }
+  for (uint32_t i = tid; i < SC_N; i += SC_THREADS) cnt[i] = 0;
+  // page moments: moment_j = (j-th backward difference)[j]
+  if (tid < int(order)) {
+    const uint32_t j = tid;
+    L acc = 0;
+    if (j < n) {
+      uint32_t binom = 1;
+      for (uint32_t q = 0; q <= j; q++) {
+        const L term = L(L(binom) * lat_at(j - q));
+        acc = (q & 1) ? L(acc - term) : L(acc + term);
+        binom = binom * (j - q) / (q + 1);
+      }
+    }
+    chunks[c].moments[0][j] = uint64_t(acc);
+  }
+  if (tid == 0) {
+    L a = 0;
+    if (stored > 0) {
+      a = lat_at(order);
+      for (uint32_t j = 1; j <= order; j++) a = L(a + L(coef[j] * lat_at(order - j)));
+      if (order > 0) a = L(a + MID);
+    }
+    sh_anchor = uint64_t(a);
+  }
+  __syncthreads();
+  const L anchor = L(sh_anchor);
+  uint16_t* __restrict__ k16 = keys16 + ep.row_base[c];
+  L mn = L(~L(0)), mx = 0;
+  switch (order) {  // the stencil's window offsets and binomials are compile-time per order
+    case 0: sc_stream<L, 0>(nums, n, stored, anchor, is_float, is_signed, k16, cnt, mn, mx); break;
+    case 1: sc_stream<L, 1>(nums, n, stored, anchor, is_float, is_signed, k16, cnt, mn, mx); break;
+    case 2: sc_stream<L, 2>(nums, n, stored, anchor, is_float, is_signed, k16, cnt, mn, mx); break;
+    case 3: sc_stream<L, 3>(nums, n, stored, anchor, is_float, is_signed, k16, cnt, mn, mx); break;
+    case 4: sc_stream<L, 4>(nums, n, stored, anchor, is_float, is_signed, k16, cnt, mn, mx); break;
+    case 5: sc_stream<L, 5>(nums, n, stored, anchor, is_float, is_signed, k16, cnt, mn, mx); break;
+    case 6: sc_stream<L, 6>(nums, n, stored, anchor, is_float, is_signed, k16, cnt, mn, mx); break;
+    default: sc_stream<L, 7>(nums, n, stored, anchor, is_float, is_signed, k16, cnt, mn, mx); break;
+  }
+  // chunk min / max
+  {
+    uint64_t a = mn <= mx ? uint64_t(mn) : ~uint64_t(0), b = mn <= mx ? uint64_t(mx) : 0;
+    for (int d = 16; d > 0; d >>= 1) {
+      a = min(a, __shfl_xor_sync(0xffffffffu, a, d));
+      b = max(b, __shfl_xor_sync(0xffffffffu, b, d));
+    }
+    if (lane == 0) { red_min[warp] = a; red_max[warp] = b; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 0; w < SC_THREADS / 32; w++) { a = min(a, red_min[w]); b = max(b, red_max[w]); }
+      sh_min = a; sh_max = b;
+      chunks[c].vmin[0] = a;
+      chunks[c].vmax[0] = b;
+      chunks[c].key_base[0] = uint64_t(anchor);
+      const uint32_t bits = b > a ? 64 - __clzll((long long)(b - a)) : 0;
+      atomicMax(&flags[0], bits);
+      if (bits > PLAN_MAX_COUNT_BITS) atomicOr(&flags[1], 1u);
+    }
+    __syncthreads();
+  }
+  if (stored == 0) return;
+  const uint64_t vmin = sh_min, vmax = sh_max;
+  if (vmax - vmin > uint64_t(SC_MASK)) return;  // wide chunk: the host re-runs the call on the two-kernel path
+  const uint32_t rot = uint32_t(L(L(vmin) - anchor)) & SC_MASK;  // counter of key k (= latent - vmin) is cnt[(k + rot) & SC_MASK]
+  // exclusive scan of the counters in key order: warp w owns a contiguous span of keys, 32 at a time
+  {
+    const uint32_t span = SC_N / (SC_THREADS / 32);
+    const uint32_t w_lo = warp * span, w_hi = w_lo + span;
+    uint32_t carry = 0;
+    for (uint32_t base = w_lo; base < w_hi; base += 32) {
+      const uint32_t pi = (base + lane + rot) & SC_MASK;
+      const uint32_t v = cnt[pi];
+      uint32_t inc = v;
+      for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+      cnt[pi] = carry + inc - v;
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) scan_part[warp] = carry;
+    __syncthreads();
+    uint32_t wbase = 0;
+    for (int w = 0; w < warp; w++) wbase += scan_part[w];
+    for (uint32_t k = w_lo + lane; k < w_hi; k += 32) cnt[(k + rot) & SC_MASK] += wbase;
+    __syncthreads();
+  }
+  auto cum = [&](uint32_t k) -> uint32_t { return k >= SC_N ? stored : cnt[(k + rot) & SC_MASK]; };
+  // key at sorted rank idx
+  auto s_at = [&](uint32_t idx) -> uint64_t {
+    uint32_t lo = 0, hi = SC_N;  // invariant: cum(lo) <= idx < cum(hi)
+    while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (cum(m) <= idx) lo = m; else hi = m; }
+    return lo;
+  };
+  PlanProbes& pr = probes[c];
+  const uint32_t n_bins_log = ep.bins_log[0];
+  const uint32_t nbk = 1u << n_bins_log;
+  auto c_count_of = [&](uint32_t b) -> uint32_t { return uint32_t((uint64_t(b + 1) * stored + nbk - 1) >> n_bins_log); };
+  if (tid == 0) pr.first = s_at(0);
+  // probes at every equal-count boundary (histograms.rs:132-140), as in plan_probe_kernel
+  for (uint32_t k = tid; k < nbk; k += SC_THREADS) {
+    const uint32_t B = c_count_of(k);
+    uint64_t vb1 = 0, vb = 0, vlm1 = 0, vr = 0;
+    uint32_t l = 0, r = 0;
+    if (B >= 1 && B <= stored) {
+      vb1 = s_at(B - 1);
+      if (B < stored) vb = s_at(B);
+      if (B < stored && vb == vb1) {
+        l = cum(uint32_t(vb1));
+        r = cum(uint32_t(vb1) + 1);
+        if (l > 0) vlm1 = s_at(l - 1);
+        if (r < stored) vr = s_at(r);
+      }
+    }
+    pr.vB1[k] = vb1; pr.vB[k] = vb; pr.vLm1[k] = vlm1; pr.vR[k] = vr; pr.runL[k] = l; pr.runR[k] = r;
+  }
 }
 
 template <typename L>
@@ -935,7 +1141,10 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_kernel(EncParams ep, uint32_t
 // search_log-deep binary search per latent.  One CTA bins BINL_BATCHES batches of one chunk, one warp per batch,
 // lanes striding the batch so that every load is a fully used 256-byte line.
 constexpr int BINL_THREADS = 256;
-constexpr int BINL_BATCHES = 128;
+#ifndef PCOB_BINL_BATCHES
+#define PCOB_BINL_BATCHES 128
+#endif
+constexpr int BINL_BATCHES = PCOB_BINL_BATCHES;  // batches per CTA: every CTA rebuilds the chunk's lookup table first
 
 template <typename L>
 __global__ void __launch_bounds__(BINL_THREADS) bin_lut_kernel(EncParams ep, uint32_t batches_per_chunk, uint32_t parts_per_chunk,
@@ -972,6 +1181,7 @@ __global__ void __launch_bounds__(BINL_THREADS) bin_lut_kernel(EncParams ep, uin
   const VarPlan& plan = plans[size_t(c) * MAX_VARS + v];
   const uint32_t n_bins = plan.n_bins;
   const L vmin = L(chunks[c].vmin[v]);
+  const uint32_t shift2 = (uint32_t(L(vmin - L(chunks[c].key_base[v]))) & 0xffffu) * 0x10001u;
   const uint32_t n_words = max(1u, (1u << range_bits) / 4);
   for (uint32_t i = tid; i < n_words; i += BINL_THREADS) lut_w[i] = 0;
   for (uint32_t i = tid; i < n_bins; i += BINL_THREADS) obs[i] = plan.ob[i];
@@ -1009,7 +1219,8 @@ __global__ void __launch_bounds__(BINL_THREADS) bin_lut_kernel(EncParams ep, uin
     const uint32_t cnt = min(uint32_t(BATCH_N), n - b * BATCH_N);
     // the keys the counting planner left behind (latent - chunk minimum, 16 bits): a lane owns 8 consecutive ones
     const uint4 k8 = *reinterpret_cast<const uint4*>(keys16 + rb + uint64_t(b) * BATCH_N + lane * 8);
-    const uint32_t kw[4] = {k8.x, k8.y, k8.z, k8.w};
+    // stored keys are (latent - key_base) mod 2^16; the table is indexed by latent - vmin
+    const uint32_t kw[4] = {__vsub2(k8.x, shift2), __vsub2(k8.y, shift2), __vsub2(k8.z, shift2), __vsub2(k8.w, shift2)};
     uint32_t bits = 0, lo = 0, hi = 0;
 #pragma unroll
     for (int e = 0; e < 8; e++) {
@@ -1447,8 +1658,8 @@ __global__ void __launch_bounds__(PACK_THREADS, PCOB_PACK_MIN_BLOCKS) pack_kerne
     for (uint32_t i = tid; i < n_bins; i += PACK_THREADS) {
       sm.lowers[v][i] = fb ? 0 : p.lower[i];
       sm.obs[v][i] = fb ? uint8_t(lbits) : p.ob[i];
-      // keys (key0/key1 non-null: the counting planner ran for this var) are latent - chunk minimum, so is this table
-      sm.lowkey_ob[v][i] = fb ? 0u : (uint32_t(L(L(p.lower[i]) - L(ch.vmin[v]))) & 0xffffu) | (uint32_t(p.ob[i]) << 16);
+      // keys (key0/key1 non-null: the counting planner ran for this var) are (latent - key_base) mod 2^16, so is this table
+      sm.lowkey_ob[v][i] = fb ? 0u : (uint32_t(L(L(p.lower[i]) - L(ch.key_base[v]))) & 0xffffu) | (uint32_t(p.ob[i]) << 16);
     }
   }
   // ---------------- head window: preamble + chunk meta + page meta ----------------
@@ -1600,7 +1811,7 @@ __global__ void __launch_bounds__(PACK_THREADS, PCOB_PACK_MIN_BLOCKS) pack_kerne
       if (a_tot) emit8_narrow(sm.win, pos + inc - a_tot, a_val, a_bits);  // a field is <= size_log <= 10 bits
       // --- offsets (chunk_latent_compressor.rs:299-327)
       if (max_ob > 0 && (v == 0 ? keyp_0 : keyp_1) != nullptr) {
-        // 16-bit keys: offset = key - (lower - minimum), all in 32 bits; offset_bits <= 15
+        // 16-bit keys: offset = key - (lower - key_base) mod 2^16; offset_bits <= 15
         const uint32_t kw[4] = {k8.x, k8.y, k8.z, k8.w};
         uint32_t o_bits[8], o32[8], o_tot = 0;
 #pragma unroll
@@ -1608,7 +1819,7 @@ __global__ void __launch_bounds__(PACK_THREADS, PCOB_PACK_MIN_BLOCKS) pack_kerne
           const uint32_t t = sm.lowkey_ob[v][sy[e]];
           const bool live = first + e < cnt;
           o_bits[e] = live ? t >> 16 : 0u;
-          o32[e] = live ? ((kw[e >> 1] >> (16 * (e & 1))) & 0xffffu) - (t & 0xffffu) : 0u;
+          o32[e] = live ? (((kw[e >> 1] >> (16 * (e & 1))) - t) & 0xffffu) : 0u;
           o_tot += o_bits[e];
         }
         uint32_t oinc = o_tot;

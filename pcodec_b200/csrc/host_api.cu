@@ -56,7 +56,8 @@ static PcoB200Error ensure_device(Context& c) {
         for (int j = 0; j < MAX_ORDER; j++) hb.full[j] = C[256][j];
         e = cudaMalloc(&c.d_binoms, sizeof(Binoms));
         if (e == cudaSuccess) e = cudaMemcpy(c.d_binoms, &hb, sizeof(Binoms), cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WalkSmem));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(walk_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WalkSmem<12>));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(walk_kernel<SMALL_MAX_SIZE_LOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WalkSmem<SMALL_MAX_SIZE_LOG>));
         if (e != cudaSuccess) c.device_err = cudaGetErrorString(e);
         else c.device_ok = true;
       }
@@ -226,7 +227,7 @@ static PcoB200Error decompress_core(const void* compressed, size_t compressed_le
     PCOB_CUDA_TRY(c.index.reserve(entries_begin + entries_bytes));
     uint8_t* d_index = c.index.as<uint8_t>();
     profiler().begin("walk_kernel", stream);
-    walk_kernel<<<1, 128, sizeof(WalkSmem), stream>>>(fp, d_index, chunks_offset, max_chunks, entries_begin, entries_begin + entries_bytes,
+    walk_kernel<12><<<1, 128, sizeof(WalkSmem<12>), stream>>>(fp, d_index, chunks_offset, max_chunks, entries_begin, entries_begin + entries_bytes,
                                                       next_byte, out_off, uint64_t(dst_len), nullptr, d_res, 1);
     profiler().end(stream);
     PCOB_CUDA_TRY(cudaGetLastError());
@@ -584,6 +585,100 @@ size_t pco_b200_index_size_bound(size_t n, size_t n_chunks_hint) {
   return sizeof(IndexHeader) + chunks * sizeof(IndexChunk) + batches * MAX_VARS * sizeof(BatchEntry) + 16 * chunks + 64;
 }
 
+// Batched decompress of chunks whose byte offsets the caller knows (SURVEY.md 8b "decompress_chunks"): a container that
+// keeps chunk / page offsets beside the bytes - pco's wrapped use case, a sharded writer's offset table - needs no side
+// index.  The per-batch index is built on the device by one tANS walk per chunk, ALL CHUNKS IN PARALLEL (the standalone
+// format's single serial cursor only exists because chunk lengths are not in the stream), then the ordinary decode runs.
+PcoB200Error pco_b200_decompress_chunks(const void* compressed, size_t compressed_len, unsigned char dtype, const uint64_t* chunk_offsets,
+                                        const uint32_t* chunk_ns, size_t n_chunks, void* dst, size_t dst_len, size_t* n_written, uint32_t flags,
+                                        void* cuda_stream) {
+  if (!nt_valid(dtype)) return fail(PCO_B200_INVALID_TYPE, "unknown number type byte: " + std::to_string(dtype));
+  if (n_written) *n_written = 0;
+  if (n_chunks == 0) return PCO_B200_OK;
+  if (!chunk_offsets || !chunk_ns) return fail(PCO_B200_INVALID_ARGUMENT, "chunk_offsets and chunk_ns are required");
+  if (n_chunks > 0x7fffffffull) return fail(PCO_B200_INVALID_ARGUMENT, "too many chunks");
+  Context& c = ctx();
+  std::lock_guard<std::mutex> lock(c.mu);
+  if (PcoB200Error e = ensure_device(c)) return e;
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  const bool src_dev = flags & PCO_B200_SRC_ON_DEVICE, dst_dev = flags & PCO_B200_DST_ON_DEVICE;
+  const size_t elem = nt_bits(dtype) / 8;
+  // a standalone file (magic present) carries the format version and the uniform type; bare chunks are format 4.1
+  uint32_t format_major = 4, uniform_type = 0;
+  {
+    uint8_t head[32] = {0};
+    const size_t avail = std::min<size_t>(compressed_len, sizeof(head));
+    if (avail) {
+      if (src_dev) { PCOB_CUDA_TRY(cudaMemcpyAsync(head, compressed, avail, cudaMemcpyDeviceToHost, stream)); PCOB_CUDA_TRY(cudaStreamSynchronize(stream)); }
+      else std::memcpy(head, compressed, avail);
+    }
+    static const uint8_t MAGIC[4] = {112, 99, 111, 33};
+    if (avail >= 4 && std::memcmp(head, MAGIC, 4) == 0 && chunk_offsets[0] >= 4) {
+      StandaloneHeader hdr;
+      if (PcoB200Error e = parse_standalone_header(head, avail, compressed_len, &hdr)) return e;
+      format_major = hdr.format_major;
+      uniform_type = hdr.uniform_type;
+    }
+  }
+  // index skeleton: chunk records from the caller's table, room for 2 vars of entries per chunk
+  const uint64_t chunks_offset = sizeof(IndexHeader);
+  std::vector<IndexChunk> recs(n_chunks);
+  uint64_t off = (chunks_offset + uint64_t(n_chunks) * sizeof(IndexChunk) + 15) & ~uint64_t(15), out_off = 0;
+  for (size_t i = 0; i < n_chunks; i++) {
+    if (chunk_offsets[i] >= compressed_len) return fail(PCO_B200_INVALID_ARGUMENT, "chunk offset " + std::to_string(i) + " lies outside the buffer");
+    if (chunk_ns[i] == 0 || chunk_ns[i] > (1u << 24)) return fail(PCO_B200_INVALID_ARGUMENT, "chunk " + std::to_string(i) + ": count must be 1..2^24");
+    recs[i].chunk_offset = chunk_offsets[i];
+    recs[i].n = chunk_ns[i];
+    recs[i].n_vars = 0;
+    recs[i].entries_offset = off;
+    recs[i].out_offset = out_off;
+    off += (uint64_t(MAX_VARS) * n_batches_of(chunk_ns[i]) * sizeof(BatchEntry) + 15) & ~uint64_t(15);
+    out_off += chunk_ns[i];
+  }
+  const uint64_t n_total = out_off;
+  if (n_total > dst_len) return fail(PCO_B200_INVALID_ARGUMENT, "dst holds " + std::to_string(dst_len) + " numbers, the chunks " + std::to_string(n_total));
+  const uint8_t* d_src;
+  if (src_dev) d_src = static_cast<const uint8_t*>(compressed);
+  else {
+    PCOB_CUDA_TRY(c.src.reserve(compressed_len + 16));
+    PCOB_CUDA_TRY(cudaMemcpyAsync(c.src.p, compressed, compressed_len, cudaMemcpyHostToDevice, stream));
+    d_src = c.src.as<uint8_t>();
+  }
+  FileParams fp{d_src, compressed_len, dtype, uniform_type, format_major};
+  PCOB_CUDA_TRY(c.index.reserve(off + 64));
+  uint8_t* d_index = c.index.as<uint8_t>();
+  PCOB_CUDA_TRY(cudaMemcpyAsync(d_index + chunks_offset, recs.data(), n_chunks * sizeof(IndexChunk), cudaMemcpyHostToDevice, stream));
+  PCOB_CUDA_TRY(c.statuses.reserve((n_chunks + 1) * sizeof(uint32_t)));
+  PCOB_CUDA_TRY(c.misc.reserve(sizeof(WalkResult)));
+  PCOB_CUDA_TRY(cudaMemsetAsync(c.statuses.p, 0xff, n_chunks * sizeof(uint32_t), stream));
+  profiler().begin("walk_kernel", stream);
+  walk_kernel<SMALL_MAX_SIZE_LOG><<<uint32_t(n_chunks), 128, sizeof(WalkSmem<SMALL_MAX_SIZE_LOG>), stream>>>(
+      fp, d_index, chunks_offset, uint32_t(n_chunks), 0, off, 0, 0, ~uint64_t(0), c.statuses.as<uint32_t>(), c.misc.as<WalkResult>(), 0);
+  profiler().end(stream);
+  PCOB_CUDA_TRY(cudaGetLastError());
+  {
+    std::vector<uint32_t> st(n_chunks);
+    PCOB_CUDA_TRY(cudaMemcpyAsync(st.data(), c.statuses.p, n_chunks * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
+    for (size_t i = 0; i < n_chunks; i++)
+      if (st[i] != ST_OK) { profiler().resolve(); return status_to_error(st[i], ("chunk " + std::to_string(i)).c_str()); }
+  }
+  void* d_out = dst;
+  if (!dst_dev) {
+    PCOB_CUDA_TRY(c.out.reserve(n_total * elem + 64));
+    d_out = c.out.p;
+  }
+  PcoB200Error e = launch_decode(c, fp, d_index, chunks_offset, uint32_t(n_chunks), d_out, dst_len, stream);
+  profiler().resolve();
+  if (e != PCO_B200_OK) return e;
+  if (!dst_dev && n_total) {
+    PCOB_CUDA_TRY(cudaMemcpyAsync(dst, d_out, n_total * elem, cudaMemcpyDeviceToHost, stream));
+    PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
+  }
+  if (n_written) *n_written = size_t(n_total);
+  return PCO_B200_OK;
+}
+
 PcoB200Error pco_b200_build_index(const void* compressed, size_t compressed_len, unsigned char dtype, void* index, size_t index_cap,
                                   size_t* index_len, uint32_t flags, void* cuda_stream) {
   if (!nt_valid(dtype)) return fail(PCO_B200_INVALID_TYPE, "unknown number type byte");
@@ -618,7 +713,7 @@ PcoB200Error pco_b200_build_index(const void* compressed, size_t compressed_len,
   PCOB_CUDA_TRY(c.index.reserve(index_cap));
   PCOB_CUDA_TRY(c.misc.reserve(sizeof(WalkResult)));
   uint8_t* d_index = c.index.as<uint8_t>();
-  walk_kernel<<<1, 128, sizeof(WalkSmem), stream>>>(fp, d_index, chunks_offset, uint32_t(max_chunks), entries_begin, index_cap, hdr.first_chunk_byte,
+  walk_kernel<12><<<1, 128, sizeof(WalkSmem<12>), stream>>>(fp, d_index, chunks_offset, uint32_t(max_chunks), entries_begin, index_cap, hdr.first_chunk_byte,
                                                     0, ~uint64_t(0), nullptr, c.misc.as<WalkResult>(), 1);
   PCOB_CUDA_TRY(cudaGetLastError());
   WalkResult res;

@@ -159,3 +159,22 @@ def simple_compress_into(nums, config=None):
 def simple_compress_with_index(nums, config=None, uniform_type=False):
     """simple_compress plus the per-batch side index the GPU decoder uses (metadata beside the .pco bytes)."""
     return _compress(nums, config, uniform_type, True)
+
+
+def decompress_chunks(src, dtype, chunk_offsets, chunk_ns):
+    """Batched, index-free decompress of chunks at known byte offsets (pco_b200_decompress_chunks): `src` is a standalone
+    file or bare chunks back to back; chunk_offsets[i] = byte offset of chunk i's type byte, chunk_ns[i] = its count.
+    The device walks every chunk's tANS stream in parallel to build the per-batch index, then decodes."""
+    L = _lib.lib()
+    arr, n = _src_buf(src)
+    offs = np.ascontiguousarray(chunk_offsets, dtype=np.uint64)
+    ns = np.ascontiguousarray(chunk_ns, dtype=np.uint32)
+    if offs.size != ns.size:
+        raise ValueError("chunk_offsets and chunk_ns differ in length")
+    dst = np.empty(int(ns.sum(dtype=np.uint64)), dtype=dtype)
+    n_written = C.c_size_t()
+    rc = L.pco_b200_decompress_chunks(arr.ctypes.data_as(C.c_void_p), C.c_size_t(n), C.c_ubyte(_lib.dtype_byte(dst.dtype)),
+                                      offs.ctypes.data_as(C.c_void_p), ns.ctypes.data_as(C.c_void_p), C.c_size_t(offs.size),
+                                      dst.ctypes.data_as(C.c_void_p), C.c_size_t(dst.size), C.byref(n_written), C.c_uint32(0), None)
+    _lib.check(rc)
+    return dst[: n_written.value]

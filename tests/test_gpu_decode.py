@@ -219,3 +219,63 @@ def test_chunks_starting_at_odd_element_offsets(sa, oracle, dtype):
         prog = sa.simple_decompress_into(data, out)
         assert prog.finished and prog.n_processed == n
         assert np.array_equal(bits_view(out), bits_view(x))
+
+
+# ---- pco_b200_decompress_chunks: batched decompress at known chunk offsets, no side index ----
+def _chunk_table(oracle, data, dtype):
+    info = oracle.inspect(data, dtype)
+    return [c["chunk_start"] for c in info["chunks"]], [c["n"] for c in info["chunks"]]
+
+
+_UNVALIDATED = pytest.mark.skipif(__import__("os").environ.get("PCOB200_UNVALIDATED") != "1", reason="not yet run on a GPU box")
+
+
+@_UNVALIDATED
+@pytest.mark.parametrize("dtype,mode,order", [(np.uint64, "classic", 1), (np.int32, "classic", 0), (np.float64, "float_mult", 2), (np.uint16, "classic", 2)])
+def test_decompress_chunks_at_known_offsets(sa, oracle, dtype, mode, order):
+    from pcodec_b200 import PcoError
+
+    n = 9 * 3000 + 17
+    if mode == "float_mult":
+        nums = (np.round(np.cumsum(np.random.default_rng(1).normal(size=n)) * 100) * 0.01).astype(dtype)
+        cfg = oracle.make_config(mode=oracle.MODE_FLOAT_MULT, float_mult_base=0.01, delta=oracle.DELTA_CONSECUTIVE, delta_order=order, max_page_n=3000)
+    else:
+        nums = _walk(dtype, n, seed=4)
+        cfg = oracle.make_config(mode=oracle.MODE_CLASSIC, delta=oracle.DELTA_CONSECUTIVE if order else oracle.DELTA_NOOP, delta_order=order, max_page_n=3000)
+    data = oracle.simple_compress(nums, cfg)
+    offs, ns = _chunk_table(oracle, data, dtype)
+    assert len(offs) > 5 and sum(ns) == n
+    got = sa.decompress_chunks(data, dtype, offs, ns)
+    assert np.array_equal(bits_view(got), bits_view(nums))
+    # any subset, in any order, lands back to back
+    pick = [4, 0, 2]
+    got = sa.decompress_chunks(data, dtype, [offs[i] for i in pick], [ns[i] for i in pick])
+    starts = np.concatenate([[0], np.cumsum(ns)])
+    want = np.concatenate([nums[starts[i]:starts[i + 1]] for i in pick])
+    assert np.array_equal(bits_view(got), bits_view(want))
+    # bare chunks (no standalone header): the bytes from the first chunk on
+    bare = data[offs[0]:]
+    got = sa.decompress_chunks(bare, dtype, [o - offs[0] for o in offs], ns)
+    assert np.array_equal(bits_view(got), bits_view(nums))
+    # a count that contradicts the chunk's own header, an offset outside the buffer, a truncated last chunk
+    bad = list(ns)
+    bad[1] += 1
+    with pytest.raises(PcoError) as e:
+        sa.decompress_chunks(data, dtype, offs, bad)
+    assert e.value.kind == "InvalidArgument"
+    with pytest.raises(PcoError) as e:
+        sa.decompress_chunks(data, dtype, offs[:-1] + [len(data) + 5], ns)
+    assert e.value.kind == "InvalidArgument"
+    with pytest.raises(PcoError) as e:
+        sa.decompress_chunks(data[: offs[-1] + 40], dtype, offs, ns)
+    assert e.value.kind in ("InsufficientData", "Corruption")
+
+
+@_UNVALIDATED
+def test_decompress_chunks_full_size(sa, oracle):
+    from pcodec_b200 import datagen
+
+    nums = np.concatenate([datagen.c2_u64_cumsum_geometric(seed=s) for s in (21, 22, 23, 24)])
+    data = oracle.simple_compress(nums, oracle.make_config(mode=oracle.MODE_CLASSIC, delta=oracle.DELTA_CONSECUTIVE, delta_order=1))
+    offs, ns = _chunk_table(oracle, data, np.uint64)
+    assert np.array_equal(sa.decompress_chunks(data, np.uint64, offs, ns), nums)

@@ -274,3 +274,67 @@ def test_reference_c_abi_compress_into(oracle):
     # too small a destination -> PcoCompressionError
     assert L.pco_standalone_simple_compress_into(nums.ctypes.data_as(C.c_void_p), C.c_size_t(nums.size), C.c_ubyte(4), None, dst.ctypes.data_as(C.c_void_p),
                                                  C.c_size_t(100), C.byref(n_written)) == 2
+
+
+# ---- split_count_kernel (one-pass split + delta + counting front end for classic-mode chunks spanning < 2^15) ----
+@pytest.mark.parametrize("dtype", [np.uint16, np.uint32, np.int64, np.float64])
+@pytest.mark.parametrize("order", [0, 1, 3, 4, 5, 6, 7])
+def test_one_pass_front_end_all_orders_and_unaligned_chunks(sa, oracle, dtype, order):
+    """Every stencil instantiation; chunk sizes that are not multiples of 4 put later chunks on the element-wise load path."""
+    rng = np.random.default_rng(order * 11 + np.dtype(dtype).itemsize)
+    n = 3 * 4099 + 2
+    # an order-`order` polynomial trend + small noise keeps the order-th differences narrow, whatever the order
+    noise = rng.integers(-40, 41, size=n).astype(np.int64)
+    base = noise.copy()
+    for _ in range(order):
+        base = np.cumsum(base)
+    dt = np.dtype(dtype)
+    if dt.kind == "f":
+        u = np.dtype(f"u{dt.itemsize}")
+        lat = (base.astype(np.uint64) + np.uint64(1 << (8 * dt.itemsize - 1)) + np.uint64(12345)).astype(u)
+        mid = u.type(1 << (8 * dt.itemsize - 1))
+        nums = np.where(lat & mid, lat ^ mid, ~lat).astype(u).view(dtype)
+    else:
+        nums = base.astype(np.uint64).astype(np.dtype(f"u{dt.itemsize}")).view(dtype)
+    ours_cfg, their_cfg = _cfgs(oracle, order=order, max_page_n=4099)
+    ours = sa.simple_compress(nums, ours_cfg)
+    theirs = oracle.simple_compress(nums, their_cfg)
+    assert ours == theirs, _diff_report(oracle, ours, theirs, dtype)
+    assert np.array_equal(bits_view(sa.simple_decompress(ours, dtype)), bits_view(nums))
+
+
+def test_one_pass_front_end_range_boundary_and_rotation(sa, oracle):
+    """Ranges of exactly 2^15 - 1 (counting path) and 2^15 (a wide chunk: the whole call is redone on the two-kernel path), with
+    the anchor (first stored latent) at the bottom, the top and the middle of the range; constant and tiny chunks."""
+    rng = np.random.default_rng(3)
+    for span in (32767, 32768, 5, 0):
+        for first in ("min", "max", "mid"):
+            vals = rng.integers(0, span + 1, size=9000).astype(np.int64)
+            vals[7], vals[8] = 0, span  # both ends are present
+            vals[0] = {"min": 0, "max": span, "mid": span // 2}[first]
+            for dtype in (np.uint32, np.int64):
+                nums = (vals + 1000).astype(np.dtype(dtype))
+                ours_cfg, their_cfg = _cfgs(oracle, order=0)
+                ours = sa.simple_compress(nums, ours_cfg)
+                theirs = oracle.simple_compress(nums, their_cfg)
+                assert ours == theirs, (span, first, dtype, _diff_report(oracle, ours, theirs, dtype))
+    for n in (1, 2, 3, 4, 5, 8, 9):
+        for order in (0, 1, 2, 7):
+            nums = (np.arange(n, dtype=np.uint64) * 3 + 7) ** 2
+            ours_cfg, their_cfg = _cfgs(oracle, order=order)
+            ours = sa.simple_compress(nums, ours_cfg)
+            theirs = oracle.simple_compress(nums, their_cfg)
+            assert ours == theirs, (n, order, _diff_report(oracle, ours, theirs, np.uint64))
+
+
+def test_one_wide_chunk_among_narrow_ones(sa, oracle):
+    rng = np.random.default_rng(8)
+    parts = [np.cumsum(rng.geometric(0.01, size=4096)).astype(np.uint64) for _ in range(5)]
+    parts[3] = rng.integers(0, 1 << 40, size=4096).astype(np.uint64)
+    nums = np.concatenate(parts)
+    for order in (0, 1):
+        ours_cfg, their_cfg = _cfgs(oracle, order=order, max_page_n=4096)
+        ours = sa.simple_compress(nums, ours_cfg)
+        theirs = oracle.simple_compress(nums, their_cfg)
+        assert ours == theirs, _diff_report(oracle, ours, theirs, np.uint64)
+        assert np.array_equal(sa.simple_decompress(ours, np.uint64), nums)
