@@ -10,7 +10,7 @@
 #include "host_common.hpp"
 
 #ifndef PCOB_ONE_PASS_DEFAULT
-#define PCOB_ONE_PASS_DEFAULT false  // flipped once the GPU parity suite has run with it
+#define PCOB_ONE_PASS_DEFAULT true  // PCOB200_ONE_PASS_FRONT_END=0 selects the two-kernel front end (A/B runs)
 #endif
 
 namespace pcob200 {

@@ -101,6 +101,7 @@ __device__ __forceinline__ void narrow_chunk(NarrowSmem& sm, const FileParams& f
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(win_sa + bufi * uint32_t(NW_WIN_WORDS * 4) + uint32_t(lane) * 16u), "l"(gp));
     asm volatile("cp.async.commit_group;");
   };
+  // (one cp.async.bulk of the 512 bytes per batch, signalled on an mbarrier, instead of 32 LDGSTS: correct, but 0.500 ms against 0.487 ms)
 
   // a batch's section start is requested two batches ahead, its symbols and its window one batch ahead
   constexpr int SY_STEP = NW_WARPS * (BATCH_N / 8);  // uint2 per round of NW_WARPS batches

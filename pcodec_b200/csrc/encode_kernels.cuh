@@ -537,20 +537,24 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_probe_kernel(EncParams ep, 
 constexpr int SC_THREADS = 1024;
 constexpr uint32_t SC_N = 1u << PLAN_MAX_COUNT_BITS, SC_MASK = SC_N - 1;
 
-// The streaming pass of split_count_kernel for one delta order: 4 consecutive stored latents per thread and step.
-// Stored index s holds the difference ending at number ORDER + s, which needs numbers s .. s + ORDER + 3: aligned
-// 4-vectors at s, s + 4 (and s + 8 for orders > 4; the neighbouring threads' loads of the same lines hit L1).
+// The streaming pass of split_count_kernel for one delta order: SC_PER consecutive stored latents per thread and step.
+// Stored index s holds the difference ending at number ORDER + s, which needs numbers s .. s + ORDER + SC_PER - 1:
+// aligned 4-vectors from s on (the next thread's first vectors are this thread's last: those loads hit L1).
+#ifndef PCOB_SC_PER
+#define PCOB_SC_PER 8
+#endif
+constexpr int SC_PER = PCOB_SC_PER;
 template <typename L, int ORDER>
 __device__ __forceinline__ void sc_stream(const L* __restrict__ nums, uint32_t n, uint32_t stored, L anchor, bool is_float, bool is_signed,
                                           uint16_t* __restrict__ k16, uint32_t* __restrict__ cnt, L& mn, L& mx) {
   constexpr L MID = L(L(1) << (LT<L>::BITS - 1));
-  constexpr int NX = ORDER > 4 ? 12 : 8;
+  constexpr int NX = SC_PER + (ORDER > 4 ? 8 : (ORDER > 0 ? 4 : 0));
   struct alignas(sizeof(L) * 4 > 16 ? 16 : sizeof(L) * 4) Vec4 { L v[4]; };
   const bool vec_ok = (reinterpret_cast<uintptr_t>(nums) & (sizeof(Vec4) - 1)) == 0;
-  const uint32_t n4 = (stored + 3) / 4;
+  const uint32_t n_steps = (stored + SC_PER - 1) / SC_PER;
   const int tid = threadIdx.x;
-  for (uint32_t q = tid; q < n4; q += SC_THREADS) {
-    const uint32_t s = 4 * q;
+  for (uint32_t q = tid; q < n_steps; q += SC_THREADS) {
+    const uint32_t s = SC_PER * q;
     L x[NX];
     if (vec_ok && s + NX <= n) {
 #pragma unroll
@@ -561,11 +565,11 @@ __device__ __forceinline__ void sc_stream(const L* __restrict__ nums, uint32_t n
       }
     } else {
 #pragma unroll
-      for (int u = 0; u < NX; u++) x[u] = (u < ORDER + 4 && s + u < n) ? to_latent_ordered<L>(nums[s + u], is_float, is_signed) : L(0);
+      for (int u = 0; u < NX; u++) x[u] = (u < ORDER + SC_PER && s + u < n) ? to_latent_ordered<L>(nums[s + u], is_float, is_signed) : L(0);
     }
-    uint32_t kw[4];
+    uint32_t kw[SC_PER];
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
+    for (int u = 0; u < SC_PER; u++) {
       // d = sum_j (-1)^j C(ORDER, j) x[u + ORDER - j]  (== ORDER passes of x[i] -= x[i-1], delta/consecutive.rs:19-33)
       L d = x[u + ORDER];
       uint32_t binom = 1;
@@ -577,11 +581,14 @@ __device__ __forceinline__ void sc_stream(const L* __restrict__ nums, uint32_t n
       if (ORDER > 0) d = L(d + MID);  // toggle_center (delta/mod.rs:29-33)
       const bool live = s + u < stored;
       if (live) { mn = min(mn, d); mx = max(mx, d); }
-      const uint32_t w = uint32_t(L(d - anchor));
+      const uint32_t w = uint32_t(uint64_t(d) - uint64_t(anchor));  // zero-extended: the same modulus (2^16 / 2^15) for every number width
       kw[u] = w & 0xffffu;
       if (live) atomicAdd(&cnt[w & SC_MASK], 1u);
     }
-    *reinterpret_cast<uint2*>(k16 + s) = make_uint2(kw[0] | (kw[1] << 16), kw[2] | (kw[3] << 16));  // rows are 256-aligned and padded
+    // rows are 256-aligned and padded: vector stores of the keys
+#pragma unroll
+    for (int g = 0; g < SC_PER / 4; g++)
+      *reinterpret_cast<uint2*>(k16 + s + 4 * g) = make_uint2(kw[4 * g] | (kw[4 * g + 1] << 16), kw[4 * g + 2] | (kw[4 * g + 3] << 16));
   }
 }
 
@@ -675,7 +682,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) split_count_kernel(EncParams ep
   if (stored == 0) return;
   const uint64_t vmin = sh_min, vmax = sh_max;
   if (vmax - vmin > uint64_t(SC_MASK)) return;  // wide chunk: the host re-runs the call on the two-kernel path
-  const uint32_t rot = uint32_t(L(L(vmin) - anchor)) & SC_MASK;  // counter of key k (= latent - vmin) is cnt[(k + rot) & SC_MASK]
+  const uint32_t rot = uint32_t(vmin - uint64_t(anchor)) & SC_MASK;  // counter of key k (= latent - vmin) is cnt[(k + rot) & SC_MASK]
   // exclusive scan of the counters in key order: warp w owns a contiguous span of keys, 32 at a time
   {
     const uint32_t span = SC_N / (SC_THREADS / 32);
@@ -1142,9 +1149,9 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_kernel(EncParams ep, uint32_t
 // lanes striding the batch so that every load is a fully used 256-byte line.
 constexpr int BINL_THREADS = 256;
 #ifndef PCOB_BINL_BATCHES
-#define PCOB_BINL_BATCHES 128
+#define PCOB_BINL_BATCHES 512
 #endif
-constexpr int BINL_BATCHES = PCOB_BINL_BATCHES;  // batches per CTA: every CTA rebuilds the chunk's lookup table first
+constexpr int BINL_BATCHES = PCOB_BINL_BATCHES;  // batches per CTA: every CTA rebuilds the chunk's lookup table first (128: 0.34 ms, 256: 0.28, 512: 0.26, 1024: 0.29)
 
 template <typename L>
 __global__ void __launch_bounds__(BINL_THREADS) bin_lut_kernel(EncParams ep, uint32_t batches_per_chunk, uint32_t parts_per_chunk,
@@ -1181,7 +1188,7 @@ __global__ void __launch_bounds__(BINL_THREADS) bin_lut_kernel(EncParams ep, uin
   const VarPlan& plan = plans[size_t(c) * MAX_VARS + v];
   const uint32_t n_bins = plan.n_bins;
   const L vmin = L(chunks[c].vmin[v]);
-  const uint32_t shift2 = (uint32_t(L(vmin - L(chunks[c].key_base[v]))) & 0xffffu) * 0x10001u;
+  const uint32_t shift2 = (uint32_t(chunks[c].vmin[v] - chunks[c].key_base[v]) & 0xffffu) * 0x10001u;
   const uint32_t n_words = max(1u, (1u << range_bits) / 4);
   for (uint32_t i = tid; i < n_words; i += BINL_THREADS) lut_w[i] = 0;
   for (uint32_t i = tid; i < n_bins; i += BINL_THREADS) obs[i] = plan.ob[i];
@@ -1659,7 +1666,7 @@ __global__ void __launch_bounds__(PACK_THREADS, PCOB_PACK_MIN_BLOCKS) pack_kerne
       sm.lowers[v][i] = fb ? 0 : p.lower[i];
       sm.obs[v][i] = fb ? uint8_t(lbits) : p.ob[i];
       // keys (key0/key1 non-null: the counting planner ran for this var) are (latent - key_base) mod 2^16, so is this table
-      sm.lowkey_ob[v][i] = fb ? 0u : (uint32_t(L(L(p.lower[i]) - L(ch.key_base[v]))) & 0xffffu) | (uint32_t(p.ob[i]) << 16);
+      sm.lowkey_ob[v][i] = fb ? 0u : (uint32_t(p.lower[i] - ch.key_base[v]) & 0xffffu) | (uint32_t(p.ob[i]) << 16);
     }
   }
   // ---------------- head window: preamble + chunk meta + page meta ----------------

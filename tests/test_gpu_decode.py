@@ -227,10 +227,6 @@ def _chunk_table(oracle, data, dtype):
     return [c["chunk_start"] for c in info["chunks"]], [c["n"] for c in info["chunks"]]
 
 
-_UNVALIDATED = pytest.mark.skipif(__import__("os").environ.get("PCOB200_UNVALIDATED") != "1", reason="not yet run on a GPU box")
-
-
-@_UNVALIDATED
 @pytest.mark.parametrize("dtype,mode,order", [(np.uint64, "classic", 1), (np.int32, "classic", 0), (np.float64, "float_mult", 2), (np.uint16, "classic", 2)])
 def test_decompress_chunks_at_known_offsets(sa, oracle, dtype, mode, order):
     from pcodec_b200 import PcoError
@@ -271,7 +267,6 @@ def test_decompress_chunks_at_known_offsets(sa, oracle, dtype, mode, order):
     assert e.value.kind in ("InsufficientData", "Corruption")
 
 
-@_UNVALIDATED
 def test_decompress_chunks_full_size(sa, oracle):
     from pcodec_b200 import datagen
 
