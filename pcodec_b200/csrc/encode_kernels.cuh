@@ -1245,7 +1245,7 @@ __global__ void __launch_bounds__(BINL_THREADS) bin_lut_kernel(EncParams ep, uin
 // ---------------------------------------------------------------------------
 // K4: reverse tANS.  One warp per (chunk, var); lanes 0-3 carry the 4 interleaved states over the whole page
 // (latency-bound serial chains); all lanes stage symbols in and results out.
-// Output per latent: u16 = ans_val | (1 << ans_bits)  (length-prefixed, ans_bits <= 14)
+// Output per latent: u16 = ans_val | ans_bits << 12  (ans_bits <= ENC_MAX_SIZE_LOG = 10)
 // ---------------------------------------------------------------------------
 // The encoder state chain of a page is serial (each step's state feeds the next, 2^16 steps per chain), but a tANS
 // step with a symbol of weight w maps all 2^size_log states onto w values, so two trajectories that start from different
@@ -1269,12 +1269,11 @@ struct AnsSmem {
   uint16_t carry[4];
 };
 
-// One tANS step (ans/encoding.rs:72-83) from a pre-resolved descriptor; returns the bit count, `o` = value | 1 << bits.
+// One tANS step (ans/encoding.rs:72-83) from a pre-resolved descriptor; returns the bit count, `o` = value | bits << 12.
 __device__ __forceinline__ uint32_t ans_step(uint32_t d, uint32_t& state, uint32_t& o, const uint16_t* next_states) {
   const uint32_t cutoff = d & 0xfffu, mr = (d >> 12) & 0xfu, base = d >> 16;
   const uint32_t bits = mr + (state >= cutoff ? 1u : 0u);
-  const uint32_t top = 1u << bits;
-  o = (state & (top - 1)) | top;
+  o = (state & ((1u << bits) - 1)) | (bits << 12);  // bits <= ENC_MAX_SIZE_LOG = 10: value in bits 0-9, width in bits 12-15
   state = next_states[base + (state >> bits) - 2048u];
   return bits;
 }
@@ -1739,6 +1738,7 @@ __global__ void __launch_bounds__(PACK_THREADS, PCOB_PACK_MIN_BLOCKS) pack_kerne
   const uint32_t stored_0 = uint32_t(ce - (fb ? cs : stored_begin(cs, ce, order))), stored_1 = uint32_t(ce - cs);
   const uint16_t* const keyp_0 = fb ? nullptr : key0;
   const uint16_t* const keyp_1 = fb ? nullptr : key1;
+  const bool lean = n_vars == 1 && keyp_0 != nullptr && ans_0 && mob_0 > 0 && mob_0 <= 15;
   uint32_t b0 = 0;
   uint64_t win_p0 = (body_bit0 + skew) & ~uint64_t(31);
   while (b0 < nb) {
@@ -1767,8 +1767,10 @@ __global__ void __launch_bounds__(PACK_THREADS, PCOB_PACK_MIN_BLOCKS) pack_kerne
     const uint32_t bv_end = b1 * n_vars;
     uint2 nx_s8 = make_uint2(0u, 0u);
     uint4 nx_a8 = make_uint4(0u, 0u, 0u, 0u), nx_k8 = make_uint4(0u, 0u, 0u, 0u);
+    uint32_t nx_pos = 0;
     auto prefetch = [&](uint32_t bvn) {
       const uint32_t bn = n_vars == 1 ? bvn : bvn / n_vars, vn = n_vars == 1 ? 0u : bvn % n_vars;
+      nx_pos = entries[(size_t(c) * MAX_VARS + vn) * batches_per_chunk + bn].bit_pos;
       const uint64_t row = rb + uint64_t(bn) * BATCH_N + lane * 8;
       nx_s8 = *reinterpret_cast<const uint2*>((vn == 0 ? sym0 : sym1) + row);
       if (vn == 0 ? ans_0 : ans_1) nx_a8 = *reinterpret_cast<const uint4*>((vn == 0 ? ans0 : ans1) + row);
@@ -1781,14 +1783,40 @@ __global__ void __launch_bounds__(PACK_THREADS, PCOB_PACK_MIN_BLOCKS) pack_kerne
       const uint32_t b = n_vars == 1 ? bv : bv / n_vars, v = n_vars == 1 ? 0u : bv % n_vars;
       const uint2 s8 = nx_s8;
       const uint4 a8 = nx_a8, k8 = nx_k8;
+      const uint32_t my_pos = nx_pos;
       if (bv + PACK_THREADS / 32 < bv_end) prefetch(bv + PACK_THREADS / 32);
       const uint32_t cnt = batch_count(v == 0 ? stored_0 : stored_1, b);
       if (cnt == 0) continue;
+      if (lean && cnt == uint32_t(BATCH_N)) {
+        // ---- the common case, without the generality: one var, tANS fields and 16-bit keys, a full batch.  Field widths
+        // come ready-made (tANS: bits 12-15 of the field; offsets: the table entry), both lane totals go through ONE scan.
+        const uint32_t p = uint32_t(my_pos + skew - win_p0);
+        const uint32_t aw[4] = {a8.x, a8.y, a8.z, a8.w}, kw[4] = {k8.x, k8.y, k8.z, k8.w};
+        uint32_t a_val[8], a_bits[8], o32[8], o_bits[8], tot = 0;
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+          const uint32_t x = aw[e >> 1] >> (16 * (e & 1));
+          a_bits[e] = (x >> 12) & 0xfu;
+          a_val[e] = x & 0xfffu;
+          const uint32_t t = sm.lowkey_ob[0][((e < 4 ? s8.x : s8.y) >> (8 * (e & 3))) & 0xffu];
+          o_bits[e] = t >> 16;
+          o32[e] = ((kw[e >> 1] >> (16 * (e & 1))) - t) & 0xffffu;
+          tot += a_bits[e] + (o_bits[e] << 16);
+        }
+        uint32_t inc = tot;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+        const uint32_t ans_total = __shfl_sync(0xffffffffu, inc, 31) & 0xffffu;
+        const uint32_t exc = inc - tot;
+        if (tot & 0xffffu) emit8_narrow(sm.win, p + (exc & 0xffffu), a_val, a_bits);
+        if (tot >> 16) emit8_narrow(sm.win, p + ans_total + (exc >> 16), o32, o_bits);
+        continue;
+      }
       const bool needs_ans = v == 0 ? ans_0 : ans_1;
       const uint32_t max_ob = v == 0 ? mob_0 : mob_1;
       const uint64_t sb = fb ? cs : stored_begin(cs, ce, v == 0 ? order : 0);
       const L* latp = (v == 0 ? lat0 : lat1) + rb + uint64_t(b) * BATCH_N;
-      uint32_t pos = uint32_t(entry_pos(b, v) - win_p0);
+      uint32_t pos = uint32_t(my_pos + skew - win_p0);
       // lane owns elements 8 lane .. 8 lane + 7: its fields are contiguous in the stream, so it assembles them in a
       // register and ORs whole 32-bit words into the window.  Rows are 256-aligned (split_delta_kernel): vector loads.
       const uint32_t first = lane * 8;
@@ -1803,9 +1831,9 @@ __global__ void __launch_bounds__(PACK_THREADS, PCOB_PACK_MIN_BLOCKS) pack_kerne
         for (int e = 0; e < 8; e++) {
           const uint32_t x = (aw[e >> 1] >> (16 * (e & 1))) & 0xffffu;
           const bool live = first + e < cnt;
-          const uint32_t nbits = live ? 31 - __clz(x | 1u) : 0u;
+          const uint32_t nbits = live ? x >> 12 : 0u;
           a_bits[e] = nbits;
-          a_val[e] = live ? x ^ (1u << nbits) : 0u;
+          a_val[e] = live ? x & 0xfffu : 0u;
           a_tot += nbits;
         }
       } else {
@@ -1879,6 +1907,9 @@ __global__ void __launch_bounds__(PACK_THREADS, PCOB_PACK_MIN_BLOCKS) pack_kerne
     {
       uint32_t* gw = dst_words + (win_p0 >> 5);
       const uint64_t byte0 = win_p0 >> 3;
+      if (byte0 >= lo_byte && byte0 + 4ull * whole_words <= hi_byte) {  // every word lies inside the body: plain copy
+        for (uint32_t i = tid; i < whole_words; i += PACK_THREADS) gw[i] = sm.win[i];
+      } else
       for (uint32_t i = tid; i < whole_words; i += PACK_THREADS) {
         const uint64_t wb0 = byte0 + 4ull * i;
         const uint32_t word = sm.win[i];
