@@ -72,8 +72,13 @@ __global__ void range_bits_kernel(ChunkEnc* chunks, uint32_t n_chunks, int v, ui
 
 // internal entries [(c, v)][batches_per_chunk] -> compact side index
 __global__ void emit_index_kernel(EncParams ep, uint32_t batches_per_chunk, const ChunkEnc* chunks, const BatchEntry* entries, uint8_t* index,
-                                  uint64_t chunks_offset, const uint64_t* entry_offsets) {
+                                  uint64_t chunks_offset, const uint64_t* entry_offsets, const uint64_t* total_bytes, uint32_t has_terminator) {
   const uint32_t c = blockIdx.x;
+  if (c == 0 && threadIdx.x == 0) {  // the file size is known on the device first: the host need not wait for it to write the header
+    IndexHeader* ih = reinterpret_cast<IndexHeader*>(index);
+    ih->file_len = *total_bytes;
+    ih->end_byte = has_terminator ? *total_bytes : 0;
+  }
   const uint64_t cs = ep.chunk_starts[c], ce = ep.chunk_starts[c + 1];
   const uint32_t n = uint32_t(ce - cs);
   const uint32_t nb = n_batches_of(n);
@@ -433,25 +438,28 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
   profiler().end(stream);
   chunk_offsets_kernel<<<1, 1024, 0, stream>>>(d_chunks, n_chunks, header.size(), chunks_only ? 0u : 1u, d_total);
   uint64_t total = 0;
-  PCOB_CUDA_TRY(cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, stream));
-  PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
-  PCOB_CUDA_TRY(cudaGetLastError());
-  if (total > dst_cap) return fail(PCO_B200_IO, "failed to write whole buffer (need " + std::to_string(total) + " bytes, dst_cap " + std::to_string(dst_cap) + ")");
   uint8_t* d_out = static_cast<uint8_t*>(dst);
   if (!dst_dev) {
+    // the staging buffer is sized from the file size, so that is needed first
+    PCOB_CUDA_TRY(cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, stream));
+    PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
+    PCOB_CUDA_TRY(cudaGetLastError());
+    if (total > dst_cap) return fail(PCO_B200_IO, "failed to write whole buffer (need " + std::to_string(total) + " bytes, dst_cap " + std::to_string(dst_cap) + ")");
     PCOB_CUDA_TRY(S.out.reserve(total + 64));
     d_out = S.out.as<uint8_t>();
   }
+  // device destination: no host round trip here - pack_kernel leaves out any chunk that would not fit dst_cap, and the size
+  // is checked when it is read back behind the kernel
+  const uint64_t out_cap = dst_dev ? uint64_t(dst_cap) : total;
   profiler().begin("pack_kernel", stream);
   pack_kernel<L><<<n_chunks, PACK_THREADS, sizeof(PackSmem), stream>>>(ep, bpc, d_lat[0], d_lat[1], d_plans, d_chunks, d_sym[0], d_sym[1], d_ans[0], d_ans[1],
-                                                                      S.entries.as<BatchEntry>(), d_out, total,
+                                                                      S.entries.as<BatchEntry>(), d_out, out_cap,
                                                                       var_range_bits[0] <= PLAN_MAX_COUNT_BITS ? S.key16_0.as<uint16_t>() : nullptr,
                                                                       (ep.n_vars > 1 && var_range_bits[1] <= PLAN_MAX_COUNT_BITS) ? S.key16_1.as<uint16_t>() : nullptr);
   profiler().end(stream);
-  if (!chunks_only) header_footer_kernel<<<1, 32, 0, stream>>>(d_out, total, d_header, uint32_t(header.size()), d_total);
+  if (!chunks_only) header_footer_kernel<<<1, 32, 0, stream>>>(d_out, out_cap, d_header, uint32_t(header.size()), d_total);
   PCOB_CUDA_TRY(cudaGetLastError());
   if (!dst_dev) PCOB_CUDA_TRY(cudaMemcpyAsync(dst, d_out, total, cudaMemcpyDeviceToHost, stream));
-  res->total_bytes = total;
   // ---- optional side index
   if (index_dst != nullptr) {
     const uint64_t chunks_offset = sizeof(IndexHeader);
@@ -469,15 +477,19 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
     PCOB_CUDA_TRY(cudaMemcpyAsync(S.seg.p, eoff.data(), size_t(n_chunks) * 8, cudaMemcpyHostToDevice, stream));
     IndexHeader ih;
     std::memset(&ih, 0, sizeof(ih));
-    ih.magic = INDEX_MAGIC; ih.version = 1; ih.n_chunks = n_chunks; ih.n_total = n; ih.file_len = total; ih.chunks_offset = chunks_offset; ih.end_byte = chunks_only ? 0 : total;
+    ih.magic = INDEX_MAGIC; ih.version = 1; ih.n_chunks = n_chunks; ih.n_total = n; ih.chunks_offset = chunks_offset;  // file_len, end_byte: emit_index_kernel
     PCOB_CUDA_TRY(cudaMemcpyAsync(idx.p, &ih, sizeof(ih), cudaMemcpyHostToDevice, stream));
-    emit_index_kernel<<<n_chunks, 256, 0, stream>>>(ep, bpc, d_chunks, S.entries.as<BatchEntry>(), idx.as<uint8_t>(), chunks_offset, S.seg.as<uint64_t>());
+    emit_index_kernel<<<n_chunks, 256, 0, stream>>>(ep, bpc, d_chunks, S.entries.as<BatchEntry>(), idx.as<uint8_t>(), chunks_offset, S.seg.as<uint64_t>(), d_total,
+                                                    chunks_only ? 0u : 1u);
     PCOB_CUDA_TRY(cudaGetLastError());
     PCOB_CUDA_TRY(cudaMemcpyAsync(index_dst, idx.p, off, (flags & PCO_B200_INDEX_ON_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, stream));
     res->index_bytes = off;
   }
+  if (dst_dev) PCOB_CUDA_TRY(cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, stream));  // read back behind the kernels
   PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
   PCOB_CUDA_TRY(cudaGetLastError());
+  if (total > dst_cap) return fail(PCO_B200_IO, "failed to write whole buffer (need " + std::to_string(total) + " bytes, dst_cap " + std::to_string(dst_cap) + ")");
+  res->total_bytes = total;
   return PCO_B200_OK;
 }
 

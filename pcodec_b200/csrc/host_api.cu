@@ -151,11 +151,21 @@ static PcoB200Error decompress_core(const void* compressed, size_t compressed_le
   // 1. standalone header (host parse of the first bytes)
   uint8_t head[32] = {0};
   size_t avail = std::min<size_t>(compressed_len, sizeof(head));
+  // the file header and (when it lives on the device) the side index header come back in one round trip
+  const bool have_index = index != nullptr && index_len >= sizeof(IndexHeader);
+  const bool idx_dev = flags & PCO_B200_INDEX_ON_DEVICE;
+  IndexHeader ih;
+  std::memset(&ih, 0, sizeof(ih));
+  bool need_sync = false;
   if (avail) {
-    if (src_dev) PCOB_CUDA_TRY(cudaMemcpyAsync(head, compressed, avail, cudaMemcpyDeviceToHost, stream));
+    if (src_dev) { PCOB_CUDA_TRY(cudaMemcpyAsync(head, compressed, avail, cudaMemcpyDeviceToHost, stream)); need_sync = true; }
     else std::memcpy(head, compressed, avail);
-    if (src_dev) PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
   }
+  if (have_index) {
+    if (idx_dev) { PCOB_CUDA_TRY(cudaMemcpyAsync(&ih, index, sizeof(ih), cudaMemcpyDeviceToHost, stream)); need_sync = true; }
+    else std::memcpy(&ih, index, sizeof(ih));
+  }
+  if (need_sync) PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
   StandaloneHeader hdr;
   if (PcoB200Error e = parse_standalone_header(head, avail, compressed_len, &hdr)) return e;
 
@@ -175,15 +185,7 @@ static PcoB200Error decompress_core(const void* compressed, size_t compressed_le
   fp.format_major = hdr.format_major;
 
   // 3a. caller-supplied side index
-  if (index != nullptr && index_len >= sizeof(IndexHeader)) {
-    const bool idx_dev = flags & PCO_B200_INDEX_ON_DEVICE;
-    IndexHeader ih;
-    if (idx_dev) {
-      PCOB_CUDA_TRY(cudaMemcpyAsync(&ih, index, sizeof(ih), cudaMemcpyDeviceToHost, stream));
-      PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
-    } else {
-      std::memcpy(&ih, index, sizeof(ih));
-    }
+  if (have_index) {
     if (ih.magic != INDEX_MAGIC || ih.version != 1 || ih.file_len != compressed_len || ih.chunks_offset + ih.n_chunks * sizeof(IndexChunk) > index_len)
       return fail(PCO_B200_INVALID_ARGUMENT, "side index does not belong to this file");
     const uint8_t* d_idx = static_cast<const uint8_t*>(index);
