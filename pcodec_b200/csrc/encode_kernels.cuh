@@ -837,14 +837,13 @@ __global__ void __launch_bounds__(SOLVE_THREADS) plan_solve_kernel(EncParams ep,
       float cost = __fadd_rn(sm.best_cost[j], bin_cost_dev(bin_meta_cost, upper - sm.h_lower[j], cci - sm.c_counts[j], total_log2));
       if (cost < my_cost) { my_cost = cost; my_j = uint32_t(j); }
     }
-    // warp argmin with "largest j among equal costs" (one warp per chunk: no block barrier on the DP's serial axis)
-    for (int d = 16; d > 0; d >>= 1) {
-      float oc = __shfl_xor_sync(0xffffffffu, my_cost, d);
-      uint32_t oj = __shfl_xor_sync(0xffffffffu, my_j, d);
-      bool take = (oj != 0xffffffffu) && (my_j == 0xffffffffu || oc < my_cost || (oc == my_cost && oj > my_j));
-      if (take) { my_cost = oc; my_j = oj; }
-    }
-    if (tid == 0) { sm.best_cost[i + 1] = my_cost; sm.best_j[i] = my_j; }
+    // warp argmin with "largest j among equal costs" (one warp per chunk: no block barrier on the DP's serial axis).
+    // Costs are non-negative floats, so their bit patterns order like the values: two hardware reductions (REDUX) - the
+    // smallest cost, then the largest j among the lanes that hold it - instead of five rounds of shuffles and compares.
+    const uint32_t cbits = my_j == 0xffffffffu ? 0xffffffffu : __float_as_uint(my_cost);
+    const uint32_t cmin = __reduce_min_sync(0xffffffffu, cbits);
+    const uint32_t jbest = __reduce_max_sync(0xffffffffu, (cbits == cmin && my_j != 0xffffffffu) ? my_j + 1u : 0u) - 1u;
+    if (tid == 0) { sm.best_cost[i + 1] = __uint_as_float(cmin); sm.best_j[i] = jbest; }
     __syncwarp();
   }
   ENC_TICK(4);  // DP
@@ -1263,25 +1262,27 @@ constexpr int ANS_WARM_BATCHES = 2;         // batches of the preceding segment 
 constexpr uint32_t ANS_MAX_SEG_BATCHES = 16;
 
 struct AnsSmem {
-  uint32_t desc_tab[ENC_MAXB];                 // per symbol: cutoff (12 bits) | min_renorm_bits << 12 | (cum - weight + 2048) << 16
+  uint32_t desc_tab[ENC_MAXB];                 // per symbol: ((min_renorm_bits + 1) << 16 - cutoff) | (cum - weight + 1024) << 20 (see ans_step)
   uint16_t next_states[1 << ENC_MAX_SIZE_LOG];  // full next state (size + slot), indexed cum + (x_s - weight)
   uint16_t out_state[ANS_SEGS][4];
   uint16_t carry[4];
 };
 
 // One tANS step (ans/encoding.rs:72-83) from a pre-resolved descriptor; returns the bit count, `o` = value | bits << 12.
+// The descriptor holds the step as two additions (the FSE formulation of the same arithmetic) in one 32-bit word:
+//   bits 0-19  A = (min_renorm_bits + 1) << 16 - cutoff :  bits = (state + A) >> 16       (= min_renorm_bits + (state >= cutoff))
+//   bits 20-31 B = cum - weight + 1024                   :  next  = next_states[B - 1024 + (state >> bits)]
+// (an 8-byte descriptor saves one more instruction per step but doubles the wavefronts of the lookups: 0.435 -> 0.467 ms)
 __device__ __forceinline__ uint32_t ans_step(uint32_t d, uint32_t& state, uint32_t& o, const uint16_t* next_states) {
-  const uint32_t cutoff = d & 0xfffu, mr = (d >> 12) & 0xfu, base = d >> 16;
-  const uint32_t bits = mr + (state >= cutoff ? 1u : 0u);
-  o = (state & ((1u << bits) - 1)) | (bits << 12);  // bits <= ENC_MAX_SIZE_LOG = 10: value in bits 0-9, width in bits 12-15
-  state = next_states[base + (state >> bits) - 2048u];
+  const uint32_t bits = ((state + d) >> 16) & 0xfu;  // state < 2^11 and B sits above bit 19: no carry into B
+  o = (state & ~(0xffffffffu << bits)) | (bits << 12);  // bits <= ENC_MAX_SIZE_LOG = 10: value in bits 0-9, width in bits 12-15
+  state = (next_states - 1024)[(d >> 20) + (state >> bits)];
   return bits;
 }
 // the same step without the output (warm-up, and the guessed trajectory replayed next to the true one)
 __device__ __forceinline__ uint32_t ans_step_quiet(uint32_t d, uint32_t& state, const uint16_t* next_states) {
-  const uint32_t cutoff = d & 0xfffu, mr = (d >> 12) & 0xfu, base = d >> 16;
-  const uint32_t bits = mr + (state >= cutoff ? 1u : 0u);
-  state = next_states[base + (state >> bits) - 2048u];
+  const uint32_t bits = ((state + d) >> 16) & 0xfu;
+  state = (next_states - 1024)[(d >> 20) + (state >> bits)];
   return bits;
 }
 
@@ -1363,7 +1364,7 @@ __global__ void __launch_bounds__(ANS_THREADS, 4) ans_encode_kernel(EncParams ep
     // entries past n_bins alias symbol 0 (never looked up: every staged symbol is < n_bins)
     const uint64_t info = plan.syminfo[i < n_bins ? i : 0];
     const uint32_t cutoff = uint32_t(info & 0xffff), mr = uint32_t(info >> 16) & 0xff, w = uint32_t(info >> 24) & 0xffff, cum = uint32_t(info >> 40) & 0xffff;
-    sm.desc_tab[i] = cutoff | (mr << 12) | ((cum + 2048u - w) << 16);
+    sm.desc_tab[i] = (((mr + 1u) << 16) - cutoff) | ((cum + 1024u - w) << 20);
   }
   for (uint32_t i = tid; i < size; i += ANS_THREADS) sm.next_states[i] = uint16_t(size + plan.next_states[i]);
   const uint32_t nb = n_batches_of(n);
