@@ -267,6 +267,38 @@ def run_gpu_arm(args, rank, world):
     ms_per_step = total_ms / max(args.steps, 1)
     value = world * U / 1e6 / (ms_per_step / 1e3)
 
+    # ---- the index-free path (not part of `value`): the same chunks decoded from their byte offsets alone
+    # (pco_b200_decompress_chunks: one tANS walk per chunk builds the per-batch index on the device, all chunks in parallel)
+    chunks_free = None
+    if hasattr(L, "pco_b200_decompress_chunks"):
+        import struct
+
+        ih = bytes(d_index[:64].cpu().numpy())
+        n_idx_chunks, chunks_off = struct.unpack_from("<Q", ih, 8)[0], struct.unpack_from("<Q", ih, 32)[0]
+        recs = bytes(d_index[chunks_off:chunks_off + 32 * n_idx_chunks].cpu().numpy())
+        offs = np.array([struct.unpack_from("<Q", recs, 32 * i)[0] for i in range(n_idx_chunks)], dtype=np.uint64)
+        cns = np.array([struct.unpack_from("<I", recs, 32 * i + 8)[0] for i in range(n_idx_chunks)], dtype=np.uint32)
+        nw_free = C.c_size_t()
+
+        def decompress_chunks():
+            rc = L.pco_b200_decompress_chunks(C.c_void_p(d_comp.data_ptr()), n_written, C.c_ubyte(2), offs.ctypes.data_as(C.c_void_p), cns.ctypes.data_as(C.c_void_p),
+                                              C.c_size_t(n_idx_chunks), C.c_void_p(d_out.data_ptr()), C.c_size_t(n), C.byref(nw_free), C.c_uint32(SRC | DST), sp)
+            _lib.check(rc)
+
+        d_out.zero_()
+        decompress_chunks()
+        torch.cuda.synchronize()
+        assert nw_free.value == n and torch.equal(d_out, nums), "index-free decompress is not bit-exact"
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        for _ in range(3):
+            decompress_chunks()
+        f1.record(stream)
+        torch.cuda.synchronize()
+        free_ms = f0.elapsed_time(f1) / 3
+        chunks_free = {"decompress_mb_s": U / 1e6 / (free_ms / 1e3), "ms": free_ms, "kernel_ms": parse_profile(L),
+                       "api": "pco_b200_decompress_chunks (chunk byte offsets only, no side index), buffers resident in HBM"}
+
     # ---- e2e: the same calls with pinned host buffers (H2D / D2H inside the timed region)
     e2e = None
     if not args.no_e2e:
@@ -361,6 +393,7 @@ def run_gpu_arm(args, rank, world):
         "roofline": {"bound": "hbm", "kernel": "decompress path: symwalk_kernel + decode_kernel (sum of both durations)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": alg_bytes,
                      "peak_source": peak_src},
+        "index_free_decompress": chunks_free,
         "cpu_baseline": cpu, "e2e": e2e, "clocks": sampler.summary(),
         # per step (profiles/r01_l_launches.csv): compress = init_chunks, split_count, plan_solve, fallback, bin_lut, ans_encode,
         # layout, chunk_offsets, pack, header_footer, emit_index; decompress = symwalk_kernel + decode_narrow_kernel +

@@ -69,3 +69,30 @@ def test_wrapped_errors(oracle):
     prog, _ = cd.read_page_into(page, 3000, dst)
     assert prog.n_processed == 1024 and not prog.finished
     np.testing.assert_array_equal(dst, x[:1024])
+
+
+@pytest.mark.parametrize("dtype,mode,order", [(np.uint64, "classic", 1), (np.float64, "float_mult", 2), (np.int32, "classic", 0)])
+def test_pages_of_a_multi_page_chunk_decode(oracle, dtype, mode, order):
+    """A chunk whose PagingSpec yields several pages (they share the chunk's bins, chunk_compressor.rs:129-140), written by
+    the oracle: every page decodes through the wrapped handles from the one chunk meta."""
+    from pcodec_b200 import wrapped
+
+    n = 3 * 5000 + 123
+    x = _walk(dtype, n, seed=33)
+    if mode == "float_mult":
+        x = (np.round(np.cumsum(np.random.default_rng(2).normal(size=n)) * 100) * 0.01).astype(dtype)
+    _, their_cfg = _cfgs(oracle, mode=mode, order=order, max_page_n=5000)
+    occ = oracle.ChunkCompressor(x, their_cfg)
+    pages_n = occ.n_per_page()
+    assert len(pages_n) == 4 and sum(pages_n) == n
+    meta = occ.write_meta()
+    cd, mused = wrapped.FileDecompressor().chunk_decompressor(meta, dtype)
+    assert mused == len(meta)
+    start = 0
+    for i, pn in enumerate(pages_n):
+        page = occ.write_page(i)
+        dst = np.zeros(pn, dtype=dtype)
+        prog, pused = cd.read_page_into(page, pn, dst)
+        assert prog.finished and prog.n_processed == pn and pused == len(page), (i, prog, pused, len(page))
+        np.testing.assert_array_equal(bits_view(dst), bits_view(x[start:start + pn]))
+        start += pn
