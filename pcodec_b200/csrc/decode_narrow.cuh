@@ -103,40 +103,29 @@ __device__ __forceinline__ void narrow_chunk(NarrowSmem& sm, const FileParams& f
   };
   // (one cp.async.bulk of the 512 bytes per batch, signalled on an mbarrier, instead of 32 LDGSTS: correct, but 0.500 ms against 0.487 ms)
 
-  // a batch's section start is requested two batches ahead, its symbols and its window one batch ahead
+  // a batch's section start is requested two batches ahead, its symbols and its window one batch ahead (symbols two ahead:
+  // 0.484 -> 0.490 ms; a __nanosleep back-off in the chain poll: no change once the hand-over was one record)
   constexpr int SY_STEP = NW_WARPS * (BATCH_N / 8);  // uint2 per round of NW_WARPS batches
-#ifdef PCOB_NW_SY2
-  constexpr bool SY_TWO_AHEAD = true;
-#else
-  constexpr bool SY_TWO_AHEAD = false;
-#endif
   uint32_t off_cur = 0, off_nxt = 0;
-  uint2 sy_nxt = make_uint2(0u, 0u), sy_n2 = make_uint2(0u, 0u);
+  uint2 sy_nxt = make_uint2(0u, 0u);
   if (uint32_t(warp) < nb_out) {
     off_cur = __ldg(off_ptr);
     issue_window(off_cur, 0);
     sy_nxt = __ldg(sy_ptr);
-    if (uint32_t(warp) + NW_WARPS < nb_out) {
-      off_nxt = __ldg(off_ptr + NW_WARPS);
-      if (SY_TWO_AHEAD) sy_n2 = __ldg(sy_ptr + SY_STEP);
-    }
+    if (uint32_t(warp) + NW_WARPS < nb_out) off_nxt = __ldg(off_ptr + NW_WARPS);
   }
   uint32_t buf = 0;
   for (uint32_t b = warp; b < nb_out; b += NW_WARPS) {
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();  // this batch's window is visible to the warp; every lane is done with the other buffer
     const uint2 sy = sy_nxt;
-    if (SY_TWO_AHEAD) sy_nxt = sy_n2;
     uint32_t off_n2 = 0;
     sy_ptr += SY_STEP;
     off_ptr += NW_WARPS;
     if (b + NW_WARPS < nb_out) {
       issue_window(off_nxt, buf ^ 1u);
-      if (!SY_TWO_AHEAD) sy_nxt = __ldg(sy_ptr);
-      if (b + 2 * NW_WARPS < nb_out) {
-        off_n2 = __ldg(off_ptr + NW_WARPS);
-        if (SY_TWO_AHEAD) sy_n2 = __ldg(sy_ptr + SY_STEP);
-      }
+      sy_nxt = __ldg(sy_ptr);
+      if (b + 2 * NW_WARPS < nb_out) off_n2 = __ldg(off_ptr + NW_WARPS);
     }
     const uint32_t cnt = batch_count(stored, b);
     // ---- bins of the lane's 8 latents
@@ -212,9 +201,6 @@ __device__ __forceinline__ void narrow_chunk(NarrowSmem& sm, const FileParams& f
       uint64_t m64, fl;
       do {
         asm volatile("ld.volatile.shared.v2.u64 {%0, %1}, [%2];" : "=l"(m64), "=l"(fl) : "r"(link_sa + 16 * slot) : "memory");
-#ifdef PCOB_NW_BACKOFF
-        if (fl != b + 1) __nanosleep(PCOB_NW_BACKOFF);
-#endif
       } while (fl != b + 1);
       const L m = L(m64);
       if (lane == 0)
