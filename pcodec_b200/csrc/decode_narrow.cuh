@@ -19,12 +19,18 @@
 
 namespace pcob200 {
 
-constexpr int NW_THREADS = 256;
+#ifndef PCOB_NW_THREADS
+#define PCOB_NW_THREADS 256
+#endif
+// warps of a chunk's CTA.  More warps per chunk would mean shorter CTAs and a smaller tail wave (1024 chunks on 592 slots = 1.73
+// waves), but the carry chain hands over once per batch (~290 cycles per link): 16 warps: 0.60 ms, 32 warps: 1.04 ms, 8 warps: 0.48 ms.
+constexpr int NW_THREADS = PCOB_NW_THREADS;
 constexpr int NW_WARPS = NW_THREADS / 32;
+constexpr int NW_RING = 2 * NW_WARPS < 32 ? 32 : 2 * NW_WARPS;  // carry-chain slots: more than the batches in flight
 constexpr int NW_WIN_WORDS = 128 + 4;  // 512 staged bytes + 16 of slack for the 3-word lane windows
 
 #ifndef PCOB_NW_MIN_BLOCKS
-#define PCOB_NW_MIN_BLOCKS 4
+#define PCOB_NW_MIN_BLOCKS (1024 / PCOB_NW_THREADS)
 #endif
 
 // one step of an inclusive warp scan: v += (value of lane - d) for lanes >= d; the shuffle's own range predicate guards the add
@@ -52,9 +58,9 @@ __device__ __forceinline__ uint32_t ones_shl_wrap(uint32_t s) {  // 0xffffffff <
 struct NarrowSmem {
   uint32_t q[SMALL_MAX_BINS];
   alignas(16) uint32_t win[NW_WARPS][2][NW_WIN_WORDS];
-  // delta carry chain: link[b % CHAIN_RING] = {first number of batch b, b + 1}, written with ONE 16-byte store and read
+  // delta carry chain: link[b % NW_RING] = {first number of batch b, b + 1}, written with ONE 16-byte store and read
   // with one 16-byte load, so the record is never seen half-written and the hand-over needs no fence
-  alignas(16) uint64_t link[CHAIN_RING][2];
+  alignas(16) uint64_t link[NW_RING][2];
   uint32_t err;
 };
 
@@ -63,8 +69,8 @@ __device__ __forceinline__ void narrow_chunk(NarrowSmem& sm, const FileParams& f
                                              uint32_t* __restrict__ statuses, L* __restrict__ out, uint64_t out_len,
                                              const uint8_t* __restrict__ d_syms, const uint32_t* __restrict__ d_offs) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  sm.q[tid] = inf->q[tid];
-  if (tid < CHAIN_RING) {
+  if (tid < SMALL_MAX_BINS) sm.q[tid] = inf->q[tid];
+  if (tid < NW_RING) {
     sm.link[tid][0] = tid == 0 ? inf->moment0 : 0;
     sm.link[tid][1] = (K == 1 && tid == 0) ? 1u : 0u;
   }
@@ -197,7 +203,7 @@ __device__ __forceinline__ void narrow_chunk(NarrowSmem& sm, const FileParams& f
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) incT = scan_step_up(incT, d);
       const uint32_t totT = __shfl_sync(0xffffffffu, incT, 31);
-      const uint32_t slot = b % CHAIN_RING, nslot = (b + 1) % CHAIN_RING;
+      const uint32_t slot = b % NW_RING, nslot = (b + 1) % NW_RING;
       uint64_t m64, fl;
       do {
         asm volatile("ld.volatile.shared.v2.u64 {%0, %1}, [%2];" : "=l"(m64), "=l"(fl) : "r"(link_sa + 16 * slot) : "memory");
