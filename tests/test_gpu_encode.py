@@ -338,3 +338,44 @@ def test_one_wide_chunk_among_narrow_ones(sa, oracle):
         theirs = oracle.simple_compress(nums, their_cfg)
         assert ours == theirs, _diff_report(oracle, ours, theirs, np.uint64)
         assert np.array_equal(sa.simple_decompress(ours, np.uint64), nums)
+
+
+def test_device_resident_buffers_round_trip_and_too_small_destination(oracle):
+    """The *_ex entry points with every buffer in HBM (flags SRC | DST | INDEX on device), as bench.py calls them; a device
+    destination that is too small is an Io error raised after the kernels (chunks that do not fit are left out, nothing is
+    written past dst_cap)."""
+    import ctypes as C
+
+    import torch
+
+    from pcodec_b200 import ChunkConfig, DeltaSpec, ModeSpec, PagingSpec, PcoError, _lib
+
+    L = _lib.lib()
+    n = 7 * 4096 + 11
+    host = np.cumsum(np.random.default_rng(12).geometric(0.01, size=n)).astype(np.uint64)
+    dev = torch.device("cuda")
+    nums = torch.from_numpy(host.view(np.int64)).to(dev)
+    cfg = ChunkConfig(mode_spec=ModeSpec.classic(), delta_spec=DeltaSpec.try_consecutive(1), paging_spec=PagingSpec.equal_pages_up_to(4096))._to_c()
+    cap = L.pco_standalone_guarantee_file_size(n, 2) + 8 * 160
+    icap = L.pco_b200_index_size_bound(n, 16)
+    d_comp = torch.zeros(cap + 64, dtype=torch.uint8, device=dev)
+    d_idx = torch.empty(icap, dtype=torch.uint8, device=dev)
+    d_out = torch.empty(n, dtype=torch.int64, device=dev)
+    nw, il = C.c_size_t(), C.c_size_t()
+    prog = _lib._CProgress()
+    _lib.check(L.pco_b200_compress_ex(C.c_void_p(nums.data_ptr()), C.c_size_t(n), C.c_ubyte(2), C.byref(cfg), C.c_int(0), C.c_void_p(d_comp.data_ptr()),
+                                      C.c_size_t(cap), C.byref(nw), C.c_void_p(d_idx.data_ptr()), C.c_size_t(icap), C.byref(il), C.c_uint32(7), None))
+    data = bytes(d_comp[: nw.value].cpu().numpy())
+    assert data == oracle.simple_compress(host, oracle.make_config(mode=oracle.MODE_CLASSIC, delta=oracle.DELTA_CONSECUTIVE, delta_order=1, max_page_n=4096))
+    _lib.check(L.pco_b200_decompress_ex(C.c_void_p(d_comp.data_ptr()), nw, C.c_ubyte(2), C.c_void_p(d_out.data_ptr()), C.c_size_t(n), C.byref(prog),
+                                        C.c_void_p(d_idx.data_ptr()), il, C.c_uint32(7), None))
+    assert prog.n_processed == n and prog.finished and torch.equal(d_out, nums)
+    # too small a device destination: Io, and the guard bytes behind dst_cap stay untouched
+    small = nw.value // 2
+    d_small = torch.full((small + 64,), 0xAB, dtype=torch.uint8, device=dev)
+    rc = L.pco_b200_compress_ex(C.c_void_p(nums.data_ptr()), C.c_size_t(n), C.c_ubyte(2), C.byref(cfg), C.c_int(0), C.c_void_p(d_small.data_ptr()),
+                                C.c_size_t(small), C.byref(nw), None, C.c_size_t(0), None, C.c_uint32(3), None)
+    with pytest.raises(PcoError) as e:
+        _lib.check(rc)
+    assert e.value.kind == "Io"
+    assert bool((d_small[small:] == 0xAB).all())
