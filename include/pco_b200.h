@@ -127,9 +127,11 @@ int pco_b200_profile_last(char *buf, size_t cap);
 int pco_b200_profile_chunk_classes(unsigned *counts8);
 
 /* ---- wrapped format (pco/src/wrapped/: FileCompressor / ChunkCompressor / FileDecompressor / ChunkDecompressor /
- * PageDecompressor), for callers that keep chunk metadata and pages in their own container.  This round: ONE page per
- * chunk (a chunk whose PagingSpec yields several pages, which share bins, is PCO_B200_UNSUPPORTED).
- * A wrapped chunk is the same bytes as a standalone chunk without its 4-byte preamble: chunk meta, then the page. */
+ * PageDecompressor), for callers that keep chunk metadata and pages in their own container.  A chunk's PagingSpec may
+ * yield several pages; they share the chunk's bins (pco/src/wrapped/chunk_compressor.rs:129-140).  Classic mode with any
+ * number of pages; the two-var modes (IntMult / FloatMult / FloatQuant) with ONE page per chunk, several are
+ * PCO_B200_UNSUPPORTED for now.
+ * A wrapped chunk with one page is the same bytes as a standalone chunk without its 4-byte preamble: chunk meta, then the page. */
 typedef struct PcoB200ChunkCompressor PcoB200ChunkCompressor;
 /* FileCompressor::write_header (pco/src/wrapped/file_compressor.rs; format version bytes, metadata/format_version.rs:87-91) */
 PcoB200Error pco_b200_file_compressor_write_header(void *dst, size_t dst_cap, size_t *n_written);

@@ -15,6 +15,11 @@
 
 namespace pcob200 {
 
+// internal flag of compress_typed (not in the public enum): the call's chunks are the PAGES of one wrapped chunk and share
+// bins trained on all of them (pco/src/wrapped/chunk_compressor.rs:129-140)
+constexpr uint32_t PCO_B200_INTERNAL_SHARED_BINS = 1u << 16;
+
+
 struct CompressScratch {
   DevBuf lat0, lat1, keys_a, keys_b, sym0, sym1, ans0, ans1, ob_sum, ans_sum, entries, plans, chunks, starts, seg, cub_tmp, out, small, index, probes, sample, sample_starts, key16_0, key16_1;
 };
@@ -209,10 +214,14 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
   for (size_t i = 0; i < pages.size(); i++) { starts[i + 1] = starts[i] + pages[i]; max_chunk_n = std::max<uint64_t>(max_chunk_n, pages[i]); }
   ep.max_chunk_n = uint32_t(max_chunk_n);
   // unoptimized_bins_log is a function of each chunk's n; the kernels take one value per call, so every chunk must agree
-  uint32_t bins_log = choose_unoptimized_bins_log(cfg.compression_level, size_t(pages[0]));
-  for (uint64_t p : pages)
-    if (choose_unoptimized_bins_log(cfg.compression_level, size_t(p)) != bins_log)
-      return fail(PCO_B200_UNSUPPORTED, "chunks whose sizes imply different unoptimized_bins_log in one call");
+  const bool shared_bins = (flags & PCO_B200_INTERNAL_SHARED_BINS) && pages.size() > 1;
+  uint32_t bins_log = choose_unoptimized_bins_log(cfg.compression_level, shared_bins ? n : size_t(pages[0]));
+  if (!shared_bins)
+    for (uint64_t p : pages)
+      if (choose_unoptimized_bins_log(cfg.compression_level, size_t(p)) != bins_log)
+        return fail(PCO_B200_UNSUPPORTED, "chunks whose sizes imply different unoptimized_bins_log in one call");
+  if (shared_bins && ep.mode != MODE_CLASSIC)
+    return fail(PCO_B200_UNSUPPORTED, "wrapped chunks with several pages: classic mode only, for now");
   if (bins_log > 8) return fail(PCO_B200_UNSUPPORTED, "compression levels that train more than 256 bins are outside the GPU hot path");
   ep.bins_log[0] = bins_log;
   ep.bins_log[1] = std::min<uint32_t>(bins_log, 6);  // LIMITED_UNOPTIMIZED_BINS_LOG (chunk_compressor.rs:238-248)
@@ -267,7 +276,7 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
 
   // ---- K1+K2 and the planner for one set of chunks (the call's chunks, or their samples during the Auto delta search)
   uint32_t var_range_bits[MAX_VARS] = {64, 64};
-  auto front = [&](const EncParams& e, uint32_t tiles, size_t slots, uint32_t (&vrb)[MAX_VARS]) -> PcoB200Error {
+  auto front = [&](const EncParams& e, uint32_t tiles, size_t slots, uint32_t (&vrb)[MAX_VARS], const std::vector<uint64_t>& sizes) -> PcoB200Error {
     init_chunks_kernel<<<(n_chunks + 255) / 256, 256, 0, stream>>>(d_chunks, n_chunks);
     static bool plan_attr_set = false;
     if (!plan_attr_set) {
@@ -295,6 +304,27 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
       uint32_t fl[2] = {0, 0};
       PCOB_CUDA_TRY(cudaMemcpyAsync(fl, d_small, 8, cudaMemcpyDeviceToHost, stream));
       PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
+      if (fl[1] == 0 && shared_bins) {
+        // pages of one chunk: one histogram over all of them, one plan, copied to every page's slot
+        static bool union_attr_set = false;
+        if (!union_attr_set) {
+          union_attr_set = true;
+          PCOB_CUDA_TRY(cudaFuncSetAttribute(union_probe_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(size_t(SC_N) * 4)));
+        }
+        PCOB_CUDA_TRY(cudaMemsetAsync(d_small, 0, 8, stream));
+        union_probe_kernel<L><<<1, SC_THREADS, size_t(SC_N) * 4, stream>>>(e, n_chunks, d_chunks, d_probes, S.key16_0.as<uint16_t>(), d_small);
+        PCOB_CUDA_TRY(cudaMemcpyAsync(fl, d_small, 8, cudaMemcpyDeviceToHost, stream));
+        PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
+        if (fl[1] == 0) {
+          vrb[0] = fl[0];
+          uint64_t stored_total = 0;
+          for (uint64_t pn : sizes) stored_total += pn > e.order ? pn - e.order : 0;
+          plan_solve_kernel<L><<<1, SOLVE_THREADS, 0, stream>>>(e, d_probes, d_chunks, d_plans, 0, uint32_t(stored_total));
+          broadcast_plan_kernel<<<n_chunks, 128, 0, stream>>>(d_plans, n_chunks);
+          return PCO_B200_OK;
+        }
+        fl[1] = 1;  // every page is narrow but their union is not: the two-kernel path below (it needs the 64-bit latents)
+      }
       if (fl[1] == 0) {
         vrb[0] = fl[0];
         profiler().begin("plan_solve_kernel", stream);
@@ -314,6 +344,42 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
     }
     profiler().end(stream);
     // ---- planner per var: range-reduced keys -> segmented radix sort over the significant bits -> plan
+    if (shared_bins) {
+      // pages of one wrapped chunk on the sort path: common minimum, the pages' keys as one gap-free segment, one sort,
+      // the union's probes and plan, copied to every page's slot (classic mode: one latent var)
+      PCOB_CUDA_TRY(cudaMemsetAsync(d_small, 0, 4, stream));
+      union_range_kernel<<<1, 32, 0, stream>>>(e, n_chunks, d_chunks, d_small);
+      uint32_t range_bits = 0;
+      PCOB_CUDA_TRY(cudaMemcpyAsync(&range_bits, d_small, 4, cudaMemcpyDeviceToHost, stream));
+      PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
+      vrb[0] = std::max<uint32_t>(range_bits, PLAN_MAX_COUNT_BITS + 1);  // binning and packing read the 64-bit latents on this path
+      std::vector<uint64_t> prefix(sizes.size() + 1, 0);
+      for (size_t i = 0; i < sizes.size(); i++) prefix[i + 1] = prefix[i] + (sizes[i] > e.order ? sizes[i] - e.order : 0);
+      const uint64_t stored_total = prefix.back();
+      PCOB_CUDA_TRY(S.keys_a.reserve(slots * sizeof(L) + 64));
+      PCOB_CUDA_TRY(S.keys_b.reserve(slots * sizeof(L) + 64));
+      PCOB_CUDA_TRY(S.seg.reserve((prefix.size() + 2) * 8 + 64));
+      uint64_t* d_prefix = S.seg.as<uint64_t>();  // [0 .. n_pages]: compaction offsets; then {segment begin, segment end}
+      PCOB_CUDA_TRY(cudaMemcpyAsync(d_prefix, prefix.data(), prefix.size() * 8, cudaMemcpyHostToDevice, stream));
+      const uint64_t seg_host[2] = {0, stored_total};
+      uint64_t* d_seg = d_prefix + prefix.size();
+      PCOB_CUDA_TRY(cudaMemcpyAsync(d_seg, seg_host, 16, cudaMemcpyHostToDevice, stream));
+      sort_keys_kernel<L><<<n_chunks * tiles, 256, 0, stream>>>(e, tiles, d_lat[0], S.keys_a.as<L>(), d_chunks, 0, d_prefix);
+      const L* sorted = S.keys_a.as<L>();
+      if (stored_total > 0) {
+        cub::DoubleBuffer<L> db(S.keys_a.as<L>(), S.keys_b.as<L>());
+        size_t tmp_bytes = 0;
+        const int end_bit = int(std::max<uint32_t>(range_bits, 1));
+        PCOB_CUDA_TRY(cub::DeviceSegmentedRadixSort::SortKeys(nullptr, tmp_bytes, db, int64_t(stored_total), int64_t(1), d_seg, d_seg + 1, 0, end_bit, stream));
+        PCOB_CUDA_TRY(S.cub_tmp.reserve(tmp_bytes + 16));
+        PCOB_CUDA_TRY(cub::DeviceSegmentedRadixSort::SortKeys(S.cub_tmp.p, tmp_bytes, db, int64_t(stored_total), int64_t(1), d_seg, d_seg + 1, 0, end_bit, stream));
+        sorted = db.Current();
+      }
+      plan_probe_kernel<L, false><<<1, PLAN_THREADS, 16, stream>>>(e, sorted, d_chunks, d_probes, 0, range_bits, nullptr, uint32_t(stored_total));
+      plan_solve_kernel<L><<<1, SOLVE_THREADS, 0, stream>>>(e, d_probes, d_chunks, d_plans, 0, uint32_t(stored_total));
+      broadcast_plan_kernel<<<n_chunks, 128, 0, stream>>>(d_plans, n_chunks);
+      return PCO_B200_OK;
+    }
     for (uint32_t v = 0; v < e.n_vars; v++) {
       const uint32_t order_v = v == 0 ? e.order : 0;
       PCOB_CUDA_TRY(cudaMemsetAsync(d_small, 0, 4, stream));
@@ -368,12 +434,13 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
   };
   if (auto_delta) {
     // ---- DeltaSpec::Auto: sampled search over consecutive orders (see gather_sample_kernel)
-    std::vector<uint64_t> s_starts(pages.size() + 1, 0), s_rows(pages.size() + 1, 0);
+    std::vector<uint64_t> s_starts(pages.size() + 1, 0), s_rows(pages.size() + 1, 0), s_sizes(pages.size(), 0);
     uint64_t max_ns = 0;
     for (size_t i = 0; i < pages.size(); i++) {
       const SampleGeom g = delta_sample_geom(pages[i]);
       const uint64_t ns = uint64_t(g.n_groups) * g.group_n;
       s_starts[i + 1] = s_starts[i] + ns;
+      s_sizes[i] = ns;
       s_rows[i + 1] = s_rows[i] + ((ns + BATCH_N - 1) / BATCH_N) * BATCH_N;
       max_ns = std::max(max_ns, ns);
     }
@@ -397,7 +464,7 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
       for (uint32_t k = 0; k <= MAX_ORDER; k++) {
         es.order = k;
         uint32_t vrb[MAX_VARS] = {64, 64};
-        if (PcoB200Error e = front(es, s_tiles, size_t(s_rows.back()), vrb)) return e;
+        if (PcoB200Error e = front(es, s_tiles, size_t(s_rows.back()), vrb, s_sizes)) return e;
         PCOB_CUDA_TRY(cudaMemsetAsync(d_cost, 0, 8, stream));
         auto_cost_kernel<<<(n_chunks + 255) / 256, 256, 0, stream>>>(es, d_plans, d_cost);
         unsigned long long cost = 0;
@@ -409,8 +476,8 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
       ep.order = best_order;
     }
   }
-  if (PcoB200Error e = front(ep, tiles_per_chunk, n_slots, var_range_bits)) return e;
-  fallback_kernel<<<(n_chunks + 255) / 256, 256, 0, stream>>>(ep, d_plans, d_chunks);
+  if (PcoB200Error e = front(ep, tiles_per_chunk, n_slots, var_range_bits, pages)) return e;
+  fallback_kernel<<<(n_chunks + 255) / 256, 256, 0, stream>>>(ep, d_plans, d_chunks, shared_bins ? n_chunks : 0u);
   // ---- K3, K4
   const uint32_t groups_per_chunk = (bpc + 7) / 8;
   for (uint32_t v = 0; v < ep.n_vars; v++)

@@ -333,18 +333,39 @@ __global__ void init_chunks_kernel(ChunkEnc* chunks, uint32_t n_chunks) {
 __device__ __forceinline__ uint64_t stored_begin(uint64_t cs, uint64_t ce, uint32_t order_v) { return min(cs + order_v, ce); }
 
 // keys = latent - min(chunk, var): order-preserving, and lets the planner's sort skip the constant high bits
+// compact_base != nullptr: chunk c's keys go to keys[compact_base[c] ...) - the pages of one wrapped chunk as ONE gap-free
+// segment (their rows in `lat` are padded to 256), for the sort over their union
 template <typename L>
 __global__ void sort_keys_kernel(EncParams ep, uint32_t tiles_per_chunk, const L* __restrict__ lat, L* __restrict__ keys,
-                                 const ChunkEnc* __restrict__ chunks, int v) {
+                                 const ChunkEnc* __restrict__ chunks, int v, const uint64_t* __restrict__ compact_base = nullptr) {
   const uint32_t c = blockIdx.x / tiles_per_chunk, t = blockIdx.x % tiles_per_chunk;
   const uint64_t cs = ep.chunk_starts[c], ce = ep.chunk_starts[c + 1];
   const uint64_t sb = stored_begin(cs, ce, v == 0 ? ep.order : 0);
   const uint64_t rb = ep.row_base[c], n = ce - sb;
+  const uint64_t ob = compact_base ? compact_base[c] : rb;
   const L mn = L(chunks[c].vmin[v]);
   for (int i = threadIdx.x; i < SPLIT_TILE; i += blockDim.x) {
     uint64_t k = uint64_t(t) * SPLIT_TILE + i;
-    if (k < n) keys[rb + k] = L(lat[rb + k] - mn);
+    if (k < n) keys[ob + k] = L(lat[rb + k] - mn);
   }
+}
+
+// The pages of one wrapped chunk share their bins: one minimum / maximum for all of them (keys, bin lowers and lookup
+// tables are relative to it).  flags[0] = range bits of the union.
+__global__ void union_range_kernel(EncParams ep, uint32_t n_pages, ChunkEnc* __restrict__ chunks, uint32_t* __restrict__ flags) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  uint64_t a = ~uint64_t(0), b = 0;
+  bool any = false;
+  for (uint32_t p = 0; p < n_pages; p++) {
+    const uint64_t cs = ep.chunk_starts[p], ce = ep.chunk_starts[p + 1];
+    if (ce == stored_begin(cs, ce, ep.order)) continue;
+    any = true;
+    a = min(a, chunks[p].vmin[0]);
+    b = max(b, chunks[p].vmax[0]);
+  }
+  if (!any) { a = 0; b = 0; }
+  for (uint32_t p = 0; p < n_pages; p++) { chunks[p].vmin[0] = a; chunks[p].vmax[0] = b; chunks[p].key_base[0] = a; }
+  flags[0] = b > a ? 64 - __clzll((long long)(b - a)) : 0;
 }
 
 // segment offsets for the segmented sort
@@ -408,7 +429,7 @@ struct PlanSmem {
 template <typename L, bool COUNTING>
 __global__ void __launch_bounds__(PLAN_THREADS) plan_probe_kernel(EncParams ep, const L* __restrict__ keys, const ChunkEnc* __restrict__ chunks,
                                                                    PlanProbes* __restrict__ probes, int v, uint32_t range_bits,
-                                                                   uint16_t* __restrict__ keys16) {
+                                                                   uint16_t* __restrict__ keys16, uint32_t n_override = 0) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* cum = reinterpret_cast<uint32_t*>(smem_raw);  // COUNTING: 2^range_bits + 1 entries
   __shared__ uint32_t scan_part[PLAN_THREADS / 32];
@@ -416,9 +437,10 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_probe_kernel(EncParams ep, 
   const int tid = threadIdx.x;
   const uint64_t cs = ep.chunk_starts[c], ce = ep.chunk_starts[c + 1];
   const uint64_t sb = stored_begin(cs, ce, v == 0 ? ep.order : 0);
-  const uint32_t n = uint32_t(ce - sb);  // stored latents
+  // stored latents; n_override (sorted path only): `keys` is the gap-free sorted union of a wrapped chunk's pages
+  const uint32_t n = n_override ? n_override : uint32_t(ce - sb);
   if (n == 0) return;
-  const L* s = keys + ep.row_base[c];
+  const L* s = n_override ? keys : keys + ep.row_base[c];
   ENC_TICK_INIT();
   const uint32_t n_vals = COUNTING ? (1u << range_bits) : 0u;
   if (COUNTING) {
@@ -734,15 +756,121 @@ __global__ void __launch_bounds__(SC_THREADS, 1) split_count_kernel(EncParams ep
   }
 }
 
+// ---------------------------------------------------------------------------
+// union_probe_kernel: the pages of ONE wrapped chunk share their bins (chunk_compressor.rs:129-140: deltas per page, one
+// histogram over all stored latents).  split_count_kernel has run per page (keys relative to each page's anchor, per-page
+// min / max); this kernel - one CTA, the multi-page wrapped path is not the bulk path - takes the minimum over the pages,
+// counts every page's keys into one 2^15-counter histogram relative to it, scans, and leaves the union's probes in probes[0].
+// Every page's vmin becomes the common minimum (the bins' lowers and the lookup tables are relative to it); key_base stays
+// per page.  flags[0] = range bits of the union, flags[1] |= 1 when it needs more than 15.
+// ---------------------------------------------------------------------------
+template <typename L>
+__global__ void __launch_bounds__(SC_THREADS, 1) union_probe_kernel(EncParams ep, uint32_t n_pages, ChunkEnc* __restrict__ chunks, PlanProbes* __restrict__ probes,
+                                                                   const uint16_t* __restrict__ keys16, uint32_t* __restrict__ flags) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(smem_raw);
+  __shared__ uint32_t scan_part[SC_THREADS / 32];
+  __shared__ uint64_t sh_min, sh_max;
+  __shared__ uint32_t sh_total;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (uint32_t i = tid; i < SC_N; i += SC_THREADS) cnt[i] = 0;
+  if (tid == 0) {
+    uint64_t a = ~uint64_t(0), b = 0;
+    uint32_t total = 0;
+    for (uint32_t p = 0; p < n_pages; p++) {
+      const uint64_t cs = ep.chunk_starts[p], ce = ep.chunk_starts[p + 1];
+      const uint32_t stored = uint32_t(ce - stored_begin(cs, ce, ep.order));
+      if (stored == 0) continue;
+      total += stored;
+      a = min(a, chunks[p].vmin[0]);
+      b = max(b, chunks[p].vmax[0]);
+    }
+    sh_min = a; sh_max = b; sh_total = total;
+    const uint32_t bits = (total && b > a) ? 64 - __clzll((long long)(b - a)) : 0;
+    flags[0] = bits;
+    if (bits > PLAN_MAX_COUNT_BITS) atomicOr(&flags[1], 1u);
+  }
+  __syncthreads();
+  const uint64_t vmin = sh_min, vmax = sh_max;
+  const uint32_t total = sh_total;
+  if (total == 0 || vmax - vmin > uint64_t(SC_MASK)) return;
+  for (uint32_t p = 0; p < n_pages; p++) {
+    const uint64_t cs = ep.chunk_starts[p], ce = ep.chunk_starts[p + 1];
+    const uint32_t stored = uint32_t(ce - stored_begin(cs, ce, ep.order));
+    const uint16_t* k16 = keys16 + ep.row_base[p];
+    const uint32_t shift = uint32_t(vmin - chunks[p].key_base[0]);  // key16 = latent - key_base (mod 2^16)
+    for (uint32_t i = tid; i < stored; i += SC_THREADS) atomicAdd(&cnt[(uint32_t(k16[i]) - shift) & SC_MASK], 1u);
+  }
+  __syncthreads();
+  if (tid < int(n_pages)) { chunks[tid].vmin[0] = vmin; chunks[tid].vmax[0] = vmax; }
+  for (uint32_t p = SC_THREADS + tid; p < n_pages; p += SC_THREADS) { chunks[p].vmin[0] = vmin; chunks[p].vmax[0] = vmax; }
+  {
+    const uint32_t span = SC_N / (SC_THREADS / 32);
+    const uint32_t w_lo = warp * span, w_hi = w_lo + span;
+    uint32_t carry = 0;
+    for (uint32_t base = w_lo; base < w_hi; base += 32) {
+      const uint32_t v = cnt[base + lane];
+      uint32_t inc = v;
+      for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+      cnt[base + lane] = carry + inc - v;
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) scan_part[warp] = carry;
+    __syncthreads();
+    uint32_t wbase = 0;
+    for (int w = 0; w < warp; w++) wbase += scan_part[w];
+    for (uint32_t k = w_lo + lane; k < w_hi; k += 32) cnt[k] += wbase;
+    __syncthreads();
+  }
+  auto cum = [&](uint32_t k) -> uint32_t { return k >= SC_N ? total : cnt[k]; };
+  auto s_at = [&](uint32_t idx) -> uint64_t {
+    uint32_t lo = 0, hi = SC_N;  // invariant: cum(lo) <= idx < cum(hi)
+    while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (cum(m) <= idx) lo = m; else hi = m; }
+    return lo;
+  };
+  PlanProbes& pr = probes[0];
+  const uint32_t n_bins_log = ep.bins_log[0];
+  const uint32_t nbk = 1u << n_bins_log;
+  auto c_count_of = [&](uint32_t b) -> uint32_t { return uint32_t((uint64_t(b + 1) * total + nbk - 1) >> n_bins_log); };
+  if (tid == 0) pr.first = s_at(0);
+  for (uint32_t k = tid; k < nbk; k += SC_THREADS) {
+    const uint32_t B = c_count_of(k);
+    uint64_t vb1 = 0, vb = 0, vlm1 = 0, vr = 0;
+    uint32_t l = 0, r = 0;
+    if (B >= 1 && B <= total) {
+      vb1 = s_at(B - 1);
+      if (B < total) vb = s_at(B);
+      if (B < total && vb == vb1) {
+        l = cum(uint32_t(vb1));
+        r = cum(uint32_t(vb1) + 1);
+        if (l > 0) vlm1 = s_at(l - 1);
+        if (r < total) vr = s_at(r);
+      }
+    }
+    pr.vB1[k] = vb1; pr.vB[k] = vb; pr.vLm1[k] = vlm1; pr.vR[k] = vr; pr.runL[k] = l; pr.runR[k] = r;
+  }
+}
+
+// plans[0] (trained on the union) -> the plan slot of every page; n_lat stays the union's (only fallback_kernel reads it)
+__global__ void broadcast_plan_kernel(VarPlan* __restrict__ plans, uint32_t n_pages) {
+  const uint32_t p = blockIdx.x + 1;
+  if (p >= n_pages) return;
+  const uint4* src = reinterpret_cast<const uint4*>(&plans[0]);
+  uint4* dst = reinterpret_cast<uint4*>(&plans[size_t(p) * MAX_VARS]);
+  for (uint32_t i = threadIdx.x; i < sizeof(VarPlan) / 16; i += blockDim.x) dst[i] = src[i];
+}
+
 template <typename L>
 __global__ void __launch_bounds__(SOLVE_THREADS) plan_solve_kernel(EncParams ep, const PlanProbes* __restrict__ probes,
-                                                                    const ChunkEnc* __restrict__ chunks, VarPlan* __restrict__ plans, int v) {
+                                                                    const ChunkEnc* __restrict__ chunks, VarPlan* __restrict__ plans, int v,
+                                                                    uint32_t n_override = 0) {
   __shared__ PlanSmem sm;
   const uint32_t c = blockIdx.x;
   const int tid = threadIdx.x;
   const uint64_t cs = ep.chunk_starts[c], ce = ep.chunk_starts[c + 1];
   const uint64_t sb = stored_begin(cs, ce, v == 0 ? ep.order : 0);
-  const uint32_t n = uint32_t(ce - sb);  // stored latents
+  // stored latents; n_override: the pages of one wrapped chunk share bins trained on all of them (union_probe_kernel)
+  const uint32_t n = n_override ? n_override : uint32_t(ce - sb);
   VarPlan& plan = plans[size_t(c) * MAX_VARS + v];
   const uint64_t vmin = chunks[c].vmin[v];
   constexpr uint32_t LBITS = LT<L>::BITS;
@@ -1049,10 +1177,29 @@ __device__ __forceinline__ uint32_t mode_payload_bits(uint32_t mode, uint32_t lb
   return mode == MODE_CLASSIC ? 0 : mode == MODE_FLOAT_QUANT ? 8 : lbits;
 }
 
-__global__ void fallback_kernel(EncParams ep, const VarPlan* __restrict__ plans, ChunkEnc* __restrict__ chunks) {
+// shared_pages = 0: every chunk of the call is its own wrapped chunk with one page.  shared_pages = P > 0: the call's P
+// "chunks" are the pages of ONE wrapped chunk (bins in plans[0], trained on all pages): one decision for all of them.
+__global__ void fallback_kernel(EncParams ep, const VarPlan* __restrict__ plans, ChunkEnc* __restrict__ chunks, uint32_t shared_pages = 0) {
   uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= ep.n_chunks) return;
   const uint32_t lbits = nt_bits(ep.dtype);
+  if (shared_pages) {
+    if (c != 0) return;
+    const uint64_t n = ep.chunk_starts[shared_pages] - ep.chunk_starts[0];
+    uint32_t fb = 0;
+    if (!(ep.order == 0 && ep.mode == MODE_CLASSIC)) {
+      const VarPlan& p = plans[0];
+      const uint64_t wc_bits = 7ull * shared_pages + p.wc_bits;
+      const uint64_t meta_bits = 4 + mode_payload_bits(ep.mode, lbits) + (4 + 5 + 5 + 64 + 32 * 32) + var_meta_bits(p.n_bins, p.size_log, lbits);
+      const uint64_t page_meta_bits = 4 * p.size_log + uint64_t(lbits) * ep.order;
+      const uint64_t worst = (meta_bits + 7) / 8 + shared_pages * ((page_meta_bits + 7) / 8) + (wc_bits + 7) / 8;
+      const uint64_t baseline_meta_bits = 4 + (4 + 5 + 5 + 64 + 32 * 32) + 4 + 15 + (lbits + offset_bits_bits(lbits));
+      const uint64_t baseline = (baseline_meta_bits + 7) / 8 + (n * lbits + 7) / 8;
+      fb = worst > baseline ? 1 : 0;
+    }
+    for (uint32_t q = 0; q < shared_pages; q++) chunks[q].fallback = fb;
+    return;
+  }
+  if (c >= ep.n_chunks) return;
   const uint64_t n = ep.chunk_starts[c + 1] - ep.chunk_starts[c];
   uint32_t fb = 0;
   if (!(ep.order == 0 && ep.mode == MODE_CLASSIC)) {

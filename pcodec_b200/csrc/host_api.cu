@@ -384,9 +384,12 @@ enum PcoError pco_standalone_simple_compress_into(const void* nums, size_t n, un
 // decoder re-frames meta + page as a one-chunk standalone file for the same kernels.
 // ---------------------------------------------------------------------------
 struct PcoB200ChunkCompressor {
-  std::vector<uint8_t> bytes;  // [type byte][n - 1 (24 bits)][chunk meta][page]
+  // one emission per page, back to back: [type byte][page_n - 1 (24 bits)][chunk meta][page]; the pages of a chunk share
+  // their bins, so every emission carries the same chunk meta
+  std::vector<uint8_t> bytes;
   size_t meta_len = 0;
   size_t n = 0;
+  std::vector<size_t> page_off, page_n;  // byte offset of each emission (+ one past the last), numbers per page
 };
 
 namespace {
@@ -462,27 +465,47 @@ PcoB200Error pco_b200_chunk_compressor_new(const void* nums, size_t n, unsigned 
   else { std::memset(&cfg, 0, sizeof(cfg)); cfg.compression_level = 8; }
   std::vector<uint64_t> pages;
   if (PcoB200Error e = n_per_page(cfg, n, &pages)) return e;
-  if (pages.size() != 1)
-    return fail(PCO_B200_UNSUPPORTED, "wrapped chunks with several pages (shared bins) are outside the GPU hot path; use one page per chunk");
   auto cc = std::make_unique<PcoB200ChunkCompressor>();
   cc->n = n;
-  cc->bytes.resize(pco_standalone_guarantee_file_size(n, dtype) + 64);
-  size_t written = 0;
-  if (PcoB200Error e = compress_dispatch(nums, n, dtype, &cfg, false, cc->bytes.data(), cc->bytes.size(), &written, nullptr, 0, nullptr,
-                                         PCO_B200_CHUNKS_ONLY, nullptr))
+  const uint32_t lbits = nt_bits(dtype);
+  size_t cap = 64;
+  for (uint64_t pn : pages) cap += standalone_chunk_size_guarantee(lbits, size_t(pn)) + 8;
+  cc->bytes.resize(cap);
+  size_t written = 0, ilen = 0;
+  std::vector<uint8_t> index(pco_b200_index_size_bound(n, pages.size()) + 64 * pages.size());
+  // several pages: the pipeline runs them as the call's chunks with ONE set of bins trained on all of them
+  const uint32_t flags = PCO_B200_CHUNKS_ONLY | (pages.size() > 1 ? PCO_B200_INTERNAL_SHARED_BINS : 0u);
+  if (PcoB200Error e = compress_dispatch(nums, n, dtype, &cfg, false, cc->bytes.data(), cc->bytes.size(), &written, index.data(), index.size(), &ilen, flags,
+                                         nullptr))
     return e;
   cc->bytes.resize(written);
-  if (written < 4) return fail(PCO_B200_CUDA, "compressor returned a truncated chunk");
-  if (PcoB200Error e = host_chunk_meta_len(cc->bytes.data() + 4, written - 4, dtype, &cc->meta_len)) return e;
+  if (written < 4 || ilen < sizeof(IndexHeader)) return fail(PCO_B200_CUDA, "compressor returned a truncated chunk");
+  IndexHeader ih;
+  std::memcpy(&ih, index.data(), sizeof(ih));
+  if (ih.n_chunks != pages.size() || ih.chunks_offset + ih.n_chunks * sizeof(IndexChunk) > ilen) return fail(PCO_B200_CUDA, "compressor returned an inconsistent page table");
+  for (size_t p = 0; p < pages.size(); p++) {
+    IndexChunk ic;
+    std::memcpy(&ic, index.data() + ih.chunks_offset + p * sizeof(IndexChunk), sizeof(ic));
+    cc->page_off.push_back(size_t(ic.chunk_offset));
+    cc->page_n.push_back(size_t(pages[p]));
+  }
+  cc->page_off.push_back(written);
+  if (PcoB200Error e = host_chunk_meta_len(cc->bytes.data() + 4, cc->page_off[1] - 4, dtype, &cc->meta_len)) return e;
+  for (size_t p = 1; p < pages.size(); p++)  // shared bins: every page's emission repeats the chunk meta
+    if (cc->page_off[p + 1] - cc->page_off[p] < 4 + cc->meta_len ||
+        std::memcmp(cc->bytes.data() + 4, cc->bytes.data() + cc->page_off[p] + 4, cc->meta_len) != 0)
+      return fail(PCO_B200_CUDA, "pages of one chunk came back with different chunk metas");
   *out = cc.release();
   return PCO_B200_OK;
 }
 void pco_b200_chunk_compressor_free(PcoB200ChunkCompressor* cc) { delete cc; }
-size_t pco_b200_chunk_compressor_n_pages(const PcoB200ChunkCompressor* cc) { return cc ? 1 : 0; }
-size_t pco_b200_chunk_compressor_page_n(const PcoB200ChunkCompressor* cc, size_t page_idx) { return (cc && page_idx == 0) ? cc->n : 0; }
+size_t pco_b200_chunk_compressor_n_pages(const PcoB200ChunkCompressor* cc) { return cc ? cc->page_n.size() : 0; }
+size_t pco_b200_chunk_compressor_page_n(const PcoB200ChunkCompressor* cc, size_t page_idx) {
+  return (cc && page_idx < cc->page_n.size()) ? cc->page_n[page_idx] : 0;
+}
 size_t pco_b200_chunk_compressor_meta_size(const PcoB200ChunkCompressor* cc) { return cc ? cc->meta_len : 0; }
 size_t pco_b200_chunk_compressor_page_size(const PcoB200ChunkCompressor* cc, size_t page_idx) {
-  return (cc && page_idx == 0) ? cc->bytes.size() - 4 - cc->meta_len : 0;
+  return (cc && page_idx < cc->page_n.size()) ? cc->page_off[page_idx + 1] - cc->page_off[page_idx] - 4 - cc->meta_len : 0;
 }
 PcoB200Error pco_b200_chunk_compressor_write_meta(const PcoB200ChunkCompressor* cc, void* dst, size_t dst_cap, size_t* n_written) {
   if (!cc) return fail(PCO_B200_INVALID_ARGUMENT, "null chunk compressor");
@@ -493,11 +516,11 @@ PcoB200Error pco_b200_chunk_compressor_write_meta(const PcoB200ChunkCompressor* 
 }
 PcoB200Error pco_b200_chunk_compressor_write_page(const PcoB200ChunkCompressor* cc, size_t page_idx, void* dst, size_t dst_cap, size_t* n_written) {
   if (!cc) return fail(PCO_B200_INVALID_ARGUMENT, "null chunk compressor");
-  if (page_idx >= 1)  // chunk_compressor.rs:661-666
-    return fail(PCO_B200_INVALID_ARGUMENT, "page idx exceeds num pages (" + std::to_string(page_idx) + " >= 1)");
-  const size_t len = cc->bytes.size() - 4 - cc->meta_len;
+  if (page_idx >= cc->page_n.size())  // chunk_compressor.rs:661-666
+    return fail(PCO_B200_INVALID_ARGUMENT, "page idx exceeds num pages (" + std::to_string(page_idx) + " >= " + std::to_string(cc->page_n.size()) + ")");
+  const size_t begin = cc->page_off[page_idx] + 4 + cc->meta_len, len = cc->page_off[page_idx + 1] - begin;
   if (dst_cap < len) return fail(PCO_B200_IO, "failed to write whole buffer");
-  std::memcpy(dst, cc->bytes.data() + 4 + cc->meta_len, len);
+  std::memcpy(dst, cc->bytes.data() + begin, len);
   if (n_written) *n_written = len;
   return PCO_B200_OK;
 }

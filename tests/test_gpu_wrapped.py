@@ -48,9 +48,9 @@ def test_wrapped_errors(oracle):
 
     x = np.arange(3000, dtype=np.uint32)
     fc = wrapped.FileCompressor()
-    cfg = ChunkConfig(mode_spec=ModeSpec.classic(), delta_spec=DeltaSpec.no_op(), paging_spec=PagingSpec.equal_pages_up_to(1000))
+    cfg = ChunkConfig(mode_spec=ModeSpec.try_int_mult(8), delta_spec=DeltaSpec.no_op(), paging_spec=PagingSpec.equal_pages_up_to(1000))
     with pytest.raises(PcoError) as e:
-        fc.chunk_compressor(x, cfg)  # three pages sharing bins: not on the GPU path yet
+        fc.chunk_compressor(x, cfg)  # several pages sharing bins: classic mode only on the GPU path so far
     assert e.value.kind == "Unsupported"
     cc = fc.chunk_compressor(x, ChunkConfig(mode_spec=ModeSpec.classic(), delta_spec=DeltaSpec.no_op()))
     with pytest.raises(PcoError) as e:
@@ -96,3 +96,63 @@ def test_pages_of_a_multi_page_chunk_decode(oracle, dtype, mode, order):
         assert prog.finished and prog.n_processed == pn and pused == len(page), (i, prog, pused, len(page))
         np.testing.assert_array_equal(bits_view(dst), bits_view(x[start:start + pn]))
         start += pn
+
+
+@pytest.mark.parametrize("dtype", [np.uint64, np.int32, np.float64, np.uint16])
+@pytest.mark.parametrize("order", [0, 1, 2])
+@pytest.mark.parametrize("exact", [None, [700, 1, 5000, 3000, 299]])
+def test_multi_page_chunk_bytes_equal_oracle(oracle, dtype, order, exact):
+    """Several pages per chunk: bins trained on all pages, deltas per page (chunk_compressor.rs:129-217).  The chunk meta and every
+    page must equal the oracle's ChunkCompressor byte for byte, and decode page by page."""
+    from pcodec_b200 import wrapped
+
+    n = 9000
+    x = _walk(dtype, n, seed=5 + order)
+    ours_cfg, their_cfg = _cfgs(oracle, order=order, max_page_n=2500, exact=exact)
+    cc = wrapped.FileCompressor().chunk_compressor(x, ours_cfg)
+    occ = oracle.ChunkCompressor(x, their_cfg)
+    assert cc.n_per_page() == occ.n_per_page() and len(cc.n_per_page()) > 1
+    meta = cc.write_meta()
+    assert meta == occ.write_meta()
+    cd, _ = wrapped.FileDecompressor().chunk_decompressor(meta, dtype)
+    start = 0
+    for i, pn in enumerate(cc.n_per_page()):
+        page = cc.write_page(i)
+        assert page == occ.write_page(i), (i, len(page), len(occ.write_page(i)))
+        dst = np.zeros(pn, dtype=dtype)
+        prog, used = cd.read_page_into(page, pn, dst)
+        assert prog.finished and used == len(page)
+        np.testing.assert_array_equal(bits_view(dst), bits_view(x[start:start + pn]))
+        start += pn
+
+
+@pytest.mark.parametrize("dtype", ["f2", "f4", "f8", "i2", "i4", "i8", "u2", "u4", "u8"])
+def test_reference_python_wrapped_case(dtype):
+    """pco_python/test/test_wrapped.py::test_compress, against pcodec_b200.wrapped (default ChunkConfig, 2 pages)."""
+    from pcodec_b200 import ChunkConfig, PagingSpec, PcoError, wrapped
+
+    data = np.random.default_rng(12345).uniform(0, 1000, size=[10]).astype(dtype)
+    page_sizes = [6, 4]
+    fc = wrapped.FileCompressor()
+    header = fc.write_header()
+    cc = fc.chunk_compressor(data, ChunkConfig(paging_spec=PagingSpec.exact_page_sizes(page_sizes)))
+    assert cc.n_per_page() == page_sizes
+    chunk_meta, page0, page1 = cc.write_meta(), cc.write_page(0), cc.write_page(1)
+    with pytest.raises(PcoError) as e:
+        cc.write_page(2)
+    assert e.value.kind == "InvalidArgument" and "page idx exceeds num pages" in str(e.value)
+    fd, n_bytes_read = wrapped.FileDecompressor.new(header)
+    assert n_bytes_read == len(header)
+    _, n_bytes_read = wrapped.FileDecompressor.new(header + b"foo")  # undershooting is fine
+    assert n_bytes_read == len(header)
+    cd, n_bytes_read = fd.chunk_decompressor(chunk_meta, np.dtype(dtype))
+    assert n_bytes_read == len(chunk_meta)
+    dst1 = np.zeros(100).astype(dtype)  # page 1 holds elements 6..10
+    _progress, n_bytes_read = cd.read_page_into(page1, 4, dst1)
+    np.testing.assert_array_equal(dst1[4:], np.zeros(96))
+    np.testing.assert_array_equal(dst1[:4], data[6:])
+    assert n_bytes_read == len(page1)
+    dst0 = np.zeros(6).astype(dtype)
+    _progress, n_bytes_read = cd.read_page_into(page0, 6, dst0)
+    np.testing.assert_array_equal(dst0, data[:6])
+    assert n_bytes_read == len(page0)
