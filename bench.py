@@ -160,6 +160,9 @@ def run_gpu_arm(args, rank, world):
     if world > 1:
         import torch.distributed as dist
 
+        # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION prints it to stdout) off it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
     if not L.pco_b200_device_available():
