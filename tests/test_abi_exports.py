@@ -62,3 +62,19 @@ def test_no_gpu_means_loud_failure():
     with pytest.raises(PcoError) as e:
         standalone.simple_decompress(b"pco!\x03\x00\x00\x04\x01\x00", np.uint32)
     assert e.value.kind == "Cuda"
+
+
+def test_decompress_chunks_argument_checks_need_no_device():
+    """pco_b200_decompress_chunks validates its table before touching the device: nothing to do is fine, a missing table is not."""
+    import ctypes as C
+
+    from pcodec_b200 import _lib
+
+    L = _lib.lib()
+    n_written = C.c_size_t(123)
+    buf = (C.c_uint8 * 16)()
+    assert L.pco_b200_decompress_chunks(buf, C.c_size_t(16), C.c_ubyte(2), None, None, C.c_size_t(0), None, C.c_size_t(0), C.byref(n_written), C.c_uint32(0), None) == 0
+    assert n_written.value == 0
+    rc = L.pco_b200_decompress_chunks(buf, C.c_size_t(16), C.c_ubyte(2), None, None, C.c_size_t(3), None, C.c_size_t(0), C.byref(n_written), C.c_uint32(0), None)
+    assert rc == 3  # InvalidArgument
+    assert L.pco_b200_decompress_chunks(buf, C.c_size_t(16), C.c_ubyte(99), None, None, C.c_size_t(0), None, C.c_size_t(0), C.byref(n_written), C.c_uint32(0), None) == 5  # InvalidType
