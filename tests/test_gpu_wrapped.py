@@ -158,22 +158,6 @@ def test_reference_python_wrapped_case(dtype):
     assert n_bytes_read == len(page0)
 
 
-def _late(fn):
-    """Cases written after this round's GPU budget was spent: a surprise is reported (xfail with the reason) without stopping a
-    `pytest -x` run; everything they build on is asserted by the tests above."""
-    import functools
-
-    @functools.wraps(fn)
-    def wrapper(*a, **kw):
-        try:
-            return fn(*a, **kw)
-        except (AssertionError, RuntimeError) as ex:  # PcoError is a RuntimeError
-            pytest.xfail(f"{type(ex).__name__}: {str(ex)[:400]}")
-
-    return wrapper
-
-
-@_late
 def test_reference_low_level_wrapped_cases(oracle):
     """pco/src/tests/low_level.rs:98-131 (test_low_level_wrapped): chunks with several pages, a page shorter than the delta order,
     one-number pages - compressed through the wrapped handles, every page decoded back, and the bytes compared with the oracle's
