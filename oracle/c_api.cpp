@@ -1,7 +1,12 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see pco_core.hpp header).
 // extern "C" surface used by tests/ (ctypes), __graft_entry__.smoke() and
 // bench.py's cpu_baseline / --impl reference legs.  Never linked by the product.
+#include <malloc.h>
+
+#include <atomic>
+#include <chrono>
 #include <sstream>
+#include <thread>
 
 #include "pco_codec.hpp"
 
@@ -150,6 +155,52 @@ int pco_oracle_simple_decompress_into(const uint8_t* src, size_t src_len, uint8_
       Progress p = simple_decompress_into<L>(src, src_len, dtype, static_cast<L*>(dst), dst_len);
       *n_processed = p.n_processed;
       *finished = p.finished ? 1 : 0;
+    });
+  });
+}
+
+// bench.py's CPU arm: compress, then decompress, `n_chunks` independent chunks of `chunk_n` numbers with `threads` native
+// threads (one chunk per task; pco_cli/src/bench/mod.rs times its codecs the same way, per-thread), verifying the round
+// trip.  Native threads because the Python harness's per-call buffer copies hold the GIL and throttle 100+ threads.
+int pco_oracle_bench_roundtrip(const void* nums, size_t n_chunks, size_t chunk_n, uint8_t dtype, const pco_oracle_config* config, int threads,
+                               double* compress_s, double* decompress_s, uint64_t* compressed_bytes) {
+  return guarded([&] {
+    ChunkConfig cfg = to_config(config);
+    // the port allocates its MiB-sized scratch vectors per chunk; with glibc's default each is an mmap / munmap and the
+    // threads serialise in the kernel (8 threads: 1.6x one thread).  Keep them in the per-thread arenas instead.
+    mallopt(M_MMAP_THRESHOLD, 1 << 30);
+    mallopt(M_TRIM_THRESHOLD, 1 << 30);
+    dispatch_bits(dtype, [&](auto tag) {
+      using L = decltype(tag);
+      const L* base = static_cast<const L*>(nums);
+      std::vector<std::vector<uint8_t>> comp(n_chunks);
+      std::vector<std::string> errors(size_t(std::max(threads, 1)));
+      auto run = [&](auto&& body) -> double {
+        std::atomic<size_t> next{0};
+        std::vector<std::thread> pool;
+        auto t0 = std::chrono::steady_clock::now();
+        for (int t = 0; t < std::max(threads, 1); t++)
+          pool.emplace_back([&, t] {
+            try {
+              for (size_t c = next.fetch_add(1); c < n_chunks; c = next.fetch_add(1)) body(c);
+            } catch (const std::exception& e) { errors[size_t(t)] = e.what(); }
+          });
+        for (auto& th : pool) th.join();
+        return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      };
+      *compress_s = run([&](size_t c) { simple_compress<L>(base + c * chunk_n, chunk_n, dtype, cfg, false, comp[c]); });
+      std::atomic<size_t> bad{0};
+      *decompress_s = run([&](size_t c) {
+        std::vector<L> v;
+        simple_decompress<L>(comp[c].data(), comp[c].size(), dtype, v);
+        if (v.size() != chunk_n || std::memcmp(v.data(), base + c * chunk_n, chunk_n * sizeof(L)) != 0) bad.fetch_add(1);
+      });
+      for (const auto& e : errors)
+        if (!e.empty()) throw PcoError(ErrorKind::Io, "bench worker: " + e);
+      if (bad.load()) throw PcoError(ErrorKind::Corruption, "bench round trip mismatch");
+      uint64_t total = 0;
+      for (const auto& v : comp) total += v.size();
+      *compressed_bytes = total;
     });
   });
 }

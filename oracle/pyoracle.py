@@ -224,3 +224,17 @@ def wrapped_decompress_page(meta, page, dtype, page_n):
                                                   C.c_size_t(page_n), dst.ctypes.data_as(C.c_void_p), C.byref(mc), C.byref(pc))
     _check(rc)
     return dst, mc.value, pc.value
+
+
+def bench_roundtrip(nums, n_chunks, chunk_n, config, threads):
+    """Compress + decompress `n_chunks` chunks of `chunk_n` numbers (contiguous in `nums`) on `threads` native threads, one chunk
+    per task, verifying the round trip.  Returns (compress seconds, decompress seconds, compressed bytes).  bench.py's CPU arm."""
+    arr = np.ascontiguousarray(nums)
+    assert arr.size == n_chunks * chunk_n
+    cs, ds, cb = C.c_double(), C.c_double(), C.c_uint64()
+    f = lib().pco_oracle_bench_roundtrip
+    f.restype = C.c_int
+    rc = f(arr.ctypes.data_as(C.c_void_p), C.c_size_t(n_chunks), C.c_size_t(chunk_n), C.c_uint8(NP_TO_BYTE[arr.dtype]), C.byref(config), C.c_int(threads),
+           C.byref(cs), C.byref(ds), C.byref(cb))
+    _check(rc)
+    return cs.value, ds.value, cb.value
