@@ -475,6 +475,16 @@ int pco_oracle_kat_ans_roundtrip(uint32_t size_log, const uint32_t* state_symbol
   });
 }
 // pco/src/delta/consecutive.rs:57-78 (u32)
+// choose_mode_sample's index draw (sampling.rs:73-95); returns -1 when n < MIN_SAMPLE
+int pco_oracle_kat_mode_sample_indices(size_t n, uint64_t* out, size_t* n_out) {
+  return guarded([&] {
+    std::vector<size_t> idx;
+    if (!choose_mode_sample_indices(n, &idx)) { *n_out = 0; return; }
+    for (size_t i = 0; i < idx.size(); i++) out[i] = idx[i];
+    *n_out = idx.size();
+  });
+}
+
 int pco_oracle_kat_consecutive_encode_u32(uint32_t* latents, size_t n, size_t order, uint32_t* moments_out) {
   return guarded([&] {
     auto m = consecutive_encode_in_place<uint32_t>(order, latents, n);

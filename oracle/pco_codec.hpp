@@ -869,6 +869,51 @@ inline bool choose_delta_sample(const std::vector<L>& primary, std::vector<L>* s
   return true;
 }
 
+// ----- sampling for the Auto MODE search (pco/src/sampling.rs:62-103) ---------------------------------------------
+// rand_xoshiro 0.6.0 Xoroshiro128PlusPlus::seed_from_u64 (Cargo.lock:2682-2685): the two state words are the first two
+// outputs of SplitMix64 started at the seed.  Not in /root/reference (a crates.io dependency): restated from the published
+// algorithm and pinned by the reference's own KAT (sampling.rs:186-201, tests/test_oracle_kats.py::test_choose_mode_sample).
+struct Xoroshiro128PlusPlus {
+  uint64_t s0, s1;
+  static uint64_t rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+  explicit Xoroshiro128PlusPlus(uint64_t seed) {
+    auto splitmix = [&seed]() {
+      seed += 0x9e3779b97f4a7c15ull;
+      uint64_t z = seed;
+      z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+      z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+      return z ^ (z >> 31);
+    };
+    s0 = splitmix();
+    s1 = splitmix();
+  }
+  uint64_t next_u64() {
+    const uint64_t r = rotl(s0 + s1, 17) + s0;
+    s1 ^= s0;
+    s0 = rotl(s0, 49) ^ s1 ^ (s1 << 21);
+    s1 = rotl(s1, 28);
+    return r;
+  }
+};
+// choose_mode_sample's index draw (Floyd's algorithm, sampling.rs:73-95): the indices it visits, in visiting order; the
+// caller applies its filter to nums[idx].  Returns false when n < MIN_SAMPLE (the reference also returns None when fewer
+// than MIN_SAMPLE numbers pass the filter - the caller's check).
+inline bool choose_mode_sample_indices(size_t n, std::vector<size_t>* out) {
+  size_t target;
+  if (!calc_sample_n(n, &target)) return false;
+  Xoroshiro128PlusPlus rng(0);
+  std::vector<uint8_t> visited((n + 7) / 8, 0);
+  out->clear();
+  out->reserve(target);
+  for (size_t j = n - target; j < n; j++) {
+    const size_t t = size_t(rng.next_u64() % (uint64_t(j) + 1));
+    const size_t idx = (visited[t / 8] >> (t % 8)) & 1 ? j : t;
+    visited[idx / 8] |= uint8_t(1u << (idx % 8));
+    out->push_back(idx);
+  }
+  return true;
+}
+
 template <typename L>
 struct SplitLatents {
   std::vector<L> primary;

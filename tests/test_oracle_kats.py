@@ -225,3 +225,21 @@ def test_file_size_guarantee(oracle):  # pco/src/standalone/guarantee.rs:11-38,5
     n = 1 << 18
     # baseline meta: ceil((4 + 1102 + 4 + 15 + (0+64+7)) / 8) = 150 bytes for u64
     assert oracle.file_size_guarantee(n, np.uint64) == 17 + (4 + 150 + n * 8) + 1
+
+
+def test_choose_mode_sample(oracle):  # pco/src/sampling.rs:186-201 (Xoroshiro128PlusPlus::seed_from_u64(0) + Floyd's algorithm)
+    L = oracle.lib()
+    nums = np.array([-float(i) for i in range(150)], dtype=np.float32)
+    out = (C.c_uint64 * 64)()
+    n_out = C.c_size_t()
+    assert L.pco_oracle_kat_mode_sample_indices(C.c_size_t(150), out, C.byref(n_out)) == 0
+    idx = list(out)[: n_out.value]
+    assert len(set(idx)) == len(idx) == 13  # calc_sample_n(150) = 13, drawn without replacement
+    sample = sorted(float(nums[i]) for i in idx if nums[i] != 0.0)  # the test's filter drops zeros
+    assert len(sample) == 13
+    assert sample[:3] == [-135.0, -131.0, -114.0]
+    # calc_sample_n (sampling.rs:141-147)
+    for n, want in ((9, 0), (10, 10), (100, 12), (1000010, 25010)):
+        big = (C.c_uint64 * max(want, 1))()
+        assert L.pco_oracle_kat_mode_sample_indices(C.c_size_t(n), big, C.byref(n_out)) == 0
+        assert n_out.value == want
