@@ -485,6 +485,25 @@ int pco_oracle_kat_mode_sample_indices(size_t n, uint64_t* out, size_t* n_out) {
   });
 }
 
+// pco/src/mode/int_mult.rs unit tests (:238-320): calc_gcd, calc_triple_gcd, solve_root_by_false_position (case 0: x*x-1 on
+// [-0.9,2], 1: x*x, 2: the zero function on [0,1]; returns 0 when there is no root), choose_candidate_base, and choose_base
+// over a whole chunk of ordered u32/u64 latents (returns 1 and *base when int mult is bid, 0 for classic)
+uint32_t pco_oracle_kat_calc_gcd_u32(uint32_t x, uint32_t y) { return calc_gcd<uint32_t>(x, y); }
+uint32_t pco_oracle_kat_calc_triple_gcd_u32(const uint32_t* triple) { return calc_triple_gcd<uint32_t>(triple); }
+int pco_oracle_kat_false_position(int which, double* root) {
+  switch (which) {
+    case 0: return solve_root_by_false_position([](double x) { return x * x - 1.0; }, -0.9, 2.0, root) ? 1 : 0;
+    case 1: return solve_root_by_false_position([](double x) { return x * x; }, -0.9, 2.0, root) ? 1 : 0;
+    default: return solve_root_by_false_position([](double) { return 0.0; }, 0.0, 1.0, root) ? 1 : 0;
+  }
+}
+int pco_oracle_kat_choose_candidate_base_u32(const uint32_t* sample, size_t n, uint32_t* base, double* bits_saved) {
+  std::vector<uint32_t> v(sample, sample + n);
+  return choose_candidate_base<uint32_t>(v, base, bits_saved) ? 1 : 0;
+}
+int pco_oracle_kat_int_mult_choose_base_u32(const uint32_t* latents, size_t n, uint32_t* base) { return int_mult_choose_base<uint32_t>(latents, n, base) ? 1 : 0; }
+int pco_oracle_kat_int_mult_choose_base_u64(const uint64_t* latents, size_t n, uint64_t* base) { return int_mult_choose_base<uint64_t>(latents, n, base) ? 1 : 0; }
+
 int pco_oracle_kat_consecutive_encode_u32(uint32_t* latents, size_t n, size_t order, uint32_t* moments_out) {
   return guarded([&] {
     auto m = consecutive_encode_in_place<uint32_t>(order, latents, n);

@@ -914,6 +914,156 @@ inline bool choose_mode_sample_indices(size_t n, std::vector<size_t>* out) {
   return true;
 }
 
+// ----- ModeSpec::Auto for integer types: IntMult base detection (pco/src/mode/int_mult.rs:57-235) ---------------------
+// data_types/unsigned.rs:28-35: Auto bids int mult alone when choose_base finds a base, else classic alone.
+// Where the reference iterates a std HashMap (most_prominent_gcd :187-204, est_bits_saved_per_num sampling.rs:110-141) its
+// order is per-process random: ties between equally scored gcds and the last ulp of the f64 sum are not defined by the
+// reference itself.  This restatement visits keys in ascending order (ties -> the larger gcd, like max_by_key over an
+// ascending iteration) - any result it gives is one the reference can give.
+template <typename L>
+inline L calc_gcd(L x, L y) {  // int_mult.rs:57-70
+  if (x == 0) return y;
+  for (;;) {
+    if (y == 0) return x;
+    x = L(x % y);
+    std::swap(x, y);
+  }
+}
+
+template <typename F>
+inline bool solve_root_by_false_position(F f, double lb, double ub, double* root) {  // int_mult.rs:72-97
+  const double X_TOLERANCE = 1E-4;
+  double flb = f(lb), fub = f(ub);
+  if (flb > 0.0 || fub < 0.0) return false;
+  while (ub - lb > X_TOLERANCE && fub - flb > 0.0) {
+    const double lb_prop = 0.001 + 0.998 * fub / (fub - flb);
+    const double mid = lb_prop * lb + (1.0 - lb_prop) * ub;
+    const double fmid = f(mid);
+    if (fmid < 0.0) {
+      lb = mid;
+      flb = fmid;
+    } else {
+      ub = mid;
+      fub = fmid;
+    }
+  }
+  *root = (lb + ub) / 2.0;
+  return true;
+}
+
+template <typename L>
+inline L calc_triple_gcd(const L* triple) {  // int_mult.rs:99-115
+  L a = triple[0], b = triple[1], c = triple[2];
+  if (a > b) std::swap(a, b);
+  if (b > c) std::swap(b, c);
+  if (a > b) std::swap(a, b);
+  return calc_gcd<L>(L(b - a), L(c - a));
+}
+
+inline double single_category_entropy(double p) { return (p == 0.0 || p == 1.0) ? 0.0 : -p * std::log2(p); }  // mode/mod.rs:7-13
+inline double worst_case_categorical_entropy(double concentrated_p, double n_categories_m1) {                // mode/mod.rs:15-18
+  return single_category_entropy(concentrated_p) + n_categories_m1 * single_category_entropy((1.0 - concentrated_p) / n_categories_m1);
+}
+
+const double MULT_REQUIRED_BITS_SAVED_PER_NUM = 0.5;  // constants.rs:48
+
+inline bool filter_score_triple_gcd(double gcd, size_t triples_w_gcd_, size_t total_triples_, double* score) {  // int_mult.rs:117-185
+  const double ZETA_OF_2 = 3.14159265358979323846264338327950288 * 3.14159265358979323846264338327950288 / 6.0;
+  const double LCB_RATIO = 1.0;
+  const double triples_w_gcd = double(triples_w_gcd_), total_triples = double(total_triples_);
+  const double prob_per_triple = triples_w_gcd / total_triples;
+  const double natural_prob_per_triple = 1.0 / (ZETA_OF_2 * gcd * gcd);
+  const double stdev = std::sqrt(natural_prob_per_triple * (1.0 - natural_prob_per_triple) / total_triples);
+  const double z_score = (prob_per_triple - natural_prob_per_triple) / stdev;
+  if (z_score < 3.0) return false;
+  const double triples_w_gcd_lcb = triples_w_gcd - LCB_RATIO * std::sqrt(triples_w_gcd);
+  if (triples_w_gcd_lcb <= 0.0) return false;
+  const double congruence_prob_per_triple_lcb = std::fmin(ZETA_OF_2 * triples_w_gcd_lcb / total_triples, 1.0);
+  const double gcd_m1 = gcd - 1.0;
+  const double gcd_m1_inv_sq = 1.0 / (gcd_m1 * gcd_m1);
+  auto cube = [](double x) { return x * x * x; };  // powi(3)
+  auto f = [&](double p) { return cube(p) + cube(1.0 - p) * gcd_m1_inv_sq - congruence_prob_per_triple_lcb; };
+  const double lb = 1.0 / gcd;
+  const double ub = std::cbrt(congruence_prob_per_triple_lcb) + 2.220446049250313e-16;  // f64::EPSILON
+  double concentrated_p;
+  if (!solve_root_by_false_position(f, lb, ub, &concentrated_p)) return false;
+  const double worst_case_entropy_mod_gcd = worst_case_categorical_entropy(concentrated_p, gcd_m1);
+  const double worst_case_bits_saved = std::log2(gcd) - worst_case_entropy_mod_gcd;
+  if (worst_case_bits_saved < MULT_REQUIRED_BITS_SAVED_PER_NUM) return false;
+  *score = worst_case_bits_saved;
+  return true;
+}
+
+// int_mult.rs:206-214 choose_candidate_base + :187-204 most_prominent_gcd.  `sample` = ordered latents.
+template <typename L>
+inline bool choose_candidate_base(const std::vector<L>& sample, L* base, double* bits_saved) {
+  std::vector<L> triple_gcds;
+  for (size_t i = 0; i + 3 <= sample.size(); i += 3) {
+    L g = calc_triple_gcd<L>(&sample[i]);
+    if (g > 1) triple_gcds.push_back(g);
+  }
+  const size_t total_triples = sample.size() / 3;
+  std::sort(triple_gcds.begin(), triple_gcds.end());
+  bool found = false;
+  for (size_t i = 0; i < triple_gcds.size();) {
+    size_t j = i;
+    while (j < triple_gcds.size() && triple_gcds[j] == triple_gcds[i]) j++;
+    // min(gcd, L::from_u64(u64::MAX)).to_u64() as f64: no-op for <= 64-bit latents
+    double score;
+    if (filter_score_triple_gcd(double(uint64_t(triple_gcds[i])), j - i, total_triples, &score)) {
+      // scores that pass are > 0, where f64::to_latent_ordered is monotone: compare the doubles directly; >= keeps the last max
+      if (!found || score >= *bits_saved) {
+        found = true;
+        *base = triple_gcds[i];
+        *bits_saved = score;
+      }
+    }
+    i = j;
+  }
+  return found;
+}
+
+// sampling.rs:105-141 est_bits_saved_per_num specialised to int mult's closure (primary = x / candidate, the same
+// bits_saved for every element): each group's savings are `bits_saved` added count times, as the reference accumulates.
+template <typename L>
+inline double est_bits_saved_per_num_int_mult(const std::vector<L>& sample, L candidate, double bits_saved) {
+  std::vector<L> primaries(sample.size());
+  for (size_t i = 0; i < sample.size(); i++) primaries[i] = L(sample[i] / candidate);
+  std::sort(primaries.begin(), primaries.end());
+  const double CLASSIC_MEMORIZABLE_BINS = double(1u << 8);  // constants.rs:50
+  const size_t infrequent_cutoff = std::max<size_t>(1, size_t(double(sample.size()) / CLASSIC_MEMORIZABLE_BINS));
+  double sample_bits_saved = 0.0;
+  for (size_t i = 0; i < primaries.size();) {
+    size_t j = i;
+    double group = 0.0;
+    while (j < primaries.size() && primaries[j] == primaries[i]) {
+      group += bits_saved;
+      j++;
+    }
+    if (j - i <= infrequent_cutoff) sample_bits_saved += group;
+    i = j;
+  }
+  return sample_bits_saved / double(sample.size());
+}
+
+// int_mult.rs:216-230 choose_base over the ordered latents of the chunk's numbers
+template <typename L>
+inline bool int_mult_choose_base(const L* ordered_latents, size_t n, L* base) {
+  std::vector<size_t> idx;
+  if (!choose_mode_sample_indices(n, &idx)) return false;  // every int passes the filter, so the sample has >= MIN_SAMPLE entries
+  std::vector<L> sample(idx.size());
+  for (size_t i = 0; i < idx.size(); i++) sample[i] = ordered_latents[idx[i]];
+  L candidate;
+  double bits_saved_per_adj;
+  if (!choose_candidate_base<L>(sample, &candidate, &bits_saved_per_adj)) return false;
+  if (est_bits_saved_per_num_int_mult<L>(sample, candidate, bits_saved_per_adj) > MULT_REQUIRED_BITS_SAVED_PER_NUM) {
+    *base = candidate;
+    return true;
+  }
+  return false;
+}
+
+
 template <typename L>
 struct SplitLatents {
   std::vector<L> primary;
@@ -1060,7 +1210,14 @@ inline SplitLatents<L> split_latents(const L* nums, size_t n, uint8_t number_typ
   SplitLatents<L> out;
   Mode mode;
   ModeSpecKind kind = config.mode_kind;
-  if (kind == ModeSpecKind::Auto) invalid_argument("oracle: ModeSpec::Auto not restated; pass an explicit mode");
+  L auto_base = 0;
+  if (kind == ModeSpecKind::Auto) {
+    // data_types/unsigned.rs:28-35 (signed.rs:41-43 forwards to it); the float search (data_types/float.rs:82-98) is not restated
+    if (isf) invalid_argument("oracle: ModeSpec::Auto restated for integer types only; pass an explicit mode for floats");
+    std::vector<L> ordered(n);
+    for (size_t i = 0; i < n; i++) ordered[i] = to_latent_ordered_bits<L>(nums[i], isf, iss);
+    kind = int_mult_choose_base<L>(ordered.data(), n, &auto_base) ? ModeSpecKind::TryIntMult : ModeSpecKind::Classic;
+  }
   if (kind == ModeSpecKind::TryDict) invalid_argument("oracle: Dict encode not restated");
   if (isf && kind == ModeSpecKind::TryIntMult) invalid_argument("unable to use int mult mode on floats");
   if (!isf && (kind == ModeSpecKind::TryFloatMult || kind == ModeSpecKind::TryFloatQuant)) invalid_argument("unable to use float mode for ints");
@@ -1071,7 +1228,7 @@ inline SplitLatents<L> split_latents(const L* nums, size_t n, uint8_t number_typ
       break;
     case ModeSpecKind::TryIntMult: {
       mode.kind = ModeKind::IntMult;
-      L base = L(config.int_mult_base);
+      L base = config.mode_kind == ModeSpecKind::Auto ? auto_base : L(config.int_mult_base);
       mode.base_latent = base;
       if (!mode_is_valid(mode, number_type)) invalid_argument("The chosen mode was invalid for the number type");
       out.has_secondary = true;

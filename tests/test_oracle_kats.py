@@ -243,3 +243,137 @@ def test_choose_mode_sample(oracle):  # pco/src/sampling.rs:186-201 (Xoroshiro12
         big = (C.c_uint64 * max(want, 1))()
         assert L.pco_oracle_kat_mode_sample_indices(C.c_size_t(n), big, C.byref(n_out)) == 0
         assert n_out.value == want
+
+
+def test_int_mult_gcd_helpers(oracle):  # pco/src/mode/int_mult.rs:238-294
+    L = oracle.lib()
+    L.pco_oracle_kat_calc_gcd_u32.restype = C.c_uint32
+    L.pco_oracle_kat_calc_triple_gcd_u32.restype = C.c_uint32
+    for x, y, want in ((0, 0, 0), (0, 1, 1), (1, 0, 1), (2, 0, 2), (2, 3, 1), (6, 3, 3), (12, 30, 6)):
+        assert L.pco_oracle_kat_calc_gcd_u32(C.c_uint32(x), C.c_uint32(y)) == want
+    for triple, want in (((1, 5, 9), 4), ((8, 5, 2), 3), ((3, 3, 3), 0), ((5, 0, 10), 5)):
+        assert L.pco_oracle_kat_calc_triple_gcd_u32((C.c_uint32 * 3)(*triple)) == want
+    root = C.c_double()
+    assert L.pco_oracle_kat_false_position(0, C.byref(root)) == 1 and abs(root.value - 1.0) < 1e-4
+    assert L.pco_oracle_kat_false_position(1, C.byref(root)) == 0
+    assert L.pco_oracle_kat_false_position(2, C.byref(root)) == 1 and root.value == 0.5
+
+
+def _candidate_base(oracle, sample):
+    a = np.asarray(sample, dtype=np.uint32)
+    base, saved = C.c_uint32(), C.c_double()
+    ok = oracle.lib().pco_oracle_kat_choose_candidate_base_u32(a.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_size_t(a.size), C.byref(base), C.byref(saved))
+    return (base.value, saved.value) if ok else None
+
+
+def test_int_mult_choose_candidate_base(oracle):  # pco/src/mode/int_mult.rs:296-320
+    assert _candidate_base(oracle, [0, 4, 8]) is None  # not significant enough
+    assert _candidate_base(oracle, [0, 4, 8, 10, 14, 18, 20, 24, 28])[0] == 4
+    assert _candidate_base(oracle, [1, 11, 21, 31, 41, 51, 61, 71, 82])[0] == 10  # 2 of 3 triples congruent
+    assert _candidate_base(oracle, [1, 11, 22, 31, 41, 51, 61, 71, 82]) is None  # 1 of 3
+    # "even just evens can be useful if the signal is strong enough": 200 random evens below 2000 (the reference draws them with
+    # rand 0.8's gen_range, which is not restated - same distribution, several seeds instead of its one draw)
+    for seed in range(5):
+        twos = np.random.default_rng(seed).integers(0, 1000, size=200).astype(np.uint32) * 2
+        assert _candidate_base(oracle, twos)[0] == 2, seed
+
+
+def _choose_base(oracle, latents):
+    L = oracle.lib()
+    a = np.ascontiguousarray(latents)
+    if a.dtype == np.uint32:
+        base = C.c_uint32()
+        ok = L.pco_oracle_kat_int_mult_choose_base_u32(a.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_size_t(a.size), C.byref(base))
+    else:
+        base = C.c_uint64()
+        ok = L.pco_oracle_kat_int_mult_choose_base_u64(a.ctypes.data_as(C.POINTER(C.c_uint64)), C.c_size_t(a.size), C.byref(base))
+    return base.value if ok else None
+
+
+def test_int_mult_choose_base(oracle):  # int_mult.rs:216-230 + sampling.rs:105-141; cases after pco/src/tests/recovery.rs + data_types/unsigned.rs
+    rng = np.random.default_rng(0)
+    n = 20000
+    # multiples of 77 with a wide spread of multipliers: int mult pays
+    assert _choose_base(oracle, (rng.integers(0, 1 << 20, size=n) * 77).astype(np.uint32)) == 77
+    assert _choose_base(oracle, (rng.integers(0, 1 << 40, size=n) * 1000 + 7).astype(np.uint64)) == 1000
+    # a few outliers off the lattice do not break it
+    lat = (rng.integers(0, 1 << 20, size=n) * 100).astype(np.uint32)
+    lat[::200] += 1
+    assert _choose_base(oracle, lat) == 100
+    # plain uniform data: no gcd stands out
+    assert _choose_base(oracle, rng.integers(0, 1 << 30, size=n).astype(np.uint32)) is None
+    # multiples of 77 but only a handful of distinct multipliers: classic memorises them (est_bits_saved_per_num's frequent groups)
+    assert _choose_base(oracle, (rng.integers(0, 8, size=n) * 77).astype(np.uint32)) is None
+    # fewer than MIN_SAMPLE numbers: no sample, classic
+    assert _choose_base(oracle, (np.arange(9) * 77).astype(np.uint32)) is None
+
+
+@pytest.mark.parametrize("dtype", [np.uint16, np.uint32, np.int32, np.uint64, np.int64])
+def test_auto_mode_for_ints_round_trips(oracle, dtype):  # data_types/unsigned.rs:28-35: Auto = int mult when choose_base finds a base, else classic
+    rng = np.random.default_rng(3)
+    n = 5000
+    info = np.iinfo(dtype)
+    span = min(int(info.max) // 50, 1 << 40)
+    mult = (rng.integers(0, span, size=n) * 50).astype(dtype)
+    if info.min < 0:
+        mult = (mult - dtype(50 * (span // 2 // 50 * 1))).astype(dtype)
+    plain = rng.integers(int(info.min), int(info.max), size=n, dtype=dtype)
+    for nums, want_mode in ((mult, "IntMult"), (plain, "Classic")):
+        cfg = oracle.make_config(mode=oracle.MODE_AUTO, delta=oracle.DELTA_NOOP)
+        data = oracle.simple_compress(nums, cfg)
+        assert np.array_equal(oracle.simple_decompress(data, dtype), nums)
+        if want_mode == "IntMult":
+            explicit = oracle.simple_compress(nums, oracle.make_config(mode=oracle.MODE_INT_MULT, int_mult_base=50, delta=oracle.DELTA_NOOP))
+            assert data == explicit  # Auto found base 50 and wrote exactly what TryIntMult(50) writes
+        else:
+            assert data == oracle.simple_compress(nums, oracle.make_config(mode=oracle.MODE_CLASSIC, delta=oracle.DELTA_NOOP))
+
+
+class _Xoroshiro128PlusPlus:
+    """Python twin of the oracle's generator (rand_xoshiro 0.6.0), used to redraw the reference's test inputs."""
+
+    M = (1 << 64) - 1
+
+    def __init__(self, seed):
+        def splitmix():
+            nonlocal seed
+            seed = (seed + 0x9E3779B97F4A7C15) & self.M
+            z = seed
+            z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & self.M
+            z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & self.M
+            return z ^ (z >> 31)
+
+        self.s0, self.s1 = splitmix(), splitmix()
+
+    @classmethod
+    def _rotl(cls, x, k):
+        return ((x << k) | (x >> (64 - k))) & cls.M
+
+    def next_u64(self):
+        r = (self._rotl((self.s0 + self.s1) & self.M, 17) + self.s0) & self.M
+        self.s1 ^= self.s0
+        self.s0 = self._rotl(self.s0, 49) ^ self.s1 ^ ((self.s1 << 21) & self.M)
+        self.s1 = self._rotl(self.s1, 28)
+        return r
+
+
+def _gen_range_i32(rng, low, high, upper_half):
+    """rand 0.8.5 UniformInt<i32>::sample_single: widening multiply with a rejection zone over one u32 draw."""
+    span = (high - low) & 0xFFFFFFFF
+    zone = ((span << (32 - span.bit_length())) - 1) & 0xFFFFFFFF
+    while True:
+        v = rng.next_u64()
+        v = (v >> 32) if upper_half else (v & 0xFFFFFFFF)
+        m = v * span
+        if (m & 0xFFFFFFFF) <= zone:
+            return low + (m >> 32)
+
+
+@pytest.mark.parametrize("upper_half", [False, True])
+def test_recovery_with_int_mult(oracle, upper_half):  # pco/src/tests/recovery.rs:294-313: Auto mode + NoOp delta on 300 i32s = 8k - 1 -> IntMult(8)
+    # the generator's next_u32 (low or high half of next_u64) is the one detail of rand_xoshiro not pinned by a KAT here: both are tried
+    rng = _Xoroshiro128PlusPlus(0)
+    nums = np.array([_gen_range_i32(rng, -1000, 1000, upper_half) * 8 - 1 for _ in range(300)], dtype=np.int32)
+    data = oracle.simple_compress(nums, oracle.make_config(mode=oracle.MODE_AUTO, delta=oracle.DELTA_NOOP))
+    assert data == oracle.simple_compress(nums, oracle.make_config(mode=oracle.MODE_INT_MULT, int_mult_base=8, delta=oracle.DELTA_NOOP))
+    assert np.array_equal(oracle.simple_decompress(data, np.int32), nums)
