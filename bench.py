@@ -56,6 +56,21 @@ def parse_args():
 _W = {}
 
 
+def host_threads():
+    """Host threads this process may really use: the affinity mask, capped by a cgroup CPU quota when one is set."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        pass
+    return max(1, n)
+
+
 def _cpu_worker_init(counter, barrier, chunks_per_worker):
     from oracle import pyoracle
     from pcodec_b200 import datagen
@@ -72,7 +87,7 @@ def _cpu_worker_init(counter, barrier, chunks_per_worker):
 def _cpu_worker_run(_):
     from oracle import pyoracle
 
-    _W["barrier"].wait()  # every worker takes exactly one task and they start together
+    _W["barrier"].wait(timeout=600)  # every worker takes exactly one task and they start together (a lost worker breaks the barrier, it does not hang)
     tc, td, cbytes = pyoracle.bench_roundtrip(_W["nums"], _W["k"], CHUNK_N, _W["cfg"], 1)  # raises if a chunk does not round-trip
     return tc, td, cbytes
 
@@ -122,7 +137,7 @@ def run_reference_arm(args, rank):
     image, so this runs the oracle port and says so (cpu_baseline.kind = "port")."""
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     k = max(1, args.cpu_sample_chunks // threads)
     sample = threads * k
     arm = CpuArm(threads, k)
@@ -439,7 +454,7 @@ def run_gpu_arm(args, rank, world):
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:  # the CPU arm beside the GPU number: rank 0 at N = 1 only
-        threads = os.cpu_count() or 1
+        threads = host_threads()
         v = cpu_roundtrip(max(threads, args.cpu_sample_chunks), threads)
         cpu = {"value": v[0], "unit": "MB/s", "cores": threads, "kind": "port",
                "sample": f"{v[4]} chunks of 2^18 u64 (same generator), one worker process per host thread; C++ restatement of pco 1.0.3 (oracle/), not the Rust crate",
