@@ -504,6 +504,73 @@ int pco_oracle_kat_choose_candidate_base_u32(const uint32_t* sample, size_t n, u
 int pco_oracle_kat_int_mult_choose_base_u32(const uint32_t* latents, size_t n, uint32_t* base) { return int_mult_choose_base<uint32_t>(latents, n, base) ? 1 : 0; }
 int pco_oracle_kat_int_mult_choose_base_u64(const uint64_t* latents, size_t n, uint64_t* base) { return int_mult_choose_base<uint64_t>(latents, n, base) ? 1 : 0; }
 
+// pco/src/mode/float_mult.rs :403-653 and float_quant.rs :155-289 unit tests, data_types/float.rs :453-520 (f32 = 0, f64 = 1 where both exist)
+float pco_oracle_kat_insignificant_float_to_f32(float x) { return insignificant_float_to<float>(x); }
+double pco_oracle_kat_insignificant_float_to_f64(double x) { return insignificant_float_to<double>(x); }
+int pco_oracle_kat_approx_pair_gcd_f32(float greater, float lesser, float* out) { return approx_pair_gcd<float>(greater, lesser, out) ? 1 : 0; }
+int pco_oracle_kat_approx_pair_gcd_f64(double greater, double lesser, double* out) { return approx_pair_gcd<double>(greater, lesser, out) ? 1 : 0; }
+int pco_oracle_kat_config_by_trailing_zeros_f32(const float* sample, size_t n, float* base, float* inv_base) {
+  FloatMultConfig<float> c;
+  if (!choose_config_by_trailing_zeros<float>(std::vector<float>(sample, sample + n), &c)) return 0;
+  *base = c.base;
+  *inv_base = c.inv_base;
+  return 1;
+}
+int pco_oracle_kat_config_by_euclidean_f32(const float* sample, size_t n, float* base, float* inv_base) {
+  FloatMultConfig<float> c;
+  if (!choose_config_by_euclidean<float>(std::vector<float>(sample, sample + n), &c)) return 0;
+  *base = c.base;
+  *inv_base = c.inv_base;
+  return 1;
+}
+int pco_oracle_kat_sample_gcd_euclidean_f32(const float* sample, size_t n, float* out) {
+  return approx_sample_gcd_euclidean<float>(std::vector<float>(sample, sample + n), out) ? 1 : 0;
+}
+float pco_oracle_kat_center_sample_base_f32(float base, const float* sample, size_t n) { return center_sample_base<float>(base, std::vector<float>(sample, sample + n)); }
+void pco_oracle_kat_snap_to_int_reciprocal_f32(float base, float* out_base, float* out_inv_base) {
+  auto c = snap_to_int_reciprocal<float>(base);
+  *out_base = c.base;
+  *out_inv_base = c.inv_base;
+}
+// bits_saved_per_num_over_classic with FloatMultConfig::from_inv_base(inv_base); returns 0 when below the required savings
+int pco_oracle_kat_float_mult_bits_saved_f32(float inv_base, const float* sample, size_t n, double* out) {
+  return bits_saved_per_num_over_classic<float>(FloatMultConfig<float>::from_inv_base(inv_base), std::vector<float>(sample, sample + n), out) ? 1 : 0;
+}
+int pco_oracle_kat_float_mult_compute_bid_f32(const float* sample, size_t n, float* base, double* bits_saved) {
+  FloatMultConfig<float> c;
+  if (!float_mult_compute_bid<float>(std::vector<float>(sample, sample + n), &c, bits_saved)) return 0;
+  *base = c.base;
+  return 1;
+}
+void pco_oracle_kat_float_quant_best_k_f32(const float* sample, size_t n, uint32_t* k, double* bits_saved) {
+  auto r = float_quant_estimate_best_k_and_bits_saved<float>(std::vector<float>(sample, sample + n));
+  *k = r.first;
+  *bits_saved = r.second;
+}
+void pco_oracle_kat_float_quant_best_k_f64(const double* sample, size_t n, uint32_t* k, double* bits_saved) {
+  auto r = float_quant_estimate_best_k_and_bits_saved<double>(std::vector<double>(sample, sample + n));
+  *k = r.first;
+  *bits_saved = r.second;
+}
+int pco_oracle_kat_float_quant_compute_bid_f32(const float* sample, size_t n, uint32_t* k, double* bits_saved) {
+  return float_quant_compute_bid<float>(std::vector<float>(sample, sample + n), k, bits_saved) ? 1 : 0;
+}
+// choose_mode over whole chunks (data_types/float.rs:453-457): kind (ModeKind), base as f64, k
+void pco_oracle_kat_choose_float_mode_f32(const float* nums, size_t n, int* kind, double* base, uint32_t* k) {
+  auto c = choose_float_mode<float>(reinterpret_cast<const uint32_t*>(nums), n);
+  *kind = int(c.kind);
+  *base = c.base;
+  *k = c.k;
+}
+void pco_oracle_kat_choose_float_mode_f64(const double* nums, size_t n, int* kind, double* base, uint32_t* k) {
+  auto c = choose_float_mode<double>(reinterpret_cast<const uint64_t*>(nums), n);
+  *kind = int(c.kind);
+  *base = c.base;
+  *k = c.k;
+}
+int32_t pco_oracle_kat_float_exponent_f32(float x) { return fl_exponent<float>(x); }
+float pco_oracle_kat_float_exp2_f32(int32_t p) { return fl_exp2<float>(p); }
+
 int pco_oracle_kat_consecutive_encode_u32(uint32_t* latents, size_t n, size_t order, uint32_t* moments_out) {
   return guarded([&] {
     auto m = consecutive_encode_in_place<uint32_t>(order, latents, n);

@@ -1064,6 +1064,331 @@ inline bool int_mult_choose_base(const L* ordered_latents, size_t n, L* base) {
 }
 
 
+// ----- ModeSpec::Auto for f32 / f64 (data_types/float.rs:70-98): classic, FloatMult and FloatQuant bid; the best estimate wins ----
+// f16 is not restated here (the half crate's arithmetic would have to be followed op by op through this search).
+template <typename F> struct NativeFloat;
+template <> struct NativeFloat<float> {
+  using L = uint32_t;
+  static constexpr Bitlen PRECISION_BITS = 23, BITS = 32;
+  static constexpr int32_t EXP_OFFSET = 127;
+  static float max_for_sampling() { return std::numeric_limits<float>::max() * 0.5f; }  // float.rs:141
+};
+template <> struct NativeFloat<double> {
+  using L = uint64_t;
+  static constexpr Bitlen PRECISION_BITS = 52, BITS = 64;
+  static constexpr int32_t EXP_OFFSET = 1023;
+  static double max_for_sampling() { return std::numeric_limits<double>::max() * 0.5; }
+};
+template <typename F> inline typename NativeFloat<F>::L fl_bits(F x) { typename NativeFloat<F>::L b; std::memcpy(&b, &x, sizeof b); return b; }
+template <typename F> inline F fl_from_bits(typename NativeFloat<F>::L b) { F x; std::memcpy(&x, &b, sizeof x); return x; }
+template <typename F> inline F fl_exp2(int32_t power) {  // float.rs:158-160 (only meant for a small range; same wrap-around outside it)
+  using L = typename NativeFloat<F>::L;
+  return fl_from_bits<F>(L(L(int64_t(NativeFloat<F>::EXP_OFFSET + power)) << NativeFloat<F>::PRECISION_BITS));
+}
+template <typename F> inline int32_t fl_exponent(F x) {  // float.rs:183-185
+  return int32_t(fl_bits<F>(std::fabs(x)) >> NativeFloat<F>::PRECISION_BITS) - NativeFloat<F>::EXP_OFFSET;
+}
+template <typename F> inline uint32_t fl_trailing_zeros(F x) {  // float.rs:188-190
+  auto b = fl_bits<F>(x);
+  if (b == 0) return NativeFloat<F>::BITS;
+  return sizeof(b) == 8 ? uint32_t(__builtin_ctzll(uint64_t(b))) : uint32_t(__builtin_ctz(uint32_t(b)));
+}
+template <typename L> inline uint32_t lat_leading_zeros(L x) {
+  if (x == 0) return 8 * sizeof(L);
+  return sizeof(L) == 8 ? uint32_t(__builtin_clzll(uint64_t(x))) : uint32_t(__builtin_clz(uint32_t(x)));
+}
+template <typename F> inline typename NativeFloat<F>::L fl_ordered(F x) { return to_latent_ordered_bits<typename NativeFloat<F>::L>(fl_bits<F>(x), true, false); }
+
+// sampling.rs:105-141 for any closure: (primary, bits_saved) per sample element in sample order.  A group's savings add up in
+// sample order as in the reference; the groups are summed in ascending primary order (HashMap order in the reference).
+template <typename L>
+inline double est_bits_saved_per_num(std::vector<std::pair<L, double>> items) {
+  const size_t n = items.size();
+  std::stable_sort(items.begin(), items.end(), [](const std::pair<L, double>& a, const std::pair<L, double>& b) { return a.first < b.first; });
+  const size_t infrequent_cutoff = std::max<size_t>(1, size_t(double(n) / 256.0));  // CLASSIC_MEMORIZABLE_BINS
+  double total = 0.0;
+  for (size_t i = 0; i < n;) {
+    size_t j = i;
+    double group = 0.0;
+    while (j < n && items[j].first == items[i].first) group += items[j++].second;
+    if (j - i <= infrequent_cutoff) total += group;
+    i = j;
+  }
+  return total / double(n);
+}
+
+template <typename F>
+struct FloatMultConfig {  // float_mult.rs:318-336
+  F base, inv_base;
+  static FloatMultConfig from_base(F base) { return {base, F(1) / base}; }
+  static FloatMultConfig from_inv_base(F inv_base) { return {F(1) / inv_base, inv_base}; }
+};
+
+const Bitlen FM_REQUIRED_PRECISION_BITS = 6;  // float_mult.rs:78-83
+template <typename F> inline F insignificant_float_to(F x) {  // :85-88
+  const Bitlen P = NativeFloat<F>::PRECISION_BITS;
+  const int32_t spare = int32_t(P > FM_REQUIRED_PRECISION_BITS ? P - FM_REQUIRED_PRECISION_BITS : 0);
+  return x * fl_exp2<F>(-spare);
+}
+template <typename F> inline bool is_approx_zero(F small, F big) { return small <= insignificant_float_to<F>(big); }          // :90-92
+template <typename F> inline bool is_small_remainder(F remainder, F original) { return remainder <= original * fl_exp2<F>(-16); }  // :94-96
+template <typename F> inline bool is_imprecise(F value, F err) { return value <= err * fl_exp2<F>(int32_t(FM_REQUIRED_PRECISION_BITS)); }  // :98-100
+
+template <typename F>
+inline bool approx_pair_gcd(F greater, F lesser, F* out) {  // float_mult.rs:102-142
+  if (is_approx_zero<F>(lesser, greater) || lesser == greater) return false;
+  struct PairMult { F value, err; };
+  const F machine_eps = fl_exp2<F>(-int32_t(NativeFloat<F>::PRECISION_BITS));
+  auto rem_assign = [&](PairMult& lhs, const PairMult& rhs) {
+    const F ratio = std::round(lhs.value / rhs.value);
+    lhs.err += ratio * rhs.err + lhs.value * machine_eps;
+    lhs.value = std::fabs(lhs.value - ratio * rhs.value);
+  };
+  PairMult p_greater{greater, F(0)}, p_lesser{lesser, F(0)};
+  for (;;) {
+    const F prev = p_greater.value;
+    rem_assign(p_greater, p_lesser);
+    if (is_small_remainder<F>(p_greater.value, prev) || p_greater.value <= p_greater.err) {
+      *out = p_lesser.value;
+      return true;
+    }
+    if (is_approx_zero<F>(p_greater.value, greater) || is_imprecise<F>(p_greater.value, p_greater.err)) return false;
+    std::swap(p_greater, p_lesser);
+  }
+}
+
+template <typename F>
+inline bool choose_config_by_trailing_zeros(const std::vector<F>& sample, FloatMultConfig<F>* out) {  // float_mult.rs:145-194
+  using L = typename NativeFloat<F>::L;
+  const Bitlen P = NativeFloat<F>::PRECISION_BITS, BITS = NativeFloat<F>::BITS;
+  auto calc_power_of_2_divisor = [&](int32_t exponent, uint32_t tz) { return exponent - int32_t(P > tz ? P - tz : 0); };
+  int32_t k = std::numeric_limits<int32_t>::max();
+  size_t count = 0;
+  for (F x : sample) {
+    const uint32_t tz = fl_trailing_zeros<F>(x);
+    if (x != F(0) && tz >= 5) {  // INTERESTING_TRAILING_ZEROS
+      count++;
+      k = std::min(k, calc_power_of_2_divisor(fl_exponent<F>(x), tz));
+    }
+  }
+  const size_t required_samples = std::max<size_t>(size_t(std::ceil(double(sample.size()) * 0.5)), 10);  // REQUIRED_TRAILING_ZEROS_FREQUENCY, MIN_SAMPLE
+  if (count < required_samples) return false;
+  std::vector<L> int_sample;
+  const Bitlen lshift = BITS - P - 1;
+  for (F x : sample) {
+    const int32_t exponent = fl_exponent<F>(x);
+    const int32_t k_prime = calc_power_of_2_divisor(exponent, fl_trailing_zeros<F>(x));
+    if (k_prime >= k && exponent < k + int32_t(BITS)) {
+      const uint32_t rshift = BITS - 1 - uint32_t(exponent - k);
+      const L lshifted_w_explicit_mantissa = L(L(fl_bits<F>(x) << lshift) | LatentTraits<L>::MID);
+      int_sample.push_back(L(lshifted_w_explicit_mantissa >> rshift));
+    }
+  }
+  if (int_sample.size() < required_samples) return false;
+  L int_base;
+  double unused;
+  if (!choose_candidate_base<L>(int_sample, &int_base, &unused)) int_base = 1;
+  *out = FloatMultConfig<F>::from_base(F(int_base) * fl_exp2<F>(k));
+  return true;
+}
+
+template <typename F>
+inline bool approx_sample_gcd_euclidean(const std::vector<F>& sample, F* out) {  // float_mult.rs:197-229
+  std::vector<F> gcds;
+  for (size_t i = 0; i + 1 < sample.size(); i += 2) {
+    F g;
+    if (approx_pair_gcd<F>(std::fmax(sample[i], sample[i + 1]), std::fmin(sample[i], sample[i + 1]), &g)) gcds.push_back(g);
+  }
+  const size_t required_pairs_with_common_gcd = 1 + size_t(std::ceil(double(sample.size()) * 0.001));  // REQUIRED_GCD_PAIR_FREQUENCY
+  if (gcds.size() < required_pairs_with_common_gcd) return false;
+  std::sort(gcds.begin(), gcds.end());
+  for (double percentile : {0.1, 0.3, 0.5}) {
+    const F candidate = gcds[size_t(percentile * double(gcds.size()))];
+    size_t similar = 0;
+    for (F g : gcds) similar += std::fabs(g - candidate) < F(0.01) * candidate;
+    if (similar >= required_pairs_with_common_gcd) {
+      *out = candidate;
+      return true;
+    }
+  }
+  return false;
+}
+
+template <typename F>
+inline F center_sample_base(F base, const std::vector<F>& sample) {  // float_mult.rs:239-259
+  const Bitlen P = NativeFloat<F>::PRECISION_BITS;
+  const F inv_base = F(1) / base;
+  F tweak_sum = 0, tweak_weight = 0;
+  for (F x : sample) {
+    const F mult = std::round(x * inv_base);
+    const Bitlen mult_exponent = Bitlen(fl_exponent<F>(mult));  // `as Bitlen`: a negative exponent wraps to a huge value
+    if (mult_exponent < P && mult != F(0)) {
+      const F overshoot = (mult * base) - x;
+      const F weight = F(double(P - mult_exponent));
+      tweak_sum += weight * (overshoot / mult);
+      tweak_weight += weight;
+    }
+  }
+  return base - tweak_sum / tweak_weight;
+}
+
+template <typename F>
+inline FloatMultConfig<F> snap_to_int_reciprocal(F base) {  // float_mult.rs:261-275
+  const F inv_base = F(1) / base;
+  const F round_inv_base = std::round(inv_base);
+  const F decimal_inv_base = F(std::pow(10.0, std::round(std::log10(double(inv_base)))));
+  if (std::fabs(inv_base - round_inv_base) < F(0.02)) return FloatMultConfig<F>::from_inv_base(round_inv_base);                 // SNAP_THRESHOLD_ABSOLUTE
+  if (std::fabs(inv_base - decimal_inv_base) / inv_base < F(0.01)) return FloatMultConfig<F>::from_inv_base(decimal_inv_base);  // SNAP_THRESHOLD_DECIMAL_RELATIVE
+  return FloatMultConfig<F>::from_base(base);
+}
+
+template <typename F>
+inline bool choose_config_by_euclidean(const std::vector<F>& sample, FloatMultConfig<F>* out) {  // float_mult.rs:231-236
+  F base;
+  if (!approx_sample_gcd_euclidean<F>(sample, &base)) return false;
+  *out = snap_to_int_reciprocal<F>(center_sample_base<F>(base, sample));
+  return true;
+}
+
+template <typename F>
+inline bool bits_saved_per_num_over_classic(const FloatMultConfig<F>& config, const std::vector<F>& sample, double* out) {  // float_mult.rs:277-315
+  using L = typename NativeFloat<F>::L;
+  const Bitlen P = NativeFloat<F>::PRECISION_BITS;
+  std::vector<std::pair<L, double>> items;
+  items.reserve(sample.size());
+  for (F x : sample) {
+    const F mult = std::round(x * config.inv_base);
+    const L primary = int_float_to_latent<L>(mult);
+    const Bitlen mult_exponent = Bitlen(fl_exponent<F>(mult));
+    const Bitlen inter_base_bits = P > mult_exponent ? P - mult_exponent : 0;
+    const L approx_unsigned = fl_ordered<F>(mult * config.base), x_as_unsigned = fl_ordered<F>(x);
+    const L abs_adj = L(std::max(x_as_unsigned, approx_unsigned) - std::min(x_as_unsigned, approx_unsigned));
+    const Bitlen adj_bits = 1 + 2 * (NativeFloat<F>::BITS - lat_leading_zeros<L>(abs_adj));
+    items.emplace_back(primary, double(inter_base_bits) - double(adj_bits));
+  }
+  const double bits_saved_per_num = est_bits_saved_per_num<L>(std::move(items));
+  if (bits_saved_per_num >= MULT_REQUIRED_BITS_SAVED_PER_NUM) {
+    *out = bits_saved_per_num;
+    return true;
+  }
+  return false;
+}
+
+// f64::total_cmp as an integer key
+inline uint64_t f64_total_order_key(double x) { uint64_t b; std::memcpy(&b, &x, 8); return to_latent_ordered_bits<uint64_t>(b, true, false); }
+
+template <typename F>
+inline bool float_mult_compute_bid(const std::vector<F>& sample, FloatMultConfig<F>* config, double* bits_saved_per_num) {  // float_mult.rs:338-358
+  bool found = false;
+  for (int which = 0; which < 2; which++) {
+    FloatMultConfig<F> c{F(0), F(0)};
+    double saved = 0.0;
+    if (!(which == 0 ? choose_config_by_trailing_zeros<F>(sample, &c) : choose_config_by_euclidean<F>(sample, &c))) continue;
+    if (!bits_saved_per_num_over_classic<F>(c, sample, &saved)) continue;
+    if (!found || f64_total_order_key(saved) >= f64_total_order_key(*bits_saved_per_num)) {  // max_by keeps the last maximum
+      found = true;
+      *config = c;
+      *bits_saved_per_num = saved;
+    }
+  }
+  return found;
+}
+
+template <typename F>
+inline std::pair<Bitlen, double> float_quant_estimate_best_k_and_bits_saved(const std::vector<F>& sample) {  // float_quant.rs:93-151
+  const Bitlen P = NativeFloat<F>::PRECISION_BITS;
+  std::vector<uint32_t> hist(P + 1, 0);
+  for (F x : sample) hist[std::min<uint32_t>(P, fl_trailing_zeros<F>(x))]++;
+  uint32_t rev_csum = 0;
+  for (size_t i = hist.size(); i-- > 0;) {
+    rev_csum += hist[i];
+    hist[i] = rev_csum;
+  }
+  const double sample_len = double(sample.size());
+  Bitlen best_k = 0;
+  double best_bits_saved = 0.0;
+  for (size_t k = 1; k < hist.size(); k++) {
+    if (hist[k] == 0) continue;
+    const double freq = double(hist[k]) / sample_len;
+    const uint64_t n_categories = (uint64_t(1) << k) - 1;
+    const double saved = double(k) - worst_case_categorical_entropy(freq, double(n_categories));
+    if (saved > best_bits_saved) {
+      best_k = Bitlen(k);
+      best_bits_saved = saved;
+    } else {
+      break;
+    }
+  }
+  return {best_k, best_bits_saved};
+}
+
+const double QUANT_REQUIRED_BITS_SAVED_PER_NUM = 1.5;  // constants.rs:49
+template <typename F>
+inline bool float_quant_compute_bid(const std::vector<F>& sample, Bitlen* k_out, double* bits_saved_per_num) {  // float_quant.rs:73-91
+  using L = typename NativeFloat<F>::L;
+  auto kb = float_quant_estimate_best_k_and_bits_saved<F>(sample);
+  std::vector<std::pair<L, double>> items;
+  items.reserve(sample.size());
+  for (F x : sample) items.emplace_back(L(fl_bits<F>(x) >> kb.first), kb.second);
+  const double saved = est_bits_saved_per_num<L>(std::move(items));
+  if (saved > QUANT_REQUIRED_BITS_SAVED_PER_NUM) {
+    *k_out = kb.first;
+    *bits_saved_per_num = saved;
+    return true;
+  }
+  return false;
+}
+
+// data_types/float.rs:70-80 filter_sample over sampling.rs:62-103's draw
+template <typename F>
+inline bool choose_float_mode_sample(const typename NativeFloat<F>::L* num_bits, size_t n, std::vector<F>* sample) {
+  std::vector<size_t> idx;
+  if (!choose_mode_sample_indices(n, &idx)) return false;
+  sample->clear();
+  for (size_t i : idx) {
+    const F x = fl_from_bits<F>(num_bits[i]);
+    if (std::isnormal(x)) {
+      const F a = std::fabs(x);
+      if (a <= NativeFloat<F>::max_for_sampling()) sample->push_back(a);
+    }
+  }
+  return sample->size() >= 10;  // MIN_SAMPLE
+}
+
+struct FloatModeChoice {
+  ModeKind kind = ModeKind::Classic;
+  double base = 0, inv_base = 0;  // FloatMult (exact in a double for f32 too)
+  Bitlen k = 0;                   // FloatQuant
+  double bits_saved_per_num = 0.0;
+};
+// data_types/float.rs:82-98 + compression_intermediates.rs:79-84: bids in the order classic, float mult, float quant; the last maximum wins
+template <typename F>
+inline FloatModeChoice choose_float_mode_from_sample(const std::vector<F>& sample) {
+  FloatModeChoice best;
+  FloatMultConfig<F> c{F(0), F(0)};
+  double saved = 0.0;
+  if (float_mult_compute_bid<F>(sample, &c, &saved) && f64_total_order_key(saved) >= f64_total_order_key(best.bits_saved_per_num)) {
+    best.kind = ModeKind::FloatMult;
+    best.base = double(c.base);
+    best.inv_base = double(c.inv_base);
+    best.bits_saved_per_num = saved;
+  }
+  Bitlen k;
+  if (float_quant_compute_bid<F>(sample, &k, &saved) && f64_total_order_key(saved) >= f64_total_order_key(best.bits_saved_per_num)) {
+    best.kind = ModeKind::FloatQuant;
+    best.k = k;
+    best.bits_saved_per_num = saved;
+  }
+  return best;
+}
+template <typename F>
+inline FloatModeChoice choose_float_mode(const typename NativeFloat<F>::L* num_bits, size_t n) {
+  std::vector<F> sample;
+  if (!choose_float_mode_sample<F>(num_bits, n, &sample)) return FloatModeChoice();
+  return choose_float_mode_from_sample<F>(sample);
+}
+
+
 template <typename L>
 struct SplitLatents {
   std::vector<L> primary;
@@ -1211,13 +1536,20 @@ inline SplitLatents<L> split_latents(const L* nums, size_t n, uint8_t number_typ
   Mode mode;
   ModeSpecKind kind = config.mode_kind;
   L auto_base = 0;
-  if (kind == ModeSpecKind::Auto) {
-    // data_types/unsigned.rs:28-35 (signed.rs:41-43 forwards to it); the float search (data_types/float.rs:82-98) is not restated
-    if (isf) invalid_argument("oracle: ModeSpec::Auto restated for integer types only; pass an explicit mode for floats");
+  FloatModeChoice auto_float;
+  if (kind == ModeSpecKind::Auto && isf) {
+    // data_types/float.rs:82-98
+    if constexpr (sizeof(L) == 4) auto_float = choose_float_mode<float>(nums, n);
+    else if constexpr (sizeof(L) == 8) auto_float = choose_float_mode<double>(nums, n);
+    else invalid_argument("oracle: ModeSpec::Auto not restated for f16; pass an explicit mode");
+    kind = auto_float.kind == ModeKind::FloatMult ? ModeSpecKind::TryFloatMult : auto_float.kind == ModeKind::FloatQuant ? ModeSpecKind::TryFloatQuant : ModeSpecKind::Classic;
+  } else if (kind == ModeSpecKind::Auto) {
+    // data_types/unsigned.rs:28-35 (signed.rs:41-43 forwards to it)
     std::vector<L> ordered(n);
     for (size_t i = 0; i < n; i++) ordered[i] = to_latent_ordered_bits<L>(nums[i], isf, iss);
     kind = int_mult_choose_base<L>(ordered.data(), n, &auto_base) ? ModeSpecKind::TryIntMult : ModeSpecKind::Classic;
   }
+  const bool is_auto = config.mode_kind == ModeSpecKind::Auto;
   if (kind == ModeSpecKind::TryDict) invalid_argument("oracle: Dict encode not restated");
   if (isf && kind == ModeSpecKind::TryIntMult) invalid_argument("unable to use int mult mode on floats");
   if (!isf && (kind == ModeSpecKind::TryFloatMult || kind == ModeSpecKind::TryFloatQuant)) invalid_argument("unable to use float mode for ints");
@@ -1242,7 +1574,7 @@ inline SplitLatents<L> split_latents(const L* nums, size_t n, uint8_t number_typ
     }
     case ModeSpecKind::TryFloatQuant: {
       mode.kind = ModeKind::FloatQuant;
-      mode.k = config.float_quant_k;
+      mode.k = is_auto ? auto_float.k : config.float_quant_k;
       if (!mode_is_valid(mode, number_type)) invalid_argument("The chosen mode was invalid for the number type");
       out.has_secondary = true;
       out.secondary.resize(n);
@@ -1261,8 +1593,9 @@ inline SplitLatents<L> split_latents(const L* nums, size_t n, uint8_t number_typ
       if constexpr (sizeof(L) == 4 || sizeof(L) == 8) {
         using FO = FloatOps<L>;
         mode.kind = ModeKind::FloatMult;
-        auto base = FO::from_f64(config.float_mult_base);
-        auto inv_base = FO::inv(base);
+        // Auto carries its own (base, inv_base) pair: snap_to_int_reciprocal may give inv_base = 100 with base = 1/100, where 1/base != 100
+        auto base = FO::from_f64(is_auto ? auto_float.base : config.float_mult_base);
+        auto inv_base = is_auto ? FO::from_f64(auto_float.inv_base) : FO::inv(base);
         mode.base_latent = to_latent_ordered_bits<L>(FO::to_bits(base), true, false);
         if (!mode_is_valid(mode, number_type)) invalid_argument("The chosen mode was invalid for the number type");
         out.has_secondary = true;

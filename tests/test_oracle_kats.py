@@ -371,9 +371,270 @@ def _gen_range_i32(rng, low, high, upper_half):
 
 @pytest.mark.parametrize("upper_half", [False, True])
 def test_recovery_with_int_mult(oracle, upper_half):  # pco/src/tests/recovery.rs:294-313: Auto mode + NoOp delta on 300 i32s = 8k - 1 -> IntMult(8)
-    # the generator's next_u32 (low or high half of next_u64) is the one detail of rand_xoshiro not pinned by a KAT here: both are tried
+    # both conventions for the generator's next_u32 reach the asserted mode here (test_recovery_decimals is the case that tells them apart)
     rng = _Xoroshiro128PlusPlus(0)
     nums = np.array([_gen_range_i32(rng, -1000, 1000, upper_half) * 8 - 1 for _ in range(300)], dtype=np.int32)
     data = oracle.simple_compress(nums, oracle.make_config(mode=oracle.MODE_AUTO, delta=oracle.DELTA_NOOP))
     assert data == oracle.simple_compress(nums, oracle.make_config(mode=oracle.MODE_INT_MULT, int_mult_base=8, delta=oracle.DELTA_NOOP))
     assert np.array_equal(oracle.simple_decompress(data, np.int32), nums)
+
+
+# ---- ModeSpec::Auto for floats: the reference's unit tests of mode/float_mult.rs, mode/float_quant.rs and data_types/float.rs ----
+F32_MAX = float(np.finfo(np.float32).max)
+TAU32 = float(np.float32(6.2831855))
+
+
+def _f32(xs):
+    return np.ascontiguousarray(np.asarray(xs, dtype=np.float32))
+
+
+def _fptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _plus_epsilons(a, eps):  # float_mult.rs:393-395 (f32)
+    a = np.float32(a)
+    bits = int(a.view(np.uint32))
+    ordered = bits ^ 0x80000000 if not (bits >> 31) else (~bits) & 0xFFFFFFFF
+    ordered = (ordered + eps) & 0xFFFFFFFF
+    back = ordered ^ 0x80000000 if (ordered >> 31) else (~ordered) & 0xFFFFFFFF
+    return float(np.uint32(back).view(np.float32))
+
+
+def test_float_helpers(oracle):  # float_mult.rs:403-417, data_types/float.rs:528-547
+    L = oracle.lib()
+    L.pco_oracle_kat_insignificant_float_to_f32.restype = C.c_float
+    L.pco_oracle_kat_insignificant_float_to_f32.argtypes = [C.c_float]
+    L.pco_oracle_kat_insignificant_float_to_f64.restype = C.c_double
+    L.pco_oracle_kat_insignificant_float_to_f64.argtypes = [C.c_double]
+    L.pco_oracle_kat_float_exponent_f32.argtypes = [C.c_float]
+    L.pco_oracle_kat_float_exp2_f32.restype = C.c_float
+    assert L.pco_oracle_kat_insignificant_float_to_f64(1.0) == 1.0 / (1 << 46)
+    assert L.pco_oracle_kat_insignificant_float_to_f32(1.0) == 1.0 / (1 << 17)
+    assert L.pco_oracle_kat_insignificant_float_to_f32(32.0) == 1.0 / (1 << 12)
+    for x, want in ((1.0, 0), (2.0, 1), (3.3333, 1), (0.3333, -2), (31.0, 4)):
+        assert L.pco_oracle_kat_float_exponent_f32(x) == want
+    for p, want in ((0, 1.0), (1, 2.0), (-1, 0.5), (2, 4.0)):
+        assert L.pco_oracle_kat_float_exp2_f32(p) == want
+
+
+def test_approx_pair_gcd(oracle):  # float_mult.rs:427-456
+    L = oracle.lib()
+    L.pco_oracle_kat_approx_pair_gcd_f32.argtypes = [C.c_float, C.c_float, C.POINTER(C.c_float)]
+    L.pco_oracle_kat_approx_pair_gcd_f64.argtypes = [C.c_double, C.c_double, C.POINTER(C.c_double)]
+
+    def g32(a, b):
+        out = C.c_float()
+        return out.value if L.pco_oracle_kat_approx_pair_gcd_f32(a, b, C.byref(out)) else None
+
+    def g64(a, b):
+        out = C.c_double()
+        return out.value if L.pco_oracle_kat_approx_pair_gcd_f64(a, b, C.byref(out)) else None
+
+    assert g32(0.0, 0.0) is None
+    assert g32(1.0, 0.0) is None
+    assert g32(1.0, 1.0) is None
+    assert g32(1.0, 2.0) == 1.0
+    assert g32(6.0, 3.0) == 3.0
+    assert g64(10.01, 0.009999999999999787) == 0.009999999999999787
+    assert g32(2.0**100, 3.0) is None
+    mfs = float(np.float32(F32_MAX) * np.float32(0.5))
+    assert g32(mfs, float(np.float32(mfs) * np.float32(0.6))) == float(np.float32(mfs) * np.float32(0.2))
+    assert g32(mfs, 0.0000000000001) is None
+    got = np.float32(g32(float(np.float32(1.0) / np.float32(3.0)), 0.25))
+    want = np.float32(1.0) / np.float32(12.0)
+    assert abs(int(got.view(np.uint32)) - int(want.view(np.uint32))) <= 1
+
+
+def test_float_mult_config_candidates(oracle):  # float_mult.rs:419-425, :458-505
+    L = oracle.lib()
+    base, inv = C.c_float(), C.c_float()
+    s = _f32([0.0, 3.0, 6.0, 21.0, 2.0**100] * 5)
+    assert L.pco_oracle_kat_config_by_trailing_zeros_f32(_fptr(s), C.c_size_t(s.size), C.byref(base), C.byref(inv)) == 1
+    assert base.value == 3.0 and np.float32(inv.value) == np.float32(1.0) / np.float32(3.0)
+    s = _f32([0.0, 2.0**-100, 0.0037, 1.0001] * 5 + [F32_MAX])
+    assert L.pco_oracle_kat_config_by_euclidean_f32(_fptr(s), C.c_size_t(s.size), C.byref(base), C.byref(inv)) == 1
+    assert abs(base.value - 1.0e-4) <= 1.0e-6
+    out = C.c_float()
+    s = _f32([0.0, 2.0**-100, 0.0037, 1.0001, F32_MAX] * 5)
+    assert L.pco_oracle_kat_sample_gcd_euclidean_f32(_fptr(s), C.c_size_t(s.size), C.byref(out)) == 1 and abs(out.value - 1.0e-4) <= 1.0e-6
+    s = _f32([0.0, 2.0**-100, 0.0037, 0.0049, 1.0001, F32_MAX] * 5)
+    assert L.pco_oracle_kat_sample_gcd_euclidean_f32(_fptr(s), C.c_size_t(s.size), C.byref(out)) == 1 and abs(out.value - 1.0e-4) <= 1.0e-9
+    # 25 uniform draws from [0, 1) have no common gcd (the reference draws them with rand's gen_range - same distribution here)
+    for seed in range(5):
+        s = np.random.default_rng(seed).random(25, dtype=np.float32)
+        assert L.pco_oracle_kat_sample_gcd_euclidean_f32(_fptr(s), C.c_size_t(s.size), C.byref(out)) == 0, seed
+    # test_center_gcd
+    L.pco_oracle_kat_center_sample_base_f32.restype = C.c_float
+    L.pco_oracle_kat_center_sample_base_f32.argtypes = [C.c_float, C.POINTER(C.c_float), C.c_size_t]
+    s = _f32([6.0 / 7.0 - 1e-4, 16.0 / 7.0 + 1e-4, 18.0 / 7.0 - 1e-4])
+    assert abs(L.pco_oracle_kat_center_sample_base_f32(0.28, _fptr(s), s.size) - 2.0 / 7.0) <= 1e-4
+
+
+def test_float_mult_snap(oracle):  # float_mult.rs:507-538
+    L = oracle.lib()
+    L.pco_oracle_kat_snap_to_int_reciprocal_f32.argtypes = [C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+
+    def snap(x):
+        b, i = C.c_float(), C.c_float()
+        L.pco_oracle_kat_snap_to_int_reciprocal_f32(x, C.byref(b), C.byref(i))
+        return np.float32(b.value), np.float32(i.value)
+
+    one = np.float32(1.0)
+    assert snap(0.01000333) == (np.float32(0.01), np.float32(100.0))
+    assert snap(0.009999666) == (np.float32(0.01), np.float32(100.0))
+    assert snap(0.143) == (one / np.float32(7.0), np.float32(7.0))
+    assert snap(0.0105) == (np.float32(0.0105), one / np.float32(0.0105))
+    assert snap(TAU32)[0] == np.float32(TAU32)
+
+
+def _fm_better(oracle, inv_base, sample):  # float_mult.rs:397-401
+    s = _f32(sample)
+    out = C.c_double()
+    L = oracle.lib()
+    L.pco_oracle_kat_float_mult_bits_saved_f32.argtypes = [C.c_float, C.POINTER(C.c_float), C.c_size_t, C.POINTER(C.c_double)]
+    return bool(L.pco_oracle_kat_float_mult_bits_saved_f32(inv_base, _fptr(s), s.size, C.byref(out))) and out.value >= 0.5
+
+
+def test_float_mult_better_or_worse_than_classic(oracle):  # float_mult.rs:540-604
+    nums = [-np.inf, -np.nan, -999.0, -0.3, 0.0, 0.1, 0.2, 0.3, 0.3, 0.4, 0.5, 0.6, 0.7, np.nan, np.inf]
+    assert _fm_better(oracle, 10.0, nums)
+    for n in (10, 1000):
+        assert _fm_better(oracle, 10.0, [_plus_epsilons(np.float32(x) * np.float32(0.1), x % 2) for x in range(n)]), n
+        assert not _fm_better(oracle, 10.0, [0.1] * n), n
+        assert not _fm_better(oracle, 10.0, [(np.float32(x) + np.float32(1.0)) * np.float32(TAU32) for x in range(n)]), n
+        # at this magnitude each increment of base is only ~2 bits
+        assert not _fm_better(oracle, 10.0, [np.float32(x + 5_000_000) * np.float32(0.1) for x in range(n)]), n
+    for seed in range(3):  # test_float_mult_worse_than_classic_zeros: 1000 zeros + 1000 uniform [0, 1) against base 1e-7
+        nums = np.concatenate([np.zeros(1000, np.float32), np.random.default_rng(seed).random(1000, dtype=np.float32)])
+        assert not _fm_better(oracle, 1e7, nums), seed
+
+
+def test_float_mult_compute_bid(oracle):  # float_mult.rs:606-653
+    L = oracle.lib()
+
+    def bid(sample):
+        s = _f32(sample)
+        base, saved = C.c_float(), C.c_double()
+        return np.float32(base.value) if L.pco_oracle_kat_float_mult_compute_bid_f32(_fptr(s), C.c_size_t(s.size), C.byref(base), C.byref(saved)) else None
+
+    sevenths = [np.float32((i % 50) - 20) * (np.float32(1.0) / np.float32(7.0)) for i in range(1000)]
+    ones = [1.0] * 1000
+    noisy_decimals = [_plus_epsilons(np.float32(0.1) * np.float32(i - 100), -7 + i % 15) for i in range(1000)]
+    junk = np.sin(np.arange(1000, dtype=np.float32)).astype(np.float32)
+    assert bid(sevenths[:50]) == np.float32(1.0) / np.float32(7.0)
+    assert bid(sevenths) is None  # (not in the reference's test) 50 multipliers x 20 occurrences each: classic memorises them
+    assert bid(noisy_decimals) == np.float32(1.0) / np.float32(10.0)
+    bid([F32_MAX] * 10 + [float(np.float32(F32_MAX) * np.float32(0.6))] * 10)  # just check this terminates
+    assert bid(ones) is None  # not enough distinct mults
+    assert bid(junk) is None
+
+
+def test_float_quant_estimates(oracle):  # float_quant.rs:155-173, :263-289
+    L = oracle.lib()
+    k, saved = C.c_uint32(), C.c_double()
+    # all but the last of these have 21 of 23 mantissa bits zeroed
+    s = _f32([1.0, 1.25, -1.5, 1.75, -0.875, 0.75, 0.625] * 3 + [float(np.uint32(0x3F800001).view(np.float32))])
+    L.pco_oracle_kat_float_quant_best_k_f32(_fptr(s), C.c_size_t(s.size), C.byref(k), C.byref(saved))
+    assert k.value == 21 and 10.0 < saved.value < 21.0
+    d = np.ones(20, dtype=np.float64)
+    L.pco_oracle_kat_float_quant_best_k_f64(d.ctypes.data_as(C.POINTER(C.c_double)), C.c_size_t(d.size), C.byref(k), C.byref(saved))
+    assert k.value == 52 and saved.value == 52.0
+
+    def qbid(sample):
+        s = _f32(sample)
+        ok = L.pco_oracle_kat_float_quant_compute_bid_f32(_fptr(s), C.c_size_t(s.size), C.byref(k), C.byref(saved))
+        return (k.value, saved.value) if ok else None
+
+    # the larger numbers in this sample have 23 - 6 = 17 bits of quantization
+    assert qbid(np.arange(100)) == (17, 17.0)
+    s = np.arange(100, dtype=np.float32)
+    s[0] += np.float32(0.1)
+    s[37] -= np.float32(0.1)
+    kk, sv = qbid(s)
+    assert kk == 17 and 15.0 < sv < 17.0
+    assert qbid([0.0, 1.0] * 50) is None  # too few primary values: memorizable
+
+
+def _choose_float_mode(oracle, nums):
+    L = oracle.lib()
+    kind, base, k = C.c_int(), C.c_double(), C.c_uint32()
+    a = np.ascontiguousarray(nums)
+    if a.dtype == np.float32:
+        L.pco_oracle_kat_choose_float_mode_f32(_fptr(a), C.c_size_t(a.size), C.byref(kind), C.byref(base), C.byref(k))
+    else:
+        L.pco_oracle_kat_choose_float_mode_f64(a.ctypes.data_as(C.POINTER(C.c_double)), C.c_size_t(a.size), C.byref(kind), C.byref(base), C.byref(k))
+    return ("Classic", "IntMult", "FloatMult", "FloatQuant", "Dict")[kind.value], base.value, k.value
+
+
+def test_choose_float_mode(oracle):  # data_types/float.rs:459-466, :511-521; tests/recovery.rs:388-402
+    assert _choose_float_mode(oracle, np.arange(2000, dtype=np.float64) * 1.5)[:2] == ("FloatMult", 1.5)
+    lowest = int(np.float64(1.0).view(np.uint64))
+    nums = (np.uint64(lowest) + (np.arange(1000, dtype=np.uint64) << np.uint64(20))).view(np.float64)
+    mode = _choose_float_mode(oracle, nums)
+    assert (mode[0], mode[2]) == ("FloatQuant", 20)
+    trivial = np.arange(100, dtype=np.float32)
+    trivial[77] += np.float32(0.0001)
+    assert _choose_float_mode(oracle, trivial)[:2] == ("FloatMult", 1.0)
+    assert _choose_float_mode(oracle, np.random.default_rng(0).standard_normal(5000))[0] == "Classic"
+    assert _choose_float_mode(oracle, np.arange(9, dtype=np.float64) * 1.5)[0] == "Classic"  # fewer than MIN_SAMPLE numbers
+
+
+def _f64_plus_epsilons(a, eps):  # tests/recovery.rs:338-340
+    bits = int(np.float64(a).view(np.uint64))
+    m = (1 << 64) - 1
+    ordered = bits ^ (1 << 63) if not (bits >> 63) else (~bits) & m
+    ordered = (ordered + eps) & m
+    back = ordered ^ (1 << 63) if (ordered >> 63) else (~ordered) & m
+    return float(np.uint64(back).view(np.float64))
+
+
+def test_recovery_decimals(oracle):  # tests/recovery.rs:332-358: ChunkConfig::default() on noisy hundredths -> FloatMult(1/100), small file
+    # This case also pins the generator's next_u32: with the upper half of next_u64 the redrawn input gives the mode the reference
+    # asserts; with the lower half the 10-element sample it leaves is a different one and the search lands on Classic.
+    upper_half = True
+    rng = _Xoroshiro128PlusPlus(0)
+    n = 300
+    nums = []
+    for _ in range(n):
+        unadjusted = float(_gen_range_i32(rng, -1, 100, upper_half)) * 0.01
+        nums.append(_f64_plus_epsilons(unadjusted, _gen_range_i32(rng, -1, 2, upper_half)))
+    nums = np.array(nums + [np.inf] * n, dtype=np.float64)
+    assert _choose_float_mode(oracle, nums)[:2] == ("FloatMult", 1.0 / 100.0)
+    data = oracle.simple_compress(nums, oracle.make_config(mode=oracle.MODE_AUTO, delta=oracle.DELTA_AUTO))
+    assert np.array_equal(oracle.simple_decompress(data, np.float64).view(np.uint64), nums.view(np.uint64))
+    overhead_bytes = 100
+    assert len(data) < (9 * n + 3 * n) // 8 + overhead_bytes
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_auto_mode_for_floats_round_trips(oracle, dtype):  # data_types/float.rs:82-98 through the whole chunk compressor
+    rng = np.random.default_rng(11)
+    n = 6000
+    u = np.dtype(f"u{np.dtype(dtype).itemsize}")
+    k = 9 if dtype == np.float32 else 30
+    cases = {
+        "FloatMult": (rng.integers(-20000, 20000, size=n).astype(dtype) * dtype(1.5)).astype(dtype),
+        "FloatQuant": ((rng.standard_normal(n).astype(dtype).view(u) >> u.type(k)) << u.type(k)).view(dtype),
+        "Classic": rng.standard_normal(n).astype(dtype),
+    }
+    for want, nums in cases.items():
+        kind, base, kk = _choose_float_mode(oracle, nums)
+        assert kind == want, (want, kind, base, kk)
+        data = oracle.simple_compress(nums, oracle.make_config(mode=oracle.MODE_AUTO, delta=oracle.DELTA_NOOP))
+        assert np.array_equal(oracle.simple_decompress(data, dtype).view(u), nums.view(u)), want
+        if want == "FloatMult":
+            assert base == 1.5
+            assert data == oracle.simple_compress(nums, oracle.make_config(mode=oracle.MODE_FLOAT_MULT, float_mult_base=1.5, delta=oracle.DELTA_NOOP))
+        elif want == "FloatQuant":
+            assert kk == k
+            assert data == oracle.simple_compress(nums, oracle.make_config(mode=oracle.MODE_FLOAT_QUANT, float_quant_k=k, delta=oracle.DELTA_NOOP))
+        else:
+            assert data == oracle.simple_compress(nums, oracle.make_config(mode=oracle.MODE_CLASSIC, delta=oracle.DELTA_NOOP))
+    # decimals: the snapped config has inv_base = 100 exactly and base = 1/100
+    nums = (rng.integers(-5000, 5000, size=n).astype(np.float64) / 100.0).astype(dtype)
+    kind, base, _ = _choose_float_mode(oracle, nums)
+    assert kind == "FloatMult" and dtype(base) == dtype(1.0) / dtype(100.0)
+    data = oracle.simple_compress(nums, oracle.make_config(mode=oracle.MODE_AUTO, delta=oracle.DELTA_AUTO))
+    assert np.array_equal(oracle.simple_decompress(data, dtype).view(u), nums.view(u))
+    assert len(data) < n * 2 + 200  # ~13.3 bits per number for the multiplier, adjustments almost free
