@@ -98,6 +98,9 @@ class CpuArm:
     def __init__(self, workers, chunks_per_worker):
         import multiprocessing as mp
 
+        from oracle import pyoracle
+
+        pyoracle.build()  # once, here: the workers must find the library up to date instead of racing to rebuild it
         ctx = mp.get_context("spawn")  # the GPU arm's process holds a CUDA context and helper threads: no fork
         self.workers, self.k = workers, chunks_per_worker
         self.pool = ctx.Pool(workers, initializer=_cpu_worker_init, initargs=(ctx.Value("i", 0), ctx.Barrier(workers), chunks_per_worker))
