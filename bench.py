@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-index-free", action="store_true", help="skip the pco_b200_decompress_chunks timing (not part of `value`)")
+    ap.add_argument("--results-csv", default=None, help="also merge this run into a CSV with the reference bench tool's schema and codec naming (pcodec_b200/benchfmt.py)")
     ap.add_argument("--gather-pages", action="store_true", help="N > 1: also all-gather the compressed page bytes (every rank ends up with the whole file)")
     return ap.parse_args()
 
@@ -485,6 +486,13 @@ def run_gpu_arm(args, rank, world):
         "gpu_launches": 15,
     }
     print(json.dumps(line))
+    if args.results_csv:
+        # the same run in the reference bench tool's format (docs/benchmark_results/*.csv): seconds per pass over the whole job
+        from pcodec_b200 import benchfmt
+
+        benchfmt.merge_results_csv(args.results_csv, [dict(
+            input=f"c2_u64_cumsum_geometric_{world * n_chunks}x2^18", codec=benchfmt.PcoCodec(level=8, delta=DeltaSpec.try_consecutive(1), mode=ModeSpec.classic()),
+            compress_dt=float(np.mean(t_c)) / 1e3, decompress_dt=float(np.mean(t_d)) / 1e3, compressed_size=world * Cbytes, uncompressed_size=world * U)])
 
 
 def main():
