@@ -104,10 +104,6 @@ def read_chunk_meta(buf, byte_pos, number_bits, format_major=4):
     return meta, r.byte
 
 
-def _ordered_to_signed(v, bits):
-    return v - (1 << (bits - 1))
-
-
 def _ordered_to_float(v, bits):
     mid = 1 << (bits - 1)
     raw = v ^ mid if v & mid else (~v) & ((1 << bits) - 1)

@@ -9,7 +9,6 @@ chunk 0, decode compared with the input.  Writes a markdown table to argv[1].
 import ctypes as C
 import os
 import sys
-import time
 
 sys.path.insert(0, os.getcwd())
 import numpy as np

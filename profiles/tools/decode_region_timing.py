@@ -1,6 +1,6 @@
-import ctypes as C, os, sys, json
+import ctypes as C, os, sys
 sys.path.insert(0, os.getcwd())
-import numpy as np, torch
+import torch
 from pcodec_b200 import _lib, datagen, ChunkConfig, ModeSpec, DeltaSpec
 L=_lib.lib()
 n_chunks=1024; CH=1<<18; n=n_chunks*CH

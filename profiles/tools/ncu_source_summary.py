@@ -1,5 +1,5 @@
 """Summarise an `ncu --page source --csv` export: stall-reason totals and the hottest SASS instructions."""
-import csv, sys, collections
+import csv, sys
 path = sys.argv[1]; topn = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 rows = list(csv.reader(open(path)))
 hdr = rows[1]; idx = {h: i for i, h in enumerate(hdr)}
