@@ -155,6 +155,7 @@ def run_reference_arm(args, rank):
     finally:
         arm.close()
     v = float(np.median([x[0] for x in vals]))
+    one = cpu_roundtrip(4, 1)  # one thread and all host cores in the same run
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "MB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
@@ -162,7 +163,8 @@ def run_reference_arm(args, rank):
                    "chunks_per_step": sample, "chunk_n": CHUNK_N},
         "cpu_baseline": {"value": v, "unit": "MB/s", "cores": threads, "kind": "port",
                          "sample": f"{sample} chunks of 2^18 u64 per step, {k} per worker process, one process per host thread; C++ restatement of pco 1.0.3 (oracle/), not the Rust crate",
-                         "compress_mb_s": float(np.median([x[1] for x in vals])), "decompress_mb_s": float(np.median([x[2] for x in vals]))},
+                         "compress_mb_s": float(np.median([x[1] for x in vals])), "decompress_mb_s": float(np.median([x[2] for x in vals])),
+                         "single_core": {"value": one[0], "compress_mb_s": one[1], "decompress_mb_s": one[2], "sample": f"{one[4]} chunks, one process"}},
         "e2e": {"value": v, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -460,9 +462,11 @@ def run_gpu_arm(args, rank, world):
     if not args.no_cpu_baseline and world == 1:  # the CPU arm beside the GPU number: rank 0 at N = 1 only
         threads = host_threads()
         v = cpu_roundtrip(max(threads, args.cpu_sample_chunks), threads)
+        one = cpu_roundtrip(4, 1)  # one thread and all host cores in the same run
         cpu = {"value": v[0], "unit": "MB/s", "cores": threads, "kind": "port",
                "sample": f"{v[4]} chunks of 2^18 u64 (same generator), one worker process per host thread; C++ restatement of pco 1.0.3 (oracle/), not the Rust crate",
-               "compress_mb_s": v[1], "decompress_mb_s": v[2]}
+               "compress_mb_s": v[1], "decompress_mb_s": v[2],
+               "single_core": {"value": one[0], "compress_mb_s": one[1], "decompress_mb_s": one[2], "sample": f"{one[4]} chunks, one process"}}
 
     line = {
         "metric": METRIC, "value": value, "unit": "MB/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
