@@ -121,3 +121,24 @@ def test_baseline_config_3_planner_parameters(oracle):  # FloatMult(0.01) + orde
     assert c["mode"] == "FloatMult(0.01)" and c["delta_encoding"].startswith("Consecutive(order=2")
     assert c["latent_var"]["primary"]["n_bins"] <= 256 and c["latent_var"]["primary"]["ans_size_log"] <= 10
     assert c["latent_var"]["secondary"]["n_bins"] <= 64 and c["latent_var"]["secondary"]["ans_size_log"] <= 8
+
+
+def test_auto_config_on_the_baseline_data(oracle):
+    """ChunkConfig::default() (Auto mode, Auto delta) on the BASELINE data: the reference's search settles on the explicit configs the
+    BASELINE names - Classic + order 1 for C2, FloatMult(0.01) + order 2 for C3, Classic + no delta for C1 - so the explicit-config
+    bench measures what a default-config user would get; C3 is the case where the mode search matters (21x smaller than Classic)."""
+    from pcodec_b200 import datagen
+
+    def chosen(nums):
+        data = oracle.simple_compress(nums, oracle.make_config(mode=oracle.MODE_AUTO, delta=oracle.DELTA_AUTO))
+        c = insp.inspect(data)["chunk"][0]
+        return c["mode"], c["delta_encoding"].split(",")[0].rstrip(")") + ")" if "(" in c["delta_encoding"] else c["delta_encoding"], len(data)
+
+    assert chosen(datagen.c1_u32_lomax(seed=0))[:2] == ("Classic", "NoOp")
+    assert chosen(datagen.c2_u64_cumsum_geometric(seed=0))[:2] == ("Classic", "Consecutive(order=1)")
+    mode, delta, size = chosen(datagen.c3_f64_decimal_sinusoid(seed=0))
+    assert (mode, delta) == ("FloatMult(0.01)", "Consecutive(order=2)")
+    nums = datagen.c3_f64_decimal_sinusoid(seed=0)
+    assert size == len(oracle.simple_compress(nums, oracle.make_config(mode=oracle.MODE_FLOAT_MULT, float_mult_base=0.01, delta=oracle.DELTA_CONSECUTIVE, delta_order=2)))
+    classic = len(oracle.simple_compress(nums, oracle.make_config(mode=oracle.MODE_CLASSIC, delta=oracle.DELTA_AUTO)))
+    assert classic > 15 * size
