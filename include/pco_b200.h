@@ -118,6 +118,22 @@ size_t pco_b200_index_size_bound(size_t n, size_t n_chunks_hint);
 PcoB200Error pco_b200_build_index(const void *compressed, size_t compressed_len, unsigned char dtype, void *index,
                                   size_t index_cap, size_t *index_len, uint32_t flags, void *cuda_stream);
 
+/* ModeSpec::Auto as the reference resolves it for ONE chunk of numbers in HOST memory (pco/src/data_types/unsigned.rs:28-35,
+ * pco/src/data_types/float.rs:70-98: int_mult::choose_base for integers; Classic vs FloatMult vs FloatQuant bids for f32 / f64 on the
+ * sample of pco/src/sampling.rs:62-103).  Host-only planner logic: needs no device, reads ~n/40 numbers.  out->mode_spec is a
+ * PCO_B200_MODE_* value with its parameter in the matching field, ready to be pasted into a PcoB200ChunkConfig; FloatMult also
+ * reports the inverse the reference's splitter would multiply by (snapping to 1/100 etc. makes it differ from 1/base in the last bit,
+ * which only changes the secondary latents' values, never validity).  f16 always answers Classic. */
+typedef struct PcoB200ModeChoice {
+  uint32_t mode_spec;
+  uint32_t float_quant_k;
+  double float_mult_base;
+  double float_mult_inv_base;
+  uint64_t int_mult_base;
+  double bits_saved_per_num; /* the winning bid's estimate (0 for Classic and IntMult) */
+} PcoB200ModeChoice;
+PcoB200Error pco_b200_choose_mode(const void *nums, size_t n, unsigned char dtype, PcoB200ModeChoice *out);
+
 /* Measurement hooks (no reference counterpart): when enabled, every kernel launched by the next call is bracketed by
  * CUDA events on the launching stream; pco_b200_profile_last returns "kernel=milliseconds;..." for the last call. */
 void pco_b200_profile_enable(int on);

@@ -8,6 +8,7 @@
 
 #include "encode_kernels.cuh"
 #include "host_common.hpp"
+#include "mode_search.hpp"
 
 #ifndef PCOB_ONE_PASS_DEFAULT
 #define PCOB_ONE_PASS_DEFAULT true  // PCOB200_ONE_PASS_FRONT_END=0 selects the two-kernel front end (A/B runs)
@@ -169,11 +170,51 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
       }
       break;
     }
-    case PCO_B200_MODE_AUTO:
-      // The reference's Auto mode search (int_mult::choose_base, float_mult / float_quant detection on a random sample,
-      // with HashMap-order-dependent ties) is not restated: Auto on the GPU path means Classic, which is always valid.
+    case PCO_B200_MODE_AUTO: {
+      // Default: Auto on the GPU path means Classic, which is always valid.  With PCOB200_AUTO_MODE_SEARCH=1 the reference's mode
+      // search (mode_search.hpp: int_mult::choose_base, FloatMult / FloatQuant bids on the reference's sample) runs on the host over
+      // the call's FIRST chunk and its answer is used for every chunk of the call (the reference searches per chunk; one array is
+      // usually one kind of data).  Opt-in until it has been measured on a GPU box.
       ep.mode = MODE_CLASSIC;
+      static const bool search = [] { const char* e = std::getenv("PCOB200_AUTO_MODE_SEARCH"); return e && e[0] == '1'; }();
+      if (search && !pages.empty() && !(is_float && lbits == 16)) {  // f16 stays Classic (no FloatMult kernel for it)
+        const size_t n0 = size_t(pages[0]);
+        std::vector<L> staged;
+        const L* first = static_cast<const L*>(nums);
+        if (src_dev) {
+          staged.resize(n0);
+          PCOB_CUDA_TRY(cudaMemcpyAsync(staged.data(), nums, n0 * sizeof(L), cudaMemcpyDeviceToHost, stream));
+          PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
+          first = staged.data();
+        }
+        mode_search::Choice c;
+        if constexpr (sizeof(L) == 8) c = is_float ? mode_search::choose_float<double>(first, n0) : mode_search::choose_int<L>(first, n0, nt_is_signed(dtype));
+        else if constexpr (sizeof(L) == 4) c = is_float ? mode_search::choose_float<float>(first, n0) : mode_search::choose_int<L>(first, n0, nt_is_signed(dtype));
+        else if (!is_float) c = mode_search::choose_int<L>(first, n0, nt_is_signed(dtype));
+        if (c.kind == 1) {
+          ep.mode = MODE_INT_MULT;
+          ep.mode_base = c.int_base;
+        } else if (c.kind == 3) {
+          ep.mode = MODE_FLOAT_QUANT;
+          ep.mode_k = c.k;
+        } else if (c.kind == 2 && lbits == 64) {
+          ep.mode = MODE_FLOAT_MULT;
+          std::memcpy(&ep.base_bits, &c.base, 8);
+          std::memcpy(&ep.inv_base_bits, &c.inv_base, 8);
+          ep.mode_base = (ep.base_bits >> 63) ? ~ep.base_bits : (ep.base_bits ^ (uint64_t(1) << 63));
+        } else if (c.kind == 2) {
+          const float base = float(c.base), inv = float(c.inv_base);
+          uint32_t bb, ib;
+          std::memcpy(&bb, &base, 4);
+          std::memcpy(&ib, &inv, 4);
+          ep.mode = MODE_FLOAT_MULT;
+          ep.base_bits = bb;
+          ep.inv_base_bits = ib;
+          ep.mode_base = (bb >> 31) ? uint32_t(~bb) : (bb ^ 0x80000000u);
+        }
+      }
       break;
+    }
     default: return fail(PCO_B200_UNSUPPORTED, "ModeSpec::TryDict is outside the GPU hot path");
   }
   bool auto_delta = false;

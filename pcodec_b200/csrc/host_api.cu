@@ -579,6 +579,29 @@ int pco_b200_debug_enc_timing(unsigned long long* out32) {
 }
 #endif
 
+// ModeSpec::Auto for one chunk in host memory (mode_search.hpp); no device involved
+PcoB200Error pco_b200_choose_mode(const void* nums, size_t n, unsigned char dtype, PcoB200ModeChoice* out) {
+  if (!out || (!nums && n)) return fail(PCO_B200_INVALID_ARGUMENT, "null argument");
+  if (!nt_valid(dtype)) return fail(PCO_B200_INVALID_ARGUMENT, "unknown number type byte");
+  if (n > (size_t(1) << 24)) return fail(PCO_B200_INVALID_ARGUMENT, "count may not exceed 16777216 per chunk");
+  std::memset(out, 0, sizeof(*out));
+  mode_search::Choice c;
+  const bool is_float = nt_is_float(dtype), is_signed = nt_is_signed(dtype);
+  switch (nt_bits(dtype)) {
+    case 64: c = is_float ? mode_search::choose_float<double>(static_cast<const uint64_t*>(nums), n) : mode_search::choose_int<uint64_t>(static_cast<const uint64_t*>(nums), n, is_signed); break;
+    case 32: c = is_float ? mode_search::choose_float<float>(static_cast<const uint32_t*>(nums), n) : mode_search::choose_int<uint32_t>(static_cast<const uint32_t*>(nums), n, is_signed); break;
+    case 16: if (!is_float) c = mode_search::choose_int<uint16_t>(static_cast<const uint16_t*>(nums), n, is_signed); break;
+    default: c = mode_search::choose_int<uint8_t>(static_cast<const uint8_t*>(nums), n, is_signed); break;
+  }
+  out->mode_spec = c.kind == 1 ? PCO_B200_MODE_TRY_INT_MULT : c.kind == 2 ? PCO_B200_MODE_TRY_FLOAT_MULT : c.kind == 3 ? PCO_B200_MODE_TRY_FLOAT_QUANT : PCO_B200_MODE_CLASSIC;
+  out->float_quant_k = c.k;
+  out->float_mult_base = c.base;
+  out->float_mult_inv_base = c.inv_base;
+  out->int_mult_base = c.int_base;
+  out->bits_saved_per_num = c.bits_saved_per_num;
+  return PCO_B200_OK;
+}
+
 void pco_b200_profile_enable(int on) { profiler().enabled = on != 0; }
 // Which decode instantiation served the chunks of the last decode launch: counts[k] = chunks of class k
 // (1, 2: decode_kernel<L, 1 / 2>; 3, 4: decode_narrow_kernel order 0 / 1).  Returns the number of chunks.

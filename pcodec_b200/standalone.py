@@ -178,3 +178,21 @@ def decompress_chunks(src, dtype, chunk_offsets, chunk_ns):
                                       dst.ctypes.data_as(C.c_void_p), C.c_size_t(dst.size), C.byref(n_written), C.c_uint32(0), None)
     _lib.check(rc)
     return dst[: n_written.value]
+
+
+class _CModeChoice(C.Structure):
+    _fields_ = [("mode_spec", C.c_uint32), ("float_quant_k", C.c_uint32), ("float_mult_base", C.c_double), ("float_mult_inv_base", C.c_double),
+                ("int_mult_base", C.c_uint64), ("bits_saved_per_num", C.c_double)]
+
+
+def choose_mode(nums):
+    """What `ModeSpec.auto()` resolves to in the reference for this chunk of numbers (pco/src/data_types/unsigned.rs:28-35,
+    float.rs:70-98): a ModeSpec to put into a ChunkConfig.  Host-side planner logic of libcpcodec.so (pco_b200_choose_mode); needs no
+    device.  `.inv_base` on a FloatMult answer is the inverse the reference's splitter multiplies by."""
+    arr = np.ascontiguousarray(nums)
+    out = _CModeChoice()
+    _lib.check(_lib.lib().pco_b200_choose_mode(C.c_void_p(arr.ctypes.data), C.c_size_t(arr.size), C.c_ubyte(_lib.dtype_byte(arr.dtype)), C.byref(out)))
+    spec = _lib.ModeSpec(out.mode_spec, base=out.float_mult_base, k=out.float_quant_k, int_base=out.int_mult_base)
+    spec.inv_base = out.float_mult_inv_base
+    spec.bits_saved_per_num = out.bits_saved_per_num
+    return spec
