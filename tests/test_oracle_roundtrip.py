@@ -131,3 +131,49 @@ def test_bit_flips_never_crash(oracle):  # corruption.rs:26-79 (sampled)
             oracle.simple_decompress(bytes(d), np.uint32)
         except oracle.OracleError:
             pass
+
+
+def _assert_recovers(oracle, nums, level):  # recovery.rs:49-84: mode in {Classic, Auto} x the delta specs the oracle encodes
+    deltas = [(oracle.DELTA_NOOP, 0), (oracle.DELTA_CONSECUTIVE, 0), (oracle.DELTA_CONSECUTIVE, 1), (oracle.DELTA_CONSECUTIVE, 7), (oracle.DELTA_LOOKBACK, 0),
+              (oracle.DELTA_AUTO, 0)]
+    modes = [oracle.MODE_CLASSIC] + ([oracle.MODE_AUTO] if nums.dtype != np.float16 else [])  # the f16 mode search is not restated
+    for mode in modes:
+        for delta, order in deltas:
+            cfg = oracle.make_config(level=level, mode=mode, delta=delta, delta_order=order, enable_8_bit=True)
+            data = oracle.simple_compress(nums, cfg)
+            got = oracle.simple_decompress(data, nums.dtype)
+            np.testing.assert_array_equal(bits_view(got), bits_view(nums), err_msg=f"mode={mode} delta={delta}@{order}")
+            assert len(data) <= oracle.file_size_guarantee(nums.size, nums.dtype)
+
+
+def test_recovery_edge_cases(oracle):  # recovery.rs:86-114
+    _assert_recovers(oracle, np.array([0, (1 << 64) - 1], dtype=np.uint64), 0)
+    _assert_recovers(oracle, np.array([np.finfo(np.float64).min, np.finfo(np.float64).max]), 0)
+    for level in (0, 1, 2):
+        _assert_recovers(oracle, np.array([1.2], dtype=np.float32), level)
+    for dtype, level in ((np.uint32, 6), (np.uint32, 0), (np.uint16, 6), (np.uint8, 6)):
+        _assert_recovers(oracle, np.zeros(0, dtype=dtype), level)
+    f16 = np.array([-np.inf, np.finfo(np.float16).min, -1.0, -0.0, np.nan, 0.0, 1.0, np.finfo(np.float16).max, np.inf], dtype=np.float16)
+    _assert_recovers(oracle, f16, 5)
+
+
+def test_recovery_moderate_and_sparse(oracle):  # recovery.rs:116-135, :318-330
+    _assert_recovers(oracle, np.arange(-50000, 50000, dtype=np.int32), 3)
+    _assert_recovers(oracle, np.array([1] * 10000 + [0, 0, 1], dtype=np.int32), 1)
+    rng = np.random.default_rng(0)
+    islands = np.concatenate([np.append(rng.integers(0, 8, size=99), rng.integers(1000, 1008)) for _ in range(20)]).astype(np.int32)
+    _assert_recovers(oracle, islands, 4)
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16, np.uint32, np.uint64, np.int8, np.int16, np.int32, np.int64, np.float32, np.float64])
+def test_recovery_codecs_with_auto_mode(oracle, dtype):  # recovery.rs:137-242: every type at several levels, extremes included
+    dt = np.dtype(dtype)
+    if dt.kind == "f":
+        fi = np.finfo(dtype)
+        nums = np.array([-np.inf, fi.min, -1.0, -0.0, np.nan, 0.0, fi.tiny / 2, 1.0, fi.max, np.inf] * 30, dtype=dtype)
+    else:
+        ii = np.iinfo(dtype)
+        nums = np.array([ii.min, ii.min + 1, -1 if ii.min < 0 else 1, 0, 1, ii.max - 1, ii.max] * 40, dtype=dtype)
+    for level in (0, 1, 5, 8):
+        _assert_recovers(oracle, nums, level)
+    _assert_recovers(oracle, _data(dtype, 3000, 4), 8)
