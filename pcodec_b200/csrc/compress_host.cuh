@@ -177,7 +177,8 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
       // usually one kind of data).  Opt-in until it has been measured on a GPU box.
       ep.mode = MODE_CLASSIC;
       static const bool search = [] { const char* e = std::getenv("PCOB200_AUTO_MODE_SEARCH"); return e && e[0] == '1'; }();
-      if (search && !pages.empty() && !(is_float && lbits == 16)) {  // f16 stays Classic (no FloatMult kernel for it)
+      const bool multi_page_chunk = (flags & PCO_B200_INTERNAL_SHARED_BINS) && pages.size() > 1;  // shared bins exist for one latent var only
+      if (search && !pages.empty() && !(is_float && lbits == 16) && !multi_page_chunk) {  // f16 stays Classic (no FloatMult kernel for it)
         const size_t n0 = size_t(pages[0]);
         std::vector<L> staged;
         const L* first = static_cast<const L*>(nums);
