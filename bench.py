@@ -109,13 +109,21 @@ class CpuArm:
     def run(self):
         """Returns (MB/s round trip, compress MB/s, decompress MB/s, compressed bytes): bytes of all workers over the slowest
         worker's time (they run concurrently from a common barrier)."""
-        res = self.pool.map(_cpu_worker_run, range(self.workers), chunksize=1)
+        # map_async + timeout: a pool whose workers die at start-up is respawned forever and a plain map() would never return
+        try:
+            res = self.pool.map_async(_cpu_worker_run, range(self.workers), chunksize=1).get(timeout=120 + 2 * self.k)
+        except Exception:
+            self.broken = True
+            raise
         mb = self.workers * self.k * CHUNK_N * 8 / 1e6
         tc, td = max(r[0] for r in res), max(r[1] for r in res)
         return mb / max(r[0] + r[1] for r in res), mb / tc, mb / td, sum(r[2] for r in res)
 
     def close(self):
-        self.pool.close()
+        if getattr(self, "broken", False):
+            self.pool.terminate()
+        else:
+            self.pool.close()
         self.pool.join()
 
 
@@ -142,7 +150,7 @@ def run_reference_arm(args, rank):
     if rank != 0:
         return
     vals, err = None, None
-    for threads in sorted({host_threads(), min(host_threads(), 32), min(host_threads(), 8), 1}, reverse=True):
+    for threads in sorted({host_threads(), min(host_threads(), 8), 1}, reverse=True):
         # all host threads; if a pool of that size cannot be brought up on this host, a smaller one still gives a line (and says so)
         k = max(1, args.cpu_sample_chunks // threads)
         sample = threads * k
