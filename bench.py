@@ -55,6 +55,7 @@ def parse_args():
 # compress), and a Python thread pool around per-chunk ctypes calls adds GIL-held buffer copies on top.  Measured on the
 # authoring box: 8 processes = 8x one.
 _W = {}
+CPU_RUN_TIMEOUT_S = 120  # one timed pass of the pool; far above the ~1 s it takes
 
 
 def host_threads():
@@ -111,7 +112,7 @@ class CpuArm:
         worker's time (they run concurrently from a common barrier)."""
         # map_async + timeout: a pool whose workers die at start-up is respawned forever and a plain map() would never return
         try:
-            res = self.pool.map_async(_cpu_worker_run, range(self.workers), chunksize=1).get(timeout=120 + 2 * self.k)
+            res = self.pool.map_async(_cpu_worker_run, range(self.workers), chunksize=1).get(timeout=CPU_RUN_TIMEOUT_S + 2 * self.k)
         except Exception:
             self.broken = True
             raise
