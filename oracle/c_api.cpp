@@ -571,6 +571,29 @@ void pco_oracle_kat_choose_float_mode_f64(const double* nums, size_t n, int* kin
 int32_t pco_oracle_kat_float_exponent_f32(float x) { return fl_exponent<float>(x); }
 float pco_oracle_kat_float_exp2_f32(int32_t p) { return fl_exp2<float>(p); }
 
+void pco_oracle_kat_conv1_v1_0_0_parameters(int on) { conv1_v1_0_0_parameters() = on != 0; }
+// pco/src/delta/conv1.rs unit tests (:503-583): matrices are row-major here (h x w), column-major inside
+void pco_oracle_kat_conv_autocov_mats(const double* v, size_t n, size_t order, double regularization, double* xtx_colmajor, double* xty) {
+  ConvMatrix xtx(0.0, 0, 0), y(0.0, 0, 0);
+  conv_autocov_mats(std::vector<double>(v, v + n), order, regularization, &xtx, &y);
+  for (size_t i = 0; i < xtx.data.size(); i++) xtx_colmajor[i] = xtx.data[i];
+  for (size_t i = 0; i < y.data.size(); i++) xty[i] = y.data[i];
+}
+static ConvMatrix conv_from_rows(const double* rows, size_t h, size_t w) {
+  ConvMatrix m(0.0, h, w);
+  for (size_t i = 0; i < h; i++) for (size_t j = 0; j < w; j++) m.at(i, j) = rows[i * w + j];
+  return m;
+}
+void pco_oracle_kat_conv_cholesky(const double* rows, size_t h, double* out_colmajor) {
+  ConvMatrix c = conv_cholesky(conv_from_rows(rows, h, h));
+  for (size_t i = 0; i < c.data.size(); i++) out_colmajor[i] = c.data[i];
+}
+void pco_oracle_kat_conv_sub(int transposed_backward, const double* l_rows, size_t h, const double* y, double* out) {
+  ConvMatrix l = conv_from_rows(l_rows, h, h), yy = conv_from_rows(y, h, 1);
+  ConvMatrix x = transposed_backward ? conv_transposed_backward_sub(l, std::move(yy)) : conv_forward_sub(l, std::move(yy));
+  for (size_t i = 0; i < h; i++) out[i] = x.data[i];
+}
+
 int pco_oracle_kat_consecutive_encode_u32(uint32_t* latents, size_t n, size_t order, uint32_t* moments_out) {
   return guarded([&] {
     auto m = consecutive_encode_in_place<uint32_t>(order, latents, n);

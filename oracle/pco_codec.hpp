@@ -312,6 +312,175 @@ inline void conv1_decode_in_place(const DeltaEncoding& cfg, std::vector<L>& stat
   for (size_t i = 0; i < order; i++) state[i] = residuals[len + i];
 }
 
+// ----- conv1 encode (delta/conv1.rs:12-147 the small matrix type, :256-461 fit + encode) --------------------------------
+// All of the fit is f64 with the reference's exact operation order: plain multiply-adds where it writes `a * b + c`, fused ones
+// (std::fma) where it calls mul_add.  Pinned by its unit tests (:503-583) and by re-encoding v1_0_0_conv1.pco byte for byte.
+struct ConvMatrix {  // column-major (conv1.rs:16-52)
+  std::vector<double> data;
+  size_t h = 0, w = 0;
+  ConvMatrix(double value, size_t h_, size_t w_) : data(h_ * w_, value), h(h_), w(w_) {}
+  double& at(size_t i, size_t j) { return data[i + j * h]; }
+  double at(size_t i, size_t j) const { return data[i + j * h]; }
+};
+inline ConvMatrix conv_cholesky(ConvMatrix m) {  // :54-93 Cholesky-Crout, L of X = L L*
+  const size_t h = m.h;
+  for (size_t j = 0; j < h; j++) {
+    for (size_t i = 0; i < j; i++) m.at(i, j) = 0.0;
+    double s = 0.0;
+    for (size_t k = 0; k < j; k++) {
+      const double value = m.at(j, k);
+      s = std::fma(value, value, s);
+    }
+    const double diag_value = std::sqrt(std::fmax(m.at(j, j) - s, 0.0));  // safe_sqrt; f64::max returns the non-NaN operand like fmax
+    m.at(j, j) = diag_value;
+    const double scale = diag_value == 0.0 ? 0.0 : 1.0 / diag_value;
+    for (size_t i = j + 1; i < h; i++) {
+      double t = 0.0;
+      for (size_t k = 0; k < j; k++) t = std::fma(m.at(i, k), m.at(j, k), t);
+      m.at(i, j) = scale * (m.at(i, j) - t);
+    }
+  }
+  return m;
+}
+inline ConvMatrix conv_forward_sub(const ConvMatrix& l, ConvMatrix y) {  // :122-146 solves L x = y
+  for (size_t k = 0; k < y.w; k++)
+    for (size_t j = 0; j < l.h; j++) {
+      const double diag_value = y.at(j, k) / l.at(j, j);
+      y.at(j, k) = diag_value;
+      for (size_t i = j + 1; i < l.h; i++) y.at(i, k) = y.at(i, k) - diag_value * l.at(i, j);
+    }
+  return y;
+}
+inline ConvMatrix conv_transposed_backward_sub(const ConvMatrix& l, ConvMatrix y) {  // :96-119 solves L^T x = y
+  for (size_t k = 0; k < y.w; k++)
+    for (size_t j = l.h; j-- > 0;) {
+      const double diag_value = y.at(j, k) / l.at(j, j);
+      y.at(j, k) = diag_value;
+      for (size_t i = 0; i < j; i++) y.at(i, k) = y.at(i, k) - diag_value * l.at(j, i);
+    }
+  return y;
+}
+constexpr size_t CONV1_ENCODE_BATCH_SIZE = 512;  // :11
+// Test knob: pco 1.0.0 (which wrote pco/assets/v1_0_0_conv1.pco) fitted without the L2 term and kept one more bit of quantization
+// than 1.0.3 does; with this set the asset re-encodes byte for byte, which pins everything else in the conv1 path and the planner.
+inline bool& conv1_v1_0_0_parameters() { static bool on = false; return on; }
+inline std::vector<double> conv_initial_autocov_dots(const std::vector<double>& v, size_t order) {  // :256-287
+  const size_t n = v.size();
+  std::vector<double> dots(order + 1, 0.0);
+  const size_t almost_n = (n - order) / CONV1_ENCODE_BATCH_SIZE * CONV1_ENCODE_BATCH_SIZE;
+  for (size_t start = 0; start < almost_n; start += CONV1_ENCODE_BATCH_SIZE)
+    for (size_t sep = 0; sep <= order; sep++) {
+      double dot0 = 0.0, dot1 = 0.0, dot2 = 0.0, dot3 = 0.0;
+      for (size_t i = start; i < start + CONV1_ENCODE_BATCH_SIZE; i += 4) {
+        dot0 += v[i] * v[i + sep];
+        dot1 += v[i + 1] * v[i + sep + 1];
+        dot2 += v[i + 2] * v[i + sep + 2];
+        dot3 += v[i + 3] * v[i + sep + 3];
+      }
+      dots[sep] += (dot0 + dot1) + (dot2 + dot3);
+    }
+  for (size_t i = almost_n; i < n - order; i++)
+    for (size_t sep = 0; sep <= order; sep++) dots[sep] += v[i] * v[i + sep];
+  return dots;
+}
+inline void conv_autocov_mats(const std::vector<double>& v, size_t order, double regularization, ConvMatrix* xtx_out, ConvMatrix* xty_out) {  // :290-346
+  const size_t n = v.size();
+  double initial_sum = 0.0;
+  for (size_t i = 0; i < n - order; i++) initial_sum += v[i];
+  const std::vector<double> initial_dots = conv_initial_autocov_dots(v, order);
+  ConvMatrix xtx(0.0, order + 1, order + 1), xty(0.0, order + 1, 1);
+  for (size_t i = 0; i < order; i++) {
+    xtx.at(i, 0) = initial_dots[i];
+    xtx.at(0, i) = initial_dots[i];
+  }
+  xtx.at(order, 0) = initial_sum;
+  xtx.at(0, order) = initial_sum;
+  xty.at(0, 0) = initial_dots[order];
+  for (size_t i = 1; i < order; i++) {
+    for (size_t j = 1; j <= i; j++) {
+      const double dot = xtx.at(i - 1, j - 1) + (v[n - order + i - 1] * v[n - order + j - 1] - v[i - 1] * v[j - 1]);
+      xtx.at(i, j) = dot;
+      xtx.at(j, i) = dot;
+    }
+    const double sum = xtx.at(order, i - 1) + (v[n - order + i - 1] - v[i - 1]);
+    xtx.at(order, i) = sum;
+    xtx.at(i, order) = sum;
+  }
+  for (size_t i = 1; i < order; i++) xty.at(i, 0) = xtx.at(order - 1, i - 1) + (v[n - order + i - 1] * v[n - 1] - v[i - 1] * v[order - 1]);
+  xtx.at(order, order) = double(n - order);
+  xty.at(order, 0) = xtx.at(order, order - 1) + (v[n - 1] - v[order - 1]);
+  for (size_t i = 0; i <= order; i++) xtx.at(i, i) = xtx.at(i, i) + regularization;
+  *xtx_out = std::move(xtx);
+  *xty_out = std::move(xty);
+}
+inline std::vector<double> conv_autocorr_least_squares(const std::vector<double>& v, size_t order) {  // :348-361
+  ConvMatrix xtx(0.0, 0, 0), xty(0.0, 0, 0);
+  conv_autocov_mats(v, order, conv1_v1_0_0_parameters() ? 0.0 : 0.1, &xtx, &xty);  // L2_REGULARIZATION
+  const ConvMatrix chol = conv_cholesky(std::move(xtx));
+  return conv_transposed_backward_sub(chol, conv_forward_sub(chol, std::move(xty))).data;
+}
+inline int64_t f64_as_i64(double x) {  // Rust `as i64`: saturating, NaN -> 0
+  if (std::isnan(x)) return 0;
+  if (x >= 9223372036854775808.0) return std::numeric_limits<int64_t>::max();
+  if (x <= -9223372036854775808.0) return std::numeric_limits<int64_t>::min();
+  return int64_t(x);
+}
+// conv1.rs:363-421 choose_config; false = None (the caller falls back to NoOp, chunk_compressor.rs:387-391)
+template <typename L>
+inline bool conv1_choose_config(size_t order, const L* latents, size_t n, DeltaEncoding* out) {
+  using S = typename ConvType<L>::S;
+  if (n < order + 1) return false;
+  const L center = choose_pivot<L>(latents, n);
+  std::vector<double> v(n);
+  for (size_t i = 0; i < n; i++) v[i] = latents[i] < center ? -double(uint64_t(L(center - latents[i]))) : double(uint64_t(L(latents[i] - center)));
+  const std::vector<double> beta = conv_autocorr_least_squares(v, order);
+  double total_weight = 0.0, total_abs_weight = 0.0;
+  for (size_t i = 0; i < order; i++) {
+    total_abs_weight += std::fabs(beta[i]);
+    total_weight += beta[i];
+  }
+  if (!std::isfinite(total_weight) || !std::isfinite(total_abs_weight)) return false;
+  const double float_bias = ((1.0 - total_weight) * double(uint64_t(center))) + beta[order];
+  const double conv_max = double(std::numeric_limits<S>::max()), l_max = double(uint64_t(std::numeric_limits<L>::max()));
+  const double lg = std::floor(std::log2(conv_max / (total_abs_weight * l_max + std::fabs(float_bias) + 1.0)));
+  int64_t q64 = std::isnan(lg) ? 0 : (lg >= 2147483647.0 ? 2147483647 : (lg <= -2147483648.0 ? -2147483648ll : int64_t(lg)));  // `as i32`
+  int32_t quantization = int32_t(std::max<int64_t>(q64 - (conv1_v1_0_0_parameters() ? 0 : 1), -2147483648ll));
+  quantization = std::min<int32_t>(quantization, int32_t(MAX_CONV1_DELTA_QUANTIZATION));
+  quantization = std::min<int32_t>(quantization, int32_t(8 * sizeof(S)) - 1);
+  if (quantization < 0) return false;
+  const double quantize_factor = std::ldexp(1.0, quantization);
+  DeltaEncoding d;
+  d.kind = DeltaKind::Conv1;
+  d.quantization = Bitlen(quantization);
+  for (size_t i = 0; i < order; i++) d.weights.push_back(f64_as_i64(std::round(beta[i] * quantize_factor)));
+  d.bias = f64_as_i64(float_bias * quantize_factor);
+  *out = d;
+  return true;
+}
+// conv1.rs:423-461 encode_in_place: residual_i = latent_i - predict(latent_{i-order..i}) + MID from the ORIGINAL latents; the first
+// `order` entries become junk (latent + MID, the reference's zero-initialised predictions) and are not stored
+template <typename L>
+inline std::vector<L> conv1_encode_in_place(const DeltaEncoding& cfg, L* latents, size_t len) {
+  using S = typename ConvType<L>::S;
+  using US = typename std::make_unsigned<S>::type;
+  const size_t order = cfg.weights.size();
+  std::vector<L> initial_state(latents, latents + std::min(order, len));
+  std::vector<L> original(latents, latents + len);
+  const S bias = S(cfg.bias);
+  for (size_t i = 0; i < len; i++) {
+    L prediction = 0;
+    if (i >= order) {
+      US s = US(bias);
+      for (size_t j = 0; j < order; j++) s = US(s + US(US(S(cfg.weights[j])) * US(S(original[i - order + j]))));
+      S ss = S(s);
+      if (ss < 0) ss = 0;
+      prediction = L(ss >> cfg.quantization);
+    }
+    latents[i] = L(L(original[i] - prediction) + LatentTraits<L>::MID);
+  }
+  return initial_state;
+}
+
 // ===========================================================================
 // Per-latent-var decompression
 // (pco/src/chunk_latent_decompressor.rs, page_latent_decompressor.rs)
@@ -1422,7 +1591,9 @@ inline std::unique_ptr<ChunkCompressor<L>> new_candidate(SplitLatents<L> latents
       case DeltaKind::NoOp: break;
       case DeltaKind::Consecutive: st = consecutive_encode_in_place<L>(enc.enc->order, v.data() + s, e - s); break;
       case DeltaKind::Lookback: st = lookback_encode_in_place<L>(*enc.enc, page_lookbacks.data(), v.data() + s, e - s); break;
-      case DeltaKind::Conv1: invalid_argument("oracle: Conv1 encode not restated"); break;
+      case DeltaKind::Conv1:
+        if constexpr (sizeof(L) <= 4) st = conv1_encode_in_place<L>(*enc.enc, v.data() + s, e - s);
+        break;
     }
     for (L x : st) pi.delta_state.push_back(uint64_t(x));
     pi.start = std::min(s + enc.n_latents_per_state(), e);
@@ -1494,7 +1665,11 @@ inline DeltaEncoding choose_delta_encoding(const SplitLatents<L>& latents, const
     case DeltaSpecKind::TryLookback: return new_lookback(n);
     case DeltaSpecKind::TryConv1:
       if (config.delta_order == 0) return noop;
-      invalid_argument("oracle: Conv1 encode not restated");
+      if constexpr (sizeof(L) <= 4) {  // delta/mod.rs:50-70 (64-bit latents were refused by validate_config)
+        DeltaEncoding d;
+        return conv1_choose_config<L>(config.delta_order, latents.primary.data(), n, &d) ? d : noop;
+      }
+      invalid_argument("Conv1 delta encoding cannot be used with 64-bit latents");
     case DeltaSpecKind::Auto: break;
   }
   // choose_auto_delta_encoding

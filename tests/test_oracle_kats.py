@@ -638,3 +638,80 @@ def test_auto_mode_for_floats_round_trips(oracle, dtype):  # data_types/float.rs
     data = oracle.simple_compress(nums, oracle.make_config(mode=oracle.MODE_AUTO, delta=oracle.DELTA_AUTO))
     assert np.array_equal(oracle.simple_decompress(data, dtype).view(u), nums.view(u))
     assert len(data) < n * 2 + 200  # ~13.3 bits per number for the multiplier, adjustments almost free
+
+
+def test_conv1_matrix_kats(oracle):  # pco/src/delta/conv1.rs:503-583
+    L = oracle.lib()
+    dp = C.POINTER(C.c_double)
+
+    def arr(x):
+        return np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+
+    v = arr([1.0, 2.0, -1.0, 5.0, -3.0])
+    xtx, xty = np.zeros(9), np.zeros(3)
+    L.pco_oracle_kat_conv_autocov_mats(v.ctypes.data_as(dp), C.c_size_t(5), C.c_size_t(2), C.c_double(0.7), xtx.ctypes.data_as(dp), xty.ctypes.data_as(dp))
+    assert xtx.tolist() == [6.7, -5.0, 2.0, -5.0, 30.7, 6.0, 2.0, 6.0, 3.7]  # exact, as the reference asserts
+    assert xty.tolist() == [12.0, -22.0, 1.0]
+    a = arr([[0.01, -0.2, -0.4], [-0.2, 13.0, 23.0], [-0.4, 23.0, 77.0]])
+    want = arr([[0.1, 0.0, 0.0], [-2.0, 3.0, 0.0], [-4.0, 5.0, 6.0]])
+    out = np.zeros(9)
+    L.pco_oracle_kat_conv_cholesky(a.ctypes.data_as(dp), C.c_size_t(3), out.ctypes.data_as(dp))
+    assert out.tolist() == want.T.reshape(-1).tolist()  # column-major data, exact
+    low, y, x = arr([[2.0, 0.0], [3.0, -4.0]]), arr([1.0, 2.0]), np.zeros(2)
+    L.pco_oracle_kat_conv_sub(0, low.ctypes.data_as(dp), C.c_size_t(2), y.ctypes.data_as(dp), x.ctypes.data_as(dp))
+    assert np.allclose(x, [0.5, -0.125], atol=1e-6)
+    L.pco_oracle_kat_conv_sub(1, low.ctypes.data_as(dp), C.c_size_t(2), y.ctypes.data_as(dp), x.ctypes.data_as(dp))
+    assert np.allclose(x, [1.25, -0.5], atol=1e-6)
+
+
+def test_conv1_asset_reencodes_byte_for_byte(oracle):
+    """pco/assets/v1_0_0_conv1.pco (2000 i32, ChunkConfig::default() + TryConv1(2), pco/src/tests/compatibility.rs:261-279) written by
+    pco 1.0.0.  Between 1.0.0 and 1.0.3 the fit gained an L2 term (L2_REGULARIZATION = 0.1) and lost one bit of quantization (the
+    `- 1` at delta/conv1.rs:403): with those two parameters set back, the oracle reproduces the asset's 1668 bytes exactly - the Auto
+    mode search, the f64 least-squares fit (bias equal in all 17 digits), the residuals, histogram, bin optimisation, tANS and
+    bit packing are then all pinned against real output of the Rust crate.  With 1.0.3's parameters the file differs as expected."""
+    from tests.golden_generators import GENERATORS, load_assets
+
+    asset, nums = load_assets()["v1_0_0_conv1"], GENERATORS["v1_0_0_conv1"]()
+    cfg = oracle.make_config(mode=oracle.MODE_AUTO, delta=oracle.DELTA_CONV1, delta_order=2)
+    L = oracle.lib()
+    try:
+        L.pco_oracle_kat_conv1_v1_0_0_parameters(1)
+        assert oracle.simple_compress(nums, cfg) == asset
+    finally:
+        L.pco_oracle_kat_conv1_v1_0_0_parameters(0)
+    current = oracle.simple_compress(nums, cfg)
+    assert current != asset and abs(len(current) - len(asset)) < 16
+    assert np.array_equal(oracle.simple_decompress(current, np.int32), nums)
+    info = oracle.inspect(current, np.int32)["chunks"][0]
+    assert info["delta"] == 3  # Conv1
+
+
+def test_conv1_recovery_cases(oracle):  # pco/src/tests/recovery.rs:454-540
+    x0, x1, x2 = 31, 77, -54
+    nums = [x0, x1, x2]
+    for _ in range(2000):
+        x = x2 - x1 + int(np.float32(0.99) * np.float32(x0)) + 3
+        nums.append(x)
+        x0, x1, x2 = x1, x2, x
+    nums = np.array(nums, dtype=np.int32)
+    data = oracle.simple_compress(nums, oracle.make_config(mode=oracle.MODE_AUTO, delta=oracle.DELTA_CONV1, delta_order=3))
+    assert oracle.inspect(data, np.int32)["chunks"][0]["delta"] == 3  # test_conv1_nominal: compressed with conv1
+    assert np.array_equal(oracle.simple_decompress(data, np.int32), nums)
+    # test_conv1_degenerate
+    for arr in (np.array([3], dtype=np.uint16), np.zeros(100, dtype=np.uint32), np.random.default_rng(0).integers(0, 1000, size=1000).astype(np.uint32)):
+        data = oracle.simple_compress(arr, oracle.make_config(mode=oracle.MODE_AUTO, delta=oracle.DELTA_CONV1, delta_order=2))
+        assert np.array_equal(oracle.simple_decompress(data, arr.dtype), arr)
+    # test_conv1_actually_applied
+    i = np.arange(1000, dtype=np.int64)
+    parabola = np.maximum(998 * 998 - i * i, 0).astype(np.uint32)
+    for order in (3, 6):
+        data = oracle.simple_compress(parabola, oracle.make_config(mode=oracle.MODE_AUTO, delta=oracle.DELTA_CONV1, delta_order=order))
+        from pcodec_b200 import inspect as insp
+
+        c = insp.inspect(data)["chunk"][0]
+        assert c["delta_encoding"].startswith("Conv1(") and c["delta_encoding"].count(",") == 1 + order  # quantization, bias, `order` weights
+        assert np.array_equal(oracle.simple_decompress(data, np.uint32), parabola)
+    # 64-bit latents are refused (delta/mod.rs:53-59, chunk_config.rs:285-295)
+    with pytest.raises(oracle.OracleError):
+        oracle.simple_compress(np.arange(100, dtype=np.uint64), oracle.make_config(mode=oracle.MODE_CLASSIC, delta=oracle.DELTA_CONV1, delta_order=2))

@@ -136,6 +136,8 @@ def test_bit_flips_never_crash(oracle):  # corruption.rs:26-79 (sampled)
 def _assert_recovers(oracle, nums, level):  # recovery.rs:49-84: mode in {Classic, Auto} x the delta specs the oracle encodes
     deltas = [(oracle.DELTA_NOOP, 0), (oracle.DELTA_CONSECUTIVE, 0), (oracle.DELTA_CONSECUTIVE, 1), (oracle.DELTA_CONSECUTIVE, 7), (oracle.DELTA_LOOKBACK, 0),
               (oracle.DELTA_AUTO, 0)]
+    if nums.dtype.itemsize <= 4:
+        deltas += [(oracle.DELTA_CONV1, 2), (oracle.DELTA_CONV1, 6)]  # 6: the reference has a specialised decode path for it
     modes = [oracle.MODE_CLASSIC] + ([oracle.MODE_AUTO] if nums.dtype != np.float16 else [])  # the f16 mode search is not restated
     for mode in modes:
         for delta, order in deltas:
