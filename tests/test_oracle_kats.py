@@ -715,3 +715,31 @@ def test_conv1_recovery_cases(oracle):  # pco/src/tests/recovery.rs:454-540
     # 64-bit latents are refused (delta/mod.rs:53-59, chunk_config.rs:285-295)
     with pytest.raises(oracle.OracleError):
         oracle.simple_compress(np.arange(100, dtype=np.uint64), oracle.make_config(mode=oracle.MODE_CLASSIC, delta=oracle.DELTA_CONV1, delta_order=2))
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("v0_0_0_classic", dict(mode="MODE_AUTO", delta="DELTA_NOOP")),               # compatibility.rs:70-82: 2000 i32, 2751-byte page
+    ("v0_3_0_f16", dict(mode="MODE_CLASSIC", delta="DELTA_AUTO")),                # :145-155: 2000 f16 (the asset's Auto mode chose Classic; the f16 search is not restated)
+    ("v0_4_0_lookback_delta", dict(mode="MODE_AUTO", delta="DELTA_LOOKBACK")),   # :182-197: lookback choice + encode
+    ("v0_4_8_minor_version", dict(mode="MODE_AUTO", delta="DELTA_AUTO")),        # :225-245
+])
+def test_older_assets_reencode_to_the_same_bins_and_page(oracle, name, kw):
+    """Assets written by older pco versions carry older header / metadata layouts, so whole files cannot match - but their bins and
+    their PAGE bytes (page meta + every batch) do: the planner and the encoder of 1.0.3, restated here, still produce exactly what
+    those versions wrote."""
+    from pcodec_b200 import inspect as insp
+    from tests.golden_generators import GENERATORS, load_assets
+
+    asset, nums = load_assets()[name], GENERATORS[name]()
+    data = oracle.simple_compress(nums, oracle.make_config(**{k: getattr(oracle, v) for k, v in kw.items()}))
+
+    def first_chunk(buf):
+        c = insp.inspect(buf)["chunk"][0]
+        start = c["byte_offset"] + c["meta_size"]
+        return c, buf[start:start + c["page_size"]]
+
+    ca, page_a = first_chunk(asset)
+    cd, page_d = first_chunk(data)
+    assert (ca["mode"], ca["delta_encoding"]) == (cd["mode"], cd["delta_encoding"])
+    assert {k: (v["ans_size_log"], v["bins"]) for k, v in ca["latent_var"].items()} == {k: (v["ans_size_log"], v["bins"]) for k, v in cd["latent_var"].items()}
+    assert page_a == page_d and len(page_a) > 0
