@@ -722,6 +722,7 @@ def test_conv1_recovery_cases(oracle):  # pco/src/tests/recovery.rs:454-540
     ("v0_3_0_f16", dict(mode="MODE_CLASSIC", delta="DELTA_AUTO")),                # :145-155: 2000 f16 (the asset's Auto mode chose Classic; the f16 search is not restated)
     ("v0_4_0_lookback_delta", dict(mode="MODE_AUTO", delta="DELTA_LOOKBACK")),   # :182-197: lookback choice + encode
     ("v0_4_8_minor_version", dict(mode="MODE_AUTO", delta="DELTA_AUTO")),        # :225-245
+    ("v0_3_0_float_quant", dict(mode="MODE_FLOAT_QUANT", float_quant_k=13, delta="DELTA_AUTO")),  # :157-178: two latent vars, 2905-byte page
 ])
 def test_older_assets_reencode_to_the_same_bins_and_page(oracle, name, kw):
     """Assets written by older pco versions carry older header / metadata layouts, so whole files cannot match - but their bins and
@@ -731,7 +732,7 @@ def test_older_assets_reencode_to_the_same_bins_and_page(oracle, name, kw):
     from tests.golden_generators import GENERATORS, load_assets
 
     asset, nums = load_assets()[name], GENERATORS[name]()
-    data = oracle.simple_compress(nums, oracle.make_config(**{k: getattr(oracle, v) for k, v in kw.items()}))
+    data = oracle.simple_compress(nums, oracle.make_config(**{k: getattr(oracle, v) if isinstance(v, str) else v for k, v in kw.items()}))
 
     def first_chunk(buf):
         c = insp.inspect(buf)["chunk"][0]
