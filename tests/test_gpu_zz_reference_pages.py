@@ -37,3 +37,12 @@ def test_gpu_reencodes_the_assets_page(name):
     assert (ca["mode"], ca["delta_encoding"]) == (cg["mode"], cg["delta_encoding"])
     assert {k: (v["ans_size_log"], v["bins"]) for k, v in ca["latent_var"].items()} == {k: (v["ans_size_log"], v["bins"]) for k, v in cg["latent_var"].items()}
     assert page_g == page_a
+
+
+@pytest.mark.parametrize("name", ["v1_0_0_u8", "v1_0_0_i8"])
+def test_gpu_reencodes_whole_current_format_assets(name):  # compatibility.rs:281-303: format 4.1 files, the whole file must match
+    import pcodec_b200 as p
+
+    asset, nums = load_assets()[name], GENERATORS[name]()
+    cfg = p.ChunkConfig(mode_spec=p.ModeSpec.classic(), delta_spec=p.DeltaSpec.try_consecutive(1), enable_8_bit=True)  # what the asset's Auto config resolved to
+    assert p.standalone.simple_compress(nums, cfg) == asset
