@@ -329,7 +329,8 @@ def run_gpu_arm(args, rank, world):
 
     # ---- timed region: resident
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if rank == 0:  # only rank 0's samples go into the line; N nvidia-smi pollers would only add host noise
+        sampler.start()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     t_c, t_d, t_g, prof_c, prof_d = [], [], [], [], []
     barrier()
@@ -448,7 +449,8 @@ def run_gpu_arm(args, rank, world):
                "d2h_bytes_per_step": int(nw2.value + il2.value + U), "ms_per_step": e2e_ms,
                "api": "pco_b200_compress_ex + pco_b200_decompress_ex (C-ABI), pinned host buffers"}
     sampler.stop_flag = True
-    sampler.join(timeout=2)
+    if rank == 0:
+        sampler.join(timeout=2)
 
     if rank != 0:
         return
