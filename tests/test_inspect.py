@@ -142,3 +142,26 @@ def test_auto_config_on_the_baseline_data(oracle):
     assert size == len(oracle.simple_compress(nums, oracle.make_config(mode=oracle.MODE_FLOAT_MULT, float_mult_base=0.01, delta=oracle.DELTA_CONSECUTIVE, delta_order=2)))
     classic = len(oracle.simple_compress(nums, oracle.make_config(mode=oracle.MODE_CLASSIC, delta=oracle.DELTA_AUTO)))
     assert classic > 15 * size
+
+
+def test_bit_flips_only_raise_inspect_errors(oracle):
+    """Corrupt input is reported (InspectError) or read as whatever valid file it now is - never an IndexError / ZeroDivisionError."""
+    rng = np.random.default_rng(4)
+    nums = _data(np.float32, 3000, 2)
+    data = oracle.simple_compress(nums, oracle.make_config(mode=oracle.MODE_FLOAT_MULT, float_mult_base=0.01, delta=oracle.DELTA_CONSECUTIVE, delta_order=1, max_page_n=1000))
+    for bit in rng.choice(min(len(data), 400) * 8, size=300, replace=False):  # the metadata-heavy front of the file
+        d = bytearray(data)
+        d[bit // 8] ^= 1 << (bit % 8)
+        try:
+            insp.inspect(bytes(d))
+        except insp.InspectError:
+            pass
+    for name in ("v0_4_0_lookback_delta", "v1_0_0_conv1", "v1_0_0_dict"):
+        base = ASSETS[name]
+        for bit in rng.choice(len(base) * 8, size=150, replace=False):
+            d = bytearray(base)
+            d[bit // 8] ^= 1 << (bit % 8)
+            try:
+                insp.inspect(bytes(d))
+            except insp.InspectError:
+                pass
