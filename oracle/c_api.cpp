@@ -568,6 +568,13 @@ void pco_oracle_kat_choose_float_mode_f64(const double* nums, size_t n, int* kin
   *base = c.base;
   *k = c.k;
 }
+uint16_t pco_oracle_kat_f64_to_f16_bits(double x) { return f64_to_f16_bits(x); }
+void pco_oracle_kat_choose_float_mode_f16(const uint16_t* nums, size_t n, int* kind, double* base, uint32_t* k) {
+  auto c = choose_float_mode<F16>(nums, n);
+  *kind = int(c.kind);
+  *base = c.base;
+  *k = c.k;
+}
 int32_t pco_oracle_kat_float_exponent_f32(float x) { return fl_exponent<float>(x); }
 float pco_oracle_kat_float_exp2_f32(int32_t p) { return fl_exp2<float>(p); }
 

@@ -99,6 +99,8 @@ template <> struct FloatOps<uint16_t> {
   static F mul(F a, F b) { return F16{f32_to_f16_bits(f16_bits_to_f32(a.bits) * f16_bits_to_f32(b.bits))}; }
   static F round_(F a) { return F16{f32_to_f16_bits(std::round(f16_bits_to_f32(a.bits)))}; }
   static F from_uint(uint16_t x) { return F16{f32_to_f16_bits(float(x))}; }
+  static F from_f64(double x);                                                                      // half::f16::from_f64, defined with the mode search
+  static F inv(F a) { return F16{f32_to_f16_bits(1.0f / f16_bits_to_f32(a.bits))}; }               // f16::ONE / a
   static uint16_t to_uint(F x) { return uint16_t(f16_bits_to_f32(x.bits)); }
   static bool lt(F a, F b) { return f16_bits_to_f32(a.bits) < f16_bits_to_f32(b.bits); }
 };
@@ -1233,20 +1235,81 @@ inline bool int_mult_choose_base(const L* ordered_latents, size_t n, L* base) {
 }
 
 
-// ----- ModeSpec::Auto for f32 / f64 (data_types/float.rs:70-98): classic, FloatMult and FloatQuant bid; the best estimate wins ----
-// f16 is not restated here (the half crate's arithmetic would have to be followed op by op through this search).
+// ----- ModeSpec::Auto for floats (data_types/float.rs:70-98): classic, FloatMult and FloatQuant bid; the best estimate wins ----
+// One generic search over the float type.  f16 follows the half crate (2.7.1, Cargo.lock:1353-1356, not under /root/reference): every
+// arithmetic operator widens to f32 and rounds the result back, from_f64 rounds once from the double, round / abs / comparisons as in
+// data_types/float.rs:254-366.
+inline uint16_t f64_to_f16_bits(double d) {  // round-to-nearest-even in one step (finite values; the search never converts NaN)
+  const uint16_t sign = std::signbit(d) ? 0x8000 : 0;
+  const double a = std::fabs(d);
+  if (std::isinf(a)) return uint16_t(sign | 0x7c00);
+  if (a == 0.0) return sign;
+  int ex;
+  std::frexp(a, &ex);
+  int e = ex - 1;  // a in [2^e, 2^(e+1))
+  if (e < -14) return uint16_t(sign | uint16_t(std::nearbyint(std::ldexp(a, 24))));  // subnormal grid of 2^-24; 1024 is the first normal
+  double r = std::nearbyint(std::ldexp(a, 10 - e));                                  // 11 significant bits
+  if (r == 2048.0) { r = 1024.0; e += 1; }
+  if (e > 15) return uint16_t(sign | 0x7c00);
+  return uint16_t(sign | uint16_t((e + 15) << 10) | uint16_t(uint32_t(r) - 1024));
+}
+inline F16 FloatOps<uint16_t>::from_f64(double x) { return F16{f64_to_f16_bits(x)}; }
+inline float f16_f32(F16 x) { return f16_bits_to_f32(x.bits); }
+inline F16 f16_from(float x) { return F16{f32_to_f16_bits(x)}; }
+inline F16 operator+(F16 a, F16 b) { return f16_from(f16_f32(a) + f16_f32(b)); }
+inline F16 operator-(F16 a, F16 b) { return f16_from(f16_f32(a) - f16_f32(b)); }
+inline F16 operator*(F16 a, F16 b) { return f16_from(f16_f32(a) * f16_f32(b)); }
+inline F16 operator/(F16 a, F16 b) { return f16_from(f16_f32(a) / f16_f32(b)); }
+inline F16& operator+=(F16& a, F16 b) { return a = a + b; }
+inline bool operator<(F16 a, F16 b) { return f16_f32(a) < f16_f32(b); }
+inline bool operator<=(F16 a, F16 b) { return f16_f32(a) <= f16_f32(b); }
+inline bool operator>(F16 a, F16 b) { return f16_f32(a) > f16_f32(b); }
+inline bool operator>=(F16 a, F16 b) { return f16_f32(a) >= f16_f32(b); }
+inline bool operator==(F16 a, F16 b) { return f16_f32(a) == f16_f32(b); }
+inline bool operator!=(F16 a, F16 b) { return f16_f32(a) != f16_f32(b); }
+
 template <typename F> struct NativeFloat;
 template <> struct NativeFloat<float> {
   using L = uint32_t;
   static constexpr Bitlen PRECISION_BITS = 23, BITS = 32;
   static constexpr int32_t EXP_OFFSET = 127;
   static float max_for_sampling() { return std::numeric_limits<float>::max() * 0.5f; }  // float.rs:141
+  static float from_f64(double x) { return float(x); }
+  static double to_f64(float x) { return double(x); }
+  static float from_latent_numerical(uint32_t l) { return float(l); }
+  static float round_(float x) { return std::round(x); }
+  static float abs_(float x) { return std::fabs(x); }
+  static float max_(float a, float b) { return std::fmax(a, b); }
+  static float min_(float a, float b) { return std::fmin(a, b); }
+  static bool is_normal(float x) { return std::isnormal(x); }
 };
 template <> struct NativeFloat<double> {
   using L = uint64_t;
   static constexpr Bitlen PRECISION_BITS = 52, BITS = 64;
   static constexpr int32_t EXP_OFFSET = 1023;
   static double max_for_sampling() { return std::numeric_limits<double>::max() * 0.5; }
+  static double from_f64(double x) { return x; }
+  static double to_f64(double x) { return x; }
+  static double from_latent_numerical(uint64_t l) { return double(l); }
+  static double round_(double x) { return std::round(x); }
+  static double abs_(double x) { return std::fabs(x); }
+  static double max_(double a, double b) { return std::fmax(a, b); }
+  static double min_(double a, double b) { return std::fmin(a, b); }
+  static bool is_normal(double x) { return std::isnormal(x); }
+};
+template <> struct NativeFloat<F16> {  // data_types/float.rs:254-366
+  using L = uint16_t;
+  static constexpr Bitlen PRECISION_BITS = 10, BITS = 16;
+  static constexpr int32_t EXP_OFFSET = 15;
+  static F16 max_for_sampling() { return F16{30719}; }
+  static F16 from_f64(double x) { return F16{f64_to_f16_bits(x)}; }
+  static double to_f64(F16 x) { return double(f16_f32(x)); }
+  static F16 from_latent_numerical(uint16_t l) { return f16_from(float(l)); }
+  static F16 round_(F16 x) { return f16_from(std::round(f16_f32(x))); }
+  static F16 abs_(F16 x) { return F16{uint16_t(x.bits & 0x7fff)}; }
+  static F16 max_(F16 a, F16 b) { return f16_from(std::fmax(f16_f32(a), f16_f32(b))); }
+  static F16 min_(F16 a, F16 b) { return f16_from(std::fmin(f16_f32(a), f16_f32(b))); }
+  static bool is_normal(F16 x) { const uint16_t e = x.bits & 0x7c00; return e != 0 && e != 0x7c00; }
 };
 template <typename F> inline typename NativeFloat<F>::L fl_bits(F x) { typename NativeFloat<F>::L b; std::memcpy(&b, &x, sizeof b); return b; }
 template <typename F> inline F fl_from_bits(typename NativeFloat<F>::L b) { F x; std::memcpy(&x, &b, sizeof x); return x; }
@@ -1255,16 +1318,16 @@ template <typename F> inline F fl_exp2(int32_t power) {  // float.rs:158-160 (on
   return fl_from_bits<F>(L(L(int64_t(NativeFloat<F>::EXP_OFFSET + power)) << NativeFloat<F>::PRECISION_BITS));
 }
 template <typename F> inline int32_t fl_exponent(F x) {  // float.rs:183-185
-  return int32_t(fl_bits<F>(std::fabs(x)) >> NativeFloat<F>::PRECISION_BITS) - NativeFloat<F>::EXP_OFFSET;
+  return int32_t(fl_bits<F>(NativeFloat<F>::abs_(x)) >> NativeFloat<F>::PRECISION_BITS) - NativeFloat<F>::EXP_OFFSET;
 }
 template <typename F> inline uint32_t fl_trailing_zeros(F x) {  // float.rs:188-190
   auto b = fl_bits<F>(x);
   if (b == 0) return NativeFloat<F>::BITS;
-  return sizeof(b) == 8 ? uint32_t(__builtin_ctzll(uint64_t(b))) : uint32_t(__builtin_ctz(uint32_t(b)));
+  return sizeof(b) == 8 ? uint32_t(__builtin_ctzll(uint64_t(b))) : uint32_t(__builtin_ctz(uint32_t(b)));  // b != 0, so narrower types are fine
 }
 template <typename L> inline uint32_t lat_leading_zeros(L x) {
   if (x == 0) return 8 * sizeof(L);
-  return sizeof(L) == 8 ? uint32_t(__builtin_clzll(uint64_t(x))) : uint32_t(__builtin_clz(uint32_t(x)));
+  return sizeof(L) == 8 ? uint32_t(__builtin_clzll(uint64_t(x))) : uint32_t(__builtin_clz(uint32_t(x))) - uint32_t(32 - 8 * sizeof(L));
 }
 template <typename F> inline typename NativeFloat<F>::L fl_ordered(F x) { return to_latent_ordered_bits<typename NativeFloat<F>::L>(fl_bits<F>(x), true, false); }
 
@@ -1289,8 +1352,8 @@ inline double est_bits_saved_per_num(std::vector<std::pair<L, double>> items) {
 template <typename F>
 struct FloatMultConfig {  // float_mult.rs:318-336
   F base, inv_base;
-  static FloatMultConfig from_base(F base) { return {base, F(1) / base}; }
-  static FloatMultConfig from_inv_base(F inv_base) { return {F(1) / inv_base, inv_base}; }
+  static FloatMultConfig from_base(F base) { return {base, NativeFloat<F>::from_f64(1.0) / base}; }
+  static FloatMultConfig from_inv_base(F inv_base) { return {NativeFloat<F>::from_f64(1.0) / inv_base, inv_base}; }
 };
 
 const Bitlen FM_REQUIRED_PRECISION_BITS = 6;  // float_mult.rs:78-83
@@ -1309,11 +1372,11 @@ inline bool approx_pair_gcd(F greater, F lesser, F* out) {  // float_mult.rs:102
   struct PairMult { F value, err; };
   const F machine_eps = fl_exp2<F>(-int32_t(NativeFloat<F>::PRECISION_BITS));
   auto rem_assign = [&](PairMult& lhs, const PairMult& rhs) {
-    const F ratio = std::round(lhs.value / rhs.value);
-    lhs.err += ratio * rhs.err + lhs.value * machine_eps;
-    lhs.value = std::fabs(lhs.value - ratio * rhs.value);
+    const F ratio = NativeFloat<F>::round_(lhs.value / rhs.value);
+    lhs.err = lhs.err + (ratio * rhs.err + lhs.value * machine_eps);
+    lhs.value = NativeFloat<F>::abs_(lhs.value - ratio * rhs.value);
   };
-  PairMult p_greater{greater, F(0)}, p_lesser{lesser, F(0)};
+  PairMult p_greater{greater, NativeFloat<F>::from_f64(0.0)}, p_lesser{lesser, NativeFloat<F>::from_f64(0.0)};
   for (;;) {
     const F prev = p_greater.value;
     rem_assign(p_greater, p_lesser);
@@ -1335,7 +1398,7 @@ inline bool choose_config_by_trailing_zeros(const std::vector<F>& sample, FloatM
   size_t count = 0;
   for (F x : sample) {
     const uint32_t tz = fl_trailing_zeros<F>(x);
-    if (x != F(0) && tz >= 5) {  // INTERESTING_TRAILING_ZEROS
+    if (x != NativeFloat<F>::from_f64(0.0) && tz >= 5) {  // INTERESTING_TRAILING_ZEROS
       count++;
       k = std::min(k, calc_power_of_2_divisor(fl_exponent<F>(x), tz));
     }
@@ -1357,7 +1420,7 @@ inline bool choose_config_by_trailing_zeros(const std::vector<F>& sample, FloatM
   L int_base;
   double unused;
   if (!choose_candidate_base<L>(int_sample, &int_base, &unused)) int_base = 1;
-  *out = FloatMultConfig<F>::from_base(F(int_base) * fl_exp2<F>(k));
+  *out = FloatMultConfig<F>::from_base(NativeFloat<F>::from_latent_numerical(int_base) * fl_exp2<F>(k));
   return true;
 }
 
@@ -1366,7 +1429,7 @@ inline bool approx_sample_gcd_euclidean(const std::vector<F>& sample, F* out) { 
   std::vector<F> gcds;
   for (size_t i = 0; i + 1 < sample.size(); i += 2) {
     F g;
-    if (approx_pair_gcd<F>(std::fmax(sample[i], sample[i + 1]), std::fmin(sample[i], sample[i + 1]), &g)) gcds.push_back(g);
+    if (approx_pair_gcd<F>(NativeFloat<F>::max_(sample[i], sample[i + 1]), NativeFloat<F>::min_(sample[i], sample[i + 1]), &g)) gcds.push_back(g);
   }
   const size_t required_pairs_with_common_gcd = 1 + size_t(std::ceil(double(sample.size()) * 0.001));  // REQUIRED_GCD_PAIR_FREQUENCY
   if (gcds.size() < required_pairs_with_common_gcd) return false;
@@ -1374,7 +1437,7 @@ inline bool approx_sample_gcd_euclidean(const std::vector<F>& sample, F* out) { 
   for (double percentile : {0.1, 0.3, 0.5}) {
     const F candidate = gcds[size_t(percentile * double(gcds.size()))];
     size_t similar = 0;
-    for (F g : gcds) similar += std::fabs(g - candidate) < F(0.01) * candidate;
+    for (F g : gcds) similar += NativeFloat<F>::abs_(g - candidate) < NativeFloat<F>::from_f64(0.01) * candidate;
     if (similar >= required_pairs_with_common_gcd) {
       *out = candidate;
       return true;
@@ -1386,14 +1449,14 @@ inline bool approx_sample_gcd_euclidean(const std::vector<F>& sample, F* out) { 
 template <typename F>
 inline F center_sample_base(F base, const std::vector<F>& sample) {  // float_mult.rs:239-259
   const Bitlen P = NativeFloat<F>::PRECISION_BITS;
-  const F inv_base = F(1) / base;
-  F tweak_sum = 0, tweak_weight = 0;
+  const F inv_base = NativeFloat<F>::from_f64(1.0) / base;
+  F tweak_sum = NativeFloat<F>::from_f64(0.0), tweak_weight = NativeFloat<F>::from_f64(0.0);
   for (F x : sample) {
-    const F mult = std::round(x * inv_base);
+    const F mult = NativeFloat<F>::round_(x * inv_base);
     const Bitlen mult_exponent = Bitlen(fl_exponent<F>(mult));  // `as Bitlen`: a negative exponent wraps to a huge value
-    if (mult_exponent < P && mult != F(0)) {
+    if (mult_exponent < P && mult != NativeFloat<F>::from_f64(0.0)) {
       const F overshoot = (mult * base) - x;
-      const F weight = F(double(P - mult_exponent));
+      const F weight = NativeFloat<F>::from_f64(double(P - mult_exponent));
       tweak_sum += weight * (overshoot / mult);
       tweak_weight += weight;
     }
@@ -1403,11 +1466,12 @@ inline F center_sample_base(F base, const std::vector<F>& sample) {  // float_mu
 
 template <typename F>
 inline FloatMultConfig<F> snap_to_int_reciprocal(F base) {  // float_mult.rs:261-275
-  const F inv_base = F(1) / base;
-  const F round_inv_base = std::round(inv_base);
-  const F decimal_inv_base = F(std::pow(10.0, std::round(std::log10(double(inv_base)))));
-  if (std::fabs(inv_base - round_inv_base) < F(0.02)) return FloatMultConfig<F>::from_inv_base(round_inv_base);                 // SNAP_THRESHOLD_ABSOLUTE
-  if (std::fabs(inv_base - decimal_inv_base) / inv_base < F(0.01)) return FloatMultConfig<F>::from_inv_base(decimal_inv_base);  // SNAP_THRESHOLD_DECIMAL_RELATIVE
+  using NF = NativeFloat<F>;
+  const F inv_base = NF::from_f64(1.0) / base;
+  const F round_inv_base = NF::round_(inv_base);
+  const F decimal_inv_base = NF::from_f64(std::pow(10.0, std::round(std::log10(NF::to_f64(inv_base)))));
+  if (NF::abs_(inv_base - round_inv_base) < NF::from_f64(0.02)) return FloatMultConfig<F>::from_inv_base(round_inv_base);                 // SNAP_THRESHOLD_ABSOLUTE
+  if (NF::abs_(inv_base - decimal_inv_base) / inv_base < NF::from_f64(0.01)) return FloatMultConfig<F>::from_inv_base(decimal_inv_base);  // SNAP_THRESHOLD_DECIMAL_RELATIVE
   return FloatMultConfig<F>::from_base(base);
 }
 
@@ -1426,7 +1490,7 @@ inline bool bits_saved_per_num_over_classic(const FloatMultConfig<F>& config, co
   std::vector<std::pair<L, double>> items;
   items.reserve(sample.size());
   for (F x : sample) {
-    const F mult = std::round(x * config.inv_base);
+    const F mult = NativeFloat<F>::round_(x * config.inv_base);
     const L primary = int_float_to_latent<L>(mult);
     const Bitlen mult_exponent = Bitlen(fl_exponent<F>(mult));
     const Bitlen inter_base_bits = P > mult_exponent ? P - mult_exponent : 0;
@@ -1450,7 +1514,7 @@ template <typename F>
 inline bool float_mult_compute_bid(const std::vector<F>& sample, FloatMultConfig<F>* config, double* bits_saved_per_num) {  // float_mult.rs:338-358
   bool found = false;
   for (int which = 0; which < 2; which++) {
-    FloatMultConfig<F> c{F(0), F(0)};
+    FloatMultConfig<F> c{NativeFloat<F>::from_f64(0.0), NativeFloat<F>::from_f64(0.0)};
     double saved = 0.0;
     if (!(which == 0 ? choose_config_by_trailing_zeros<F>(sample, &c) : choose_config_by_euclidean<F>(sample, &c))) continue;
     if (!bits_saved_per_num_over_classic<F>(c, sample, &saved)) continue;
@@ -1516,8 +1580,8 @@ inline bool choose_float_mode_sample(const typename NativeFloat<F>::L* num_bits,
   sample->clear();
   for (size_t i : idx) {
     const F x = fl_from_bits<F>(num_bits[i]);
-    if (std::isnormal(x)) {
-      const F a = std::fabs(x);
+    if (NativeFloat<F>::is_normal(x)) {
+      const F a = NativeFloat<F>::abs_(x);
       if (a <= NativeFloat<F>::max_for_sampling()) sample->push_back(a);
     }
   }
@@ -1534,12 +1598,12 @@ struct FloatModeChoice {
 template <typename F>
 inline FloatModeChoice choose_float_mode_from_sample(const std::vector<F>& sample) {
   FloatModeChoice best;
-  FloatMultConfig<F> c{F(0), F(0)};
+  FloatMultConfig<F> c{NativeFloat<F>::from_f64(0.0), NativeFloat<F>::from_f64(0.0)};
   double saved = 0.0;
   if (float_mult_compute_bid<F>(sample, &c, &saved) && f64_total_order_key(saved) >= f64_total_order_key(best.bits_saved_per_num)) {
     best.kind = ModeKind::FloatMult;
-    best.base = double(c.base);
-    best.inv_base = double(c.inv_base);
+    best.base = NativeFloat<F>::to_f64(c.base);
+    best.inv_base = NativeFloat<F>::to_f64(c.inv_base);
     best.bits_saved_per_num = saved;
   }
   Bitlen k;
@@ -1716,7 +1780,7 @@ inline SplitLatents<L> split_latents(const L* nums, size_t n, uint8_t number_typ
     // data_types/float.rs:82-98
     if constexpr (sizeof(L) == 4) auto_float = choose_float_mode<float>(nums, n);
     else if constexpr (sizeof(L) == 8) auto_float = choose_float_mode<double>(nums, n);
-    else invalid_argument("oracle: ModeSpec::Auto not restated for f16; pass an explicit mode");
+    else if constexpr (sizeof(L) == 2) auto_float = choose_float_mode<F16>(nums, n);
     kind = auto_float.kind == ModeKind::FloatMult ? ModeSpecKind::TryFloatMult : auto_float.kind == ModeKind::FloatQuant ? ModeSpecKind::TryFloatQuant : ModeSpecKind::Classic;
   } else if (kind == ModeSpecKind::Auto) {
     // data_types/unsigned.rs:28-35 (signed.rs:41-43 forwards to it)
@@ -1765,7 +1829,7 @@ inline SplitLatents<L> split_latents(const L* nums, size_t n, uint8_t number_typ
       break;
     }
     case ModeSpecKind::TryFloatMult: {
-      if constexpr (sizeof(L) == 4 || sizeof(L) == 8) {
+      if constexpr (sizeof(L) == 2 || sizeof(L) == 4 || sizeof(L) == 8) {
         using FO = FloatOps<L>;
         mode.kind = ModeKind::FloatMult;
         // Auto carries its own (base, inv_base) pair: snap_to_int_reciprocal may give inv_base = 100 with base = 1/100, where 1/base != 100
@@ -1784,7 +1848,7 @@ inline SplitLatents<L> split_latents(const L* nums, size_t n, uint8_t number_typ
           out.secondary[i] = L(L(a - b) + LatentTraits<L>::MID);
         }
       } else {
-        invalid_argument("oracle: FloatMult encode restated for f32/f64 only");
+        invalid_argument("unable to use float mode for ints");
       }
       break;
     }

@@ -719,7 +719,7 @@ def test_conv1_recovery_cases(oracle):  # pco/src/tests/recovery.rs:454-540
 
 @pytest.mark.parametrize("name,kw", [
     ("v0_0_0_classic", dict(mode="MODE_AUTO", delta="DELTA_NOOP")),               # compatibility.rs:70-82: 2000 i32, 2751-byte page
-    ("v0_3_0_f16", dict(mode="MODE_CLASSIC", delta="DELTA_AUTO")),                # :145-155: 2000 f16 (the asset's Auto mode chose Classic; the f16 search is not restated)
+    ("v0_3_0_f16", dict(mode="MODE_AUTO", delta="DELTA_AUTO")),                   # :145-155: 2000 f16, ChunkConfig::default()
     ("v0_4_0_lookback_delta", dict(mode="MODE_AUTO", delta="DELTA_LOOKBACK")),   # :182-197: lookback choice + encode
     ("v0_4_8_minor_version", dict(mode="MODE_AUTO", delta="DELTA_AUTO")),        # :225-245
     ("v0_3_0_float_quant", dict(mode="MODE_FLOAT_QUANT", float_quant_k=13, delta="DELTA_AUTO")),  # :157-178: two latent vars, 2905-byte page
@@ -744,3 +744,49 @@ def test_older_assets_reencode_to_the_same_bins_and_page(oracle, name, kw):
     assert (ca["mode"], ca["delta_encoding"]) == (cd["mode"], cd["delta_encoding"])
     assert {k: (v["ans_size_log"], v["bins"]) for k, v in ca["latent_var"].items()} == {k: (v["ans_size_log"], v["bins"]) for k, v in cd["latent_var"].items()}
     assert page_a == page_d and len(page_a) > 0
+
+
+def test_f16_arithmetic_and_mode_search(oracle):  # data_types/float.rs:254-366 (half 2.7.1), tests/recovery.rs:360-374, compatibility.rs:145-155
+    L = oracle.lib()
+    L.pco_oracle_kat_f64_to_f16_bits.restype = C.c_uint16
+    L.pco_oracle_kat_f64_to_f16_bits.argtypes = [C.c_double]
+    rng = np.random.default_rng(12)
+    xs = np.concatenate([rng.standard_normal(2000) * 10.0 ** rng.integers(-9, 6, size=2000), [0.0, -0.0, 65504.0, 65519.99, 65520.0, 1e9, -1e9, 2.0**-24, 2.0**-25, 1.5 * 2.0**-25,
+                                                                                         2.0**-14, 2.0**-14 - 2.0**-25, np.inf, -np.inf, 0.1, 100.0, 0.01]])
+    for x in xs:  # numpy converts double -> half directly, rounding once to nearest even
+        with np.errstate(over="ignore"):
+            want = int(np.float64(x).astype(np.float16).view(np.uint16))
+        assert L.pco_oracle_kat_f64_to_f16_bits(float(x)) == want, x
+
+    def mode(nums):
+        a = np.ascontiguousarray(nums, dtype=np.float16)
+        kind, base, k = C.c_int(), C.c_double(), C.c_uint32()
+        L.pco_oracle_kat_choose_float_mode_f16(a.view(np.uint16).ctypes.data_as(C.POINTER(C.c_uint16)), C.c_size_t(a.size), C.byref(kind), C.byref(base), C.byref(k))
+        return ("Classic", "IntMult", "FloatMult", "FloatQuant", "Dict")[kind.value], base.value, k.value
+
+    # the f16 golden asset was written with ChunkConfig::default(): Auto mode settled on Classic there
+    from tests.golden_generators import GENERATORS, load_assets
+
+    assert mode(GENERATORS["v0_3_0_f16"]())[0] == "Classic"
+    assert mode(np.arange(300) % 200)[0] in ("FloatMult", "FloatQuant")  # small integers leave mantissa bits unused: a mult or a quant mode, not Classic
+    # whole files with the default config: round trip, and the asset's page is reproduced from Auto / Auto
+    nums = GENERATORS["v0_3_0_f16"]()
+    data = oracle.simple_compress(nums, oracle.make_config(mode=oracle.MODE_AUTO, delta=oracle.DELTA_AUTO))
+    assert np.array_equal(oracle.simple_decompress(data, np.float16).view(np.uint16), nums.view(np.uint16))
+    from pcodec_b200 import inspect as insp
+
+    def page(buf):
+        c = insp.inspect(buf)["chunk"][0]
+        s0 = c["byte_offset"] + c["meta_size"]
+        return buf[s0:s0 + c["page_size"]]
+
+    assert page(data) == page(load_assets()["v0_3_0_f16"])
+    # test_f16_mult: explicit TryFloatMult(100) on f16
+    nums = np.array([100.1, 299.9, 200.0] * 100, dtype=np.float16)
+    data = oracle.simple_compress(nums, oracle.make_config(mode=oracle.MODE_FLOAT_MULT, float_mult_base=100.0, delta=oracle.DELTA_AUTO))
+    assert insp.inspect(data)["chunk"][0]["mode"] == "FloatMult(100.0)"
+    assert np.array_equal(oracle.simple_decompress(data, np.float16).view(np.uint16), nums.view(np.uint16))
+    for arr in (rng.integers(-500, 500, size=3000) * 0.5, rng.standard_normal(3000), rng.integers(0, 60, size=3000) / 8.0):
+        arr = arr.astype(np.float16)
+        data = oracle.simple_compress(arr, oracle.make_config(mode=oracle.MODE_AUTO, delta=oracle.DELTA_AUTO))
+        assert np.array_equal(oracle.simple_decompress(data, np.float16).view(np.uint16), arr.view(np.uint16))

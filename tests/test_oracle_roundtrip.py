@@ -138,7 +138,7 @@ def _assert_recovers(oracle, nums, level):  # recovery.rs:49-84: mode in {Classi
               (oracle.DELTA_AUTO, 0)]
     if nums.dtype.itemsize <= 4:
         deltas += [(oracle.DELTA_CONV1, 2), (oracle.DELTA_CONV1, 6)]  # 6: the reference has a specialised decode path for it
-    modes = [oracle.MODE_CLASSIC] + ([oracle.MODE_AUTO] if nums.dtype != np.float16 else [])  # the f16 mode search is not restated
+    modes = [oracle.MODE_CLASSIC, oracle.MODE_AUTO]
     for mode in modes:
         for delta, order in deltas:
             cfg = oracle.make_config(level=level, mode=mode, delta=delta, delta_order=order, enable_8_bit=True)
@@ -167,7 +167,7 @@ def test_recovery_moderate_and_sparse(oracle):  # recovery.rs:116-135, :318-330
     _assert_recovers(oracle, islands, 4)
 
 
-@pytest.mark.parametrize("dtype", [np.uint8, np.uint16, np.uint32, np.uint64, np.int8, np.int16, np.int32, np.int64, np.float32, np.float64])
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16, np.uint32, np.uint64, np.int8, np.int16, np.int32, np.int64, np.float16, np.float32, np.float64])
 def test_recovery_codecs_with_auto_mode(oracle, dtype):  # recovery.rs:137-242: every type at several levels, extremes included
     dt = np.dtype(dtype)
     if dt.kind == "f":
