@@ -578,6 +578,7 @@ void pco_oracle_kat_choose_float_mode_f16(const uint16_t* nums, size_t n, int* k
 int32_t pco_oracle_kat_float_exponent_f32(float x) { return fl_exponent<float>(x); }
 float pco_oracle_kat_float_exp2_f32(int32_t p) { return fl_exp2<float>(p); }
 
+void pco_oracle_kat_dict_tie_order(const uint64_t* values, size_t n) { dict_tie_order().assign(values, values + n); }
 void pco_oracle_kat_conv1_v1_0_0_parameters(int on) { conv1_v1_0_0_parameters() = on != 0; }
 // pco/src/delta/conv1.rs unit tests (:503-583): matrices are row-major here (h x w), column-major inside
 void pco_oracle_kat_conv_autocov_mats(const double* v, size_t n, size_t order, double regularization, double* xtx_colmajor, double* xty) {

@@ -1789,7 +1789,7 @@ inline SplitLatents<L> split_latents(const L* nums, size_t n, uint8_t number_typ
     kind = int_mult_choose_base<L>(ordered.data(), n, &auto_base) ? ModeSpecKind::TryIntMult : ModeSpecKind::Classic;
   }
   const bool is_auto = config.mode_kind == ModeSpecKind::Auto;
-  if (kind == ModeSpecKind::TryDict) invalid_argument("oracle: Dict encode not restated");
+  if (kind == ModeSpecKind::TryDict) invalid_argument("oracle: Dict mode is encoded by simple_compress (its latents are u32 indices); the wrapped handle does not carry it");
   if (isf && kind == ModeSpecKind::TryIntMult) invalid_argument("unable to use int mult mode on floats");
   if (!isf && (kind == ModeSpecKind::TryFloatMult || kind == ModeSpecKind::TryFloatQuant)) invalid_argument("unable to use float mode for ints");
   out.primary.resize(n);
@@ -1859,6 +1859,38 @@ inline SplitLatents<L> split_latents(const L* nums, size_t n, uint8_t number_typ
 }
 
 // chunk_compressor.rs:396-500 ChunkCompressor::new (+ fallback_chunk_compressor)
+// chunk_compressor.rs:400-436 fallback_chunk_compressor: Classic, NoOp, one bin {weight 1, lower 0, offset_bits L::BITS}
+template <typename L>
+inline std::unique_ptr<ChunkCompressor<L>> fallback_chunk_compressor(const L* nums, size_t n, uint8_t number_type, const ChunkConfig& config,
+                                                                     const std::vector<size_t>& page_ns) {
+  ChunkConfig cfg = config;
+  cfg.mode_kind = ModeSpecKind::Classic;
+  Mode classic;
+  SplitLatents<L> split = split_latents<L>(nums, n, number_type, cfg, &classic);
+  std::unique_ptr<ChunkCompressor<L>> cc(new ChunkCompressor<L>());
+  cc->number_type = number_type;
+  cc->page_ns = page_ns;
+  cc->meta.number_bits = sizeof(L) * 8;
+  cc->meta.primary.latent_bits = sizeof(L) * 8;
+  cc->meta.primary.ans_size_log = 0;
+  cc->meta.primary.bins = {Bin{1, 0, Bitlen(sizeof(L) * 8)}};
+  size_t s = 0;
+  for (size_t page_n : page_ns) {
+    PageInfoVar<L> pi;
+    pi.start = s;
+    pi.end = s + page_n;
+    cc->pi_primary.push_back(pi);
+    s += page_n;
+  }
+  TrainedBins<L> trained;
+  trained.infos = {BinCompressionInfo<L>{1, 0, LatentTraits<L>::MAX, Bitlen(sizeof(L) * 8), 0}};
+  trained.ans_size_log = 0;
+  trained.counts = {Weight(n)};
+  cc->counts_primary = trained.counts;
+  cc->vc_primary.reset(new VarCompressor<L>(trained, cc->meta.primary, std::move(split.primary)));
+  return cc;
+}
+
 template <typename L>
 inline std::unique_ptr<ChunkCompressor<L>> new_chunk_compressor(const L* nums, size_t n, uint8_t number_type, const ChunkConfig& config) {
   validate_config(config, sizeof(L) * 8);
@@ -1870,35 +1902,7 @@ inline std::unique_ptr<ChunkCompressor<L>> new_chunk_compressor(const L* nums, s
   DeltaEncoding delta = choose_delta_encoding<L>(latents, config, unoptimized_bins_log, number_type);
   std::vector<size_t> page_ns = n_per_page(config, n);
   auto candidate = new_candidate<L>(std::move(latents), page_ns, mode, delta, unoptimized_bins_log, number_type);
-  if (candidate->should_fallback(n)) {
-    // fallback_chunk_compressor: Classic, NoOp, one bin {weight 1, lower 0, offset_bits L::BITS}
-    ChunkConfig cfg = config;
-    cfg.mode_kind = ModeSpecKind::Classic;
-    Mode classic;
-    SplitLatents<L> split = split_latents<L>(nums, n, number_type, cfg, &classic);
-    std::unique_ptr<ChunkCompressor<L>> cc(new ChunkCompressor<L>());
-    cc->number_type = number_type;
-    cc->page_ns = page_ns;
-    cc->meta.number_bits = sizeof(L) * 8;
-    cc->meta.primary.latent_bits = sizeof(L) * 8;
-    cc->meta.primary.ans_size_log = 0;
-    cc->meta.primary.bins = {Bin{1, 0, Bitlen(sizeof(L) * 8)}};
-    size_t s = 0;
-    for (size_t page_n : page_ns) {
-      PageInfoVar<L> pi;
-      pi.start = s;
-      pi.end = s + page_n;
-      cc->pi_primary.push_back(pi);
-      s += page_n;
-    }
-    TrainedBins<L> trained;
-    trained.infos = {BinCompressionInfo<L>{1, 0, LatentTraits<L>::MAX, Bitlen(sizeof(L) * 8), 0}};
-    trained.ans_size_log = 0;
-    trained.counts = {Weight(n)};
-    cc->counts_primary = trained.counts;
-    cc->vc_primary.reset(new VarCompressor<L>(trained, cc->meta.primary, std::move(split.primary)));
-    return cc;
-  }
+  if (candidate->should_fallback(n)) return fallback_chunk_compressor<L>(nums, n, number_type, config, page_ns);
   return candidate;
 }
 
@@ -1916,6 +1920,57 @@ inline void write_standalone_chunk(ChunkCompressor<L>& cc, std::vector<uint8_t>&
   cc.write_page(0, dst);
 }
 
+// ModeSpec::TryDict (mode/dict.rs:10-68): the distinct ordered latents by descending count form the dictionary (chunk meta), their u32
+// indices are the primary latents; then everything runs as for any other u32 latent var.  Equal counts come out in HashMap order in
+// the reference (unspecified); here ascending by value, unless a test names the order (dict_tie_order, used to match a golden asset).
+inline std::vector<uint64_t>& dict_tie_order() { static std::vector<uint64_t> order; return order; }
+template <typename L>
+inline void write_standalone_dict_chunk(const L* nums, size_t n, uint8_t number_type, const ChunkConfig& config, std::vector<uint8_t>& dst) {
+  validate_config(config, sizeof(L) * 8);
+  if (n == 0) invalid_argument("cannot compress empty chunk");
+  if (n > MAX_ENTRIES) invalid_argument("count may not exceed 16777216 per chunk");
+  const bool isf = number_type_is_float(number_type), iss = number_type_is_signed(number_type);
+  std::vector<L> ordered(n);
+  for (size_t i = 0; i < n; i++) ordered[i] = to_latent_ordered_bits<L>(nums[i], isf, iss);
+  std::vector<L> uniq = ordered;
+  std::sort(uniq.begin(), uniq.end());
+  std::vector<std::pair<L, uint32_t>> counts;
+  for (size_t i = 0; i < uniq.size();) {
+    size_t j = i;
+    while (j < uniq.size() && uniq[j] == uniq[i]) j++;
+    counts.emplace_back(uniq[i], uint32_t(j - i));
+    i = j;
+  }
+  const std::vector<uint64_t>& pref = dict_tie_order();
+  auto rank = [&](L v) { auto it = std::find(pref.begin(), pref.end(), uint64_t(v)); return size_t(it - pref.begin()); };
+  std::stable_sort(counts.begin(), counts.end(), [&](const std::pair<L, uint32_t>& a, const std::pair<L, uint32_t>& b) {
+    if (a.second != b.second) return a.second > b.second;
+    return rank(a.first) < rank(b.first);  // equal ranks (no preference) keep ascending value order
+  });
+  Mode mode;
+  mode.kind = ModeKind::Dict;
+  for (auto& c : counts) mode.dict.push_back(uint64_t(c.first));
+  if (!mode_is_valid(mode, number_type)) invalid_argument("The chosen mode was invalid for the number type");
+  SplitLatents<uint32_t> split;
+  split.primary.resize(n);
+  std::vector<std::pair<L, uint32_t>> index_of;  // value -> position in the dictionary
+  for (size_t i = 0; i < counts.size(); i++) index_of.emplace_back(counts[i].first, uint32_t(i));
+  std::sort(index_of.begin(), index_of.end());
+  for (size_t i = 0; i < n; i++)
+    split.primary[i] = std::lower_bound(index_of.begin(), index_of.end(), std::make_pair(ordered[i], uint32_t(0)))->second;
+  const Bitlen unoptimized_bins_log = choose_unoptimized_bins_log(config.compression_level, n);
+  const DeltaEncoding delta = choose_delta_encoding<uint32_t>(split, config, unoptimized_bins_log, number_type);
+  const std::vector<size_t> page_ns = n_per_page(config, n);
+  auto cand = new_candidate<uint32_t>(std::move(split), page_ns, mode, delta, unoptimized_bins_log, number_type);
+  cand->meta.number_bits = sizeof(L) * 8;  // the dictionary entries and the size baseline are in the NUMBER's width
+  if (cand->should_fallback(n)) {
+    auto cc = fallback_chunk_compressor<L>(nums, n, number_type, config, page_ns);
+    write_standalone_chunk<L>(*cc, dst);
+  } else {
+    write_standalone_chunk<uint32_t>(*cand, dst);
+  }
+}
+
 // standalone/simple.rs:22-91; `uniform_type` selects the _into flavour (header byte 5)
 template <typename L>
 inline void simple_compress(const L* nums, size_t n, uint8_t number_type, const ChunkConfig& config, bool uniform_type,
@@ -1927,8 +1982,12 @@ inline void simple_compress(const L* nums, size_t n, uint8_t number_type, const 
   for (size_t page_n : chunks) {
     this_cfg.paging_kind = PagingKind::Exact;
     this_cfg.exact_pages = {page_n};
-    auto cc = new_chunk_compressor<L>(nums + start, page_n, number_type, this_cfg);
-    write_standalone_chunk<L>(*cc, dst);
+    if (config.mode_kind == ModeSpecKind::TryDict) {
+      write_standalone_dict_chunk<L>(nums + start, page_n, number_type, this_cfg, dst);
+    } else {
+      auto cc = new_chunk_compressor<L>(nums + start, page_n, number_type, this_cfg);
+      write_standalone_chunk<L>(*cc, dst);
+    }
     start += page_n;
   }
   dst.push_back(MAGIC_TERMINATION_BYTE);

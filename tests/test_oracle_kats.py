@@ -790,3 +790,39 @@ def test_f16_arithmetic_and_mode_search(oracle):  # data_types/float.rs:254-366 
         arr = arr.astype(np.float16)
         data = oracle.simple_compress(arr, oracle.make_config(mode=oracle.MODE_AUTO, delta=oracle.DELTA_AUTO))
         assert np.array_equal(oracle.simple_decompress(data, np.float16).view(np.uint16), arr.view(np.uint16))
+
+
+def test_dict_mode_encode(oracle):  # pco/src/mode/dict.rs:10-68, tests/recovery.rs:426-451, compatibility.rs:247-259
+    from pcodec_b200 import inspect as insp
+    from tests.golden_generators import GENERATORS, load_assets
+
+    # test_dict: 2000 distinct squares, five of each
+    nums = np.repeat(np.arange(2000, dtype=np.int64) ** 2, 5)
+    data = oracle.simple_compress(nums, oracle.make_config(mode=oracle.MODE_DICT, delta=oracle.DELTA_NOOP))
+    c = insp.inspect(data)["chunk"][0]
+    assert c["mode"] == "Dict(2000 values)" and set(c["latent_var"]) == {"primary"} and c["latent_var"]["primary"]["latent_type"] == "U32"
+    assert np.array_equal(oracle.simple_decompress(data, np.int64), nums)
+    # the golden asset: three u64 values x 1000, equally frequent - the dictionary order is whatever the writer's HashMap gave,
+    # so the asset's own order is passed as the tie order; then the whole 664-byte file is reproduced
+    asset, anums = load_assets()["v1_0_0_dict"], GENERATORS["v1_0_0_dict"]()
+    meta, _ = insp.read_chunk_meta(asset, insp.inspect(asset)["chunk"][0]["byte_offset"] + 4, 64)
+    order = (C.c_uint64 * 3)(*meta["mode"]["dict"])
+    L = oracle.lib()
+    try:
+        L.pco_oracle_kat_dict_tie_order(order, C.c_size_t(3))
+        assert oracle.simple_compress(anums, oracle.make_config(mode=oracle.MODE_DICT, delta=oracle.DELTA_NOOP)) == asset
+    finally:
+        L.pco_oracle_kat_dict_tie_order(order, C.c_size_t(0))
+    # other types, deltas on the indices, the fallback for incompressible input, several chunks
+    rng = np.random.default_rng(2)
+    for dtype in (np.uint8, np.int16, np.uint32, np.float32, np.float64):
+        vals = rng.integers(0, 40, size=5000).astype(dtype) * dtype(3)
+        for delta, order_ in ((oracle.DELTA_NOOP, 0), (oracle.DELTA_CONSECUTIVE, 1), (oracle.DELTA_AUTO, 0), (oracle.DELTA_LOOKBACK, 0)):
+            data = oracle.simple_compress(vals, oracle.make_config(mode=oracle.MODE_DICT, delta=delta, delta_order=order_, max_page_n=2000))
+            assert np.array_equal(oracle.simple_decompress(data, dtype).view(np.uint8), vals.view(np.uint8)), (dtype, delta)
+            if np.dtype(dtype).itemsize >= 4:  # narrow types can hit the worst-case size fallback (Classic), which is legitimate
+                assert all(ch["mode"].startswith("Dict(") for ch in insp.inspect(data)["chunk"]), (dtype, delta)
+    noise = rng.integers(0, 1 << 62, size=3000).astype(np.uint64)  # every value distinct: the dictionary costs more than it saves
+    data = oracle.simple_compress(noise, oracle.make_config(mode=oracle.MODE_DICT, delta=oracle.DELTA_NOOP))
+    assert insp.inspect(data)["chunk"][0]["mode"] == "Classic" and len(data) <= oracle.file_size_guarantee(noise.size, np.uint64)
+    assert np.array_equal(oracle.simple_decompress(data, np.uint64), noise)
