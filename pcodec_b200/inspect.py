@@ -277,3 +277,16 @@ def index_chunk_offsets(index):
 
 
 __all__ = ["inspect", "read_chunk_meta", "page_size", "var_summary", "describe_mode", "describe_delta", "index_chunk_offsets", "InspectError"]
+
+
+if __name__ == "__main__":  # python -m pcodec_b200.inspect file.pco  (the summary as JSON; bins left out unless --bins)
+    import json
+    import sys
+
+    with open(sys.argv[1], "rb") as fh:
+        summary = inspect(fh.read())
+    if "--bins" not in sys.argv:
+        for ch in summary["chunk"]:
+            for v in ch["latent_var"].values():
+                v.pop("bins")
+    print(json.dumps(summary, indent=1))
