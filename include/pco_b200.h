@@ -123,7 +123,8 @@ PcoB200Error pco_b200_build_index(const void *compressed, size_t compressed_len,
  * sample of pco/src/sampling.rs:62-103).  Host-only planner logic: needs no device, reads ~n/40 numbers.  out->mode_spec is a
  * PCO_B200_MODE_* value with its parameter in the matching field, ready to be pasted into a PcoB200ChunkConfig; FloatMult also
  * reports the inverse the reference's splitter would multiply by (snapping to 1/100 etc. makes it differ from 1/base in the last bit,
- * which only changes the secondary latents' values, never validity).  f16 always answers Classic. */
+ * which only changes the secondary latents' values, never validity).  f16 is searched in the half crate's arithmetic like the
+ * reference does; a FloatMult answer for f16 is the reference's choice, but the GPU path has no f16 FloatMult kernel (PCO_B200_UNSUPPORTED). */
 typedef struct PcoB200ModeChoice {
   uint32_t mode_spec;
   uint32_t float_quant_k;

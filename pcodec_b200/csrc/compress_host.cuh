@@ -178,7 +178,7 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
       ep.mode = MODE_CLASSIC;
       static const bool search = [] { const char* e = std::getenv("PCOB200_AUTO_MODE_SEARCH"); return e && e[0] == '1'; }();
       const bool multi_page_chunk = (flags & PCO_B200_INTERNAL_SHARED_BINS) && pages.size() > 1;  // shared bins exist for one latent var only
-      if (search && !pages.empty() && !(is_float && lbits == 16) && !multi_page_chunk) {  // f16 stays Classic (no FloatMult kernel for it)
+      if (search && !pages.empty() && !multi_page_chunk) {
         const size_t n0 = size_t(pages[0]);
         std::vector<L> staged;
         const L* first = static_cast<const L*>(nums);
@@ -191,7 +191,10 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
         mode_search::Choice c;
         if constexpr (sizeof(L) == 8) c = is_float ? mode_search::choose_float<double>(first, n0) : mode_search::choose_int<L>(first, n0, nt_is_signed(dtype));
         else if constexpr (sizeof(L) == 4) c = is_float ? mode_search::choose_float<float>(first, n0) : mode_search::choose_int<L>(first, n0, nt_is_signed(dtype));
-        else if (!is_float) c = mode_search::choose_int<L>(first, n0, nt_is_signed(dtype));
+        else if constexpr (sizeof(L) == 2) {
+          c = is_float ? mode_search::choose_float<mode_search::Half>(first, n0) : mode_search::choose_int<L>(first, n0, nt_is_signed(dtype));
+          if (is_float && c.kind == 2) c = mode_search::Choice();  // there is no f16 FloatMult kernel: Classic instead
+        } else c = mode_search::choose_int<L>(first, n0, nt_is_signed(dtype));
         if (c.kind == 1) {
           ep.mode = MODE_INT_MULT;
           ep.mode_base = c.int_base;

@@ -3,7 +3,7 @@
 // reference's, not part of the per-number hot path.
 //   ints   (pco/src/data_types/unsigned.rs:28-35): IntMult(base) when int_mult::choose_base finds one, else Classic
 //   floats (pco/src/data_types/float.rs:70-98):    the best of Classic, FloatMult (trailing-zeros and Euclidean candidates, centred
-//                                                  and snapped) and FloatQuant by estimated bits saved; f16 stays Classic here
+//                                                  and snapped) and FloatQuant by estimated bits saved; f16 in the half crate's arithmetic
 // Sample: pco/src/sampling.rs:62-103 (Floyd's algorithm over Xoroshiro128++ seeded with 0; rand_xoshiro 0.6.0 is a crates.io
 // dependency of the reference, restated from its published algorithm).  Where the reference iterates a std HashMap
 // (mode/int_mult.rs:187-204, sampling.rs:110-141) its order is random per process; keys are visited in ascending order here, so
@@ -178,16 +178,80 @@ inline bool int_mult_base(const std::vector<L>& sample, L* base) {  // :216-230
 }
 
 // ---- floats ---------------------------------------------------------------------------------------------------------------
+// f16 as the reference computes with it (half 2.7.1; data_types/float.rs:254-366): every operator widens to f32 and rounds the result
+// back to nearest-even, from_f64 rounds once from the double
+struct Half { uint16_t bits; };
+inline float half_to_float(Half h) {
+  const int e = (h.bits >> 10) & 0x1f, m = h.bits & 0x3ff;
+  float v = e == 0 ? std::ldexp(float(m), -24) : e == 31 ? (m ? std::numeric_limits<float>::quiet_NaN() : std::numeric_limits<float>::infinity()) : std::ldexp(float(m | 0x400), e - 25);
+  return (h.bits & 0x8000) ? -v : v;
+}
+inline Half half_from_double(double d) {  // one rounding, ties to even (the current rounding mode is round-to-nearest)
+  const uint16_t sign = std::signbit(d) ? 0x8000 : 0;
+  const double a = std::fabs(d);
+  if (std::isnan(a)) return Half{uint16_t(sign | 0x7e00)};
+  if (std::isinf(a)) return Half{uint16_t(sign | 0x7c00)};
+  if (a == 0.0) return Half{sign};
+  int ex;
+  std::frexp(a, &ex);
+  int e = ex - 1;
+  if (e < -14) return Half{uint16_t(sign | uint16_t(std::nearbyint(std::ldexp(a, 24))))};
+  double r = std::nearbyint(std::ldexp(a, 10 - e));
+  if (r == 2048.0) { r = 1024.0; e += 1; }
+  if (e > 15) return Half{uint16_t(sign | 0x7c00)};
+  return Half{uint16_t(sign | uint16_t((e + 15) << 10) | uint16_t(uint32_t(r) - 1024))};
+}
+inline Half operator+(Half a, Half b) { return half_from_double(double(half_to_float(a) + half_to_float(b))); }
+inline Half operator-(Half a, Half b) { return half_from_double(double(half_to_float(a) - half_to_float(b))); }
+inline Half operator*(Half a, Half b) { return half_from_double(double(half_to_float(a) * half_to_float(b))); }
+inline Half operator/(Half a, Half b) { return half_from_double(double(half_to_float(a) / half_to_float(b))); }
+inline bool operator<(Half a, Half b) { return half_to_float(a) < half_to_float(b); }
+inline bool operator<=(Half a, Half b) { return half_to_float(a) <= half_to_float(b); }
+inline bool operator==(Half a, Half b) { return half_to_float(a) == half_to_float(b); }
+inline bool operator!=(Half a, Half b) { return half_to_float(a) != half_to_float(b); }
+
 template <typename F> struct Fl;
 template <> struct Fl<float> {
   using L = uint32_t;
   static constexpr uint32_t P = 23, BITS = 32;
   static constexpr int32_t BIAS = 127;
+  static float of(double x) { return float(x); }
+  static double wide(float x) { return double(x); }
+  static float of_int(uint32_t l) { return float(l); }
+  static float round_(float x) { return std::round(x); }
+  static float abs_(float x) { return std::fabs(x); }
+  static float max_(float a, float b) { return std::fmax(a, b); }
+  static float min_(float a, float b) { return std::fmin(a, b); }
+  static bool normal(float x) { return std::isnormal(x); }
+  static float sample_cap() { return std::numeric_limits<float>::max() * 0.5f; }  // MAX_FOR_SAMPLING
 };
 template <> struct Fl<double> {
   using L = uint64_t;
   static constexpr uint32_t P = 52, BITS = 64;
   static constexpr int32_t BIAS = 1023;
+  static double of(double x) { return x; }
+  static double wide(double x) { return x; }
+  static double of_int(uint64_t l) { return double(l); }
+  static double round_(double x) { return std::round(x); }
+  static double abs_(double x) { return std::fabs(x); }
+  static double max_(double a, double b) { return std::fmax(a, b); }
+  static double min_(double a, double b) { return std::fmin(a, b); }
+  static bool normal(double x) { return std::isnormal(x); }
+  static double sample_cap() { return std::numeric_limits<double>::max() * 0.5; }
+};
+template <> struct Fl<Half> {
+  using L = uint16_t;
+  static constexpr uint32_t P = 10, BITS = 16;
+  static constexpr int32_t BIAS = 15;
+  static Half of(double x) { return half_from_double(x); }
+  static double wide(Half x) { return double(half_to_float(x)); }
+  static Half of_int(uint16_t l) { return half_from_double(double(float(l))); }
+  static Half round_(Half x) { return half_from_double(double(std::round(half_to_float(x)))); }
+  static Half abs_(Half x) { return Half{uint16_t(x.bits & 0x7fff)}; }
+  static Half max_(Half a, Half b) { return half_from_double(double(std::fmax(half_to_float(a), half_to_float(b)))); }
+  static Half min_(Half a, Half b) { return half_from_double(double(std::fmin(half_to_float(a), half_to_float(b)))); }
+  static bool normal(Half x) { const uint16_t e = x.bits & 0x7c00; return e != 0 && e != 0x7c00; }
+  static Half sample_cap() { return Half{30719}; }
 };
 template <typename F> inline typename Fl<F>::L bits_of(F x) { typename Fl<F>::L b; std::memcpy(&b, &x, sizeof b); return b; }
 template <typename F> inline F from_bits(typename Fl<F>::L b) { F x; std::memcpy(&x, &b, sizeof x); return x; }
@@ -195,9 +259,9 @@ template <typename F> inline F pow2(int32_t p) {  // data_types/float.rs:158-160
   using L = typename Fl<F>::L;
   return from_bits<F>(L(L(int64_t(Fl<F>::BIAS + p)) << Fl<F>::P));
 }
-template <typename F> inline int32_t exponent_of(F x) { return int32_t(bits_of<F>(std::fabs(x)) >> Fl<F>::P) - Fl<F>::BIAS; }  // :183-185
+template <typename F> inline int32_t exponent_of(F x) { return int32_t(bits_of<F>(Fl<F>::abs_(x)) >> Fl<F>::P) - Fl<F>::BIAS; }  // :183-185
 template <typename L> inline uint32_t ctz(L x) { return x == 0 ? 8 * sizeof(L) : (sizeof(L) == 8 ? uint32_t(__builtin_ctzll(uint64_t(x))) : uint32_t(__builtin_ctz(uint32_t(x)))); }
-template <typename L> inline uint32_t clz(L x) { return x == 0 ? 8 * sizeof(L) : (sizeof(L) == 8 ? uint32_t(__builtin_clzll(uint64_t(x))) : uint32_t(__builtin_clz(uint32_t(x)))); }
+template <typename L> inline uint32_t clz(L x) { return x == 0 ? 8 * sizeof(L) : (sizeof(L) == 8 ? uint32_t(__builtin_clzll(uint64_t(x))) : uint32_t(__builtin_clz(uint32_t(x))) - uint32_t(32 - 8 * sizeof(L))); }
 template <typename F> inline typename Fl<F>::L ordered(F x) {  // data_types/float.rs:402-411
   using L = typename Fl<F>::L;
   const L b = bits_of<F>(x), mid = L(1) << (Fl<F>::BITS - 1);
@@ -207,25 +271,25 @@ template <typename F> inline typename Fl<F>::L int_float_to_latent(F x) {  // da
   using L = typename Fl<F>::L;
   const L mid = L(1) << (Fl<F>::BITS - 1), b = bits_of<F>(x), abs_bits = L(b & ~mid);
   const L gpi = L(1) << (Fl<F>::P + 1);
-  const F gpi_f = F(gpi), a = from_bits<F>(abs_bits);
-  const L abs_int = a < gpi_f ? L(a) : L(gpi + (abs_bits - bits_of<F>(gpi_f)));
+  const F gpi_f = Fl<F>::of_int(gpi), a = from_bits<F>(abs_bits);
+  const L abs_int = a < gpi_f ? L(Fl<F>::wide(a)) : L(gpi + (abs_bits - bits_of<F>(gpi_f)));
   return (b & mid) ? L(mid - 1 - abs_int) : L(mid + abs_int);
 }
 
 template <typename F> struct MultConfig { F base, inv_base; };
-template <typename F> inline MultConfig<F> from_base(F b) { return {b, F(1) / b}; }
-template <typename F> inline MultConfig<F> from_inv_base(F i) { return {F(1) / i, i}; }
+template <typename F> inline MultConfig<F> from_base(F b) { return {b, Fl<F>::of(1.0) / b}; }
+template <typename F> inline MultConfig<F> from_inv_base(F i) { return {Fl<F>::of(1.0) / i, i}; }
 
 template <typename F> inline bool approx_zero(F small, F big) { return small <= big * pow2<F>(-int32_t(Fl<F>::P - 6)); }  // mode/float_mult.rs:85-92
 template <typename F>
 inline bool pair_gcd(F greater, F lesser, F* out) {  // :102-142: Euclid with an error bound carried along
   if (approx_zero<F>(lesser, greater) || lesser == greater) return false;
   const F eps = pow2<F>(-int32_t(Fl<F>::P));
-  F gv = greater, ge = 0, lv = lesser, le = 0;
+  F gv = greater, ge = Fl<F>::of(0.0), lv = lesser, le = Fl<F>::of(0.0);
   for (;;) {
-    const F prev = gv, ratio = std::round(gv / lv);
-    ge += ratio * le + gv * eps;
-    gv = std::fabs(gv - ratio * lv);
+    const F prev = gv, ratio = Fl<F>::round_(gv / lv);
+    ge = ge + (ratio * le + gv * eps);
+    gv = Fl<F>::abs_(gv - ratio * lv);
     if (gv <= prev * pow2<F>(-16) || gv <= ge) {
       *out = lv;
       return true;
@@ -244,7 +308,7 @@ inline bool config_by_trailing_zeros(const std::vector<F>& sample, MultConfig<F>
   size_t count = 0;
   for (F x : sample) {
     const uint32_t tz = ctz(bits_of<F>(x));
-    if (x != F(0) && tz >= 5) {
+    if (x != Fl<F>::of(0.0) && tz >= 5) {
       count++;
       k = std::min(k, pow2_divisor(exponent_of<F>(x), tz));
     }
@@ -263,7 +327,7 @@ inline bool config_by_trailing_zeros(const std::vector<F>& sample, MultConfig<F>
   L int_base;
   double unused;
   if (!candidate_base<L>(ints, &int_base, &unused)) int_base = 1;
-  *out = from_base<F>(F(int_base) * pow2<F>(k));
+  *out = from_base<F>(Fl<F>::of_int(int_base) * pow2<F>(k));
   return true;
 }
 template <typename F>
@@ -271,7 +335,7 @@ inline bool sample_gcd_euclidean(const std::vector<F>& sample, F* out) {  // :19
   std::vector<F> gcds;
   for (size_t i = 0; i + 1 < sample.size(); i += 2) {
     F g;
-    if (pair_gcd<F>(std::fmax(sample[i], sample[i + 1]), std::fmin(sample[i], sample[i + 1]), &g)) gcds.push_back(g);
+    if (pair_gcd<F>(Fl<F>::max_(sample[i], sample[i + 1]), Fl<F>::min_(sample[i], sample[i + 1]), &g)) gcds.push_back(g);
   }
   const size_t required = 1 + size_t(std::ceil(double(sample.size()) * 0.001));
   if (gcds.size() < required) return false;
@@ -279,7 +343,7 @@ inline bool sample_gcd_euclidean(const std::vector<F>& sample, F* out) {  // :19
   for (double percentile : {0.1, 0.3, 0.5}) {
     const F cand = gcds[size_t(percentile * double(gcds.size()))];
     size_t similar = 0;
-    for (F g : gcds) similar += std::fabs(g - cand) < F(0.01) * cand;
+    for (F g : gcds) similar += Fl<F>::abs_(g - cand) < Fl<F>::of(0.01) * cand;
     if (similar >= required) {
       *out = cand;
       return true;
@@ -289,25 +353,25 @@ inline bool sample_gcd_euclidean(const std::vector<F>& sample, F* out) {  // :19
 }
 template <typename F>
 inline F center_base(F base, const std::vector<F>& sample) {  // :239-259
-  const F inv = F(1) / base;
-  F tweak = 0, weight_sum = 0;
+  const F inv = Fl<F>::of(1.0) / base;
+  F tweak = Fl<F>::of(0.0), weight_sum = Fl<F>::of(0.0);
   for (F x : sample) {
-    const F mult = std::round(x * inv);
+    const F mult = Fl<F>::round_(x * inv);
     const uint32_t me = uint32_t(exponent_of<F>(mult));
-    if (me < Fl<F>::P && mult != F(0)) {
-      const F weight = F(double(Fl<F>::P - me));
-      tweak += weight * (((mult * base) - x) / mult);
-      weight_sum += weight;
+    if (me < Fl<F>::P && mult != Fl<F>::of(0.0)) {
+      const F weight = Fl<F>::of(double(Fl<F>::P - me));
+      tweak = tweak + weight * (((mult * base) - x) / mult);
+      weight_sum = weight_sum + weight;
     }
   }
   return base - tweak / weight_sum;
 }
 template <typename F>
 inline MultConfig<F> snap_to_int_reciprocal(F base) {  // :261-275
-  const F inv = F(1) / base, rounded = std::round(inv);
-  const F decimal = F(std::pow(10.0, std::round(std::log10(double(inv)))));
-  if (std::fabs(inv - rounded) < F(0.02)) return from_inv_base<F>(rounded);
-  if (std::fabs(inv - decimal) / inv < F(0.01)) return from_inv_base<F>(decimal);
+  const F inv = Fl<F>::of(1.0) / base, rounded = Fl<F>::round_(inv);
+  const F decimal = Fl<F>::of(std::pow(10.0, std::round(std::log10(Fl<F>::wide(inv)))));
+  if (Fl<F>::abs_(inv - rounded) < Fl<F>::of(0.02)) return from_inv_base<F>(rounded);
+  if (Fl<F>::abs_(inv - decimal) / inv < Fl<F>::of(0.01)) return from_inv_base<F>(decimal);
   return from_base<F>(base);
 }
 template <typename F>
@@ -316,7 +380,7 @@ inline bool mult_savings(const MultConfig<F>& c, const std::vector<F>& sample, d
   std::vector<std::pair<L, double>> items;
   items.reserve(sample.size());
   for (F x : sample) {
-    const F mult = std::round(x * c.inv_base);
+    const F mult = Fl<F>::round_(x * c.inv_base);
     const uint32_t me = uint32_t(exponent_of<F>(mult));
     const uint32_t inter_base_bits = Fl<F>::P > me ? Fl<F>::P - me : 0;
     const L approx = ordered<F>(mult * c.base), exact = ordered<F>(x);
@@ -333,7 +397,7 @@ template <typename F>
 inline bool float_mult_bid(const std::vector<F>& sample, MultConfig<F>* config, double* saved) {  // :338-358
   bool found = false;
   for (int which = 0; which < 2; which++) {
-    MultConfig<F> c{F(0), F(0)};
+    MultConfig<F> c{Fl<F>::of(0.0), Fl<F>::of(0.0)};
     double s = 0.0;
     bool ok = which == 0 ? config_by_trailing_zeros<F>(sample, &c) : false;
     if (which == 1) {
@@ -382,17 +446,17 @@ inline Choice choose_float(const typename Fl<F>::L* num_bits, size_t n) {
   std::vector<F> sample;
   for (size_t i : sample_positions(n)) {  // data_types/float.rs:70-80: normal, not huge, by magnitude
     const F x = from_bits<F>(num_bits[i]);
-    if (std::isnormal(x) && std::fabs(x) <= std::numeric_limits<F>::max() * F(0.5)) sample.push_back(std::fabs(x));
+    if (Fl<F>::normal(x) && Fl<F>::abs_(x) <= Fl<F>::sample_cap()) sample.push_back(Fl<F>::abs_(x));
   }
   if (sample.size() < MIN_SAMPLE) return best;
-  MultConfig<F> c{F(0), F(0)};
+  MultConfig<F> c{Fl<F>::of(0.0), Fl<F>::of(0.0)};
   double s = 0.0;
   uint32_t k = 0;
   // bids in the order classic (0 bits saved), float mult, float quant; the last maximum wins (compression_intermediates.rs:79-84)
   if (float_mult_bid<F>(sample, &c, &s) && total_order(s) >= total_order(best.bits_saved_per_num)) {
     best.kind = 2;
-    best.base = double(c.base);
-    best.inv_base = double(c.inv_base);
+    best.base = Fl<F>::wide(c.base);
+    best.inv_base = Fl<F>::wide(c.inv_base);
     best.bits_saved_per_num = s;
   }
   if (float_quant_bid<F>(sample, &k, &s) && total_order(s) >= total_order(best.bits_saved_per_num)) {

@@ -114,7 +114,6 @@ def test_floats_agree_with_the_oracle(oracle, sa, dtype):
             nums = rng.integers(0, 1 << 20, size=n).astype(dtype)
         _agree(oracle, sa, nums)
     assert sa.choose_mode(np.zeros(1000, dtype=dtype)).kind == 1  # zeros are not normal: nothing to sample
-    assert sa.choose_mode(np.ones(1000, dtype=np.float16)).kind == 1  # f16: always Classic
 
 
 def test_argument_checks(sa):
@@ -129,3 +128,47 @@ def test_argument_checks(sa):
     a = np.zeros(4, dtype=np.uint32)
     assert L.pco_b200_choose_mode(C.c_void_p(a.ctypes.data), C.c_size_t(4), C.c_ubyte(99), C.byref(out)) != 0
     assert L.pco_b200_choose_mode(C.c_void_p(a.ctypes.data), C.c_size_t(4), C.c_ubyte(1), None) != 0
+
+
+def test_f16_agrees_with_the_oracle(oracle, sa):  # the half crate's widen-to-f32 arithmetic, op by op (data_types/float.rs:254-366)
+    import ctypes as C
+
+    def oracle_mode(a):
+        kind, base, k = C.c_int(), C.c_double(), C.c_uint32()
+        oracle.lib().pco_oracle_kat_choose_float_mode_f16(a.view(np.uint16).ctypes.data_as(C.POINTER(C.c_uint16)), C.c_size_t(a.size), C.byref(kind), C.byref(base), C.byref(k))
+        return {0: 1, 2: 2, 3: 3}[kind.value], base.value, k.value
+
+    rng = np.random.default_rng(21)
+    seen = set()
+    for trial in range(120):
+        n = int(rng.choice([10, 64, 300, 5000, 1 << 15]))
+        pick = trial % 6
+        if pick == 0:
+            nums = rng.integers(-300, 300, size=n) * float(rng.choice([0.5, 0.25, 1.0, 2.0, 0.125, 3.0]))
+        elif pick == 1:
+            nums = rng.integers(0, 60, size=n) / 8.0
+        elif pick == 2:
+            nums = rng.standard_normal(n)
+        elif pick == 3:
+            k = int(rng.integers(1, 9))
+            nums = ((rng.standard_normal(n).astype(np.float16).view(np.uint16) >> np.uint16(k)) << np.uint16(k)).view(np.float16)
+        elif pick == 4:
+            nums = rng.integers(0, 2000, size=n).astype(np.float64)
+        else:
+            nums = np.round(rng.standard_normal(n) * 20.0, 1)
+        a = np.ascontiguousarray(nums, dtype=np.float16)
+        if pick == 5:
+            a[::13] = np.inf
+            a[3::31] = np.nan
+        got = sa.choose_mode(a)
+        want = oracle_mode(a)
+        assert got.kind == want[0], (trial, got.kind, want)
+        if want[0] == 2:
+            assert got.base == want[1]
+        if want[0] == 3:
+            assert got.k == want[2]
+        seen.add(want[0])
+    assert seen == {1, 2, 3}  # all three outcomes occurred
+    from tests.golden_generators import GENERATORS
+
+    assert sa.choose_mode(GENERATORS["v0_3_0_f16"]()).kind == 1  # the f16 golden asset: its Auto config resolved to Classic
