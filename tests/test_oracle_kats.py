@@ -826,3 +826,14 @@ def test_dict_mode_encode(oracle):  # pco/src/mode/dict.rs:10-68, tests/recovery
     data = oracle.simple_compress(noise, oracle.make_config(mode=oracle.MODE_DICT, delta=oracle.DELTA_NOOP))
     assert insp.inspect(data)["chunk"][0]["mode"] == "Classic" and len(data) <= oracle.file_size_guarantee(noise.size, np.uint64)
     assert np.array_equal(oracle.simple_decompress(data, np.uint64), noise)
+
+
+def test_minimal_file_of_the_reference_docs(oracle):  # pco/src/standalone/decompressor.rs:45: "the minimal .pco file"
+    from pcodec_b200 import inspect as insp
+
+    minimal = bytes([112, 99, 111, 33, 0, 0])
+    assert oracle.simple_decompress(minimal, np.int64).size == 0
+    dst = np.zeros(256, dtype=np.int64)
+    assert oracle.simple_decompress_into(minimal, dst) == (0, True)
+    s = insp.inspect(minimal)
+    assert (s["n"], s["n_chunks"], s["compressed"]["total_size"], s["compressed"]["unknown_trailing_bytes"]) == (0, 0, 6, 0)
