@@ -12,7 +12,7 @@ import sys
 
 import pytest
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("PCOB200_RUN_UNVALIDATED") != "1", reason="opt-in wiring, not yet validated on a GPU box")]
+pytestmark = pytest.mark.gpu
 
 CHILD = r"""
 import sys

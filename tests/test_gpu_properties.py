@@ -2,10 +2,7 @@
 order, level and paging, the GPU writes the oracle's bytes and decodes them back bit for bit; anything the path refuses is refused as
 Unsupported, never mis-encoded.  Same generators as tests/test_oracle_properties.py.
 
-Written after round 1's GPU budget was spent: runs only with PCOB200_RUN_UNVALIDATED=1 until it has passed on a B200 once
-(profiles/tools/r02_first_call.sh), then the gate goes away."""
-import os
-
+First run on a B200 in round 2 (profiles/r02_a_unvalidated_tests.txt: passed), un-gated since."""
 import numpy as np
 import pytest
 from hypothesis import HealthCheck, given, settings
@@ -14,7 +11,7 @@ from hypothesis import strategies as st
 from tests.golden_generators import bits_view
 from tests.test_oracle_properties import arrays
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("PCOB200_RUN_UNVALIDATED") != "1", reason="not yet validated on a GPU box")]
+pytestmark = pytest.mark.gpu
 
 
 @st.composite
