@@ -119,6 +119,7 @@ __host__ __device__ inline uint64_t scratch_rows_total(uint64_t out_len, uint32_
 // by decode_kernel<L, 1>), 3 / 4 = decode_narrow_kernel (decode_narrow.cuh) with delta order 0 / 1.
 // ---------------------------------------------------------------------------
 constexpr uint32_t CLS_NARROW0 = 3, CLS_NARROW1 = 4;
+constexpr uint32_t CLS_DONE = 0x80;  // fused_narrow_kernel (decode_fused.cuh) has finished the chunk: the two-kernel path skips it
 constexpr uint32_t NARROW_MAX_OB = 15, NARROW_LOW_BITS = 16;
 
 struct NarrowInfo {   // one per chunk, in HBM scratch; only written for chunks of a narrow class
@@ -807,8 +808,9 @@ struct SymWalkSmem {
 };
 
 __global__ void __launch_bounds__(SW_THREADS) symwalk_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, const uint8_t* __restrict__ index_base,
-                                                              uint64_t out_len, uint8_t* __restrict__ d_syms, uint32_t* __restrict__ d_offs,
-                                                              uint8_t* __restrict__ d_nvars, NarrowInfo* __restrict__ d_narrow) {
+                                                              uint64_t index_len, uint64_t out_len, uint8_t* __restrict__ d_syms, uint32_t* __restrict__ d_offs,
+                                                              uint8_t* __restrict__ d_nvars, NarrowInfo* __restrict__ d_narrow, int classes_preset) {
+  if (classes_preset && (d_nvars[blockIdx.x] & CLS_DONE)) return;  // fused_narrow_kernel has decoded (or refused) this chunk
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SymWalkSmem& sm = *reinterpret_cast<SymWalkSmem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -838,6 +840,8 @@ __global__ void __launch_bounds__(SW_THREADS) symwalk_kernel(FileParams fp, cons
   const uint32_t n_vars = sm.hdr.n_vars;
   const bool need_index = (sm.hdr.var[0].n_bins > 1) || (n_vars > 1 && sm.hdr.var[1].n_bins > 1);
   if (!need_index || task.entries_offset == 0 || !index_base) return;  // trivial vars: section starts are closed-form
+  // a stale or foreign index must not send the walk outside the index buffer (decode_kernel reports it)
+  if (task.entries_offset > index_len || uint64_t(n_vars) * n_batches_of(sm.hdr.n) * sizeof(BatchEntry) > index_len - task.entries_offset) return;
   for (uint32_t v = 0; v < n_vars; v++)
     build_var_tables<false>(src, sm.hdr, v, sm.b.node_plain[v], sm.b.build.bin_lower[v], sm.b.build.bin_ob[v], sm.b.build.bin_weight[v],
                             sm.b.build.bin_cum[v], sm.b.build.sym_of_state[v], sm.b.build.rank_counter[v], &sm.err, false);
@@ -1012,7 +1016,7 @@ __global__ void __launch_bounds__(SW_THREADS) symwalk_kernel(FileParams fp, cons
 // chunk's var count) - one-var chunks then run with the registers of one var and a third CTA per SM.
 template <typename L, int NV>
 __global__ void __launch_bounds__(DEC_THREADS, NV == 1 ? PCOB_DEC_NV1_BLOCKS : 2)
-decode_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, uint32_t* __restrict__ statuses, const uint8_t* __restrict__ index_base,
+decode_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, uint32_t* __restrict__ statuses, const uint8_t* __restrict__ index_base, uint64_t index_len,
               L* __restrict__ out, uint64_t out_len, const Binoms* __restrict__ binoms, const uint8_t* __restrict__ d_syms,
               const uint32_t* __restrict__ d_offs, const uint8_t* __restrict__ d_nvars) {
   if (d_nvars[blockIdx.x] != NV) return;
@@ -1100,8 +1104,9 @@ decode_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, uint32_t* __
   const bool need_index = (sm.hdr.var[0].n_bins > 1) || (n_vars > 1 && sm.hdr.var[1].n_bins > 1);
   const BatchEntry* entries = (task.entries_offset != 0 && index_base)
                                   ? reinterpret_cast<const BatchEntry*>(index_base + task.entries_offset) : nullptr;
-  if (need_index && !entries) {
-    if (tid == 0) statuses[blockIdx.x] = ST_INVALID_ARGUMENT;
+  if (need_index && (!entries || task.entries_offset > index_len ||
+                     uint64_t(n_vars) * nb_total * sizeof(BatchEntry) > index_len - task.entries_offset)) {
+    if (tid == 0) statuses[blockIdx.x] = ST_INVALID_ARGUMENT;  // no index, or one that does not cover this chunk (stale / foreign)
     return;
   }
   // closed-form section sizes when every var is trivial (n_bins <= 1)

@@ -6,6 +6,7 @@
 #include "compress_host.cuh"
 #include "decode_kernels.cuh"
 #include "decode_narrow.cuh"
+#include "decode_fused.cuh"
 #include "host_common.hpp"
 
 namespace pcob200 {
@@ -20,6 +21,8 @@ struct Context {
   Binoms* d_binoms = nullptr;
   int sm_count = 0;
   uint32_t last_decode_chunks = 0;  // chunks of the last decode launch (their class bytes are still in dec_nvars)
+  std::vector<uint8_t> host_cls;    // class bytes of the last fused launch as the kernel reported them (0 = decoded there)
+  bool last_classes_fused = false;  // every chunk of the last launch was served by fused_narrow_kernel
 };
 
 static Context& ctx() {
@@ -83,50 +86,87 @@ struct DecodeOutcome {
   bool terminated = false;
 };
 
-// Launch the fused decode over `n_chunks` IndexChunk records that live on the device.
-static PcoB200Error launch_decode(Context& c, const FileParams& fp, const uint8_t* d_index, uint64_t chunks_offset, uint32_t n_chunks,
+// Launch the decode over `n_chunks` IndexChunk records that live on the device.
+//   1. fused_narrow_kernel (decode_fused.cuh): parses and classifies every chunk and fully decodes the narrow class;
+//   2. only if some chunk is of another class: symwalk_kernel + decode_kernel<L, 1 / 2> for those.
+// PCOB200_FUSED=0 selects the round-1 pair symwalk_kernel + decode_narrow_kernel (kept for A/B measurements).
+static PcoB200Error launch_decode(Context& c, const FileParams& fp, const uint8_t* d_index, uint64_t index_len, uint64_t chunks_offset, uint32_t n_chunks,
                                   void* d_out, uint64_t out_len, cudaStream_t stream) {
   if (n_chunks == 0) return PCO_B200_OK;
   PCOB_CUDA_TRY(c.statuses.reserve(size_t(n_chunks + 1) * sizeof(uint32_t)));
   uint32_t* d_st = c.statuses.as<uint32_t>();
   PCOB_CUDA_TRY(cudaMemsetAsync(d_st, 0xff, size_t(n_chunks) * sizeof(uint32_t), stream));
   const IndexChunk* d_chunks = reinterpret_cast<const IndexChunk*>(d_index + chunks_offset);
-  // scratch between the two kernels: one symbol byte per latent the destination can take, one section start per batch
-  const uint64_t rows = scratch_rows_total(out_len, n_chunks);
-  PCOB_CUDA_TRY(c.dec_syms.reserve(rows * BATCH_N + 64));
-  PCOB_CUDA_TRY(c.dec_offs.reserve(rows * sizeof(uint32_t) + 64));
   PCOB_CUDA_TRY(c.dec_nvars.reserve(size_t(n_chunks) + 64));
-  const bool narrow_ok = nt_bits(fp.dtype) >= 32;  // decode_narrow_kernel serves the 32- and 64-bit number types
-  if (narrow_ok) PCOB_CUDA_TRY(c.dec_narrow.reserve(size_t(n_chunks) * sizeof(NarrowInfo)));
+  static const bool use_fused = [] { const char* e = std::getenv("PCOB200_FUSED"); return !(e && e[0] == '0'); }();
+  const bool narrow_ok = nt_bits(fp.dtype) >= 32;  // the narrow class serves the 32- and 64-bit number types
   static bool attr_set = false;
   if (!attr_set) {
     attr_set = true;
     PCOB_CUDA_TRY(cudaFuncSetAttribute(symwalk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SymWalkSmem)));
     PCOB_CUDA_TRY(cudaFuncSetAttribute(symwalk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    PCOB_CUDA_TRY(cudaFuncSetAttribute(fused_narrow_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem)));
+    PCOB_CUDA_TRY(cudaFuncSetAttribute(fused_narrow_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem)));
+    PCOB_CUDA_TRY(cudaFuncSetAttribute(fused_narrow_kernel<uint64_t>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    PCOB_CUDA_TRY(cudaFuncSetAttribute(fused_narrow_kernel<uint32_t>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
   }
   c.last_decode_chunks = n_chunks;
+  std::vector<uint32_t> st(n_chunks);
+  bool fused_ran = false;
+  if (use_fused && narrow_ok) {
+    fused_ran = true;
+    profiler().begin("fused_narrow_kernel", stream);
+    if (nt_bits(fp.dtype) == 64)
+      fused_narrow_kernel<uint64_t><<<n_chunks, FZ_THREADS, sizeof(FusedSmem), stream>>>(fp, d_chunks, d_index, index_len, d_st, c.dec_nvars.as<uint8_t>(),
+                                                                                         static_cast<uint64_t*>(d_out), out_len);
+    else
+      fused_narrow_kernel<uint32_t><<<n_chunks, FZ_THREADS, sizeof(FusedSmem), stream>>>(fp, d_chunks, d_index, index_len, d_st, c.dec_nvars.as<uint8_t>(),
+                                                                                         static_cast<uint32_t*>(d_out), out_len);
+    profiler().end(stream);
+    PCOB_CUDA_TRY(cudaGetLastError());
+    // statuses and class bytes come back in one round trip; the general kernels only run if some chunk still needs them
+    c.host_cls.resize(n_chunks);
+    PCOB_CUDA_TRY(cudaMemcpyAsync(st.data(), d_st, size_t(n_chunks) * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    PCOB_CUDA_TRY(cudaMemcpyAsync(c.host_cls.data(), c.dec_nvars.p, size_t(n_chunks), cudaMemcpyDeviceToHost, stream));
+    PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
+    bool pending = false;
+    for (uint32_t i = 0; i < n_chunks; i++) {
+      if (!(c.host_cls[i] & CLS_DONE)) { pending = true; continue; }
+      if (st[i] != ST_OK) return status_to_error(st[i], ("chunk " + std::to_string(i)).c_str());
+    }
+    c.last_classes_fused = true;
+    if (!pending) return PCO_B200_OK;
+  }
+  c.last_classes_fused = false;
+  // scratch between the two kernels: one symbol byte per latent the destination can take, one section start per batch
+  const uint64_t rows = scratch_rows_total(out_len, n_chunks);
+  PCOB_CUDA_TRY(c.dec_syms.reserve(rows * BATCH_N + 64));
+  PCOB_CUDA_TRY(c.dec_offs.reserve(rows * sizeof(uint32_t) + 64));
+  const bool old_narrow = narrow_ok && !fused_ran;
+  if (old_narrow) PCOB_CUDA_TRY(c.dec_narrow.reserve(size_t(n_chunks) * sizeof(NarrowInfo)));
   profiler().begin("symwalk_kernel", stream);
-  symwalk_kernel<<<n_chunks, SW_THREADS, sizeof(SymWalkSmem), stream>>>(fp, d_chunks, d_index, out_len, c.dec_syms.as<uint8_t>(), c.dec_offs.as<uint32_t>(),
-                                                                        c.dec_nvars.as<uint8_t>(), narrow_ok ? c.dec_narrow.as<NarrowInfo>() : nullptr);
+  symwalk_kernel<<<n_chunks, SW_THREADS, sizeof(SymWalkSmem), stream>>>(fp, d_chunks, d_index, index_len, out_len, c.dec_syms.as<uint8_t>(), c.dec_offs.as<uint32_t>(),
+                                                                        c.dec_nvars.as<uint8_t>(), old_narrow ? c.dec_narrow.as<NarrowInfo>() : nullptr, fused_ran ? 1 : 0);
   profiler().end(stream);
   profiler().begin("decode_kernel", stream);  // the span covers every decode instantiation (a chunk runs in exactly one)
-  if (nt_bits(fp.dtype) == 64)
-    decode_narrow_kernel<uint64_t><<<n_chunks, NW_THREADS, 0, stream>>>(fp, d_chunks, d_st, static_cast<uint64_t*>(d_out), out_len, c.dec_syms.as<uint8_t>(),
-                                                                      c.dec_offs.as<uint32_t>(), c.dec_nvars.as<uint8_t>(), c.dec_narrow.as<NarrowInfo>());
-  else if (nt_bits(fp.dtype) == 32)
-    decode_narrow_kernel<uint32_t><<<n_chunks, NW_THREADS, 0, stream>>>(fp, d_chunks, d_st, static_cast<uint32_t*>(d_out), out_len, c.dec_syms.as<uint8_t>(),
-                                                                      c.dec_offs.as<uint32_t>(), c.dec_nvars.as<uint8_t>(), c.dec_narrow.as<NarrowInfo>());
+  if (old_narrow) {
+    if (nt_bits(fp.dtype) == 64)
+      decode_narrow_kernel<uint64_t><<<n_chunks, NW_THREADS, 0, stream>>>(fp, d_chunks, d_st, static_cast<uint64_t*>(d_out), out_len, c.dec_syms.as<uint8_t>(),
+                                                                        c.dec_offs.as<uint32_t>(), c.dec_nvars.as<uint8_t>(), c.dec_narrow.as<NarrowInfo>());
+    else
+      decode_narrow_kernel<uint32_t><<<n_chunks, NW_THREADS, 0, stream>>>(fp, d_chunks, d_st, static_cast<uint32_t*>(d_out), out_len, c.dec_syms.as<uint8_t>(),
+                                                                        c.dec_offs.as<uint32_t>(), c.dec_nvars.as<uint8_t>(), c.dec_narrow.as<NarrowInfo>());
+  }
   dispatch_latent(fp.dtype, [&](auto tag) {
     using L = decltype(tag);
-    decode_kernel<L, 1><<<n_chunks, DEC_THREADS, sizeof(DecodeSmem), stream>>>(fp, d_chunks, d_st, d_index, static_cast<L*>(d_out), out_len, c.d_binoms,
+    decode_kernel<L, 1><<<n_chunks, DEC_THREADS, sizeof(DecodeSmem), stream>>>(fp, d_chunks, d_st, d_index, index_len, static_cast<L*>(d_out), out_len, c.d_binoms,
                                                                                 c.dec_syms.as<uint8_t>(), c.dec_offs.as<uint32_t>(), c.dec_nvars.as<uint8_t>());
-    decode_kernel<L, 2><<<n_chunks, DEC_THREADS, sizeof(DecodeSmem), stream>>>(fp, d_chunks, d_st, d_index, static_cast<L*>(d_out), out_len, c.d_binoms,
+    decode_kernel<L, 2><<<n_chunks, DEC_THREADS, sizeof(DecodeSmem), stream>>>(fp, d_chunks, d_st, d_index, index_len, static_cast<L*>(d_out), out_len, c.d_binoms,
                                                                                 c.dec_syms.as<uint8_t>(), c.dec_offs.as<uint32_t>(), c.dec_nvars.as<uint8_t>());
     return 0;
   });
   profiler().end(stream);
   PCOB_CUDA_TRY(cudaGetLastError());
-  std::vector<uint32_t> st(n_chunks);
   PCOB_CUDA_TRY(cudaMemcpyAsync(st.data(), d_st, size_t(n_chunks) * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
   PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
   for (uint32_t i = 0; i < n_chunks; i++)
@@ -186,7 +226,10 @@ static PcoB200Error decompress_core(const void* compressed, size_t compressed_le
 
   // 3a. caller-supplied side index
   if (have_index) {
-    if (ih.magic != INDEX_MAGIC || ih.version != 1 || ih.file_len != compressed_len || ih.chunks_offset + ih.n_chunks * sizeof(IndexChunk) > index_len)
+    // overflow-safe: the chunk table must lie inside the index; per-chunk fields are bounded on the device (entries inside the
+    // index, chunk_offset inside the file, writes inside the destination)
+    if (ih.magic != INDEX_MAGIC || ih.version != 1 || ih.file_len != compressed_len || ih.chunks_offset > index_len ||
+        ih.n_chunks > (index_len - ih.chunks_offset) / sizeof(IndexChunk))
       return fail(PCO_B200_INVALID_ARGUMENT, "side index does not belong to this file");
     const uint8_t* d_idx = static_cast<const uint8_t*>(index);
     if (!idx_dev) {
@@ -201,7 +244,8 @@ static PcoB200Error decompress_core(const void* compressed, size_t compressed_le
       d_out = c.out.p;
     }
     if (ih.n_chunks > 0xffffffffull) return fail(PCO_B200_INVALID_ARGUMENT, "too many chunks");
-    if (PcoB200Error e = launch_decode(c, fp, d_idx, ih.chunks_offset, uint32_t(ih.n_chunks), d_out, dst_len, stream)) return e;
+    // a host destination is staged in c.out, which holds n_emit numbers: that is the kernels' bound, whatever the index claims
+    if (PcoB200Error e = launch_decode(c, fp, d_idx, index_len, ih.chunks_offset, uint32_t(ih.n_chunks), d_out, dst_dev ? uint64_t(dst_len) : n_emit, stream)) return e;
     if (!dst_dev && n_emit) {
       PCOB_CUDA_TRY(cudaMemcpyAsync(dst, d_out, n_emit * elem, cudaMemcpyDeviceToHost, stream));
       PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
@@ -244,7 +288,7 @@ static PcoB200Error decompress_core(const void* compressed, size_t compressed_le
         PCOB_CUDA_TRY(c.out.grow_preserve(round_emit_end * elem + 64, std::min<uint64_t>(out_off, dst_len) * elem, stream));
         d_out = c.out.p;
       }
-      if (PcoB200Error e = launch_decode(c, fp, d_index, chunks_offset, res.n_chunks, d_out, dst_len, stream)) return e;
+      if (PcoB200Error e = launch_decode(c, fp, d_index, entries_begin + entries_bytes, chunks_offset, res.n_chunks, d_out, dst_dev ? uint64_t(dst_len) : round_emit_end, stream)) return e;
     }
     out_off += res.n_total;
     next_byte = res.next_byte;
@@ -612,7 +656,7 @@ int pco_b200_profile_chunk_classes(unsigned* counts8) {
   if (!c.device_ok || c.last_decode_chunks == 0 || !c.dec_nvars.p) return 0;
   std::vector<uint8_t> cls(c.last_decode_chunks);
   if (cudaMemcpy(cls.data(), c.dec_nvars.p, cls.size(), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
-  for (uint8_t k : cls) counts8[k < 8 ? k : 0]++;
+  for (uint8_t k : cls) counts8[(k & 0x7f) < 8 ? (k & 0x7f) : 0]++;
   return int(cls.size());
 }
 // Copies "name=ms;name=ms;..." of the last finished call into buf; returns the number of spans.
@@ -716,7 +760,7 @@ PcoB200Error pco_b200_decompress_chunks(const void* compressed, size_t compresse
     PCOB_CUDA_TRY(c.out.reserve(n_total * elem + 64));
     d_out = c.out.p;
   }
-  PcoB200Error e = launch_decode(c, fp, d_index, chunks_offset, uint32_t(n_chunks), d_out, dst_len, stream);
+  PcoB200Error e = launch_decode(c, fp, d_index, off, chunks_offset, uint32_t(n_chunks), d_out, dst_dev ? uint64_t(dst_len) : n_total, stream);
   profiler().resolve();
   if (e != PCO_B200_OK) return e;
   if (!dst_dev && n_total) {
