@@ -139,6 +139,11 @@ PcoB200Error pco_b200_choose_mode(const void *nums, size_t n, unsigned char dtyp
  * CUDA events on the launching stream; pco_b200_profile_last returns "kernel=milliseconds;..." for the last call. */
 void pco_b200_profile_enable(int on);
 int pco_b200_profile_last(char *buf, size_t cap);
+/* Threading: the library keeps one scratch context per calling host thread (device buffers grown on demand and reused by that
+ * thread's next call), so calls from different threads - each with its own cudaStream_t - run concurrently, e.g. compress of
+ * chunk group g + 1 on one thread while group g decompresses on another (both PCIe directions busy).  A worker thread that is
+ * about to exit returns its device scratch with pco_b200_thread_release(). */
+void pco_b200_thread_release(void);
 /* counts8[k] = chunks of the last decode launch served by decode class k (1, 2: general kernel with 1 / 2 latent vars;
  * 3, 4: narrow kernel, delta order 0 / 1); returns the number of chunks. */
 int pco_b200_profile_chunk_classes(unsigned *counts8);

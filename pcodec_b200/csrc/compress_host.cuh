@@ -23,6 +23,12 @@ constexpr uint32_t PCO_B200_INTERNAL_SHARED_BINS = 1u << 16;
 
 struct CompressScratch {
   DevBuf lat0, lat1, keys_a, keys_b, sym0, sym1, ans0, ans1, ob_sum, ans_sum, entries, plans, chunks, starts, seg, cub_tmp, out, small, index, probes, sample, sample_starts, key16_0, key16_1;
+  bool plan_attr_set = false, union_attr_set = false;
+  void release() {
+    for (DevBuf* b : {&lat0, &lat1, &keys_a, &keys_b, &sym0, &sym1, &ans0, &ans1, &ob_sum, &ans_sum, &entries, &plans, &chunks, &starts, &seg, &cub_tmp, &out, &small,
+                      &index, &probes, &sample, &sample_starts, &key16_0, &key16_1})
+      b->release();
+  }
 };
 
 // pco/src/wrapped/chunk_compressor.rs:362-371
@@ -323,9 +329,8 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
   uint32_t var_range_bits[MAX_VARS] = {64, 64};
   auto front = [&](const EncParams& e, uint32_t tiles, size_t slots, uint32_t (&vrb)[MAX_VARS], const std::vector<uint64_t>& sizes) -> PcoB200Error {
     init_chunks_kernel<<<(n_chunks + 255) / 256, 256, 0, stream>>>(d_chunks, n_chunks);
-    static bool plan_attr_set = false;
-    if (!plan_attr_set) {
-      plan_attr_set = true;
+    if (!S.plan_attr_set) {
+      S.plan_attr_set = true;
       PCOB_CUDA_TRY(cudaFuncSetAttribute(plan_probe_kernel<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(((size_t(1) << PLAN_MAX_COUNT_BITS) + 1) * 4 + 16)));
       PCOB_CUDA_TRY(cudaFuncSetAttribute(split_count_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(size_t(SC_N) * 4)));
@@ -351,9 +356,8 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
       PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
       if (fl[1] == 0 && shared_bins) {
         // pages of one chunk: one histogram over all of them, one plan, copied to every page's slot
-        static bool union_attr_set = false;
-        if (!union_attr_set) {
-          union_attr_set = true;
+        if (!S.union_attr_set) {
+          S.union_attr_set = true;
           PCOB_CUDA_TRY(cudaFuncSetAttribute(union_probe_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(size_t(SC_N) * 4)));
         }
         PCOB_CUDA_TRY(cudaMemsetAsync(d_small, 0, 8, stream));

@@ -7,11 +7,11 @@
 //     (cp.async.bulk + mbarrier transaction count - the TMA engine, no register staging); thread 0 parses the header out of
 //     shared memory, the CTA builds the decoder nodes and the packed bin table and classifies the chunk.  A chunk that is
 //     not of the narrow class only gets its class byte; the host then runs symwalk_kernel + decode_kernel for those.
-//   * ONE walker warp (page_latent_decompressor.rs:89-177): a lane per batch, 32 consecutive batches at a time; it stages the
+//   * FZ_WALKERS walker warps (page_latent_decompressor.rs:89-177): a lane per batch, 32 consecutive batches at a time; a walker stages the
 //     tANS bytes of its lanes with cp.async rows, walks 4 interleaved chains per lane and writes the bin indices into a
-//     shared-memory ring (two buffers of 32 symbol rows), together with the bit position where each batch's offsets
+//     shared-memory ring (FZ_NBUF buffers of 32 symbol rows), together with the bit position where each batch's offsets
 //     section starts.  full/empty mbarriers carry the hand-over.
-//   * SEVEN decoder warps, a warp per batch in batch order (page_latent_decompressor.rs:15-44, delta/consecutive.rs:35-50,
+//   * the other (FZ_DECODERS) warps decode, a warp per batch in batch order (page_latent_decompressor.rs:15-44, delta/consecutive.rs:35-50,
 //     mode/classic.rs:14-24): symbols from the ring, the offsets window by cp.async one batch ahead, fields peeled off
 //     register windows, the order-1 un-delta as one 32-bit scan + the fence-free carry record, 32-byte stores.
 // Compared with symwalk_kernel + decode_narrow_kernel the symbol bytes never leave the SM (no 0.27 GB scratch written and
@@ -22,7 +22,17 @@
 namespace pcob200 {
 
 #ifndef PCOB_FZ_NBUF
-#define PCOB_FZ_NBUF 2
+#define PCOB_FZ_NBUF 3
+#endif
+#ifndef PCOB_FZ_WALKERS
+#define PCOB_FZ_WALKERS 2
+#endif
+// measured on C2 (1024 chunks x 2^18 u64, profiles/r02_c_fused_variants.txt), kernel / decompress call in ms:
+//   1 walker, 2 buffers, rows of 64: 1.010 / 1.068    2 walkers, 3 buffers, rows of 64: 0.676 / 0.753    rows of 128: 0.658 / 0.727
+//   3 walkers (5 decoders): 0.706 / 0.823             2 walkers, 2 buffers: 0.734 / 0.812              rows of 256 (3 CTAs/SM): 0.708 / 0.786
+//   round-1 pair symwalk_kernel + decode_narrow_kernel: 0.751 / 0.823
+#ifndef PCOB_FZ_ROW_SYMS
+#define PCOB_FZ_ROW_SYMS 128
 #endif
 #ifndef PCOB_FZ_NODE_WORDS
 #define PCOB_FZ_NODE_WORDS 2048
@@ -32,14 +42,21 @@ namespace pcob200 {
 #endif
 constexpr int FZ_THREADS = 256;
 constexpr int FZ_WARPS = FZ_THREADS / 32;
-constexpr int FZ_DECODERS = FZ_WARPS - 1;
-constexpr int FZ_NBUF = PCOB_FZ_NBUF;               // ring buffers of 32 symbol rows
+constexpr int FZ_WALKERS = PCOB_FZ_WALKERS;          // walker warps: walker w takes the groups g = w (mod FZ_WALKERS)
+constexpr int FZ_DECODERS = FZ_WARPS - FZ_WALKERS;
+constexpr int FZ_NBUF = PCOB_FZ_NBUF;               // ring buffers of 32 symbol rows: group g lives in buffer g mod FZ_NBUF
+// a walker lane's stage row: the bytes its next FZ_ROW_SYMS symbols can read (<= 10 bits each + 16 bytes of start alignment + the
+// window's over-read), refilled with 16-byte cp.async from its exact position
+constexpr int FZ_ROW_SYMS = PCOB_FZ_ROW_SYMS;
+constexpr int FZ_ROW_BLOCKS = ((FZ_ROW_SYMS * SMALL_MAX_SIZE_LOG / 8 + 15) / 16 + 2) | 1;  // odd: rows start in different banks
+constexpr int FZ_STAGE_WORDS = 32 * FZ_ROW_BLOCKS * 4;
+static_assert(BATCH_N % FZ_ROW_SYMS == 0, "a batch is a whole number of stage rows");
+static_assert(FZ_NBUF >= 2 && FZ_NBUF >= FZ_WALKERS, "every walker needs a buffer to work on");
 constexpr int FZ_ROW_WORDS = 65;                     // 256 symbol bytes + 1 word: odd stride, a lane per row writes conflict-free
 constexpr int FZ_BUF_WORDS = 32 * FZ_ROW_WORDS;
 constexpr int FZ_NODE_WORDS = PCOB_FZ_NODE_WORDS;    // decoder nodes, replicated when the table is small
 constexpr int FZ_HEAD_BYTES = 4096;                  // bulk-staged head of the chunk: header + <= 256 bins + page meta of one var
 constexpr int FZ_RING = 32;                          // carry-chain slots (> batches in flight)
-static_assert(FZ_NBUF == 2, "ring parities below assume two buffers");
 
 // ---- mbarrier / bulk-copy primitives (shared::cta addresses as 32-bit values) ----
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
@@ -84,7 +101,7 @@ struct FusedSmem {
     } pro;
     struct {
       uint32_t ring[FZ_NBUF][FZ_BUF_WORDS];
-      alignas(16) uint32_t stage[SW_STAGE_WORDS + 16];
+      alignas(16) uint32_t stage[FZ_WALKERS][FZ_STAGE_WORDS + 16];
       alignas(16) uint32_t win[FZ_DECODERS][2][NW_WIN_WORDS];
     } run;
   };
@@ -92,25 +109,25 @@ struct FusedSmem {
 
 // The walker warp: lane k walks batch 32 g + k of group g.
 __device__ __forceinline__ void fused_walker(FusedSmem& sm, const BitSrc& src, uint64_t chunk_bit0, const BatchEntry* __restrict__ entries, uint32_t nb_out,
-                                             uint32_t stored, uint32_t size_log, uint32_t rep_log, int lane) {
+                                             uint32_t stored, uint32_t size_log, uint32_t rep_log, int walker, int lane) {
   const uint64_t max_blk = (src.n_bits == 0 ? 0 : (src.n_bits - 1) >> 6) >> 1;
   const uint32_t node_sa = smem_addr(sm.node + (uint32_t(lane) & ((1u << rep_log) - 1)));  // this lane's copy
   const uint32_t sl = rep_log + 2;                                                           // states are byte offsets into the lane's copy
   const uint32_t smask = (1u << size_log) - 1;
-  const uint32_t stg_sa = smem_addr(sm.run.stage);
-  const uint32_t row_g = stg_sa + uint32_t(lane) * (SW_ROW_BLOCKS * 16);
-  const uint32_t* rowp = sm.run.stage + lane * (SW_ROW_BLOCKS * 4);
+  const uint32_t stg_sa = smem_addr(sm.run.stage[walker]);
+  const uint32_t row_g = stg_sa + uint32_t(lane) * (FZ_ROW_BLOCKS * 16);
+  const uint32_t* rowp = sm.run.stage[walker] + lane * (FZ_ROW_BLOCKS * 4);
   const uint32_t groups = (nb_out + 31) / 32;
   BatchEntry e_nxt;
   e_nxt.bit_pos = 0; e_nxt.st[0] = e_nxt.st[1] = e_nxt.st[2] = e_nxt.st[3] = 0;
-  if (uint32_t(lane) < nb_out) e_nxt = entries[lane];
-  for (uint32_t g = 0; g < groups; g++) {
-    const uint32_t rb = g & 1u;
+  if (uint32_t(walker) * 32 + lane < nb_out) e_nxt = entries[uint32_t(walker) * 32 + lane];
+  for (uint32_t g = walker; g < groups; g += FZ_WALKERS) {
+    const uint32_t rb = g % FZ_NBUF, ph = g / FZ_NBUF;
     const BatchEntry e = e_nxt;
     const uint32_t b = g * 32 + lane;
     const bool mine = b < nb_out;
-    if (b + 32 < nb_out) e_nxt = entries[b + 32];  // the next group's entry is in flight while this group is walked
-    if (g >= uint32_t(FZ_NBUF)) mbar_wait(smem_addr(&sm.empty_bar[rb]), ((g >> 1) - 1) & 1u);
+    if (b + 32 * FZ_WALKERS < nb_out) e_nxt = entries[b + 32 * FZ_WALKERS];  // the walker's next entry is in flight while this group is walked
+    if (ph > 0) mbar_wait(smem_addr(&sm.empty_bar[rb]), (ph - 1) & 1u);  // the decoders have taken group g - FZ_NBUF out of the buffer
     const int cnt = mine ? int(batch_count(stored, b)) : 0;
     uint32_t s0 = min(uint32_t(e.st[0]), smask) << sl, s1 = min(uint32_t(e.st[1]), smask) << sl;
     uint32_t s2 = min(uint32_t(e.st[2]), smask) << sl, s3 = min(uint32_t(e.st[3]), smask) << sl;
@@ -118,11 +135,11 @@ __device__ __forceinline__ void fused_walker(FusedSmem& sm, const BitSrc& src, u
     uint64_t bit = min(chunk_bit0 + e.bit_pos, src.n_bits);
     // word w of a row holds symbols 4w..4w+3; decoder lane l wants words 2l and 2l+1: even words go to slot l, odd ones to 32 + l
     auto slot = [](int i) -> uint32_t { return uint32_t(((i >> 3) + ((i & 4) << 3)) << 2); };  // byte offset of symbol group i (multiple of 4)
-    for (int part = 0; part < BATCH_N / SW_ROW_SYMS; part++) {
+    for (int part = 0; part < BATCH_N / FZ_ROW_SYMS; part++) {
       const uint64_t blk = bit >> 7;
-      if (cnt > part * SW_ROW_SYMS) {
+      if (cnt > part * FZ_ROW_SYMS) {
 #pragma unroll
-        for (uint32_t qd = 0; qd < uint32_t(SW_ROW_BLOCKS); qd++) {
+        for (uint32_t qd = 0; qd < uint32_t(FZ_ROW_BLOCKS); qd++) {
           const void* gp = reinterpret_cast<const ulonglong2*>(src.words) + min(blk + qd, max_blk);
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(row_g + qd * 16), "l"(gp));
         }
@@ -132,10 +149,10 @@ __device__ __forceinline__ void fused_walker(FusedSmem& sm, const BitSrc& src, u
       uint32_t wpos = uint32_t(bit & 127);
       uint32_t w = wpos >> 5;
       uint32_t x0 = lds_u32(row_g + 4 * w), x1 = lds_u32(row_g + 4 * w + 4), x2 = lds_u32(row_g + 4 * w + 8);
-      const int i0 = part * SW_ROW_SYMS;
+      const int i0 = part * FZ_ROW_SYMS;
       if (size_log <= 8) {
 #pragma unroll 4
-        for (int i = i0; i < i0 + SW_ROW_SYMS; i += 4) {
+        for (int i = i0; i < i0 + FZ_ROW_SYMS; i += 4) {
           if (i + 4 <= cnt) {
             const uint32_t n0 = lds_u32(node_sa + s0), n1 = lds_u32(node_sa + s1), n2 = lds_u32(node_sa + s2), n3 = lds_u32(node_sa + s3);
             const uint32_t gw = __funnelshift_r(x0, x1, wpos & 31);
@@ -152,7 +169,7 @@ __device__ __forceinline__ void fused_walker(FusedSmem& sm, const BitSrc& src, u
         }
       } else {
 #pragma unroll 2
-        for (int i = i0; i < i0 + SW_ROW_SYMS; i += 4) {
+        for (int i = i0; i < i0 + FZ_ROW_SYMS; i += 4) {
           if (i + 4 <= cnt) {
             const uint32_t n0 = lds_u32(node_sa + s0), n1 = lds_u32(node_sa + s1), n2 = lds_u32(node_sa + s2), n3 = lds_u32(node_sa + s3);
             const uint32_t r = wpos & 31;
@@ -169,7 +186,7 @@ __device__ __forceinline__ void fused_walker(FusedSmem& sm, const BitSrc& src, u
           }
         }
       }
-      if (cnt > i0 && cnt < i0 + SW_ROW_SYMS && (cnt & 3)) {  // ragged tail of the page's last batch (page_latent_decompressor.rs:144-177)
+      if (cnt > i0 && cnt < i0 + FZ_ROW_SYMS && (cnt & 3)) {  // ragged tail of the page's last batch (page_latent_decompressor.rs:144-177)
         const int i = cnt & ~3;
         uint32_t packed = 0;
         uint32_t sarr[4] = {s0, s1, s2, s3};
@@ -191,7 +208,7 @@ __device__ __forceinline__ void fused_walker(FusedSmem& sm, const BitSrc& src, u
   }
 }
 
-// A decoder warp: batches d, d + 7, ... of the chunk (K = consecutive delta order, 0 or 1).
+// A decoder warp: batches d, d + FZ_DECODERS, ... of the chunk (K = consecutive delta order, 0 or 1).
 template <typename L, int K>
 __device__ __forceinline__ void fused_decoder(FusedSmem& sm, const FileParams& fp, const BitSrc& src, const IndexChunk& task, uint64_t chunk_bit0, L* __restrict__ out,
                                               uint32_t n, uint32_t n_out, int d, int lane) {
@@ -218,7 +235,7 @@ __device__ __forceinline__ void fused_decoder(FusedSmem& sm, const FileParams& f
   };
   // symbols (8 per lane) and section start of batch bb out of the ring; non-blocking variant for the look-ahead
   auto fetch = [&](uint32_t bb, uint32_t& off, uint2& sy, bool blocking) -> bool {
-    const uint32_t g = bb >> 5, rb = g & 1u, parity = (g >> 1) & 1u;
+    const uint32_t g = bb >> 5, rb = g % FZ_NBUF, parity = (g / FZ_NBUF) & 1u;
     const uint32_t bar = smem_addr(&sm.full_bar[rb]);
     if (blocking) mbar_wait(bar, parity);
     else if (!__all_sync(0xffffffffu, mbar_test(bar, parity) ? 1 : 0)) return false;  // every lane acquires the phase itself
@@ -497,14 +514,14 @@ fused_narrow_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, const 
     sm.link[tid][1] = (K == 1 && tid == 0) ? 1u : 0u;
   }
   __syncthreads();
-  // the walker's warp slot rotates with the CTA so that the 4 CTAs of an SM do not all put it on the same scheduler
-  const int walker = int(blockIdx.x & 3u);
-  if (warp == walker) {
+  // the walkers' warp slots rotate with the CTA so that the CTAs of an SM do not all put them on the same schedulers
+  const int role = (warp + 8 - int((blockIdx.x * FZ_WALKERS) & 7u)) & 7;  // 0 .. FZ_WALKERS - 1: walkers, the rest: decoders
+  if (role < FZ_WALKERS) {
     const BatchEntry* entries = reinterpret_cast<const BatchEntry*>(index_base + task.entries_offset);
     const uint32_t rep_log = min(5u, uint32_t(31 - __clz(uint32_t(FZ_NODE_WORDS) >> vh0.ans_size_log)));
-    fused_walker(sm, src, chunk_bit0, entries, nb_out, var_stored_n(n, K), vh0.ans_size_log, rep_log, lane);
+    fused_walker(sm, src, chunk_bit0, entries, nb_out, var_stored_n(n, K), vh0.ans_size_log, rep_log, role, lane);
   } else {
-    const int d = warp < walker ? warp : warp - 1;
+    const int d = role - FZ_WALKERS;
     if (K == 1) fused_decoder<L, 1>(sm, fp, src, task, chunk_bit0, out, n, n_out, d, lane);
     else fused_decoder<L, 0>(sm, fp, src, task, chunk_bit0, out, n, n_out, d, lane);
   }

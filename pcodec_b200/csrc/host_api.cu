@@ -11,8 +11,13 @@
 
 namespace pcob200 {
 
+// One Context per host thread (thread_local): its scratch buffers, events and the last call's profile belong to the calling
+// thread, so calls from different threads run concurrently (e.g. compress of chunk group g + 1 while group g decompresses, each
+// on its own stream) and the entry points are thread-safe the way the reference documents its own (pco_c/src/lib.rs:57-70).
+// The context follows the thread's current device: a cudaSetDevice between calls drops the scratch of the previous device.
 struct Context {
-  std::mutex mu;
+  int device = -1;
+  bool attrs_set = false;
   bool initialized = false;
   bool device_ok = false;
   std::string device_err;
@@ -26,11 +31,30 @@ struct Context {
 };
 
 static Context& ctx() {
-  static Context c;
+  static thread_local Context c;
   return c;
 }
 
+static void release_buffers(Context& c) {
+  for (DevBuf* b : {&c.src, &c.out, &c.index, &c.statuses, &c.misc, &c.dec_syms, &c.dec_offs, &c.dec_nvars, &c.dec_narrow}) b->release();
+  c.enc.release();
+  if (c.d_binoms) cudaFree(c.d_binoms);
+  c.d_binoms = nullptr;
+}
+
 static PcoB200Error ensure_device(Context& c) {
+  if (c.initialized && c.device_ok) {
+    int cur = -1;
+    if (cudaGetDevice(&cur) == cudaSuccess && cur != c.device) {  // the thread moved to another device: start over there
+      const int now = cur;
+      cudaSetDevice(c.device);
+      release_buffers(c);
+      cudaSetDevice(now);
+      c.initialized = false;
+      c.device_ok = false;
+      c.attrs_set = false;
+    }
+  }
   if (!c.initialized) {
     c.initialized = true;
     int n = 0;
@@ -42,13 +66,14 @@ static PcoB200Error ensure_device(Context& c) {
       cudaDeviceProp prop;
       int dev = 0;
       cudaGetDevice(&dev);
+      c.device = dev;
       e = cudaGetDeviceProperties(&prop, dev);
       if (e != cudaSuccess) c.device_err = cudaGetErrorString(e);
       else if (prop.major < 10) c.device_err = std::string("device ") + prop.name + " is not sm_100";
       else {
         c.sm_count = prop.multiProcessorCount;
         // binomials mod 2^64 by Pascal additions
-        static Binoms hb;
+        Binoms hb;
         std::vector<std::vector<uint64_t>> C(257, std::vector<uint64_t>(MAX_ORDER, 0));
         for (int nn = 0; nn <= 256; nn++) {
           C[nn][0] = 1;
@@ -100,9 +125,8 @@ static PcoB200Error launch_decode(Context& c, const FileParams& fp, const uint8_
   PCOB_CUDA_TRY(c.dec_nvars.reserve(size_t(n_chunks) + 64));
   static const bool use_fused = [] { const char* e = std::getenv("PCOB200_FUSED"); return !(e && e[0] == '0'); }();
   const bool narrow_ok = nt_bits(fp.dtype) >= 32;  // the narrow class serves the 32- and 64-bit number types
-  static bool attr_set = false;
-  if (!attr_set) {
-    attr_set = true;
+  if (!c.attrs_set) {
+    c.attrs_set = true;
     PCOB_CUDA_TRY(cudaFuncSetAttribute(symwalk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SymWalkSmem)));
     PCOB_CUDA_TRY(cudaFuncSetAttribute(symwalk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     PCOB_CUDA_TRY(cudaFuncSetAttribute(fused_narrow_kernel<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem)));
@@ -182,7 +206,6 @@ static PcoB200Error decompress_core(const void* compressed, size_t compressed_le
                                     DecodeOutcome* outcome) {
   if (!nt_valid(dtype)) return fail(PCO_B200_INVALID_TYPE, "unknown number type byte: " + std::to_string(dtype));
   Context& c = ctx();
-  std::lock_guard<std::mutex> lock(c.mu);
   if (PcoB200Error e = ensure_device(c)) return e;
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
   const bool src_dev = flags & PCO_B200_SRC_ON_DEVICE, dst_dev = flags & PCO_B200_DST_ON_DEVICE;
@@ -317,7 +340,6 @@ const char* pco_b200_last_error_message(void) { return last_error_ref().c_str();
 
 int pco_b200_device_available(void) {
   Context& c = ctx();
-  std::lock_guard<std::mutex> lock(c.mu);
   return ensure_device(c) == PCO_B200_OK ? 1 : 0;
 }
 
@@ -379,7 +401,6 @@ static PcoB200Error compress_dispatch(const void* nums, size_t n, unsigned char 
     cfg.compression_level = 8;
   }
   Context& c = ctx();
-  std::lock_guard<std::mutex> lock(c.mu);
   if (PcoB200Error e = ensure_device(c)) return e;
   CompressResult res;
   PcoB200Error e = dispatch_latent(dtype, [&](auto tag) {
@@ -646,12 +667,17 @@ PcoB200Error pco_b200_choose_mode(const void* nums, size_t n, unsigned char dtyp
   return PCO_B200_OK;
 }
 
-void pco_b200_profile_enable(int on) { profiler().enabled = on != 0; }
+void pco_b200_profile_enable(int on) { profiler_enabled().store(on != 0); }
+// Frees the calling thread's device scratch (a worker thread calls this before it exits; the buffers are otherwise kept for the
+// thread's next call).
+void pco_b200_thread_release(void) {
+  Context& c = ctx();
+  if (c.initialized && c.device_ok) release_buffers(c);
+}
 // Which decode instantiation served the chunks of the last decode launch: counts[k] = chunks of class k
 // (1, 2: decode_kernel<L, 1 / 2>; 3, 4: decode_narrow_kernel order 0 / 1).  Returns the number of chunks.
 int pco_b200_profile_chunk_classes(unsigned* counts8) {
   Context& c = ctx();
-  std::lock_guard<std::mutex> lock(c.mu);
   for (int i = 0; i < 8; i++) counts8[i] = 0;
   if (!c.device_ok || c.last_decode_chunks == 0 || !c.dec_nvars.p) return 0;
   std::vector<uint8_t> cls(c.last_decode_chunks);
@@ -690,7 +716,6 @@ PcoB200Error pco_b200_decompress_chunks(const void* compressed, size_t compresse
   if (!chunk_offsets || !chunk_ns) return fail(PCO_B200_INVALID_ARGUMENT, "chunk_offsets and chunk_ns are required");
   if (n_chunks > 0x7fffffffull) return fail(PCO_B200_INVALID_ARGUMENT, "too many chunks");
   Context& c = ctx();
-  std::lock_guard<std::mutex> lock(c.mu);
   if (PcoB200Error e = ensure_device(c)) return e;
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
   const bool src_dev = flags & PCO_B200_SRC_ON_DEVICE, dst_dev = flags & PCO_B200_DST_ON_DEVICE;
@@ -775,7 +800,6 @@ PcoB200Error pco_b200_build_index(const void* compressed, size_t compressed_len,
                                   size_t* index_len, uint32_t flags, void* cuda_stream) {
   if (!nt_valid(dtype)) return fail(PCO_B200_INVALID_TYPE, "unknown number type byte");
   Context& c = ctx();
-  std::lock_guard<std::mutex> lock(c.mu);
   if (PcoB200Error e = ensure_device(c)) return e;
   cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
   const bool src_dev = flags & PCO_B200_SRC_ON_DEVICE;

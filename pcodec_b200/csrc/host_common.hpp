@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdint>
 #include <cstring>
 #include <mutex>
@@ -47,13 +48,16 @@ inline PcoB200Error status_to_error(uint32_t st, const char* where) {
 }
 
 // ---- optional per-kernel timing (CUDA events on the launching stream; off by default) ----
+inline std::atomic<bool>& profiler_enabled() {  // process-wide switch; spans and results are per thread
+  static std::atomic<bool> on{false};
+  return on;
+}
 struct Profiler {
-  bool enabled = false;
   struct Span { std::string name; cudaEvent_t e0, e1; };
   std::vector<Span> spans;                              // of the call in flight
   std::vector<std::pair<std::string, float>> last;      // resolved spans of the last finished call
   void begin(const char* name, cudaStream_t s) {
-    if (!enabled) return;
+    if (!profiler_enabled().load(std::memory_order_relaxed)) return;
     Span sp;
     sp.name = name;
     cudaEventCreate(&sp.e0);
@@ -62,11 +66,11 @@ struct Profiler {
     spans.push_back(sp);
   }
   void end(cudaStream_t s) {
-    if (!enabled || spans.empty()) return;
+    if (spans.empty()) return;
     cudaEventRecord(spans.back().e1, s);
   }
   void resolve() {  // call after the stream has been synchronised
-    if (!enabled) return;
+    if (spans.empty() && !profiler_enabled().load(std::memory_order_relaxed)) return;
     last.clear();
     for (auto& sp : spans) {
       float ms = 0.f;
@@ -80,7 +84,7 @@ struct Profiler {
   }
 };
 inline Profiler& profiler() {
-  static Profiler p;
+  static thread_local Profiler p;
   return p;
 }
 
@@ -115,6 +119,11 @@ struct DevBuf {
     p = np;
     cap = want;
     return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
   }
   template <typename T> T* as() const { return static_cast<T*>(p); }
 };
