@@ -148,6 +148,29 @@ void pco_b200_thread_release(void);
  * 3, 4: narrow kernel, delta order 0 / 1); returns the number of chunks. */
 int pco_b200_profile_chunk_classes(unsigned *counts8);
 
+/* ---- sharded writers (no reference counterpart): chunk c of the logical standalone file is compressed on rank
+ * c mod G (PCO_B200_CHUNKS_ONLY); the page gather then leaves the WHOLE file - header | chunk_0 | chunk_1 | ... | 0x00, byte-identical
+ * to a single-GPU / reference file of the same numbers (pco/src/standalone/simple.rs:62-91, compressor.rs:157) - in every rank's file
+ * buffer.  The ranks' GPUs do the exchange themselves: a device-side scan of all ranks' chunk sizes gives every chunk's file offset
+ * and each rank stores its chunks into every rank's buffer over NVLink (peer memory mapped through cudaIpc handles; no host copy,
+ * no size on the host).  One process per GPU; handles are exchanged once by whatever the host uses for rendezvous. */
+/* a device buffer other processes can map, and its 64-byte handle */
+PcoB200Error pco_b200_ipc_alloc(size_t bytes, void **dev_ptr, unsigned char *handle64);
+PcoB200Error pco_b200_ipc_open(const unsigned char *handle64, void **dev_ptr); /* map another rank's buffer (peer access is enabled on demand) */
+PcoB200Error pco_b200_ipc_close(void *dev_ptr);
+PcoB200Error pco_b200_ipc_free(void *dev_ptr);
+/* sizes_dev[i] = bytes of chunk i of a CHUNKS_ONLY compress, from its side index (both on the device; asynchronous on cuda_stream) */
+PcoB200Error pco_b200_chunk_sizes(const void *index_dev, size_t index_len, uint64_t *sizes_dev, size_t n_chunks, void *cuda_stream);
+/* chunks_dev: this rank's chunk bytes back to back (+ 16 readable bytes of slack); all_sizes_dev[r * n_local + i]: bytes of rank r's
+ * i-th chunk = chunk i * world + r of the file (0 where a rank has fewer chunks), e.g. one all-gather of the pco_b200_chunk_sizes
+ * outputs; peer_files[r]: rank r's file buffer as mapped in this process (file_cap bytes each; peer_files[rank] is this rank's own);
+ * file_len_dev: receives the file length; max_ctas bounds the copy kernel's grid (0 = one CTA per SM) so that it can run beside
+ * other work.  Asynchronous on cuda_stream; pco_b200_gather_status waits for it and reports a buffer that was too small. */
+PcoB200Error pco_b200_gather_pages(const void *chunks_dev, const uint64_t *all_sizes_dev, uint32_t world, uint32_t rank, size_t n_local, size_t n_total_numbers,
+                                   unsigned char uniform_type, void *const *peer_files, size_t file_cap, uint64_t *file_len_dev, uint32_t max_ctas,
+                                   void *cuda_stream);
+PcoB200Error pco_b200_gather_status(void *cuda_stream);
+
 /* ---- wrapped format (pco/src/wrapped/: FileCompressor / ChunkCompressor / FileDecompressor / ChunkDecompressor /
  * PageDecompressor), for callers that keep chunk metadata and pages in their own container.  A chunk's PagingSpec may
  * yield several pages; they share the chunk's bins (pco/src/wrapped/chunk_compressor.rs:129-140).  Classic mode with any

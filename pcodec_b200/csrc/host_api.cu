@@ -7,6 +7,7 @@
 #include "decode_kernels.cuh"
 #include "decode_narrow.cuh"
 #include "decode_fused.cuh"
+#include "gather_kernels.cuh"
 #include "host_common.hpp"
 
 namespace pcob200 {
@@ -21,13 +22,14 @@ struct Context {
   bool initialized = false;
   bool device_ok = false;
   std::string device_err;
-  DevBuf src, out, index, statuses, misc, dec_syms, dec_offs, dec_nvars, dec_narrow;
+  DevBuf src, out, index, statuses, misc, dec_syms, dec_offs, dec_nvars, dec_narrow, gather;
   CompressScratch enc;
   Binoms* d_binoms = nullptr;
   int sm_count = 0;
   uint32_t last_decode_chunks = 0;  // chunks of the last decode launch (their class bytes are still in dec_nvars)
   std::vector<uint8_t> host_cls;    // class bytes of the last fused launch as the kernel reported them (0 = decoded there)
-  bool last_classes_fused = false;  // every chunk of the last launch was served by fused_narrow_kernel
+  bool last_classes_fused = false;
+  uint32_t* gather_err = nullptr;   // error word of the last page gather (inside `gather`)  // every chunk of the last launch was served by fused_narrow_kernel
 };
 
 static Context& ctx() {
@@ -36,8 +38,9 @@ static Context& ctx() {
 }
 
 static void release_buffers(Context& c) {
-  for (DevBuf* b : {&c.src, &c.out, &c.index, &c.statuses, &c.misc, &c.dec_syms, &c.dec_offs, &c.dec_nvars, &c.dec_narrow}) b->release();
+  for (DevBuf* b : {&c.src, &c.out, &c.index, &c.statuses, &c.misc, &c.dec_syms, &c.dec_offs, &c.dec_nvars, &c.dec_narrow, &c.gather}) b->release();
   c.enc.release();
+  c.gather_err = nullptr;
   if (c.d_binoms) cudaFree(c.d_binoms);
   c.d_binoms = nullptr;
 }
@@ -853,6 +856,101 @@ PcoB200Error pco_b200_build_index(const void* compressed, size_t compressed_len,
     PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
   }
   if (index_len) *index_len = used;
+  return PCO_B200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Sharded writers: device buffers other ranks can map, and the page gather (gather_kernels.cuh)
+// ---------------------------------------------------------------------------
+PcoB200Error pco_b200_ipc_alloc(size_t bytes, void** dev_ptr, unsigned char* handle64) {
+  if (!dev_ptr || !handle64) return fail(PCO_B200_INVALID_ARGUMENT, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the handle travels as 64 bytes");
+  Context& c = ctx();
+  if (PcoB200Error e = ensure_device(c)) return e;
+  void* p = nullptr;
+  PCOB_CUDA_TRY(cudaMalloc(&p, bytes + 64));
+  cudaIpcMemHandle_t h;
+  cudaError_t ce = cudaIpcGetMemHandle(&h, p);
+  if (ce != cudaSuccess) { cudaFree(p); return cuda_fail(ce, "cudaIpcGetMemHandle"); }
+  std::memcpy(handle64, &h, 64);
+  *dev_ptr = p;
+  return PCO_B200_OK;
+}
+PcoB200Error pco_b200_ipc_open(const unsigned char* handle64, void** dev_ptr) {
+  if (!dev_ptr || !handle64) return fail(PCO_B200_INVALID_ARGUMENT, "null argument");
+  Context& c = ctx();
+  if (PcoB200Error e = ensure_device(c)) return e;
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle64, 64);
+  PCOB_CUDA_TRY(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return PCO_B200_OK;
+}
+PcoB200Error pco_b200_ipc_close(void* dev_ptr) {
+  if (dev_ptr) PCOB_CUDA_TRY(cudaIpcCloseMemHandle(dev_ptr));
+  return PCO_B200_OK;
+}
+PcoB200Error pco_b200_ipc_free(void* dev_ptr) {
+  if (dev_ptr) PCOB_CUDA_TRY(cudaFree(dev_ptr));
+  return PCO_B200_OK;
+}
+
+PcoB200Error pco_b200_chunk_sizes(const void* index_dev, size_t index_len, uint64_t* sizes_dev, size_t n_chunks, void* cuda_stream) {
+  if (n_chunks == 0) return PCO_B200_OK;
+  if (!index_dev || !sizes_dev) return fail(PCO_B200_INVALID_ARGUMENT, "null argument");
+  Context& c = ctx();
+  if (PcoB200Error e = ensure_device(c)) return e;
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  PCOB_CUDA_TRY(c.misc.reserve(256));
+  uint32_t* d_err = c.misc.as<uint32_t>() + 32;
+  PCOB_CUDA_TRY(cudaMemsetAsync(d_err, 0, 4, stream));
+  chunk_sizes_kernel<<<uint32_t(std::min<size_t>((n_chunks + 255) / 256, 1024)), 256, 0, stream>>>(static_cast<const uint8_t*>(index_dev), index_len, sizes_dev, uint32_t(n_chunks), d_err);
+  PCOB_CUDA_TRY(cudaGetLastError());
+  return PCO_B200_OK;  // asynchronous: a malformed index shows up as sizes the gather rejects (file length over capacity) or as d_err in pco_b200_gather_pages
+}
+
+PcoB200Error pco_b200_gather_pages(const void* chunks_dev, const uint64_t* all_sizes_dev, uint32_t world, uint32_t rank, size_t n_local, size_t n_total_numbers,
+                                   unsigned char uniform_type, void* const* peer_files, size_t file_cap, uint64_t* file_len_dev, uint32_t max_ctas, void* cuda_stream) {
+  if (world == 0 || world > uint32_t(GATHER_MAX_WORLD) || rank >= world) return fail(PCO_B200_INVALID_ARGUMENT, "world must be 1..16 and rank < world");
+  if (!chunks_dev || !all_sizes_dev || !peer_files || !file_len_dev) return fail(PCO_B200_INVALID_ARGUMENT, "null argument");
+  if (n_local > 0x7fffffffull) return fail(PCO_B200_INVALID_ARGUMENT, "too many chunks");
+  Context& c = ctx();
+  if (PcoB200Error e = ensure_device(c)) return e;
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  GatherPeers peers;
+  for (uint32_t r = 0; r < uint32_t(GATHER_MAX_WORLD); r++) peers.file[r] = r < world ? static_cast<uint8_t*>(peer_files[r]) : nullptr;
+  for (uint32_t r = 0; r < world; r++)
+    if (!peers.file[r]) return fail(PCO_B200_INVALID_ARGUMENT, "peer file buffer " + std::to_string(r) + " is null");
+  const std::vector<uint8_t> header = make_standalone_header(n_total_numbers, uniform_type);
+  // scratch: [src_off | dst_off] (2 x n_local u64), header bytes, error word; owned by the calling thread's context and reused
+  const size_t off_bytes = 2 * n_local * sizeof(uint64_t);
+  PCOB_CUDA_TRY(c.gather.reserve(off_bytes + 256));
+  uint64_t* d_src_off = c.gather.as<uint64_t>();
+  uint64_t* d_dst_off = d_src_off + n_local;
+  uint8_t* d_header = c.gather.as<uint8_t>() + off_bytes;
+  uint32_t* d_err = reinterpret_cast<uint32_t*>(d_header + 128);
+  PCOB_CUDA_TRY(cudaMemcpyAsync(d_header, header.data(), header.size(), cudaMemcpyHostToDevice, stream));
+  PCOB_CUDA_TRY(cudaMemsetAsync(d_err, 0, 4, stream));
+  c.gather_err = d_err;
+  gather_offsets_kernel<<<1, 1024, 0, stream>>>(all_sizes_dev, world, rank, uint32_t(n_local), header.size(), d_src_off, d_dst_off, file_len_dev);
+  const uint32_t ctas = std::max(1u, max_ctas ? max_ctas : uint32_t(c.sm_count));
+  // (no profiler span here: the gather is meant to run asynchronously beside the caller's next calls, whose span resolution would wait for it)
+  push_pages_kernel<<<ctas, GATHER_THREADS, 0, stream>>>(static_cast<const uint8_t*>(chunks_dev), all_sizes_dev, d_src_off, d_dst_off, file_len_dev, peers, world, rank,
+                                                        uint32_t(n_local), file_cap, d_header, uint32_t(header.size()), d_err);
+  PCOB_CUDA_TRY(cudaGetLastError());
+  return PCO_B200_OK;  // asynchronous on `stream`; pco_b200_gather_status reports a file buffer that was too small
+}
+
+// Blocks until the calling thread's last pco_b200_gather_pages has finished on `cuda_stream` and reports it: PCO_B200_IO when a
+// file buffer was too small for the gathered file, PCO_B200_INVALID_ARGUMENT for a malformed side index.
+PcoB200Error pco_b200_gather_status(void* cuda_stream) {
+  Context& c = ctx();
+  if (!c.gather_err) return PCO_B200_OK;
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  uint32_t st = 0;
+  PCOB_CUDA_TRY(cudaMemcpyAsync(&st, c.gather_err, 4, cudaMemcpyDeviceToHost, stream));
+  PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
+  if (st == ST_INSUFFICIENT_DATA) return fail(PCO_B200_IO, "failed to write whole buffer: a rank's file buffer is smaller than the gathered file");
+  if (st != ST_OK) return status_to_error(st, "the page gather");
   return PCO_B200_OK;
 }
 

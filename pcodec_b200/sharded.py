@@ -116,3 +116,81 @@ def gather_standalone_file(local_bytes, local_sizes, n_total, world, rank, group
         parts.append(g[r, offs[r, j]: offs[r, j + 1]].tobytes())
     parts.append(b"\x00")
     return b"".join(parts)
+
+
+class DevicePageGather:
+    """The page gather done by the GPUs themselves (pcodec_b200/csrc/gather_kernels.cuh; include/pco_b200.h "sharded writers").
+
+    Every rank owns a file buffer in HBM that the other ranks map through cudaIpc handles (exchanged once, here, with
+    all_gather_object); per call the per-chunk byte sizes are all-gathered as a DEVICE tensor (no size visits the host),
+    one scan kernel turns them into file offsets and one copy kernel stores this rank's chunks into every rank's buffer
+    over NVLink at their final positions.  `gather()` is asynchronous on the given stream; `wait()` reports the outcome.
+    One process per GPU (several ranks may also share one GPU: the peer buffers are then ordinary local memory)."""
+
+    def __init__(self, file_cap, world, rank, group=None):
+        import ctypes as C
+
+        import torch.distributed as dist
+
+        from . import _lib
+
+        self.L, self.C = _lib.lib(), C
+        self._check = _lib.check
+        self.world, self.rank, self.group, self.file_cap = world, rank, group, int(file_cap)
+        L = self.L
+        L.pco_b200_gather_pages.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_size_t, C.c_size_t, C.c_ubyte, C.c_void_p, C.c_size_t, C.c_void_p,
+                                            C.c_uint32, C.c_void_p]
+        L.pco_b200_chunk_sizes.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.pco_b200_gather_status.argtypes = [C.c_void_p]
+        ptr, handle = C.c_void_p(), (C.c_ubyte * 64)()
+        self._check(L.pco_b200_ipc_alloc(C.c_size_t(self.file_cap), C.byref(ptr), handle))
+        self.own = ptr.value
+        handles = [None] * world
+        if world > 1:
+            dist.all_gather_object(handles, bytes(handle), group=group)
+        else:
+            handles[0] = bytes(handle)
+        self.peers = (C.c_void_p * world)()
+        self._opened = []
+        for r in range(world):
+            if r == rank:
+                self.peers[r] = self.own
+            else:
+                p = C.c_void_p()
+                self._check(L.pco_b200_ipc_open((C.c_ubyte * 64).from_buffer_copy(handles[r]), C.byref(p)))
+                self.peers[r] = p.value
+                self._opened.append(p.value)
+
+    def gather(self, chunks_ptr, all_sizes_ptr, n_local, n_total_numbers, file_len_ptr, stream_ptr, uniform_type=0, max_ctas=0):
+        """chunks_ptr: this rank's chunk bytes (device); all_sizes_ptr: device u64 [world][n_local]; file_len_ptr: device u64 out."""
+        C = self.C
+        self._check(self.L.pco_b200_gather_pages(C.c_void_p(chunks_ptr), C.c_void_p(all_sizes_ptr), C.c_uint32(self.world), C.c_uint32(self.rank), C.c_size_t(n_local),
+                                                 C.c_size_t(n_total_numbers), C.c_ubyte(uniform_type), C.cast(self.peers, C.c_void_p), C.c_size_t(self.file_cap),
+                                                 C.c_void_p(file_len_ptr), C.c_uint32(max_ctas), C.c_void_p(stream_ptr)))
+
+    def chunk_sizes(self, index_ptr, index_len, sizes_ptr, n_chunks, stream_ptr):
+        C = self.C
+        self._check(self.L.pco_b200_chunk_sizes(C.c_void_p(index_ptr), C.c_size_t(index_len), C.c_void_p(sizes_ptr), C.c_size_t(n_chunks), C.c_void_p(stream_ptr)))
+
+    def wait(self, stream_ptr):
+        self._check(self.L.pco_b200_gather_status(self.C.c_void_p(stream_ptr)))
+
+    def file_tensor(self):
+        """This rank's file buffer as a uint8 torch tensor view (no copy)."""
+        import torch
+
+        class _Holder:
+            pass
+
+        h = _Holder()
+        h.__cuda_array_interface__ = {"shape": (self.file_cap,), "typestr": "|u1", "data": (self.own, False), "version": 2}
+        return torch.as_tensor(h, device="cuda")
+
+    def close(self):
+        """Collective in spirit: call on every rank after a barrier (a peer must not be writing into a freed buffer)."""
+        for p in self._opened:
+            self.L.pco_b200_ipc_close(self.C.c_void_p(p))
+        self._opened = []
+        if self.own:
+            self.L.pco_b200_ipc_free(self.C.c_void_p(self.own))
+            self.own = None
