@@ -4,7 +4,11 @@
 #include <cstdlib>
 #include <cub/device/device_segmented_radix_sort.cuh>
 
+#include <atomic>
 #include <cmath>
+#include <map>
+#include <mutex>
+#include <thread>
 
 #include "encode_kernels.cuh"
 #include "host_common.hpp"
@@ -22,11 +26,11 @@ constexpr uint32_t PCO_B200_INTERNAL_SHARED_BINS = 1u << 16;
 
 
 struct CompressScratch {
-  DevBuf lat0, lat1, keys_a, keys_b, sym0, sym1, ans0, ans1, ob_sum, ans_sum, entries, plans, chunks, starts, seg, cub_tmp, out, small, index, probes, sample, sample_starts, key16_0, key16_1;
+  DevBuf lat0, lat1, keys_a, keys_b, sym0, sym1, ans0, ans1, ob_sum, ans_sum, entries, plans, chunks, starts, seg, cub_tmp, out, small, index, probes, sample, sample_starts, key16_0, key16_1, idx_out;
   bool plan_attr_set = false, union_attr_set = false;
   void release() {
     for (DevBuf* b : {&lat0, &lat1, &keys_a, &keys_b, &sym0, &sym1, &ans0, &ans1, &ob_sum, &ans_sum, &entries, &plans, &chunks, &starts, &seg, &cub_tmp, &out, &small,
-                      &index, &probes, &sample, &sample_starts, &key16_0, &key16_1})
+                      &index, &probes, &sample, &sample_starts, &key16_0, &key16_1, &idx_out})
       b->release();
   }
 };
@@ -82,11 +86,13 @@ __global__ void range_bits_kernel(ChunkEnc* chunks, uint32_t n_chunks, int v, ui
   chunks[c].key_base[v] = a;  // plan_probe_kernel's keys are latent - vmin
 }
 
-// internal entries [(c, v)][batches_per_chunk] -> compact side index
+// internal entries [(c, v)][batches_per_chunk] of one run -> its piece of the compact side index.  chunk_base / elem_base: index of the run's
+// first chunk in the call and element offset of its first number; the file-level header fields are written by the call's last run.
 __global__ void emit_index_kernel(EncParams ep, uint32_t batches_per_chunk, const ChunkEnc* chunks, const BatchEntry* entries, uint8_t* index,
-                                  uint64_t chunks_offset, const uint64_t* entry_offsets, const uint64_t* total_bytes, uint32_t has_terminator) {
+                                  uint64_t chunks_offset, const uint64_t* entry_offsets, const uint64_t* total_bytes, uint32_t has_terminator, uint32_t chunk_base,
+                                  uint64_t elem_base, uint32_t last_run) {
   const uint32_t c = blockIdx.x;
-  if (c == 0 && threadIdx.x == 0) {  // the file size is known on the device first: the host need not wait for it to write the header
+  if (c == 0 && threadIdx.x == 0 && last_run) {  // the file size is known on the device first: the host need not wait for it to write the header
     IndexHeader* ih = reinterpret_cast<IndexHeader*>(index);
     ih->file_len = *total_bytes;
     ih->end_byte = has_terminator ? *total_bytes : 0;
@@ -101,8 +107,8 @@ __global__ void emit_index_kernel(EncParams ep, uint32_t batches_per_chunk, cons
     ic.n = n;
     ic.n_vars = n_vars;
     ic.entries_offset = entry_offsets[c];
-    ic.out_offset = cs;
-    reinterpret_cast<IndexChunk*>(index + chunks_offset)[c] = ic;
+    ic.out_offset = elem_base + cs;
+    reinterpret_cast<IndexChunk*>(index + chunks_offset)[chunk_base + c] = ic;
   }
   BatchEntry* dst = reinterpret_cast<BatchEntry*>(index + entry_offsets[c]);
   for (uint32_t i = threadIdx.x; i < n_vars * nb; i += blockDim.x) {
@@ -111,10 +117,124 @@ __global__ void emit_index_kernel(EncParams ep, uint32_t batches_per_chunk, cons
   }
 }
 
+// several runs: the first writes the standalone header, the last the terminator byte (standalone/compressor.rs:85-105,157-163)
+__global__ void run_edge_kernel(uint8_t* out, uint64_t out_cap, const uint8_t* header, uint32_t header_bytes, const uint64_t* total_bytes, uint32_t footer) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const uint64_t total = *total_bytes;
+    if (total > out_cap) return;
+    for (uint32_t i = 0; i < header_bytes; i++) out[i] = header[i];
+    if (footer) out[total - 1] = 0;
+  }
+}
+
 struct CompressResult {
   uint64_t total_bytes = 0;
   uint64_t index_bytes = 0;
 };
+
+// A chunk's resolved mode: what EncParams carries about it
+struct ModeSel {
+  uint32_t mode = MODE_CLASSIC;
+  uint64_t mode_base = 0, base_bits = 0, inv_base_bits = 0;
+  uint32_t mode_k = 0;
+  bool operator==(const ModeSel& o) const {
+    return mode == o.mode && mode_base == o.mode_base && base_bits == o.base_bits && inv_base_bits == o.inv_base_bits && mode_k == o.mode_k;
+  }
+};
+
+inline void set_float_mult(ModeSel* ms, uint32_t lbits, double base_d, double inv_d) {
+  ms->mode = MODE_FLOAT_MULT;
+  if (lbits == 64) {
+    std::memcpy(&ms->base_bits, &base_d, 8);
+    std::memcpy(&ms->inv_base_bits, &inv_d, 8);
+    ms->mode_base = (ms->base_bits >> 63) ? ~ms->base_bits : (ms->base_bits ^ (uint64_t(1) << 63));
+  } else {
+    const float base = float(base_d), inv = float(inv_d);
+    uint32_t bb, ib;
+    std::memcpy(&bb, &base, 4);
+    std::memcpy(&ib, &inv, 4);
+    ms->base_bits = bb;
+    ms->inv_base_bits = ib;
+    ms->mode_base = (bb >> 31) ? uint32_t(~bb) : (bb ^ 0x80000000u);
+  }
+}
+
+// the numbers of every chunk at the positions choose_mode_sample visits (sampling.rs:73-95): positions depend on the chunk's n only
+template <typename L>
+__global__ void gather_positions_kernel(const L* __restrict__ nums, const uint64_t* __restrict__ chunk_starts, const uint32_t* __restrict__ chunk_ids,
+                                        const uint32_t* __restrict__ pos, uint32_t m, L* __restrict__ out) {
+  const uint32_t c = chunk_ids[blockIdx.x];
+  const L* src = nums + chunk_starts[c];
+  L* dst = out + size_t(blockIdx.x) * m;
+  for (uint32_t j = threadIdx.x; j < m; j += blockDim.x) dst[j] = src[pos[j]];
+}
+
+// the delta sample (sampling.rs:21-60) of every chunk's PRIMARY latents under the chunk's own mode, as unsigned numbers of width L
+struct ModeSelDev { uint32_t mode, mode_k; uint64_t mode_base, base_bits, inv_base_bits; };
+template <typename L>
+__global__ void gather_primary_sample_kernel(const L* __restrict__ nums, const uint64_t* __restrict__ chunk_starts, const uint64_t* __restrict__ sample_starts,
+                                             const ModeSelDev* __restrict__ modes, uint32_t dtype, L* __restrict__ sample) {
+  const uint32_t c = blockIdx.x;
+  const uint64_t cs = chunk_starts[c], n = chunk_starts[c + 1] - cs;
+  const SampleGeom g = delta_sample_geom(n);
+  const uint32_t ns = g.n_groups * g.group_n;
+  L* dst = sample + sample_starts[c];
+  const ModeSelDev ms = modes[c];
+  EncParams ep;
+  ep.dtype = dtype; ep.mode = ms.mode; ep.mode_k = ms.mode_k; ep.mode_base = ms.mode_base; ep.base_bits = ms.base_bits; ep.inv_base_bits = ms.inv_base_bits;
+  const bool is_float = nt_is_float(dtype), is_signed = nt_is_signed(dtype);
+  for (uint32_t i = threadIdx.x; i < ns; i += blockDim.x) {
+    const L x = nums[cs + uint64_t(i / g.group_n) * g.stride + i % g.group_n];
+    L pr, se;
+    switch (ms.mode) {
+      case MODE_INT_MULT: split_one<L, MODE_INT_MULT>(x, ep, is_float, is_signed, pr, se); break;
+      case MODE_FLOAT_MULT: split_one<L, MODE_FLOAT_MULT>(x, ep, is_float, is_signed, pr, se); break;
+      case MODE_FLOAT_QUANT: split_one<L, MODE_FLOAT_QUANT>(x, ep, is_float, is_signed, pr, se); break;
+      default: split_one<L, MODE_CLASSIC>(x, ep, is_float, is_signed, pr, se); break;
+    }
+    dst[i] = pr;
+  }
+}
+
+// what the Auto delta search needs of a trial plan: bin count, table size and per bin (weight, offset bits) - 772 bytes per chunk
+struct PlanSummary { uint32_t n_bins, size_log; uint16_t weight[ENC_MAXB]; uint8_t ob[ENC_MAXB]; };
+__global__ void plan_summary_kernel(const VarPlan* __restrict__ plans, uint32_t n_chunks, PlanSummary* __restrict__ out) {
+  const uint32_t c = blockIdx.x;
+  if (c >= n_chunks) return;
+  const VarPlan& p = plans[size_t(c) * MAX_VARS];
+  if (threadIdx.x == 0) { out[c].n_bins = p.n_bins; out[c].size_log = p.size_log; }
+  for (uint32_t i = threadIdx.x; i < uint32_t(ENC_MAXB); i += blockDim.x) { out[c].weight[i] = p.weight[i]; out[c].ob[i] = p.ob[i]; }
+}
+// calculate_compressed_sample_size (chunk_compressor.rs:289-307): meta_size_hint() + page_size_hint_inner(0, 1.0) of a Classic one-page
+// chunk holding the sample, as f32.  avg_bits_per_latent: metadata/bins.rs:23-32 (f64, bins in order).
+inline float sample_cost(const PlanSummary& p, uint32_t lbits, uint32_t order, uint64_t sample_n) {
+  const uint64_t meta_bits = 4 + (4 + 5 + 5 + 64 + 32 * 32) + 4 + 15 + uint64_t(p.n_bins) * (p.size_log + lbits + offset_bits_bits(lbits));
+  const uint64_t page_bits = uint64_t(order) * lbits + 4ull * p.size_log;
+  const double total_weight = double(uint64_t(1) << p.size_log);
+  double acc = 0.0;
+  for (uint32_t b = 0; b < p.n_bins; b++) {
+    const double ans_bits = double(p.size_log) - std::log2(double(p.weight[b]));
+    acc += (ans_bits + double(p.ob[b])) * double(p.weight[b]) / total_weight;
+  }
+  const uint64_t n_stored = sample_n > order ? sample_n - order : 0;
+  const uint64_t body_bits = uint64_t(std::ceil(double(n_stored) * acc * 1.0));
+  return float((meta_bits + 7) / 8 + (page_bits + 7) / 8 + (body_bits + 7) / 8);
+}
+
+// mode sample positions per chunk size (host, computed once per distinct n; sampling.rs:73-95)
+inline const std::vector<uint32_t>& mode_sample_positions(size_t n) {
+  static std::mutex mu;
+  static std::map<size_t, std::vector<uint32_t>> cache;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(n);
+  if (it == cache.end()) {
+    std::vector<uint32_t> v;
+    for (size_t p : mode_search::sample_positions(n)) v.push_back(uint32_t(p));
+    if (cache.size() > 64) cache.clear();
+    it = cache.emplace(n, std::move(v)).first;
+  }
+  return it->second;
+}
 
 template <typename L>
 static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t n, uint32_t dtype, const PcoB200ChunkConfig& cfg, bool uniform_type,
@@ -133,115 +253,51 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
   if (PcoB200Error e = n_per_page(cfg, n, &pages)) return e;
   for (uint64_t p : pages)
     if (p > (uint64_t(1) << 24)) return fail(PCO_B200_INVALID_ARGUMENT, "count may not exceed 16777216 per chunk");
-  // ---- specs the GPU hot path implements (Auto, Dict, Lookback, Conv1 are "next")
-  EncParams ep;
-  std::memset(&ep, 0, sizeof(ep));
-  ep.dtype = dtype;
-  ep.uniform_type = uniform_type ? dtype : 0;
+  // ---- the explicit mode, if any (Auto is resolved per chunk below)
+  ModeSel explicit_mode;
+  bool auto_mode = false;
   switch (cfg.mode_spec) {
-    case PCO_B200_MODE_CLASSIC: ep.mode = MODE_CLASSIC; break;
+    case PCO_B200_MODE_CLASSIC: break;
     case PCO_B200_MODE_TRY_INT_MULT:
       if (is_float) return fail(PCO_B200_INVALID_ARGUMENT, "unable to use int mult mode on floats");
-      ep.mode = MODE_INT_MULT;
-      ep.mode_base = lbits == 64 ? cfg.int_mult_base : (cfg.int_mult_base & ((uint64_t(1) << lbits) - 1));
-      if (ep.mode_base == 0) return fail(PCO_B200_INVALID_ARGUMENT, "The chosen mode of IntMult(0) was invalid");
+      explicit_mode.mode = MODE_INT_MULT;
+      explicit_mode.mode_base = lbits == 64 ? cfg.int_mult_base : (cfg.int_mult_base & ((uint64_t(1) << lbits) - 1));
+      if (explicit_mode.mode_base == 0) return fail(PCO_B200_INVALID_ARGUMENT, "The chosen mode of IntMult(0) was invalid");
       break;
     case PCO_B200_MODE_TRY_FLOAT_QUANT: {
       if (!is_float) return fail(PCO_B200_INVALID_ARGUMENT, "unable to use float mode for ints");
       uint32_t precision = lbits == 64 ? 52 : lbits == 32 ? 23 : 10;
       if (cfg.float_quant_k == 0 || cfg.float_quant_k > precision) return fail(PCO_B200_INVALID_ARGUMENT, "The chosen mode of FloatQuant was invalid");
-      ep.mode = MODE_FLOAT_QUANT;
-      ep.mode_k = cfg.float_quant_k;
+      explicit_mode.mode = MODE_FLOAT_QUANT;
+      explicit_mode.mode_k = cfg.float_quant_k;
       break;
     }
     case PCO_B200_MODE_TRY_FLOAT_MULT: {
       if (!is_float) return fail(PCO_B200_INVALID_ARGUMENT, "unable to use float mode for ints");
       if (lbits == 16) return fail(PCO_B200_UNSUPPORTED, "f16 FloatMult is outside the GPU hot path");
-      ep.mode = MODE_FLOAT_MULT;
-      if (lbits == 64) {
-        double base = cfg.float_mult_base, inv = 1.0 / base;
-        std::memcpy(&ep.base_bits, &base, 8);
-        std::memcpy(&ep.inv_base_bits, &inv, 8);
-        if (!std::isfinite(base) || base == 0.0) return fail(PCO_B200_INVALID_ARGUMENT, "The chosen mode of FloatMult was invalid");
-        ep.mode_base = (ep.base_bits >> 63) ? ~ep.base_bits : (ep.base_bits ^ (uint64_t(1) << 63));
-      } else {
-        float base = float(cfg.float_mult_base), inv = 1.0f / base;
-        uint32_t bb, ib;
-        std::memcpy(&bb, &base, 4);
-        std::memcpy(&ib, &inv, 4);
-        if (!std::isfinite(base) || base == 0.0f) return fail(PCO_B200_INVALID_ARGUMENT, "The chosen mode of FloatMult was invalid");
-        ep.base_bits = bb;
-        ep.inv_base_bits = ib;
-        ep.mode_base = (bb >> 31) ? uint32_t(~bb) : (bb ^ 0x80000000u);
-      }
+      const bool finite_nonzero = lbits == 64 ? (std::isfinite(cfg.float_mult_base) && cfg.float_mult_base != 0.0)
+                                              : (std::isfinite(float(cfg.float_mult_base)) && float(cfg.float_mult_base) != 0.0f);
+      if (!finite_nonzero) return fail(PCO_B200_INVALID_ARGUMENT, "The chosen mode of FloatMult was invalid");
+      if (lbits == 64) set_float_mult(&explicit_mode, 64, cfg.float_mult_base, 1.0 / cfg.float_mult_base);
+      else set_float_mult(&explicit_mode, 32, double(float(cfg.float_mult_base)), double(1.0f / float(cfg.float_mult_base)));
       break;
     }
-    case PCO_B200_MODE_AUTO: {
-      // Default: Auto on the GPU path means Classic, which is always valid.  With PCOB200_AUTO_MODE_SEARCH=1 the reference's mode
-      // search (mode_search.hpp: int_mult::choose_base, FloatMult / FloatQuant bids on the reference's sample) runs on the host over
-      // the call's FIRST chunk and its answer is used for every chunk of the call (the reference searches per chunk; one array is
-      // usually one kind of data).  Opt-in until it has been measured on a GPU box.
-      ep.mode = MODE_CLASSIC;
-      static const bool search = [] { const char* e = std::getenv("PCOB200_AUTO_MODE_SEARCH"); return e && e[0] == '1'; }();
-      const bool multi_page_chunk = (flags & PCO_B200_INTERNAL_SHARED_BINS) && pages.size() > 1;  // shared bins exist for one latent var only
-      if (search && !pages.empty() && !multi_page_chunk) {
-        const size_t n0 = size_t(pages[0]);
-        std::vector<L> staged;
-        const L* first = static_cast<const L*>(nums);
-        if (src_dev) {
-          staged.resize(n0);
-          PCOB_CUDA_TRY(cudaMemcpyAsync(staged.data(), nums, n0 * sizeof(L), cudaMemcpyDeviceToHost, stream));
-          PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
-          first = staged.data();
-        }
-        mode_search::Choice c;
-        if constexpr (sizeof(L) == 8) c = is_float ? mode_search::choose_float<double>(first, n0) : mode_search::choose_int<L>(first, n0, nt_is_signed(dtype));
-        else if constexpr (sizeof(L) == 4) c = is_float ? mode_search::choose_float<float>(first, n0) : mode_search::choose_int<L>(first, n0, nt_is_signed(dtype));
-        else if constexpr (sizeof(L) == 2) {
-          c = is_float ? mode_search::choose_float<mode_search::Half>(first, n0) : mode_search::choose_int<L>(first, n0, nt_is_signed(dtype));
-          if (is_float && c.kind == 2) c = mode_search::Choice();  // there is no f16 FloatMult kernel: Classic instead
-        } else c = mode_search::choose_int<L>(first, n0, nt_is_signed(dtype));
-        if (c.kind == 1) {
-          ep.mode = MODE_INT_MULT;
-          ep.mode_base = c.int_base;
-        } else if (c.kind == 3) {
-          ep.mode = MODE_FLOAT_QUANT;
-          ep.mode_k = c.k;
-        } else if (c.kind == 2 && lbits == 64) {
-          ep.mode = MODE_FLOAT_MULT;
-          std::memcpy(&ep.base_bits, &c.base, 8);
-          std::memcpy(&ep.inv_base_bits, &c.inv_base, 8);
-          ep.mode_base = (ep.base_bits >> 63) ? ~ep.base_bits : (ep.base_bits ^ (uint64_t(1) << 63));
-        } else if (c.kind == 2) {
-          const float base = float(c.base), inv = float(c.inv_base);
-          uint32_t bb, ib;
-          std::memcpy(&bb, &base, 4);
-          std::memcpy(&ib, &inv, 4);
-          ep.mode = MODE_FLOAT_MULT;
-          ep.base_bits = bb;
-          ep.inv_base_bits = ib;
-          ep.mode_base = (bb >> 31) ? uint32_t(~bb) : (bb ^ 0x80000000u);
-        }
-      }
-      break;
-    }
+    case PCO_B200_MODE_AUTO: auto_mode = true; break;
     default: return fail(PCO_B200_UNSUPPORTED, "ModeSpec::TryDict is outside the GPU hot path");
   }
   bool auto_delta = false;
+  uint32_t explicit_order = 0;
   switch (cfg.delta_spec) {
-    case PCO_B200_DELTA_NOOP: ep.order = 0; break;
-    case PCO_B200_DELTA_TRY_CONSECUTIVE: ep.order = cfg.delta_order; break;
-    case PCO_B200_DELTA_AUTO: auto_delta = true; ep.order = 0; break;  // resolved below by the sampled order search
+    case PCO_B200_DELTA_NOOP: break;
+    case PCO_B200_DELTA_TRY_CONSECUTIVE: explicit_order = cfg.delta_order; break;
+    case PCO_B200_DELTA_AUTO: auto_delta = true; break;  // resolved per chunk below by the sampled search
     case PCO_B200_DELTA_TRY_CONV1:
-      if (cfg.delta_order == 0) { ep.order = 0; break; }
+      if (cfg.delta_order == 0) break;
       return fail(PCO_B200_UNSUPPORTED, "DeltaSpec::TryConv1 is outside the GPU hot path");
     default: return fail(PCO_B200_UNSUPPORTED, "DeltaSpec::TryLookback is outside the GPU hot path");
   }
-  ep.n_vars = ep.mode == MODE_CLASSIC ? 1 : 2;
-  ep.n_total = n;
-  ep.n_chunks = uint32_t(pages.size());
   const bool chunks_only = flags & PCO_B200_CHUNKS_ONLY;
-  std::vector<uint8_t> header = make_standalone_header(n, uint8_t(ep.uniform_type));
+  std::vector<uint8_t> header = make_standalone_header(n, uint8_t(uniform_type ? dtype : 0));
   if (chunks_only) header.clear();
   // empty input: header + terminator only (standalone/simple.rs:62-91)
   if (n == 0) {
@@ -260,10 +316,10 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
     }
     return PCO_B200_OK;
   }
+  const uint32_t n_chunks_all = uint32_t(pages.size());
   std::vector<uint64_t> starts(pages.size() + 1, 0);
   uint64_t max_chunk_n = 0;
   for (size_t i = 0; i < pages.size(); i++) { starts[i + 1] = starts[i] + pages[i]; max_chunk_n = std::max<uint64_t>(max_chunk_n, pages[i]); }
-  ep.max_chunk_n = uint32_t(max_chunk_n);
   // unoptimized_bins_log is a function of each chunk's n; the kernels take one value per call, so every chunk must agree
   const bool shared_bins = (flags & PCO_B200_INTERNAL_SHARED_BINS) && pages.size() > 1;
   uint32_t bins_log = choose_unoptimized_bins_log(cfg.compression_level, shared_bins ? n : size_t(pages[0]));
@@ -271,63 +327,43 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
     for (uint64_t p : pages)
       if (choose_unoptimized_bins_log(cfg.compression_level, size_t(p)) != bins_log)
         return fail(PCO_B200_UNSUPPORTED, "chunks whose sizes imply different unoptimized_bins_log in one call");
-  if (shared_bins && ep.mode != MODE_CLASSIC)
-    return fail(PCO_B200_UNSUPPORTED, "wrapped chunks with several pages: classic mode only, for now");
   if (bins_log > 8) return fail(PCO_B200_UNSUPPORTED, "compression levels that train more than 256 bins are outside the GPU hot path");
-  ep.bins_log[0] = bins_log;
-  ep.bins_log[1] = std::min<uint32_t>(bins_log, 6);  // LIMITED_UNOPTIMIZED_BINS_LOG (chunk_compressor.rs:238-248)
 
-  // ---- device buffers
-  const uint32_t n_chunks = ep.n_chunks;
-  const uint32_t bpc = n_batches_of(uint32_t(max_chunk_n));
-  const uint32_t tiles_per_chunk = uint32_t((max_chunk_n + SPLIT_TILE - 1) / SPLIT_TILE);
+  // ---- the numbers in HBM
   const void* d_nums = nums;
-  // every chunk's rows start on a 256-slot boundary in the latent / symbol / ans arrays (vector accesses per batch row)
-  std::vector<uint64_t> rows(pages.size() + 1, 0);
-  for (size_t i = 0; i < pages.size(); i++) rows[i + 1] = rows[i] + ((pages[i] + BATCH_N - 1) / BATCH_N) * BATCH_N;
-  const size_t n_slots = size_t(rows.back());
-  PCOB_CUDA_TRY(S.lat0.reserve(n_slots * sizeof(L) + 64));
-  if (ep.n_vars > 1) PCOB_CUDA_TRY(S.lat1.reserve(n_slots * sizeof(L) + 64));
-  PCOB_CUDA_TRY(S.sym0.reserve(n_slots + 64));
-  PCOB_CUDA_TRY(S.ans0.reserve(n_slots * 2 + 64));
-  if (ep.n_vars > 1) { PCOB_CUDA_TRY(S.sym1.reserve(n_slots + 64)); PCOB_CUDA_TRY(S.ans1.reserve(n_slots * 2 + 64)); }
-  const size_t n_cvb = size_t(n_chunks) * MAX_VARS * bpc;
-  PCOB_CUDA_TRY(S.ob_sum.reserve(n_cvb * 4));
-  PCOB_CUDA_TRY(S.ans_sum.reserve(n_cvb * 4));
-  PCOB_CUDA_TRY(S.entries.reserve(n_cvb * sizeof(BatchEntry)));
-  PCOB_CUDA_TRY(S.plans.reserve(size_t(n_chunks) * MAX_VARS * sizeof(VarPlan)));
-  PCOB_CUDA_TRY(S.chunks.reserve(size_t(n_chunks) * sizeof(ChunkEnc)));
-  PCOB_CUDA_TRY(S.starts.reserve(starts.size() * 16));
-  PCOB_CUDA_TRY(S.seg.reserve(size_t(n_chunks) * 16));
-  PCOB_CUDA_TRY(S.small.reserve(256 + header.size()));
-  // a dedicated input staging buffer when nums live on the host (kept apart from the sort buffers)
-  DevBuf& in_stage = S.index;
+  DevBuf& in_stage = S.index;  // a dedicated input staging buffer when nums live on the host (kept apart from the sort buffers)
   if (!src_dev) {
     PCOB_CUDA_TRY(in_stage.reserve(n * sizeof(L) + 64));
     PCOB_CUDA_TRY(cudaMemcpyAsync(in_stage.p, nums, n * sizeof(L), cudaMemcpyHostToDevice, stream));
     d_nums = in_stage.p;
   }
-  ep.nums = d_nums;
-  PCOB_CUDA_TRY(cudaMemcpyAsync(S.starts.p, starts.data(), starts.size() * 8, cudaMemcpyHostToDevice, stream));
-  ep.chunk_starts = S.starts.as<uint64_t>();
-  PCOB_CUDA_TRY(cudaMemcpyAsync(S.starts.as<uint64_t>() + starts.size(), rows.data(), rows.size() * 8, cudaMemcpyHostToDevice, stream));
-  ep.row_base = S.starts.as<uint64_t>() + starts.size();
+  // scratch sized for the whole call; every run below (and the Auto searches) indexes it from 0
+  std::vector<uint64_t> rows_all(pages.size() + 1, 0);
+  for (size_t i = 0; i < pages.size(); i++) rows_all[i + 1] = rows_all[i] + ((pages[i] + BATCH_N - 1) / BATCH_N) * BATCH_N;
+  const uint32_t bpc_all = n_batches_of(uint32_t(max_chunk_n));
+  PCOB_CUDA_TRY(S.plans.reserve(size_t(n_chunks_all) * MAX_VARS * sizeof(VarPlan)));
+  PCOB_CUDA_TRY(S.chunks.reserve(size_t(n_chunks_all) * sizeof(ChunkEnc)));
+  PCOB_CUDA_TRY(S.starts.reserve((starts.size() + 1) * 32));
+  PCOB_CUDA_TRY(S.seg.reserve(size_t(n_chunks_all) * 16));
+  PCOB_CUDA_TRY(S.small.reserve(256 + header.size()));
+  PCOB_CUDA_TRY(S.probes.reserve(size_t(n_chunks_all) * sizeof(PlanProbes)));
   ChunkEnc* d_chunks = S.chunks.as<ChunkEnc>();
   VarPlan* d_plans = S.plans.as<VarPlan>();
-  PCOB_CUDA_TRY(S.probes.reserve(size_t(n_chunks) * sizeof(PlanProbes)));
   PlanProbes* d_probes = S.probes.as<PlanProbes>();
-  L* d_lat[2] = {S.lat0.as<L>(), S.lat1.as<L>()};
-  uint8_t* d_sym[2] = {S.sym0.as<uint8_t>(), S.sym1.as<uint8_t>()};
-  uint16_t* d_ans[2] = {S.ans0.as<uint16_t>(), S.ans1.as<uint16_t>()};
   uint32_t* d_small = S.small.as<uint32_t>();  // [0]: range bits, [2..3]: total bytes (u64), header at byte 64
   uint64_t* d_total = reinterpret_cast<uint64_t*>(d_small + 2);
   uint8_t* d_header = reinterpret_cast<uint8_t*>(d_small) + 64;
-  PCOB_CUDA_TRY(cudaMemcpyAsync(d_header, header.data(), header.size(), cudaMemcpyHostToDevice, stream));
-  PCOB_CUDA_TRY(cudaMemsetAsync(S.ob_sum.p, 0, n_cvb * 4, stream));
+  if (!header.empty()) PCOB_CUDA_TRY(cudaMemcpyAsync(d_header, header.data(), header.size(), cudaMemcpyHostToDevice, stream));
 
-  // ---- K1+K2 and the planner for one set of chunks (the call's chunks, or their samples during the Auto delta search)
-  uint32_t var_range_bits[MAX_VARS] = {64, 64};
-  auto front = [&](const EncParams& e, uint32_t tiles, size_t slots, uint32_t (&vrb)[MAX_VARS], const std::vector<uint64_t>& sizes) -> PcoB200Error {
+  // ---- K1+K2 and the planner for one set of chunks (a run of the call's chunks, or the chunks' samples during the Auto delta search).
+  // `e` describes the set (its own chunk_starts / row_base, counted from 0); plans and probes land in slots 0 .. e.n_chunks - 1.
+  L* d_lat[2] = {nullptr, nullptr};
+  auto front = [&](const EncParams& e, uint32_t tiles, size_t slots, uint32_t (&vrb)[MAX_VARS], const std::vector<uint64_t>& sizes, bool shared) -> PcoB200Error {
+    const uint32_t n_chunks = e.n_chunks;
+    PCOB_CUDA_TRY(S.lat0.reserve(slots * sizeof(L) + 64));
+    if (e.n_vars > 1) PCOB_CUDA_TRY(S.lat1.reserve(slots * sizeof(L) + 64));
+    d_lat[0] = S.lat0.as<L>();
+    d_lat[1] = S.lat1.as<L>();
     init_chunks_kernel<<<(n_chunks + 255) / 256, 256, 0, stream>>>(d_chunks, n_chunks);
     if (!S.plan_attr_set) {
       S.plan_attr_set = true;
@@ -354,7 +390,7 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
       uint32_t fl[2] = {0, 0};
       PCOB_CUDA_TRY(cudaMemcpyAsync(fl, d_small, 8, cudaMemcpyDeviceToHost, stream));
       PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
-      if (fl[1] == 0 && shared_bins) {
+      if (fl[1] == 0 && shared) {
         // pages of one chunk: one histogram over all of them, one plan, copied to every page's slot
         if (!S.union_attr_set) {
           S.union_attr_set = true;
@@ -393,7 +429,7 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
     }
     profiler().end(stream);
     // ---- planner per var: range-reduced keys -> segmented radix sort over the significant bits -> plan
-    if (shared_bins) {
+    if (shared) {
       // pages of one wrapped chunk on the sort path: common minimum, the pages' keys as one gap-free segment, one sort,
       // the union's probes and plan, copied to every page's slot (classic mode: one latent var)
       PCOB_CUDA_TRY(cudaMemsetAsync(d_small, 0, 4, stream));
@@ -442,8 +478,8 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
         const size_t smem = ((size_t(1) << range_bits) + 1) * 4 + 16;
         profiler().begin("plan_probe_kernel_counting", stream);
         PCOB_CUDA_TRY((v == 0 ? S.key16_0 : S.key16_1).reserve(slots * 2 + 64));
-      plan_probe_kernel<L, true><<<n_chunks, PLAN_THREADS, smem, stream>>>(e, d_lat[v], d_chunks, d_probes, int(v), range_bits,
-                                                                            (v == 0 ? S.key16_0 : S.key16_1).as<uint16_t>());
+        plan_probe_kernel<L, true><<<n_chunks, PLAN_THREADS, smem, stream>>>(e, d_lat[v], d_chunks, d_probes, int(v), range_bits,
+                                                                              (v == 0 ? S.key16_0 : S.key16_1).as<uint16_t>());
         profiler().end(stream);
         profiler().begin("plan_solve_kernel", stream);
         plan_solve_kernel<L><<<n_chunks, SOLVE_THREADS, 0, stream>>>(e, d_probes, d_chunks, d_plans, int(v));
@@ -481,131 +517,317 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
     }
     return PCO_B200_OK;
   };
-  if (auto_delta) {
-    // ---- DeltaSpec::Auto: sampled search over consecutive orders (see gather_sample_kernel)
-    std::vector<uint64_t> s_starts(pages.size() + 1, 0), s_rows(pages.size() + 1, 0), s_sizes(pages.size(), 0);
-    uint64_t max_ns = 0;
-    for (size_t i = 0; i < pages.size(); i++) {
-      const SampleGeom g = delta_sample_geom(pages[i]);
-      const uint64_t ns = uint64_t(g.n_groups) * g.group_n;
-      s_starts[i + 1] = s_starts[i] + ns;
-      s_sizes[i] = ns;
-      s_rows[i + 1] = s_rows[i] + ((ns + BATCH_N - 1) / BATCH_N) * BATCH_N;
-      max_ns = std::max(max_ns, ns);
+
+  // ---- ModeSpec::Auto and DeltaSpec::Auto are the reference's PER-CHUNK searches (chunk_compressor.rs:396-440): every chunk of the
+  // call gets its own answer; with shared bins (the pages of ONE wrapped chunk) the whole input is the unit.
+  const size_t n_units = shared_bins ? 1 : pages.size();
+  auto unit_begin = [&](size_t u) -> uint64_t { return shared_bins ? 0 : starts[u]; };
+  auto unit_n = [&](size_t u) -> uint64_t { return shared_bins ? uint64_t(n) : pages[u]; };
+  std::vector<ModeSel> unit_mode(n_units, explicit_mode);
+  std::vector<uint32_t> unit_order(n_units, explicit_order);
+  if (auto_mode) {
+    // the reference's search (mode_search.hpp) reads ~n/40 numbers per chunk at positions that depend on n only: the device gathers
+    // every chunk's sample, the host (one task per chunk on its worker threads) runs the scalar analysis
+    std::map<uint64_t, std::vector<uint32_t>> by_n;
+    for (size_t u = 0; u < n_units; u++) by_n[unit_n(u)].push_back(uint32_t(u));
+    std::vector<uint64_t> ustarts(n_units + 1, 0);
+    for (size_t u = 0; u < n_units; u++) ustarts[u] = unit_begin(u);
+    ustarts[n_units] = n;
+    PCOB_CUDA_TRY(S.sample_starts.reserve((n_units + 1) * 8 + n_units * 4 + 64));
+    uint64_t* d_ustarts = S.sample_starts.as<uint64_t>();
+    PCOB_CUDA_TRY(cudaMemcpyAsync(d_ustarts, ustarts.data(), ustarts.size() * 8, cudaMemcpyHostToDevice, stream));
+    for (auto& kv : by_n) {
+      const std::vector<uint32_t>& pos = mode_sample_positions(size_t(kv.first));
+      const uint32_t m = uint32_t(pos.size());
+      if (m == 0) continue;  // fewer than MIN_SAMPLE numbers: Classic (sampling.rs:14-20)
+      const std::vector<uint32_t>& ids = kv.second;
+      PCOB_CUDA_TRY(S.sample.reserve(ids.size() * size_t(m) * sizeof(L) + 64));
+      PCOB_CUDA_TRY(S.seg.reserve((ids.size() + m) * 4 + 64));
+      uint32_t* d_ids = S.seg.as<uint32_t>();
+      uint32_t* d_pos = d_ids + ids.size();
+      PCOB_CUDA_TRY(cudaMemcpyAsync(d_ids, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice, stream));
+      PCOB_CUDA_TRY(cudaMemcpyAsync(d_pos, pos.data(), size_t(m) * 4, cudaMemcpyHostToDevice, stream));
+      gather_positions_kernel<L><<<uint32_t(ids.size()), 256, 0, stream>>>(static_cast<const L*>(d_nums), d_ustarts, d_ids, d_pos, m, S.sample.as<L>());
+      std::vector<L> h_sample(ids.size() * size_t(m));
+      PCOB_CUDA_TRY(cudaMemcpyAsync(h_sample.data(), S.sample.p, h_sample.size() * sizeof(L), cudaMemcpyDeviceToHost, stream));
+      PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
+      std::vector<mode_search::Choice> choices(ids.size());
+      auto work = [&](size_t i) {
+        const L* sp = h_sample.data() + i * size_t(m);
+        mode_search::Choice c;
+        if constexpr (sizeof(L) == 8) c = is_float ? mode_search::choose_float_from_sample<double>(sp, m) : mode_search::choose_int_from_sample<L>(sp, m, nt_is_signed(dtype));
+        else if constexpr (sizeof(L) == 4) c = is_float ? mode_search::choose_float_from_sample<float>(sp, m) : mode_search::choose_int_from_sample<L>(sp, m, nt_is_signed(dtype));
+        else if constexpr (sizeof(L) == 2) c = is_float ? mode_search::choose_float_from_sample<mode_search::Half>(sp, m) : mode_search::choose_int_from_sample<L>(sp, m, nt_is_signed(dtype));
+        else c = mode_search::choose_int_from_sample<L>(sp, m, nt_is_signed(dtype));
+        choices[i] = c;
+      };
+      const size_t n_threads = std::max<size_t>(1, std::min<size_t>(ids.size(), std::min<size_t>(std::thread::hardware_concurrency(), 32)));
+      if (n_threads <= 1) {
+        for (size_t i = 0; i < ids.size(); i++) work(i);
+      } else {
+        std::atomic<size_t> next{0};
+        std::vector<std::thread> pool;
+        for (size_t t = 0; t < n_threads; t++)
+          pool.emplace_back([&] { for (size_t i = next.fetch_add(1); i < ids.size(); i = next.fetch_add(1)) work(i); });
+        for (auto& th : pool) th.join();
+      }
+      for (size_t i = 0; i < ids.size(); i++) {
+        const mode_search::Choice& c = choices[i];
+        ModeSel ms;
+        if (c.kind == 1) { ms.mode = MODE_INT_MULT; ms.mode_base = c.int_base; }
+        else if (c.kind == 3) { ms.mode = MODE_FLOAT_QUANT; ms.mode_k = c.k; }
+        else if (c.kind == 2) {
+          if (lbits == 16) return fail(PCO_B200_UNSUPPORTED, "ModeSpec::Auto chose FloatMult for an f16 chunk: f16 FloatMult is outside the GPU hot path");
+          set_float_mult(&ms, lbits, c.base, c.inv_base);
+        }
+        unit_mode[ids[i]] = ms;
+      }
     }
+  }
+  if (shared_bins && unit_mode[0].mode != MODE_CLASSIC)
+    return fail(PCO_B200_UNSUPPORTED, "wrapped chunks with several pages: classic mode only, for now");
+  if (auto_delta) {
+    // choose_auto_delta_encoding (chunk_compressor.rs:310-360) per chunk: the sample of the chunk's primary latents (sampling.rs:21-60) is
+    // trial-compressed in Classic mode with NoOp, then consecutive orders 1, 2, ... while the cost keeps falling.  Every order is planned
+    // for all chunks at once by the ordinary front end + planner kernels; the costs are the reference's f32 formula (sample_cost).
+    // The Lookback candidate (chunk_compressor.rs:326-338) is not evaluated: where it would win this path writes a consecutive order.
+    std::vector<uint64_t> s_starts(n_units + 1, 0), s_rows(n_units + 1, 0), s_sizes(n_units, 0), ustarts(n_units + 1, 0);
+    uint64_t max_ns = 0;
+    for (size_t u = 0; u < n_units; u++) {
+      const SampleGeom g = delta_sample_geom(unit_n(u));
+      const uint64_t ns = uint64_t(g.n_groups) * g.group_n;
+      s_starts[u + 1] = s_starts[u] + ns;
+      s_sizes[u] = ns;
+      s_rows[u + 1] = s_rows[u] + ((ns + BATCH_N - 1) / BATCH_N) * BATCH_N;
+      max_ns = std::max(max_ns, ns);
+      ustarts[u] = unit_begin(u);
+    }
+    ustarts[n_units] = n;
     if (s_starts.back() > 0) {
+      std::vector<ModeSelDev> hm(n_units);
+      for (size_t u = 0; u < n_units; u++) hm[u] = ModeSelDev{unit_mode[u].mode, unit_mode[u].mode_k, unit_mode[u].mode_base, unit_mode[u].base_bits, unit_mode[u].inv_base_bits};
       PCOB_CUDA_TRY(S.sample.reserve(s_starts.back() * sizeof(L) + 64));
-      PCOB_CUDA_TRY(S.sample_starts.reserve(s_starts.size() * 16 + 16));
+      const size_t words = 3 * (n_units + 1);
+      PCOB_CUDA_TRY(S.sample_starts.reserve(words * 8 + n_units * sizeof(ModeSelDev) + n_units * sizeof(PlanSummary) + 256));
       uint64_t* d_ss = S.sample_starts.as<uint64_t>();
+      uint64_t* d_srows = d_ss + (n_units + 1);
+      uint64_t* d_ustarts = d_srows + (n_units + 1);
+      ModeSelDev* d_modes = reinterpret_cast<ModeSelDev*>(d_ustarts + (n_units + 1));
+      PlanSummary* d_sum = reinterpret_cast<PlanSummary*>(d_modes + n_units);
       PCOB_CUDA_TRY(cudaMemcpyAsync(d_ss, s_starts.data(), s_starts.size() * 8, cudaMemcpyHostToDevice, stream));
-      PCOB_CUDA_TRY(cudaMemcpyAsync(d_ss + s_starts.size(), s_rows.data(), s_rows.size() * 8, cudaMemcpyHostToDevice, stream));
-      gather_sample_kernel<L><<<n_chunks, 256, 0, stream>>>(static_cast<const L*>(d_nums), ep.chunk_starts, d_ss, S.sample.as<L>());
-      EncParams es = ep;
+      PCOB_CUDA_TRY(cudaMemcpyAsync(d_srows, s_rows.data(), s_rows.size() * 8, cudaMemcpyHostToDevice, stream));
+      PCOB_CUDA_TRY(cudaMemcpyAsync(d_ustarts, ustarts.data(), ustarts.size() * 8, cudaMemcpyHostToDevice, stream));
+      PCOB_CUDA_TRY(cudaMemcpyAsync(d_modes, hm.data(), hm.size() * sizeof(ModeSelDev), cudaMemcpyHostToDevice, stream));
+      gather_primary_sample_kernel<L><<<uint32_t(n_units), 256, 0, stream>>>(static_cast<const L*>(d_nums), d_ustarts, d_ss, d_modes, dtype, S.sample.as<L>());
+      EncParams es;
+      std::memset(&es, 0, sizeof(es));
+      es.dtype = lbits == 8 ? NT_U8 : lbits == 16 ? NT_U16 : lbits == 32 ? NT_U32 : NT_U64;  // the sample holds latents: unsigned numbers of the same width
+      es.mode = MODE_CLASSIC;
+      es.n_vars = 1;
       es.nums = S.sample.p;
       es.chunk_starts = d_ss;
-      es.row_base = d_ss + s_starts.size();
+      es.row_base = d_srows;
       es.n_total = s_starts.back();
+      es.n_chunks = uint32_t(n_units);
       es.max_chunk_n = uint32_t(max_ns);
+      es.bins_log[0] = bins_log;
+      es.bins_log[1] = std::min<uint32_t>(bins_log, 6);
       const uint32_t s_tiles = uint32_t((max_ns + SPLIT_TILE - 1) / SPLIT_TILE);
-      unsigned long long* d_cost = reinterpret_cast<unsigned long long*>(d_small + 4);
-      unsigned long long best_cost = 0;
-      uint32_t best_order = 0;
-      for (uint32_t k = 0; k <= MAX_ORDER; k++) {
+      std::vector<PlanSummary> h_sum(n_units);
+      std::vector<float> best_cost(n_units, 0.f);
+      std::vector<uint8_t> open(n_units, 1);
+      size_t n_open = n_units;
+      for (uint32_t k = 0; k <= MAX_ORDER && n_open > 0; k++) {
         es.order = k;
         uint32_t vrb[MAX_VARS] = {64, 64};
-        if (PcoB200Error e = front(es, s_tiles, size_t(s_rows.back()), vrb, s_sizes)) return e;
-        PCOB_CUDA_TRY(cudaMemsetAsync(d_cost, 0, 8, stream));
-        auto_cost_kernel<<<(n_chunks + 255) / 256, 256, 0, stream>>>(es, d_plans, d_cost);
-        unsigned long long cost = 0;
-        PCOB_CUDA_TRY(cudaMemcpyAsync(&cost, d_cost, 8, cudaMemcpyDeviceToHost, stream));
+        if (PcoB200Error e = front(es, s_tiles, size_t(s_rows.back()), vrb, s_sizes, false)) return e;
+        plan_summary_kernel<<<uint32_t(n_units), 128, 0, stream>>>(d_plans, uint32_t(n_units), d_sum);
+        PCOB_CUDA_TRY(cudaMemcpyAsync(h_sum.data(), d_sum, n_units * sizeof(PlanSummary), cudaMemcpyDeviceToHost, stream));
         PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
-        if (k == 0 || cost < best_cost) { best_cost = cost; best_order = k; }
-        else break;  // "it's almost always convex" (chunk_compressor.rs:347-357)
+        for (size_t u = 0; u < n_units; u++) {
+          if (!open[u]) continue;
+          if (s_sizes[u] == 0) { open[u] = 0; n_open--; continue; }  // no sample: NoOp (chunk_compressor.rs:314-316)
+          const float cost = sample_cost(h_sum[u], lbits, k, s_sizes[u]);
+          if (k == 0) best_cost[u] = cost;
+          else if (cost < best_cost[u]) { best_cost[u] = cost; unit_order[u] = k; }
+          else { open[u] = 0; n_open--; }  // "it's almost always convex" (chunk_compressor.rs:347-357)
+        }
       }
-      ep.order = best_order;
     }
   }
-  if (PcoB200Error e = front(ep, tiles_per_chunk, n_slots, var_range_bits, pages)) return e;
-  fallback_kernel<<<(n_chunks + 255) / 256, 256, 0, stream>>>(ep, d_plans, d_chunks, shared_bins ? n_chunks : 0u);
-  // ---- K3, K4
-  const uint32_t groups_per_chunk = (bpc + 7) / 8;
-  for (uint32_t v = 0; v < ep.n_vars; v++)
-  {
-    if (var_range_bits[v] <= PLAN_MAX_COUNT_BITS) {
-      const uint32_t parts = (bpc + BINL_BATCHES - 1) / BINL_BATCHES;
-      profiler().begin("bin_lut_kernel", stream);
-      bin_lut_kernel<L><<<n_chunks * parts, BINL_THREADS, (size_t(1) << var_range_bits[v]) + 16, stream>>>(ep, bpc, parts, (v == 0 ? S.key16_0 : S.key16_1).as<uint16_t>(), d_plans, d_chunks, d_sym[v],
-                                                                                                           S.ob_sum.as<uint32_t>(), int(v), var_range_bits[v]);
-      profiler().end(stream);
-      continue;
+
+  // ---- runs of consecutive chunks with the same resolved (mode, order): each is one pass of the pipeline; a call with explicit specs
+  // (and the usual homogeneous array under Auto) is a single run
+  struct Run { size_t c0, c1; ModeSel ms; uint32_t order; };
+  std::vector<Run> runs;
+  if (shared_bins) runs.push_back(Run{0, pages.size(), unit_mode[0], unit_order[0]});
+  else
+    for (size_t c = 0; c < pages.size(); c++) {
+      if (!runs.empty() && runs.back().ms == unit_mode[c] && runs.back().order == unit_order[c]) runs.back().c1 = c + 1;
+      else runs.push_back(Run{c, c + 1, unit_mode[c], unit_order[c]});
     }
-    profiler().begin("bin_kernel", stream);
-    bin_kernel<L><<<n_chunks * groups_per_chunk, BIN_THREADS, 0, stream>>>(ep, bpc, d_lat[v], d_plans, d_chunks, d_sym[v], S.ob_sum.as<uint32_t>(), int(v));
-    profiler().end(stream);
-  }
-  // the ans kernel indexes (chunk, var) by blockIdx; both vars share the launch via separate symbol arrays
-  profiler().begin("ans_encode_kernel", stream);
-  ans_encode_kernel<<<n_chunks * MAX_VARS, ANS_THREADS, 0, stream>>>(ep, bpc, d_plans, d_chunks, d_sym[0], d_sym[1], d_ans[0], d_ans[1], S.ans_sum.as<uint32_t>(),
-                                                                     S.entries.as<BatchEntry>());
-  profiler().end(stream);
-  // ---- layout, offsets, K5
-  profiler().begin("layout_kernel", stream);
-  layout_kernel<<<n_chunks, LAYOUT_THREADS, 0, stream>>>(ep, bpc, d_plans, d_chunks, S.ans_sum.as<uint32_t>(), S.ob_sum.as<uint32_t>(), S.entries.as<BatchEntry>());
-  profiler().end(stream);
-  chunk_offsets_kernel<<<1, 1024, 0, stream>>>(d_chunks, n_chunks, header.size(), chunks_only ? 0u : 1u, d_total);
-  uint64_t total = 0;
-  uint8_t* d_out = static_cast<uint8_t*>(dst);
-  if (!dst_dev) {
-    // the staging buffer is sized from the file size, so that is needed first
-    PCOB_CUDA_TRY(cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, stream));
-    PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
-    PCOB_CUDA_TRY(cudaGetLastError());
-    if (total > dst_cap) return fail(PCO_B200_IO, "failed to write whole buffer (need " + std::to_string(total) + " bytes, dst_cap " + std::to_string(dst_cap) + ")");
-    PCOB_CUDA_TRY(S.out.reserve(total + 64));
-    d_out = S.out.as<uint8_t>();
-  }
-  // device destination: no host round trip here - pack_kernel leaves out any chunk that would not fit dst_cap, and the size
-  // is checked when it is read back behind the kernel
-  const uint64_t out_cap = dst_dev ? uint64_t(dst_cap) : total;
-  profiler().begin("pack_kernel", stream);
-  pack_kernel<L><<<n_chunks, PACK_THREADS, sizeof(PackSmem), stream>>>(ep, bpc, d_lat[0], d_lat[1], d_plans, d_chunks, d_sym[0], d_sym[1], d_ans[0], d_ans[1],
-                                                                      S.entries.as<BatchEntry>(), d_out, out_cap,
-                                                                      var_range_bits[0] <= PLAN_MAX_COUNT_BITS ? S.key16_0.as<uint16_t>() : nullptr,
-                                                                      (ep.n_vars > 1 && var_range_bits[1] <= PLAN_MAX_COUNT_BITS) ? S.key16_1.as<uint16_t>() : nullptr);
-  profiler().end(stream);
-  if (!chunks_only) header_footer_kernel<<<1, 32, 0, stream>>>(d_out, out_cap, d_header, uint32_t(header.size()), d_total);
-  PCOB_CUDA_TRY(cudaGetLastError());
-  if (!dst_dev) PCOB_CUDA_TRY(cudaMemcpyAsync(dst, d_out, total, cudaMemcpyDeviceToHost, stream));
-  // ---- optional side index
+  // side index layout (host): entries of chunk c take n_vars(c) x batches(c) records
+  const uint64_t chunks_offset = sizeof(IndexHeader);
+  std::vector<uint64_t> eoff(n_chunks_all, 0);
+  uint64_t index_total = 0;
   if (index_dst != nullptr) {
-    const uint64_t chunks_offset = sizeof(IndexHeader);
-    std::vector<uint64_t> eoff(n_chunks);
-    uint64_t off = (chunks_offset + uint64_t(n_chunks) * sizeof(IndexChunk) + 15) & ~uint64_t(15);
-    for (uint32_t c = 0; c < n_chunks; c++) {
-      eoff[c] = off;
-      off += (uint64_t(ep.n_vars) * n_batches_of(uint32_t(pages[c])) * sizeof(BatchEntry) + 15) & ~uint64_t(15);
-    }
+    uint64_t off = (chunks_offset + uint64_t(n_chunks_all) * sizeof(IndexChunk) + 15) & ~uint64_t(15);
+    for (const Run& r : runs)
+      for (size_t c = r.c0; c < r.c1; c++) {
+        eoff[c] = off;
+        off += (uint64_t(r.ms.mode == MODE_CLASSIC ? 1 : 2) * n_batches_of(uint32_t(pages[c])) * sizeof(BatchEntry) + 15) & ~uint64_t(15);
+      }
     if (off > index_cap) return fail(PCO_B200_IO, "index buffer too small (need " + std::to_string(off) + " bytes)");
-    // assemble on the device (the input staging buffer is free again), then one copy out
-    DevBuf& idx = S.keys_b;  // sort buffers are idle now
-    PCOB_CUDA_TRY(idx.reserve(off + 64));
-    PCOB_CUDA_TRY(S.seg.reserve(size_t(n_chunks) * 16));
-    PCOB_CUDA_TRY(cudaMemcpyAsync(S.seg.p, eoff.data(), size_t(n_chunks) * 8, cudaMemcpyHostToDevice, stream));
-    IndexHeader ih;
-    std::memset(&ih, 0, sizeof(ih));
-    ih.magic = INDEX_MAGIC; ih.version = 1; ih.n_chunks = n_chunks; ih.n_total = n; ih.chunks_offset = chunks_offset;  // file_len, end_byte: emit_index_kernel
-    PCOB_CUDA_TRY(cudaMemcpyAsync(idx.p, &ih, sizeof(ih), cudaMemcpyHostToDevice, stream));
-    emit_index_kernel<<<n_chunks, 256, 0, stream>>>(ep, bpc, d_chunks, S.entries.as<BatchEntry>(), idx.as<uint8_t>(), chunks_offset, S.seg.as<uint64_t>(), d_total,
-                                                    chunks_only ? 0u : 1u);
-    PCOB_CUDA_TRY(cudaGetLastError());
-    PCOB_CUDA_TRY(cudaMemcpyAsync(index_dst, idx.p, off, (flags & PCO_B200_INDEX_ON_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, stream));
-    res->index_bytes = off;
+    index_total = off;
+    PCOB_CUDA_TRY(S.idx_out.reserve(off + 64));  // assembled on the device run by run, one copy out
   }
-  if (dst_dev) PCOB_CUDA_TRY(cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, stream));  // read back behind the kernels
-  PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
-  PCOB_CUDA_TRY(cudaGetLastError());
-  if (total > dst_cap) return fail(PCO_B200_IO, "failed to write whole buffer (need " + std::to_string(total) + " bytes, dst_cap " + std::to_string(dst_cap) + ")");
-  res->total_bytes = total;
+  uint64_t file_off = header.size();  // bytes of the file in front of the next run's first chunk
+  uint8_t* d_out = static_cast<uint8_t*>(dst);
+  for (size_t ri = 0; ri < runs.size(); ri++) {
+    const Run& run = runs[ri];
+    const bool first_run = ri == 0, last_run = ri + 1 == runs.size();
+    const uint32_t n_chunks = uint32_t(run.c1 - run.c0);
+    std::vector<uint64_t> rpages(pages.begin() + run.c0, pages.begin() + run.c1);
+    std::vector<uint64_t> rstarts(n_chunks + 1, 0), rrows(n_chunks + 1, 0);
+    uint64_t run_max_n = 0;
+    for (uint32_t i = 0; i < n_chunks; i++) {
+      rstarts[i + 1] = rstarts[i] + rpages[i];
+      rrows[i + 1] = rrows[i] + ((rpages[i] + BATCH_N - 1) / BATCH_N) * BATCH_N;
+      run_max_n = std::max(run_max_n, rpages[i]);
+    }
+    EncParams ep;
+    std::memset(&ep, 0, sizeof(ep));
+    ep.dtype = dtype;
+    ep.uniform_type = uniform_type ? dtype : 0;
+    ep.mode = run.ms.mode;
+    ep.mode_base = run.ms.mode_base;
+    ep.base_bits = run.ms.base_bits;
+    ep.inv_base_bits = run.ms.inv_base_bits;
+    ep.mode_k = run.ms.mode_k;
+    ep.order = run.order;
+    ep.n_vars = ep.mode == MODE_CLASSIC ? 1 : 2;
+    ep.n_total = rstarts.back();
+    ep.n_chunks = n_chunks;
+    ep.max_chunk_n = uint32_t(run_max_n);
+    ep.bins_log[0] = bins_log;
+    ep.bins_log[1] = std::min<uint32_t>(bins_log, 6);  // LIMITED_UNOPTIMIZED_BINS_LOG (chunk_compressor.rs:238-248)
+    ep.nums = static_cast<const L*>(d_nums) + starts[run.c0];
+    const uint32_t bpc = n_batches_of(uint32_t(run_max_n));
+    const uint32_t tiles_per_chunk = uint32_t((run_max_n + SPLIT_TILE - 1) / SPLIT_TILE);
+    const size_t n_slots = size_t(rrows.back());
+    PCOB_CUDA_TRY(S.sym0.reserve(n_slots + 64));
+    PCOB_CUDA_TRY(S.ans0.reserve(n_slots * 2 + 64));
+    if (ep.n_vars > 1) { PCOB_CUDA_TRY(S.sym1.reserve(n_slots + 64)); PCOB_CUDA_TRY(S.ans1.reserve(n_slots * 2 + 64)); }
+    const size_t n_cvb = size_t(n_chunks) * MAX_VARS * bpc;
+    PCOB_CUDA_TRY(S.ob_sum.reserve(n_cvb * 4));
+    PCOB_CUDA_TRY(S.ans_sum.reserve(n_cvb * 4));
+    PCOB_CUDA_TRY(S.entries.reserve(n_cvb * sizeof(BatchEntry)));
+    uint64_t* d_rstarts = S.starts.as<uint64_t>();
+    PCOB_CUDA_TRY(cudaMemcpyAsync(d_rstarts, rstarts.data(), rstarts.size() * 8, cudaMemcpyHostToDevice, stream));
+    PCOB_CUDA_TRY(cudaMemcpyAsync(d_rstarts + rstarts.size(), rrows.data(), rrows.size() * 8, cudaMemcpyHostToDevice, stream));
+    ep.chunk_starts = d_rstarts;
+    ep.row_base = d_rstarts + rstarts.size();
+    uint8_t* d_sym[2] = {S.sym0.as<uint8_t>(), S.sym1.as<uint8_t>()};
+    uint16_t* d_ans[2] = {S.ans0.as<uint16_t>(), S.ans1.as<uint16_t>()};
+    PCOB_CUDA_TRY(cudaMemsetAsync(S.ob_sum.p, 0, n_cvb * 4, stream));
+    uint32_t var_range_bits[MAX_VARS] = {64, 64};
+    if (PcoB200Error e = front(ep, tiles_per_chunk, n_slots, var_range_bits, rpages, shared_bins)) return e;
+    fallback_kernel<<<(n_chunks + 255) / 256, 256, 0, stream>>>(ep, d_plans, d_chunks, shared_bins ? n_chunks : 0u);
+    // ---- K3, K4
+    const uint32_t groups_per_chunk = (bpc + 7) / 8;
+    for (uint32_t v = 0; v < ep.n_vars; v++) {
+      if (var_range_bits[v] <= PLAN_MAX_COUNT_BITS) {
+        const uint32_t parts = (bpc + BINL_BATCHES - 1) / BINL_BATCHES;
+        profiler().begin("bin_lut_kernel", stream);
+        bin_lut_kernel<L><<<n_chunks * parts, BINL_THREADS, (size_t(1) << var_range_bits[v]) + 16, stream>>>(ep, bpc, parts, (v == 0 ? S.key16_0 : S.key16_1).as<uint16_t>(), d_plans, d_chunks, d_sym[v],
+                                                                                                             S.ob_sum.as<uint32_t>(), int(v), var_range_bits[v]);
+        profiler().end(stream);
+        continue;
+      }
+      profiler().begin("bin_kernel", stream);
+      bin_kernel<L><<<n_chunks * groups_per_chunk, BIN_THREADS, 0, stream>>>(ep, bpc, d_lat[v], d_plans, d_chunks, d_sym[v], S.ob_sum.as<uint32_t>(), int(v));
+      profiler().end(stream);
+    }
+    // the ans kernel indexes (chunk, var) by blockIdx; both vars share the launch via separate symbol arrays
+    profiler().begin("ans_encode_kernel", stream);
+    ans_encode_kernel<<<n_chunks * MAX_VARS, ANS_THREADS, 0, stream>>>(ep, bpc, d_plans, d_chunks, d_sym[0], d_sym[1], d_ans[0], d_ans[1], S.ans_sum.as<uint32_t>(),
+                                                                       S.entries.as<BatchEntry>());
+    profiler().end(stream);
+    // ---- layout, offsets, K5
+    profiler().begin("layout_kernel", stream);
+    layout_kernel<<<n_chunks, LAYOUT_THREADS, 0, stream>>>(ep, bpc, d_plans, d_chunks, S.ans_sum.as<uint32_t>(), S.ob_sum.as<uint32_t>(), S.entries.as<BatchEntry>());
+    profiler().end(stream);
+    const uint32_t footer = (last_run && !chunks_only) ? 1u : 0u;
+    chunk_offsets_kernel<<<1, 1024, 0, stream>>>(d_chunks, n_chunks, file_off, footer, d_total);
+    uint64_t total = 0;
+    const bool need_total_now = !dst_dev || !last_run;  // a host destination is staged (sized from the file size); a later run starts where this one ends
+    if (need_total_now) {
+      PCOB_CUDA_TRY(cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, stream));
+      PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
+      PCOB_CUDA_TRY(cudaGetLastError());
+      if (total > dst_cap) return fail(PCO_B200_IO, "failed to write whole buffer (need " + std::to_string(total) + " bytes, dst_cap " + std::to_string(dst_cap) + ")");
+    }
+    if (!dst_dev) {
+      PCOB_CUDA_TRY(S.out.reserve(total - (first_run ? 0 : file_off) + 64));
+      // the run's bytes are staged at their file offsets relative to the run's first byte (the header belongs to the first run)
+      d_out = S.out.as<uint8_t>() - (first_run ? 0 : file_off);
+    }
+    // device destination: no host round trip for the last run - pack_kernel leaves out any chunk that would not fit dst_cap, and the size
+    // is checked when it is read back behind the kernel
+    const uint64_t out_cap = dst_dev ? uint64_t(dst_cap) : total;
+    profiler().begin("pack_kernel", stream);
+    pack_kernel<L><<<n_chunks, PACK_THREADS, sizeof(PackSmem), stream>>>(ep, bpc, d_lat[0], d_lat[1], d_plans, d_chunks, d_sym[0], d_sym[1], d_ans[0], d_ans[1],
+                                                                        S.entries.as<BatchEntry>(), d_out, out_cap,
+                                                                        var_range_bits[0] <= PLAN_MAX_COUNT_BITS ? S.key16_0.as<uint16_t>() : nullptr,
+                                                                        (ep.n_vars > 1 && var_range_bits[1] <= PLAN_MAX_COUNT_BITS) ? S.key16_1.as<uint16_t>() : nullptr);
+    profiler().end(stream);
+    if (!chunks_only && (first_run || last_run)) {
+      if (runs.size() == 1) header_footer_kernel<<<1, 32, 0, stream>>>(d_out, out_cap, d_header, uint32_t(header.size()), d_total);
+      else run_edge_kernel<<<1, 32, 0, stream>>>(d_out, out_cap, d_header, first_run ? uint32_t(header.size()) : 0u, d_total, last_run ? 1u : 0u);
+    }
+    PCOB_CUDA_TRY(cudaGetLastError());
+    if (!dst_dev) {
+      const uint64_t from = first_run ? 0 : file_off;
+      PCOB_CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t*>(dst) + from, d_out + from, total - from, cudaMemcpyDeviceToHost, stream));
+    }
+    // ---- this run's piece of the side index
+    if (index_dst != nullptr) {
+      DevBuf& idx = S.idx_out;
+      PCOB_CUDA_TRY(S.seg.reserve(size_t(n_chunks) * 16));
+      PCOB_CUDA_TRY(cudaMemcpyAsync(S.seg.p, eoff.data() + run.c0, size_t(n_chunks) * 8, cudaMemcpyHostToDevice, stream));
+      if (first_run) {
+        IndexHeader ih;
+        std::memset(&ih, 0, sizeof(ih));
+        ih.magic = INDEX_MAGIC; ih.version = 1; ih.n_chunks = n_chunks_all; ih.n_total = n; ih.chunks_offset = chunks_offset;  // file_len, end_byte: emit_index_kernel
+        PCOB_CUDA_TRY(cudaMemcpyAsync(idx.p, &ih, sizeof(ih), cudaMemcpyHostToDevice, stream));
+      }
+      emit_index_kernel<<<n_chunks, 256, 0, stream>>>(ep, bpc, d_chunks, S.entries.as<BatchEntry>(), idx.as<uint8_t>(), chunks_offset, S.seg.as<uint64_t>(), d_total,
+                                                      chunks_only ? 0u : 1u, uint32_t(run.c0), starts[run.c0], last_run ? 1u : 0u);
+      PCOB_CUDA_TRY(cudaGetLastError());
+    }
+    if (!last_run || !dst_dev) {
+      // the scratch is reused by the next run, and a host destination must be complete before the call returns
+      PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
+      PCOB_CUDA_TRY(cudaGetLastError());
+      file_off = total - footer;
+      res->total_bytes = total;
+    } else {
+      PCOB_CUDA_TRY(cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, stream));  // read back behind the kernels
+      if (index_dst != nullptr)
+        PCOB_CUDA_TRY(cudaMemcpyAsync(index_dst, S.idx_out.p, index_total, (flags & PCO_B200_INDEX_ON_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, stream));
+      PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
+      PCOB_CUDA_TRY(cudaGetLastError());
+      if (total > dst_cap) return fail(PCO_B200_IO, "failed to write whole buffer (need " + std::to_string(total) + " bytes, dst_cap " + std::to_string(dst_cap) + ")");
+      res->total_bytes = total;
+      res->index_bytes = index_total;
+      return PCO_B200_OK;
+    }
+  }
+  if (index_dst != nullptr) {
+    PCOB_CUDA_TRY(cudaMemcpyAsync(index_dst, S.idx_out.p, index_total, (flags & PCO_B200_INDEX_ON_DEVICE) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, stream));
+    PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
+    res->index_bytes = index_total;
+  }
   return PCO_B200_OK;
 }
 

@@ -71,7 +71,14 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
   asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok != 0;
 }
+#ifndef PCOB_FZ_WAIT_NS
+#define PCOB_FZ_WAIT_NS 0
+#endif
+// A waiting warp must not eat the issue slots of the warps it waits for: between two failed tries it sleeps (PCOB_FZ_WAIT_NS > 0).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#if PCOB_FZ_WAIT_NS > 0
+  while (!mbar_test(bar, parity)) __nanosleep(PCOB_FZ_WAIT_NS);
+#else
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "WAIT_LOOP:\n\t"
@@ -79,6 +86,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "@p bra.uni WAIT_DONE;\n\t"
       "bra.uni WAIT_LOOP;\n\t"
       "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+#endif
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");

@@ -218,90 +218,6 @@ __device__ void build_var_tables(const BitSrc& src, ChunkHdr& hdr, int v, uint32
   __syncthreads();
 }
 
-// ---------------------------------------------------------------------------
-// tANS symbol walk of one batch by ONE thread (page_latent_decompressor.rs:89-177).
-//   cw   : aligned words of the file; bit: absolute bit position; max_word: last readable word index
-//   Returns the bit position after the batch's ANS section and (WALKER) the sum of offset bits.
-// ---------------------------------------------------------------------------
-struct WalkState {
-  uint32_t st[4];
-};
-
-template <bool WALKER>
-__device__ __forceinline__ uint64_t ans_walk_batch(const uint64_t* __restrict__ cw, uint64_t max_word, uint64_t bit, WalkState& ws,
-                                                   const uint32_t* __restrict__ node, int count, uint32_t* __restrict__ sym_row,
-                                                   uint32_t& ob_sum) {
-  // The stream is read as 16-byte blocks (two u64 words): the current block and the next one live in registers, the
-  // next one having been requested a whole block (~3 iterations) before its first use.  One 16-byte load per 128 bits
-  // halves the L1 wavefronts of these per-thread scattered reads compared with 8-byte refills.
-  auto ld = [&](uint64_t i) -> uint64_t { return __ldg(cw + (i <= max_word ? i : max_word)); };
-  const uint64_t max_blk = max_word >> 1;
-  auto ldb = [&](uint64_t bidx) -> ulonglong2 {
-    return __ldg(reinterpret_cast<const ulonglong2*>(cw) + (bidx <= max_blk ? bidx : max_blk));
-  };
-  uint64_t blk = bit >> 7;
-  uint32_t pb = uint32_t(bit & 127);
-  ulonglong2 cb = ldb(blk), nb = ldb(blk + 1), nb2 = ldb(blk + 2);
-  uint32_t s0 = ws.st[0], s1 = ws.st[1], s2 = ws.st[2], s3 = ws.st[3];
-  uint32_t obs = 0;
-  int i = 0;
-  for (; i + 4 <= count; i += 4) {
-    uint32_t n0 = node[s0], n1 = node[s1], n2 = node[s2], n3 = node[s3];
-    const bool upper = pb >= 64;
-    const uint64_t lo = upper ? cb.y : cb.x, hi = upper ? nb.x : cb.y;
-    const uint32_t r = pb & 63;
-    uint64_t g = r ? ((lo >> r) | (hi << (64 - r))) : lo;
-    uint32_t b0 = node_btr(n0), b1 = node_btr(n1), b2 = node_btr(n2), b3 = node_btr(n3);
-    uint32_t sh1 = b0, sh2 = b0 + b1, sh3 = sh2 + b2, tot = sh3 + b3;
-    uint32_t v0 = uint32_t(g) & ((1u << b0) - 1);
-    uint32_t v1 = uint32_t(g >> sh1) & ((1u << b1) - 1);
-    uint32_t v2 = uint32_t(g >> sh2) & ((1u << b2) - 1);
-    uint32_t v3 = uint32_t(g >> sh3) & ((1u << b3) - 1);
-    if (WALKER) {
-      obs += node_field(n0) + node_field(n1) + node_field(n2) + node_field(n3);
-    } else {
-      sym_row[i >> 2] = node_field(n0) | (node_field(n1) << 8) | (node_field(n2) << 16) | (node_field(n3) << 24);
-    }
-    s0 = node_base(n0) + v0;
-    s1 = node_base(n1) + v1;
-    s2 = node_base(n2) + v2;
-    s3 = node_base(n3) + v3;
-    pb += tot;
-    if (pb >= 128) {
-      pb -= 128;
-      blk += 1;
-      cb = nb;
-      nb = nb2;
-      nb2 = ldb(blk + 2);  // two blocks (~6 iterations) ahead of its first use
-      if ((blk & 7) == 0) {  // entering a new 128-byte line: pull the line after next into L2
-        const uint64_t pblk = blk + 16 <= max_blk ? blk + 16 : max_blk;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const ulonglong2*>(cw) + pblk));
-      }
-    }
-  }
-  bit = (blk << 7) + pb;
-  if (i < count) {  // ragged tail of the page's last batch (page_latent_decompressor.rs:144-177)
-    uint32_t packed = 0;
-    uint32_t sarr[4] = {s0, s1, s2, s3};
-    for (int j = 0; i + j < count; j++) {
-      uint32_t n = node[sarr[j]];
-      uint32_t r = uint32_t(bit & 63);
-      uint64_t lo = ld(bit >> 6), hi = ld((bit >> 6) + 1);
-      uint64_t g = r ? ((lo >> r) | (hi << (64 - r))) : lo;
-      uint32_t b = node_btr(n);
-      uint32_t v = uint32_t(g) & ((1u << b) - 1);
-      if (WALKER) obs += node_field(n); else packed |= node_field(n) << (8 * j);
-      sarr[j] = node_base(n) + v;
-      bit += b;
-    }
-    if (!WALKER) sym_row[i >> 2] = packed;
-    s0 = sarr[0]; s1 = sarr[1]; s2 = sarr[2]; s3 = sarr[3];
-  }
-  ws.st[0] = s0; ws.st[1] = s1; ws.st[2] = s2; ws.st[3] = s3;
-  ob_sum = obs;
-  return bit;
-}
-
 struct FileParams {
   const void* src;
   uint64_t src_len;
@@ -318,6 +234,9 @@ struct FileParams {
 //   serial_file_mode = 0: one CTA per pre-filled IndexChunk (offsets, n and entries_offset known).
 // Layout written: index_base + chunks_offset : IndexChunk[]; entries at index_base + entries_offset.
 // ---------------------------------------------------------------------------
+constexpr int WR_BLOCKS = 128;  // ring: 128 blocks of 16 bytes
+constexpr int WR_AHEAD = 64;    // blocks kept requested ahead of the cursor
+constexpr int WR_STEP = 8;      // blocks per cp.async group
 template <int CAP_LOG>   // 12: any table the format allows on this path; 10: what the decode kernels take (4x less shared memory)
 struct WalkSmem {
   ChunkHdr hdr;
@@ -330,6 +249,7 @@ struct WalkSmem {
   uint32_t err;
   uint64_t next_chunk_byte;
   uint32_t status;
+  alignas(16) uint32_t ring[WR_BLOCKS * 4];  // the walking thread's window on the stream (WalkRing)
 };
 
 struct WalkResult {     // written by the serial walker
@@ -342,37 +262,140 @@ struct WalkResult {     // written by the serial walker
 
 __host__ __device__ inline uint32_t n_batches_of(uint32_t n) { return (n + BATCH_N - 1) / BATCH_N; }
 
-// Walk one chunk whose header is already parsed and tables built (WALKER nodes). One thread: splitting the 4 interleaved
-// chains over 4 lanes (one lookup + a two-shuffle prefix of the bit counts per step) was measured SLOWER - 17.0 ms against
-// 14.0 ms for 1024 chunks - the shuffles sit on the serial cursor dependency.
-template <int CAP_LOG>
-__device__ inline uint32_t walk_chunk_serial(const BitSrc& src, const ChunkHdr& hdr, const uint32_t (*node)[1 << CAP_LOG], uint64_t chunk_bit0,
-                                             BatchEntry* entries, uint64_t* end_bit_out) {
-  const uint64_t max_word = src.n_bits == 0 ? 0 : (src.n_bits - 1) >> 6;
-  const uint32_t nb = n_batches_of(hdr.n);
-  uint64_t bit = hdr.body_bit;
-  WalkState ws[MAX_VARS];
-  for (uint32_t v = 0; v < hdr.n_vars; v++)
-    for (int j = 0; j < 4; j++) ws[v].st[j] = hdr.init_state[v][j];
-  for (uint32_t b = 0; b < nb; b++) {
-    for (uint32_t v = 0; v < hdr.n_vars; v++) {
-      const VarHdr& vh = hdr.var[v];
-      uint32_t cnt = batch_count(var_stored_n(hdr.n, vh.delta_order), b);
-      BatchEntry e;
-      e.bit_pos = uint32_t(bit - chunk_bit0);
-      for (int j = 0; j < 4; j++) e.st[j] = uint16_t(ws[v].st[j]);
-      entries[size_t(v) * nb + b] = e;
-      if (cnt == 0) continue;
-      uint32_t obs;
-      if (vh.n_bins > 1) {
-        bit = ans_walk_batch<true>(src.words, max_word, bit, ws[v], node[v], int(cnt), nullptr, obs);
-      } else {
-        obs = cnt * node_field(node[v][0]);
+// Walk one chunk whose header is already parsed and tables built (WALKER nodes: the field byte is the bin's offset_bits), by ONE
+// thread: the chunk's bit cursor is a single serial chain (batch boundaries are not in the stream: a batch's offsets section is as long
+// as the sum of the offset bits of the symbols just walked, page_latent_decompressor.rs:106-134).  What the chain costs per group of 4
+// symbols is its latency, so the loop is kept to the chain: the four node lookups go out together (32-bit shared addresses, states held
+// as byte offsets), the stream is read from a shared-memory ring that cp.async fills ~1 KB ahead of the cursor (no global load and no
+// 64-bit address arithmetic inside the chain), the four offset_bits bytes are summed with one dot product, and nothing lives in local
+// memory (the states of the two latent vars are separate registers).  Splitting the 4 interleaved chains over 4 lanes (one lookup + a
+// two-shuffle prefix of the bit counts per step) was measured SLOWER than one thread - the shuffles sit on the cursor dependency.
+
+struct WalkRing {
+  uint32_t ring_sa;                 // shared address of the ring
+  const ulonglong2* blocks;         // the file as 16-byte blocks
+  uint64_t max_blk;                 // last readable block
+  uint64_t base_blk;                // block the relative bit positions count from
+  uint64_t fetched;                 // blocks [.., fetched) have been requested (absolute block index, multiple of WR_STEP)
+  __device__ __forceinline__ void request_upto(uint64_t upto) {
+    while (fetched < upto) {
+#pragma unroll
+      for (int q = 0; q < WR_STEP; q++) {
+        const uint64_t bi = fetched + q;
+        const void* gp = blocks + (bi <= max_blk ? bi : max_blk);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring_sa + uint32_t(bi % WR_BLOCKS) * 16u), "l"(gp));
       }
-      bit += obs;
-      if (bit > src.n_bits) return ST_INSUFFICIENT_DATA;
+      asm volatile("cp.async.commit_group;");
+      fetched += WR_STEP;
     }
   }
+  // the cursor is at relative bit `rbit`: keep WR_AHEAD blocks requested ahead of it and make the blocks it can touch next readable
+  __device__ __forceinline__ void advance(uint32_t rbit) {
+    const uint64_t cur = base_blk + (rbit >> 7);
+    if (cur + 8 > fetched || fetched == 0) {  // first use, or a jump past what was requested (a long offsets section): start over at the cursor
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      fetched = cur & ~uint64_t(WR_STEP - 1);
+      request_upto(fetched + WR_AHEAD + WR_STEP);
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      return;
+    }
+    request_upto(((cur + WR_AHEAD) & ~uint64_t(WR_STEP - 1)) + WR_STEP);
+    // fetched >= cur + WR_AHEAD + 1; all but the 6 newest groups (48 blocks) are complete: blocks < cur + 17 are in the ring
+    asm volatile("cp.async.wait_group 6;" ::: "memory");
+  }
+  __device__ __forceinline__ uint32_t word(uint32_t rel_word) const {  // 32-bit word `rel_word` counted from base_blk
+    return lds_u32(ring_sa + (((uint32_t(base_blk & (WR_BLOCKS - 1)) << 2) + rel_word) & (WR_BLOCKS * 4 - 1)) * 4u);
+  }
+};
+
+template <int CAP_LOG>
+__device__ inline uint32_t walk_chunk_serial(const BitSrc& src, const ChunkHdr& hdr, const uint32_t (*node)[1 << CAP_LOG], uint64_t chunk_bit0,
+                                             BatchEntry* entries, uint64_t* end_bit_out, uint32_t ring_sa) {
+  const uint32_t nb = n_batches_of(hdr.n);
+  WalkRing ring;
+  ring.ring_sa = ring_sa;
+  ring.blocks = reinterpret_cast<const ulonglong2*>(src.words);
+  ring.max_blk = (src.n_bits == 0 ? 0 : (src.n_bits - 1) >> 6) >> 1;
+  ring.base_blk = chunk_bit0 >> 7;
+  ring.fetched = 0;
+  const uint64_t base_bit = ring.base_blk << 7;
+  // relative positions fit 32 bits: a chunk holds <= 2^24 numbers of <= 14 + 64 bits
+  if (hdr.body_bit - base_bit > 0xffffffffull) return ST_CORRUPTION;
+  uint32_t rbit = uint32_t(hdr.body_bit - base_bit);
+  const uint64_t limit64 = src.n_bits - base_bit;
+  const uint32_t limit = limit64 > 0xffffffffull ? 0xffffffffu : uint32_t(limit64);
+  const uint32_t nv = hdr.n_vars;
+  // states as byte offsets into the var's node table
+  uint32_t a0 = hdr.init_state[0][0] << 2, a1 = hdr.init_state[0][1] << 2, a2 = hdr.init_state[0][2] << 2, a3 = hdr.init_state[0][3] << 2;
+  uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+  if (nv > 1) { b0 = hdr.init_state[1][0] << 2; b1 = hdr.init_state[1][1] << 2; b2 = hdr.init_state[1][2] << 2; b3 = hdr.init_state[1][3] << 2; }
+  const uint32_t node_sa0 = smem_addr(node[0]), node_sa1 = smem_addr(node[nv > 1 ? 1 : 0]);
+  const uint32_t stored0 = var_stored_n(hdr.n, hdr.var[0].delta_order), stored1 = nv > 1 ? var_stored_n(hdr.n, hdr.var[1].delta_order) : 0;
+  const uint32_t nbins0 = hdr.var[0].n_bins, nbins1 = nv > 1 ? hdr.var[1].n_bins : 0;
+  const uint32_t chunk_rel = uint32_t(chunk_bit0 - base_bit);  // entries count bits from the chunk's type byte
+  ring.advance(rbit);
+  for (uint32_t b = 0; b < nb; b++) {
+#pragma unroll
+    for (uint32_t v = 0; v < 2; v++) {
+      if (v >= nv) break;
+      const uint32_t cnt = batch_count(v == 0 ? stored0 : stored1, b);
+      uint32_t s0 = v == 0 ? a0 : b0, s1 = v == 0 ? a1 : b1, s2 = v == 0 ? a2 : b2, s3 = v == 0 ? a3 : b3;
+      BatchEntry e;
+      e.bit_pos = rbit - chunk_rel;
+      e.st[0] = uint16_t(s0 >> 2); e.st[1] = uint16_t(s1 >> 2); e.st[2] = uint16_t(s2 >> 2); e.st[3] = uint16_t(s3 >> 2);
+      entries[size_t(v) * nb + b] = e;
+      if (cnt == 0) continue;
+      const uint32_t node_sa = v == 0 ? node_sa0 : node_sa1;
+      uint32_t obs = 0;
+      if ((v == 0 ? nbins0 : nbins1) > 1) {
+        uint32_t w = rbit >> 5;
+        uint32_t x0 = ring.word(w), x1 = ring.word(w + 1), x2 = ring.word(w + 2);
+        uint32_t kblk = rbit >> 10;  // 8-block (1024-bit) region of the cursor: the ring is topped up when it changes
+        uint32_t i = 0;
+        for (; i + 4 <= cnt; i += 4) {
+          const uint32_t n0 = lds_u32(node_sa + s0), n1 = lds_u32(node_sa + s1), n2 = lds_u32(node_sa + s2), n3 = lds_u32(node_sa + s3);
+          const uint32_t r = rbit & 31;
+          const uint64_t g = (uint64_t(__funnelshift_r(x1, x2, r)) << 32) | __funnelshift_r(x0, x1, r);
+          const uint32_t c0 = node_btr(n0), c1 = node_btr(n1), c2 = node_btr(n2), c3 = node_btr(n3);
+          const uint32_t sh2 = c0 + c1, sh3 = sh2 + c2;
+          s0 = (node_base(n0) + (uint32_t(g) & ((1u << c0) - 1))) << 2;
+          s1 = (node_base(n1) + (uint32_t(g >> c0) & ((1u << c1) - 1))) << 2;
+          s2 = (node_base(n2) + (uint32_t(g >> sh2) & ((1u << c2) - 1))) << 2;
+          s3 = (node_base(n3) + (uint32_t(g >> sh3) & ((1u << c3) - 1))) << 2;
+          obs = __dp4a(node_fields4(n0, n1, n2, n3), 0x01010101u, obs);
+          rbit += sh3 + c3;
+          if ((rbit >> 5) != w) {
+            if ((rbit >> 10) != kblk) { kblk = rbit >> 10; ring.advance(rbit); }
+            w = rbit >> 5;
+            x0 = ring.word(w); x1 = ring.word(w + 1); x2 = ring.word(w + 2);
+          }
+        }
+        // ragged tail of the page's last batch (page_latent_decompressor.rs:144-177)
+        auto tail_step = [&](uint32_t& sj) {
+          const uint32_t nn = lds_u32(node_sa + sj);
+          const uint32_t ww = rbit >> 5, r = rbit & 31;
+          const uint32_t val = __funnelshift_r(ring.word(ww), ring.word(ww + 1), r) & ((1u << node_btr(nn)) - 1);
+          obs += node_field(nn);
+          sj = (node_base(nn) + val) << 2;
+          rbit += node_btr(nn);
+        };
+        if (i < cnt) tail_step(s0);
+        if (i + 1 < cnt) tail_step(s1);
+        if (i + 2 < cnt) tail_step(s2);
+      } else {
+        obs = cnt * node_field(lds_u32(node_sa));
+      }
+      if (v == 0) { a0 = s0; a1 = s1; a2 = s2; a3 = s3; } else { b0 = s0; b1 = s1; b2 = s2; b3 = s3; }
+      // the offsets section: obs bits (<= 256 x 64)
+      if (obs > limit - min(rbit, limit)) return ST_INSUFFICIENT_DATA;
+      rbit += obs;
+      if (rbit > limit) return ST_INSUFFICIENT_DATA;
+      if (rbit > 0xfff00000u) return ST_CORRUPTION;  // cannot happen for a chunk of <= 2^24 numbers
+      ring.advance(rbit);
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  uint64_t bit = base_bit + rbit;
   // trailing bits of the page must be zero (wrapped/page_decompressor.rs:184-188)
   uint32_t pad = uint32_t((8 - (bit & 7)) & 7);
   if (pad && read_bits_safe(src, bit, pad) != 0) return ST_CORRUPTION;
@@ -429,7 +452,7 @@ __global__ void __launch_bounds__(128) walk_kernel(FileParams fp, uint8_t* index
         if (eo + need > entries_cap_end) {
           st = ST_INDEX_FULL;
         } else {
-          st = walk_chunk_serial<CAP_LOG>(src, sm.hdr, sm.node, chunk_bit0, reinterpret_cast<BatchEntry*>(index_base + eo), &end_bit);
+          st = walk_chunk_serial<CAP_LOG>(src, sm.hdr, sm.node, chunk_bit0, reinterpret_cast<BatchEntry*>(index_base + eo), &end_bit, smem_addr(sm.ring));
           if (st == ST_OK) {
             IndexChunk ic;
             ic.chunk_offset = chunk_byte;

@@ -1128,8 +1128,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS) plan_solve_kernel(EncParams ep,
 // DeltaSpec::Auto on the GPU path: the reference (chunk_compressor.rs:310-360) trial-compresses a sample of each chunk -
 // groups of 200 consecutive numbers at a regular stride (sampling.rs:21-60) - with consecutive orders 1, 2, ... until the
 // estimated size stops shrinking (and with Lookback, which this path does not encode).  Here the same sample of every
-// chunk is gathered into a side array, the ordinary split/delta + planner kernels run on it per order, and
-// auto_cost_kernel adds up the estimated sizes; one order is chosen for the whole call.
+// chunk's PRIMARY latents is gathered into a side array (gather_primary_sample_kernel, compress_host.cuh), the ordinary split/delta +
+// planner kernels run on it per order, and the host evaluates the reference's f32 size formula per chunk (sample_cost): every chunk gets its
+// own order.
 // ---------------------------------------------------------------------------
 struct SampleGeom { uint32_t group_n, n_groups, stride; };
 __host__ __device__ inline SampleGeom delta_sample_geom(uint64_t n) {
@@ -1142,29 +1143,6 @@ __host__ __device__ inline SampleGeom delta_sample_geom(uint64_t n) {
   const uint64_t spare = n > nominal ? n - nominal : 0;
   g.stride = uint32_t(g.group_n + spare / ((g.n_groups > 2 ? g.n_groups : 2) - 1));
   return g;
-}
-
-template <typename L>
-__global__ void gather_sample_kernel(const L* __restrict__ nums, const uint64_t* __restrict__ chunk_starts, const uint64_t* __restrict__ sample_starts,
-                                     L* __restrict__ sample) {
-  const uint32_t c = blockIdx.x;
-  const uint64_t cs = chunk_starts[c], n = chunk_starts[c + 1] - cs;
-  const SampleGeom g = delta_sample_geom(n);
-  const uint32_t ns = g.n_groups * g.group_n;
-  L* dst = sample + sample_starts[c];
-  for (uint32_t i = threadIdx.x; i < ns; i += blockDim.x) dst[i] = nums[cs + uint64_t(i / g.group_n) * g.stride + i % g.group_n];
-}
-
-// estimated compressed bits of the sampled chunks at the delta order the plans were trained with
-__global__ void auto_cost_kernel(EncParams ep, const VarPlan* __restrict__ plans, unsigned long long* __restrict__ cost) {
-  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= ep.n_chunks) return;
-  if (ep.chunk_starts[c + 1] == ep.chunk_starts[c]) return;
-  const uint32_t lbits = nt_bits(ep.dtype);
-  const VarPlan& p = plans[size_t(c) * MAX_VARS];
-  const uint32_t stride = p.size_log + lbits + offset_bits_bits(lbits);
-  const unsigned long long bits = 4 + 15 + uint64_t(p.n_bins) * stride + uint64_t(ep.order) * lbits + 4 * p.size_log + p.est_bits;
-  atomicAdd(cost, bits);
 }
 
 // ---------------------------------------------------------------------------

@@ -440,12 +440,13 @@ inline bool float_quant_bid(const std::vector<F>& sample, uint32_t* k_out, doubl
   return true;
 }
 
+// `sample_bits`: the chunk's numbers at sample_positions(n), in visiting order, as raw bits (e.g. gathered on the device)
 template <typename F>
-inline Choice choose_float(const typename Fl<F>::L* num_bits, size_t n) {
+inline Choice choose_float_from_sample(const typename Fl<F>::L* sample_bits, size_t m) {
   Choice best;
   std::vector<F> sample;
-  for (size_t i : sample_positions(n)) {  // data_types/float.rs:70-80: normal, not huge, by magnitude
-    const F x = from_bits<F>(num_bits[i]);
+  for (size_t j = 0; j < m; j++) {  // data_types/float.rs:70-80: normal, not huge, by magnitude
+    const F x = from_bits<F>(sample_bits[j]);
     if (Fl<F>::normal(x) && Fl<F>::abs_(x) <= Fl<F>::sample_cap()) sample.push_back(Fl<F>::abs_(x));
   }
   if (sample.size() < MIN_SAMPLE) return best;
@@ -467,20 +468,33 @@ inline Choice choose_float(const typename Fl<F>::L* num_bits, size_t n) {
   }
   return best;
 }
+template <typename F>
+inline Choice choose_float(const typename Fl<F>::L* num_bits, size_t n) {
+  std::vector<typename Fl<F>::L> picked;
+  for (size_t i : sample_positions(n)) picked.push_back(num_bits[i]);
+  return choose_float_from_sample<F>(picked.data(), picked.size());
+}
 
-// nums: the chunk's numbers as raw bits of width L; is_signed / is_float say how they order (to_latent_ordered)
+// `sample_bits`: the chunk's numbers at sample_positions(n) as raw bits of width L; is_signed says how they order (to_latent_ordered)
 template <typename L>
-inline Choice choose_int(const L* nums, size_t n, bool is_signed) {
+inline Choice choose_int_from_sample(const L* sample_bits, size_t m, bool is_signed) {
   Choice best;
   std::vector<L> sample;
   const L mid = L(L(1) << (8 * sizeof(L) - 1));
-  for (size_t i : sample_positions(n)) sample.push_back(is_signed ? L(nums[i] ^ mid) : nums[i]);
+  for (size_t j = 0; j < m; j++) sample.push_back(is_signed ? L(sample_bits[j] ^ mid) : sample_bits[j]);
   L base;
   if (sample.size() >= MIN_SAMPLE && int_mult_base<L>(sample, &base)) {
     best.kind = 1;
     best.int_base = uint64_t(base);
   }
   return best;
+}
+// nums: the chunk's numbers as raw bits of width L
+template <typename L>
+inline Choice choose_int(const L* nums, size_t n, bool is_signed) {
+  std::vector<L> picked;
+  for (size_t i : sample_positions(n)) picked.push_back(nums[i]);
+  return choose_int_from_sample<L>(picked.data(), picked.size(), is_signed);
 }
 
 }  // namespace mode_search
