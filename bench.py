@@ -39,6 +39,7 @@ def parse_args():
     ap.add_argument("--chunks", type=int, default=N_CHUNKS, help="chunks per rank (default: BASELINE config 2)")
     ap.add_argument("--cpu-sample-chunks", type=int, default=1024, help="chunks of the CPU arm per step, spread over one worker process per host thread (about 12 s of core time)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--abi3-chunks", type=int, default=32, help="chunks of the three-function-ABI leg (its index-free decompress walks the chunks one after the other)")
     ap.add_argument("--e2e-groups", type=int, default=8, help="chunk groups the streamed e2e leg cuts the array into")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-index-free", action="store_true", help="skip the pco_b200_decompress_chunks timing (not part of `value`)")
@@ -620,6 +621,38 @@ def run_gpu_arm(args, rank, world):
                       "while another decompresses group g (per-thread library contexts, one stream each)",
                "single_call": {"value": world * U / 1e6 / (single_ms / 1e3), "ms_per_step": single_ms,
                                "api": "one pco_b200_compress_ex + one pco_b200_decompress_ex over the whole array (H2D, kernels, D2H back to back)"}}
+    # ---- the reference's own three-function C ABI, unmodified (pco_c/include/cpcodec_generated.h:33-64): default config (Auto mode, Auto
+    # delta, resolved per chunk), host buffers, no side index and no chunk offsets - the decompressor has to find every chunk boundary by
+    # walking the stream (chunk lengths are not in the format), one chunk after the other.  A bounded sample of the workload.
+    abi3 = None
+    if not args.no_e2e and rank == 0:
+        try:
+            k3 = max(1, min(args.abi3_chunks, n_chunks))
+            n3 = k3 * CHUNK_N
+            src3 = h_np[:n3]
+            cap3 = L.pco_standalone_guarantee_file_size(n3, 2)
+            dst3 = np.empty(cap3, dtype=np.uint8)
+            out3 = np.empty(n3, dtype=np.uint64)
+            nw3, nd3 = C.c_size_t(), C.c_size_t()
+
+            def abi3_step():
+                rc = L.pco_standalone_simple_compress_into(src3.ctypes.data_as(C.c_void_p), C.c_size_t(n3), C.c_ubyte(2), None, dst3.ctypes.data_as(C.c_void_p), C.c_size_t(cap3), C.byref(nw3))
+                assert rc == 0, f"pco_standalone_simple_compress_into: {rc}"
+                t_mid = time.perf_counter()
+                rc = L.pco_standalone_simple_decompress_into(dst3.ctypes.data_as(C.c_void_p), nw3, C.c_ubyte(2), out3.ctypes.data_as(C.c_void_p), C.c_size_t(n3), C.byref(nd3))
+                assert rc == 0 and nd3.value == n3, f"pco_standalone_simple_decompress_into: {rc}"
+                return t_mid
+
+            abi3_step()
+            assert np.array_equal(out3, src3), "3-function ABI round trip is not bit-exact"
+            t0 = time.perf_counter()
+            t_mid = abi3_step()
+            t1 = time.perf_counter()
+            abi3 = {"value": n3 * 8 / 1e6 / (t1 - t0), "unit": "MB/s", "compress_mb_s": n3 * 8 / 1e6 / (t_mid - t0), "decompress_mb_s": n3 * 8 / 1e6 / (t1 - t_mid),
+                    "sample": f"{k3} chunks of 2^18 u64 in one standalone file, pageable host buffers, wall clock",
+                    "api": "pco_standalone_simple_compress_into(config = NULL) + pco_standalone_simple_decompress_into: the reference's C ABI as is"}
+        except Exception as ex:  # noqa: BLE001
+            abi3 = {"value": None, "error": f"{type(ex).__name__}: {ex}"}
     sampler.stop_flag = True
     if rank == 0:
         sampler.join(timeout=2)
@@ -691,7 +724,7 @@ def run_gpu_arm(args, rank, world):
                                   "what": "the whole pco_b200_compress_ex call: U read + C written"}},
         "parity": parity,
         "index_free_decompress": ({**chunks_free, "roofline": {**chunks_free["roofline"], "peak": peak, "frac": chunks_free["roofline"]["achieved"] / peak}} if chunks_free else None),
-        "cpu_baseline": cpu, "e2e": e2e, "clocks": sampler.summary(),
+        "cpu_baseline": cpu, "e2e": ({**e2e, "reference_abi": abi3} if e2e else e2e), "clocks": sampler.summary(),
         # per step (profiles/r01_l_launches.csv): compress = init_chunks, split_count, plan_solve, fallback, bin_lut, ans_encode,
         # layout, chunk_offsets, pack, header_footer, emit_index; decompress = symwalk_kernel + decode_narrow_kernel +
         # decode_kernel<L,1> + decode_kernel<L,2> (a chunk is decoded by exactly one of the three; the others' CTAs exit at once)

@@ -2,7 +2,6 @@
 // chunks, runs the encode kernels on one stream and returns the .pco bytes (+ optional side index).
 #pragma once
 #include <cstdlib>
-#include <cub/device/device_segmented_radix_sort.cuh>
 
 #include <atomic>
 #include <cmath>
@@ -26,10 +25,11 @@ constexpr uint32_t PCO_B200_INTERNAL_SHARED_BINS = 1u << 16;
 
 
 struct CompressScratch {
-  DevBuf lat0, lat1, keys_a, keys_b, sym0, sym1, ans0, ans1, ob_sum, ans_sum, entries, plans, chunks, starts, seg, cub_tmp, out, small, index, probes, sample, sample_starts, key16_0, key16_1, idx_out;
-  bool plan_attr_set = false, union_attr_set = false;
+  DevBuf lat0, lat1, keys_a, keys_b, sym0, sym1, ans0, ans1, ob_sum, ans_sum, entries, plans, chunks, starts, seg, out, small, index, probes, sample, sample_starts, key16_0, key16_1, idx_out;
+  // kernel attributes are per instantiation: one flag per latent width (index log2(sizeof(L)))
+  bool plan_attr_set[4] = {false, false, false, false}, union_attr_set[4] = {false, false, false, false}, sort_attr_set[4] = {false, false, false, false};
   void release() {
-    for (DevBuf* b : {&lat0, &lat1, &keys_a, &keys_b, &sym0, &sym1, &ans0, &ans1, &ob_sum, &ans_sum, &entries, &plans, &chunks, &starts, &seg, &cub_tmp, &out, &small,
+    for (DevBuf* b : {&lat0, &lat1, &keys_a, &keys_b, &sym0, &sym1, &ans0, &ans1, &ob_sum, &ans_sum, &entries, &plans, &chunks, &starts, &seg, &out, &small,
                       &index, &probes, &sample, &sample_starts, &key16_0, &key16_1, &idx_out})
       b->release();
   }
@@ -242,6 +242,7 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
                                    CompressResult* res) {
   const bool src_dev = flags & PCO_B200_SRC_ON_DEVICE, dst_dev = flags & PCO_B200_DST_ON_DEVICE;
   const uint32_t lbits = sizeof(L) * 8;
+  constexpr int LW = sizeof(L) == 1 ? 0 : sizeof(L) == 2 ? 1 : sizeof(L) == 4 ? 2 : 3;
   const bool is_float = nt_is_float(dtype);
   // ---- config validation (pco/src/chunk_config.rs:269-314)
   if (cfg.compression_level > 12) return fail(PCO_B200_INVALID_ARGUMENT, "compression level may not exceed 12");
@@ -358,6 +359,12 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
   // ---- K1+K2 and the planner for one set of chunks (a run of the call's chunks, or the chunks' samples during the Auto delta search).
   // `e` describes the set (its own chunk_starts / row_base, counted from 0); plans and probes land in slots 0 .. e.n_chunks - 1.
   L* d_lat[2] = {nullptr, nullptr};
+  constexpr size_t RS_SMEM = size_t(RS_WARPS) * RS_BINS * sizeof(uint32_t);
+  auto ensure_sort_attr = [&]() -> cudaError_t {
+    if (S.sort_attr_set[LW]) return cudaSuccess;
+    S.sort_attr_set[LW] = true;
+    return cudaFuncSetAttribute(radix_sort_segments_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM);
+  };
   auto front = [&](const EncParams& e, uint32_t tiles, size_t slots, uint32_t (&vrb)[MAX_VARS], const std::vector<uint64_t>& sizes, bool shared) -> PcoB200Error {
     const uint32_t n_chunks = e.n_chunks;
     PCOB_CUDA_TRY(S.lat0.reserve(slots * sizeof(L) + 64));
@@ -365,8 +372,8 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
     d_lat[0] = S.lat0.as<L>();
     d_lat[1] = S.lat1.as<L>();
     init_chunks_kernel<<<(n_chunks + 255) / 256, 256, 0, stream>>>(d_chunks, n_chunks);
-    if (!S.plan_attr_set) {
-      S.plan_attr_set = true;
+    if (!S.plan_attr_set[LW]) {
+      S.plan_attr_set[LW] = true;
       PCOB_CUDA_TRY(cudaFuncSetAttribute(plan_probe_kernel<L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(((size_t(1) << PLAN_MAX_COUNT_BITS) + 1) * 4 + 16)));
       PCOB_CUDA_TRY(cudaFuncSetAttribute(split_count_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(size_t(SC_N) * 4)));
@@ -387,13 +394,14 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
       profiler().begin("split_count_kernel", stream);
       split_count_kernel<L><<<n_chunks, SC_THREADS, size_t(SC_N) * 4, stream>>>(e, d_chunks, d_probes, S.key16_0.as<uint16_t>(), d_small);
       profiler().end(stream);
+      PCOB_CUDA_TRY(cudaGetLastError());  // a failed launch must not read as "no chunk raised a flag"
       uint32_t fl[2] = {0, 0};
       PCOB_CUDA_TRY(cudaMemcpyAsync(fl, d_small, 8, cudaMemcpyDeviceToHost, stream));
       PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
       if (fl[1] == 0 && shared) {
         // pages of one chunk: one histogram over all of them, one plan, copied to every page's slot
-        if (!S.union_attr_set) {
-          S.union_attr_set = true;
+        if (!S.union_attr_set[LW]) {
+          S.union_attr_set[LW] = true;
           PCOB_CUDA_TRY(cudaFuncSetAttribute(union_probe_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(size_t(SC_N) * 4)));
         }
         PCOB_CUDA_TRY(cudaMemsetAsync(d_small, 0, 8, stream));
@@ -451,14 +459,11 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
       PCOB_CUDA_TRY(cudaMemcpyAsync(d_seg, seg_host, 16, cudaMemcpyHostToDevice, stream));
       sort_keys_kernel<L><<<n_chunks * tiles, 256, 0, stream>>>(e, tiles, d_lat[0], S.keys_a.as<L>(), d_chunks, 0, d_prefix);
       const L* sorted = S.keys_a.as<L>();
-      if (stored_total > 0) {
-        cub::DoubleBuffer<L> db(S.keys_a.as<L>(), S.keys_b.as<L>());
-        size_t tmp_bytes = 0;
-        const int end_bit = int(std::max<uint32_t>(range_bits, 1));
-        PCOB_CUDA_TRY(cub::DeviceSegmentedRadixSort::SortKeys(nullptr, tmp_bytes, db, int64_t(stored_total), int64_t(1), d_seg, d_seg + 1, 0, end_bit, stream));
-        PCOB_CUDA_TRY(S.cub_tmp.reserve(tmp_bytes + 16));
-        PCOB_CUDA_TRY(cub::DeviceSegmentedRadixSort::SortKeys(S.cub_tmp.p, tmp_bytes, db, int64_t(stored_total), int64_t(1), d_seg, d_seg + 1, 0, end_bit, stream));
-        sorted = db.Current();
+      if (stored_total > 1) {
+        const uint32_t sort_bits = std::max<uint32_t>(range_bits, 1);
+        PCOB_CUDA_TRY(ensure_sort_attr());
+        radix_sort_segments_kernel<L><<<1, RS_THREADS, RS_SMEM, stream>>>(S.keys_a.as<L>(), S.keys_b.as<L>(), d_seg, d_seg + 1, sort_bits);
+        if (((sort_bits + RS_BITS - 1) / RS_BITS) & 1) sorted = S.keys_b.as<L>();
       }
       plan_probe_kernel<L, false><<<1, PLAN_THREADS, 16, stream>>>(e, sorted, d_chunks, d_probes, 0, range_bits, nullptr, uint32_t(stored_total));
       plan_solve_kernel<L><<<1, SOLVE_THREADS, 0, stream>>>(e, d_probes, d_chunks, d_plans, 0, uint32_t(stored_total));
@@ -497,16 +502,12 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
       segment_offsets_kernel<<<(n_chunks + 255) / 256, 256, 0, stream>>>(e, order_v, seg_begin, seg_end);
       const L* sorted = S.keys_a.as<L>();
       {
-        cub::DoubleBuffer<L> db(S.keys_a.as<L>(), S.keys_b.as<L>());
-        size_t tmp_bytes = 0;
-        PCOB_CUDA_TRY(cub::DeviceSegmentedRadixSort::SortKeys(nullptr, tmp_bytes, db, int64_t(slots), int64_t(n_chunks), seg_begin, seg_end, 0,
-                                                              int(range_bits), stream));
-        PCOB_CUDA_TRY(S.cub_tmp.reserve(tmp_bytes + 16));
-        profiler().begin("cub_segmented_radix_sort", stream);
-        PCOB_CUDA_TRY(cub::DeviceSegmentedRadixSort::SortKeys(S.cub_tmp.p, tmp_bytes, db, int64_t(slots), int64_t(n_chunks), seg_begin, seg_end, 0,
-                                                              int(range_bits), stream));
+        const uint32_t sort_bits = std::max<uint32_t>(range_bits, 1);
+        PCOB_CUDA_TRY(ensure_sort_attr());
+        profiler().begin("radix_sort_segments_kernel", stream);
+        radix_sort_segments_kernel<L><<<n_chunks, RS_THREADS, RS_SMEM, stream>>>(S.keys_a.as<L>(), S.keys_b.as<L>(), seg_begin, seg_end, sort_bits);
         profiler().end(stream);
-        sorted = db.Current();
+        if (((sort_bits + RS_BITS - 1) / RS_BITS) & 1) sorted = S.keys_b.as<L>();  // an odd number of passes ends in the second buffer
       }
       profiler().begin("plan_probe_kernel_sorted", stream);
       plan_probe_kernel<L, false><<<n_chunks, PLAN_THREADS, 16, stream>>>(e, sorted, d_chunks, d_probes, int(v), range_bits, nullptr);
@@ -641,6 +642,7 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
         es.order = k;
         uint32_t vrb[MAX_VARS] = {64, 64};
         if (PcoB200Error e = front(es, s_tiles, size_t(s_rows.back()), vrb, s_sizes, false)) return e;
+        PCOB_CUDA_TRY(cudaGetLastError());
         plan_summary_kernel<<<uint32_t(n_units), 128, 0, stream>>>(d_plans, uint32_t(n_units), d_sum);
         PCOB_CUDA_TRY(cudaMemcpyAsync(h_sum.data(), d_sum, n_units * sizeof(PlanSummary), cudaMemcpyDeviceToHost, stream));
         PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
@@ -732,6 +734,7 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
     PCOB_CUDA_TRY(cudaMemsetAsync(S.ob_sum.p, 0, n_cvb * 4, stream));
     uint32_t var_range_bits[MAX_VARS] = {64, 64};
     if (PcoB200Error e = front(ep, tiles_per_chunk, n_slots, var_range_bits, rpages, shared_bins)) return e;
+    PCOB_CUDA_TRY(cudaGetLastError());
     fallback_kernel<<<(n_chunks + 255) / 256, 256, 0, stream>>>(ep, d_plans, d_chunks, shared_bins ? n_chunks : 0u);
     // ---- K3, K4
     const uint32_t groups_per_chunk = (bpc + 7) / 8;

@@ -57,6 +57,7 @@ constexpr int FZ_BUF_WORDS = 32 * FZ_ROW_WORDS;
 constexpr int FZ_NODE_WORDS = PCOB_FZ_NODE_WORDS;    // decoder nodes, replicated when the table is small
 constexpr int FZ_HEAD_BYTES = 4096;                  // bulk-staged head of the chunk: header + <= 256 bins + page meta of one var
 constexpr int FZ_RING = 32;                          // carry-chain slots (> batches in flight)
+constexpr int FZ_MRING = 16;                         // moment-chain slots for delta orders >= 2
 
 // ---- mbarrier / bulk-copy primitives (shared::cta addresses as 32-bit values) ----
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
@@ -96,7 +97,13 @@ struct FusedSmem {
   ChunkHdr hdr;
   uint32_t q[SMALL_MAX_BINS];                       // offset_bits | (lower - lower_0) << 7
   uint32_t node[FZ_NODE_WORDS];
-  alignas(16) uint64_t link[FZ_RING][2];            // carry chain: {first number of batch b, b + 1}
+  union {
+    alignas(16) uint64_t link[FZ_RING][2];          // order 1 carry chain: {first number of batch b, b + 1}
+    struct {                                        // orders >= 2: mvec[b % FZ_MRING] = true moments at the start of batch b once m_flag[...] == b + 1
+      uint64_t mvec[FZ_MRING][MAX_ORDER];
+      volatile uint32_t m_flag[FZ_MRING];
+    } mo;
+  };
   alignas(8) uint64_t full_bar[FZ_NBUF], empty_bar[FZ_NBUF], head_bar;
   uint32_t ring_off[FZ_NBUF][32];                   // chunk-relative bit position of each batch's offsets section
   uint32_t err, not_narrow;
@@ -216,6 +223,57 @@ __device__ __forceinline__ void fused_walker(FusedSmem& sm, const BitSrc& src, u
   }
 }
 
+// Consecutive un-delta of order K >= 2 (delta/consecutive.rs:35-50) for a batch held 8 per lane: K nested zero-seeded warp scans, this
+// warp's link of the moment chain m_{b+1} = A^256 m_b + c_b (A = I + superdiagonal, (A^n)_{j,j+t} = C(n, t)), then m_b folded into the
+// lane's values by linearity - the general kernel's scheme (decode_kernels.cuh undelta_chain) with the binomials C(8 lane, t) and
+// C(256, t) computed in registers (exact: < 2^40) instead of read from a table.
+template <typename L, int K>
+__device__ __forceinline__ void fused_undelta(L (&x)[8], FusedSmem& sm, uint32_t b, int lane) {
+  L c[K];
+  undelta_local<L, K>(x, c, lane);
+  uint64_t bl[K], bf[K];
+  bl[0] = 1;
+  bf[0] = 1;
+  const uint64_t n8 = uint64_t(lane) * 8;
+#pragma unroll
+  for (int t = 1; t < K; t++) {
+    bl[t] = n8 + 1 >= uint64_t(t) + 1 && n8 >= uint64_t(t - 1) ? bl[t - 1] * (n8 - uint64_t(t - 1)) / uint64_t(t) : 0;  // C(n, t) = C(n, t-1) (n - t + 1) / t
+    bf[t] = bf[t - 1] * uint64_t(256 - (t - 1)) / uint64_t(t);
+  }
+  const uint32_t slot = b % FZ_MRING, nslot = (b + 1) % FZ_MRING;
+  while (sm.mo.m_flag[slot] != b + 1) {
+  }
+  __threadfence_block();
+  L m[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) m[k] = L(sm.mo.mvec[slot][k]);
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+      L acc = c[j];
+#pragma unroll
+      for (int t = 0; j + t < K; t++) acc = L(acc + L(L(bf[t]) * m[j + t]));
+      sm.mo.mvec[nslot][j] = uint64_t(acc);
+    }
+    __threadfence_block();
+    sm.mo.m_flag[nslot] = b + 2;
+  }
+  L sft[K];
+#pragma unroll
+  for (int j = 0; j < K; j++) {
+    L acc = 0;
+#pragma unroll
+    for (int t = 0; j + t < K; t++) acc = L(acc + L(L(bl[t]) * m[j + t]));
+    sft[j] = acc;
+  }
+#pragma unroll
+  for (int e = 0; e < 8; e++) {
+    x[e] = L(x[e] + sft[0]);
+#pragma unroll
+    for (int j = 0; j + 1 < K; j++) sft[j] = L(sft[j] + sft[j + 1]);
+  }
+}
+
 // A decoder warp: batches d, d + FZ_DECODERS, ... of the chunk (K = consecutive delta order, 0 or 1).
 template <typename L, int K>
 __device__ __forceinline__ void fused_decoder(FusedSmem& sm, const FileParams& fp, const BitSrc& src, const IndexChunk& task, uint64_t chunk_bit0, L* __restrict__ out,
@@ -330,6 +388,12 @@ __device__ __forceinline__ void fused_decoder(FusedSmem& sm, const FileParams& f
     if (K == 0) {
 #pragma unroll
       for (int e = 0; e < 8; e++) res[e] = L(base + L((q[e] >> 7) + f[e]));
+    } else if (K >= 2) {
+      // stored deltas (lower + offset, MID folded into base); positions past the page's stored latents hold values that cannot reach
+      // an emitted number (page_latent_decompressor.rs:244-248)
+#pragma unroll
+      for (int e = 0; e < 8; e++) res[e] = L(base + L((q[e] >> 7) + f[e]));
+      fused_undelta<L, (K >= 2 ? K : 2)>(res, sm, b, lane);
     } else {
       uint32_t F[8];
       F[0] = f[0];
@@ -461,7 +525,7 @@ fused_narrow_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, const 
   const uint32_t n_vars = sm.hdr.n_vars;
   const VarHdr vh0 = sm.hdr.var[0];
   // everything the general kernels serve is handed over untouched
-  const bool candidate = n_vars == 1 && sm.hdr.mode == MODE_CLASSIC && vh0.delta_order <= 1 && vh0.latent_bits >= 32 && vh0.n_bins >= 2 &&
+  const bool candidate = n_vars == 1 && sm.hdr.mode == MODE_CLASSIC && vh0.latent_bits >= 32 && vh0.n_bins >= 2 &&
                          task.entries_offset != 0 && index_base != nullptr;
   if (!candidate) {
     if (tid == 0) d_cls[blockIdx.x] = uint8_t(n_vars == 2 ? 2 : 1);
@@ -517,9 +581,14 @@ fused_narrow_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, const 
     return;
   }
   const uint32_t K = vh0.delta_order;
-  if (tid < FZ_RING) {
-    sm.link[tid][0] = tid == 0 ? sm.moment0 : 0;
-    sm.link[tid][1] = (K == 1 && tid == 0) ? 1u : 0u;
+  if (K <= 1) {
+    if (tid < FZ_RING) {
+      sm.link[tid][0] = tid == 0 ? sm.moment0 : 0;
+      sm.link[tid][1] = (K == 1 && tid == 0) ? 1u : 0u;
+    }
+  } else {
+    if (tid < FZ_MRING) sm.mo.m_flag[tid] = tid == 0 ? 1u : 0u;
+    if (tid < int(K)) sm.mo.mvec[0][tid] = sm.hdr.moments[0][tid];
   }
   __syncthreads();
   // the walkers' warp slots rotate with the CTA so that the CTAs of an SM do not all put them on the same schedulers
@@ -530,11 +599,19 @@ fused_narrow_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, const 
     fused_walker(sm, src, chunk_bit0, entries, nb_out, var_stored_n(n, K), vh0.ans_size_log, rep_log, role, lane);
   } else {
     const int d = role - FZ_WALKERS;
-    if (K == 1) fused_decoder<L, 1>(sm, fp, src, task, chunk_bit0, out, n, n_out, d, lane);
-    else fused_decoder<L, 0>(sm, fp, src, task, chunk_bit0, out, n, n_out, d, lane);
+    switch (K) {
+      case 0: fused_decoder<L, 0>(sm, fp, src, task, chunk_bit0, out, n, n_out, d, lane); break;
+      case 1: fused_decoder<L, 1>(sm, fp, src, task, chunk_bit0, out, n, n_out, d, lane); break;
+      case 2: fused_decoder<L, 2>(sm, fp, src, task, chunk_bit0, out, n, n_out, d, lane); break;
+      case 3: fused_decoder<L, 3>(sm, fp, src, task, chunk_bit0, out, n, n_out, d, lane); break;
+      case 4: fused_decoder<L, 4>(sm, fp, src, task, chunk_bit0, out, n, n_out, d, lane); break;
+      case 5: fused_decoder<L, 5>(sm, fp, src, task, chunk_bit0, out, n, n_out, d, lane); break;
+      case 6: fused_decoder<L, 6>(sm, fp, src, task, chunk_bit0, out, n, n_out, d, lane); break;
+      default: fused_decoder<L, 7>(sm, fp, src, task, chunk_bit0, out, n, n_out, d, lane); break;
+    }
   }
   __syncthreads();
-  if (tid == 0) { statuses[blockIdx.x] = sm.err; d_cls[blockIdx.x] = uint8_t(CLS_DONE | (K ? CLS_NARROW1 : CLS_NARROW0)); }
+  if (tid == 0) { statuses[blockIdx.x] = sm.err; d_cls[blockIdx.x] = uint8_t(CLS_DONE | (K == 0 ? CLS_NARROW0 : K == 1 ? CLS_NARROW1 : CLS_NARROWK)); }
 }
 
 }  // namespace pcob200

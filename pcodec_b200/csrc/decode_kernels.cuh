@@ -118,7 +118,7 @@ __host__ __device__ inline uint64_t scratch_rows_total(uint64_t out_len, uint32_
 // instantiation owns the chunk (d_cls, one byte per chunk): 1 / 2 = decode_kernel<L, 1 / 2> (any refusal is reported
 // by decode_kernel<L, 1>), 3 / 4 = decode_narrow_kernel (decode_narrow.cuh) with delta order 0 / 1.
 // ---------------------------------------------------------------------------
-constexpr uint32_t CLS_NARROW0 = 3, CLS_NARROW1 = 4;
+constexpr uint32_t CLS_NARROW0 = 3, CLS_NARROW1 = 4, CLS_NARROWK = 5;  // narrow class with delta order 0 / 1 / 2..7
 constexpr uint32_t CLS_DONE = 0x80;  // fused_narrow_kernel (decode_fused.cuh) has finished the chunk: the two-kernel path skips it
 constexpr uint32_t NARROW_MAX_OB = 15, NARROW_LOW_BITS = 16;
 
@@ -241,11 +241,13 @@ template <int CAP_LOG>   // 12: any table the format allows on this path; 10: wh
 struct WalkSmem {
   ChunkHdr hdr;
   uint32_t node[MAX_VARS][1 << CAP_LOG];
-  uint8_t bin_ob[MAX_VARS][1 << CAP_LOG];
-  uint16_t bin_weight[MAX_VARS][1 << CAP_LOG];
-  uint32_t bin_cum[MAX_VARS][(1 << CAP_LOG) + 1];
-  uint16_t sym_of_state[MAX_VARS][1 << CAP_LOG];
-  uint32_t rank_counter[MAX_VARS][1 << CAP_LOG];
+  // build scratch of ONE var (the vars' tables are built one after the other): 23 KB per CTA at CAP_LOG 10, so that 9 CTAs share an
+  // SM and 1024 chunks are walked in a single wave (with per-var scratch: 36 KB, 6 CTAs, two waves - twice the time)
+  uint8_t bin_ob[1 << CAP_LOG];
+  uint16_t bin_weight[1 << CAP_LOG];
+  uint32_t bin_cum[(1 << CAP_LOG) + 1];
+  uint16_t sym_of_state[1 << CAP_LOG];
+  uint32_t rank_counter[1 << CAP_LOG];
   uint32_t err;
   uint64_t next_chunk_byte;
   uint32_t status;
@@ -348,36 +350,55 @@ __device__ inline uint32_t walk_chunk_serial(const BitSrc& src, const ChunkHdr& 
       const uint32_t node_sa = v == 0 ? node_sa0 : node_sa1;
       uint32_t obs = 0;
       if ((v == 0 ? nbins0 : nbins1) > 1) {
-        uint32_t w = rbit >> 5;
-        uint32_t x0 = ring.word(w), x1 = ring.word(w + 1), x2 = ring.word(w + 2);
-        uint32_t kblk = rbit >> 10;  // 8-block (1024-bit) region of the cursor: the ring is topped up when it changes
+        // bit reader: `acc` holds the next `avail` (> 32) bits of the stream, `nxt` the word after them - loaded ahead, so the refill that
+        // follows every pair of symbols is a shift and an OR, and no shared-memory address on the chain depends on the cursor
+        uint32_t wp = rbit >> 5;
+        uint64_t acc = ((uint64_t(ring.word(wp + 1)) << 32) | ring.word(wp)) >> (rbit & 31);
+        uint32_t avail = 64 - (rbit & 31);
+        wp += 2;
+        uint32_t nxt = ring.word(wp);
+        auto refill = [&]() {
+          if (avail <= 32) {
+            acc |= uint64_t(nxt) << avail;
+            avail += 32;
+            wp += 1;
+            if ((wp & 31) == 0) ring.advance(wp << 5);  // entering a new 1024-bit region: top the ring up
+            nxt = ring.word(wp);
+          }
+        };
         uint32_t i = 0;
         for (; i + 4 <= cnt; i += 4) {
           const uint32_t n0 = lds_u32(node_sa + s0), n1 = lds_u32(node_sa + s1), n2 = lds_u32(node_sa + s2), n3 = lds_u32(node_sa + s3);
-          const uint32_t r = rbit & 31;
-          const uint64_t g = (uint64_t(__funnelshift_r(x1, x2, r)) << 32) | __funnelshift_r(x0, x1, r);
           const uint32_t c0 = node_btr(n0), c1 = node_btr(n1), c2 = node_btr(n2), c3 = node_btr(n3);
-          const uint32_t sh2 = c0 + c1, sh3 = sh2 + c2;
-          s0 = (node_base(n0) + (uint32_t(g) & ((1u << c0) - 1))) << 2;
-          s1 = (node_base(n1) + (uint32_t(g >> c0) & ((1u << c1) - 1))) << 2;
-          s2 = (node_base(n2) + (uint32_t(g >> sh2) & ((1u << c2) - 1))) << 2;
-          s3 = (node_base(n3) + (uint32_t(g >> sh3) & ((1u << c3) - 1))) << 2;
           obs = __dp4a(node_fields4(n0, n1, n2, n3), 0x01010101u, obs);
-          rbit += sh3 + c3;
-          if ((rbit >> 5) != w) {
-            if ((rbit >> 10) != kblk) { kblk = rbit >> 10; ring.advance(rbit); }
-            w = rbit >> 5;
-            x0 = ring.word(w); x1 = ring.word(w + 1); x2 = ring.word(w + 2);
+          {
+            const uint32_t g = uint32_t(acc);  // c0 + c1 <= 28 bits
+            s0 = (node_base(n0) + (g & ((1u << c0) - 1))) << 2;
+            s1 = (node_base(n1) + ((g >> c0) & ((1u << c1) - 1))) << 2;
+            acc >>= (c0 + c1);
+            avail -= c0 + c1;
+            refill();
           }
+          {
+            const uint32_t g = uint32_t(acc);
+            s2 = (node_base(n2) + (g & ((1u << c2) - 1))) << 2;
+            s3 = (node_base(n3) + ((g >> c2) & ((1u << c3) - 1))) << 2;
+            acc >>= (c2 + c3);
+            avail -= c2 + c3;
+            refill();
+          }
+          rbit += c0 + c1 + c2 + c3;
         }
         // ragged tail of the page's last batch (page_latent_decompressor.rs:144-177)
         auto tail_step = [&](uint32_t& sj) {
           const uint32_t nn = lds_u32(node_sa + sj);
-          const uint32_t ww = rbit >> 5, r = rbit & 31;
-          const uint32_t val = __funnelshift_r(ring.word(ww), ring.word(ww + 1), r) & ((1u << node_btr(nn)) - 1);
+          const uint32_t cb = node_btr(nn);
           obs += node_field(nn);
-          sj = (node_base(nn) + val) << 2;
-          rbit += node_btr(nn);
+          sj = (node_base(nn) + (uint32_t(acc) & ((1u << cb) - 1))) << 2;
+          acc >>= cb;
+          avail -= cb;
+          rbit += cb;
+          refill();
         };
         if (i < cnt) tail_step(s0);
         if (i + 1 < cnt) tail_step(s1);
@@ -438,8 +459,7 @@ __global__ void __launch_bounds__(128) walk_kernel(FileParams fp, uint8_t* index
     uint32_t st = sm.hdr.status;
     if (st == ST_OK) {
       for (uint32_t v = 0; v < sm.hdr.n_vars; v++)
-        build_var_tables<true>(src, sm.hdr, v, sm.node[v], nullptr, sm.bin_ob[v], sm.bin_weight[v], sm.bin_cum[v], sm.sym_of_state[v],
-                               sm.rank_counter[v], &sm.err, false);
+        build_var_tables<true>(src, sm.hdr, v, sm.node[v], nullptr, sm.bin_ob, sm.bin_weight, sm.bin_cum, sm.sym_of_state, sm.rank_counter, &sm.err, false);
       __syncthreads();
       if (sm.err) st = sm.err;
     }

@@ -378,6 +378,101 @@ __global__ void segment_offsets_kernel(EncParams ep, uint32_t order_v, uint64_t*
 }
 
 // ---------------------------------------------------------------------------
+// radix_sort_segments_kernel: the wide-key-range planner's sort (histograms.rs:208-281 needs order statistics of the chunk's latents; a
+// key range above 2^15 does not fit the shared-memory counting path).  One CTA per segment (= a chunk's stored keys, latent - minimum)
+// sorts it by least-significant-digit passes of 11 bits over the `bits` significant bits, ping-ponging between the two key buffers:
+//   count   : warp w owns a contiguous tile of the segment and histograms its digits - lanes with equal digits find each other with
+//             match_any, one of them adds the group's size to the warp's own counter row (no atomics);
+//   scan    : exclusive prefix over (digit, warp) - all keys of digit d from warp w go after those of smaller digits and of lower warps;
+//   scatter : the warp walks its tile again in the same order; a key's place is its (digit, warp) offset plus its rank among the
+//             equal-digit lanes of the step - a stable pass, so the passes compose into a sort.
+// 6 passes for 64-bit keys, 3 for 32-bit ones, each two reads and one write of the segment: HBM-bound streaming, no library call.
+// ---------------------------------------------------------------------------
+constexpr int RS_THREADS = 512;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_BITS = 11;
+constexpr int RS_BINS = 1 << RS_BITS;
+
+template <typename L>
+__global__ void __launch_bounds__(RS_THREADS, 1) radix_sort_segments_kernel(L* __restrict__ buf_a, L* __restrict__ buf_b, const uint64_t* __restrict__ seg_begin,
+                                                                            const uint64_t* __restrict__ seg_end, uint32_t bits) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t (*hist)[RS_BINS] = reinterpret_cast<uint32_t (*)[RS_BINS]>(smem_raw);  // [RS_WARPS][RS_BINS]
+  __shared__ uint32_t part[RS_THREADS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint64_t s0 = seg_begin[blockIdx.x];
+  const uint64_t n64 = seg_end[blockIdx.x] - s0;
+  const uint32_t n = uint32_t(n64);
+  const uint32_t passes = (bits + RS_BITS - 1) / RS_BITS;
+  if (n <= 1) {  // nothing to sort, but the caller reads the buffer an odd number of passes ends in
+    if (n == 1 && (passes & 1) && threadIdx.x == 0) buf_b[s0] = buf_a[s0];
+    return;
+  }
+  // tiles: multiples of 32 keys, so that every step of a warp is a full step except the last of the segment
+  const uint32_t per = ((n + RS_WARPS - 1) / RS_WARPS + 31) & ~31u;
+  const uint32_t lo = min(n, uint32_t(warp) * per), hi = min(n, lo + per);
+  L* in = buf_a + s0;
+  L* out = buf_b + s0;
+  for (uint32_t p = 0; p < passes; p++) {
+    const uint32_t shift = p * RS_BITS;
+    const uint32_t dmask = (1u << min(uint32_t(RS_BITS), bits - shift)) - 1;
+    for (uint32_t i = tid; i < uint32_t(RS_WARPS * RS_BINS); i += RS_THREADS) hist[0][i] = 0;
+    __syncthreads();
+    // ---- count
+    for (uint32_t i = lo; i < hi; i += 32) {
+      const bool act = i + lane < hi;
+      const uint32_t amask = __ballot_sync(0xffffffffu, act);
+      if (act) {
+        const uint32_t d = uint32_t(uint64_t(in[i + lane]) >> shift) & dmask;
+        const uint32_t m = __match_any_sync(amask, d);
+        if (lane == __ffs(m) - 1) hist[warp][d] += __popc(m);
+      }
+    }
+    __syncthreads();
+    // ---- scan over (digit major, warp minor): thread t owns digits [4t, 4t + 4)
+    {
+      uint32_t sum = 0;
+#pragma unroll
+      for (int dd = 0; dd < RS_BINS / RS_THREADS; dd++)
+        for (int w = 0; w < RS_WARPS; w++) sum += hist[w][tid * (RS_BINS / RS_THREADS) + dd];
+      uint32_t inc = sum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+      part[tid] = inc;
+      __syncthreads();
+      uint32_t base = inc - sum;
+      for (int w = 0; w < warp; w++) base += part[w * 32 + 31];
+      __syncthreads();
+#pragma unroll
+      for (int dd = 0; dd < RS_BINS / RS_THREADS; dd++)
+        for (int w = 0; w < RS_WARPS; w++) {
+          const uint32_t c = hist[w][tid * (RS_BINS / RS_THREADS) + dd];
+          hist[w][tid * (RS_BINS / RS_THREADS) + dd] = base;
+          base += c;
+        }
+    }
+    __syncthreads();
+    // ---- scatter (same order as the count)
+    for (uint32_t i = lo; i < hi; i += 32) {
+      const bool act = i + lane < hi;
+      const uint32_t amask = __ballot_sync(0xffffffffu, act);
+      if (act) {
+        const L key = in[i + lane];
+        const uint32_t d = uint32_t(uint64_t(key) >> shift) & dmask;
+        const uint32_t m = __match_any_sync(amask, d);
+        const uint32_t off = hist[warp][d];
+        __syncwarp(amask);
+        out[off + __popc(m & ((1u << lane) - 1))] = key;
+        if (lane == __ffs(m) - 1) hist[warp][d] = off + __popc(m);
+      }
+      __syncwarp();
+    }
+    __syncthreads();  // the pass's writes are visible to the whole CTA (same-CTA global writes are ordered by the barrier)
+    L* t = in; in = out; out = t;
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Bin training (train_infos, chunk_compressor.rs:52-99) in two kernels per latent var:
 //   plan_probe_kernel — one 512-thread CTA per chunk, HBM-bound: order statistics at the 2^log equal-count boundaries
 //                       (from shared-memory counters when the key range is narrow, else from the sorted keys)
