@@ -8,6 +8,7 @@
 #include "decode_narrow.cuh"
 #include "decode_fused.cuh"
 #include "gather_kernels.cuh"
+#include "decode_cold.cuh"
 #include "host_common.hpp"
 
 namespace pcob200 {
@@ -22,7 +23,7 @@ struct Context {
   bool initialized = false;
   bool device_ok = false;
   std::string device_err;
-  DevBuf src, out, index, statuses, misc, dec_syms, dec_offs, dec_nvars, dec_narrow, gather;
+  DevBuf src, out, index, statuses, misc, dec_syms, dec_offs, dec_nvars, dec_narrow, gather, cold;
   CompressScratch enc;
   Binoms* d_binoms = nullptr;
   int sm_count = 0;
@@ -38,7 +39,7 @@ static Context& ctx() {
 }
 
 static void release_buffers(Context& c) {
-  for (DevBuf* b : {&c.src, &c.out, &c.index, &c.statuses, &c.misc, &c.dec_syms, &c.dec_offs, &c.dec_nvars, &c.dec_narrow, &c.gather}) b->release();
+  for (DevBuf* b : {&c.src, &c.out, &c.index, &c.statuses, &c.misc, &c.dec_syms, &c.dec_offs, &c.dec_nvars, &c.dec_narrow, &c.gather, &c.cold}) b->release();
   c.enc.release();
   c.gather_err = nullptr;
   if (c.d_binoms) cudaFree(c.d_binoms);
@@ -204,9 +205,8 @@ static PcoB200Error launch_decode(Context& c, const FileParams& fp, const uint8_
 // Core of every decompress entry point.
 //   stop_when_full: pco::standalone::simple_decompress_into semantics (stop reading once dst is full);
 //                   false = simple_decompress semantics (walk the whole file; the caller checks capacity).
-static PcoB200Error decompress_core(const void* compressed, size_t compressed_len, uint32_t dtype, void* dst, size_t dst_len,
-                                    const void* index, size_t index_len, uint32_t flags, void* cuda_stream, bool stop_when_full,
-                                    DecodeOutcome* outcome) {
+static PcoB200Error decompress_fast(const void* compressed, size_t compressed_len, uint32_t dtype, void* dst, size_t dst_len,
+                                    const void* index, size_t index_len, uint32_t flags, void* cuda_stream, DecodeOutcome* outcome) {
   if (!nt_valid(dtype)) return fail(PCO_B200_INVALID_TYPE, "unknown number type byte: " + std::to_string(dtype));
   Context& c = ctx();
   if (PcoB200Error e = ensure_device(c)) return e;
@@ -323,7 +323,6 @@ static PcoB200Error decompress_core(const void* compressed, size_t compressed_le
     if (res.status == ST_DST_FULL) break;
     if (res.n_chunks == 0) return fail(PCO_B200_UNSUPPORTED, "a single chunk exceeds the device index scratch");
   }
-  (void)stop_when_full;
   outcome->n_total = out_off;
   uint64_t n_emit = std::min<uint64_t>(out_off, dst_len);
   if (!dst_dev && n_emit) {
@@ -331,6 +330,78 @@ static PcoB200Error decompress_core(const void* compressed, size_t compressed_le
     PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
   }
   return PCO_B200_OK;
+}
+
+// The catch-all behind the fast kernels: the whole file through cold_decode_kernel (decode_cold.cuh) - one GPU thread, any valid pco.
+static PcoB200Error decompress_cold(const void* compressed, size_t compressed_len, uint32_t dtype, void* dst, size_t dst_len, uint32_t flags, void* cuda_stream,
+                                    DecodeOutcome* outcome) {
+  Context& c = ctx();
+  if (PcoB200Error e = ensure_device(c)) return e;
+  cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+  const bool src_dev = flags & PCO_B200_SRC_ON_DEVICE, dst_dev = flags & PCO_B200_DST_ON_DEVICE;
+  const size_t elem = nt_bits(dtype) / 8;
+  uint8_t head[32] = {0};
+  const size_t avail = std::min<size_t>(compressed_len, sizeof(head));
+  if (avail) {
+    if (src_dev) { PCOB_CUDA_TRY(cudaMemcpyAsync(head, compressed, avail, cudaMemcpyDeviceToHost, stream)); PCOB_CUDA_TRY(cudaStreamSynchronize(stream)); }
+    else std::memcpy(head, compressed, avail);
+  }
+  StandaloneHeader hdr;
+  if (PcoB200Error e = parse_standalone_header(head, avail, compressed_len, &hdr)) return e;
+  const uint8_t* d_src = static_cast<const uint8_t*>(compressed);
+  if (!src_dev) {
+    PCOB_CUDA_TRY(c.src.reserve(compressed_len + 16));
+    PCOB_CUDA_TRY(cudaMemcpyAsync(c.src.p, compressed, compressed_len, cudaMemcpyHostToDevice, stream));
+    d_src = c.src.as<uint8_t>();
+  }
+  FileParams fp{d_src, compressed_len, dtype, hdr.uniform_type, hdr.format_major};
+  void* d_out = dst;
+  if (!dst_dev) {
+    PCOB_CUDA_TRY(c.out.reserve(dst_len * elem + 64));
+    d_out = c.out.p;
+  }
+  PCOB_CUDA_TRY(c.misc.reserve(256));
+  ColdResult* d_res = reinterpret_cast<ColdResult*>(c.misc.as<uint8_t>() + 160);
+  ColdResult res;
+  for (uint32_t window_cap : {16u, COLD_MAX_WINDOW_LOG}) {  // lookback windows beyond 2^16 numbers get the large scratch on a second try
+    PCOB_CUDA_TRY(c.cold.reserve(cold_scratch_bytes(window_cap)));
+    profiler().begin("cold_decode_kernel", stream);
+    dispatch_latent(dtype, [&](auto tag) {
+      using L = decltype(tag);
+      cold_decode_kernel<L><<<1, 32, 0, stream>>>(fp, hdr.first_chunk_byte, static_cast<L*>(d_out), uint64_t(dst_len), c.cold.as<uint8_t>(), window_cap, d_res);
+      return 0;
+    });
+    profiler().end(stream);
+    PCOB_CUDA_TRY(cudaGetLastError());
+    PCOB_CUDA_TRY(cudaMemcpyAsync(&res, d_res, sizeof(res), cudaMemcpyDeviceToHost, stream));
+    PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
+    if (res.status != ST_UNSUPPORTED) break;
+  }
+  // like the walk path: the chunks before a failing one have been emitted (the reference's decoder stops where the error is)
+  const uint64_t n_emit = std::min<uint64_t>(res.n_total, dst_len);
+  if (!dst_dev && n_emit) {
+    PCOB_CUDA_TRY(cudaMemcpyAsync(dst, d_out, n_emit * elem, cudaMemcpyDeviceToHost, stream));
+    PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
+  }
+  if (res.status != ST_TERMINATOR && res.status != ST_DST_FULL) return status_to_error(res.status, ("chunk " + std::to_string(res.n_chunks)).c_str());
+  outcome->n_total = res.n_total;
+  outcome->terminated = res.status == ST_TERMINATOR;
+  return PCO_B200_OK;
+}
+
+// Core of every decompress entry point: the fast kernels, and for streams they decline (valid pco with Dict mode, Lookback / Conv1
+// deltas, tANS tables beyond 2^10 states or 256 bins, ...) the single-thread device decoder.  PCOB200_COLD_DECODE=0 keeps the refusal.
+static PcoB200Error decompress_core(const void* compressed, size_t compressed_len, uint32_t dtype, void* dst, size_t dst_len,
+                                    const void* index, size_t index_len, uint32_t flags, void* cuda_stream, bool stop_when_full,
+                                    DecodeOutcome* outcome) {
+  (void)stop_when_full;
+  PcoB200Error e = decompress_fast(compressed, compressed_len, dtype, dst, dst_len, index, index_len, flags, cuda_stream, outcome);
+  static const bool cold_ok = [] { const char* v = std::getenv("PCOB200_COLD_DECODE"); return !(v && v[0] == '0'); }();
+  if (e == PCO_B200_UNSUPPORTED && cold_ok) {
+    *outcome = DecodeOutcome();
+    e = decompress_cold(compressed, compressed_len, dtype, dst, dst_len, flags, cuda_stream, outcome);
+  }
+  return e;
 }
 
 }  // namespace pcob200

@@ -27,8 +27,9 @@ def simple_decompress(src, dtype=None, index=None):
         dtype = peek_dtype(src)
         if dtype is None:
             return None
-    # size the destination from n_hint when present, growing if the file holds more
-    cap = max(n_hint(src), 1)
+    # size the destination from n_hint when present, growing if the file holds more.  n_hint is untrusted (a 20-byte file may claim 2^64
+    # numbers): the first allocation is capped at 2^32 bytes like the reference's (pco/src/standalone/constants.rs:10-17, decompressor.rs:265-269)
+    cap = max(min(n_hint(src), (1 << 32) // np.dtype(dtype).itemsize), 1)
     while True:
         dst = np.empty(cap, dtype=dtype)
         prog = decompress_into_with_index(src, dst, index)

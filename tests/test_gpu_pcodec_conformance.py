@@ -15,7 +15,7 @@ ALL_DTYPES = ("f2", "f4", "f8", "i2", "i4", "i8", "u2", "u4", "u8")
 
 @pytest.fixture(scope="module")
 def api():
-    import pcodec_b200 as p
+    import pcodec as p  # the reference's import name, served by pcodec_b200 (pcodec/__init__.py)
 
     return p
 
