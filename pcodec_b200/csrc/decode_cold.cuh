@@ -187,12 +187,14 @@ __device__ inline uint32_t cold_undelta(const ColdChunk& ch, ColdVar& v, const u
       const uint64_t pred = uint64_t(ss >> ch.quant) & lmask;
       v.lat[i] = (latent + pred) & lmask;
     }
-    // new state = the last `order` entries of (state ++ decoded batch)
+    // the window is (state ++ decoded batch): its last `order` entries are the next state, its FIRST dst_len entries are the batch's output
+    // (conv1.rs:464-483: the decoded values come out `order` positions late, the page's first numbers being the state itself)
     uint64_t ns[32];
     for (uint32_t j = 0; j < order; j++) {
       const uint32_t idx = dst_len + j;  // position in the window of length order + dst_len
       ns[j] = idx < order ? v.dstate[idx] : v.lat[idx - order];
     }
+    for (uint32_t i = dst_len; i-- > 0;) v.lat[i] = i < order ? v.dstate[i] : v.lat[i - order];
     for (uint32_t j = 0; j < order; j++) v.dstate[j] = ns[j];
   } else if (v.delta_kind == DELTA_LOOKBACK) {  // lookback.rs:201-246
     const uint64_t window_n = uint64_t(1) << ch.window_n_log, state_n = uint64_t(1) << ch.state_n_log;

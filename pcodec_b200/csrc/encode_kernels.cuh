@@ -392,6 +392,7 @@ constexpr int RS_THREADS = 512;
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_BITS = 11;
 constexpr int RS_BINS = 1 << RS_BITS;
+constexpr int RS_UNROLL = 8;  // 256 keys of a warp in flight per iteration
 
 template <typename L>
 __global__ void __launch_bounds__(RS_THREADS, 1) radix_sort_segments_kernel(L* __restrict__ buf_a, L* __restrict__ buf_b, const uint64_t* __restrict__ seg_begin,
@@ -418,14 +419,22 @@ __global__ void __launch_bounds__(RS_THREADS, 1) radix_sort_segments_kernel(L* _
     const uint32_t dmask = (1u << min(uint32_t(RS_BITS), bits - shift)) - 1;
     for (uint32_t i = tid; i < uint32_t(RS_WARPS * RS_BINS); i += RS_THREADS) hist[0][i] = 0;
     __syncthreads();
-    // ---- count
-    for (uint32_t i = lo; i < hi; i += 32) {
-      const bool act = i + lane < hi;
-      const uint32_t amask = __ballot_sync(0xffffffffu, act);
-      if (act) {
-        const uint32_t d = uint32_t(uint64_t(in[i + lane]) >> shift) & dmask;
-        const uint32_t m = __match_any_sync(amask, d);
-        if (lane == __ffs(m) - 1) hist[warp][d] += __popc(m);
+    // ---- count: RS_UNROLL steps of 32 keys per iteration, their loads issued together (the pass is a latency chain otherwise: one
+    // 256-byte load per warp in flight)
+    for (uint32_t i = lo; i < hi; i += 32 * RS_UNROLL) {
+      L k[RS_UNROLL];
+#pragma unroll
+      for (int u = 0; u < RS_UNROLL; u++) k[u] = i + 32 * u + lane < hi ? in[i + 32 * u + lane] : L(0);
+#pragma unroll
+      for (int u = 0; u < RS_UNROLL; u++) {
+        const bool act = i + 32 * u + lane < hi;
+        const uint32_t amask = __ballot_sync(0xffffffffu, act);
+        if (act) {
+          const uint32_t d = uint32_t(uint64_t(k[u]) >> shift) & dmask;
+          const uint32_t m = __match_any_sync(amask, d);
+          if (lane == __ffs(m) - 1) hist[warp][d] += __popc(m);
+        }
+        __syncwarp();
       }
     }
     __syncthreads();
@@ -453,19 +462,24 @@ __global__ void __launch_bounds__(RS_THREADS, 1) radix_sort_segments_kernel(L* _
     }
     __syncthreads();
     // ---- scatter (same order as the count)
-    for (uint32_t i = lo; i < hi; i += 32) {
-      const bool act = i + lane < hi;
-      const uint32_t amask = __ballot_sync(0xffffffffu, act);
-      if (act) {
-        const L key = in[i + lane];
-        const uint32_t d = uint32_t(uint64_t(key) >> shift) & dmask;
-        const uint32_t m = __match_any_sync(amask, d);
-        const uint32_t off = hist[warp][d];
-        __syncwarp(amask);
-        out[off + __popc(m & ((1u << lane) - 1))] = key;
-        if (lane == __ffs(m) - 1) hist[warp][d] = off + __popc(m);
+    for (uint32_t i = lo; i < hi; i += 32 * RS_UNROLL) {
+      L k[RS_UNROLL];
+#pragma unroll
+      for (int u = 0; u < RS_UNROLL; u++) k[u] = i + 32 * u + lane < hi ? in[i + 32 * u + lane] : L(0);
+#pragma unroll
+      for (int u = 0; u < RS_UNROLL; u++) {
+        const bool act = i + 32 * u + lane < hi;
+        const uint32_t amask = __ballot_sync(0xffffffffu, act);
+        if (act) {
+          const uint32_t d = uint32_t(uint64_t(k[u]) >> shift) & dmask;
+          const uint32_t m = __match_any_sync(amask, d);
+          const uint32_t off = hist[warp][d];
+          __syncwarp(amask);
+          out[off + __popc(m & ((1u << lane) - 1))] = k[u];
+          if (lane == __ffs(m) - 1) hist[warp][d] = off + __popc(m);
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
     __syncthreads();  // the pass's writes are visible to the whole CTA (same-CTA global writes are ordered by the barrier)
     L* t = in; in = out; out = t;

@@ -68,7 +68,7 @@ def test_levels_above_8_decode(sa, oracle, level):
     nums = (rng.lognormal(10, 2, size=1 << 16)).astype(np.uint64)
     data = _roundtrip(sa, oracle, nums, oracle.make_config(level=level, mode=oracle.MODE_CLASSIC, delta=oracle.DELTA_NOOP), expect_kernel="cold_decode_kernel" if level >= 12 else None)
     info = oracle.inspect(data, np.uint64)["chunks"][0]
-    if level >= 10:
+    if level >= 12:
         assert max(len(v["bins"]) for v in info["vars"]) > 256 or max(v["ans_size_log"] for v in info["vars"]) > 10
 
 

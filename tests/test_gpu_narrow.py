@@ -106,11 +106,12 @@ def test_conditions_that_must_miss_the_narrow_path(sa, oracle):
         assert np.array_equal(got, nums)
         n_chunks, counts = _classes()
         assert n_chunks == 1 and counts[1] == 1, counts
-    # delta order 2 and 16-bit types stay on the general kernel
-    nums = _narrow_data(np.uint64, 9000, 0, 1)
-    data = oracle.simple_compress(nums, _cfg(oracle, 2))
-    assert np.array_equal(sa.simple_decompress(data, np.uint64), nums)
-    assert _classes()[1][1] == 1
+    # delta orders 2..7 are served by the fused kernel too (class 5); 16-bit types stay on the general kernel
+    for order in (2, 3, 7):
+        nums = _narrow_data(np.uint64, 9000, 0, 1)
+        data = oracle.simple_compress(nums, _cfg(oracle, order))
+        assert np.array_equal(sa.simple_decompress(data, np.uint64), nums)
+        assert _classes()[1][5] == 1
     nums16 = (np.cumsum(rng.integers(0, 5, size=9000)) % 60000).astype(np.uint16)
     data = oracle.simple_compress(nums16, _cfg(oracle, 1))
     assert np.array_equal(sa.simple_decompress(data, np.uint16), nums16)
