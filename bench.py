@@ -570,15 +570,18 @@ def run_gpu_arm(args, rank, world):
                         self.done.put(ex)
 
         handoff = queue.Queue()
+        trace = []  # (call, group, start, end) of the last streamed pass: shows how far the two directions overlap
 
         def produce(_):
             try:
                 sa = C.c_void_p(streams[0].cuda_stream)
                 for g in range(G):
+                    t_a = time.perf_counter()
                     rc = L.pco_b200_compress_ex(C.c_void_p(h_nums.data_ptr() + 8 * bounds[g] * CHUNK_N), C.c_size_t(g_n[g]), C.c_ubyte(2), C.byref(cfg), C.c_int(0),
                                                 C.c_void_p(h_comp_g.data_ptr() + int(g_coff[g])), C.c_size_t(g_cap[g]), C.byref(g_nw[g]),
                                                 C.c_void_p(h_index_g.data_ptr() + int(g_ioff[g])), C.c_size_t(g_icap[g]), C.byref(g_il[g]), C.c_uint32(0), sa)
                     _lib.check(rc)
+                    trace.append(("c", g, t_a, time.perf_counter()))
                     handoff.put(g)
             finally:
                 handoff.put(None)
@@ -590,15 +593,18 @@ def run_gpu_arm(args, rank, world):
                 g = handoff.get()
                 if g is None:
                     return
+                t_b = time.perf_counter()
                 rc = L.pco_b200_decompress_ex(C.c_void_p(h_comp_g.data_ptr() + int(g_coff[g])), g_nw[g], C.c_ubyte(2),
                                               C.c_void_p(h_out.data_ptr() + 8 * bounds[g] * CHUNK_N), C.c_size_t(g_n[g]), C.byref(pr),
                                               C.c_void_p(h_index_g.data_ptr() + int(g_ioff[g])), g_il[g], C.c_uint32(0), sb)
                 _lib.check(rc)
+                trace.append(("d", g, t_b, time.perf_counter()))
                 assert pr.n_processed == g_n[g] and pr.finished
 
         workers = [_Worker(produce), _Worker(consume)]
 
         def e2e_pipelined():
+            trace.clear()
             for w in workers:
                 w.jobs.put(1)
             errs = [w.done.get() for w in workers]
@@ -632,6 +638,8 @@ def run_gpu_arm(args, rank, world):
         e2e_pipelined()  # second warm-up: both threads' contexts have their scratch
         e2e_ms = timed(e2e_pipelined, max(1, args.steps))
         single_ms = timed(e2e_single_call, max(1, min(args.steps, 3)))
+        t_first = min(t[2] for t in trace) if trace else 0.0
+        e2e_trace = [[t[0], t[1], round((t[2] - t_first) * 1e3, 2), round((t[3] - t_first) * 1e3, 2)] for t in sorted(trace, key=lambda t: t[2])]
         for w in workers:
             w.jobs.put(None)
         for w in workers:
@@ -641,6 +649,7 @@ def run_gpu_arm(args, rank, world):
                "d2h_bytes_per_step": int(cg + ig + U), "ms_per_step": e2e_ms, "steps": max(1, args.steps),
                "api": f"pco_b200_compress_ex + pco_b200_decompress_ex (C-ABI), pinned host buffers, streamed in {G} groups of chunks: one host thread compresses group g+1 "
                       "while another decompresses group g (per-thread library contexts, one stream each)",
+               "trace_ms": e2e_trace,
                "single_call": {"value": world * U / 1e6 / (single_ms / 1e3), "ms_per_step": single_ms,
                                "api": "one pco_b200_compress_ex + one pco_b200_decompress_ex over the whole array (H2D, kernels, D2H back to back)"}}
     # ---- the reference's own three-function C ABI, unmodified (pco_c/include/cpcodec_generated.h:33-64): default config (Auto mode, Auto

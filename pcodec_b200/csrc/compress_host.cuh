@@ -25,12 +25,12 @@ constexpr uint32_t PCO_B200_INTERNAL_SHARED_BINS = 1u << 16;
 
 
 struct CompressScratch {
-  DevBuf lat0, lat1, keys_a, keys_b, sym0, sym1, ans0, ans1, ob_sum, ans_sum, entries, plans, chunks, starts, seg, out, small, index, probes, sample, sample_starts, key16_0, key16_1, idx_out;
+  DevBuf lat0, lat1, keys_a, keys_b, sym0, sym1, ans0, ans1, ob_sum, ans_sum, entries, plans, chunks, starts, seg, out, small, index, probes, sample, sample_starts, key16_0, key16_1, idx_out, lb_vals, lb_resid, lb_scratch;
   // kernel attributes are per instantiation: one flag per latent width (index log2(sizeof(L)))
   bool plan_attr_set[4] = {false, false, false, false}, union_attr_set[4] = {false, false, false, false}, sort_attr_set[4] = {false, false, false, false};
   void release() {
     for (DevBuf* b : {&lat0, &lat1, &keys_a, &keys_b, &sym0, &sym1, &ans0, &ans1, &ob_sum, &ans_sum, &entries, &plans, &chunks, &starts, &seg, &out, &small,
-                      &index, &probes, &sample, &sample_starts, &key16_0, &key16_1, &idx_out})
+                      &index, &probes, &sample, &sample_starts, &key16_0, &key16_1, &idx_out, &lb_vals, &lb_resid, &lb_scratch})
       b->release();
   }
 };
@@ -196,6 +196,92 @@ __global__ void gather_primary_sample_kernel(const L* __restrict__ nums, const u
   }
 }
 
+// The Lookback candidate of the Auto delta search (chunk_compressor.rs:326-338) on every chunk's delta sample: choose_lookbacks
+// (delta/lookback.rs:96-159: brute-force, repeating and hashed proposals, the best by goodness = leading zeros of the difference + a
+// popularity bonus) and encode_in_place (:166-187), by ONE thread per chunk - the search is a serial state machine (hash table of last
+// positions, running popularity counts).  Outputs per chunk, len - 1 entries each at out_starts[c]: the lookbacks as u32 numbers and
+// the residuals (latent - latent[i - lookback] + MID) as numbers of width L; both then go through the ordinary planner as trial vars.
+constexpr uint32_t LB_PROPOSED = 16, LB_BRUTE = 6, LB_REPEATING = 4;
+__host__ __device__ inline uint32_t lookback_window_n_log(uint64_t n) {  // delta::new_lookback (delta/mod.rs:37-48): state_n_log = 0
+  const uint32_t x = uint32_t(n - 1);
+  const uint32_t bits = x == 0 ? 0u : 32u -
+#ifdef __CUDA_ARCH__
+                                     uint32_t(__clz(x));
+#else
+                                     uint32_t(__builtin_clz(x));
+#endif
+  return bits < 4 ? 4u : bits > 15 ? 15u : bits;
+}
+template <typename L>
+__global__ void lookback_trial_kernel(const L* __restrict__ sample, const uint64_t* __restrict__ sample_starts, const uint64_t* __restrict__ out_starts,
+                                      uint32_t* __restrict__ lookbacks, L* __restrict__ resid, uint32_t* __restrict__ hash_scratch,
+                                      uint32_t* __restrict__ count_scratch, uint32_t hash_stride, uint32_t count_stride) {
+  const uint32_t c = blockIdx.x;
+  const uint64_t len = sample_starts[c + 1] - sample_starts[c];
+  if (len <= 1) return;
+  const L* lat = sample + sample_starts[c];
+  uint32_t* lb_out = lookbacks + out_starts[c];
+  L* r_out = resid + out_starts[c];
+  const uint32_t wlog = lookback_window_n_log(len);
+  const uint32_t window_n = 1u << wlog, hash_table_n = 1u << (wlog + 1), hash_mask = hash_table_n - 1;
+  uint32_t* table = hash_scratch + size_t(c) * hash_stride;   // [2][hash_table_n] last position of a bucket
+  uint32_t* counts = count_scratch + size_t(c) * count_stride;  // [min(window_n, len)] how often a lookback was used
+  const uint32_t n_counts = uint32_t(min(uint64_t(window_n), len));
+  for (uint32_t i = threadIdx.x; i < 2 * hash_table_n; i += blockDim.x) table[i] = 0;
+  for (uint32_t i = threadIdx.x; i < n_counts; i += blockDim.x) counts[i] = 1;
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  constexpr L MID = L(L(1) << (sizeof(L) * 8 - 1));
+  uint32_t proposed[LB_PROPOSED];
+#pragma unroll
+  for (uint32_t i = 0; i < LB_PROPOSED; i++) proposed[i] = 1;  // (i + 1).min(state_n), state_n = 1
+  uint32_t best_lookback = 1, repeating_idx = 0;
+  auto hash_fn = [&](uint64_t x) -> uint32_t {
+    x = (x ^ (x >> 32)) * 11400714819323197441ull;
+    x = x ^ (x >> 32);
+    return uint32_t(x) & hash_mask;
+  };
+  for (uint32_t i = 1; i < uint32_t(len); i++) {
+    const L l = lat[i];
+    const uint32_t new_brute = min(i, LB_PROPOSED);
+    proposed[new_brute - 1] = new_brute;
+    uint32_t proposal_idx = LB_BRUTE + LB_REPEATING, offset = 0;
+#pragma unroll
+    for (uint32_t coarse = 0; coarse < 2; coarse++) {  // COARSENESSES = [0, 8]
+      const uint64_t bucket = uint64_t(l) >> (coarse * 8);
+      const uint32_t h0 = hash_fn(bucket - 1), h1 = hash_fn(bucket), h2 = hash_fn(bucket + 1);
+      const uint32_t hs[3] = {h0, h1, h2};
+#pragma unroll
+      for (int t = 0; t < 3; t++) {
+        const uint32_t last = i - table[offset + hs[t]];
+        proposed[proposal_idx] = last <= window_n ? last : min(proposal_idx, i);
+        proposal_idx++;
+      }
+      table[offset + h1] = i;
+      offset += hash_table_n;
+    }
+    uint32_t best_goodness = 0, new_best = 0;
+#pragma unroll
+    for (uint32_t t = 0; t < LB_PROPOSED; t++) {
+      const uint32_t lookback = proposed[t];
+      const uint32_t cnt = counts[lookback - 1];
+      const L other = lat[i - lookback];
+      const uint32_t lookback_goodness = 32 - uint32_t(__clz(cnt));
+      const L d0 = L(l - other), d1 = L(other - l);
+      const L delta = d0 < d1 ? d0 : d1;
+      const uint32_t lz = sizeof(L) == 8 ? uint32_t(__clzll((long long)uint64_t(delta))) : uint32_t(__clz(uint32_t(delta))) - uint32_t(32 - sizeof(L) * 8);
+      const uint32_t goodness = lookback_goodness + lz;
+      if (goodness > best_goodness) { best_goodness = goodness; new_best = lookback; }
+    }
+    if (new_best != best_lookback) repeating_idx += 1;
+    proposed[LB_BRUTE + repeating_idx % LB_REPEATING] = new_best;
+    best_lookback = new_best;
+    lb_out[i - 1] = new_best;
+    r_out[i - 1] = L(L(l - lat[i - new_best]) + MID);
+    counts[new_best - 1] += 1;
+  }
+}
+
 // what the Auto delta search needs of a trial plan: bin count, table size and per bin (weight, offset bits) - 772 bytes per chunk
 struct PlanSummary { uint32_t n_bins, size_log; uint16_t weight[ENC_MAXB]; uint8_t ob[ENC_MAXB]; };
 __global__ void plan_summary_kernel(const VarPlan* __restrict__ plans, uint32_t n_chunks, PlanSummary* __restrict__ out) {
@@ -221,6 +307,21 @@ inline float sample_cost(const PlanSummary& p, uint32_t lbits, uint32_t order, u
   return float((meta_bits + 7) / 8 + (page_bits + 7) / 8 + (body_bits + 7) / 8);
 }
 
+// the same for the Lookback trial chunk: delta var (the lookbacks, u32) + primary (residuals, one latent of delta state per page)
+inline float lookback_sample_cost(const PlanSummary& d, const PlanSummary& p, uint32_t lbits, uint64_t n_stored) {
+  const uint64_t meta_bits = 4 + (4 + 5 + 5 + 64 + 32 * 32) + (4 + 15 + uint64_t(d.n_bins) * (d.size_log + 32 + offset_bits_bits(32))) +
+                             (4 + 15 + uint64_t(p.n_bins) * (p.size_log + lbits + offset_bits_bits(lbits)));
+  const uint64_t page_bits = 4ull * d.size_log + (uint64_t(lbits) + 4ull * p.size_log);
+  auto avg_bits = [](const PlanSummary& v) {
+    const double total_weight = double(uint64_t(1) << v.size_log);
+    double acc = 0.0;
+    for (uint32_t b = 0; b < v.n_bins; b++) acc += ((double(v.size_log) - std::log2(double(v.weight[b]))) + double(v.ob[b])) * double(v.weight[b]) / total_weight;
+    return acc;
+  };
+  const uint64_t body_bits = uint64_t(std::ceil(double(n_stored) * avg_bits(d))) + uint64_t(std::ceil(double(n_stored) * avg_bits(p)));
+  return float((meta_bits + 7) / 8 + (page_bits + 7) / 8 + (body_bits + 7) / 8);
+}
+
 // mode sample positions per chunk size (host, computed once per distinct n; sampling.rs:73-95)
 inline const std::vector<uint32_t>& mode_sample_positions(size_t n) {
   static std::mutex mu;
@@ -236,136 +337,24 @@ inline const std::vector<uint32_t>& mode_sample_positions(size_t n) {
   return it->second;
 }
 
+// K1+K2 and the planner for one set of chunks (a run of a call's chunks, the chunks' samples during the Auto delta search, or a trial
+// latent var of that search).  `e` describes the set (its own chunk_starts / row_base, counted from 0); plans and probes land in slots
+// 0 .. e.n_chunks - 1 of the scratch.  T is the latent width the set is planned in (the number's, or u32 for lookback indices).
 template <typename L>
-static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t n, uint32_t dtype, const PcoB200ChunkConfig& cfg, bool uniform_type,
-                                   void* dst, size_t dst_cap, void* index_dst, size_t index_cap, uint32_t flags, cudaStream_t stream,
-                                   CompressResult* res) {
-  const bool src_dev = flags & PCO_B200_SRC_ON_DEVICE, dst_dev = flags & PCO_B200_DST_ON_DEVICE;
-  const uint32_t lbits = sizeof(L) * 8;
+static PcoB200Error plan_front(CompressScratch& S, cudaStream_t stream, const EncParams& e, uint32_t tiles, size_t slots, uint32_t (&vrb)[MAX_VARS],
+                               const std::vector<uint64_t>& sizes, bool shared, L* (&d_lat)[2]) {
   constexpr int LW = sizeof(L) == 1 ? 0 : sizeof(L) == 2 ? 1 : sizeof(L) == 4 ? 2 : 3;
-  const bool is_float = nt_is_float(dtype);
-  // ---- config validation (pco/src/chunk_config.rs:269-314)
-  if (cfg.compression_level > 12) return fail(PCO_B200_INVALID_ARGUMENT, "compression level may not exceed 12");
-  if (cfg.delta_spec == PCO_B200_DELTA_TRY_CONSECUTIVE && cfg.delta_order > 7)
-    return fail(PCO_B200_INVALID_ARGUMENT, "consecutive delta order may not exceed 7");
-  if (lbits == 8 && !cfg.enable_8_bit)
-    return fail(PCO_B200_INVALID_ARGUMENT, "compressing 8-bit types with Pco is often a mistake; enable them on the ChunkConfig if you know what you're doing");
-  std::vector<uint64_t> pages;
-  if (PcoB200Error e = n_per_page(cfg, n, &pages)) return e;
-  for (uint64_t p : pages)
-    if (p > (uint64_t(1) << 24)) return fail(PCO_B200_INVALID_ARGUMENT, "count may not exceed 16777216 per chunk");
-  // ---- the explicit mode, if any (Auto is resolved per chunk below)
-  ModeSel explicit_mode;
-  bool auto_mode = false;
-  switch (cfg.mode_spec) {
-    case PCO_B200_MODE_CLASSIC: break;
-    case PCO_B200_MODE_TRY_INT_MULT:
-      if (is_float) return fail(PCO_B200_INVALID_ARGUMENT, "unable to use int mult mode on floats");
-      explicit_mode.mode = MODE_INT_MULT;
-      explicit_mode.mode_base = lbits == 64 ? cfg.int_mult_base : (cfg.int_mult_base & ((uint64_t(1) << lbits) - 1));
-      if (explicit_mode.mode_base == 0) return fail(PCO_B200_INVALID_ARGUMENT, "The chosen mode of IntMult(0) was invalid");
-      break;
-    case PCO_B200_MODE_TRY_FLOAT_QUANT: {
-      if (!is_float) return fail(PCO_B200_INVALID_ARGUMENT, "unable to use float mode for ints");
-      uint32_t precision = lbits == 64 ? 52 : lbits == 32 ? 23 : 10;
-      if (cfg.float_quant_k == 0 || cfg.float_quant_k > precision) return fail(PCO_B200_INVALID_ARGUMENT, "The chosen mode of FloatQuant was invalid");
-      explicit_mode.mode = MODE_FLOAT_QUANT;
-      explicit_mode.mode_k = cfg.float_quant_k;
-      break;
-    }
-    case PCO_B200_MODE_TRY_FLOAT_MULT: {
-      if (!is_float) return fail(PCO_B200_INVALID_ARGUMENT, "unable to use float mode for ints");
-      if (lbits == 16) return fail(PCO_B200_UNSUPPORTED, "f16 FloatMult is outside the GPU hot path");
-      const bool finite_nonzero = lbits == 64 ? (std::isfinite(cfg.float_mult_base) && cfg.float_mult_base != 0.0)
-                                              : (std::isfinite(float(cfg.float_mult_base)) && float(cfg.float_mult_base) != 0.0f);
-      if (!finite_nonzero) return fail(PCO_B200_INVALID_ARGUMENT, "The chosen mode of FloatMult was invalid");
-      if (lbits == 64) set_float_mult(&explicit_mode, 64, cfg.float_mult_base, 1.0 / cfg.float_mult_base);
-      else set_float_mult(&explicit_mode, 32, double(float(cfg.float_mult_base)), double(1.0f / float(cfg.float_mult_base)));
-      break;
-    }
-    case PCO_B200_MODE_AUTO: auto_mode = true; break;
-    default: return fail(PCO_B200_UNSUPPORTED, "ModeSpec::TryDict is outside the GPU hot path");
-  }
-  bool auto_delta = false;
-  uint32_t explicit_order = 0;
-  switch (cfg.delta_spec) {
-    case PCO_B200_DELTA_NOOP: break;
-    case PCO_B200_DELTA_TRY_CONSECUTIVE: explicit_order = cfg.delta_order; break;
-    case PCO_B200_DELTA_AUTO: auto_delta = true; break;  // resolved per chunk below by the sampled search
-    case PCO_B200_DELTA_TRY_CONV1:
-      if (cfg.delta_order == 0) break;
-      return fail(PCO_B200_UNSUPPORTED, "DeltaSpec::TryConv1 is outside the GPU hot path");
-    default: return fail(PCO_B200_UNSUPPORTED, "DeltaSpec::TryLookback is outside the GPU hot path");
-  }
-  const bool chunks_only = flags & PCO_B200_CHUNKS_ONLY;
-  std::vector<uint8_t> header = make_standalone_header(n, uint8_t(uniform_type ? dtype : 0));
-  if (chunks_only) header.clear();
-  // empty input: header + terminator only (standalone/simple.rs:62-91)
-  if (n == 0) {
-    if (!chunks_only) header.push_back(0);
-    if (header.size() > dst_cap) return fail(PCO_B200_IO, "failed to write whole buffer");
-    if (dst_dev && !header.empty()) PCOB_CUDA_TRY(cudaMemcpyAsync(dst, header.data(), header.size(), cudaMemcpyHostToDevice, stream));
-    else if (!header.empty()) std::memcpy(dst, header.data(), header.size());
-    PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
-    res->total_bytes = header.size();
-    if (index_dst && index_cap >= sizeof(IndexHeader)) {
-      IndexHeader ih;
-      std::memset(&ih, 0, sizeof(ih));
-      ih.magic = INDEX_MAGIC; ih.version = 1; ih.file_len = header.size(); ih.chunks_offset = sizeof(IndexHeader); ih.end_byte = header.size();
-      std::memcpy(index_dst, &ih, sizeof(ih));
-      res->index_bytes = sizeof(ih);
-    }
-    return PCO_B200_OK;
-  }
-  const uint32_t n_chunks_all = uint32_t(pages.size());
-  std::vector<uint64_t> starts(pages.size() + 1, 0);
-  uint64_t max_chunk_n = 0;
-  for (size_t i = 0; i < pages.size(); i++) { starts[i + 1] = starts[i] + pages[i]; max_chunk_n = std::max<uint64_t>(max_chunk_n, pages[i]); }
-  // unoptimized_bins_log is a function of each chunk's n; the kernels take one value per call, so every chunk must agree
-  const bool shared_bins = (flags & PCO_B200_INTERNAL_SHARED_BINS) && pages.size() > 1;
-  uint32_t bins_log = choose_unoptimized_bins_log(cfg.compression_level, shared_bins ? n : size_t(pages[0]));
-  if (!shared_bins)
-    for (uint64_t p : pages)
-      if (choose_unoptimized_bins_log(cfg.compression_level, size_t(p)) != bins_log)
-        return fail(PCO_B200_UNSUPPORTED, "chunks whose sizes imply different unoptimized_bins_log in one call");
-  if (bins_log > 8) return fail(PCO_B200_UNSUPPORTED, "compression levels that train more than 256 bins are outside the GPU hot path");
-
-  // ---- the numbers in HBM
-  const void* d_nums = nums;
-  DevBuf& in_stage = S.index;  // a dedicated input staging buffer when nums live on the host (kept apart from the sort buffers)
-  if (!src_dev) {
-    PCOB_CUDA_TRY(in_stage.reserve(n * sizeof(L) + 64));
-    PCOB_CUDA_TRY(cudaMemcpyAsync(in_stage.p, nums, n * sizeof(L), cudaMemcpyHostToDevice, stream));
-    d_nums = in_stage.p;
-  }
-  // scratch sized for the whole call; every run below (and the Auto searches) indexes it from 0
-  std::vector<uint64_t> rows_all(pages.size() + 1, 0);
-  for (size_t i = 0; i < pages.size(); i++) rows_all[i + 1] = rows_all[i] + ((pages[i] + BATCH_N - 1) / BATCH_N) * BATCH_N;
-  const uint32_t bpc_all = n_batches_of(uint32_t(max_chunk_n));
-  PCOB_CUDA_TRY(S.plans.reserve(size_t(n_chunks_all) * MAX_VARS * sizeof(VarPlan)));
-  PCOB_CUDA_TRY(S.chunks.reserve(size_t(n_chunks_all) * sizeof(ChunkEnc)));
-  PCOB_CUDA_TRY(S.starts.reserve((starts.size() + 1) * 32));
-  PCOB_CUDA_TRY(S.seg.reserve(size_t(n_chunks_all) * 16));
-  PCOB_CUDA_TRY(S.small.reserve(256 + header.size()));
-  PCOB_CUDA_TRY(S.probes.reserve(size_t(n_chunks_all) * sizeof(PlanProbes)));
+  constexpr size_t RS_SMEM = size_t(RS_WARPS) * RS_BINS * sizeof(uint32_t);
   ChunkEnc* d_chunks = S.chunks.as<ChunkEnc>();
   VarPlan* d_plans = S.plans.as<VarPlan>();
   PlanProbes* d_probes = S.probes.as<PlanProbes>();
-  uint32_t* d_small = S.small.as<uint32_t>();  // [0]: range bits, [2..3]: total bytes (u64), header at byte 64
-  uint64_t* d_total = reinterpret_cast<uint64_t*>(d_small + 2);
-  uint8_t* d_header = reinterpret_cast<uint8_t*>(d_small) + 64;
-  if (!header.empty()) PCOB_CUDA_TRY(cudaMemcpyAsync(d_header, header.data(), header.size(), cudaMemcpyHostToDevice, stream));
-
-  // ---- K1+K2 and the planner for one set of chunks (a run of the call's chunks, or the chunks' samples during the Auto delta search).
-  // `e` describes the set (its own chunk_starts / row_base, counted from 0); plans and probes land in slots 0 .. e.n_chunks - 1.
-  L* d_lat[2] = {nullptr, nullptr};
-  constexpr size_t RS_SMEM = size_t(RS_WARPS) * RS_BINS * sizeof(uint32_t);
+  uint32_t* d_small = S.small.as<uint32_t>();
   auto ensure_sort_attr = [&]() -> cudaError_t {
     if (S.sort_attr_set[LW]) return cudaSuccess;
     S.sort_attr_set[LW] = true;
     return cudaFuncSetAttribute(radix_sort_segments_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM);
   };
-  auto front = [&](const EncParams& e, uint32_t tiles, size_t slots, uint32_t (&vrb)[MAX_VARS], const std::vector<uint64_t>& sizes, bool shared) -> PcoB200Error {
+
     const uint32_t n_chunks = e.n_chunks;
     PCOB_CUDA_TRY(S.lat0.reserve(slots * sizeof(L) + 64));
     if (e.n_vars > 1) PCOB_CUDA_TRY(S.lat1.reserve(slots * sizeof(L) + 64));
@@ -517,6 +506,133 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
       profiler().end(stream);
     }
     return PCO_B200_OK;
+}
+
+template <typename L>
+static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t n, uint32_t dtype, const PcoB200ChunkConfig& cfg, bool uniform_type,
+                                   void* dst, size_t dst_cap, void* index_dst, size_t index_cap, uint32_t flags, cudaStream_t stream,
+                                   CompressResult* res) {
+  const bool src_dev = flags & PCO_B200_SRC_ON_DEVICE, dst_dev = flags & PCO_B200_DST_ON_DEVICE;
+  const uint32_t lbits = sizeof(L) * 8;
+  constexpr int LW = sizeof(L) == 1 ? 0 : sizeof(L) == 2 ? 1 : sizeof(L) == 4 ? 2 : 3;
+  const bool is_float = nt_is_float(dtype);
+  // ---- config validation (pco/src/chunk_config.rs:269-314)
+  if (cfg.compression_level > 12) return fail(PCO_B200_INVALID_ARGUMENT, "compression level may not exceed 12");
+  if (cfg.delta_spec == PCO_B200_DELTA_TRY_CONSECUTIVE && cfg.delta_order > 7)
+    return fail(PCO_B200_INVALID_ARGUMENT, "consecutive delta order may not exceed 7");
+  if (lbits == 8 && !cfg.enable_8_bit)
+    return fail(PCO_B200_INVALID_ARGUMENT, "compressing 8-bit types with Pco is often a mistake; enable them on the ChunkConfig if you know what you're doing");
+  std::vector<uint64_t> pages;
+  if (PcoB200Error e = n_per_page(cfg, n, &pages)) return e;
+  for (uint64_t p : pages)
+    if (p > (uint64_t(1) << 24)) return fail(PCO_B200_INVALID_ARGUMENT, "count may not exceed 16777216 per chunk");
+  // ---- the explicit mode, if any (Auto is resolved per chunk below)
+  ModeSel explicit_mode;
+  bool auto_mode = false;
+  switch (cfg.mode_spec) {
+    case PCO_B200_MODE_CLASSIC: break;
+    case PCO_B200_MODE_TRY_INT_MULT:
+      if (is_float) return fail(PCO_B200_INVALID_ARGUMENT, "unable to use int mult mode on floats");
+      explicit_mode.mode = MODE_INT_MULT;
+      explicit_mode.mode_base = lbits == 64 ? cfg.int_mult_base : (cfg.int_mult_base & ((uint64_t(1) << lbits) - 1));
+      if (explicit_mode.mode_base == 0) return fail(PCO_B200_INVALID_ARGUMENT, "The chosen mode of IntMult(0) was invalid");
+      break;
+    case PCO_B200_MODE_TRY_FLOAT_QUANT: {
+      if (!is_float) return fail(PCO_B200_INVALID_ARGUMENT, "unable to use float mode for ints");
+      uint32_t precision = lbits == 64 ? 52 : lbits == 32 ? 23 : 10;
+      if (cfg.float_quant_k == 0 || cfg.float_quant_k > precision) return fail(PCO_B200_INVALID_ARGUMENT, "The chosen mode of FloatQuant was invalid");
+      explicit_mode.mode = MODE_FLOAT_QUANT;
+      explicit_mode.mode_k = cfg.float_quant_k;
+      break;
+    }
+    case PCO_B200_MODE_TRY_FLOAT_MULT: {
+      if (!is_float) return fail(PCO_B200_INVALID_ARGUMENT, "unable to use float mode for ints");
+      if (lbits == 16) return fail(PCO_B200_UNSUPPORTED, "f16 FloatMult is outside the GPU hot path");
+      const bool finite_nonzero = lbits == 64 ? (std::isfinite(cfg.float_mult_base) && cfg.float_mult_base != 0.0)
+                                              : (std::isfinite(float(cfg.float_mult_base)) && float(cfg.float_mult_base) != 0.0f);
+      if (!finite_nonzero) return fail(PCO_B200_INVALID_ARGUMENT, "The chosen mode of FloatMult was invalid");
+      if (lbits == 64) set_float_mult(&explicit_mode, 64, cfg.float_mult_base, 1.0 / cfg.float_mult_base);
+      else set_float_mult(&explicit_mode, 32, double(float(cfg.float_mult_base)), double(1.0f / float(cfg.float_mult_base)));
+      break;
+    }
+    case PCO_B200_MODE_AUTO: auto_mode = true; break;
+    default: return fail(PCO_B200_UNSUPPORTED, "ModeSpec::TryDict is outside the GPU hot path");
+  }
+  bool auto_delta = false;
+  uint32_t explicit_order = 0;
+  switch (cfg.delta_spec) {
+    case PCO_B200_DELTA_NOOP: break;
+    case PCO_B200_DELTA_TRY_CONSECUTIVE: explicit_order = cfg.delta_order; break;
+    case PCO_B200_DELTA_AUTO: auto_delta = true; break;  // resolved per chunk below by the sampled search
+    case PCO_B200_DELTA_TRY_CONV1:
+      if (cfg.delta_order == 0) break;
+      return fail(PCO_B200_UNSUPPORTED, "DeltaSpec::TryConv1 is outside the GPU hot path");
+    default: return fail(PCO_B200_UNSUPPORTED, "DeltaSpec::TryLookback is outside the GPU hot path");
+  }
+  const bool chunks_only = flags & PCO_B200_CHUNKS_ONLY;
+  std::vector<uint8_t> header = make_standalone_header(n, uint8_t(uniform_type ? dtype : 0));
+  if (chunks_only) header.clear();
+  // empty input: header + terminator only (standalone/simple.rs:62-91)
+  if (n == 0) {
+    if (!chunks_only) header.push_back(0);
+    if (header.size() > dst_cap) return fail(PCO_B200_IO, "failed to write whole buffer");
+    if (dst_dev && !header.empty()) PCOB_CUDA_TRY(cudaMemcpyAsync(dst, header.data(), header.size(), cudaMemcpyHostToDevice, stream));
+    else if (!header.empty()) std::memcpy(dst, header.data(), header.size());
+    PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
+    res->total_bytes = header.size();
+    if (index_dst && index_cap >= sizeof(IndexHeader)) {
+      IndexHeader ih;
+      std::memset(&ih, 0, sizeof(ih));
+      ih.magic = INDEX_MAGIC; ih.version = 1; ih.file_len = header.size(); ih.chunks_offset = sizeof(IndexHeader); ih.end_byte = header.size();
+      std::memcpy(index_dst, &ih, sizeof(ih));
+      res->index_bytes = sizeof(ih);
+    }
+    return PCO_B200_OK;
+  }
+  const uint32_t n_chunks_all = uint32_t(pages.size());
+  std::vector<uint64_t> starts(pages.size() + 1, 0);
+  uint64_t max_chunk_n = 0;
+  for (size_t i = 0; i < pages.size(); i++) { starts[i + 1] = starts[i] + pages[i]; max_chunk_n = std::max<uint64_t>(max_chunk_n, pages[i]); }
+  // unoptimized_bins_log is a function of each chunk's n; the kernels take one value per call, so every chunk must agree
+  const bool shared_bins = (flags & PCO_B200_INTERNAL_SHARED_BINS) && pages.size() > 1;
+  uint32_t bins_log = choose_unoptimized_bins_log(cfg.compression_level, shared_bins ? n : size_t(pages[0]));
+  if (!shared_bins)
+    for (uint64_t p : pages)
+      if (choose_unoptimized_bins_log(cfg.compression_level, size_t(p)) != bins_log)
+        return fail(PCO_B200_UNSUPPORTED, "chunks whose sizes imply different unoptimized_bins_log in one call");
+  if (bins_log > 8) return fail(PCO_B200_UNSUPPORTED, "compression levels that train more than 256 bins are outside the GPU hot path");
+
+  // ---- the numbers in HBM
+  const void* d_nums = nums;
+  DevBuf& in_stage = S.index;  // a dedicated input staging buffer when nums live on the host (kept apart from the sort buffers)
+  if (!src_dev) {
+    PCOB_CUDA_TRY(in_stage.reserve(n * sizeof(L) + 64));
+    PCOB_CUDA_TRY(cudaMemcpyAsync(in_stage.p, nums, n * sizeof(L), cudaMemcpyHostToDevice, stream));
+    d_nums = in_stage.p;
+  }
+  // scratch sized for the whole call; every run below (and the Auto searches) indexes it from 0
+  std::vector<uint64_t> rows_all(pages.size() + 1, 0);
+  for (size_t i = 0; i < pages.size(); i++) rows_all[i + 1] = rows_all[i] + ((pages[i] + BATCH_N - 1) / BATCH_N) * BATCH_N;
+  const uint32_t bpc_all = n_batches_of(uint32_t(max_chunk_n));
+  PCOB_CUDA_TRY(S.plans.reserve(size_t(n_chunks_all) * MAX_VARS * sizeof(VarPlan)));
+  PCOB_CUDA_TRY(S.chunks.reserve(size_t(n_chunks_all) * sizeof(ChunkEnc)));
+  PCOB_CUDA_TRY(S.starts.reserve((starts.size() + 1) * 32));
+  PCOB_CUDA_TRY(S.seg.reserve(size_t(n_chunks_all) * 16));
+  PCOB_CUDA_TRY(S.small.reserve(256 + header.size()));
+  PCOB_CUDA_TRY(S.probes.reserve(size_t(n_chunks_all) * sizeof(PlanProbes)));
+  ChunkEnc* d_chunks = S.chunks.as<ChunkEnc>();
+  VarPlan* d_plans = S.plans.as<VarPlan>();
+  PlanProbes* d_probes = S.probes.as<PlanProbes>();
+  uint32_t* d_small = S.small.as<uint32_t>();  // [0]: range bits, [2..3]: total bytes (u64), header at byte 64
+  uint64_t* d_total = reinterpret_cast<uint64_t*>(d_small + 2);
+  uint8_t* d_header = reinterpret_cast<uint8_t*>(d_small) + 64;
+  if (!header.empty()) PCOB_CUDA_TRY(cudaMemcpyAsync(d_header, header.data(), header.size(), cudaMemcpyHostToDevice, stream));
+
+  // ---- K1+K2 and the planner for one set of chunks (a run of the call's chunks, or the chunks' samples during the Auto delta search).
+  // `e` describes the set (its own chunk_starts / row_base, counted from 0); plans and probes land in slots 0 .. e.n_chunks - 1.
+  L* d_lat[2] = {nullptr, nullptr};
+  auto front = [&](const EncParams& e, uint32_t tiles, size_t slots, uint32_t (&vrb)[MAX_VARS], const std::vector<uint64_t>& sizes, bool shared) -> PcoB200Error {
+    return plan_front<L>(S, stream, e, tiles, slots, vrb, sizes, shared, d_lat);
   };
 
   // ---- ModeSpec::Auto and DeltaSpec::Auto are the reference's PER-CHUNK searches (chunk_compressor.rs:396-440): every chunk of the
@@ -591,7 +707,8 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
     // choose_auto_delta_encoding (chunk_compressor.rs:310-360) per chunk: the sample of the chunk's primary latents (sampling.rs:21-60) is
     // trial-compressed in Classic mode with NoOp, then consecutive orders 1, 2, ... while the cost keeps falling.  Every order is planned
     // for all chunks at once by the ordinary front end + planner kernels; the costs are the reference's f32 formula (sample_cost).
-    // The Lookback candidate (chunk_compressor.rs:326-338) is not evaluated: where it would win this path writes a consecutive order.
+    // The Lookback candidate (chunk_compressor.rs:326-338) is weighed like the reference does; this path does not ENCODE Lookback, so a
+    // chunk on which it wins makes the call fail with PCO_B200_UNSUPPORTED rather than write bytes the reference would not.
     std::vector<uint64_t> s_starts(n_units + 1, 0), s_rows(n_units + 1, 0), s_sizes(n_units, 0), ustarts(n_units + 1, 0);
     uint64_t max_ns = 0;
     for (size_t u = 0; u < n_units; u++) {
@@ -636,7 +753,7 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
       const uint32_t s_tiles = uint32_t((max_ns + SPLIT_TILE - 1) / SPLIT_TILE);
       std::vector<PlanSummary> h_sum(n_units);
       std::vector<float> best_cost(n_units, 0.f);
-      std::vector<uint8_t> open(n_units, 1);
+      std::vector<uint8_t> open(n_units, 1), lookback_best(n_units, 0);
       size_t n_open = n_units;
       for (uint32_t k = 0; k <= MAX_ORDER && n_open > 0; k++) {
         es.order = k;
@@ -651,10 +768,80 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
           if (s_sizes[u] == 0) { open[u] = 0; n_open--; continue; }  // no sample: NoOp (chunk_compressor.rs:314-316)
           const float cost = sample_cost(h_sum[u], lbits, k, s_sizes[u]);
           if (k == 0) best_cost[u] = cost;
-          else if (cost < best_cost[u]) { best_cost[u] = cost; unit_order[u] = k; }
+          else if (cost < best_cost[u]) { best_cost[u] = cost; unit_order[u] = k; lookback_best[u] = 0; }
           else { open[u] = 0; n_open--; }  // "it's almost always convex" (chunk_compressor.rs:347-357)
         }
+        if (k == 0 && n_open > 0) {
+          // ---- the Lookback candidate (chunk_compressor.rs:326-338), weighed right after NoOp: the sample is lookback-encoded on the
+          // device (lookback_trial_kernel), its two latent vars - the lookbacks as u32, the residuals in the number's width - are
+          // planned by the ordinary kernels, and the cost is the same f32 formula plus the required-savings penalty
+          bool any = false;
+          for (size_t u = 0; u < n_units; u++) any = any || (open[u] && best_cost[u] > 0.25f * float(s_sizes[u]));
+          if (any) {
+            std::vector<uint64_t> lb_starts(n_units + 1, 0), lb_rows(n_units + 1, 0), lb_sizes(n_units, 0);
+            uint64_t max_lb = 0;
+            for (size_t u = 0; u < n_units; u++) {
+              lb_sizes[u] = s_sizes[u] > 0 ? s_sizes[u] - 1 : 0;  // state_n = 1
+              lb_starts[u + 1] = lb_starts[u] + lb_sizes[u];
+              lb_rows[u + 1] = lb_rows[u] + ((lb_sizes[u] + BATCH_N - 1) / BATCH_N) * BATCH_N;
+              max_lb = std::max(max_lb, lb_sizes[u]);
+            }
+            const uint32_t wlog_max = lookback_window_n_log(std::max<uint64_t>(max_ns, 2));
+            const uint32_t hash_stride = 2u << (wlog_max + 1), count_stride = 1u << wlog_max;
+            PCOB_CUDA_TRY(S.lb_vals.reserve(lb_starts.back() * 4 + 64));
+            PCOB_CUDA_TRY(S.lb_resid.reserve(lb_starts.back() * sizeof(L) + 64));
+            PCOB_CUDA_TRY(S.lb_scratch.reserve(n_units * (size_t(hash_stride) + count_stride) * 4 + 3 * (n_units + 1) * 8 + 64));
+            uint32_t* d_hash = S.lb_scratch.as<uint32_t>();
+            uint32_t* d_cnt = d_hash + n_units * size_t(hash_stride);
+            uint64_t* d_lbs = reinterpret_cast<uint64_t*>(d_cnt + n_units * size_t(count_stride));
+            uint64_t* d_lbrows = d_lbs + (n_units + 1);
+            PCOB_CUDA_TRY(cudaMemcpyAsync(d_lbs, lb_starts.data(), lb_starts.size() * 8, cudaMemcpyHostToDevice, stream));
+            PCOB_CUDA_TRY(cudaMemcpyAsync(d_lbrows, lb_rows.data(), lb_rows.size() * 8, cudaMemcpyHostToDevice, stream));
+            lookback_trial_kernel<L><<<uint32_t(n_units), 128, 0, stream>>>(S.sample.as<L>(), d_ss, d_lbs, S.lb_vals.as<uint32_t>(), S.lb_resid.as<L>(), d_hash, d_cnt,
+                                                                            hash_stride, count_stride);
+            PCOB_CUDA_TRY(cudaGetLastError());
+            EncParams el = es;
+            el.order = 0;
+            el.chunk_starts = d_lbs;
+            el.row_base = d_lbrows;
+            el.n_total = lb_starts.back();
+            el.max_chunk_n = uint32_t(max_lb);
+            const uint32_t l_tiles = uint32_t((max_lb + SPLIT_TILE - 1) / SPLIT_TILE);
+            std::vector<PlanSummary> sum_d(n_units), sum_p(n_units);
+            {  // the delta var: lookbacks, planned as u32 with the chunk's unoptimized_bins_log (chunk_compressor.rs:238-248)
+              EncParams ed = el;
+              ed.dtype = NT_U32;
+              ed.nums = S.lb_vals.p;
+              uint32_t vrb[MAX_VARS] = {64, 64};
+              uint32_t* lat32[2] = {nullptr, nullptr};
+              if (PcoB200Error e = plan_front<uint32_t>(S, stream, ed, l_tiles, size_t(lb_rows.back()), vrb, lb_sizes, false, lat32)) return e;
+              PCOB_CUDA_TRY(cudaGetLastError());
+              plan_summary_kernel<<<uint32_t(n_units), 128, 0, stream>>>(d_plans, uint32_t(n_units), d_sum);
+              PCOB_CUDA_TRY(cudaMemcpyAsync(sum_d.data(), d_sum, n_units * sizeof(PlanSummary), cudaMemcpyDeviceToHost, stream));
+              PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
+            }
+            {  // the primary: residuals
+              EncParams epr = el;
+              epr.nums = S.lb_resid.p;
+              uint32_t vrb[MAX_VARS] = {64, 64};
+              if (PcoB200Error e = front(epr, l_tiles, size_t(lb_rows.back()), vrb, lb_sizes, false)) return e;
+              PCOB_CUDA_TRY(cudaGetLastError());
+              plan_summary_kernel<<<uint32_t(n_units), 128, 0, stream>>>(d_plans, uint32_t(n_units), d_sum);
+              PCOB_CUDA_TRY(cudaMemcpyAsync(sum_p.data(), d_sum, n_units * sizeof(PlanSummary), cudaMemcpyDeviceToHost, stream));
+              PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
+            }
+            for (size_t u = 0; u < n_units; u++) {
+              const float penalty = 0.25f * float(s_sizes[u]);  // LOOKBACK_REQUIRED_BYTE_SAVINGS_PER_N * sample_n
+              if (!open[u] || !(best_cost[u] > penalty) || lb_sizes[u] == 0) continue;
+              const float cost = lookback_sample_cost(sum_d[u], sum_p[u], lbits, lb_sizes[u]) + penalty;
+              if (cost < best_cost[u]) { best_cost[u] = cost; lookback_best[u] = 1; }
+            }
+          }
+        }
       }
+      for (size_t u = 0; u < n_units; u++)
+        if (lookback_best[u])
+          return fail(PCO_B200_UNSUPPORTED, "DeltaSpec::Auto: the Lookback delta wins on chunk " + std::to_string(u) + "; the GPU hot path does not encode Lookback (pass a consecutive DeltaSpec)");
     }
   }
 

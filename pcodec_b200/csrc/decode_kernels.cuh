@@ -425,8 +425,11 @@ __device__ inline uint32_t walk_chunk_serial(const BitSrc& src, const ChunkHdr& 
   return ST_OK;
 }
 
+// 64 threads build the tables, one of them walks: with <= 64 threads the register file lets 8 CTAs of up to 128 registers share an SM (1024
+// chunks in one wave) and the walker keeps its loop-invariant shared addresses in registers (at 64 registers it re-derived them per step)
+constexpr int WALK_THREADS = 64;
 template <int CAP_LOG>
-__global__ void __launch_bounds__(128) walk_kernel(FileParams fp, uint8_t* index_base, uint64_t chunks_offset, uint32_t max_chunks,
+__global__ void __launch_bounds__(WALK_THREADS, 8) walk_kernel(FileParams fp, uint8_t* index_base, uint64_t chunks_offset, uint32_t max_chunks,
                                                    uint64_t entries_begin, uint64_t entries_cap_end, uint64_t first_chunk_byte,
                                                    uint64_t first_out_offset, uint64_t stop_after_total, uint32_t* statuses, WalkResult* result,
                                                    int serial_file_mode) {

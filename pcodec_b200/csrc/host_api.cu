@@ -299,7 +299,7 @@ static PcoB200Error decompress_fast(const void* compressed, size_t compressed_le
     PCOB_CUDA_TRY(c.index.reserve(entries_begin + entries_bytes));
     uint8_t* d_index = c.index.as<uint8_t>();
     profiler().begin("walk_kernel", stream);
-    walk_kernel<12><<<1, 128, sizeof(WalkSmem<12>), stream>>>(fp, d_index, chunks_offset, max_chunks, entries_begin, entries_begin + entries_bytes,
+    walk_kernel<12><<<1, WALK_THREADS, sizeof(WalkSmem<12>), stream>>>(fp, d_index, chunks_offset, max_chunks, entries_begin, entries_begin + entries_bytes,
                                                       next_byte, out_off, uint64_t(dst_len), nullptr, d_res, 1);
     profiler().end(stream);
     PCOB_CUDA_TRY(cudaGetLastError());
@@ -843,7 +843,7 @@ PcoB200Error pco_b200_decompress_chunks(const void* compressed, size_t compresse
   PCOB_CUDA_TRY(c.misc.reserve(sizeof(WalkResult)));
   PCOB_CUDA_TRY(cudaMemsetAsync(c.statuses.p, 0xff, n_chunks * sizeof(uint32_t), stream));
   profiler().begin("walk_kernel", stream);
-  walk_kernel<SMALL_MAX_SIZE_LOG><<<uint32_t(n_chunks), 128, sizeof(WalkSmem<SMALL_MAX_SIZE_LOG>), stream>>>(
+  walk_kernel<SMALL_MAX_SIZE_LOG><<<uint32_t(n_chunks), WALK_THREADS, sizeof(WalkSmem<SMALL_MAX_SIZE_LOG>), stream>>>(
       fp, d_index, chunks_offset, uint32_t(n_chunks), 0, off, 0, 0, ~uint64_t(0), c.statuses.as<uint32_t>(), c.misc.as<WalkResult>(), 0);
   profiler().end(stream);
   PCOB_CUDA_TRY(cudaGetLastError());
@@ -903,7 +903,7 @@ PcoB200Error pco_b200_build_index(const void* compressed, size_t compressed_len,
   PCOB_CUDA_TRY(c.index.reserve(index_cap));
   PCOB_CUDA_TRY(c.misc.reserve(sizeof(WalkResult)));
   uint8_t* d_index = c.index.as<uint8_t>();
-  walk_kernel<12><<<1, 128, sizeof(WalkSmem<12>), stream>>>(fp, d_index, chunks_offset, uint32_t(max_chunks), entries_begin, index_cap, hdr.first_chunk_byte,
+  walk_kernel<12><<<1, WALK_THREADS, sizeof(WalkSmem<12>), stream>>>(fp, d_index, chunks_offset, uint32_t(max_chunks), entries_begin, index_cap, hdr.first_chunk_byte,
                                                     0, ~uint64_t(0), nullptr, c.misc.as<WalkResult>(), 1);
   PCOB_CUDA_TRY(cudaGetLastError());
   WalkResult res;

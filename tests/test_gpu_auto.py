@@ -95,3 +95,24 @@ def test_reference_abi_with_null_config_is_byte_identical(oracle, dtype_byte, dt
     assert rc == 0
     want = oracle.simple_compress(nums, oracle.make_config(mode=oracle.MODE_AUTO, delta=oracle.DELTA_AUTO, enable_8_bit=True), uniform_type=True)
     assert dst[: nw.value].tobytes() == want
+
+
+def test_auto_refuses_loudly_where_lookback_wins(sa, oracle):
+    """The reference's Auto delta also weighs Lookback (chunk_compressor.rs:326-338).  This path weighs it the same way but does not encode
+    it: on a chunk where it wins the call fails with Unsupported instead of writing bytes the reference would not write."""
+    from pcodec_b200 import PcoError
+
+    rng = np.random.default_rng(1)
+    motif = rng.integers(0, 1 << 30, size=97)
+    nums = np.tile(motif, 700)[:60000].astype(np.uint32)
+    ours_cfg, their_cfg = _auto_cfgs(oracle)
+    info = oracle.inspect(oracle.simple_compress(nums, their_cfg), np.uint32)
+    assert info["chunks"][0]["delta"] == 2, "the oracle is expected to pick Lookback on a repeating motif"
+    with pytest.raises(PcoError) as e:
+        sa.simple_compress(nums, ours_cfg)
+    assert e.value.kind == "Unsupported"
+    # a chunk before it that picks a consecutive order does not change that
+    walk = np.cumsum(rng.geometric(0.01, size=30000)).astype(np.uint32)
+    with pytest.raises(PcoError) as e:
+        sa.simple_compress(np.concatenate([walk, nums[:30000]]), _auto_cfgs(oracle, 30000)[0])
+    assert e.value.kind == "Unsupported"
