@@ -252,7 +252,7 @@ __device__ __forceinline__ void fused_undelta(L (&x)[8], FusedSmem& sm, uint32_t
     for (int j = 0; j < K; j++) {
       L acc = c[j];
 #pragma unroll
-      for (int t = 0; j + t < K; t++) acc = L(acc + L(L(bf[t]) * m[j + t]));
+      for (int t = 0; j + t < K; t++) acc = L(acc + L(bf[t] * uint64_t(m[j + t])));
       sm.mo.mvec[nslot][j] = uint64_t(acc);
     }
     __threadfence_block();
@@ -263,7 +263,7 @@ __device__ __forceinline__ void fused_undelta(L (&x)[8], FusedSmem& sm, uint32_t
   for (int j = 0; j < K; j++) {
     L acc = 0;
 #pragma unroll
-    for (int t = 0; j + t < K; t++) acc = L(acc + L(L(bl[t]) * m[j + t]));
+    for (int t = 0; j + t < K; t++) acc = L(acc + L(bl[t] * uint64_t(m[j + t])));
     sft[j] = acc;
   }
 #pragma unroll
@@ -411,9 +411,9 @@ __device__ __forceinline__ void fused_decoder(FusedSmem& sm, const FileParams& f
       } while (fl != b + 1);
       const L m = L(m64);
       if (lane == 0)
-        asm volatile("st.volatile.shared.v2.u64 [%0], {%1, %2};" ::"r"(link_sa + 16 * nslot), "l"(uint64_t(L(L(m + L(base << 8)) + L(totT)))),
+        asm volatile("st.volatile.shared.v2.u64 [%0], {%1, %2};" ::"r"(link_sa + 16 * nslot), "l"(uint64_t(L(L(m + L(uint64_t(base) << 8)) + L(totT)))),
                      "l"(uint64_t(b + 2)) : "memory");
-      L D = L(L(m + L(base * L(lane * 8))) + L(incT - T));
+      L D = L(L(m + L(uint64_t(base) * uint64_t(lane * 8))) + L(incT - T));
       res[0] = D;
 #pragma unroll
       for (int e = 1; e < 8; e++) {
@@ -426,7 +426,7 @@ __device__ __forceinline__ void fused_decoder(FusedSmem& sm, const FileParams& f
       for (int e = 0; e < 8; e++) res[e] = from_latent_kind<L>(res[e], kind);
     }
     const uint32_t out_cnt = min(uint32_t(BATCH_N), n_out - b * BATCH_N);
-    if (out_cnt == uint32_t(BATCH_N) && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    if (out_cnt == uint32_t(BATCH_N) && (reinterpret_cast<uintptr_t>(dst) & (sizeof(L) >= 4 ? 15 : sizeof(L) * 8 - 1)) == 0) {
       store8<L>(dst, res);
     } else {
 #pragma unroll
@@ -525,7 +525,7 @@ fused_narrow_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, const 
   const uint32_t n_vars = sm.hdr.n_vars;
   const VarHdr vh0 = sm.hdr.var[0];
   // everything the general kernels serve is handed over untouched
-  const bool candidate = n_vars == 1 && sm.hdr.mode == MODE_CLASSIC && vh0.latent_bits >= 32 && vh0.n_bins >= 2 &&
+  const bool candidate = n_vars == 1 && sm.hdr.mode == MODE_CLASSIC && vh0.n_bins >= 2 &&
                          task.entries_offset != 0 && index_base != nullptr;
   if (!candidate) {
     if (tid == 0) d_cls[blockIdx.x] = uint8_t(n_vars == 2 ? 2 : 1);

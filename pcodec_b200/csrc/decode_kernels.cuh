@@ -427,9 +427,15 @@ __device__ inline uint32_t walk_chunk_serial(const BitSrc& src, const ChunkHdr& 
 
 // 64 threads build the tables, one of them walks: with <= 64 threads the register file lets 8 CTAs of up to 128 registers share an SM (1024
 // chunks in one wave) and the walker keeps its loop-invariant shared addresses in registers (at 64 registers it re-derived them per step)
-constexpr int WALK_THREADS = 64;
+#ifndef PCOB_WALK_THREADS
+#define PCOB_WALK_THREADS 64
+#endif
+#ifndef PCOB_WALK_MIN_BLOCKS
+#define PCOB_WALK_MIN_BLOCKS 8
+#endif
+constexpr int WALK_THREADS = PCOB_WALK_THREADS;
 template <int CAP_LOG>
-__global__ void __launch_bounds__(WALK_THREADS, 8) walk_kernel(FileParams fp, uint8_t* index_base, uint64_t chunks_offset, uint32_t max_chunks,
+__global__ void __launch_bounds__(WALK_THREADS, PCOB_WALK_MIN_BLOCKS) walk_kernel(FileParams fp, uint8_t* index_base, uint64_t chunks_offset, uint32_t max_chunks,
                                                    uint64_t entries_begin, uint64_t entries_cap_end, uint64_t first_chunk_byte,
                                                    uint64_t first_out_offset, uint64_t stop_after_total, uint32_t* statuses, WalkResult* result,
                                                    int serial_file_mode) {
@@ -767,9 +773,22 @@ __device__ __forceinline__ void store8(L* __restrict__ dst, const L (&r)[8]) {
         asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * q), "r"(uint32_t(r[4 * q])), "r"(uint32_t(r[4 * q + 1])),
                      "r"(uint32_t(r[4 * q + 2])), "r"(uint32_t(r[4 * q + 3])) : "memory");
     }
-  } else {
+  } else if (sizeof(L) == 2) {  // 8 numbers = 16 bytes: one store when aligned
+    if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+      asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(uint32_t(r[0]) | (uint32_t(r[1]) << 16)), "r"(uint32_t(r[2]) | (uint32_t(r[3]) << 16)),
+                   "r"(uint32_t(r[4]) | (uint32_t(r[5]) << 16)), "r"(uint32_t(r[6]) | (uint32_t(r[7]) << 16)) : "memory");
+    } else {
 #pragma unroll
-    for (int e = 0; e < 8; e++) dst[e] = r[e];
+      for (int e = 0; e < 8; e++) dst[e] = r[e];
+    }
+  } else {  // 8 numbers = 8 bytes
+    if ((reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
+      asm volatile("st.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(uint32_t(r[0]) | (uint32_t(r[1]) << 8) | (uint32_t(r[2]) << 16) | (uint32_t(r[3]) << 24)),
+                   "r"(uint32_t(r[4]) | (uint32_t(r[5]) << 8) | (uint32_t(r[6]) << 16) | (uint32_t(r[7]) << 24)) : "memory");
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; e++) dst[e] = r[e];
+    }
   }
 }
 template <typename L>

@@ -128,7 +128,7 @@ static PcoB200Error launch_decode(Context& c, const FileParams& fp, const uint8_
   const IndexChunk* d_chunks = reinterpret_cast<const IndexChunk*>(d_index + chunks_offset);
   PCOB_CUDA_TRY(c.dec_nvars.reserve(size_t(n_chunks) + 64));
   static const bool use_fused = [] { const char* e = std::getenv("PCOB200_FUSED"); return !(e && e[0] == '0'); }();
-  const bool narrow_ok = nt_bits(fp.dtype) >= 32;  // the narrow class serves the 32- and 64-bit number types
+  const bool narrow_ok = true;  // the fused kernel serves every number width
   if (!c.attrs_set) {
     c.attrs_set = true;
     PCOB_CUDA_TRY(cudaFuncSetAttribute(symwalk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SymWalkSmem)));
@@ -137,6 +137,10 @@ static PcoB200Error launch_decode(Context& c, const FileParams& fp, const uint8_
     PCOB_CUDA_TRY(cudaFuncSetAttribute(fused_narrow_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem)));
     PCOB_CUDA_TRY(cudaFuncSetAttribute(fused_narrow_kernel<uint64_t>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     PCOB_CUDA_TRY(cudaFuncSetAttribute(fused_narrow_kernel<uint32_t>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    PCOB_CUDA_TRY(cudaFuncSetAttribute(fused_narrow_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem)));
+    PCOB_CUDA_TRY(cudaFuncSetAttribute(fused_narrow_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem)));
+    PCOB_CUDA_TRY(cudaFuncSetAttribute(fused_narrow_kernel<uint16_t>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    PCOB_CUDA_TRY(cudaFuncSetAttribute(fused_narrow_kernel<uint8_t>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
   }
   c.last_decode_chunks = n_chunks;
   std::vector<uint32_t> st(n_chunks);
@@ -144,12 +148,11 @@ static PcoB200Error launch_decode(Context& c, const FileParams& fp, const uint8_
   if (use_fused && narrow_ok) {
     fused_ran = true;
     profiler().begin("fused_narrow_kernel", stream);
-    if (nt_bits(fp.dtype) == 64)
-      fused_narrow_kernel<uint64_t><<<n_chunks, FZ_THREADS, sizeof(FusedSmem), stream>>>(fp, d_chunks, d_index, index_len, d_st, c.dec_nvars.as<uint8_t>(),
-                                                                                         static_cast<uint64_t*>(d_out), out_len);
-    else
-      fused_narrow_kernel<uint32_t><<<n_chunks, FZ_THREADS, sizeof(FusedSmem), stream>>>(fp, d_chunks, d_index, index_len, d_st, c.dec_nvars.as<uint8_t>(),
-                                                                                         static_cast<uint32_t*>(d_out), out_len);
+    dispatch_latent(fp.dtype, [&](auto tag) {
+      using L = decltype(tag);
+      fused_narrow_kernel<L><<<n_chunks, FZ_THREADS, sizeof(FusedSmem), stream>>>(fp, d_chunks, d_index, index_len, d_st, c.dec_nvars.as<uint8_t>(), static_cast<L*>(d_out), out_len);
+      return 0;
+    });
     profiler().end(stream);
     PCOB_CUDA_TRY(cudaGetLastError());
     // statuses and class bytes come back in one round trip; the general kernels only run if some chunk still needs them
@@ -170,7 +173,7 @@ static PcoB200Error launch_decode(Context& c, const FileParams& fp, const uint8_
   const uint64_t rows = scratch_rows_total(out_len, n_chunks);
   PCOB_CUDA_TRY(c.dec_syms.reserve(rows * BATCH_N + 64));
   PCOB_CUDA_TRY(c.dec_offs.reserve(rows * sizeof(uint32_t) + 64));
-  const bool old_narrow = narrow_ok && !fused_ran;
+  const bool old_narrow = nt_bits(fp.dtype) >= 32 && !fused_ran;  // PCOB200_FUSED=0: the round-1 narrow kernel serves 32- and 64-bit types
   if (old_narrow) PCOB_CUDA_TRY(c.dec_narrow.reserve(size_t(n_chunks) * sizeof(NarrowInfo)));
   profiler().begin("symwalk_kernel", stream);
   symwalk_kernel<<<n_chunks, SW_THREADS, sizeof(SymWalkSmem), stream>>>(fp, d_chunks, d_index, index_len, out_len, c.dec_syms.as<uint8_t>(), c.dec_offs.as<uint32_t>(),
