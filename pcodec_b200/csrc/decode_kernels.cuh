@@ -425,10 +425,10 @@ __device__ inline uint32_t walk_chunk_serial(const BitSrc& src, const ChunkHdr& 
   return ST_OK;
 }
 
-// 64 threads build the tables, one of them walks: with <= 64 threads the register file lets 8 CTAs of up to 128 registers share an SM (1024
-// chunks in one wave) and the walker keeps its loop-invariant shared addresses in registers (at 64 registers it re-derived them per step)
+// One warp builds the tables, its first lane walks.  Measured for 1024 chunks (profiles/r02_k_walk_variants.txt): 128 threads x 8 CTAs/SM
+// (64 registers) 10.6 ms, 64 x 8 (128 registers) 13.6 ms, 64 x 16 15.3 ms, 32 x 8 8.5 ms
 #ifndef PCOB_WALK_THREADS
-#define PCOB_WALK_THREADS 64
+#define PCOB_WALK_THREADS 32
 #endif
 #ifndef PCOB_WALK_MIN_BLOCKS
 #define PCOB_WALK_MIN_BLOCKS 8

@@ -106,7 +106,7 @@ def test_conditions_that_must_miss_the_narrow_path(sa, oracle):
         assert np.array_equal(got, nums)
         n_chunks, counts = _classes()
         assert n_chunks == 1 and counts[1] == 1, counts
-    # delta orders 2..7 are served by the fused kernel too (class 5); 16-bit types stay on the general kernel
+    # delta orders 2..7 are served by the fused kernel too (class 5)
     for order in (2, 3, 7):
         steps = rng.geometric(0.002, size=9000).astype(np.int64)  # the order-th differences: a small multi-bin distribution
         vals = steps
@@ -117,10 +117,11 @@ def test_conditions_that_must_miss_the_narrow_path(sa, oracle):
         assert np.array_equal(sa.simple_decompress(data, np.uint64), nums)
         n_chunks, counts = _classes()
         assert n_chunks == 1 and counts[5] == 1, (order, counts)
+    # 16-bit (and 8-bit) types are served by the fused kernel as well
     nums16 = (np.cumsum(rng.integers(0, 5, size=9000)) % 60000).astype(np.uint16)
     data = oracle.simple_compress(nums16, _cfg(oracle, 1))
     assert np.array_equal(sa.simple_decompress(data, np.uint16), nums16)
-    assert _classes()[1][1] == 1
+    assert _classes()[1][4] == 1
 
 
 def test_mixed_classes_in_one_file(sa, oracle):

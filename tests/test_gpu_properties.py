@@ -52,4 +52,8 @@ def test_gpu_bytes_equal_the_oracles(oracle, data):
     except p.PcoError as e:
         assert e.kind == "Unsupported", (kw, e)
         return
-    assert np.array_equal(bits_view(back), bits_view(nums)), kw
+    if not np.array_equal(bits_view(back), bits_view(nums)):
+        a, b = bits_view(back), bits_view(nums)
+        bad = np.nonzero(a != b)[0] if a.shape == b.shape else np.array([], dtype=int)
+        raise AssertionError(f"GPU decode of the oracle's file differs: {kw}, dtype {nums.dtype}, n {nums.size} vs {back.size}, first differing indices {bad[:5].tolist()}, "
+                             f"got {[hex(int(x)) for x in a[bad[:5]]]} want {[hex(int(x)) for x in b[bad[:5]]]}, nums bits {[hex(int(x)) for x in b[:40]]}")
