@@ -607,7 +607,7 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
   DevBuf& in_stage = S.index;  // a dedicated input staging buffer when nums live on the host (kept apart from the sort buffers)
   if (!src_dev) {
     PCOB_CUDA_TRY(in_stage.reserve(n * sizeof(L) + 64));
-    PCOB_CUDA_TRY(cudaMemcpyAsync(in_stage.p, nums, n * sizeof(L), cudaMemcpyHostToDevice, stream));
+    PCOB_CUDA_TRY(copy_sliced(in_stage.p, nums, n * sizeof(L), cudaMemcpyHostToDevice, stream));
     d_nums = in_stage.p;
   }
   // scratch sized for the whole call; every run below (and the Auto searches) indexes it from 0
@@ -978,7 +978,7 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
     PCOB_CUDA_TRY(cudaGetLastError());
     if (!dst_dev) {
       const uint64_t from = first_run ? 0 : file_off;
-      PCOB_CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t*>(dst) + from, d_out + from, total - from, cudaMemcpyDeviceToHost, stream));
+      PCOB_CUDA_TRY(copy_sliced(static_cast<uint8_t*>(dst) + from, d_out + from, total - from, cudaMemcpyDeviceToHost, stream));
     }
     // ---- this run's piece of the side index
     if (index_dst != nullptr) {

@@ -243,7 +243,7 @@ static PcoB200Error decompress_fast(const void* compressed, size_t compressed_le
   if (src_dev) d_src = static_cast<const uint8_t*>(compressed);
   else {
     PCOB_CUDA_TRY(c.src.reserve(compressed_len + 16));
-    PCOB_CUDA_TRY(cudaMemcpyAsync(c.src.p, compressed, compressed_len, cudaMemcpyHostToDevice, stream));
+    PCOB_CUDA_TRY(copy_sliced(c.src.p, compressed, compressed_len, cudaMemcpyHostToDevice, stream));
     d_src = c.src.as<uint8_t>();
   }
   FileParams fp;
@@ -263,7 +263,7 @@ static PcoB200Error decompress_fast(const void* compressed, size_t compressed_le
     const uint8_t* d_idx = static_cast<const uint8_t*>(index);
     if (!idx_dev) {
       PCOB_CUDA_TRY(c.index.reserve(index_len));
-      PCOB_CUDA_TRY(cudaMemcpyAsync(c.index.p, index, index_len, cudaMemcpyHostToDevice, stream));
+      PCOB_CUDA_TRY(copy_sliced(c.index.p, index, index_len, cudaMemcpyHostToDevice, stream));
       d_idx = c.index.as<uint8_t>();
     }
     uint64_t n_emit = std::min<uint64_t>(ih.n_total, dst_len);
@@ -276,7 +276,7 @@ static PcoB200Error decompress_fast(const void* compressed, size_t compressed_le
     // a host destination is staged in c.out, which holds n_emit numbers: that is the kernels' bound, whatever the index claims
     if (PcoB200Error e = launch_decode(c, fp, d_idx, index_len, ih.chunks_offset, uint32_t(ih.n_chunks), d_out, dst_dev ? uint64_t(dst_len) : n_emit, stream)) return e;
     if (!dst_dev && n_emit) {
-      PCOB_CUDA_TRY(cudaMemcpyAsync(dst, d_out, n_emit * elem, cudaMemcpyDeviceToHost, stream));
+      PCOB_CUDA_TRY(copy_sliced(dst, d_out, n_emit * elem, cudaMemcpyDeviceToHost, stream));
       PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
     }
     outcome->n_total = ih.n_total;
@@ -329,7 +329,7 @@ static PcoB200Error decompress_fast(const void* compressed, size_t compressed_le
   outcome->n_total = out_off;
   uint64_t n_emit = std::min<uint64_t>(out_off, dst_len);
   if (!dst_dev && n_emit) {
-    PCOB_CUDA_TRY(cudaMemcpyAsync(dst, d_out, n_emit * elem, cudaMemcpyDeviceToHost, stream));
+    PCOB_CUDA_TRY(copy_sliced(dst, d_out, n_emit * elem, cudaMemcpyDeviceToHost, stream));
     PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
   }
   return PCO_B200_OK;
@@ -354,7 +354,7 @@ static PcoB200Error decompress_cold(const void* compressed, size_t compressed_le
   const uint8_t* d_src = static_cast<const uint8_t*>(compressed);
   if (!src_dev) {
     PCOB_CUDA_TRY(c.src.reserve(compressed_len + 16));
-    PCOB_CUDA_TRY(cudaMemcpyAsync(c.src.p, compressed, compressed_len, cudaMemcpyHostToDevice, stream));
+    PCOB_CUDA_TRY(copy_sliced(c.src.p, compressed, compressed_len, cudaMemcpyHostToDevice, stream));
     d_src = c.src.as<uint8_t>();
   }
   FileParams fp{d_src, compressed_len, dtype, hdr.uniform_type, hdr.format_major};
@@ -383,7 +383,7 @@ static PcoB200Error decompress_cold(const void* compressed, size_t compressed_le
   // like the walk path: the chunks before a failing one have been emitted (the reference's decoder stops where the error is)
   const uint64_t n_emit = std::min<uint64_t>(res.n_total, dst_len);
   if (!dst_dev && n_emit) {
-    PCOB_CUDA_TRY(cudaMemcpyAsync(dst, d_out, n_emit * elem, cudaMemcpyDeviceToHost, stream));
+    PCOB_CUDA_TRY(copy_sliced(dst, d_out, n_emit * elem, cudaMemcpyDeviceToHost, stream));
     PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
   }
   if (res.status != ST_TERMINATOR && res.status != ST_DST_FULL) return status_to_error(res.status, ("chunk " + std::to_string(res.n_chunks)).c_str());
@@ -835,7 +835,7 @@ PcoB200Error pco_b200_decompress_chunks(const void* compressed, size_t compresse
   if (src_dev) d_src = static_cast<const uint8_t*>(compressed);
   else {
     PCOB_CUDA_TRY(c.src.reserve(compressed_len + 16));
-    PCOB_CUDA_TRY(cudaMemcpyAsync(c.src.p, compressed, compressed_len, cudaMemcpyHostToDevice, stream));
+    PCOB_CUDA_TRY(copy_sliced(c.src.p, compressed, compressed_len, cudaMemcpyHostToDevice, stream));
     d_src = c.src.as<uint8_t>();
   }
   FileParams fp{d_src, compressed_len, dtype, uniform_type, format_major};
@@ -866,7 +866,7 @@ PcoB200Error pco_b200_decompress_chunks(const void* compressed, size_t compresse
   profiler().resolve();
   if (e != PCO_B200_OK) return e;
   if (!dst_dev && n_total) {
-    PCOB_CUDA_TRY(cudaMemcpyAsync(dst, d_out, n_total * elem, cudaMemcpyDeviceToHost, stream));
+    PCOB_CUDA_TRY(copy_sliced(dst, d_out, n_total * elem, cudaMemcpyDeviceToHost, stream));
     PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
   }
   if (n_written) *n_written = size_t(n_total);
@@ -892,7 +892,7 @@ PcoB200Error pco_b200_build_index(const void* compressed, size_t compressed_len,
   if (src_dev) d_src = static_cast<const uint8_t*>(compressed);
   else {
     PCOB_CUDA_TRY(c.src.reserve(compressed_len + 16));
-    PCOB_CUDA_TRY(cudaMemcpyAsync(c.src.p, compressed, compressed_len, cudaMemcpyHostToDevice, stream));
+    PCOB_CUDA_TRY(copy_sliced(c.src.p, compressed, compressed_len, cudaMemcpyHostToDevice, stream));
     d_src = c.src.as<uint8_t>();
   }
   FileParams fp{d_src, compressed_len, dtype, hdr.uniform_type, hdr.format_major};

@@ -88,6 +88,22 @@ inline Profiler& profiler() {
   return p;
 }
 
+// ---- large host <-> device copies in slices ---------------------------------
+// One cudaMemcpyAsync of hundreds of megabytes occupies its copy engine for milliseconds; a small copy that ANOTHER stream issues in the
+// same direction meanwhile (a status word, a file header, the compressed bytes of the opposite call) queues behind all of it.  Two host
+// threads that stream chunk groups through compress and decompress then wait for each other's big copy in turn, and the two PCIe directions
+// never overlap (measured: each call twice as long as alone).  Slices give the engine a boundary every few hundred microseconds.
+inline cudaError_t copy_sliced(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t stream) {
+  constexpr size_t SLICE = size_t(4) << 20;
+  if (bytes <= 2 * SLICE) return cudaMemcpyAsync(dst, src, bytes, kind, stream);
+  for (size_t off = 0; off < bytes; off += SLICE) {
+    const size_t len = bytes - off < SLICE ? bytes - off : SLICE;
+    cudaError_t e = cudaMemcpyAsync(static_cast<uint8_t*>(dst) + off, static_cast<const uint8_t*>(src) + off, len, kind, stream);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
 // ---- grow-only device buffer -----------------------------------------------
 struct DevBuf {
   void* p = nullptr;
