@@ -387,6 +387,7 @@ static PcoB200Error plan_front(CompressScratch& S, cudaStream_t stream, const En
       uint32_t fl[2] = {0, 0};
       PCOB_CUDA_TRY(cudaMemcpyAsync(fl, d_small, 8, cudaMemcpyDeviceToHost, stream));
       PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
+      call_trace().mark("c.flags");
       if (fl[1] == 0 && shared) {
         // pages of one chunk: one histogram over all of them, one plan, copied to every page's slot
         if (!S.union_attr_set[LW]) {
@@ -607,7 +608,9 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
   DevBuf& in_stage = S.index;  // a dedicated input staging buffer when nums live on the host (kept apart from the sort buffers)
   if (!src_dev) {
     PCOB_CUDA_TRY(in_stage.reserve(n * sizeof(L) + 64));
+    call_trace().mark("c.begin");
     PCOB_CUDA_TRY(copy_sliced(in_stage.p, nums, n * sizeof(L), cudaMemcpyHostToDevice, stream));
+    call_trace().mark("c.h2d_submitted");
     d_nums = in_stage.p;
   }
   // scratch sized for the whole call; every run below (and the Auto searches) indexes it from 0
@@ -955,6 +958,7 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
       PCOB_CUDA_TRY(cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, stream));
       PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
       PCOB_CUDA_TRY(cudaGetLastError());
+      call_trace().mark("c.total");
       if (total > dst_cap) return fail(PCO_B200_IO, "failed to write whole buffer (need " + std::to_string(total) + " bytes, dst_cap " + std::to_string(dst_cap) + ")");
     }
     if (!dst_dev) {
@@ -999,6 +1003,7 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
       // the scratch is reused by the next run, and a host destination must be complete before the call returns
       PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
       PCOB_CUDA_TRY(cudaGetLastError());
+      call_trace().mark("c.run_done");
       file_off = total - footer;
       res->total_bytes = total;
     } else {
@@ -1018,6 +1023,8 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
     PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
     res->index_bytes = index_total;
   }
+  call_trace().mark("c.end");
+  call_trace().flush("compress");
   return PCO_B200_OK;
 }
 

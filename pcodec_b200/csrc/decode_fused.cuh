@@ -40,8 +40,12 @@ namespace pcob200 {
 #ifndef PCOB_FZ_MIN_BLOCKS
 #define PCOB_FZ_MIN_BLOCKS 4
 #endif
-constexpr int FZ_THREADS = 256;
+#ifndef PCOB_FZ_THREADS
+#define PCOB_FZ_THREADS 256
+#endif
+constexpr int FZ_THREADS = PCOB_FZ_THREADS;
 constexpr int FZ_WARPS = FZ_THREADS / 32;
+static_assert(FZ_WARPS == 8 || FZ_WARPS == 4, "the role rotation below masks with FZ_WARPS - 1");
 constexpr int FZ_WALKERS = PCOB_FZ_WALKERS;          // walker warps: walker w takes the groups g = w (mod FZ_WALKERS)
 constexpr int FZ_DECODERS = FZ_WARPS - FZ_WALKERS;
 constexpr int FZ_NBUF = PCOB_FZ_NBUF;               // ring buffers of 32 symbol rows: group g lives in buffer g mod FZ_NBUF
@@ -528,7 +532,7 @@ fused_narrow_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, const 
   const bool candidate = n_vars == 1 && sm.hdr.mode == MODE_CLASSIC && vh0.n_bins >= 2 &&
                          task.entries_offset != 0 && index_base != nullptr;
   if (!candidate) {
-    if (tid == 0) d_cls[blockIdx.x] = uint8_t(n_vars == 2 ? 2 : 1);
+    if (tid == 0) { statuses[blockIdx.x] = 0xffffffffu; d_cls[blockIdx.x] = uint8_t(n_vars == 2 ? 2 : 1); }  // status: not decoded yet
     return;
   }
   {
@@ -542,7 +546,7 @@ fused_narrow_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, const 
     return;
   }
   if (sm.hdr.var[0].max_offset_bits > NARROW_MAX_OB) {
-    if (tid == 0) d_cls[blockIdx.x] = 1;
+    if (tid == 0) { statuses[blockIdx.x] = 0xffffffffu; d_cls[blockIdx.x] = 1; }
     return;
   }
   {
@@ -569,7 +573,7 @@ fused_narrow_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, const 
   }
   __syncthreads();  // q, nodes, base in place; the prologue scratch (aliased by ring, stage and windows) is dead
   if (sm.not_narrow) {
-    if (tid == 0) d_cls[blockIdx.x] = 1;
+    if (tid == 0) { statuses[blockIdx.x] = 0xffffffffu; d_cls[blockIdx.x] = 1; }
     return;
   }
   const uint32_t n = sm.hdr.n;
@@ -592,7 +596,7 @@ fused_narrow_kernel(FileParams fp, const IndexChunk* __restrict__ chunks, const 
   }
   __syncthreads();
   // the walkers' warp slots rotate with the CTA so that the CTAs of an SM do not all put them on the same schedulers
-  const int role = (warp + 8 - int((blockIdx.x * FZ_WALKERS) & 7u)) & 7;  // 0 .. FZ_WALKERS - 1: walkers, the rest: decoders
+  const int role = (warp + FZ_WARPS - int((blockIdx.x * FZ_WALKERS) & uint32_t(FZ_WARPS - 1))) & (FZ_WARPS - 1);  // 0 .. FZ_WALKERS - 1: walkers, the rest: decoders
   if (role < FZ_WALKERS) {
     const BatchEntry* entries = reinterpret_cast<const BatchEntry*>(index_base + task.entries_offset);
     const uint32_t rep_log = min(5u, uint32_t(31 - __clz(uint32_t(FZ_NODE_WORDS) >> vh0.ans_size_log)));

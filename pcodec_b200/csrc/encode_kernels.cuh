@@ -490,11 +490,12 @@ __global__ void __launch_bounds__(RS_THREADS, 1) radix_sort_segments_kernel(L* _
 // Bin training (train_infos, chunk_compressor.rs:52-99) in two kernels per latent var:
 //   plan_probe_kernel — one 512-thread CTA per chunk, HBM-bound: order statistics at the 2^log equal-count boundaries
 //                       (from shared-memory counters when the key range is narrow, else from the sorted keys)
-//   plan_solve_kernel — one WARP per chunk, latency-bound and short: histogram state machine, bin-merge DP, weight
-//                       quantisation, tANS tables.  All chunks are resident at once, so the serial parts overlap.
+//   plan_solve_kernel — four warps per chunk, latency-bound and short: histogram state machine (one thread), bin-merge DP
+//                       (the candidates of a step spread over the CTA, one barrier per step), weight quantisation, tANS
+//                       tables.  All chunks are resident at once, so the serial parts overlap.
 // ---------------------------------------------------------------------------
 constexpr int PLAN_THREADS = 512;
-constexpr int SOLVE_THREADS = 32;
+constexpr int SOLVE_THREADS = 128;
 constexpr uint32_t PLAN_MAX_COUNT_BITS = 15;  // counting histogram (no sort) when the key range fits 2^15 shared-memory counters
 
 // Order statistics handed from the probe kernel to the solver (per chunk and var, in HBM scratch)
@@ -527,6 +528,7 @@ struct PlanSmem {
   uint32_t c_counts[ENC_MAXB + 1];
   float best_cost[ENC_MAXB + 1];
   uint32_t best_j[ENC_MAXB];
+  uint32_t red_cost[2][SOLVE_THREADS / 32], red_j[2][SOLVE_THREADS / 32];  // per-warp argmin of a DP step
   uint32_t n_opt;
   uint32_t size_log;
 };
@@ -991,7 +993,18 @@ __global__ void __launch_bounds__(SOLVE_THREADS) plan_solve_kernel(EncParams ep,
   const uint32_t n_bins_log = ep.bins_log[v];
   const uint32_t nbk = 1u << n_bins_log;
   const bool small_n = n <= (1u << 20);  // (cc << n_bins_log) fits 32 bits (n_bins_log <= 8)
-  auto bin_idx_of = [&](uint64_t cc) -> uint32_t { return small_n ? (uint32_t(cc) << n_bins_log) / n : uint32_t((cc << n_bins_log) / n); };
+  // (cc << n_bins_log) / n, cc <= n: the quotient is at most 2^n_bins_log <= 256, so a float estimate is within 1 of it and one
+  // remainder check makes it exact (an integer division is ~100 dependent cycles on the state machine's serial path)
+  const float rcp_n = __frcp_rn(__uint2float_rn(n));
+  auto bin_idx_of = [&](uint64_t cc) -> uint32_t {
+    if (!small_n) return uint32_t((cc << n_bins_log) / n);
+    const uint32_t num = uint32_t(cc) << n_bins_log;
+    uint32_t q = __float2uint_rz(__fmul_rn(__uint2float_rz(num), rcp_n));
+    const uint32_t r = num - q * n;
+    if (int32_t(r) < 0) q -= 1;
+    else if (r >= n) q += 1;
+    return q;
+  };
   auto c_count_of = [&](uint32_t b) -> uint32_t { return uint32_t((uint64_t(b + 1) * n + nbk - 1) >> n_bins_log); };
   {
     // stage this chunk's probes (coalesced 16-byte copies)
@@ -1074,14 +1087,25 @@ __global__ void __launch_bounds__(SOLVE_THREADS) plan_solve_kernel(EncParams ep,
       float cost = __fadd_rn(sm.best_cost[j], bin_cost_dev(bin_meta_cost, upper - sm.h_lower[j], cci - sm.c_counts[j], total_log2));
       if (cost < my_cost) { my_cost = cost; my_j = uint32_t(j); }
     }
-    // warp argmin with "largest j among equal costs" (one warp per chunk: no block barrier on the DP's serial axis).
-    // Costs are non-negative floats, so their bit patterns order like the values: two hardware reductions (REDUX) - the
-    // smallest cost, then the largest j among the lanes that hold it - instead of five rounds of shuffles and compares.
+    // argmin with "largest j among equal costs".  Costs are non-negative floats, so their bit patterns order like the values: per
+    // warp two hardware reductions (REDUX) - the smallest cost, then the largest j among the lanes that hold it - and across the
+    // warps one barrier per step (the per-warp results are double-buffered; thread 0, which writes best_cost[i + 1], is also the
+    // only thread that reads it in step i + 1).
     const uint32_t cbits = my_j == 0xffffffffu ? 0xffffffffu : __float_as_uint(my_cost);
     const uint32_t cmin = __reduce_min_sync(0xffffffffu, cbits);
-    const uint32_t jbest = __reduce_max_sync(0xffffffffu, (cbits == cmin && my_j != 0xffffffffu) ? my_j + 1u : 0u) - 1u;
-    if (tid == 0) { sm.best_cost[i + 1] = __uint_as_float(cmin); sm.best_j[i] = jbest; }
-    __syncwarp();
+    const uint32_t jbest = __reduce_max_sync(0xffffffffu, (cbits == cmin && my_j != 0xffffffffu) ? my_j + 1u : 0u);
+    if ((tid & 31) == 0) { sm.red_cost[i & 1][tid >> 5] = cmin; sm.red_j[i & 1][tid >> 5] = jbest; }
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t gmin = 0xffffffffu, gj = 0;
+#pragma unroll
+      for (int w = 0; w < SOLVE_THREADS / 32; w++) {
+        const uint32_t cw = sm.red_cost[i & 1][w], jw = sm.red_j[i & 1][w];
+        if (cw < gmin || (cw == gmin && jw > gj)) { gmin = cw; gj = jw; }
+      }
+      sm.best_cost[i + 1] = __uint_as_float(gmin);
+      sm.best_j[i] = gj - 1u;
+    }
   }
   ENC_TICK(4);  // DP
   // ---- 4. shortcuts, rewind, weights (thread 0: short sequential f32 sums whose order matters)
@@ -1494,12 +1518,22 @@ constexpr int ANS_THREADS = 256;
 constexpr int ANS_SEGS = ANS_THREADS / 4;   // segments per round: one thread per (segment, interleaved chain)
 constexpr int ANS_WARM_BATCHES = 2;         // batches of the preceding segment replayed to form the guess
 constexpr uint32_t ANS_MAX_SEG_BATCHES = 16;
+constexpr uint32_t ANS_TF_MAX = 32;         // largest weight the transfer-function path enumerates
+constexpr int ANS_TF_LOOK = 4;              // it picks the lightest symbol among a chain's first ANS_TF_LOOK steps of the segment
 
 struct AnsSmem {
   uint32_t desc_tab[ENC_MAXB];                 // per symbol: ((min_renorm_bits + 1) << 16 - cutoff) | (cum - weight + 1024) << 20 (see ans_step)
   uint16_t next_states[1 << ENC_MAX_SIZE_LOG];  // full next state (size + slot), indexed cum + (x_s - weight)
   uint16_t out_state[ANS_SEGS][4];
   uint16_t carry[4];
+  // transfer-function path (tables whose trajectories do not merge): per (segment, chain) the descriptors of its first steps, which of
+  // them is the pivot (the lightest symbol) and its weight, the segment's output state for each slot the pivot step can land in, and the
+  // resolved true input state
+  uint16_t tf[ANS_SEGS][4][ANS_TF_MAX];
+  uint32_t first_desc[ANS_SEGS][4][ANS_TF_LOOK];
+  uint8_t pivot[ANS_SEGS][4];
+  uint8_t pivot_w[ANS_SEGS][4];
+  uint16_t true_in[ANS_SEGS][4];
 };
 
 // One tANS step (ans/encoding.rs:72-83) from a pre-resolved descriptor; returns the bit count, `o` = value | bits << 12.
@@ -1644,34 +1678,131 @@ __global__ void __launch_bounds__(ANS_THREADS, 4) ans_encode_kernel(EncParams ep
         ans_full_batch<true>(sm, symp + uint64_t(b - 1) * BATCH_N, nullptr, j, gmask, g);
       my_in = g;
     }
-    uint32_t state = my_in;
-    if (active) {
+    // the segment's batches from input state `st` (the 4 lanes of the group together); returns the output state
+    auto encode_segment = [&](uint32_t st) -> uint32_t {
       for (uint32_t b = b_hi; b > b_lo; b--) {
         const uint32_t bb = b - 1;
-        uint32_t bits = bb < nb_full ? ans_full_batch<false>(sm, symp + uint64_t(bb) * BATCH_N, ansp + uint64_t(bb) * BATCH_N, j, gmask, state)
-                                     : short_batch(bb, state);
+        uint32_t bits = bb < nb_full ? ans_full_batch<false>(sm, symp + uint64_t(bb) * BATCH_N, ansp + uint64_t(bb) * BATCH_N, j, gmask, st)
+                                     : short_batch(bb, st);
         bits += __shfl_xor_sync(gmask, bits, 1);
         bits += __shfl_xor_sync(gmask, bits, 2);
         // decoder state at the START of a batch == encoder state after encoding it (side index)
         if (j == 0) { sums[bb] = bits; ent[bb].bit_pos = 0; }
-        ent[bb].st[j] = uint16_t(state - size);
+        ent[bb].st[j] = uint16_t(st - size);
       }
+      return st;
+    };
+    uint32_t state = my_in;
+    if (active) {
+      state = encode_segment(my_in);
       sm.out_state[s][j] = uint16_t(state);
     }
     uint32_t my_out = state;
     __syncthreads();
-    if (done == 0) {
+    {
+      // Many wrong guesses (more than a quarter of the round's): the table merges trajectories slowly.  First a deeper guess: two probe
+      // trajectories from far-apart states over 4, 8, 16, 32 batches of the preceding segments until they coincide - a table with one
+      // rare light symbol (weights like 205 / 50 / 1) merges everything at that symbol's next occurrence, a few batches back - and the
+      // segments whose guess moved are encoded again.  What is still wrong after that goes to the exact paths below.
+      const uint32_t in_chk0 = (s == 0 || !active) ? my_in : uint32_t(sm.out_state[s - 1][j]);
+      const int wrong0 = __syncthreads_count(active && s > 0 && in_chk0 != my_in);
+      if (uint32_t(wrong0) > min(n_segs - done, uint32_t(ANS_SEGS))) {
+        // the 4 chains of a group decide together (encode_segment shuffles within the group)
+        const bool mine_wrong = active && s > 0 && in_chk0 != my_in;
+        const bool group_wrong = (__ballot_sync(0xffffffffu, mine_wrong) & gmask) != 0;
+        uint32_t g = my_in;
+        if (active && s > 0 && group_wrong) {
+          for (uint32_t wb = 4;; wb *= 2) {
+            const uint32_t w_hi = min(b_hi + wb, nb_full);
+            uint32_t h = 2 * size - 1;
+            g = size;
+            for (uint32_t b = w_hi; b > b_hi; b--) {
+              ans_full_batch<true>(sm, symp + uint64_t(b - 1) * BATCH_N, nullptr, j, gmask, g);
+              ans_full_batch<true>(sm, symp + uint64_t(b - 1) * BATCH_N, nullptr, j, gmask, h);
+            }
+            if (g == h || w_hi >= nb_full || wb >= 32) break;
+          }
+        }
+        const bool redo = (__ballot_sync(0xffffffffu, g != my_in) & gmask) != 0;
+        __syncthreads();  // every thread has read its predecessor's old output
+        if (redo) {
+          my_in = g;
+          state = encode_segment(my_in);
+          sm.out_state[s][j] = uint16_t(state);
+          my_out = state;
+        }
+        __syncthreads();
+      }
+    }
+    {
       // The speculation rests on tANS trajectories merging (a symbol of weight w maps all states onto w values).  Tables whose weights are
       // (nearly) all equal - what equal-count bins of smooth wide-range data give - act on the state's top bits as near-permutations: guesses
       // are wrong about 3 times in 4 and the corrections never meet the old trajectory, so the fix-up below would re-encode segment after
-      // segment element-wise (measured: 8.5 ms for 128 chunks of C5 int64 order 0).  When more than a quarter of the first round's guesses
-      // are wrong, the page is encoded once, in order, by one group of four lanes instead - the serial encoder (all chunks still run
-      // side by side, one CTA each).
+      // segment element-wise at the serial encoder's pace (measured: 8.5 ms per launch on C5 int64 order 0).  When more than a quarter of a
+      // round's guesses are wrong the round is solved exactly instead.  After a step with a symbol of weight w the state is one of w values
+      // (next_states[cum + slot], slot = (state >> bits) - w), whatever it was before: each (segment, chain) takes the lightest symbol among
+      // its first ANS_TF_LOOK steps as the pivot, replays the rest of the segment quietly once per slot of the pivot (its transfer function,
+      // <= ANS_TF_MAX entries), four threads chain the true inputs through the 64 transfer functions, and every segment is encoded once
+      // more from its true input.  Tables whose lightest early symbol is heavier fall back to one in-order pass by a single group of four lanes.
       const uint32_t in_chk = (s == 0 || !active) ? my_in : uint32_t(sm.out_state[s - 1][j]);
       const int wrong = __syncthreads_count(active && s > 0 && in_chk != my_in);
-      const uint32_t n_round = min(n_segs, uint32_t(ANS_SEGS));
+      const uint32_t n_round = min(n_segs - done, uint32_t(ANS_SEGS));
       if (uint32_t(wrong) > n_round) {  // 4 lanes per segment: wrong / 4 > n_round / 4
-        if (s == 0) {
+        const bool top_full = b_hi >= 1 && b_hi - 1 < nb_full;  // only the round's top segment (s == 0) can hold the page's short batch
+        uint32_t pv = 0, pw = 0xffffu;
+        if (active && s > 0 && top_full) {
+          // the chain's first steps in this segment: elements 252 + j, 248 + j, ... of batch b_hi - 1
+          const uint8_t* rs = symp + uint64_t(b_hi - 1) * BATCH_N;
+#pragma unroll
+          for (int k = 0; k < ANS_TF_LOOK; k++) {
+            const uint32_t sy = rs[4 * (63 - k) + j];
+            sm.first_desc[s][j][k] = sm.desc_tab[sy];
+            const uint32_t w = uint32_t(plan.syminfo[sy] >> 24) & 0xffff;
+            if (w < pw) { pw = w; pv = uint32_t(k); }
+          }
+          sm.pivot[s][j] = uint8_t(pv);
+          sm.pivot_w[s][j] = uint8_t(min(pw, 255u));
+        }
+        const bool enumerable = !(active && s > 0) || (top_full && pw <= ANS_TF_MAX);
+        if (__syncthreads_and(enumerable ? 1 : 0)) {
+          if (active && s > 0) {
+            const uint8_t* rs = symp + uint64_t(b_hi - 1) * BATCH_N;
+            const uint32_t dp = sm.first_desc[s][j][pv];
+            for (uint32_t idx = 0; idx < pw; idx++) {
+              uint32_t g = (sm.next_states - 1024)[(dp >> 20) + pw + idx];  // the state after the pivot step landed in slot idx
+              for (int m = 62 - int(pv); m >= 0; m--) ans_step_quiet(sm.desc_tab[rs[4 * m + j]], g, sm.next_states);  // rest of the top batch
+              for (uint32_t b = b_hi - 1; b > b_lo; b--) ans_full_batch<true>(sm, symp + uint64_t(b - 1) * BATCH_N, nullptr, j, gmask, g);
+              sm.tf[s][j][idx] = uint16_t(g);
+            }
+          }
+          __syncthreads();
+          if (tid < 4) {  // chain tid: the true input of every segment of the round, in encode order
+            uint32_t st = sm.out_state[0][tid];
+            for (uint32_t s2 = 1; s2 < n_round; s2++) {
+              sm.true_in[s2][tid] = uint16_t(st);
+              const uint32_t pv2 = sm.pivot[s2][tid], pw2 = sm.pivot_w[s2][tid];
+              for (uint32_t k = 0; k < pv2; k++) ans_step_quiet(sm.first_desc[s2][tid][k], st, sm.next_states);
+              const uint32_t bits = ((st + sm.first_desc[s2][tid][pv2]) >> 16) & 0xfu;
+              st = sm.tf[s2][tid][(st >> bits) - pw2];
+            }
+            sm.carry[tid] = uint16_t(st);
+          }
+          __syncthreads();
+          if (active && s > 0) {
+            uint32_t st = sm.true_in[s][j];
+            for (uint32_t b = b_hi; b > b_lo; b--) {
+              const uint32_t bb = b - 1;
+              uint32_t bits = ans_full_batch<false>(sm, symp + uint64_t(bb) * BATCH_N, ansp + uint64_t(bb) * BATCH_N, j, gmask, st);
+              bits += __shfl_xor_sync(gmask, bits, 1);
+              bits += __shfl_xor_sync(gmask, bits, 2);
+              if (j == 0) { sums[bb] = bits; ent[bb].bit_pos = 0; }
+              ent[bb].st[j] = uint16_t(st - size);
+            }
+          }
+          __syncthreads();
+          continue;  // next round (the carry is set)
+        }
+        if (s == 0) {  // in-order pass over the whole page from the default state (idempotent: it overwrites what the rounds so far wrote)
           uint32_t st = size;
           for (uint32_t b = nb; b > 0; b--) {
             const uint32_t bb = b - 1;

@@ -23,12 +23,15 @@ struct Context {
   bool initialized = false;
   bool device_ok = false;
   std::string device_err;
-  DevBuf src, out, index, statuses, misc, dec_syms, dec_offs, dec_nvars, dec_narrow, gather, cold;
+  DevBuf src, out, index, statuses, misc, dec_syms, dec_offs, dec_narrow, gather, cold;
   CompressScratch enc;
   Binoms* d_binoms = nullptr;
   int sm_count = 0;
-  uint32_t last_decode_chunks = 0;  // chunks of the last decode launch (their class bytes are still in dec_nvars)
+  uint32_t last_decode_chunks = 0;  // chunks of the last decode launch (their class bytes are still at d_cls)
   std::vector<uint8_t> host_cls;    // class bytes of the last fused launch as the kernel reported them (0 = decoded there)
+  uint8_t* d_cls = nullptr;         // class bytes of the last decode launch (they live behind the status words in `statuses`)
+  void* pinned_res = nullptr;       // page-locked landing buffer for the statuses + class bytes of a decode launch
+  size_t pinned_cap = 0;
   bool last_classes_fused = false;
   uint32_t* gather_err = nullptr;   // error word of the last page gather (inside `gather`)  // every chunk of the last launch was served by fused_narrow_kernel
 };
@@ -39,9 +42,13 @@ static Context& ctx() {
 }
 
 static void release_buffers(Context& c) {
-  for (DevBuf* b : {&c.src, &c.out, &c.index, &c.statuses, &c.misc, &c.dec_syms, &c.dec_offs, &c.dec_nvars, &c.dec_narrow, &c.gather, &c.cold}) b->release();
+  for (DevBuf* b : {&c.src, &c.out, &c.index, &c.statuses, &c.misc, &c.dec_syms, &c.dec_offs, &c.dec_narrow, &c.gather, &c.cold}) b->release();
   c.enc.release();
   c.gather_err = nullptr;
+  c.d_cls = nullptr;
+  if (c.pinned_res) cudaFreeHost(c.pinned_res);
+  c.pinned_res = nullptr;
+  c.pinned_cap = 0;
   if (c.d_binoms) cudaFree(c.d_binoms);
   c.d_binoms = nullptr;
 }
@@ -122,11 +129,20 @@ struct DecodeOutcome {
 static PcoB200Error launch_decode(Context& c, const FileParams& fp, const uint8_t* d_index, uint64_t index_len, uint64_t chunks_offset, uint32_t n_chunks,
                                   void* d_out, uint64_t out_len, cudaStream_t stream) {
   if (n_chunks == 0) return PCO_B200_OK;
-  PCOB_CUDA_TRY(c.statuses.reserve(size_t(n_chunks + 1) * sizeof(uint32_t)));
+  // status words and class bytes side by side: one copy brings both back
+  const size_t res_bytes = size_t(n_chunks) * (sizeof(uint32_t) + 1);
+  PCOB_CUDA_TRY(c.statuses.reserve(res_bytes + 64));
   uint32_t* d_st = c.statuses.as<uint32_t>();
-  PCOB_CUDA_TRY(cudaMemsetAsync(d_st, 0xff, size_t(n_chunks) * sizeof(uint32_t), stream));
+  uint8_t* d_cls = reinterpret_cast<uint8_t*>(d_st + n_chunks);
+  c.d_cls = d_cls;
+  if (c.pinned_cap < res_bytes) {
+    if (c.pinned_res) cudaFreeHost(c.pinned_res);
+    c.pinned_res = nullptr;
+    c.pinned_cap = 0;
+    PCOB_CUDA_TRY(cudaHostAlloc(&c.pinned_res, res_bytes + (res_bytes >> 1) + 4096, cudaHostAllocDefault));
+    c.pinned_cap = res_bytes + (res_bytes >> 1) + 4096;
+  }
   const IndexChunk* d_chunks = reinterpret_cast<const IndexChunk*>(d_index + chunks_offset);
-  PCOB_CUDA_TRY(c.dec_nvars.reserve(size_t(n_chunks) + 64));
   static const bool use_fused = [] { const char* e = std::getenv("PCOB200_FUSED"); return !(e && e[0] == '0'); }();
   const bool narrow_ok = true;  // the fused kernel serves every number width
   if (!c.attrs_set) {
@@ -143,26 +159,27 @@ static PcoB200Error launch_decode(Context& c, const FileParams& fp, const uint8_
     PCOB_CUDA_TRY(cudaFuncSetAttribute(fused_narrow_kernel<uint8_t>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
   }
   c.last_decode_chunks = n_chunks;
-  std::vector<uint32_t> st(n_chunks);
+  const uint32_t* st = static_cast<const uint32_t*>(c.pinned_res);
   bool fused_ran = false;
+  if (!(use_fused && narrow_ok)) PCOB_CUDA_TRY(cudaMemsetAsync(d_st, 0xff, size_t(n_chunks) * sizeof(uint32_t), stream));  // the fused kernel writes every word itself
   if (use_fused && narrow_ok) {
     fused_ran = true;
     profiler().begin("fused_narrow_kernel", stream);
     dispatch_latent(fp.dtype, [&](auto tag) {
       using L = decltype(tag);
-      fused_narrow_kernel<L><<<n_chunks, FZ_THREADS, sizeof(FusedSmem), stream>>>(fp, d_chunks, d_index, index_len, d_st, c.dec_nvars.as<uint8_t>(), static_cast<L*>(d_out), out_len);
+      fused_narrow_kernel<L><<<n_chunks, FZ_THREADS, sizeof(FusedSmem), stream>>>(fp, d_chunks, d_index, index_len, d_st, d_cls, static_cast<L*>(d_out), out_len);
       return 0;
     });
     profiler().end(stream);
     PCOB_CUDA_TRY(cudaGetLastError());
     // statuses and class bytes come back in one round trip; the general kernels only run if some chunk still needs them
-    c.host_cls.resize(n_chunks);
-    PCOB_CUDA_TRY(cudaMemcpyAsync(st.data(), d_st, size_t(n_chunks) * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-    PCOB_CUDA_TRY(cudaMemcpyAsync(c.host_cls.data(), c.dec_nvars.p, size_t(n_chunks), cudaMemcpyDeviceToHost, stream));
+    PCOB_CUDA_TRY(cudaMemcpyAsync(c.pinned_res, d_st, res_bytes, cudaMemcpyDeviceToHost, stream));
     PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
+    const uint8_t* cls = reinterpret_cast<const uint8_t*>(st + n_chunks);
+    c.host_cls.assign(cls, cls + n_chunks);
     bool pending = false;
     for (uint32_t i = 0; i < n_chunks; i++) {
-      if (!(c.host_cls[i] & CLS_DONE)) { pending = true; continue; }
+      if (!(cls[i] & CLS_DONE)) { pending = true; continue; }
       if (st[i] != ST_OK) return status_to_error(st[i], ("chunk " + std::to_string(i)).c_str());
     }
     c.last_classes_fused = true;
@@ -177,28 +194,28 @@ static PcoB200Error launch_decode(Context& c, const FileParams& fp, const uint8_
   if (old_narrow) PCOB_CUDA_TRY(c.dec_narrow.reserve(size_t(n_chunks) * sizeof(NarrowInfo)));
   profiler().begin("symwalk_kernel", stream);
   symwalk_kernel<<<n_chunks, SW_THREADS, sizeof(SymWalkSmem), stream>>>(fp, d_chunks, d_index, index_len, out_len, c.dec_syms.as<uint8_t>(), c.dec_offs.as<uint32_t>(),
-                                                                        c.dec_nvars.as<uint8_t>(), old_narrow ? c.dec_narrow.as<NarrowInfo>() : nullptr, fused_ran ? 1 : 0);
+                                                                        d_cls, old_narrow ? c.dec_narrow.as<NarrowInfo>() : nullptr, fused_ran ? 1 : 0);
   profiler().end(stream);
   profiler().begin("decode_kernel", stream);  // the span covers every decode instantiation (a chunk runs in exactly one)
   if (old_narrow) {
     if (nt_bits(fp.dtype) == 64)
       decode_narrow_kernel<uint64_t><<<n_chunks, NW_THREADS, 0, stream>>>(fp, d_chunks, d_st, static_cast<uint64_t*>(d_out), out_len, c.dec_syms.as<uint8_t>(),
-                                                                        c.dec_offs.as<uint32_t>(), c.dec_nvars.as<uint8_t>(), c.dec_narrow.as<NarrowInfo>());
+                                                                        c.dec_offs.as<uint32_t>(), d_cls, c.dec_narrow.as<NarrowInfo>());
     else
       decode_narrow_kernel<uint32_t><<<n_chunks, NW_THREADS, 0, stream>>>(fp, d_chunks, d_st, static_cast<uint32_t*>(d_out), out_len, c.dec_syms.as<uint8_t>(),
-                                                                        c.dec_offs.as<uint32_t>(), c.dec_nvars.as<uint8_t>(), c.dec_narrow.as<NarrowInfo>());
+                                                                        c.dec_offs.as<uint32_t>(), d_cls, c.dec_narrow.as<NarrowInfo>());
   }
   dispatch_latent(fp.dtype, [&](auto tag) {
     using L = decltype(tag);
     decode_kernel<L, 1><<<n_chunks, DEC_THREADS, sizeof(DecodeSmem), stream>>>(fp, d_chunks, d_st, d_index, index_len, static_cast<L*>(d_out), out_len, c.d_binoms,
-                                                                                c.dec_syms.as<uint8_t>(), c.dec_offs.as<uint32_t>(), c.dec_nvars.as<uint8_t>());
+                                                                                c.dec_syms.as<uint8_t>(), c.dec_offs.as<uint32_t>(), d_cls);
     decode_kernel<L, 2><<<n_chunks, DEC_THREADS, sizeof(DecodeSmem), stream>>>(fp, d_chunks, d_st, d_index, index_len, static_cast<L*>(d_out), out_len, c.d_binoms,
-                                                                                c.dec_syms.as<uint8_t>(), c.dec_offs.as<uint32_t>(), c.dec_nvars.as<uint8_t>());
+                                                                                c.dec_syms.as<uint8_t>(), c.dec_offs.as<uint32_t>(), d_cls);
     return 0;
   });
   profiler().end(stream);
   PCOB_CUDA_TRY(cudaGetLastError());
-  PCOB_CUDA_TRY(cudaMemcpyAsync(st.data(), d_st, size_t(n_chunks) * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+  PCOB_CUDA_TRY(cudaMemcpyAsync(c.pinned_res, d_st, size_t(n_chunks) * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
   PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
   for (uint32_t i = 0; i < n_chunks; i++)
     if (st[i] != ST_OK) return status_to_error(st[i], ("chunk " + std::to_string(i)).c_str());
@@ -243,7 +260,9 @@ static PcoB200Error decompress_fast(const void* compressed, size_t compressed_le
   if (src_dev) d_src = static_cast<const uint8_t*>(compressed);
   else {
     PCOB_CUDA_TRY(c.src.reserve(compressed_len + 16));
+    call_trace().mark("d.begin");
     PCOB_CUDA_TRY(copy_sliced(c.src.p, compressed, compressed_len, cudaMemcpyHostToDevice, stream));
+    call_trace().mark("d.h2d_submitted");
     d_src = c.src.as<uint8_t>();
   }
   FileParams fp;
@@ -275,10 +294,14 @@ static PcoB200Error decompress_fast(const void* compressed, size_t compressed_le
     if (ih.n_chunks > 0xffffffffull) return fail(PCO_B200_INVALID_ARGUMENT, "too many chunks");
     // a host destination is staged in c.out, which holds n_emit numbers: that is the kernels' bound, whatever the index claims
     if (PcoB200Error e = launch_decode(c, fp, d_idx, index_len, ih.chunks_offset, uint32_t(ih.n_chunks), d_out, dst_dev ? uint64_t(dst_len) : n_emit, stream)) return e;
+    call_trace().mark("d.decoded");
     if (!dst_dev && n_emit) {
       PCOB_CUDA_TRY(copy_sliced(dst, d_out, n_emit * elem, cudaMemcpyDeviceToHost, stream));
+      call_trace().mark("d.d2h_submitted");
       PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
     }
+    call_trace().mark("d.end");
+    call_trace().flush("decompress");
     outcome->n_total = ih.n_total;
     outcome->terminated = ih.end_byte != 0;
     return PCO_B200_OK;
@@ -756,9 +779,9 @@ void pco_b200_thread_release(void) {
 int pco_b200_profile_chunk_classes(unsigned* counts8) {
   Context& c = ctx();
   for (int i = 0; i < 8; i++) counts8[i] = 0;
-  if (!c.device_ok || c.last_decode_chunks == 0 || !c.dec_nvars.p) return 0;
+  if (!c.device_ok || c.last_decode_chunks == 0 || !c.d_cls) return 0;
   std::vector<uint8_t> cls(c.last_decode_chunks);
-  if (cudaMemcpy(cls.data(), c.dec_nvars.p, cls.size(), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  if (cudaMemcpy(cls.data(), c.d_cls, cls.size(), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
   for (uint8_t k : cls) counts8[(k & 0x7f) < 8 ? (k & 0x7f) : 0]++;
   return int(cls.size());
 }

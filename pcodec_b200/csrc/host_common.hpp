@@ -4,6 +4,9 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstdint>
 #include <cstring>
 #include <mutex>
@@ -88,17 +91,60 @@ inline Profiler& profiler() {
   return p;
 }
 
-// ---- large host <-> device copies in slices ---------------------------------
-// One cudaMemcpyAsync of hundreds of megabytes occupies its copy engine for milliseconds; a small copy that ANOTHER stream issues in the
-// same direction meanwhile (a status word, a file header, the compressed bytes of the opposite call) queues behind all of it.  Two host
-// threads that stream chunk groups through compress and decompress then wait for each other's big copy in turn, and the two PCIe directions
-// never overlap (measured: each call twice as long as alone).  Slices give the engine a boundary every few hundred microseconds.
+// ---- PCOB200_TRACE=1: host-clock marks of a call's phases on stderr (one line per call; all threads share the epoch) ------------------
+inline bool trace_enabled() {
+  static const bool on = std::getenv("PCOB200_TRACE") != nullptr;
+  return on;
+}
+struct CallTrace {
+  std::string line;
+  static double now_ms() {
+    static const auto epoch = std::chrono::steady_clock::now();
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - epoch).count();
+  }
+  void mark(const char* what) {
+    if (!trace_enabled()) return;
+    char buf[64];
+    std::snprintf(buf, sizeof(buf), " %s=%.2f", what, now_ms());
+    line += buf;
+  }
+  void flush(const char* call) {
+    if (!trace_enabled()) return;
+    std::fprintf(stderr, "[pcob200 trace] %s%s\n", call, line.c_str());
+    line.clear();
+  }
+};
+inline CallTrace& call_trace() {
+  static thread_local CallTrace t;
+  return t;
+}
+
+// ---- large host <-> device copies: sliced, and submitted no more than two slices ahead ------------------------------------------
+// A copy engine serves the copies of one direction in the order they were SUBMITTED, whatever stream they came on (measured on this B200:
+// `profiles/r02_m_e2e_probe.txt`, `e2e.trace_ms` of the bench).  One cudaMemcpyAsync of hundreds of megabytes - or sixty-four 4 MB slices
+// submitted in one go - therefore holds back every small copy another host thread issues in that direction meanwhile (a status word, a
+// file header, the compressed bytes of the opposite call) for milliseconds, and two threads that stream chunk groups through compress and
+// decompress wait for each other's big copy in turn: the two PCIe directions never overlap.  So big copies go out in 8 MB slices and the
+// host submits slice k + 2 only when slice k has finished; another thread's copy then waits for at most two slices (~0.3 ms).
 inline cudaError_t copy_sliced(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t stream) {
-  constexpr size_t SLICE = size_t(4) << 20;
+  constexpr size_t SLICE = size_t(8) << 20;
+  constexpr int DEPTH = 2;
   if (bytes <= 2 * SLICE) return cudaMemcpyAsync(dst, src, bytes, kind, stream);
-  for (size_t off = 0; off < bytes; off += SLICE) {
+  static thread_local cudaEvent_t ev[DEPTH] = {nullptr, nullptr};
+  for (int i = 0; i < DEPTH; i++)
+    if (!ev[i]) {
+      cudaError_t e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+      if (e != cudaSuccess) return e;
+    }
+  size_t k = 0;
+  for (size_t off = 0; off < bytes; off += SLICE, k++) {
+    if (k >= size_t(DEPTH)) {
+      cudaError_t e = cudaEventSynchronize(ev[k % DEPTH]);  // slice k - DEPTH is done
+      if (e != cudaSuccess) return e;
+    }
     const size_t len = bytes - off < SLICE ? bytes - off : SLICE;
     cudaError_t e = cudaMemcpyAsync(static_cast<uint8_t*>(dst) + off, static_cast<const uint8_t*>(src) + off, len, kind, stream);
+    if (e == cudaSuccess) e = cudaEventRecord(ev[k % DEPTH], stream);
     if (e != cudaSuccess) return e;
   }
   return cudaSuccess;
