@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--abi3-chunks", type=int, default=32, help="chunks of the three-function-ABI leg (its index-free decompress walks the chunks one after the other)")
     ap.add_argument("--e2e-groups", type=int, default=8, help="chunk groups the streamed e2e leg cuts the array into")
+    ap.add_argument("--e2e-threads", type=int, default=2, help="host threads per direction in the streamed e2e leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-index-free", action="store_true", help="skip the pco_b200_decompress_chunks timing (not part of `value`)")
     ap.add_argument("--results-csv", default=None, help="also merge this run into a CSV with the reference bench tool's schema and codec naming (pcodec_b200/benchfmt.py)")
@@ -546,7 +547,6 @@ def run_gpu_arm(args, rank, world):
         h_comp_g, h_index_g = h_comp, h_index
         g_nw = [C.c_size_t() for _ in range(G)]
         g_il = [C.c_size_t() for _ in range(G)]
-        streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
         import queue
 
         # two persistent worker threads (the library keeps its scratch per calling thread: a worker that lived for one pass would allocate
@@ -570,39 +570,47 @@ def run_gpu_arm(args, rank, world):
                     except Exception as ex:  # noqa: BLE001
                         self.done.put(ex)
 
-        handoff = queue.Queue()
+        P = max(1, min(args.e2e_threads, G))  # host threads per direction: producer p compresses groups p, p + P, ..., consumer p decompresses them
+        streams = [torch.cuda.Stream(device=dev) for _ in range(2 * P)]
+        handoffs = [queue.Queue() for _ in range(P)]
         trace = []  # (call, group, start, end) of the last streamed pass: shows how far the two directions overlap
 
-        def produce(_):
-            try:
-                sa = C.c_void_p(streams[0].cuda_stream)
-                for g in range(G):
-                    t_a = time.perf_counter()
-                    rc = L.pco_b200_compress_ex(C.c_void_p(h_nums.data_ptr() + 8 * bounds[g] * CHUNK_N), C.c_size_t(g_n[g]), C.c_ubyte(2), C.byref(cfg), C.c_int(0),
-                                                C.c_void_p(h_comp_g.data_ptr() + int(g_coff[g])), C.c_size_t(g_cap[g]), C.byref(g_nw[g]),
-                                                C.c_void_p(h_index_g.data_ptr() + int(g_ioff[g])), C.c_size_t(g_icap[g]), C.byref(g_il[g]), C.c_uint32(0), sa)
+        def make_produce(p):
+            def produce(_):
+                try:
+                    sa = C.c_void_p(streams[p].cuda_stream)
+                    for g in range(p, G, P):
+                        t_a = time.perf_counter()
+                        rc = L.pco_b200_compress_ex(C.c_void_p(h_nums.data_ptr() + 8 * bounds[g] * CHUNK_N), C.c_size_t(g_n[g]), C.c_ubyte(2), C.byref(cfg), C.c_int(0),
+                                                    C.c_void_p(h_comp_g.data_ptr() + int(g_coff[g])), C.c_size_t(g_cap[g]), C.byref(g_nw[g]),
+                                                    C.c_void_p(h_index_g.data_ptr() + int(g_ioff[g])), C.c_size_t(g_icap[g]), C.byref(g_il[g]), C.c_uint32(0), sa)
+                        _lib.check(rc)
+                        trace.append(("c", g, t_a, time.perf_counter()))
+                        handoffs[p].put(g)
+                finally:
+                    handoffs[p].put(None)
+
+            return produce
+
+        def make_consume(p):
+            def consume(_):
+                sb = C.c_void_p(streams[P + p].cuda_stream)
+                pr = _lib._CProgress()
+                while True:
+                    g = handoffs[p].get()
+                    if g is None:
+                        return
+                    t_b = time.perf_counter()
+                    rc = L.pco_b200_decompress_ex(C.c_void_p(h_comp_g.data_ptr() + int(g_coff[g])), g_nw[g], C.c_ubyte(2),
+                                                  C.c_void_p(h_out.data_ptr() + 8 * bounds[g] * CHUNK_N), C.c_size_t(g_n[g]), C.byref(pr),
+                                                  C.c_void_p(h_index_g.data_ptr() + int(g_ioff[g])), g_il[g], C.c_uint32(0), sb)
                     _lib.check(rc)
-                    trace.append(("c", g, t_a, time.perf_counter()))
-                    handoff.put(g)
-            finally:
-                handoff.put(None)
+                    trace.append(("d", g, t_b, time.perf_counter()))
+                    assert pr.n_processed == g_n[g] and pr.finished
 
-        def consume(_):
-            sb = C.c_void_p(streams[1].cuda_stream)
-            pr = _lib._CProgress()
-            while True:
-                g = handoff.get()
-                if g is None:
-                    return
-                t_b = time.perf_counter()
-                rc = L.pco_b200_decompress_ex(C.c_void_p(h_comp_g.data_ptr() + int(g_coff[g])), g_nw[g], C.c_ubyte(2),
-                                              C.c_void_p(h_out.data_ptr() + 8 * bounds[g] * CHUNK_N), C.c_size_t(g_n[g]), C.byref(pr),
-                                              C.c_void_p(h_index_g.data_ptr() + int(g_ioff[g])), g_il[g], C.c_uint32(0), sb)
-                _lib.check(rc)
-                trace.append(("d", g, t_b, time.perf_counter()))
-                assert pr.n_processed == g_n[g] and pr.finished
+            return consume
 
-        workers = [_Worker(produce), _Worker(consume)]
+        workers = [_Worker(make_produce(p)) for p in range(P)] + [_Worker(make_consume(p)) for p in range(P)]
 
         def e2e_pipelined():
             trace.clear()
@@ -653,8 +661,8 @@ def run_gpu_arm(args, rank, world):
         cg, ig = sum(x.value for x in g_nw), sum(x.value for x in g_il)
         e2e = {"value": world * U / 1e6 / (e2e_ms / 1e3), "unit": "MB/s", "h2d_bytes_per_step": int(U + cg + ig),
                "d2h_bytes_per_step": int(cg + ig + U), "ms_per_step": e2e_ms, "steps": max(1, args.steps),
-               "api": f"pco_b200_compress_ex + pco_b200_decompress_ex (C-ABI), pinned host buffers, streamed in {G} groups of chunks: one host thread compresses group g+1 "
-                      "while another decompresses group g (per-thread library contexts, one stream each)",
+               "api": f"pco_b200_compress_ex + pco_b200_decompress_ex (C-ABI), pinned host buffers, streamed in {G} groups of chunks by {P} + {P} host threads: "
+                      "compress of later groups runs beside decompress of earlier ones (per-thread library contexts, one stream each; every group is a standalone file)",
                "trace_ms": e2e_trace, "pass_wall_ms": streamed_wall,
                "single_call": {"value": world * U / 1e6 / (single_ms / 1e3), "ms_per_step": single_ms,
                                "api": "one pco_b200_compress_ex + one pco_b200_decompress_ex over the whole array (H2D, kernels, D2H back to back)"}}

@@ -490,12 +490,12 @@ __global__ void __launch_bounds__(RS_THREADS, 1) radix_sort_segments_kernel(L* _
 // Bin training (train_infos, chunk_compressor.rs:52-99) in two kernels per latent var:
 //   plan_probe_kernel — one 512-thread CTA per chunk, HBM-bound: order statistics at the 2^log equal-count boundaries
 //                       (from shared-memory counters when the key range is narrow, else from the sorted keys)
-//   plan_solve_kernel — four warps per chunk, latency-bound and short: histogram state machine (one thread), bin-merge DP
-//                       (the candidates of a step spread over the CTA, one barrier per step), weight quantisation, tANS
-//                       tables.  All chunks are resident at once, so the serial parts overlap.
+//   plan_solve_kernel — one warp per chunk (SOLVE_THREADS; the code also runs with more), latency-bound and short: histogram
+//                       state machine (one thread), bin-merge DP (the candidates of a step spread over the threads), weight
+//                       quantisation, tANS tables.  All chunks are resident at once, so the serial parts overlap.
 // ---------------------------------------------------------------------------
 constexpr int PLAN_THREADS = 512;
-constexpr int SOLVE_THREADS = 128;
+constexpr int SOLVE_THREADS = 32;   // 128 (a barrier per DP step) measured slower with every chunk resident: 0.26 ms against 0.225 on C2
 constexpr uint32_t PLAN_MAX_COUNT_BITS = 15;  // counting histogram (no sort) when the key range fits 2^15 shared-memory counters
 
 // Order statistics handed from the probe kernel to the solver (per chunk and var, in HBM scratch)
@@ -1664,6 +1664,62 @@ __global__ void __launch_bounds__(ANS_THREADS, 4) ans_encode_kernel(EncParams ep
     }
     return bits_total;
   };
+  // Last resort for tables on which neither the speculation nor the transfer functions work (every thread of the CTA calls it together):
+  auto serial_pass = [&]() {
+    // In-order pass over the whole page from the default state (idempotent: it overwrites what the rounds so far wrote).  The serial
+    // part is the state chain alone: four lanes walk the four chains and leave every step's INPUT state in the output slot; the bits
+    // and values follow from (state, symbol) per element, which the whole CTA then does in parallel.
+    if (tid < 4) {
+      uint32_t st = size;
+      for (uint32_t b = nb; b > 0; b--) {
+        const uint32_t bb = b - 1;
+        const uint8_t* rs = symp + uint64_t(bb) * BATCH_N;
+        uint16_t* ro = ansp + uint64_t(bb) * BATCH_N;
+        if (bb < nb_full) {
+          const uint4* src = reinterpret_cast<const uint4*>(rs);
+          const uint32_t pick = 0x4440u | uint32_t(j);
+          uint4 cur = src[15], nxt = cur;
+#pragma unroll 2
+          for (int q = 15; q >= 0; q--) {
+            if (q > 0) nxt = src[q - 1];
+            const uint32_t d3 = sm.desc_tab[__byte_perm(cur.w, 0, pick)], d2 = sm.desc_tab[__byte_perm(cur.z, 0, pick)];
+            const uint32_t d1 = sm.desc_tab[__byte_perm(cur.y, 0, pick)], d0 = sm.desc_tab[__byte_perm(cur.x, 0, pick)];
+            ro[16 * q + 12 + j] = uint16_t(st);
+            ans_step_quiet(d3, st, sm.next_states);
+            ro[16 * q + 8 + j] = uint16_t(st);
+            ans_step_quiet(d2, st, sm.next_states);
+            ro[16 * q + 4 + j] = uint16_t(st);
+            ans_step_quiet(d1, st, sm.next_states);
+            ro[16 * q + j] = uint16_t(st);
+            ans_step_quiet(d0, st, sm.next_states);
+            cur = nxt;
+          }
+        } else {
+          const uint32_t cnt = n - bb * BATCH_N;
+          const int steps = cnt > uint32_t(j) ? int((cnt - 1 - j) / 4 + 1) : 0;
+          for (int m = steps - 1; m >= 0; m--) {
+            ro[4 * m + j] = uint16_t(st);
+            ans_step_quiet(sm.desc_tab[rs[4 * m + j]], st, sm.next_states);
+          }
+        }
+        if (j == 0) { sums[bb] = 0; ent[bb].bit_pos = 0; }
+        ent[bb].st[j] = uint16_t(st - size);
+      }
+      chunks[c].final_state[v][j] = st - size;
+    }
+    __syncthreads();
+    for (uint32_t bb = 0; bb < nb; bb++) {  // batch bb: one element per thread
+      const uint32_t i = bb * BATCH_N + uint32_t(tid);
+      uint32_t bits = 0;
+      if (i < n) {
+        const uint32_t st = ansp[i], d = sm.desc_tab[symp[i]];
+        bits = ((st + d) >> 16) & 0xfu;
+        ansp[i] = uint16_t((st & ~(0xffffffffu << bits)) | (bits << 12));
+      }
+      for (int dd = 16; dd > 0; dd >>= 1) bits += __shfl_xor_sync(0xffffffffu, bits, dd);
+      if ((tid & 31) == 0 && bits) atomicAdd(&sums[bb], bits);
+    }
+  };
   for (uint32_t done = 0; done < n_segs; done += ANS_SEGS) {
     // this round: segments n_segs-1-done, n_segs-2-done, ... (encode order); thread group s takes the s-th of them
     const bool active = done + uint32_t(s) < n_segs;
@@ -1700,46 +1756,11 @@ __global__ void __launch_bounds__(ANS_THREADS, 4) ans_encode_kernel(EncParams ep
     uint32_t my_out = state;
     __syncthreads();
     {
-      // Many wrong guesses (more than a quarter of the round's): the table merges trajectories slowly.  First a deeper guess: two probe
-      // trajectories from far-apart states over 4, 8, 16, 32 batches of the preceding segments until they coincide - a table with one
-      // rare light symbol (weights like 205 / 50 / 1) merges everything at that symbol's next occurrence, a few batches back - and the
-      // segments whose guess moved are encoded again.  What is still wrong after that goes to the exact paths below.
-      const uint32_t in_chk0 = (s == 0 || !active) ? my_in : uint32_t(sm.out_state[s - 1][j]);
-      const int wrong0 = __syncthreads_count(active && s > 0 && in_chk0 != my_in);
-      if (uint32_t(wrong0) > min(n_segs - done, uint32_t(ANS_SEGS))) {
-        // the 4 chains of a group decide together (encode_segment shuffles within the group)
-        const bool mine_wrong = active && s > 0 && in_chk0 != my_in;
-        const bool group_wrong = (__ballot_sync(0xffffffffu, mine_wrong) & gmask) != 0;
-        uint32_t g = my_in;
-        if (active && s > 0 && group_wrong) {
-          for (uint32_t wb = 4;; wb *= 2) {
-            const uint32_t w_hi = min(b_hi + wb, nb_full);
-            uint32_t h = 2 * size - 1;
-            g = size;
-            for (uint32_t b = w_hi; b > b_hi; b--) {
-              ans_full_batch<true>(sm, symp + uint64_t(b - 1) * BATCH_N, nullptr, j, gmask, g);
-              ans_full_batch<true>(sm, symp + uint64_t(b - 1) * BATCH_N, nullptr, j, gmask, h);
-            }
-            if (g == h || w_hi >= nb_full || wb >= 32) break;
-          }
-        }
-        const bool redo = (__ballot_sync(0xffffffffu, g != my_in) & gmask) != 0;
-        __syncthreads();  // every thread has read its predecessor's old output
-        if (redo) {
-          my_in = g;
-          state = encode_segment(my_in);
-          sm.out_state[s][j] = uint16_t(state);
-          my_out = state;
-        }
-        __syncthreads();
-      }
-    }
-    {
       // The speculation rests on tANS trajectories merging (a symbol of weight w maps all states onto w values).  Tables whose weights are
       // (nearly) all equal - what equal-count bins of smooth wide-range data give - act on the state's top bits as near-permutations: guesses
       // are wrong about 3 times in 4 and the corrections never meet the old trajectory, so the fix-up below would re-encode segment after
-      // segment element-wise at the serial encoder's pace (measured: 8.5 ms per launch on C5 int64 order 0).  When more than a quarter of a
-      // round's guesses are wrong the round is solved exactly instead.  After a step with a symbol of weight w the state is one of w values
+      // segment element-wise at the serial encoder's pace (measured: 8.5 ms per launch on C5 int64 order 0).  When more than half of a
+      // round's guesses are wrong the round is solved exactly instead (a third wrong, as on C5 float64 order 0, is still cheaper to fix up).  After a step with a symbol of weight w the state is one of w values
       // (next_states[cum + slot], slot = (state >> bits) - w), whatever it was before: each (segment, chain) takes the lightest symbol among
       // its first ANS_TF_LOOK steps as the pivot, replays the rest of the segment quietly once per slot of the pivot (its transfer function,
       // <= ANS_TF_MAX entries), four threads chain the true inputs through the 64 transfer functions, and every segment is encoded once
@@ -1747,7 +1768,7 @@ __global__ void __launch_bounds__(ANS_THREADS, 4) ans_encode_kernel(EncParams ep
       const uint32_t in_chk = (s == 0 || !active) ? my_in : uint32_t(sm.out_state[s - 1][j]);
       const int wrong = __syncthreads_count(active && s > 0 && in_chk != my_in);
       const uint32_t n_round = min(n_segs - done, uint32_t(ANS_SEGS));
-      if (uint32_t(wrong) > n_round) {  // 4 lanes per segment: wrong / 4 > n_round / 4
+      if (uint32_t(wrong) > 2 * n_round) {  // 4 lanes per segment: more than half of the round's (segment, chain) pairs
         const bool top_full = b_hi >= 1 && b_hi - 1 < nb_full;  // only the round's top segment (s == 0) can hold the page's short batch
         uint32_t pv = 0, pw = 0xffffu;
         if (active && s > 0 && top_full) {
@@ -1802,23 +1823,16 @@ __global__ void __launch_bounds__(ANS_THREADS, 4) ans_encode_kernel(EncParams ep
           __syncthreads();
           continue;  // next round (the carry is set)
         }
-        if (s == 0) {  // in-order pass over the whole page from the default state (idempotent: it overwrites what the rounds so far wrote)
-          uint32_t st = size;
-          for (uint32_t b = nb; b > 0; b--) {
-            const uint32_t bb = b - 1;
-            uint32_t bits = bb < nb_full ? ans_full_batch<false>(sm, symp + uint64_t(bb) * BATCH_N, ansp + uint64_t(bb) * BATCH_N, j, gmask, st)
-                                         : short_batch(bb, st);
-            bits += __shfl_xor_sync(gmask, bits, 1);
-            bits += __shfl_xor_sync(gmask, bits, 2);
-            if (j == 0) { sums[bb] = bits; ent[bb].bit_pos = 0; }
-            ent[bb].st[j] = uint16_t(st - size);
-          }
-          chunks[c].final_state[v][j] = st - size;
-        }
+        serial_pass();
         return;
       }
     }
-    while (true) {
+    for (int iter = 0;; iter++) {
+      if (iter == 32) {  // corrections keep running off their segments (a cascade moves one segment per iteration, ~0.13 ms each): the
+                         // in-order pass (~4 ms) is cheaper than the rest of it.  C5 float64 order 0 takes ~10 cheap iterations (1 ms in all).
+        serial_pass();
+        return;
+      }
       const uint32_t in_true = (s == 0 || !active) ? my_in : uint32_t(sm.out_state[s - 1][j]);
       bool changed = false;
       if (in_true != my_in) {

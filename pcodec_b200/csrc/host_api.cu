@@ -222,9 +222,10 @@ static PcoB200Error launch_decode(Context& c, const FileParams& fp, const uint8_
   return PCO_B200_OK;
 }
 
-// Core of every decompress entry point.
-//   stop_when_full: pco::standalone::simple_decompress_into semantics (stop reading once dst is full);
-//                   false = simple_decompress semantics (walk the whole file; the caller checks capacity).
+// The fast kernels behind every decompress entry point.  The walk goes on while the numbers seen fit the destination - an exact fit still
+// has to find the terminator (a truncated file is an error for both of the reference's semantics) - and stops with `terminated = false`
+// and n_total > dst_len at the first chunk that does not fit: pco_standalone_simple_decompress_into turns that into its "exceeds dst_cap"
+// error (pco_c/src/lib.rs:98-120), pco_b200_decompress_ex into Progress{finished = false} (standalone/simple.rs:115-140).
 static PcoB200Error decompress_fast(const void* compressed, size_t compressed_len, uint32_t dtype, void* dst, size_t dst_len,
                                     const void* index, size_t index_len, uint32_t flags, void* cuda_stream, DecodeOutcome* outcome) {
   if (!nt_valid(dtype)) return fail(PCO_B200_INVALID_TYPE, "unknown number type byte: " + std::to_string(dtype));
@@ -418,9 +419,7 @@ static PcoB200Error decompress_cold(const void* compressed, size_t compressed_le
 // Core of every decompress entry point: the fast kernels, and for streams they decline (valid pco with Dict mode, Lookback / Conv1
 // deltas, tANS tables beyond 2^10 states or 256 bins, ...) the single-thread device decoder.  PCOB200_COLD_DECODE=0 keeps the refusal.
 static PcoB200Error decompress_core(const void* compressed, size_t compressed_len, uint32_t dtype, void* dst, size_t dst_len,
-                                    const void* index, size_t index_len, uint32_t flags, void* cuda_stream, bool stop_when_full,
-                                    DecodeOutcome* outcome) {
-  (void)stop_when_full;
+                                    const void* index, size_t index_len, uint32_t flags, void* cuda_stream, DecodeOutcome* outcome) {
   PcoB200Error e = decompress_fast(compressed, compressed_len, dtype, dst, dst_len, index, index_len, flags, cuda_stream, outcome);
   static const bool cold_ok = [] { const char* v = std::getenv("PCOB200_COLD_DECODE"); return !(v && v[0] == '0'); }();
   if (e == PCO_B200_UNSUPPORTED && cold_ok) {
@@ -462,7 +461,7 @@ enum PcoError pco_standalone_simple_decompress_into(const void* compressed, size
                                                     size_t dst_cap, size_t* n_written) {
   if (!nt_valid(dtype)) return PcoInvalidType;
   DecodeOutcome oc;
-  PcoB200Error e = decompress_core(compressed, compressed_len, dtype, dst, dst_cap, nullptr, 0, 0, nullptr, /*stop_when_full=*/false, &oc);
+  PcoB200Error e = decompress_core(compressed, compressed_len, dtype, dst, dst_cap, nullptr, 0, 0, nullptr, &oc);
   if (e != PCO_B200_OK) return PcoDecompressionError;
   if (oc.n_total > dst_cap) {
     fail(PCO_B200_IO, "decompressed count exceeds dst_cap");
@@ -475,7 +474,7 @@ enum PcoError pco_standalone_simple_decompress_into(const void* compressed, size
 PcoB200Error pco_b200_decompress_ex(const void* compressed, size_t compressed_len, unsigned char dtype, void* dst, size_t dst_len,
                                     PcoB200Progress* progress, const void* index, size_t index_len, uint32_t flags, void* cuda_stream) {
   DecodeOutcome oc;
-  PcoB200Error e = decompress_core(compressed, compressed_len, dtype, dst, dst_len, index, index_len, flags, cuda_stream, true, &oc);
+  PcoB200Error e = decompress_core(compressed, compressed_len, dtype, dst, dst_len, index, index_len, flags, cuda_stream, &oc);
   profiler().resolve();
   if (e != PCO_B200_OK) return e;
   if (progress) {

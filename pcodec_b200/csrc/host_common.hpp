@@ -119,32 +119,31 @@ inline CallTrace& call_trace() {
   return t;
 }
 
-// ---- large host <-> device copies: sliced, and submitted no more than two slices ahead ------------------------------------------
-// A copy engine serves the copies of one direction in the order they were SUBMITTED, whatever stream they came on (measured on this B200:
-// `profiles/r02_m_e2e_probe.txt`, `e2e.trace_ms` of the bench).  One cudaMemcpyAsync of hundreds of megabytes - or sixty-four 4 MB slices
-// submitted in one go - therefore holds back every small copy another host thread issues in that direction meanwhile (a status word, a
-// file header, the compressed bytes of the opposite call) for milliseconds, and two threads that stream chunk groups through compress and
-// decompress wait for each other's big copy in turn: the two PCIe directions never overlap.  So big copies go out in 8 MB slices and the
-// host submits slice k + 2 only when slice k has finished; another thread's copy then waits for at most two slices (~0.3 ms).
+// ---- large host <-> device copies: sliced, one slice in flight -----------------------------------------------------------------------
+// Copies of one direction issued on different streams do not share the link slice by slice: a copy engine stays with the stream it is
+// serving for as long as that stream has a copy queued (measured on this B200 with PCOB200_TRACE, profiles/r02_p_trace_tail.txt: with a
+// 268 MB upload running - whole, in 4 MB slices submitted in one go, or throttled to two slices in the queue - another host thread's
+// 48 MB upload waited until the last byte of the big one, 5 ms; the same in the other direction).  Two host threads that stream chunk
+// groups through compress and decompress then wait for each other's big copy in turn and the two PCIe directions never overlap.  So a
+// big copy goes out in 8 MB slices and the host submits a slice only when the previous one has finished: the stream's queue runs empty
+// every 0.15 ms, the engine turns to whoever else is waiting, and the copies of two threads alternate.  Cost: the submit latency of
+// ~10 us per slice when the thread has the link for itself.
 inline cudaError_t copy_sliced(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t stream) {
   constexpr size_t SLICE = size_t(8) << 20;
-  constexpr int DEPTH = 2;
   if (bytes <= 2 * SLICE) return cudaMemcpyAsync(dst, src, bytes, kind, stream);
-  static thread_local cudaEvent_t ev[DEPTH] = {nullptr, nullptr};
-  for (int i = 0; i < DEPTH; i++)
-    if (!ev[i]) {
-      cudaError_t e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
-      if (e != cudaSuccess) return e;
-    }
-  size_t k = 0;
-  for (size_t off = 0; off < bytes; off += SLICE, k++) {
-    if (k >= size_t(DEPTH)) {
-      cudaError_t e = cudaEventSynchronize(ev[k % DEPTH]);  // slice k - DEPTH is done
+  static thread_local cudaEvent_t ev = nullptr;
+  if (!ev) {
+    cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (e != cudaSuccess) return e;
+  }
+  for (size_t off = 0; off < bytes; off += SLICE) {
+    if (off) {
+      cudaError_t e = cudaEventSynchronize(ev);  // the previous slice is done
       if (e != cudaSuccess) return e;
     }
     const size_t len = bytes - off < SLICE ? bytes - off : SLICE;
     cudaError_t e = cudaMemcpyAsync(static_cast<uint8_t*>(dst) + off, static_cast<const uint8_t*>(src) + off, len, kind, stream);
-    if (e == cudaSuccess) e = cudaEventRecord(ev[k % DEPTH], stream);
+    if (e == cudaSuccess) e = cudaEventRecord(ev, stream);
     if (e != cudaSuccess) return e;
   }
   return cudaSuccess;

@@ -157,6 +157,12 @@ def test_reference_c_abi(oracle):
                                                    C.c_size_t(10000), C.byref(n)) == 1
     assert L.pco_standalone_simple_decompress_into(buf.ctypes.data_as(C.c_void_p), C.c_size_t(len(data)), C.c_ubyte(2), dst.ctypes.data_as(C.c_void_p),
                                                    C.c_size_t(10000), C.byref(n)) == 3
+    # a file that lost its terminator byte is an error even when its numbers fill dst_cap exactly (simple_decompress reads to the end:
+    # standalone/simple.rs:93-113), and so is a file cut inside its last chunk
+    for cut in (1, 40):
+        short = np.frombuffer(data[:-cut], dtype=np.uint8)
+        assert L.pco_standalone_simple_decompress_into(short.ctypes.data_as(C.c_void_p), C.c_size_t(len(data) - cut), C.c_ubyte(4),
+                                                       dst.ctypes.data_as(C.c_void_p), C.c_size_t(10000), C.byref(n)) == 3
 
 
 @pytest.mark.parametrize("case", ["short_bins", "multi_bin_delta"])
