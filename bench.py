@@ -40,7 +40,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-chunks", type=int, default=1024, help="chunks of the CPU arm per step, spread over one worker process per host thread (about 12 s of core time)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--abi3-chunks", type=int, default=32, help="chunks of the three-function-ABI leg (its index-free decompress walks the chunks one after the other)")
-    ap.add_argument("--e2e-groups", type=int, default=8, help="chunk groups the streamed e2e leg cuts the array into")
+    ap.add_argument("--e2e-groups", type=int, default=16, help="chunk groups the streamed e2e leg cuts the array into")
     ap.add_argument("--e2e-threads", type=int, default=2, help="host threads per direction in the streamed e2e leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-index-free", action="store_true", help="skip the pco_b200_decompress_chunks timing (not part of `value`)")

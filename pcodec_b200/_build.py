@@ -47,10 +47,14 @@ def build(force=False, verbose=False):
         return LIB
     # the image exports CXX=/opt/gcc/bin/g++ (links libstdc++ statically); use the system g++ as nvcc's host compiler
     ccbin = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
-    cmd = [_nvcc(), "-ccbin", ccbin] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    tmp = LIB + f".tmp{os.getpid()}"  # linked beside the target and renamed into place: a reader never sees a half-written library
+    cmd = [_nvcc(), "-ccbin", ccbin] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + SOURCES
     res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if res.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    os.replace(tmp, LIB)
     if verbose:
         print(res.stderr)
     return LIB

@@ -243,12 +243,17 @@ __device__ inline uint32_t cold_join(const ColdChunk& ch, const ColdReader& r0, 
           const bool neg = l < 0x8000u;
           const uint16_t abs_int = neg ? uint16_t(0x7fffu - l) : uint16_t(l - 0x8000u);
           const uint16_t gpi = 1u << 11;
-          float f = abs_int < gpi ? float(abs_int) : __half2float(__ushort_as_half(uint16_t(0x6800u + (abs_int - gpi))));
-          if (neg) f = -f;
           const uint16_t base_bits = from_latent_ordered<uint16_t>(uint16_t(ch.mode_base), true, false);
-          const __half fh = __float2half_rn(f);  // int_float_from_latent yields an f16
-          const float prod = __fmul_rn(__half2float(fh), __half2float(__ushort_as_half(base_bits)));
-          un = L(__half_as_ushort(__float2half_rn(prod)));
+          if (abs_int >= gpi && uint16_t(0x6800u + (abs_int - gpi)) > 0x7c00u) {
+            // int_float_from_latent gave a NaN: widened to f32, multiplied and narrowed again it keeps its sign and payload and comes
+            // back quiet (half's conversions and the CPU's multiply; a GPU multiply would return the canonical NaN)
+            un = L(uint16_t((neg ? 0x8000u : 0u) | uint16_t(0x6800u + (abs_int - gpi)) | 0x0200u));
+          } else {
+            const uint16_t hb = abs_int < gpi ? __half_as_ushort(__float2half_rn(float(abs_int))) : uint16_t(0x6800u + (abs_int - gpi));  // an f16
+            const float f = __half2float(__ushort_as_half(uint16_t(hb | (neg ? 0x8000u : 0u))));  // the sign as a bit, not as a negation
+            const float prod = __fmul_rn(f, __half2float(__ushort_as_half(base_bits)));
+            un = L(__half_as_ushort(__float2half_rn(prod)));
+          }
         } else if constexpr (sizeof(L) >= 4) {
           un = float_mult_unadjusted(p, from_latent_ordered<L>(L(ch.mode_base), true, false));
         } else {

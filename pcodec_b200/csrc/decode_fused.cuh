@@ -83,6 +83,15 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 #if PCOB_FZ_WAIT_NS > 0
   while (!mbar_test(bar, parity)) __nanosleep(PCOB_FZ_WAIT_NS);
+#elif defined(PCOB_FZ_TRYWAIT_HINT_NS)
+  // try_wait with a suspend-time hint: the warp may sleep in hardware up to that long and is woken by the phase completion
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra.uni WAIT_DONE;\n\t"
+      "bra.uni WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity), "r"(uint32_t(PCOB_FZ_TRYWAIT_HINT_NS)) : "memory");
 #else
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -410,9 +419,13 @@ __device__ __forceinline__ void fused_decoder(FusedSmem& sm, const FileParams& f
       const uint32_t totT = __shfl_sync(0xffffffffu, incT, 31);
       const uint32_t slot = b % FZ_RING, nslot = (b + 1) % FZ_RING;
       uint64_t m64, fl;
-      do {
+      for (;;) {
         asm volatile("ld.volatile.shared.v2.u64 {%0, %1}, [%2];" : "=l"(m64), "=l"(fl) : "r"(link_sa + 16 * slot) : "memory");
-      } while (fl != b + 1);
+        if (fl == b + 1) break;
+#ifdef PCOB_FZ_LINK_SLEEP_NS
+        __nanosleep(PCOB_FZ_LINK_SLEEP_NS);
+#endif
+      }
       const L m = L(m64);
       if (lane == 0)
         asm volatile("st.volatile.shared.v2.u64 [%0], {%1, %2};" ::"r"(link_sa + 16 * nslot), "l"(uint64_t(L(L(m + L(uint64_t(base) << 8)) + L(totT)))),

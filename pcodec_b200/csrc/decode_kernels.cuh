@@ -547,24 +547,28 @@ __device__ __forceinline__ L to_latent_ordered(L bits, bool is_float, bool is_si
 // int_float_from_latent (data_types/float.rs:208-226) then `* base` without FMA contraction, returned as bits
 __device__ __forceinline__ uint64_t float_mult_unadjusted(uint64_t l, uint64_t base_bits) {
   const uint64_t MID = uint64_t(1) << 63;
-  bool neg = l < MID;
-  uint64_t abs_int = neg ? (MID - 1 - l) : (l - MID);
+  const bool neg = l < MID;
+  const uint64_t abs_int = neg ? (MID - 1 - l) : (l - MID);
   const uint64_t gpi = uint64_t(1) << 53;
-  double f = abs_int < gpi ? __ull2double_rn(abs_int) : __longlong_as_double((long long)(0x4340000000000000ull + (abs_int - gpi)));
-  if (neg) f = -f;
+  // The sign goes on as a bit, never as a floating-point negation: the value may be a NaN, the sign of a NaN is not a value the
+  // compiler has to keep through `-f`, and it did not always (negative NaNs came back positive in some builds).
+  uint64_t fb = abs_int < gpi ? (uint64_t)__double_as_longlong(__ull2double_rn(abs_int)) : 0x4340000000000000ull + (abs_int - gpi);
+  if (neg) fb ^= MID;
+  const double f = __longlong_as_double((long long)fb);
   // x86/ARM propagate the operand NaN (quieted, sign and payload kept); NVIDIA GPUs return the canonical NaN.
   // The reference runs on the CPU, so reproduce its bits (base is validated finite, so only f can be NaN).
-  if (f != f) return (uint64_t)__double_as_longlong(f) | 0x0008000000000000ull;
+  if (f != f) return fb | 0x0008000000000000ull;
   return (uint64_t)__double_as_longlong(__dmul_rn(f, __longlong_as_double((long long)base_bits)));
 }
 __device__ __forceinline__ uint32_t float_mult_unadjusted(uint32_t l, uint32_t base_bits) {
   const uint32_t MID = 1u << 31;
-  bool neg = l < MID;
-  uint32_t abs_int = neg ? (MID - 1 - l) : (l - MID);
+  const bool neg = l < MID;
+  const uint32_t abs_int = neg ? (MID - 1 - l) : (l - MID);
   const uint32_t gpi = 1u << 24;
-  float f = abs_int < gpi ? __uint2float_rn(abs_int) : __uint_as_float(0x4b800000u + (abs_int - gpi));
-  if (neg) f = -f;
-  if (f != f) return __float_as_uint(f) | 0x00400000u;  // CPU NaN propagation, see the f64 overload
+  uint32_t fb = abs_int < gpi ? __float_as_uint(__uint2float_rn(abs_int)) : 0x4b800000u + (abs_int - gpi);
+  if (neg) fb ^= MID;  // see the f64 overload
+  const float f = __uint_as_float(fb);
+  if (f != f) return fb | 0x00400000u;  // CPU NaN propagation
   return __float_as_uint(__fmul_rn(f, __uint_as_float(base_bits)));
 }
 __device__ __forceinline__ uint16_t float_mult_unadjusted(uint16_t, uint16_t) { return 0; }  // f16 float_mult: not on the GPU path

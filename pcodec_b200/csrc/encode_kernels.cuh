@@ -1518,7 +1518,7 @@ constexpr int ANS_THREADS = 256;
 constexpr int ANS_SEGS = ANS_THREADS / 4;   // segments per round: one thread per (segment, interleaved chain)
 constexpr int ANS_WARM_BATCHES = 2;         // batches of the preceding segment replayed to form the guess
 constexpr uint32_t ANS_MAX_SEG_BATCHES = 16;
-constexpr uint32_t ANS_TF_MAX = 32;         // largest weight the transfer-function path enumerates
+constexpr uint32_t ANS_TF_MAX = 8;          // largest pivot weight the transfer-function path enumerates (a quiet replay of the segment per slot, ~0.12 ms each)
 constexpr int ANS_TF_LOOK = 4;              // it picks the lightest symbol among a chain's first ANS_TF_LOOK steps of the segment
 
 struct AnsSmem {
@@ -1755,114 +1755,116 @@ __global__ void __launch_bounds__(ANS_THREADS, 4) ans_encode_kernel(EncParams ep
     }
     uint32_t my_out = state;
     __syncthreads();
-    {
-      // The speculation rests on tANS trajectories merging (a symbol of weight w maps all states onto w values).  Tables whose weights are
-      // (nearly) all equal - what equal-count bins of smooth wide-range data give - act on the state's top bits as near-permutations: guesses
-      // are wrong about 3 times in 4 and the corrections never meet the old trajectory, so the fix-up below would re-encode segment after
-      // segment element-wise at the serial encoder's pace (measured: 8.5 ms per launch on C5 int64 order 0).  When more than half of a
-      // round's guesses are wrong the round is solved exactly instead (a third wrong, as on C5 float64 order 0, is still cheaper to fix up).  After a step with a symbol of weight w the state is one of w values
-      // (next_states[cum + slot], slot = (state >> bits) - w), whatever it was before: each (segment, chain) takes the lightest symbol among
-      // its first ANS_TF_LOOK steps as the pivot, replays the rest of the segment quietly once per slot of the pivot (its transfer function,
-      // <= ANS_TF_MAX entries), four threads chain the true inputs through the 64 transfer functions, and every segment is encoded once
-      // more from its true input.  Tables whose lightest early symbol is heavier fall back to one in-order pass by a single group of four lanes.
-      const uint32_t in_chk = (s == 0 || !active) ? my_in : uint32_t(sm.out_state[s - 1][j]);
-      const int wrong = __syncthreads_count(active && s > 0 && in_chk != my_in);
-      const uint32_t n_round = min(n_segs - done, uint32_t(ANS_SEGS));
-      if (uint32_t(wrong) > 2 * n_round) {  // 4 lanes per segment: more than half of the round's (segment, chain) pairs
-        const bool top_full = b_hi >= 1 && b_hi - 1 < nb_full;  // only the round's top segment (s == 0) can hold the page's short batch
-        uint32_t pv = 0, pw = 0xffffu;
-        if (active && s > 0 && top_full) {
-          // the chain's first steps in this segment: elements 252 + j, 248 + j, ... of batch b_hi - 1
-          const uint8_t* rs = symp + uint64_t(b_hi - 1) * BATCH_N;
+    // The speculation rests on tANS trajectories merging (a symbol of weight w maps all states onto w values).  Tables that merge slowly
+    // need other means, chosen by what they cost (times for 128 chunks per launch, r02_t / r02_u):
+    //   fix-up        a wrong segment re-runs from its true input next to the old trajectory until the two meet.  Cheap when they meet
+    //                 soon (C5 float64 order 0: a third of the guesses wrong, ~10 iterations, 1 ms in all); a correction that runs off its
+    //                 segment moves the problem one segment on per iteration (~0.13 ms each, 8.5 ms for a whole page).
+    //   transfer fn   after a step with a symbol of weight w the state is one of w values (next_states[cum + slot], slot =
+    //                 (state >> bits) - w) whatever it was before.  Each (segment, chain) takes the lightest symbol among its first
+    //                 ANS_TF_LOOK steps as the pivot, replays the rest of the segment quietly once per slot (<= ANS_TF_MAX of them, ~0.12 ms
+    //                 per replay), four threads chain the true inputs through the 64 transfer functions, every segment is encoded once
+    //                 more from its true input.  For equal-weight tables (equal-count bins of smooth wide-range data: 3 guesses in 4
+    //                 wrong, corrections never merge).
+    //   in-order      serial_pass above, ~4.3 ms: tables with heavy symbols in long runs (C5 int64 order 0: weights 205 / 50 / 1).
+    // One fix-up iteration always runs.  If more than a quarter of the round's (segment, chain) pairs ran off their segments in it, a
+    // cascade is on its way: transfer functions if every pivot is light enough, else in-order.  Otherwise the fix-up goes on, and if it
+    // has not converged after 24 iterations the same choice.
+    const uint32_t n_round = min(n_segs - done, uint32_t(ANS_SEGS));
+    uint32_t pv = 0, pw = 0xffffu;
+    auto pivots_enumerable = [&]() -> bool {  // CTA-uniform
+      const bool top_full = b_hi >= 1 && b_hi - 1 < nb_full;  // only the round's top segment (s == 0) can hold the page's short batch
+      pv = 0;
+      pw = 0xffffu;
+      if (active && s > 0 && top_full) {
+        // the chain's first steps in this segment: elements 252 + j, 248 + j, ... of batch b_hi - 1
+        const uint8_t* rs = symp + uint64_t(b_hi - 1) * BATCH_N;
 #pragma unroll
-          for (int k = 0; k < ANS_TF_LOOK; k++) {
-            const uint32_t sy = rs[4 * (63 - k) + j];
-            sm.first_desc[s][j][k] = sm.desc_tab[sy];
-            const uint32_t w = uint32_t(plan.syminfo[sy] >> 24) & 0xffff;
-            if (w < pw) { pw = w; pv = uint32_t(k); }
-          }
-          sm.pivot[s][j] = uint8_t(pv);
-          sm.pivot_w[s][j] = uint8_t(min(pw, 255u));
+        for (int k = 0; k < ANS_TF_LOOK; k++) {
+          const uint32_t sy = rs[4 * (63 - k) + j];
+          sm.first_desc[s][j][k] = sm.desc_tab[sy];
+          const uint32_t w = uint32_t(plan.syminfo[sy] >> 24) & 0xffff;
+          if (w < pw) { pw = w; pv = uint32_t(k); }
         }
-        const bool enumerable = !(active && s > 0) || (top_full && pw <= ANS_TF_MAX);
-        if (__syncthreads_and(enumerable ? 1 : 0)) {
-          if (active && s > 0) {
-            const uint8_t* rs = symp + uint64_t(b_hi - 1) * BATCH_N;
-            const uint32_t dp = sm.first_desc[s][j][pv];
-            for (uint32_t idx = 0; idx < pw; idx++) {
-              uint32_t g = (sm.next_states - 1024)[(dp >> 20) + pw + idx];  // the state after the pivot step landed in slot idx
-              for (int m = 62 - int(pv); m >= 0; m--) ans_step_quiet(sm.desc_tab[rs[4 * m + j]], g, sm.next_states);  // rest of the top batch
-              for (uint32_t b = b_hi - 1; b > b_lo; b--) ans_full_batch<true>(sm, symp + uint64_t(b - 1) * BATCH_N, nullptr, j, gmask, g);
-              sm.tf[s][j][idx] = uint16_t(g);
-            }
-          }
-          __syncthreads();
-          if (tid < 4) {  // chain tid: the true input of every segment of the round, in encode order
-            uint32_t st = sm.out_state[0][tid];
-            for (uint32_t s2 = 1; s2 < n_round; s2++) {
-              sm.true_in[s2][tid] = uint16_t(st);
-              const uint32_t pv2 = sm.pivot[s2][tid], pw2 = sm.pivot_w[s2][tid];
-              for (uint32_t k = 0; k < pv2; k++) ans_step_quiet(sm.first_desc[s2][tid][k], st, sm.next_states);
-              const uint32_t bits = ((st + sm.first_desc[s2][tid][pv2]) >> 16) & 0xfu;
-              st = sm.tf[s2][tid][(st >> bits) - pw2];
-            }
-            sm.carry[tid] = uint16_t(st);
-          }
-          __syncthreads();
-          if (active && s > 0) {
-            uint32_t st = sm.true_in[s][j];
-            for (uint32_t b = b_hi; b > b_lo; b--) {
-              const uint32_t bb = b - 1;
-              uint32_t bits = ans_full_batch<false>(sm, symp + uint64_t(bb) * BATCH_N, ansp + uint64_t(bb) * BATCH_N, j, gmask, st);
-              bits += __shfl_xor_sync(gmask, bits, 1);
-              bits += __shfl_xor_sync(gmask, bits, 2);
-              if (j == 0) { sums[bb] = bits; ent[bb].bit_pos = 0; }
-              ent[bb].st[j] = uint16_t(st - size);
-            }
-          }
-          __syncthreads();
-          continue;  // next round (the carry is set)
+        sm.pivot[s][j] = uint8_t(pv);
+        sm.pivot_w[s][j] = uint8_t(min(pw, 255u));
+      }
+      const bool enumerable = !(active && s > 0) || (top_full && pw <= ANS_TF_MAX);
+      return __syncthreads_and(enumerable ? 1 : 0) != 0;
+    };
+    auto transfer_round = [&]() {  // after pivots_enumerable() == true; leaves the round's carry in sm.carry
+      if (active && s > 0) {
+        const uint8_t* rs = symp + uint64_t(b_hi - 1) * BATCH_N;
+        const uint32_t dp = sm.first_desc[s][j][pv];
+        for (uint32_t idx = 0; idx < pw; idx++) {
+          uint32_t g = (sm.next_states - 1024)[(dp >> 20) + pw + idx];  // the state after the pivot step landed in slot idx
+          for (int m = 62 - int(pv); m >= 0; m--) ans_step_quiet(sm.desc_tab[rs[4 * m + j]], g, sm.next_states);  // rest of the top batch
+          for (uint32_t b = b_hi - 1; b > b_lo; b--) ans_full_batch<true>(sm, symp + uint64_t(b - 1) * BATCH_N, nullptr, j, gmask, g);
+          sm.tf[s][j][idx] = uint16_t(g);
         }
-        serial_pass();
-        return;
+      }
+      __syncthreads();
+      if (tid < 4) {  // chain tid: the true input of every segment of the round, in encode order
+        uint32_t st = sm.out_state[0][tid];
+        for (uint32_t s2 = 1; s2 < n_round; s2++) {
+          sm.true_in[s2][tid] = uint16_t(st);
+          const uint32_t pv2 = sm.pivot[s2][tid], pw2 = sm.pivot_w[s2][tid];
+          for (uint32_t k = 0; k < pv2; k++) ans_step_quiet(sm.first_desc[s2][tid][k], st, sm.next_states);
+          const uint32_t bits = ((st + sm.first_desc[s2][tid][pv2]) >> 16) & 0xfu;
+          st = sm.tf[s2][tid][(st >> bits) - pw2];
+        }
+        sm.carry[tid] = uint16_t(st);
+      }
+      __syncthreads();
+      if (active && s > 0) encode_segment(sm.true_in[s][j]);
+      __syncthreads();
+    };
+    bool solved = false;
+    {
+      bool converged = false;
+      for (int iter = 0; iter < 24 && !converged; iter++) {
+        const uint32_t in_true = (s == 0 || !active) ? my_in : uint32_t(sm.out_state[s - 1][j]);
+        bool changed = false;
+        if (in_true != my_in) {
+          // re-run from the true input next to the old trajectory until they meet (element-wise path)
+          uint32_t a = in_true, g = my_in;
+          for (uint32_t b = b_hi; b > b_lo && a != g; b--) {
+            const uint32_t bb = b - 1;
+            const uint32_t cnt = min(uint32_t(BATCH_N), n - bb * BATCH_N);
+            const int steps = cnt > uint32_t(j) ? int((cnt - 1 - j) / 4 + 1) : 0;
+            const uint8_t* rs = symp + uint64_t(bb) * BATCH_N;
+            uint16_t* ro = ansp + uint64_t(bb) * BATCH_N;
+            int delta = 0;
+            int m = steps - 1;
+            for (; m >= 0 && a != g; m--) {
+              const uint32_t d = sm.desc_tab[rs[4 * m + j]];
+              uint32_t o;
+              delta += int(ans_step(d, a, o, sm.next_states));
+              delta -= int(ans_step_quiet(d, g, sm.next_states));
+              ro[4 * m + j] = uint16_t(o);
+            }
+            if (delta != 0) atomicAdd(&sums[bb], uint32_t(delta));
+            if (m < 0 && a != g) ent[bb].st[j] = uint16_t(a - size);  // the batch ended on the corrected trajectory
+          }
+          my_in = in_true;
+          if (a != g) { changed = true; my_out = a; }  // ran off the segment without meeting the old trajectory
+        }
+        __syncthreads();  // every segment has read its predecessor's output
+        if (changed) sm.out_state[s][j] = uint16_t(my_out);
+        const uint32_t n_changed = uint32_t(__syncthreads_count(changed ? 1 : 0));
+        converged = n_changed == 0;
+        if (iter == 0 && n_changed > n_round) break;  // more than a quarter of the 4 n_round pairs (an eighth sent C5 float64 order 0 in-order: 3 ms instead of 1)
+      }
+      if (!converged) {
+        if (!pivots_enumerable()) {
+          serial_pass();
+          return;
+        }
+        transfer_round();
+        solved = true;
       }
     }
-    for (int iter = 0;; iter++) {
-      if (iter == 32) {  // corrections keep running off their segments (a cascade moves one segment per iteration, ~0.13 ms each): the
-                         // in-order pass (~4 ms) is cheaper than the rest of it.  C5 float64 order 0 takes ~10 cheap iterations (1 ms in all).
-        serial_pass();
-        return;
-      }
-      const uint32_t in_true = (s == 0 || !active) ? my_in : uint32_t(sm.out_state[s - 1][j]);
-      bool changed = false;
-      if (in_true != my_in) {
-        // re-run from the true input next to the old trajectory until they meet (rare: element-wise path)
-        uint32_t a = in_true, g = my_in;
-        for (uint32_t b = b_hi; b > b_lo && a != g; b--) {
-          const uint32_t bb = b - 1;
-          const uint32_t cnt = min(uint32_t(BATCH_N), n - bb * BATCH_N);
-          const int steps = cnt > uint32_t(j) ? int((cnt - 1 - j) / 4 + 1) : 0;
-          const uint8_t* rs = symp + uint64_t(bb) * BATCH_N;
-          uint16_t* ro = ansp + uint64_t(bb) * BATCH_N;
-          int delta = 0;
-          int m = steps - 1;
-          for (; m >= 0 && a != g; m--) {
-            const uint32_t d = sm.desc_tab[rs[4 * m + j]];
-            uint32_t o;
-            delta += int(ans_step(d, a, o, sm.next_states));
-            delta -= int(ans_step_quiet(d, g, sm.next_states));
-            ro[4 * m + j] = uint16_t(o);
-          }
-          if (delta != 0) atomicAdd(&sums[bb], uint32_t(delta));
-          if (m < 0 && a != g) ent[bb].st[j] = uint16_t(a - size);  // the batch ended on the corrected trajectory
-        }
-        my_in = in_true;
-        if (a != g) { changed = true; my_out = a; }  // ran off the segment without meeting the old trajectory
-      }
-      __syncthreads();  // every segment has read its predecessor's output
-      if (changed) sm.out_state[s][j] = uint16_t(my_out);
-      if (!__syncthreads_or(changed ? 1 : 0)) break;
-    }
+    if (solved) continue;  // transfer_round left the carry
     if (active && done + uint32_t(s) + 1 == min(n_segs, done + ANS_SEGS)) sm.carry[j] = uint16_t(my_out);  // the round's last segment
     __syncthreads();
   }

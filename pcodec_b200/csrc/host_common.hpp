@@ -125,11 +125,16 @@ inline CallTrace& call_trace() {
 // 268 MB upload running - whole, in 4 MB slices submitted in one go, or throttled to two slices in the queue - another host thread's
 // 48 MB upload waited until the last byte of the big one, 5 ms; the same in the other direction).  Two host threads that stream chunk
 // groups through compress and decompress then wait for each other's big copy in turn and the two PCIe directions never overlap.  So a
-// big copy goes out in 8 MB slices and the host submits a slice only when the previous one has finished: the stream's queue runs empty
-// every 0.15 ms, the engine turns to whoever else is waiting, and the copies of two threads alternate.  Cost: the submit latency of
-// ~10 us per slice when the thread has the link for itself.
+// big copy goes out in 32 MB slices and the host submits a slice only when the previous one has finished: the stream's queue runs empty
+// every 0.6 ms, the engine turns to whoever else is waiting, and the copies of two threads alternate.  Cost: the submit latency of
+// ~10 us per slice when the thread has the link for itself (8 / 16 / 32 MB slices: streamed e2e 72.7 / 67.0 / 66.4 ms, one whole-array
+// call 101.6 / 98.2 / 96.6 ms; without slicing 96-97 ms for both).
 inline cudaError_t copy_sliced(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t stream) {
-  constexpr size_t SLICE = size_t(8) << 20;
+  static const size_t SLICE = [] {  // PCOB200_COPY_SLICE_MB: experiments (0 = whole copies)
+    const char* e = std::getenv("PCOB200_COPY_SLICE_MB");
+    const long mb = e ? std::atol(e) : 32;
+    return mb <= 0 ? ~size_t(0) / 4 : size_t(mb) << 20;
+  }();
   if (bytes <= 2 * SLICE) return cudaMemcpyAsync(dst, src, bytes, kind, stream);
   static thread_local cudaEvent_t ev = nullptr;
   if (!ev) {

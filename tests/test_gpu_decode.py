@@ -277,3 +277,32 @@ def test_decompress_chunks_full_size(sa, oracle):
     data = oracle.simple_compress(nums, oracle.make_config(mode=oracle.MODE_CLASSIC, delta=oracle.DELTA_CONSECUTIVE, delta_order=1))
     offs, ns = _chunk_table(oracle, data, np.uint64)
     assert np.array_equal(sa.decompress_chunks(data, np.uint64, offs, ns), nums)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32, np.float16])
+@pytest.mark.parametrize("order", [0, 1])
+def test_float_mult_nan_signs_and_payloads(sa, oracle, dtype, order):
+    """FloatMult multiplies a NaN primary by the base (mode/float_mult.rs:17-36): the CPU keeps the operand NaN's sign and payload and
+    quiets it; the join has to produce those bits (found by the property test: negative NaNs came back positive)."""
+    from pcodec_b200 import ChunkConfig, DeltaSpec, ModeSpec, PcoError
+
+    dt = np.dtype(dtype)
+    u = {8: np.uint64, 4: np.uint32, 2: np.uint16}[dt.itemsize]
+    ones = int(np.iinfo(u).max)
+    exp_all = {8: 0x7ff0000000000000, 4: 0x7f800000, 2: 0x7c00}[dt.itemsize]
+    sign = 1 << (8 * dt.itemsize - 1)
+    bits = [ones, ones ^ sign, exp_all | 1, exp_all | 1 | sign, exp_all | (exp_all >> 3), 1, 0, sign, 1 | sign, exp_all, exp_all | sign]
+    rng = np.random.default_rng(5)
+    body = (rng.integers(-50, 50, size=300) * 0.5).astype(dt).view(u)
+    nums = np.concatenate([np.array(bits, dtype=u), body, np.array(bits[::-1], dtype=u)]).view(dt)
+    ocfg = oracle.make_config(level=4, mode=oracle.MODE_FLOAT_MULT, float_mult_base=0.5, delta=oracle.DELTA_CONSECUTIVE if order else oracle.DELTA_NOOP, delta_order=order)
+    want = oracle.simple_compress(nums, ocfg)
+    back = sa.simple_decompress(want, dt)
+    np.testing.assert_array_equal(back.view(u), nums.view(u))
+    cfg = ChunkConfig(compression_level=4, mode_spec=ModeSpec.try_float_mult(0.5), delta_spec=DeltaSpec.try_consecutive(order) if order else DeltaSpec.no_op())
+    try:
+        got = sa.simple_compress(nums, cfg)
+    except PcoError as e:  # f16 FloatMult is decoded on the device but not encoded
+        assert dt.itemsize == 2 and e.kind == "Unsupported", e
+    else:
+        assert got == want

@@ -24,6 +24,23 @@ def gpu_configs(draw, dtype):
     return kw
 
 
+def _dump_failure(nums, kw, got, want):
+    """A falsifying example is data: keep it (numbers, config, both files) where the GPU call's scratch directory travels back from."""
+    import hashlib
+    import json
+    import os
+
+    root = os.environ.get("PCOB200_PROP_DUMP") or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(root, exist_ok=True)
+        tag = hashlib.sha1(nums.tobytes() + repr(sorted((k, str(v)) for k, v in kw.items())).encode()).hexdigest()[:12]
+        np.save(os.path.join(root, f"prop_fail_{tag}_{nums.dtype.name}.npy"), nums.view(f"u{nums.dtype.itemsize}"))
+        with open(os.path.join(root, f"prop_fail_{tag}.json"), "w") as f:
+            json.dump({"kw": kw, "dtype": nums.dtype.name, "n": int(nums.size), "got_hex": (got or b"").hex(), "want_hex": want.hex()}, f)
+    except OSError:
+        pass
+
+
 @settings(max_examples=400, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large])
 @given(data=st.data())
 def test_gpu_bytes_equal_the_oracles(oracle, data):
@@ -43,16 +60,22 @@ def test_gpu_bytes_equal_the_oracles(oracle, data):
     try:
         got = p.standalone.simple_compress(nums, cfg)
     except p.PcoError as e:
+        if e.kind != "Unsupported":
+            _dump_failure(nums, dict(kw, error=str(e), where="compress"), None, want)
         assert e.kind == "Unsupported", (kw, e)  # e.g. more than 256 bins at the highest levels
         got = None
-    if got is not None:
+    if got is not None and got != want:
+        _dump_failure(nums, kw, got, want)
         assert got == want, kw
     try:
         back = p.standalone.simple_decompress(want, nums.dtype)
     except p.PcoError as e:
+        if e.kind != "Unsupported":
+            _dump_failure(nums, dict(kw, error=str(e), where="decompress"), None, want)
         assert e.kind == "Unsupported", (kw, e)
         return
     if not np.array_equal(bits_view(back), bits_view(nums)):
+        _dump_failure(nums, dict(kw, where="decode differs"), back.tobytes(), want)
         a, b = bits_view(back), bits_view(nums)
         bad = np.nonzero(a != b)[0] if a.shape == b.shape else np.array([], dtype=int)
         raise AssertionError(f"GPU decode of the oracle's file differs: {kw}, dtype {nums.dtype}, n {nums.size} vs {back.size}, first differing indices {bad[:5].tolist()}, "
