@@ -144,6 +144,13 @@ int pco_b200_profile_last(char *buf, size_t cap);
  * chunk group g + 1 on one thread while group g decompresses on another (both PCIe directions busy).  A worker thread that is
  * about to exit returns its device scratch with pco_b200_thread_release(). */
 void pco_b200_thread_release(void);
+/* Page-locked host buffers in place ("zero copy"): with bit 0 set, pco_b200_compress_ex (explicit Classic configs) reads a HOST `nums`
+ * that is page-locked (cudaHostAlloc / cudaHostRegister, e.g. torch pin_memory) straight over PCIe in its one pass over the input; with
+ * bit 1 set, pco_b200_decompress_ex (side-index path) has the decode kernels store into a page-locked HOST `dst` directly; with bit 2
+ * set, pco_b200_compress_ex has the bit-pack kernel store the file into a page-locked HOST `dst` directly.  No staging
+ * buffer in HBM and no copy-engine transfer for those streams; pageable buffers take the staged path whatever the mask says.  The mask is
+ * process-wide; the call returns the previous one (a negative argument only reads it).  Environment: PCOB200_ZEROCOPY. */
+int pco_b200_zero_copy(int mask);
 /* counts8[k] = chunks of the last decode launch served by decode class k (1, 2: general kernel with 1 / 2 latent vars;
  * 3, 4: narrow kernel, delta order 0 / 1); returns the number of chunks. */
 int pco_b200_profile_chunk_classes(unsigned *counts8);

@@ -28,6 +28,7 @@ struct CompressScratch {
   DevBuf lat0, lat1, keys_a, keys_b, sym0, sym1, ans0, ans1, ob_sum, ans_sum, entries, plans, chunks, starts, seg, out, small, index, probes, sample, sample_starts, key16_0, key16_1, idx_out, lb_vals, lb_resid, lb_scratch;
   // kernel attributes are per instantiation: one flag per latent width (index log2(sizeof(L)))
   bool plan_attr_set[4] = {false, false, false, false}, union_attr_set[4] = {false, false, false, false}, sort_attr_set[4] = {false, false, false, false};
+  bool src_in_place = false;  // this call reads its numbers from the caller's page-locked host buffer (host_common.hpp, zero copy)
   void release() {
     for (DevBuf* b : {&lat0, &lat1, &keys_a, &keys_b, &sym0, &sym1, &ans0, &ans1, &ob_sum, &ans_sum, &entries, &plans, &chunks, &starts, &seg, &out, &small,
                       &index, &probes, &sample, &sample_starts, &key16_0, &key16_1, &idx_out, &lb_vals, &lb_resid, &lb_scratch})
@@ -341,7 +342,7 @@ inline const std::vector<uint32_t>& mode_sample_positions(size_t n) {
 // latent var of that search).  `e` describes the set (its own chunk_starts / row_base, counted from 0); plans and probes land in slots
 // 0 .. e.n_chunks - 1 of the scratch.  T is the latent width the set is planned in (the number's, or u32 for lookback indices).
 template <typename L>
-static PcoB200Error plan_front(CompressScratch& S, cudaStream_t stream, const EncParams& e, uint32_t tiles, size_t slots, uint32_t (&vrb)[MAX_VARS],
+static PcoB200Error plan_front(CompressScratch& S, cudaStream_t stream, EncParams& e, uint32_t tiles, size_t slots, uint32_t (&vrb)[MAX_VARS],
                                const std::vector<uint64_t>& sizes, bool shared, L* (&d_lat)[2]) {
   constexpr int LW = sizeof(L) == 1 ? 0 : sizeof(L) == 2 ? 1 : sizeof(L) == 4 ? 2 : 3;
   constexpr size_t RS_SMEM = size_t(RS_WARPS) * RS_BINS * sizeof(uint32_t);
@@ -416,6 +417,13 @@ static PcoB200Error plan_front(CompressScratch& S, cudaStream_t stream, const En
         return PCO_B200_OK;
       }
       init_chunks_kernel<<<(n_chunks + 255) / 256, 256, 0, stream>>>(d_chunks, n_chunks);
+      if (S.src_in_place) {
+        // the speculation read the numbers in place over PCIe; the two-kernel path would read them again: bring this set into HBM
+        // first (the in-place pointer of a page-locked buffer is also its host address)
+        PCOB_CUDA_TRY(S.index.reserve(size_t(e.n_total) * sizeof(L) + 64));
+        PCOB_CUDA_TRY(copy_sliced(S.index.p, e.nums, size_t(e.n_total) * sizeof(L), cudaMemcpyHostToDevice, stream));
+        e.nums = S.index.p;
+      }
     }
 #endif
     profiler().begin("split_delta_kernel", stream);
@@ -606,12 +614,23 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
   // ---- the numbers in HBM
   const void* d_nums = nums;
   DevBuf& in_stage = S.index;  // a dedicated input staging buffer when nums live on the host (kept apart from the sort buffers)
+  S.src_in_place = false;
   if (!src_dev) {
-    PCOB_CUDA_TRY(in_stage.reserve(n * sizeof(L) + 64));
+    // explicit classic configs read a page-locked input in place (one pass of split_count_kernel over PCIe, no staging); the Auto
+    // searches gather samples from all over the array and the two-latent modes take the two-kernel front end: those stage as before
+    void* in_place = nullptr;
+    if ((zero_copy_mask().load(std::memory_order_relaxed) & 1) && !auto_mode && !auto_delta && explicit_mode.mode == MODE_CLASSIC && !shared_bins)
+      in_place = mapped_host_ptr(nums);
     call_trace().mark("c.begin");
-    PCOB_CUDA_TRY(copy_sliced(in_stage.p, nums, n * sizeof(L), cudaMemcpyHostToDevice, stream));
+    if (in_place) {
+      d_nums = in_place;
+      S.src_in_place = true;
+    } else {
+      PCOB_CUDA_TRY(in_stage.reserve(n * sizeof(L) + 64));
+      PCOB_CUDA_TRY(copy_sliced(in_stage.p, nums, n * sizeof(L), cudaMemcpyHostToDevice, stream));
+      d_nums = in_stage.p;
+    }
     call_trace().mark("c.h2d_submitted");
-    d_nums = in_stage.p;
   }
   // scratch sized for the whole call; every run below (and the Auto searches) indexes it from 0
   std::vector<uint64_t> rows_all(pages.size() + 1, 0);
@@ -634,7 +653,7 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
   // ---- K1+K2 and the planner for one set of chunks (a run of the call's chunks, or the chunks' samples during the Auto delta search).
   // `e` describes the set (its own chunk_starts / row_base, counted from 0); plans and probes land in slots 0 .. e.n_chunks - 1.
   L* d_lat[2] = {nullptr, nullptr};
-  auto front = [&](const EncParams& e, uint32_t tiles, size_t slots, uint32_t (&vrb)[MAX_VARS], const std::vector<uint64_t>& sizes, bool shared) -> PcoB200Error {
+  auto front = [&](EncParams& e, uint32_t tiles, size_t slots, uint32_t (&vrb)[MAX_VARS], const std::vector<uint64_t>& sizes, bool shared) -> PcoB200Error {
     return plan_front<L>(S, stream, e, tiles, slots, vrb, sizes, shared, d_lat);
   };
 
@@ -875,6 +894,15 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
   }
   uint64_t file_off = header.size();  // bytes of the file in front of the next run's first chunk
   uint8_t* d_out = static_cast<uint8_t*>(dst);
+  // a page-locked host destination is written in place by pack_kernel (word stores, every byte once), exactly like a device destination:
+  // no staging, no file-size round trip in front of the pack (host_common.hpp, zero copy)
+  bool dst_direct = dst_dev;
+  if (!dst_dev && (zero_copy_mask().load(std::memory_order_relaxed) & 4)) {
+    if (void* in_place = mapped_host_ptr(dst)) {
+      d_out = static_cast<uint8_t*>(in_place);
+      dst_direct = true;
+    }
+  }
   for (size_t ri = 0; ri < runs.size(); ri++) {
     const Run& run = runs[ri];
     const bool first_run = ri == 0, last_run = ri + 1 == runs.size();
@@ -953,7 +981,7 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
     const uint32_t footer = (last_run && !chunks_only) ? 1u : 0u;
     chunk_offsets_kernel<<<1, 1024, 0, stream>>>(d_chunks, n_chunks, file_off, footer, d_total);
     uint64_t total = 0;
-    const bool need_total_now = !dst_dev || !last_run;  // a host destination is staged (sized from the file size); a later run starts where this one ends
+    const bool need_total_now = !dst_direct || !last_run;  // a host destination is staged (sized from the file size); a later run starts where this one ends
     if (need_total_now) {
       PCOB_CUDA_TRY(cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, stream));
       PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
@@ -961,14 +989,14 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
       call_trace().mark("c.total");
       if (total > dst_cap) return fail(PCO_B200_IO, "failed to write whole buffer (need " + std::to_string(total) + " bytes, dst_cap " + std::to_string(dst_cap) + ")");
     }
-    if (!dst_dev) {
+    if (!dst_direct) {
       PCOB_CUDA_TRY(S.out.reserve(total - (first_run ? 0 : file_off) + 64));
       // the run's bytes are staged at their file offsets relative to the run's first byte (the header belongs to the first run)
       d_out = S.out.as<uint8_t>() - (first_run ? 0 : file_off);
     }
     // device destination: no host round trip for the last run - pack_kernel leaves out any chunk that would not fit dst_cap, and the size
     // is checked when it is read back behind the kernel
-    const uint64_t out_cap = dst_dev ? uint64_t(dst_cap) : total;
+    const uint64_t out_cap = dst_direct ? uint64_t(dst_cap) : total;
     profiler().begin("pack_kernel", stream);
     pack_kernel<L><<<n_chunks, PACK_THREADS, sizeof(PackSmem), stream>>>(ep, bpc, d_lat[0], d_lat[1], d_plans, d_chunks, d_sym[0], d_sym[1], d_ans[0], d_ans[1],
                                                                         S.entries.as<BatchEntry>(), d_out, out_cap,
@@ -980,7 +1008,7 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
       else run_edge_kernel<<<1, 32, 0, stream>>>(d_out, out_cap, d_header, first_run ? uint32_t(header.size()) : 0u, d_total, last_run ? 1u : 0u);
     }
     PCOB_CUDA_TRY(cudaGetLastError());
-    if (!dst_dev) {
+    if (!dst_direct) {
       const uint64_t from = first_run ? 0 : file_off;
       PCOB_CUDA_TRY(copy_sliced(static_cast<uint8_t*>(dst) + from, d_out + from, total - from, cudaMemcpyDeviceToHost, stream));
     }
@@ -999,7 +1027,7 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
                                                       chunks_only ? 0u : 1u, uint32_t(run.c0), starts[run.c0], last_run ? 1u : 0u);
       PCOB_CUDA_TRY(cudaGetLastError());
     }
-    if (!last_run || !dst_dev) {
+    if (!last_run || !dst_direct) {
       // the scratch is reused by the next run, and a host destination must be complete before the call returns
       PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
       PCOB_CUDA_TRY(cudaGetLastError());

@@ -23,7 +23,7 @@ struct Context {
   bool initialized = false;
   bool device_ok = false;
   std::string device_err;
-  DevBuf src, out, index, statuses, misc, dec_syms, dec_offs, dec_narrow, gather, cold;
+  DevBuf src, out, index, statuses, misc, dec_syms, dec_offs, dec_narrow, gather, cold, spec;
   CompressScratch enc;
   Binoms* d_binoms = nullptr;
   int sm_count = 0;
@@ -42,7 +42,7 @@ static Context& ctx() {
 }
 
 static void release_buffers(Context& c) {
-  for (DevBuf* b : {&c.src, &c.out, &c.index, &c.statuses, &c.misc, &c.dec_syms, &c.dec_offs, &c.dec_narrow, &c.gather, &c.cold}) b->release();
+  for (DevBuf* b : {&c.src, &c.out, &c.index, &c.statuses, &c.misc, &c.dec_syms, &c.dec_offs, &c.dec_narrow, &c.gather, &c.cold, &c.spec}) b->release();
   c.enc.release();
   c.gather_err = nullptr;
   c.d_cls = nullptr;
@@ -222,6 +222,129 @@ static PcoB200Error launch_decode(Context& c, const FileParams& fp, const uint8_
   return PCO_B200_OK;
 }
 
+// Index-free decompress, the parallel part (the reference's decompressor walks chunk after chunk, standalone/decompressor.rs:150-215;
+// so did this library's serial walk_kernel<<<1>>>, at one GPU thread's ~0.2 GB/s).  Chunk lengths are not in the file, but the chunks
+// of a file nearly always start with the same 4 bytes - the type byte and count - 1 (docs/format.md:186-192).  So, from the first
+// unread chunk at `*next_byte`:
+//   1. find_chunk_starts_kernel lists every position behind it that carries the same 4 bytes (the real chunk starts of that size
+//      plus, once per ~4 GB of compressed bytes, a coincidence);
+//   2. walk_kernel walks ALL of them at once, one thread each, as if each were a chunk start: index entries, status, end position;
+//   3. the host follows the chain from the first chunk: the chunk at p is real, it ends at e(p), and if e(p) is on the list the chunk
+//      there is real too (a coincidence is never reached: no verified chunk ends on it).  The verified chunks are decoded by the
+//      ordinary kernels, their output offsets being k * n.
+// The loop repeats from where the chain stopped (chunks of another size - typically the file's last one - start a new pattern) and
+// hands over to the serial walker as soon as a round verifies nothing: the terminator, a chunk that does not fit `dst`, a corrupt or
+// truncated chunk and every other special case keep the serial path's semantics and error reporting.
+// `host_src` is the file in host memory (nullptr when it only lives on the device).  PCOB200_SPECULATIVE_WALK=0 turns this off.
+static PcoB200Error speculative_walk_rounds(Context& c, const FileParams& fp, const uint8_t* host_src, void* dst, uint64_t dst_len, bool dst_dev, size_t elem,
+                                            cudaStream_t stream, uint64_t* next_byte, uint64_t* out_off, void** d_out_io) {
+  static const bool enabled = [] { const char* e = std::getenv("PCOB200_SPECULATIVE_WALK"); return !(e && e[0] == '0'); }();
+  if (!enabled) return PCO_B200_OK;
+  constexpr uint32_t CAND_CAP = 1u << 16;                  // candidates listed per round
+  constexpr uint64_t INDEX_BUDGET = uint64_t(768) << 20;   // bytes of index scratch per round
+  for (int round = 0; round < 4096; round++) {
+    const uint64_t pos = *next_byte;
+    if (pos + 4 > fp.src_len) return PCO_B200_OK;
+    uint8_t h4[4];
+    if (host_src) std::memcpy(h4, host_src + pos, 4);
+    else {
+      PCOB_CUDA_TRY(cudaMemcpyAsync(h4, static_cast<const uint8_t*>(fp.src) + pos, 4, cudaMemcpyDeviceToHost, stream));
+      PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
+    }
+    if (h4[0] != fp.dtype) return PCO_B200_OK;  // the terminator (0), or a type byte the serial path will report
+    const uint32_t n0 = (uint32_t(h4[1]) | (uint32_t(h4[2]) << 8) | (uint32_t(h4[3]) << 16)) + 1;
+    if (*out_off + n0 > dst_len) return PCO_B200_OK;  // the serial path owns the too-small-destination semantics
+    const uint32_t pattern = uint32_t(h4[0]) | (uint32_t(h4[1]) << 8) | (uint32_t(h4[2]) << 16) | (uint32_t(h4[3]) << 24);
+    // scratch: count | candidate positions | chunk ends | statuses
+    PCOB_CUDA_TRY(c.spec.reserve(64 + size_t(CAND_CAP) * (8 + 8 + 4)));
+    uint32_t* d_count = c.spec.as<uint32_t>();
+    uint64_t* d_cand = reinterpret_cast<uint64_t*>(c.spec.as<uint8_t>() + 64);
+    uint64_t* d_ends = d_cand + CAND_CAP;
+    uint32_t* d_stat = reinterpret_cast<uint32_t*>(d_ends + CAND_CAP);
+    PCOB_CUDA_TRY(cudaMemsetAsync(d_count, 0, 4, stream));
+    const uint64_t scan_end = fp.src_len - 3;  // last position + 1 whose 4 bytes lie inside the file
+    const uint64_t per_block = uint64_t(FIND_THREADS) * FIND_PER_THREAD;
+    const uint64_t blocks = (scan_end - pos + per_block - 1) / per_block;
+    if (blocks > 0x7fffffffull) return PCO_B200_OK;
+    profiler().begin("find_chunk_starts_kernel", stream);
+    find_chunk_starts_kernel<<<uint32_t(blocks), FIND_THREADS, 0, stream>>>(static_cast<const uint8_t*>(fp.src), pos, scan_end, pattern, d_cand, CAND_CAP, d_count);
+    profiler().end(stream);
+    PCOB_CUDA_TRY(cudaGetLastError());
+    uint32_t count = 0;
+    PCOB_CUDA_TRY(cudaMemcpyAsync(&count, d_count, 4, cudaMemcpyDeviceToHost, stream));
+    PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
+    if (count == 0 || count > CAND_CAP) return PCO_B200_OK;  // a file full of the pattern: not worth speculating on
+    std::vector<uint64_t> cand(count);
+    PCOB_CUDA_TRY(cudaMemcpyAsync(cand.data(), d_cand, size_t(count) * 8, cudaMemcpyDeviceToHost, stream));
+    PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
+    std::sort(cand.begin(), cand.end());
+    if (cand[0] != pos) return PCO_B200_OK;
+    // walk as many candidates (in file order) as the index budget and the destination allow
+    const uint32_t nb0 = n_batches_of(n0);
+    const uint64_t stride = (uint64_t(MAX_VARS) * nb0 * sizeof(BatchEntry) + 15) & ~uint64_t(15);
+    const uint64_t fit = (dst_len - *out_off) / n0;  // chunks of this size the destination can still take (>= 1)
+    uint64_t m64 = std::min<uint64_t>(count, std::max<uint64_t>(1, INDEX_BUDGET / (stride + sizeof(IndexChunk))));
+    m64 = std::min<uint64_t>(m64, fit + 8);  // a few more than fit: coincidences in front of the last chunk needed
+    const uint32_t m = uint32_t(m64);
+    const uint64_t chunks_offset = sizeof(IndexHeader);
+    const uint64_t entries_begin = (chunks_offset + uint64_t(m) * sizeof(IndexChunk) + 15) & ~uint64_t(15);
+    const uint64_t index_bytes = entries_begin + uint64_t(m) * stride;
+    std::vector<IndexChunk> recs(m);
+    for (uint32_t k = 0; k < m; k++) {
+      recs[k].chunk_offset = cand[k];
+      recs[k].n = n0;
+      recs[k].n_vars = 0;
+      recs[k].entries_offset = entries_begin + uint64_t(k) * stride;
+      recs[k].out_offset = 0;
+    }
+    PCOB_CUDA_TRY(c.index.reserve(index_bytes + 64));
+    uint8_t* d_index = c.index.as<uint8_t>();
+    PCOB_CUDA_TRY(cudaMemcpyAsync(d_index + chunks_offset, recs.data(), size_t(m) * sizeof(IndexChunk), cudaMemcpyHostToDevice, stream));
+    PCOB_CUDA_TRY(cudaMemsetAsync(d_stat, 0xff, size_t(m) * 4, stream));
+    PCOB_CUDA_TRY(cudaMemsetAsync(d_ends, 0, size_t(m) * 8, stream));
+    PCOB_CUDA_TRY(c.misc.reserve(sizeof(WalkResult)));
+    profiler().begin("walk_kernel", stream);
+    walk_kernel<SMALL_MAX_SIZE_LOG><<<m, WALK_THREADS, sizeof(WalkSmem<SMALL_MAX_SIZE_LOG>), stream>>>(
+        fp, d_index, chunks_offset, m, 0, index_bytes, 0, 0, ~uint64_t(0), d_stat, c.misc.as<WalkResult>(), 0, d_ends);
+    profiler().end(stream);
+    PCOB_CUDA_TRY(cudaGetLastError());
+    std::vector<uint32_t> st(m);
+    std::vector<uint64_t> ends(m);
+    PCOB_CUDA_TRY(cudaMemcpyAsync(st.data(), d_stat, size_t(m) * 4, cudaMemcpyDeviceToHost, stream));
+    PCOB_CUDA_TRY(cudaMemcpyAsync(ends.data(), d_ends, size_t(m) * 8, cudaMemcpyDeviceToHost, stream));
+    PCOB_CUDA_TRY(cudaMemcpyAsync(recs.data(), d_index + chunks_offset, size_t(m) * sizeof(IndexChunk), cudaMemcpyDeviceToHost, stream));  // n_vars as walked
+    PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
+    // the chain of real chunks
+    std::vector<IndexChunk> real;
+    uint64_t p = pos;
+    for (;;) {
+      const auto it = std::lower_bound(cand.begin(), cand.begin() + m, p);
+      if (it == cand.begin() + m || *it != p) break;
+      const size_t k = size_t(it - cand.begin());
+      if (st[k] != ST_OK || ends[k] <= p || ends[k] > fp.src_len) break;  // the serial walker reports what is wrong with this chunk
+      if (*out_off + (uint64_t(real.size()) + 1) * n0 > dst_len) break;
+      IndexChunk ic = recs[k];
+      ic.out_offset = *out_off + uint64_t(real.size()) * n0;
+      real.push_back(ic);
+      p = ends[k];
+    }
+    if (real.empty()) return PCO_B200_OK;
+    PCOB_CUDA_TRY(cudaMemcpyAsync(d_index + chunks_offset, real.data(), real.size() * sizeof(IndexChunk), cudaMemcpyHostToDevice, stream));
+    const uint64_t emit_end = *out_off + uint64_t(real.size()) * n0;
+    void* d_out = dst;
+    if (!dst_dev) {
+      PCOB_CUDA_TRY(c.out.grow_preserve(emit_end * elem + 64, *out_off * elem, stream));
+      d_out = c.out.p;
+    }
+    if (PcoB200Error e = launch_decode(c, fp, d_index, index_bytes, chunks_offset, uint32_t(real.size()), d_out, dst_dev ? dst_len : emit_end, stream)) return e;
+    *d_out_io = d_out;
+    *out_off = emit_end;
+    *next_byte = p;
+  }
+  return PCO_B200_OK;
+}
+
+
 // The fast kernels behind every decompress entry point.  The walk goes on while the numbers seen fit the destination - an exact fit still
 // has to find the terminator (a truncated file is an error for both of the reference's semantics) - and stops with `terminated = false`
 // and n_total > dst_len at the first chunk that does not fit: pco_standalone_simple_decompress_into turns that into its "exceeds dst_cap"
@@ -288,15 +411,26 @@ static PcoB200Error decompress_fast(const void* compressed, size_t compressed_le
     }
     uint64_t n_emit = std::min<uint64_t>(ih.n_total, dst_len);
     void* d_out = dst;
+    bool dst_in_place = false;
     if (!dst_dev) {
-      PCOB_CUDA_TRY(c.out.reserve(n_emit * elem + 64));
-      d_out = c.out.p;
+      // a page-locked destination is written in place by the decode kernels (every number is stored once, in 32-byte pieces that a
+      // warp lays down as 1 KiB runs): no staging buffer, no copy behind the kernel (host_common.hpp, zero copy)
+      void* in_place = (zero_copy_mask().load(std::memory_order_relaxed) & 2) ? mapped_host_ptr(dst) : nullptr;
+      if (in_place) {
+        d_out = in_place;
+        dst_in_place = true;
+      } else {
+        PCOB_CUDA_TRY(c.out.reserve(n_emit * elem + 64));
+        d_out = c.out.p;
+      }
     }
     if (ih.n_chunks > 0xffffffffull) return fail(PCO_B200_INVALID_ARGUMENT, "too many chunks");
-    // a host destination is staged in c.out, which holds n_emit numbers: that is the kernels' bound, whatever the index claims
+    // a host destination holds (or is staged in c.out, which holds) n_emit numbers: that is the kernels' bound, whatever the index claims
     if (PcoB200Error e = launch_decode(c, fp, d_idx, index_len, ih.chunks_offset, uint32_t(ih.n_chunks), d_out, dst_dev ? uint64_t(dst_len) : n_emit, stream)) return e;
     call_trace().mark("d.decoded");
-    if (!dst_dev && n_emit) {
+    if (dst_in_place) {
+      PCOB_CUDA_TRY(cudaStreamSynchronize(stream));  // launch_decode has read the statuses back already: the stores are in host memory
+    } else if (!dst_dev && n_emit) {
       PCOB_CUDA_TRY(copy_sliced(dst, d_out, n_emit * elem, cudaMemcpyDeviceToHost, stream));
       call_trace().mark("d.d2h_submitted");
       PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
@@ -313,9 +447,13 @@ static PcoB200Error decompress_fast(const void* compressed, size_t compressed_le
   const uint32_t max_chunks = uint32_t(std::min<uint64_t>(uint64_t(compressed_len) / 5 + 2, 1u << 16));
   uint64_t next_byte = hdr.first_chunk_byte;
   uint64_t out_off = 0;
+  void* d_out = dst;
+  // runs of same-sized chunks are found, walked and decoded in parallel; what is left (the terminator at least) goes through the serial walk
+  if (PcoB200Error e = speculative_walk_rounds(c, fp, src_dev ? nullptr : static_cast<const uint8_t*>(compressed), dst, uint64_t(dst_len), dst_dev, elem, stream,
+                                               &next_byte, &out_off, &d_out))
+    return e;
   PCOB_CUDA_TRY(c.misc.reserve(sizeof(WalkResult)));
   WalkResult* d_res = c.misc.as<WalkResult>();
-  void* d_out = dst;
   for (;;) {
     // scratch index: header | IndexChunk[max_chunks] | entries for the batches dst can still take (+2 per chunk) x 2 vars
     const uint64_t chunks_offset = sizeof(IndexHeader);
@@ -767,6 +905,7 @@ PcoB200Error pco_b200_choose_mode(const void* nums, size_t n, unsigned char dtyp
 }
 
 void pco_b200_profile_enable(int on) { profiler_enabled().store(on != 0); }
+int pco_b200_zero_copy(int mask) { return mask < 0 ? zero_copy_mask().load() : zero_copy_mask().exchange(mask & 7); }
 // Frees the calling thread's device scratch (a worker thread calls this before it exits; the buffers are otherwise kept for the
 // thread's next call).
 void pco_b200_thread_release(void) {

@@ -154,6 +154,37 @@ inline cudaError_t copy_sliced(void* dst, const void* src, size_t bytes, cudaMem
   return cudaSuccess;
 }
 
+// ---- in-place access to page-locked host buffers ("zero copy") -------------------------------------------------------------------------
+// A caller's host buffer that is page-locked (cudaHostAlloc / cudaHostRegister: what torch's pin_memory, CuPy's pinned pool and most I/O
+// stacks hand out) is addressable by the SMs through the same pointer under unified addressing.  The two big streams of the path are
+// touched exactly once by exactly one kernel - the numbers by the split kernel of compress, the decoded numbers by the decode kernel of
+// decompress - so those kernels can read / write the host buffer directly over PCIe: no staging buffer in HBM, no copy engine (copies of
+// two host threads queue behind each other on an engine, see copy_sliced below; loads and stores of two kernels share the link word by
+// word), and the transfer overlaps the kernel's own work.  Bit 0: compress reads its input in place; bit 1: decompress writes its output
+// in place.  Pageable buffers (cudaMemoryTypeUnregistered) always take the staged path.  PCOB200_ZEROCOPY overrides the default mask.
+#ifndef PCOB_ZEROCOPY_DEFAULT
+#define PCOB_ZEROCOPY_DEFAULT 0
+#endif
+inline std::atomic<int>& zero_copy_mask() {
+  static std::atomic<int> m{[] {
+    const char* e = std::getenv("PCOB200_ZEROCOPY");
+    return e ? std::atoi(e) : PCOB_ZEROCOPY_DEFAULT;
+  }()};
+  return m;
+}
+// the device alias of a page-locked host buffer, or nullptr when the buffer is pageable / not addressable from the current device
+inline void* mapped_host_ptr(const void* host) {
+  if (!host) return nullptr;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, host) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  if (a.type != cudaMemoryTypeHost || a.devicePointer == nullptr) return nullptr;
+  // the staging fallback of compress copies from the same pointer, so insist on the unified-addressing identity
+  return a.devicePointer == host ? a.devicePointer : nullptr;
+}
+
 // ---- grow-only device buffer -----------------------------------------------
 struct DevBuf {
   void* p = nullptr;

@@ -12,7 +12,7 @@ lib = sys.argv[1] if len(sys.argv) > 1 else "pcodec_b200/libcpcodec.so"
 out = sys.argv[2] if len(sys.argv) > 2 else "gpurun_out/sass_summary.md"
 flt = re.compile(sys.argv[3]) if len(sys.argv) > 3 else None
 
-MNEMONICS = ["LDGSTS", "STG.E.ENL2.256", "STG.E.128", "STG.E.64", "LDG.E.128", "LDG.E.64", "LDS", "STS", "ATOMS", "REDUX", "SHFL", "SHF", "LOP3", "BAR", "LDL", "STL", "UTMALDG", "SYNCS"]
+MNEMONICS = ["LDGSTS", "STG.E.ENL2.256", "STG.E.128", "STG.E.64", "LDG.E.128", "LDG.E.64", "LDS", "STS", "ATOMS", "REDUX", "SHFL", "SHF", "LOP3", "BAR", "LDL", "STL", "UTMALDG", "UBLKCP", "SYNCS"]
 
 
 def demangle(names):
