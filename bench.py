@@ -6,8 +6,10 @@ chunks of 2^18 u64 (BASELINE config 2: classic mode, consecutive delta order 1; 
 scaling (8 ranks = config 4's 8192 chunks).  MB = 10^6 uncompressed bytes (pco_cli/src/bench/mod.rs:233-241).
 
   value     resident: inputs already in HBM, device buffers in and out, through the C-ABI (*_ex, flags DEVICE).
-  e2e       same calls with pinned HOST buffers (H2D of the inputs and D2H of the results inside the timed region).
-  roofline  decompress kernels (symwalk_kernel + the decode kernels, decode_narrow_kernel on this data): (U + C + side index) bytes / their CUDA-event durations vs MEASURED_PEAKS.json hbm_gbs.
+  e2e       same calls with pinned HOST buffers (H2D of the inputs and D2H of the results inside the timed region), streamed in chunk groups by
+            2 + 2 host threads; e2e.single_call = one call pair over the whole array; e2e.reference_abi = the reference's 3-function ABI as is.
+  roofline  fused_narrow_kernel (the decompress kernel on this data): (U + C) bytes / its CUDA-event duration vs MEASURED_PEAKS.json hbm_gbs;
+            roofline.call / roofline.compress = the same bytes over the whole decompress / compress call.
   cpu_baseline / --impl reference: oracle/ (C++ restatement of pco 1.0.3; the Rust reference cannot be built here)
             on the host cores - one worker process per host thread - on a bounded sample of the same chunks.
 """
@@ -39,7 +41,7 @@ def parse_args():
     ap.add_argument("--chunks", type=int, default=N_CHUNKS, help="chunks per rank (default: BASELINE config 2)")
     ap.add_argument("--cpu-sample-chunks", type=int, default=1024, help="chunks of the CPU arm per step, spread over one worker process per host thread (about 12 s of core time)")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--abi3-chunks", type=int, default=32, help="chunks of the three-function-ABI leg (its index-free decompress walks the chunks one after the other)")
+    ap.add_argument("--abi3-chunks", type=int, default=256, help="chunks of the three-function-ABI leg (no side index, no chunk offsets: the decompressor finds the chunks by speculation, host_api.cu speculative_walk_rounds)")
     ap.add_argument("--e2e-groups", type=int, default=16, help="chunk groups the streamed e2e leg cuts the array into")
     ap.add_argument("--e2e-threads", type=int, default=2, help="host threads per direction in the streamed e2e leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -662,7 +664,8 @@ def run_gpu_arm(args, rank, world):
         e2e = {"value": world * U / 1e6 / (e2e_ms / 1e3), "unit": "MB/s", "h2d_bytes_per_step": int(U + cg + ig),
                "d2h_bytes_per_step": int(cg + ig + U), "ms_per_step": e2e_ms, "steps": max(1, args.steps),
                "api": f"pco_b200_compress_ex + pco_b200_decompress_ex (C-ABI), pinned host buffers, streamed in {G} groups of chunks by {P} + {P} host threads: "
-                      "compress of later groups runs beside decompress of earlier ones (per-thread library contexts, one stream each; every group is a standalone file)",
+                      "compress of later groups runs beside decompress of earlier ones (per-thread library contexts, one stream each; every group is a standalone file; "
+                      "big copies of one direction take turns, 32 MB slices)",
                "trace_ms": e2e_trace, "pass_wall_ms": streamed_wall,
                "single_call": {"value": world * U / 1e6 / (single_ms / 1e3), "ms_per_step": single_ms,
                                "api": "one pco_b200_compress_ex + one pco_b200_decompress_ex over the whole array (H2D, kernels, D2H back to back)"}}
@@ -770,10 +773,9 @@ def run_gpu_arm(args, rank, world):
         "parity": parity,
         "index_free_decompress": ({**chunks_free, "roofline": {**chunks_free["roofline"], "peak": peak, "frac": chunks_free["roofline"]["achieved"] / peak}} if chunks_free else None),
         "cpu_baseline": cpu, "e2e": ({**e2e, "reference_abi": abi3} if e2e else e2e), "clocks": sampler.summary(),
-        # per step (profiles/r01_l_launches.csv): compress = init_chunks, split_count, plan_solve, fallback, bin_lut, ans_encode,
-        # layout, chunk_offsets, pack, header_footer, emit_index; decompress = symwalk_kernel + decode_narrow_kernel +
-        # decode_kernel<L,1> + decode_kernel<L,2> (a chunk is decoded by exactly one of the three; the others' CTAs exit at once)
-        "gpu_launches": 15,
+        # per step (profiles/r02_zz_launches.csv): compress = init_chunks, split_count, publish (flags readback), plan_solve, fallback, bin_lut,
+        # ans_encode, layout, chunk_offsets, pack, header_footer, emit_index; decompress = fused_narrow_kernel + publish (statuses readback)
+        "gpu_launches": 14,
     }
     print(json.dumps(line))
     if args.results_csv:

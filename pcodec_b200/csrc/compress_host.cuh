@@ -386,8 +386,7 @@ static PcoB200Error plan_front(CompressScratch& S, cudaStream_t stream, EncParam
       profiler().end(stream);
       PCOB_CUDA_TRY(cudaGetLastError());  // a failed launch must not read as "no chunk raised a flag"
       uint32_t fl[2] = {0, 0};
-      PCOB_CUDA_TRY(cudaMemcpyAsync(fl, d_small, 8, cudaMemcpyDeviceToHost, stream));
-      PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
+      PCOB_CUDA_TRY(readback_small_sync(fl, d_small, 8, stream));
       call_trace().mark("c.flags");
       if (fl[1] == 0 && shared) {
         // pages of one chunk: one histogram over all of them, one plan, copied to every page's slot
@@ -983,8 +982,7 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
     uint64_t total = 0;
     const bool need_total_now = !dst_direct || !last_run;  // a host destination is staged (sized from the file size); a later run starts where this one ends
     if (need_total_now) {
-      PCOB_CUDA_TRY(cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, stream));
-      PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
+      PCOB_CUDA_TRY(readback_small_sync(&total, d_total, 8, stream));
       PCOB_CUDA_TRY(cudaGetLastError());
       call_trace().mark("c.total");
       if (total > dst_cap) return fail(PCO_B200_IO, "failed to write whole buffer (need " + std::to_string(total) + " bytes, dst_cap " + std::to_string(dst_cap) + ")");

@@ -173,8 +173,7 @@ static PcoB200Error launch_decode(Context& c, const FileParams& fp, const uint8_
     profiler().end(stream);
     PCOB_CUDA_TRY(cudaGetLastError());
     // statuses and class bytes come back in one round trip; the general kernels only run if some chunk still needs them
-    PCOB_CUDA_TRY(cudaMemcpyAsync(c.pinned_res, d_st, res_bytes, cudaMemcpyDeviceToHost, stream));
-    PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
+    PCOB_CUDA_TRY(readback_small_sync(c.pinned_res, d_st, (res_bytes + 3) & ~size_t(3), stream));  // the buffers hold res_bytes + 64
     const uint8_t* cls = reinterpret_cast<const uint8_t*>(st + n_chunks);
     c.host_cls.assign(cls, cls + n_chunks);
     bool pending = false;
@@ -215,8 +214,7 @@ static PcoB200Error launch_decode(Context& c, const FileParams& fp, const uint8_
   });
   profiler().end(stream);
   PCOB_CUDA_TRY(cudaGetLastError());
-  PCOB_CUDA_TRY(cudaMemcpyAsync(c.pinned_res, d_st, size_t(n_chunks) * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-  PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
+  PCOB_CUDA_TRY(readback_small_sync(c.pinned_res, d_st, size_t(n_chunks) * sizeof(uint32_t), stream));
   for (uint32_t i = 0; i < n_chunks; i++)
     if (st[i] != ST_OK) return status_to_error(st[i], ("chunk " + std::to_string(i)).c_str());
   return PCO_B200_OK;
@@ -238,8 +236,10 @@ static PcoB200Error launch_decode(Context& c, const FileParams& fp, const uint8_
 // `host_src` is the file in host memory (nullptr when it only lives on the device).  PCOB200_SPECULATIVE_WALK=0 turns this off.
 static PcoB200Error speculative_walk_rounds(Context& c, const FileParams& fp, const uint8_t* host_src, void* dst, uint64_t dst_len, bool dst_dev, size_t elem,
                                             cudaStream_t stream, uint64_t* next_byte, uint64_t* out_off, void** d_out_io) {
-  static const bool enabled = [] { const char* e = std::getenv("PCOB200_SPECULATIVE_WALK"); return !(e && e[0] == '0'); }();
-  if (!enabled) return PCO_B200_OK;
+  {  // read per call: tests of the serial walk switch it off in-process
+    const char* e = std::getenv("PCOB200_SPECULATIVE_WALK");
+    if (e && e[0] == '0') return PCO_B200_OK;
+  }
   constexpr uint32_t CAND_CAP = 1u << 16;                  // candidates listed per round
   constexpr uint64_t INDEX_BUDGET = uint64_t(768) << 20;   // bytes of index scratch per round
   for (int round = 0; round < 4096; round++) {
@@ -911,6 +911,7 @@ int pco_b200_zero_copy(int mask) { return mask < 0 ? zero_copy_mask().load() : z
 void pco_b200_thread_release(void) {
   Context& c = ctx();
   if (c.initialized && c.device_ok) release_buffers(c);
+  readback_bounce().release();
 }
 // Which decode instantiation served the chunks of the last decode launch: counts[k] = chunks of class k
 // (1, 2: decode_kernel<L, 1 / 2>; 3, 4: decode_narrow_kernel order 0 / 1).  Returns the number of chunks.

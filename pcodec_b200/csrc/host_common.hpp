@@ -129,11 +129,28 @@ inline CallTrace& call_trace() {
 // every 0.6 ms, the engine turns to whoever else is waiting, and the copies of two threads alternate.  Cost: the submit latency of
 // ~10 us per slice when the thread has the link for itself (8 / 16 / 32 MB slices: streamed e2e 72.7 / 67.0 / 66.4 ms, one whole-array
 // call 101.6 / 98.2 / 96.6 ms; without slicing 96-97 ms for both).
+// Big copies of one direction take turns (r02_w: bench.py e2e trace): two host threads that each stream chunk groups through compress
+// start their uploads together, share the link slice by slice, finish together - and then both run their kernels and their small
+// downloads while the upload direction idles (2.5 ms of every 8.4 ms epoch), in lockstep for the rest of the array.  A process-wide turn
+// per direction makes the second thread's big upload wait for the first one's: the threads fall out of step, one uploads while the
+// other computes, and the link stays busy.  Small copies (a group's compressed bytes, at most two slices) do not take a turn: they slip
+// in between two slices of whoever holds it.  PCOB200_COPY_FIFO=0 restores plain slice-by-slice sharing.
+#ifndef PCOB_COPY_FIFO_DEFAULT
+#define PCOB_COPY_FIFO_DEFAULT 1
+#endif
+inline std::mutex& big_copy_turn(cudaMemcpyKind kind) {
+  static std::mutex turn[2];
+  return turn[kind == cudaMemcpyDeviceToHost ? 1 : 0];
+}
 inline cudaError_t copy_sliced(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t stream) {
   static const size_t SLICE = [] {  // PCOB200_COPY_SLICE_MB: experiments (0 = whole copies)
     const char* e = std::getenv("PCOB200_COPY_SLICE_MB");
     const long mb = e ? std::atol(e) : 32;
     return mb <= 0 ? ~size_t(0) / 4 : size_t(mb) << 20;
+  }();
+  static const bool FIFO = [] {
+    const char* e = std::getenv("PCOB200_COPY_FIFO");
+    return e ? e[0] != '0' : PCOB_COPY_FIFO_DEFAULT != 0;
   }();
   if (bytes <= 2 * SLICE) return cudaMemcpyAsync(dst, src, bytes, kind, stream);
   static thread_local cudaEvent_t ev = nullptr;
@@ -141,6 +158,8 @@ inline cudaError_t copy_sliced(void* dst, const void* src, size_t bytes, cudaMem
     cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     if (e != cudaSuccess) return e;
   }
+  std::unique_lock<std::mutex> turn(big_copy_turn(kind), std::defer_lock);
+  if (FIFO && (kind == cudaMemcpyHostToDevice || kind == cudaMemcpyDeviceToHost)) turn.lock();  // released when the last slice has been submitted
   for (size_t off = 0; off < bytes; off += SLICE) {
     if (off) {
       cudaError_t e = cudaEventSynchronize(ev);  // the previous slice is done
@@ -152,6 +171,62 @@ inline cudaError_t copy_sliced(void* dst, const void* src, size_t bytes, cudaMem
     if (e != cudaSuccess) return e;
   }
   return cudaSuccess;
+}
+
+// ---- small device -> host readbacks that do not queue on a copy engine --------------------------------------------------------------
+// A call reads a few words back between its kernels (the one-pass front end's flags, the file size, the decode statuses) and waits for
+// them.  As a cudaMemcpyAsync such a readback is an entry in the device-to-host copy queue - behind whatever 32 MB slice another host
+// thread's download has in flight there, up to 0.6 ms each time (r02_y phase trace of the streamed e2e leg: 1.1-1.75 ms from the last
+// upload slice to the flags of a 64-chunk group, for 0.1 ms of kernels).  publish_kernel stores the words into a page-locked, device-
+// mapped bounce buffer of the calling thread instead: an ordinary kernel on the call's stream, nothing in any copy queue; the stream
+// synchronisation that follows makes the stores visible to the host.  Readbacks beyond the bounce buffer, and PCOB200_READBACK_KERNEL=0,
+// take the copy.
+__global__ void publish_kernel(uint32_t* __restrict__ dst_mapped, const uint32_t* __restrict__ src, uint32_t n_words) {
+  for (uint32_t i = threadIdx.x; i < n_words; i += blockDim.x) dst_mapped[i] = src[i];
+}
+struct ReadbackBounce {
+  void* host = nullptr;
+  void* dev = nullptr;
+  int device = -1;
+  static constexpr size_t CAP = 64 << 10;
+  void release() {
+    if (host) cudaFreeHost(host);
+    host = dev = nullptr;
+    device = -1;
+  }
+};
+inline ReadbackBounce& readback_bounce() {
+  static thread_local ReadbackBounce b;
+  return b;
+}
+// Copies `bytes` (a multiple of 4, 4-byte aligned source) from device memory to `host_dst` and returns with the stream synchronised.
+inline cudaError_t readback_small_sync(void* host_dst, const void* dev_src, size_t bytes, cudaStream_t stream) {
+  static const bool use_kernel = [] { const char* e = std::getenv("PCOB200_READBACK_KERNEL"); return !(e && e[0] == '0'); }();
+  ReadbackBounce& b = readback_bounce();
+  bool ok = use_kernel && bytes <= ReadbackBounce::CAP && (bytes & 3) == 0 && (reinterpret_cast<uintptr_t>(dev_src) & 3) == 0;
+  if (ok) {
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) ok = false;
+    if (ok && b.host && b.device != dev) b.release();
+    if (ok && !b.host) {
+      if (cudaHostAlloc(&b.host, ReadbackBounce::CAP, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess || cudaHostGetDevicePointer(&b.dev, b.host, 0) != cudaSuccess) {
+        cudaGetLastError();
+        b.release();
+        ok = false;
+      } else {
+        b.device = dev;
+      }
+    }
+  }
+  if (!ok) {
+    cudaError_t e = cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, stream);
+    return e != cudaSuccess ? e : cudaStreamSynchronize(stream);
+  }
+  if (bytes) publish_kernel<<<1, 256, 0, stream>>>(static_cast<uint32_t*>(b.dev), static_cast<const uint32_t*>(dev_src), uint32_t(bytes / 4));
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  if (e == cudaSuccess && bytes) std::memcpy(host_dst, b.host, bytes);
+  return e;
 }
 
 // ---- in-place access to page-locked host buffers ("zero copy") -------------------------------------------------------------------------

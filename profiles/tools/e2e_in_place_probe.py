@@ -1,6 +1,7 @@
 """e2e (pinned host buffers in, pinned host buffers out) of BASELINE config 2 for every in-place mask of pco_b200_zero_copy, as one
 whole-array call pair and streamed in chunk groups by P + P host threads - the same two C-ABI calls bench.py's e2e leg makes.
-Usage: python profiles/tools/e2e_in_place_probe.py [chunks]      (prints one line per variant; host wall clock around synchronous calls)"""
+Usage: python profiles/tools/e2e_in_place_probe.py [chunks] [masks, e.g. 0,1,2,3,7] [variants GxP, e.g. 16x2,32x3]      (prints one line per variant; host wall clock around
+synchronous calls; PCOB200_COPY_FIFO / PCOB200_COPY_SLICE_MB select the library's copy policy for the whole process)"""
 import ctypes as C
 import os
 import queue
@@ -147,8 +148,12 @@ def timed(fn, reps=3):
     return ts
 
 
-variants = [(16, 2), (32, 2), (16, 3), (32, 3), (8, 1)]
-for mask in (0, 1, 2, 3, 7):
+variants = [(16, 2), (32, 2), (16, 3), (32, 3), (8, 1), (16, 1), (64, 2)]
+if len(sys.argv) > 3:  # e.g. 16x2,32x3
+    variants = [tuple(int(v) for v in t.split('x')) for t in sys.argv[3].split(',')]
+MASKS = [int(x) for x in sys.argv[2].split(',')] if len(sys.argv) > 2 else [0, 1, 2, 3, 7]
+print('copy policy: FIFO', os.environ.get('PCOB200_COPY_FIFO', 'default'), 'slice MB', os.environ.get('PCOB200_COPY_SLICE_MB', 'default'), flush=True)
+for mask in MASKS:
     L.pco_b200_zero_copy(C.c_int(mask))
     h_out.zero_()
     single()
@@ -162,6 +167,7 @@ for mask in (0, 1, 2, 3, 7):
         fn()
         ok = torch.equal(h_out, h_nums)
         fn()
+        print(f'=== timed passes G={G} P={P} mask {mask}', file=sys.stderr, flush=True)
         ts = timed(fn)
         print(f"mask {mask} streamed G={G} P={P}: {min(ts):.1f} ms (all {[round(t, 1) for t in ts]}) = {U / 1e6 / min(ts):.1f} GB/s, exact {ok}", flush=True)
 L.pco_b200_zero_copy(C.c_int(0))

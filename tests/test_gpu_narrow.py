@@ -73,7 +73,10 @@ def test_narrow_chunks_vs_oracle(sa, oracle, dtype, order, n):
 
 @pytest.mark.parametrize("dtype", [np.uint64, np.int32, np.float64])
 @pytest.mark.parametrize("order", [0, 1])
-def test_narrow_kernel_is_the_one_that_runs(sa, oracle, dtype, order):
+def test_narrow_kernel_is_the_one_that_runs(sa, oracle, dtype, order, monkeypatch):
+    # the class counters describe the LAST decode launch: the speculative walk decodes runs of same-sized chunks launch by launch (five
+    # chunks of 7033 numbers, then two of 7032), the serial walk hands all seven chunks over at once
+    monkeypatch.setenv("PCOB200_SPECULATIVE_WALK", "0")
     nums = _narrow_data(dtype, 6 * 8192 + 77, 1, order)
     data = oracle.simple_compress(nums, _cfg(oracle, order, max_page_n=8192))
     got = sa.simple_decompress(data, dtype)

@@ -152,3 +152,14 @@ def test_many_chunks_in_one_call():
     x = np.cumsum(rng.geometric(0.02, size=n)).astype(np.uint32)
     data = oracle.simple_compress(x, oracle.make_config(mode=oracle.MODE_CLASSIC, delta=oracle.DELTA_CONSECUTIVE, delta_order=1, max_page_n=256))
     assert np.array_equal(_abi3_decompress(data, np.uint32, n), x)
+
+
+def test_the_serial_walk_alone_gives_the_same_numbers(monkeypatch):
+    """PCOB200_SPECULATIVE_WALK=0: chunk after chunk, as before - the path that still owns the tail of every file and every error"""
+    monkeypatch.setenv("PCOB200_SPECULATIVE_WALK", "0")
+    x, data = _planted_file()
+    assert np.array_equal(standalone.simple_decompress(data, np.uint64), x)
+    rng = np.random.default_rng(11)
+    y = np.cumsum(rng.geometric(0.01, size=5 * 2048 + 3)).astype(np.uint64)
+    ydata = oracle.simple_compress(y, oracle.make_config(mode=oracle.MODE_CLASSIC, delta=oracle.DELTA_CONSECUTIVE, delta_order=1, max_page_n=2048))
+    assert np.array_equal(_abi3_decompress(ydata, np.uint64, y.size), y)
