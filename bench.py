@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument("--no-index-free", action="store_true", help="skip the pco_b200_decompress_chunks timing (not part of `value`)")
     ap.add_argument("--results-csv", default=None, help="also merge this run into a CSV with the reference bench tool's schema and codec naming (pcodec_b200/benchfmt.py)")
     ap.add_argument("--no-gather-pages", action="store_true", help="N > 1: exchange only the per-chunk sizes; the default also gathers the compressed pages on the device (every rank ends up with the whole file)")
-    ap.add_argument("--gather-ctas", type=int, default=24, help="CTAs of the page-gather copy kernel (it runs beside the next step's kernels)")
+    ap.add_argument("--gather-ctas", type=int, default=0, help="CTAs of the page-gather copy kernel (it runs beside the next step's kernels on a high-priority stream); 0 = 16 per rank of the job, at most 64 (profiles/r02_zz3_gather_sweep.txt)")
     return ap.parse_args()
 
 
@@ -324,7 +324,9 @@ def run_gpu_arm(args, rank, world):
     # --no-gather-pages: only the per-rank compressed sizes are exchanged (a sharded writer's file offsets), pages stay sharded.
     push_done = [None, None]
     gather_events = []
-    side = torch.cuda.Stream(device=dev) if world > 1 else None
+    # the gather's few CTAs must not queue behind the 1024-CTA grids of the step it overlaps: high priority
+    side = torch.cuda.Stream(device=dev, priority=-1) if world > 1 else None
+    gather_ctas = args.gather_ctas if args.gather_ctas > 0 else min(16 * world, 64)
     pg = None
     sizes_dev = all_sizes_dev = file_len_dev = None
     first_chunk_off = [0]
@@ -352,7 +354,7 @@ def run_gpu_arm(args, rank, world):
                 pg.chunk_sizes(d_index.data_ptr(), ilen.value, sizes_dev.data_ptr(), n_chunks, side.cuda_stream)
                 dist.all_gather_into_tensor(all_sizes_dev, sizes_dev)
                 pg.gather(d_comp.data_ptr() + first_chunk_off[0], all_sizes_dev.data_ptr(), n_chunks, world * n, file_len_dev.data_ptr(), side.cuda_stream,
-                          max_ctas=args.gather_ctas)
+                          max_ctas=gather_ctas)
                 g1.record(side)
                 push_done[k % n_bufs] = g1
                 gather_events.append((g0, g1))
@@ -432,13 +434,15 @@ def run_gpu_arm(args, rank, world):
     sampler = ClockSampler(local_rank)
     if rank == 0:  # only rank 0's samples go into the line; N nvidia-smi pollers would only add host noise
         sampler.start()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     t_c, t_d, t_g, prof_c, prof_d = [], [], [], [], []
     gather_events.clear()
     barrier()
     ev_all0, ev_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev_all0.record(stream)
-    for _ in range(args.steps):
+    for ev in evs:
+        # no device-wide synchronisation inside the timed region: the page gather of step k (side stream) runs beside decompress(k) AND
+        # compress(k + 1); the library calls synchronise their own stream, the per-step spans are read after the closing barrier
         ev[0].record(stream)
         compress_resident()
         ev[1].record(stream)
@@ -448,12 +452,14 @@ def run_gpu_arm(args, rank, world):
         decompress_resident()
         ev[3].record(stream)
         prof_d.append(parse_profile(L))
-        torch.cuda.synchronize()
+    if side is not None:
+        stream.wait_stream(side)  # the last step's gather belongs to the timed region
+    ev_all1.record(stream)
+    barrier()
+    for ev in evs:
         t_c.append(ev[0].elapsed_time(ev[1]))
         t_g.append(ev[1].elapsed_time(ev[2]))
         t_d.append(ev[2].elapsed_time(ev[3]))
-    ev_all1.record(stream)
-    barrier()
     total_ms = ev_all0.elapsed_time(ev_all1)
     if world > 1:
         import torch.distributed as dist
@@ -464,7 +470,8 @@ def run_gpu_arm(args, rank, world):
     ms_per_step = total_ms / max(args.steps, 1)
     if gather_on and gather_info is not None:
         gather_info["device_ms"] = float(np.mean([a.elapsed_time(b) for a, b in gather_events])) if gather_events else None
-        gather_info["what"] = "sizes all-gather + scan + copy kernel on the side stream (overlaps decompress of the same step and compress of the next)"
+        gather_info["ctas"] = gather_ctas
+        gather_info["what"] = "sizes all-gather + scan + copy kernel on a high-priority side stream (overlaps decompress of the same step and compress of the next)"
     value = world * U / 1e6 / (ms_per_step / 1e3)
 
     # ---- the index-free path (not part of `value`): the same chunks decoded from their byte offsets alone

@@ -91,8 +91,11 @@ __global__ void __launch_bounds__(1024) gather_offsets_kernel(const uint64_t* __
 // `n` bytes from src to dst by one CTA, any alignment on either side.  dst is written in aligned 16-byte stores (the unit NVLink moves
 // well); each is assembled from two ALIGNED 16-byte loads of the source (the second one is the next thread's first: an L1 hit) with a
 // word select and a funnel shift.  A thread keeps GATHER_UNROLL units in flight - the loop is bound by the latency of its loads, the
-// stores are posted - which is what lets a few CTAs fill the links (one unit per thread and iteration: 7 GB/s per CTA, measured).
-constexpr int GATHER_UNROLL = 4;
+// stores are posted - which is what lets a few CTAs fill the links (one unit per thread and iteration: 7 GB/s per CTA, four: ~13 GB/s, measured).
+#ifndef PCOB_GATHER_UNROLL
+#define PCOB_GATHER_UNROLL 8
+#endif
+constexpr int GATHER_UNROLL = PCOB_GATHER_UNROLL;
 
 __device__ __forceinline__ uint4 ld16(const uint4* p) {
   uint32_t x, y, z, w;
