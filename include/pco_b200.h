@@ -151,6 +151,11 @@ void pco_b200_thread_release(void);
  * buffer in HBM and no copy-engine transfer for those streams; pageable buffers take the staged path whatever the mask says.  The mask is
  * process-wide; the call returns the previous one (a negative argument only reads it).  Environment: PCOB200_ZEROCOPY. */
 int pco_b200_zero_copy(int mask);
+/* Host logic of the index-free decompressor, exposed for tests (needs no device): among `m` sorted candidate chunk starts with the
+ * status and end position a speculative walk gave each, follow the chain of real chunks from `pos` (a chunk is real when a verified
+ * chunk ends on it).  Returns how many were verified; their candidate indices in `verified[0..]`, the position behind the last in *next_pos. */
+size_t pco_b200_debug_follow_chain(const uint64_t *cand, const uint32_t *statuses, const uint64_t *ends, uint32_t m, uint64_t pos, uint64_t n0,
+                                   uint64_t out_off, uint64_t dst_len, uint64_t src_len, uint32_t *verified, uint64_t *next_pos);
 /* counts8[k] = chunks of the last decode launch served by decode class k (1, 2: general kernel with 1 / 2 latent vars;
  * 3, 4: narrow kernel, delta order 0 / 1); returns the number of chunks. */
 int pco_b200_profile_chunk_classes(unsigned *counts8);

@@ -315,18 +315,14 @@ static PcoB200Error speculative_walk_rounds(Context& c, const FileParams& fp, co
     PCOB_CUDA_TRY(cudaMemcpyAsync(recs.data(), d_index + chunks_offset, size_t(m) * sizeof(IndexChunk), cudaMemcpyDeviceToHost, stream));  // n_vars as walked
     PCOB_CUDA_TRY(cudaStreamSynchronize(stream));
     // the chain of real chunks
-    std::vector<IndexChunk> real;
     uint64_t p = pos;
-    for (;;) {
-      const auto it = std::lower_bound(cand.begin(), cand.begin() + m, p);
-      if (it == cand.begin() + m || *it != p) break;
-      const size_t k = size_t(it - cand.begin());
-      if (st[k] != ST_OK || ends[k] <= p || ends[k] > fp.src_len) break;  // the serial walker reports what is wrong with this chunk
-      if (*out_off + (uint64_t(real.size()) + 1) * n0 > dst_len) break;
+    const std::vector<uint32_t> chain = follow_chunk_chain(cand.data(), st.data(), ends.data(), m, pos, n0, *out_off, dst_len, fp.src_len, &p);
+    std::vector<IndexChunk> real;
+    real.reserve(chain.size());
+    for (uint32_t k : chain) {
       IndexChunk ic = recs[k];
       ic.out_offset = *out_off + uint64_t(real.size()) * n0;
       real.push_back(ic);
-      p = ends[k];
     }
     if (real.empty()) return PCO_B200_OK;
     PCOB_CUDA_TRY(cudaMemcpyAsync(d_index + chunks_offset, real.data(), real.size() * sizeof(IndexChunk), cudaMemcpyHostToDevice, stream));
@@ -905,6 +901,16 @@ PcoB200Error pco_b200_choose_mode(const void* nums, size_t n, unsigned char dtyp
 }
 
 void pco_b200_profile_enable(int on) { profiler_enabled().store(on != 0); }
+// Test hook for the host logic of the speculative index-free walk (no device involved): follow_chunk_chain over caller-made tables.
+// Returns the number of verified chunks; their candidate indices go to `verified` (room for m), the position behind the last one to *next_pos.
+size_t pco_b200_debug_follow_chain(const uint64_t* cand, const uint32_t* statuses, const uint64_t* ends, uint32_t m, uint64_t pos, uint64_t n0, uint64_t out_off,
+                                   uint64_t dst_len, uint64_t src_len, uint32_t* verified, uint64_t* next_pos) {
+  uint64_t p = pos;
+  const std::vector<uint32_t> chain = follow_chunk_chain(cand, statuses, ends, m, pos, n0, out_off, dst_len, src_len, &p);
+  for (size_t i = 0; i < chain.size(); i++) verified[i] = chain[i];
+  if (next_pos) *next_pos = p;
+  return chain.size();
+}
 int pco_b200_zero_copy(int mask) { return mask < 0 ? zero_copy_mask().load() : zero_copy_mask().exchange(mask & 7); }
 // Frees the calling thread's device scratch (a worker thread calls this before it exits; the buffers are otherwise kept for the
 // thread's next call).
