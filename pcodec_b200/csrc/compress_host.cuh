@@ -601,14 +601,22 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
   std::vector<uint64_t> starts(pages.size() + 1, 0);
   uint64_t max_chunk_n = 0;
   for (size_t i = 0; i < pages.size(); i++) { starts[i + 1] = starts[i] + pages[i]; max_chunk_n = std::max<uint64_t>(max_chunk_n, pages[i]); }
-  // unoptimized_bins_log is a function of each chunk's n; the kernels take one value per call, so every chunk must agree
+  // unoptimized_bins_log is a function of each chunk's n (chunk_compressor.rs:362-371); the kernels take one value per launch, so chunks
+  // that disagree (small chunks on either side of a power of two) go through the pipeline in separate runs below.  The Auto searches plan
+  // all chunks' samples in one launch: they still need one value.
   const bool shared_bins = (flags & PCO_B200_INTERNAL_SHARED_BINS) && pages.size() > 1;
-  uint32_t bins_log = choose_unoptimized_bins_log(cfg.compression_level, shared_bins ? n : size_t(pages[0]));
+  const uint32_t bins_log = choose_unoptimized_bins_log(cfg.compression_level, shared_bins ? n : size_t(pages[0]));
+  std::vector<uint32_t> chunk_bins_log(pages.size(), bins_log);
+  bool bins_log_uniform = true;
   if (!shared_bins)
-    for (uint64_t p : pages)
-      if (choose_unoptimized_bins_log(cfg.compression_level, size_t(p)) != bins_log)
-        return fail(PCO_B200_UNSUPPORTED, "chunks whose sizes imply different unoptimized_bins_log in one call");
-  if (bins_log > 8) return fail(PCO_B200_UNSUPPORTED, "compression levels that train more than 256 bins are outside the GPU hot path");
+    for (size_t i = 0; i < pages.size(); i++) {
+      chunk_bins_log[i] = choose_unoptimized_bins_log(cfg.compression_level, size_t(pages[i]));
+      if (chunk_bins_log[i] != bins_log) bins_log_uniform = false;
+    }
+  if (!bins_log_uniform && (auto_mode || auto_delta))
+    return fail(PCO_B200_UNSUPPORTED, "ModeSpec::Auto / DeltaSpec::Auto over chunks whose sizes imply different unoptimized_bins_log in one call");
+  for (uint32_t bl : chunk_bins_log)
+    if (bl > 8) return fail(PCO_B200_UNSUPPORTED, "compression levels that train more than 256 bins are outside the GPU hot path");
 
   // ---- the numbers in HBM
   const void* d_nums = nums;
@@ -868,13 +876,13 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
 
   // ---- runs of consecutive chunks with the same resolved (mode, order): each is one pass of the pipeline; a call with explicit specs
   // (and the usual homogeneous array under Auto) is a single run
-  struct Run { size_t c0, c1; ModeSel ms; uint32_t order; };
+  struct Run { size_t c0, c1; ModeSel ms; uint32_t order, bins_log; };
   std::vector<Run> runs;
-  if (shared_bins) runs.push_back(Run{0, pages.size(), unit_mode[0], unit_order[0]});
+  if (shared_bins) runs.push_back(Run{0, pages.size(), unit_mode[0], unit_order[0], bins_log});
   else
     for (size_t c = 0; c < pages.size(); c++) {
-      if (!runs.empty() && runs.back().ms == unit_mode[c] && runs.back().order == unit_order[c]) runs.back().c1 = c + 1;
-      else runs.push_back(Run{c, c + 1, unit_mode[c], unit_order[c]});
+      if (!runs.empty() && runs.back().ms == unit_mode[c] && runs.back().order == unit_order[c] && runs.back().bins_log == chunk_bins_log[c]) runs.back().c1 = c + 1;
+      else runs.push_back(Run{c, c + 1, unit_mode[c], unit_order[c], chunk_bins_log[c]});
     }
   // side index layout (host): entries of chunk c take n_vars(c) x batches(c) records
   const uint64_t chunks_offset = sizeof(IndexHeader);
@@ -928,8 +936,8 @@ static PcoB200Error compress_typed(CompressScratch& S, const void* nums, size_t 
     ep.n_total = rstarts.back();
     ep.n_chunks = n_chunks;
     ep.max_chunk_n = uint32_t(run_max_n);
-    ep.bins_log[0] = bins_log;
-    ep.bins_log[1] = std::min<uint32_t>(bins_log, 6);  // LIMITED_UNOPTIMIZED_BINS_LOG (chunk_compressor.rs:238-248)
+    ep.bins_log[0] = run.bins_log;
+    ep.bins_log[1] = std::min<uint32_t>(run.bins_log, 6);  // LIMITED_UNOPTIMIZED_BINS_LOG (chunk_compressor.rs:238-248)
     ep.nums = static_cast<const L*>(d_nums) + starts[run.c0];
     const uint32_t bpc = n_batches_of(uint32_t(run_max_n));
     const uint32_t tiles_per_chunk = uint32_t((run_max_n + SPLIT_TILE - 1) / SPLIT_TILE);

@@ -193,6 +193,25 @@ def test_exact_paging(sa, oracle):
     assert a == b
 
 
+@pytest.mark.parametrize("dtype,order", [(np.uint64, 1), (np.uint32, 0), (np.int16, 2), (np.float64, 0)])
+def test_chunks_whose_sizes_imply_different_unoptimized_bins_log(sa, oracle, dtype, order):
+    """chunk_compressor.rs:362-371: level 8 trains 2^7 bins on 1024 numbers, 2^6 on 1023 or 600, 2^7 on 3000 - an explicit config goes
+    through the pipeline in runs of equal values and the bytes are the oracle's; the side index spans the runs"""
+    sizes = [1024, 1023, 600, 3000, 1023, 1024, 1024, 4096, 5000]
+    nums = _walk(dtype, sum(sizes), 21)
+    cfg, ocfg = _cfgs(oracle, order=order, exact=sizes)
+    data, idx = sa.simple_compress_with_index(nums, cfg)
+    assert data == oracle.simple_compress(nums, ocfg)
+    assert np.array_equal(bits_view(sa.simple_decompress(data, dtype)), bits_view(nums))
+    assert np.array_equal(bits_view(sa.simple_decompress(data, dtype, index=idx)), bits_view(nums))
+    # the Auto searches plan all chunks' samples in one launch: differing values are still refused, loudly
+    from pcodec_b200 import ChunkConfig, PagingSpec, PcoError
+
+    with pytest.raises(PcoError) as e:
+        sa.simple_compress(nums, ChunkConfig(paging_spec=PagingSpec.exact_page_sizes(sizes), enable_8_bit=True))
+    assert e.value.kind == "Unsupported"
+
+
 def test_sharded_chunks_only_equals_whole_file(sa, oracle):
     """SURVEY §8e on one GPU: two virtual ranks compress their round-robin chunk shards with PCO_B200_CHUNKS_ONLY;
     header | chunks in order | 0x00 must equal the whole-array compress (ours and the oracle's)."""
