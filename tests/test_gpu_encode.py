@@ -181,7 +181,8 @@ def test_header_flavours_empty_and_errors(sa, oracle):
 def test_exact_paging(sa, oracle):
     nums = _walk(np.int64, 5000, 1)
     cfg, ocfg = _cfgs(oracle, order=1, exact=[700, 4300])
-    # chunks of different n may imply different unoptimized_bins_log; both sizes here give 8 at level 8? (700 -> 7): expect a loud refusal or equality
+    # chunks of 700 and 4300 numbers imply different unoptimized_bins_log at level 8 (6 and 8): two runs since round 2 (the refusal this test
+    # used to allow is what test_chunks_whose_sizes_imply_different_unoptimized_bins_log now forbids for explicit configs)
     from pcodec_b200 import PcoError
 
     try:
