@@ -782,7 +782,7 @@ def run_gpu_arm(args, rank, world):
         "cpu_baseline": cpu, "e2e": ({**e2e, "reference_abi": abi3} if e2e else e2e), "clocks": sampler.summary(),
         # per step (profiles/r02_zz_launches.csv): compress = init_chunks, split_count, publish (flags readback), plan_solve, fallback, bin_lut,
         # ans_encode, layout, chunk_offsets, pack, header_footer, emit_index; decompress = fused_narrow_kernel + publish (statuses readback)
-        "gpu_launches": 14,
+        "gpu_launches": 14 + (3 if gather_on else 0),  # + chunk_sizes_kernel, gather_offsets_kernel, push_pages_kernel of the page gather
     }
     print(json.dumps(line))
     if args.results_csv:
